@@ -1,0 +1,173 @@
+"""ctypes front-end of the CPU oracle (oracle/city_oracle.c, oracle/vehicle_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+class OCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "W", "H", "wall", "ring_w", "ring_type", "optimized", "sub_int", "sub_type", "min_sub",
+        "tl_range", "fwd", "fwd_mode", "entr_level", "fast_reach")]
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("city_oracle.c", "vehicle_oracle.c")]
+    if force or not os.path.exists(_LIB) or any(
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.oracle_city_sizeof.restype = C.c_size_t
+        _lib.oracle_light_links.restype = C.c_int64
+    return _lib
+
+
+ROAD_CODE = {None: 0, "R1": 1, "R2": 2, "R3": 3}
+FWD_MODES = ["Skip", "Include in Range", "Include as Extra"]
+
+
+def make_cfg(width=200, height=200, wall_thickness=15, sidewalk_ring_width=2, ring_road_type="R2",
+             optimized_intersections=True, subblock_roads_have_intersections=True,
+             subblock_road_type="R3", min_subblock_spacing=5, traffic_light_range=10,
+             forward_traffic_light_range=False, forward_traffic_light_range_intersections="Skip",
+             block_entrance_road_level=0, fast_reach=0, **_ignored):
+    return OCfg(width, height, wall_thickness, sidewalk_ring_width, ROAD_CODE[ring_road_type],
+                int(optimized_intersections), int(subblock_roads_have_intersections),
+                ROAD_CODE[subblock_road_type], min_subblock_spacing, traffic_light_range,
+                int(forward_traffic_light_range), FWD_MODES.index(forward_traffic_light_range_intersections),
+                block_entrance_road_level, fast_reach)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class OracleCity:
+    """Holds planes + band lists and runs the restated passes one by one."""
+
+    def __init__(self, cfg: OCfg, hbands, vbands):
+        self.cfg = cfg
+        W, H = cfg.W, cfg.H
+        self.W, self.H = W, H
+        self.cell_type = np.zeros((H, W), np.uint8)
+        self.dirs = np.zeros((H, W), np.uint16)
+        self.aux = np.zeros((H, W), np.uint8)
+        self.block_id = np.zeros((H, W), np.int32)
+        self.hb = np.ascontiguousarray(hbands, np.int32).reshape(-1, 4)
+        self.vb = np.ascontiguousarray(vbands, np.int32).reshape(-1, 4)
+        self._city = C.create_string_buffer(lib().oracle_city_sizeof())
+        lib().oracle_bind(self._city, C.byref(cfg), _p(self.cell_type, C.c_uint8), _p(self.dirs, C.c_uint16),
+                          _p(self.aux, C.c_uint8), _p(self.block_id, C.c_int32),
+                          _p(self.hb, C.c_int32), len(self.hb), _p(self.vb, C.c_int32), len(self.vb))
+        self.n_blocks = 0
+        self.entrances = None
+        self.sweeps = 0
+
+    def planes(self):
+        return {"cell_type": self.cell_type, "dirs": self.dirs, "aux": self.aux, "block_id": self.block_id}
+
+    def frame(self):
+        lib().oracle_frame(self._city)
+
+    def roads(self):
+        lib().oracle_roads(self._city)
+
+    def nothing_blobs(self):
+        cap = max(16, self.W * self.H // 4)
+        out = np.zeros((cap, 6), np.int32)
+        n = lib().oracle_nothing_blobs(self._city, _p(out, C.c_int32), cap)
+        return out[:n].copy()
+
+    def carve(self, tape):
+        tape = np.ascontiguousarray(tape, np.int32).reshape(-1, 8)
+        n = lib().oracle_carve(self._city, _p(tape, C.c_int32), len(tape))
+        if n < 0:
+            raise ValueError("carve tape too short")
+        return n
+
+    def zones(self, zone_by_block):
+        z = np.ascontiguousarray(zone_by_block, np.uint8)
+        n = lib().oracle_zones(self._city, _p(z, C.c_uint8), len(z))
+        if n < 0:
+            raise ValueError("zone tape too short")
+        self.n_blocks = n
+        return n
+
+    def dead_ends(self):
+        self.sweeps = lib().oracle_dead_ends(self._city)
+        return self.sweeps
+
+    def upgrade_r2(self):
+        lib().oracle_upgrade_r2(self._city)
+
+    def entrances_pass(self, run_by_block=None):
+        n = self.n_blocks
+        run = np.zeros(max(n, 1), np.int32) if run_by_block is None else np.ascontiguousarray(run_by_block, np.int32)
+        assert len(run) >= n
+        out = np.full(max(n, 1), -1, np.int32)
+        rc = lib().oracle_entrances(self._city, n, _p(run, C.c_int32), _p(out, C.c_int32))
+        if rc < 0:
+            raise ValueError("entrance tape index out of range")
+        self.entrances = out[:n]
+        return self.entrances
+
+    def validate_dirs(self):
+        lib().oracle_validate_dirs(self._city)
+
+    def entrance_dirs(self):
+        lib().oracle_entrance_dirs(self._city)
+
+    def lights(self):
+        lib().oracle_lights(self._city)
+        out = {}
+        for which, name in enumerate(("ctrl", "incoming", "outgoing")):
+            n = lib().oracle_light_links(which, None)
+            a = np.zeros((n, 2), np.int32)
+            if n:
+                lib().oracle_light_links(which, _p(a, C.c_int32))
+            out[name] = a
+        t = self.cell_type.reshape(-1)
+        out["lights"] = np.flatnonzero(t == 15).astype(np.int32)
+        self.links = out
+        return out
+
+    def simple_maps(self):
+        maps = {k: np.zeros((self.H, self.W), np.uint8)
+                for k in ("is_road_map", "road_type_map", "intersection_map", "allowed_dirs_map")}
+        lib().oracle_simple_maps(self._city, _p(maps["is_road_map"], C.c_uint8), _p(maps["road_type_map"], C.c_uint8),
+                                 _p(maps["intersection_map"], C.c_uint8), _p(maps["allowed_dirs_map"], C.c_uint8))
+        return maps
+
+    def run_all(self, tape_zone, tape_carve=None, tape_entrance=None, carve=False):
+        self.frame()
+        self.roads()
+        if carve:
+            self.carve(tape_carve)
+        self.zones(tape_zone)
+        self.dead_ends()
+        self.upgrade_r2()
+        self.entrances_pass(tape_entrance)
+        self.validate_dirs()
+        self.entrance_dirs()
+        self.lights()
+        return self.planes()

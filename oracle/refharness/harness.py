@@ -138,9 +138,10 @@ def extract_light_links(model):
       lights[n]            TrafficLight cells, sorted
       ctrl[m,2]            (light cell, controlled road cell) pairs, sorted, with multiplicity
       incoming[k,2]        (light cell, assigned incoming lane cell) pairs, sorted, with multiplicity
+      outgoing[j,2]        same for assigned_outgoing_road_blocks (forward_traffic_light_range only)
     """
     W = model.width
-    lights, ctrl, inc = [], [], []
+    lights, ctrl, inc, outg = [], [], [], []
     for tl in model.traffic_lights:
         lx, ly = tl.position
         li = ly * W + lx
@@ -149,10 +150,13 @@ def extract_light_links(model):
             ctrl.append((li, cb.position[1] * W + cb.position[0]))
         for rb in tl.assigned_incoming_road_blocks:
             inc.append((li, rb.position[1] * W + rb.position[0]))
+        for rb in tl.assigned_outgoing_road_blocks:
+            outg.append((li, rb.position[1] * W + rb.position[0]))
     lights = np.array(sorted(lights), np.int32)
     ctrl = np.array(sorted(ctrl), np.int32).reshape(-1, 2)
     inc = np.array(sorted(inc), np.int32).reshape(-1, 2)
-    return {"lights": lights, "ctrl": ctrl, "incoming": inc}
+    outg = np.array(sorted(outg), np.int32).reshape(-1, 2)
+    return {"lights": lights, "ctrl": ctrl, "incoming": inc, "outgoing": outg}
 
 
 class _Recorder:
