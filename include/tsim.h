@@ -1,0 +1,179 @@
+/*
+ * tsim.h -- C ABI of the B200-native CityModel hot path (libtsim.so).
+ *
+ * Drop-in boundary.  The reference has no plugin point for this
+ * path; its seam is structural:
+ *   - layout:  the pass methods called from CityModel.__init__, Simulation/city_model.py:125-139
+ *              (each `tsim_layout_*` entry cites the method it replaces), whose only mutator is
+ *              place_cell (city_model.py:1864-1870) and only reader get_cell_contents (:1965-1972);
+ *   - maps:    _build_simple_maps, city_model.py:2151-2199;
+ *   - tick:    CityModel.step (city_model.py:1831-1860) -> VehicleAgent.step_decide/step
+ *              (agents/vehicles/vehicle_base.py:616-685) and IntersectionLightGroup.step
+ *              (agents/city_structure_entities/intersection_light_group.py:396-423).
+ * The only FFI precedent upstream is the pybind11 module utilities/pathfinding/astar_cpp.cpp:117-128
+ * (flat C-contiguous [y,x] arrays, borrowed pointers); this ABI keeps those conventions and drops
+ * its silent dtype casts and silent CPU fallback.
+ *
+ * Conventions
+ *   - every plane is row-major [H][W] with y the slow axis (y up, N = +y, config.py:64);
+ *   - all plane / table pointers are DEVICE pointers owned by the caller (torch tensors);
+ *     the library allocates nothing persistent and keeps no global state;
+ *   - every entry point is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - every entry point returns a tsim_status; tsim_last_error() gives a thread-local message;
+ *   - results that the host must read (counts, flags) are written to caller-provided device
+ *     memory; the caller synchronises and reads them.
+ */
+#ifndef TSIM_H
+#define TSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSIM_ABI_VERSION 1
+
+/* cell_type codes = index into Defaults.ZONES (Simulation/config.py:74-95) */
+enum tsim_cell_type {
+    TSIM_RESIDENTIAL = 0, TSIM_OFFICE, TSIM_MARKET, TSIM_LEISURE, TSIM_OTHER, TSIM_EMPTY,
+    TSIM_NOTHING, TSIM_SIDEWALK, TSIM_WALL, TSIM_R1, TSIM_R2, TSIM_R3, TSIM_INTERSECTION,
+    TSIM_HIGHWAY_ENTRANCE, TSIM_HIGHWAY_EXIT, TSIM_TRAFFIC_LIGHT, TSIM_TRAFFIC_LIGHT_STOP,
+    TSIM_CONTROLLED_ROAD, TSIM_CONTROLLED_ROAD_STOP, TSIM_BLOCK_ENTRANCE
+};
+
+/* direction indices; the bit (1 << index) is the allowed_dirs_map bit (city_model.py:2191-2196) */
+enum tsim_dir { TSIM_N = 0, TSIM_E = 1, TSIM_S = 2, TSIM_W = 3 };
+
+/* `dirs` plane, u16: bits0-3 mask, bits 4+2i..5+2i i-th entry of the ordered list, bits12-14 length */
+/* `aux`  plane, u8 : */
+#define TSIM_AUX_ORIG_MASK 0x1f /* original cell_type of a ControlledRoad (CellAgent.road_type) */
+#define TSIM_AUX_RING      0x20 /* member of CityModel._ring_road_cells (forced ring corners)   */
+#define TSIM_AUX_EVER_INT  0x40 /* member of CityModel._intersection_cells                       */
+#define TSIM_AUX_HAS_LIGHT 0x80 /* CellAgent.light is not None                                   */
+
+typedef enum tsim_status {
+    TSIM_OK = 0,
+    TSIM_ERR_CONFIG = 1,      /* invalid configuration / null pointer / misaligned plane */
+    TSIM_ERR_WORKSPACE = 2,   /* workspace too small (see tsim_workspace_bytes)          */
+    TSIM_ERR_CUDA = 3,        /* a CUDA call failed; message in tsim_last_error()        */
+    TSIM_ERR_TAPE = 4,        /* a tape is too short / holds an illegal decision         */
+    TSIM_ERR_UNSUPPORTED = 5, /* configuration not implemented on the GPU path           */
+    TSIM_ERR_CAPACITY = 6     /* a bounded device structure overflowed                   */
+} tsim_status;
+
+/* POD copy of the CityModel constructor kwargs the passes read (city_model.py:27-53) */
+typedef struct tsim_cfg {
+    int32_t width, height;
+    int32_t wall_thickness, sidewalk_ring_width;
+    int32_t ring_road_type;                    /* 0 None, 1 R1, 2 R2, 3 R3 */
+    int32_t optimized_intersections;
+    int32_t subblock_roads_have_intersections;
+    int32_t subblock_road_type;                /* 1..3 */
+    int32_t min_subblock_spacing;
+    int32_t traffic_light_range;
+    int32_t forward_traffic_light_range;       /* must be 0 on the GPU path (TSIM_ERR_UNSUPPORTED) */
+    int32_t forward_intersections_mode;
+    int32_t block_entrance_road_level;         /* Defaults.BLOCK_ENTRANCE_ROAD_LEVEL, config.py:26 */
+    /* row-band shard window: this device holds global rows [row0, row0 + rows) plus `halo`
+       rows above and below inside the same allocation; single device: row0=0, rows=height, halo=0 */
+    int32_t row0, rows, halo;
+} tsim_cfg;
+
+typedef struct tsim_planes {
+    uint8_t  *cell_type;
+    uint16_t *dirs;
+    uint8_t  *aux;
+    int32_t  *block_id;
+} tsim_planes;
+
+/* per-row / per-column band descriptors (device, uint32 each), built by tsim_build_line_table */
+typedef struct tsim_lines {
+    const uint32_t *row;   /* [height] */
+    const uint32_t *col;   /* [width]  */
+} tsim_lines;
+
+/* component table produced by the labelling passes, one row per component in raster
+   discovery order (id = row + 1): minx, miny, maxx, maxy, size, root cell index */
+#define TSIM_BLOB_STRIDE 6
+
+int         tsim_version(void);
+const char *tsim_last_error(void);
+
+/* host-side helper: band list (n rows of start,end,type,dir) -> line table of `len` entries.
+   Restates _find_band_covering (city_model.py:1269-1273: first band in list order wins) and the
+   forced-band membership used by _override_corner_lane_dirs (:519-527) and
+   _upgrade_r2_to_intersections (:859-866). */
+tsim_status tsim_build_line_table(const int32_t *bands, int32_t n_bands, int32_t len, uint32_t *out_host);
+
+/* bytes of device workspace every tsim_layout_* / tsim_maps call may use */
+tsim_status tsim_workspace_bytes(const tsim_cfg *cfg, size_t *out_bytes);
+
+/* _place_thick_wall + _place_sidewalk_inner_ring + _clear_interior (city_model.py:315-369) and
+   _build_roads_and_sidewalks from the band lists on (:396-495, incl. _make_intersection :211-306,
+   _compute_lane_dirs :1275-1368, _override_corner_lane_dirs :498-558,
+   _replace_boundary_highways_with_entrances :1370-1420), fused: writes cell_type, dirs, aux, block_id */
+tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines,
+                                    void *stream);
+
+/* 4-connected components of `Nothing` in raster discovery order (the flood fills at
+   city_model.py:632-647 and :746-763).  Writes labels (1-based id, 0 elsewhere) into p->block_id,
+   the component table into blobs[cap][TSIM_BLOB_STRIDE] and the count into *n_blobs (device). */
+tsim_status tsim_layout_label_nothing(const tsim_cfg *cfg, const tsim_planes *p, int32_t *blobs,
+                                      int32_t cap, int32_t *n_blobs, void *workspace, size_t ws_bytes,
+                                      void *stream);
+
+/* _carve_subblock_roads (city_model.py:563-737) given the labels of tsim_layout_label_nothing and
+   the carve tape: one row of 8 int32 per blob (drawn, carved, px, py, hor_dir, ver_dir,
+   inbound_is_horizontal, tries).  err_flag (device int32) is set non-zero on an illegal row. */
+tsim_status tsim_layout_carve(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines,
+                              const int32_t *blobs, const int32_t *n_blobs, const int32_t *tape,
+                              int32_t n_tape, int32_t *err_flag, void *stream);
+
+/* _flood_fill_blocks_storing_data (city_model.py:742-806) given fresh labels: fills each block with
+   Empty (bbox < 3) or the zone zone_by_block[id-1]; block_id keeps the labels. */
+tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes *p, const int32_t *blobs,
+                              const int32_t *n_blobs, const uint8_t *zone_by_block, int32_t n_tape,
+                              int32_t *err_flag, void *stream);
+
+/* _eliminate_dead_ends (city_model.py:811-840); *sweeps (device) receives the sweep count */
+tsim_status tsim_layout_dead_ends(const tsim_cfg *cfg, const tsim_planes *p, int32_t *sweeps,
+                                  void *workspace, size_t ws_bytes, void *stream);
+
+/* _upgrade_r2_to_intersections (city_model.py:842-879) */
+tsim_status tsim_layout_upgrade_r2(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines,
+                                   int32_t *err_flag, void *stream);
+
+/* _final_place_block_entrances (city_model.py:884-963); run_by_block[id-1] = canonical index of the
+   chosen run among the longest ones; entrances[id-1] receives the cell index or -1 */
+tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_planes *p, const int32_t *blobs,
+                                  const int32_t *n_blobs, const int32_t *run_by_block, int32_t n_tape,
+                                  int32_t *entrances, int32_t *err_flag, void *stream);
+
+/* _remove_invalid_intersection_directions + _add_entrance_directions (city_model.py:969-1070), fused */
+tsim_status tsim_layout_fix_dirs(const tsim_cfg *cfg, const tsim_planes *p, void *stream);
+
+/* link tables of _add_traffic_lights: CSR by light, lights in ascending cell index */
+typedef struct tsim_light_links {
+    int32_t *n_lights;        /* device scalar                                          */
+    int32_t *light_cell;      /* [cap_lights]                                            */
+    int32_t *ctrl_off;        /* [cap_lights + 1]  controlled road cells per light       */
+    int32_t *ctrl_cell;       /* [cap_ctrl]                                              */
+    int32_t *inc_off;         /* [cap_lights + 1]  assigned incoming lane cells (multiset) */
+    int32_t *inc_cell;        /* [cap_inc]                                               */
+    int32_t cap_lights, cap_ctrl, cap_inc;
+} tsim_light_links;
+
+/* _add_traffic_lights (city_model.py:1422-1548, CellAgent.leads_to cell.py:201-227) */
+tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *links,
+                               int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
+
+/* _build_simple_maps (city_model.py:2151-2199) */
+tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint8_t *is_road, uint8_t *road_type,
+                      uint8_t *intersection, uint8_t *allowed_dirs, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSIM_H */

@@ -1,0 +1,75 @@
+"""ctypes binding of libtsim.so -- the C ABI declared in include/tsim.h.
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtsim.so")
+
+STATUS_NAMES = {0: "TSIM_OK", 1: "TSIM_ERR_CONFIG", 2: "TSIM_ERR_WORKSPACE", 3: "TSIM_ERR_CUDA",
+                4: "TSIM_ERR_TAPE", 5: "TSIM_ERR_UNSUPPORTED", 6: "TSIM_ERR_CAPACITY"}
+
+# every symbol include/tsim.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "tsim_version", "tsim_last_error", "tsim_build_line_table", "tsim_workspace_bytes",
+    "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_layout_carve", "tsim_layout_zones",
+    "tsim_layout_dead_ends", "tsim_layout_upgrade_r2", "tsim_layout_entrances", "tsim_layout_fix_dirs",
+    "tsim_layout_lights", "tsim_maps",
+]
+
+
+class TsimError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+class Cfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "width", "height", "wall_thickness", "sidewalk_ring_width", "ring_road_type",
+        "optimized_intersections", "subblock_roads_have_intersections", "subblock_road_type",
+        "min_subblock_spacing", "traffic_light_range", "forward_traffic_light_range",
+        "forward_intersections_mode", "block_entrance_road_level", "row0", "rows", "halo")]
+
+
+class Planes(C.Structure):
+    _fields_ = [("cell_type", C.c_void_p), ("dirs", C.c_void_p), ("aux", C.c_void_p), ("block_id", C.c_void_p)]
+
+
+class Lines(C.Structure):
+    _fields_ = [("row", C.c_void_p), ("col", C.c_void_p)]
+
+
+class LightLinks(C.Structure):
+    _fields_ = [("n_lights", C.c_void_p), ("light_cell", C.c_void_p), ("ctrl_off", C.c_void_p),
+                ("ctrl_cell", C.c_void_p), ("inc_off", C.c_void_p), ("inc_cell", C.c_void_p),
+                ("cap_lights", C.c_int32), ("cap_ctrl", C.c_int32), ("cap_inc", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libtsim.so (built by `__graft_entry__.build()` / `make -C trafficsimulation_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "trafficsimulation_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.tsim_last_error.restype = C.c_char_p
+    for name in SYMBOLS:
+        getattr(lib, name)   # AttributeError if the library does not export a declared symbol
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise TsimError(status, load().tsim_last_error().decode())

@@ -1,0 +1,90 @@
+// abi.cu -- host-side part of the C ABI that needs no kernels: version, errors, config checks,
+// line tables, workspace sizing.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace tsim {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+tsim_status check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return TSIM_OK;
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return TSIM_ERR_CUDA;
+}
+
+tsim_status check_cfg(const tsim_cfg *c) {
+    if (!c) { set_error("cfg is NULL"); return TSIM_ERR_CONFIG; }
+    if (c->width < 1 || c->height < 1 || (long long)c->width * c->height > 0x7fffffffLL) {
+        set_error("grid %d x %d out of range (cell indices are int32)", c->width, c->height);
+        return TSIM_ERR_CONFIG;
+    }
+    if (c->wall_thickness < 0 || c->sidewalk_ring_width < 0) { set_error("negative frame widths"); return TSIM_ERR_CONFIG; }
+    if (c->ring_road_type < 0 || c->ring_road_type > 3) { set_error("ring_road_type %d", c->ring_road_type); return TSIM_ERR_CONFIG; }
+    if (c->subblock_road_type < 1 || c->subblock_road_type > 3) { set_error("subblock_road_type %d", c->subblock_road_type); return TSIM_ERR_CONFIG; }
+    if (c->rows < 1 || c->row0 < 0 || c->row0 + c->rows > c->height || c->halo < 0) {
+        set_error("bad shard window row0=%d rows=%d halo=%d height=%d", c->row0, c->rows, c->halo, c->height);
+        return TSIM_ERR_CONFIG;
+    }
+    return TSIM_OK;
+}
+
+}  // namespace tsim
+
+using namespace tsim;
+
+extern "C" int tsim_version(void) { return TSIM_ABI_VERSION; }
+
+extern "C" const char *tsim_last_error(void) { return g_err; }
+
+// Restates _find_band_covering (city_model.py:1269-1273): the FIRST band in list order that covers
+// an index wins; plus membership in bands[0] / bands[-1], which _override_corner_lane_dirs (:519-527)
+// and _upgrade_r2_to_intersections (:859-866) test independently of the covering band.
+extern "C" tsim_status tsim_build_line_table(const int32_t *bands, int32_t n, int32_t len, uint32_t *out) {
+    if (!out || len < 0 || n < 0 || (n > 0 && !bands)) { set_error("tsim_build_line_table: bad arguments"); return TSIM_ERR_CONFIG; }
+    for (int i = 0; i < n; i++) {
+        const int32_t *b = bands + 4 * i;
+        if (b[2] < 1 || b[2] > 3 || b[1] < b[0] || b[1] - b[0] + 1 > 7 || b[3] < -1 || b[3] > 3) {
+            set_error("band %d = (%d,%d,%d,%d) is not representable", i, b[0], b[1], b[2], b[3]);
+            return TSIM_ERR_CONFIG;
+        }
+    }
+    for (int idx = 0; idx < len; idx++) {
+        uint32_t e = 0;
+        for (int i = 0; i < n; i++) {
+            const int32_t *b = bands + 4 * i;
+            if (b[0] <= idx && idx <= b[1]) {
+                uint32_t dir = b[3] < 0 ? 7u : (uint32_t)b[3];
+                e = 1u | ((uint32_t)b[2] << 1) | (dir << 3) | ((uint32_t)(idx - b[0]) << 6) | ((uint32_t)(b[1] - b[0] + 1) << 9);
+                break;
+            }
+        }
+        if (n > 0) {
+            const int32_t *f = bands, *l = bands + 4 * (n - 1);
+            if (f[0] <= idx && idx <= f[1]) { int o = idx - f[0]; e |= (1u << 12) | ((uint32_t)(o > 2 ? 2 : o) << 13); }
+            if (l[0] <= idx && idx <= l[1]) { int o = idx - l[0]; e |= (1u << 15) | ((uint32_t)(o > 2 ? 2 : o) << 16); }
+        }
+        out[idx] = e;
+    }
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_workspace_bytes(const tsim_cfg *cfg, size_t *out) {
+    tsim_status s = check_cfg(cfg);
+    if (s != TSIM_OK) return s;
+    if (!out) { set_error("out is NULL"); return TSIM_ERR_CONFIG; }
+    size_t cells = (size_t)cfg->width * (size_t)(cfg->rows + 2 * cfg->halo);
+    // largest user: tsim_layout_lights (reach bits 1 B + per-cell scratch 4 B) and the labelling
+    // passes (scan partials); see each pass for its own layout.  16 B per cell + 1 MiB covers all.
+    *out = cells * 16 + (1u << 20);
+    return TSIM_OK;
+}

@@ -1,0 +1,133 @@
+// k_carve.cu -- _carve_subblock_roads (city_model.py:563-737): one thread per Nothing blob.
+//
+// The reference visits blobs in raster discovery order and carves each with the decisions it draws
+// (the carve tape, one row per blob).  Blobs are disjoint and a carve only touches its own blob, the
+// sidewalk ring between the blob and the first road it reaches, and that first road cell -- where the
+// update (_make_intersection, or one extra arrow) is idempotent -- so blobs can be carved
+// concurrently.  Work per blob is O(perimeter): two legs, two extensions, the pivot's 8 neighbours.
+#include "cells_stencil.cuh"
+
+namespace tsim {
+
+struct LiveGrid {   // read/write access to the live planes (own writes are visible to the thread)
+    uint8_t *T; uint16_t *D; uint8_t *A;
+    int W, H;
+    __device__ __forceinline__ bool has(int x, int y) const { return x >= 0 && x < W && y >= 0 && y < H; }
+    __device__ __forceinline__ size_t at(int x, int y) const { return (size_t)y * W + x; }
+    __device__ __forceinline__ int t(int x, int y) const { return has(x, y) ? (int)((volatile uint8_t *)T)[at(x, y)] : -1; }
+    __device__ __forceinline__ uint32_t d(int x, int y) const { return ((volatile uint16_t *)D)[at(x, y)]; }
+    __device__ __forceinline__ void place(int x, int y, int t) const {   // place_cell (:1864-1870)
+        const size_t i = at(x, y);
+        T[i] = (uint8_t)t; D[i] = 0; A[i] &= (AUX_RING | AUX_EVER);
+    }
+};
+
+// lay_r4_cell (:588-601)
+__device__ __forceinline__ void lay_cell(const LiveGrid &g, int sub_t, int x, int y, int arrow) {
+    if (!g.has(x, y)) return;
+    if (!is_road_like(g.t(x, y))) {
+        g.place(x, y, sub_t);
+        g.D[g.at(x, y)] = (uint16_t)dl_one(arrow);
+    }
+    if (g.t(x + 1, y) == T_NOTHING) g.place(x + 1, y, T_SIDEWALK);
+    if (g.t(x - 1, y) == T_NOTHING) g.place(x - 1, y, T_SIDEWALK);
+    if (g.t(x, y + 1) == T_NOTHING) g.place(x, y + 1, T_SIDEWALK);
+    if (g.t(x, y - 1) == T_NOTHING) g.place(x, y - 1, T_SIDEWALK);
+}
+
+// extend_to_road (:603-627)
+__device__ void extend(const tsim_cfg &c, const LiveGrid &g, const uint32_t *rowt, const uint32_t *colt, int sub_t, int sx, int sy,
+                       int march, int arrow, int32_t *err) {
+    int cx = sx, cy = sy;
+    while (g.has(cx, cy)) {
+        const int t = g.t(cx, cy);
+        if (is_road_like(t)) {
+            const size_t i = g.at(cx, cy);
+            if (c.subblock_roads_have_intersections) {
+                int t_new; uint32_t d_new;
+                const int r = make_intersection_cell(c, g, __ldg(rowt + cy), __ldg(colt + cx), cx, cy, t_new, d_new);
+                if (r == 3) { *err = 3; }
+                else if (r != 0) { g.place(cx, cy, t_new); g.D[i] = (uint16_t)d_new; }
+                g.A[i] |= AUX_EVER;   // :617 adds the cell to _intersection_cells unconditionally
+            } else {
+                // one extra arrow into the road.  Two blobs may reach the same cell from opposite sides;
+                // CAS keeps both arrows.  (List order then follows arrival order, not blob order: flagged.)
+                const uint32_t od = g.d(cx, cy);
+                if (!dl_has(od, arrow)) {
+                    unsigned short *p = (unsigned short *)(g.D + i);
+                    unsigned short seen = (unsigned short)od;
+                    for (;;) {
+                        if (dl_has(seen, arrow)) break;
+                        const unsigned short prev = atomicCAS(p, seen, (unsigned short)dl_append(seen, arrow));
+                        if (prev == seen) break;
+                        seen = prev;
+                        *err = 4;   // concurrent append: order may differ from the reference
+                    }
+                }
+            }
+            return;
+        }
+        if (t == T_SIDEWALK || t == T_NOTHING) { lay_cell(g, sub_t, cx, cy, arrow); cx += dx_of(march); cy += dy_of(march); }
+        else return;
+    }
+}
+
+__global__ void __launch_bounds__(128) carve_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, const uint32_t *__restrict__ rowt,
+                                                    const uint32_t *__restrict__ colt, const int32_t *__restrict__ blobs,
+                                                    const int32_t *__restrict__ n_blobs, const int32_t *__restrict__ tape, int n_tape,
+                                                    int32_t *err) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = *n_blobs;
+    if (b == 0 && nb > n_tape) *err = 1;
+    if (b >= nb) return;
+    const int32_t *row = tape + (size_t)b * 8;
+    if (!row[1]) return;
+    const int32_t *bl = blobs + (size_t)b * TSIM_BLOB_STRIDE;
+    const int minx = bl[0], miny = bl[1], maxx = bl[2], maxy = bl[3];
+    const int px = row[2], py = row[3], hd = row[4], vd = row[5], inb_h = row[6];
+    const int ms = c.min_subblock_spacing;
+    // the tape must hold a decision the reference could have drawn (:659-675)
+    if (!((hd == DW || hd == DE) && (vd == DN || vd == DS)) || px < minx + ms || px > maxx - ms || py < miny + ms || py > maxy - ms ||
+        (long long)(maxx - minx + 1) * (maxy - miny + 1) != bl[4] /* non-rectangular blob: carve footprints may interact */) {
+        *err = 2;
+        return;
+    }
+    const LiveGrid g{T, D, A, c.width, c.height};
+    const int sub_t = T_R1 - 1 + c.subblock_road_type;
+    const int h_arrow = inb_h ? opp_of(hd) : hd;   // :683-696
+    const int v_arrow = inb_h ? vd : opp_of(vd);   // :707-708
+    int hx_end, vy_end;
+    if (hd == DW) { for (int hx = px - 1; hx >= minx; hx--) lay_cell(g, sub_t, hx, py, h_arrow); hx_end = minx; }
+    else { for (int hx = px + 1; hx <= maxx; hx++) lay_cell(g, sub_t, hx, py, h_arrow); hx_end = maxx; }
+    if (vd == DS) { for (int vy = py; vy >= miny; vy--) lay_cell(g, sub_t, px, vy, v_arrow); vy_end = miny; }
+    else { for (int vy = py; vy <= maxy; vy++) lay_cell(g, sub_t, px, vy, v_arrow); vy_end = maxy; }
+    g.D[g.at(px, py)] = (uint16_t)dl_one(inb_h ? v_arrow : h_arrow);   // pivot shows the outbound arrow only (:713-715)
+    extend(c, g, rowt, colt, sub_t, hx_end + dx_of(hd), py, hd, h_arrow, err);
+    extend(c, g, rowt, colt, sub_t, px, vy_end + dy_of(vd), vd, v_arrow, err);
+    for (int dy = -1; dy <= 1; dy++)   // :731-737
+        for (int dx = -1; dx <= 1; dx++) {
+            if (!dx && !dy) continue;
+            const int t = g.t(px + dx, py + dy);
+            if (t >= 0 && !is_road_like(t) && t != T_WALL) g.place(px + dx, py + dy, T_SIDEWALK);
+        }
+}
+
+}  // namespace tsim
+
+using namespace tsim;
+
+extern "C" tsim_status tsim_layout_carve(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines, const int32_t *blobs,
+                                         const int32_t *n_blobs, const int32_t *tape, int32_t n_tape, int32_t *err_flag, void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if (!p || !p->cell_type || !p->dirs || !p->aux || !lines || !lines->row || !lines->col || !blobs || !n_blobs || !tape || !err_flag || n_tape < 0) {
+        set_error("tsim_layout_carve: bad arguments");
+        return TSIM_ERR_CONFIG;
+    }
+    if (cfg->halo != 0 || cfg->rows != cfg->height) { set_error("tsim_layout_carve: run on the gathered grid (shards carve after the blob merge)"); return TSIM_ERR_UNSUPPORTED; }
+    if (n_tape == 0) return TSIM_OK;
+    carve_kernel<<<div_up(n_tape, 128), 128, 0, (cudaStream_t)stream>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, blobs,
+                                                                        n_blobs, tape, n_tape, err_flag);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}

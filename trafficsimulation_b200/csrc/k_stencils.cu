@@ -1,0 +1,285 @@
+// k_stencils.cu -- the 1-halo stencil passes over the packed planes:
+//   tsim_layout_dead_ends   (city_model.py:811-840)
+//   tsim_layout_upgrade_r2  (city_model.py:842-879, 211-306)
+//   tsim_layout_fix_dirs    (city_model.py:969-1012 then :1035-1070)
+//   tsim_maps               (city_model.py:2151-2199)
+//
+// All of them are SPARSE: only road cells (~30 % of a city) can change, and a road cell changes
+// only by looking at its 4 neighbours.  Each thread streams 16 cells of the type plane with one
+// 128-bit load, rejects strips without candidate types with a couple of ALU ops, and touches the
+// neighbours (L1/L2 hits: they are the lines its own warp or the adjacent row's warp just loaded)
+// only for candidates.  DRAM traffic is therefore the 1 B/cell type plane plus the few changed
+// sectors -- the algorithmic bytes of SURVEY.md §8(d).
+#include <cooperative_groups.h>
+#include "cells_stencil.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tsim {
+
+struct Shard {   // local row window of a shard allocation
+    int W, H, y0, nrows, ylo, yhi;   // allocation holds rows [y0, y0+nrows); this device OWNS [ylo, yhi)
+    __host__ explicit Shard(const tsim_cfg &c) {
+        W = c.width; H = c.height; y0 = c.row0 - c.halo; nrows = c.rows + 2 * c.halo; ylo = c.row0; yhi = c.row0 + c.rows;
+    }
+};
+
+__device__ __forceinline__ PlaneView make_view(const Shard &s, const uint8_t *T, const uint16_t *D, const uint8_t *A) {
+    PlaneView v; v.T = T; v.D = D; v.A = A; v.W = s.W; v.H = s.H; v.y0 = s.y0; v.nrows = s.nrows;
+    return v;
+}
+
+// does any byte of the 16-byte strip belong to `set`?
+__device__ __forceinline__ uint32_t strip_mask(const uint4 &q, uint32_t set) {
+    uint32_t m = 0;
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) m |= ((set >> ((w[k] >> (8 * b)) & 31u)) & 1u) << (4 * k + b);
+    return m;
+}
+
+// Generic sparse sweep: calls f(x, y) for every owned cell whose type is in `set`.
+template <class F>
+__device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, uint32_t set, F f, long long tid, long long nthreads) {
+    if ((s.W & 15) == 0) {
+        const int sw = s.W >> 4;
+        const long long nstrips = (long long)sw * (s.yhi - s.ylo);
+        for (long long i = tid; i < nstrips; i += nthreads) {
+            const int y = s.ylo + (int)(i / sw), x0 = (int)(i % sw) << 4;
+            const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(T + (size_t)(y - s.y0) * s.W + x0));
+            uint32_t m = strip_mask(q, set);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                f(x0 + b, y);
+            }
+        }
+    } else {
+        const long long n = (long long)s.W * (s.yhi - s.ylo);
+        for (long long i = tid; i < n; i += nthreads) {
+            const int y = s.ylo + (int)(i / s.W), x = (int)(i % s.W);
+            const int t = T[(size_t)(y - s.y0) * s.W + x];
+            if ((set >> t) & 1u) f(x, y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dead ends: persistent cooperative kernel, sweeps until a whole sweep changes nothing.
+// Removal is monotone (a removed cell never comes back and only lowers its neighbours' counts), so
+// the fixed point is unique and any asynchronous order reaches it; stale reads can only delay a
+// removal, never cause a wrong one.  A thread that removes a cell follows the stub it just exposed.
+// ------------------------------------------------------------------------------------------------
+struct CoherentView {   // L2-coherent reads (bypass L1) for planes that other SMs modify in this kernel
+    uint8_t *T; int W, H, y0;
+    __device__ __forceinline__ int t(int x, int y) const {
+        return (x >= 0 && x < W && y >= 0 && y < H) ? (int)__ldcg(T + (size_t)(y - y0) * W + x) : -1;
+    }
+};
+
+__global__ void __launch_bounds__(256) dead_ends_kernel(Shard s, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *flags /* [0]=changed, [1]=sweeps */) {
+    cg::grid_group grid = cg::this_grid();
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    CoherentView v{T, s.W, s.H, s.y0};
+    int sweeps = 0;
+    for (;;) {
+        sweeps++;
+        bool changed = false;
+        sparse_sweep(s, T, SET_REMOVABLE, [&](int x, int y) {
+            int cx = x, cy = y;
+            for (int guard = 0; guard < (1 << 20); guard++) {
+                if (!dead_end_cell(v, cx, cy)) break;
+                const size_t i = (size_t)(cy - s.y0) * s.W + cx;
+                T[i] = T_SIDEWALK; D[i] = 0; A[i] &= (AUX_RING | AUX_EVER);   // place_cell(..., "Sidewalk")
+                changed = true;
+                // follow the stub: the single remaining road-like neighbour, if it is removable and owned
+                int nx = -1, ny = -1;
+                const int ox[4] = {1, -1, 0, 0}, oy[4] = {0, 0, 1, -1};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int t = v.t(cx + ox[k], cy + oy[k]);
+                    if (t >= 0 && in_set(SET_REMOVABLE, t)) { nx = cx + ox[k]; ny = cy + oy[k]; }
+                }
+                if (nx < 0 || ny < s.ylo || ny >= s.yhi) break;
+                cx = nx; cy = ny;
+            }
+        }, tid, nthreads);
+        if (changed) flags[0] = 1;
+        grid.sync();
+        const int any = *((volatile int32_t *)flags);
+        grid.sync();
+        if (tid == 0) { flags[0] = 0; flags[1] = sweeps; }
+        if (!any) break;
+        grid.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upgrade_r2_kernel(tsim_cfg c, Shard s, uint8_t *T, uint16_t *D, uint8_t *A,
+                                                         const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt, int32_t *err) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    const PlaneView v = make_view(s, T, D, A);
+    sparse_sweep(s, T, M(T_R2), [&](int x, int y) {
+        int t_new; uint32_t d_new;
+        const int r = upgrade_r2_cell(c, v, __ldg(rowt + y), __ldg(colt + x), x, y, t_new, d_new);
+        if (r == 0) return;
+        if (r == 3) { *err = 1; return; }
+        const size_t i = v.at(x, y);
+        // in place is safe: the pass reads Sidewalk-ness and sub-block-road-ness of neighbours, which it
+        // never changes (an R2 neighbour matters only when subblock_road_type == R2, where the cell's own
+        // type already decides).
+        T[i] = (uint8_t)t_new; D[i] = (uint16_t)d_new;
+        const uint8_t a = A[i] & (AUX_RING | AUX_EVER);
+        A[i] = r == 1 ? (uint8_t)(a | AUX_EVER) : (uint8_t)(a & ~AUX_EVER);
+    }, tid, nthreads);
+}
+
+__global__ void __launch_bounds__(256) validate_dirs_kernel(Shard s, const uint8_t *T, uint16_t *D) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    const PlaneView v = make_view(s, T, D, nullptr);
+    // in place is safe: only Intersection lists are written, and an Intersection neighbour's list is never read
+    sparse_sweep(s, T, M(T_INTER), [&](int x, int y) {
+        const size_t i = v.at(x, y);
+        const uint32_t od = D[i], nd = validate_dirs_cell(v, x, y, od);
+        if (nd != od) D[i] = (uint16_t)nd;
+    }, tid, nthreads);
+}
+
+__global__ void __launch_bounds__(256) entrance_dirs_kernel(Shard s, const uint8_t *T, uint16_t *D) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    const PlaneView v = make_view(s, T, D, nullptr);
+    // in place is safe: a cell's new list depends on its own old list and on neighbour TYPES only
+    sparse_sweep(s, T, SET_ROAD_LIKE, [&](int x, int y) {
+        const size_t i = v.at(x, y);
+        const uint32_t od = D[i], nd = entrance_dirs_cell(v, x, y, (int)T[i], od);
+        if (nd != od) D[i] = (uint16_t)nd;
+    }, tid, nthreads);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) maps_kernel(long long n, const uint8_t *__restrict__ T, const uint16_t *__restrict__ D,
+                                                   const uint8_t *__restrict__ A, uint8_t *__restrict__ o_road, uint8_t *__restrict__ o_type,
+                                                   uint8_t *__restrict__ o_int, uint8_t *__restrict__ o_dirs) {
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (i0 >= n) return;
+    if (VEC == 16) {
+        const uint4 tq = __ldg(reinterpret_cast<const uint4 *>(T + i0)), aq = __ldg(reinterpret_cast<const uint4 *>(A + i0));
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(D + i0)), d1 = __ldg(reinterpret_cast<const uint4 *>(D + i0 + 8));
+        const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w}, aw[4] = {aq.x, aq.y, aq.z, aq.w};
+        const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        uint32_t r[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0}, in[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int t = (tw[k >> 2] >> (8 * (k & 3))) & 0xff;
+            const uint32_t a = (aw[k >> 2] >> (8 * (k & 3))) & 0xff, d = (dw[k >> 1] >> (16 * (k & 1))) & 0xffff;
+            uint8_t q0, q1, q2, q3;
+            maps_cell(t, d, a, q0, q1, q2, q3);
+            r[k >> 2] |= (uint32_t)q0 << (8 * (k & 3)); ty[k >> 2] |= (uint32_t)q1 << (8 * (k & 3));
+            in[k >> 2] |= (uint32_t)q2 << (8 * (k & 3)); al[k >> 2] |= (uint32_t)q3 << (8 * (k & 3));
+        }
+        *reinterpret_cast<uint4 *>(o_road + i0) = make_uint4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<uint4 *>(o_type + i0) = make_uint4(ty[0], ty[1], ty[2], ty[3]);
+        *reinterpret_cast<uint4 *>(o_int + i0) = make_uint4(in[0], in[1], in[2], in[3]);
+        *reinterpret_cast<uint4 *>(o_dirs + i0) = make_uint4(al[0], al[1], al[2], al[3]);
+    } else {
+        maps_cell(T[i0], D[i0], A[i0], o_road[i0], o_type[i0], o_int[i0], o_dirs[i0]);
+    }
+}
+
+static int coop_grid(const void *kernel, int threads) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+static int sweep_grid(const Shard &s) {
+    const long long strips = ((s.W & 15) == 0) ? (long long)(s.W >> 4) * (s.yhi - s.ylo) : (long long)s.W * (s.yhi - s.ylo);
+    long long blocks = (strips + 255) / 256;
+    const long long cap = 148LL * 32;   // persistent-ish: 32 CTAs per SM worth of work per launch, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace tsim
+
+using namespace tsim;
+
+static tsim_status check_planes(const tsim_planes *p, const char *who) {
+    if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id) { set_error("%s: NULL plane", who); return TSIM_ERR_CONFIG; }
+    if (((uintptr_t)p->cell_type | (uintptr_t)p->dirs | (uintptr_t)p->aux | (uintptr_t)p->block_id) & 15) {
+        set_error("%s: planes must be 16-byte aligned", who);
+        return TSIM_ERR_CONFIG;
+    }
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_layout_dead_ends(const tsim_cfg *cfg, const tsim_planes *p, int32_t *sweeps, void *workspace,
+                                             size_t ws_bytes, void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if ((st = check_planes(p, "tsim_layout_dead_ends")) != TSIM_OK) return st;
+    if (!workspace || ws_bytes < 64) { set_error("tsim_layout_dead_ends: workspace too small"); return TSIM_ERR_WORKSPACE; }
+    cudaStream_t cs = (cudaStream_t)stream;
+    Shard s(*cfg);
+    int32_t *flags = (int32_t *)workspace;
+    TSIM_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), cs));
+    int grid = coop_grid((const void *)dead_ends_kernel, 256);
+    uint8_t *T = p->cell_type; uint16_t *D = p->dirs; uint8_t *A = p->aux;
+    void *args[] = {&s, &T, &D, &A, &flags};
+    TSIM_CUDA(cudaLaunchCooperativeKernel((const void *)dead_ends_kernel, dim3(grid), dim3(256), args, 0, cs));
+    if (sweeps) TSIM_CUDA(cudaMemcpyAsync(sweeps, flags + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_layout_upgrade_r2(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines, int32_t *err_flag,
+                                              void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if ((st = check_planes(p, "tsim_layout_upgrade_r2")) != TSIM_OK) return st;
+    if (!lines || !lines->row || !lines->col) { set_error("tsim_layout_upgrade_r2: NULL line table"); return TSIM_ERR_CONFIG; }
+    if (!err_flag) { set_error("tsim_layout_upgrade_r2: NULL err_flag"); return TSIM_ERR_CONFIG; }
+    cudaStream_t cs = (cudaStream_t)stream;
+    Shard s(*cfg);
+    upgrade_r2_kernel<<<sweep_grid(s), 256, 0, cs>>>(*cfg, s, p->cell_type, p->dirs, p->aux, lines->row, lines->col, err_flag);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_layout_fix_dirs(const tsim_cfg *cfg, const tsim_planes *p, void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if ((st = check_planes(p, "tsim_layout_fix_dirs")) != TSIM_OK) return st;
+    cudaStream_t cs = (cudaStream_t)stream;
+    Shard s(*cfg);
+    validate_dirs_kernel<<<sweep_grid(s), 256, 0, cs>>>(s, p->cell_type, p->dirs);
+    TSIM_LAUNCH_CHECK();
+    entrance_dirs_kernel<<<sweep_grid(s), 256, 0, cs>>>(s, p->cell_type, p->dirs);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint8_t *is_road, uint8_t *road_type, uint8_t *intersection,
+                                 uint8_t *allowed_dirs, void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if ((st = check_planes(p, "tsim_maps")) != TSIM_OK) return st;
+    if (!is_road || !road_type || !intersection || !allowed_dirs) { set_error("tsim_maps: NULL output"); return TSIM_ERR_CONFIG; }
+    cudaStream_t cs = (cudaStream_t)stream;
+    // maps are produced for the rows this device owns; outputs are [rows][W] starting at row0
+    const long long n = (long long)cfg->width * cfg->rows;
+    const size_t off = (size_t)cfg->halo * cfg->width;
+    const bool aligned = (n % 16 == 0) && (off % 16 == 0) &&
+                         !(((uintptr_t)is_road | (uintptr_t)road_type | (uintptr_t)intersection | (uintptr_t)allowed_dirs) & 15);
+    if (aligned)
+        maps_kernel<16><<<div_up(n, 16 * 256), 256, 0, cs>>>(n, p->cell_type + off, p->dirs + off, p->aux + off, is_road, road_type, intersection, allowed_dirs);
+    else
+        maps_kernel<1><<<div_up(n, 256), 256, 0, cs>>>(n, p->cell_type + off, p->dirs + off, p->aux + off, is_road, road_type, intersection, allowed_dirs);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
