@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native CityModel hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S]
+
+Workload (BASELINE.json configs[1]): a S x S synthetic city (default 4096 x 4096), ALL layout
+generation passes -- frame, roads, sub-block carving, flood-fill zoning, dead ends, R2 upgrade, block
+entrances, direction fixes, traffic lights with controlled-road linking, derived maps.  One "step" is
+one full generation of the city from its band lists and tapes.
+
+Prints ONE JSON line (see the task contract): `value` = cells/s with inputs resident in HBM,
+`e2e` = the same through the public API with host buffers (tapes H2D, planes + maps D2H inside the
+timed region), `roofline` for the dominant pass, `cpu_baseline` = the C oracle port on the host.
+`--impl reference` times the CPU restatement (oracle port; the Python reference cannot travel to
+the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per cell per pass
+PASS_BYTES = {"frame_roads": 4, "carve": 6, "zones": 6, "dead_ends": 2, "upgrade_r2": 4, "entrances": 6,
+              "fix_dirs": 10, "lights": 5, "maps": 8}
+KERNELS_PER_STEP = {"frame_roads": 1, "carve": 7, "zones": 7, "dead_ends": 1, "upgrade_r2": 1, "entrances": 1,
+                    "fix_dirs": 2, "lights": 20, "maps": 1}
+CPU_SAMPLE = 2048   # the CPU arm runs a CPU_SAMPLE x CPU_SAMPLE city per step
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_inputs(size, seed, carve=True):
+    from trafficsimulation_b200 import tapes
+    hb, vb = tapes.synth_bands(seed, width=size, height=size)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    return hb, vb, cap, tapes.synth_zone_tape(seed, cap), np.zeros(cap, np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(size, steps, warmup, seed=4096):
+    """The C oracle port, single thread, full pipeline on a size x size city."""
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    hb, vb, cap, tz, te = synth_inputs(size, seed)
+    cfg = O.make_cfg(width=size, height=size, fast_reach=1)
+    o0 = O.OracleCity(cfg, hb, vb)
+    o0.frame(); o0.roads()
+    tc = tapes.synth_carve_tape(seed, o0.nothing_blobs())
+    times = []
+    for i in range(warmup + steps):
+        oc = O.OracleCity(cfg, hb, vb)
+        t0 = time.perf_counter()
+        oc.run_all(tz, tc, te, carve=True)
+        oc.simple_maps()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return size * size * len(times) / sum(times), sum(times) / len(times)
+
+
+class ClockSampler:
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6 and parts[0].isdigit():
+                self.rows.append(parts)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons)}
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    size, seed = args.size, 4096 + rank    # weak scaling: every rank generates its own size x size city
+    hb, vb, cap, tz, te = synth_inputs(size, seed)
+    city = GpuCityLayout(width=size, height=size, carve_subblock_roads=True, device=dev)
+    city.set_bands(hb, vb)
+    city._build_roads_and_sidewalks()
+    n_blobs, table = city.label_nothing()
+    tc = tapes.synth_carve_tape(seed, table.cpu().numpy())
+    d_tz, d_te = torch.from_numpy(tz).to(dev), torch.from_numpy(te).to(dev)
+    d_tc = torch.from_numpy(tc).to(dev)
+    cells = size * size
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step():
+        city.generate(d_tz, d_tc, d_te, check=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    city._check_flag("warmup")
+
+    # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events on the launch stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local) as clocks:
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            step()
+            b.record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    city._check_flag("timed steps")
+    t_dev = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms = float(t_dev.item())
+    value = cells * world * args.steps / (ms * 1e-3)
+
+    # ---- per-pass breakdown (rank 0, same stream, events between passes)
+    passes = {}
+    if rank == 0:
+        names = ["frame_roads", "carve", "zones", "dead_ends", "upgrade_r2", "entrances", "fix_dirs", "lights", "maps"]
+        calls = [city._build_roads_and_sidewalks, lambda: city._carve_subblock_roads(d_tc, check=False),
+                 lambda: city._flood_fill_blocks_storing_data(d_tz, check=False), city._eliminate_dead_ends,
+                 lambda: city._upgrade_r2_to_intersections(check=False), lambda: city._final_place_block_entrances(d_te, check=False),
+                 lambda: (city._remove_invalid_intersection_directions(), city._add_entrance_directions()),
+                 lambda: city._add_traffic_lights(check=False), city._build_simple_maps]
+        acc = {n: 0.0 for n in names}
+        reps = max(3, min(args.steps, 10))
+        for _ in range(reps):
+            flush.fill_(1)
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            marks[0].record()
+            for i, f in enumerate(calls):
+                f()
+                marks[i + 1].record()
+            torch.cuda.synchronize()
+            for i, n in enumerate(names):
+                acc[n] += marks[i].elapsed_time(marks[i + 1])
+        peak, peak_src = measured_peaks()
+        sweeps = city.sweeps()
+        for n in names:
+            t = acc[n] / reps
+            bpc = PASS_BYTES[n] * (sweeps if n == "dead_ends" else 1)
+            gbs = cells * bpc / (t * 1e-3) / 1e9
+            passes[n] = {"ms": round(t, 4), "cells_per_s": cells / (t * 1e-3), "alg_bytes_per_cell": bpc,
+                         "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4)}
+
+    # ---- end to end through the public API with host buffers
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_tz, h_tc, h_te = pin(tz), pin(tc), pin(te)
+    h_rows, h_cols = city.row_table.cpu().pin_memory(), city.col_table.cpu().pin_memory()
+    outs = {"cell_type": city.cell_type, "dirs": city.dirs, "aux": city.aux, "block_id": city.block_id}
+    h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
+    h_maps = None
+    h2d = sum(t.numel() * t.element_size() for t in (h_tz, h_tc, h_te, h_rows, h_cols))
+
+    def e2e_step():
+        nonlocal h_maps
+        city.row_table.copy_(h_rows, non_blocking=True); city.col_table.copy_(h_cols, non_blocking=True)
+        d_tz.copy_(h_tz, non_blocking=True); d_tc.copy_(h_tc, non_blocking=True); d_te.copy_(h_te, non_blocking=True)
+        city.generate(d_tz, d_tc, d_te, check=False)
+        if h_maps is None:
+            h_maps = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in city.maps.items()}
+        for k, v in outs.items():
+            h_out[k].copy_(v, non_blocking=True)
+        for k, v in city.maps.items():
+            h_maps[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+        city._check_flag("e2e")
+
+    e2e_step()
+    d2h = sum(t.numel() * t.element_size() for t in list(h_out.values()) + list(h_maps.values()))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = cells * world * args.steps / float(t_e2e.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        top = max(passes, key=lambda n: passes[n]["ms"])
+        alg_bytes = cells * passes[top]["alg_bytes_per_cell"]
+        roof = {"bound": "hbm", "kernel": top, "achieved": passes[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": passes[top]["frac_of_measured_peak"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes}
+        total_alg = sum(cells * p["alg_bytes_per_cell"] for p in passes.values())
+        pipeline_gbs = total_alg * args.steps / (ms * 1e-3) / 1e9 / world
+        cpu_val, cpu_s = cpu_arm(CPU_SAMPLE, 2, 1)
+        line = {
+            "metric": "grid cells/sec, full layout generation (all passes)", "value": value, "unit": "cells/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{size}x{size} synthetic city layout, all generation passes (carve + lights + maps)",
+                       "cells_per_gpu": cells, "parallelism": "one city per GPU" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB write)", "seed": 4096,
+                       "blocks": int(city.flags[2].item()), "lights": int(city.flags[3].item()), "dead_end_sweeps": city.sweeps()},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": sum(KERNELS_PER_STEP.values()) * args.steps,
+            "roofline": roof,
+            "pipeline": {"algorithmic_bytes_per_cell": total_alg / cells, "achieved_gbs": round(pipeline_gbs, 1),
+                         "frac_of_measured_peak": round(pipeline_gbs / peak, 4)},
+            "passes": passes,
+            "cpu_baseline": {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
+                             "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, sec = cpu_arm(CPU_SAMPLE, args.steps, args.warmup)
+    cores = 1
+    line = {
+        "impl": "reference", "metric": "grid cells/sec, full layout generation (all passes)", "value": val, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.size}x{args.size} synthetic city layout, all generation passes (carve + lights + maps)",
+                   "sample": f"{CPU_SAMPLE}x{CPU_SAMPLE} city per step"},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port",
+                         "sample": f"C restatement of the reference's passes (oracle/city_oracle.c), {CPU_SAMPLE}x{CPU_SAMPLE} city per step; "
+                                   "the Python reference itself cannot travel to the GPU box (BASELINE.md has its numbers)"},
+        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=4096)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        reference(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

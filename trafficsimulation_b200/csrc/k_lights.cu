@@ -24,14 +24,13 @@ namespace cg = cooperative_groups;
 
 namespace tsim {
 
-constexpr int RT = 64;              // reach tile edge
 constexpr int F_CR = 1, F_TL = 2;   // flag plane bits
 constexpr int BFS_CAP = 160;        // visited cells of an exact fallback search
 
 struct LightsCtx {
     int W, H, tl_range, cap_lights;
     const uint8_t *T; const uint16_t *D;
-    const uint8_t *R;   // reach bits: 1 = FW, 2 = BW
+    const unsigned long long *fw, *bw; int wp;   // reach bit-planes: FW = reachable from the pivot, BW = reaches it
     const uint8_t *F;   // F_CR / F_TL
     int32_t *err;
     __device__ __forceinline__ bool has(int x, int y) const { return x >= 0 && x < W && y >= 0 && y < H; }
@@ -50,84 +49,169 @@ __global__ void __launch_bounds__(256) pivot_kernel(long long n, long long mid, 
 
 __global__ void init_pivot_kernel(int32_t *piv) { piv[0] = 0x7fffffff; piv[1] = 0x7fffffff; }
 
-__global__ void reach_seed_kernel(int W, int32_t *piv, uint8_t *R, uint8_t *dirty) {
+// ---------------------------------------------------------------- arrow bit-planes
+// One bit per cell and direction: AR[d][y][wx] bit (x & 63) = cell (x,y) has arrow d.  64 cells per
+// word turn a lane march of 64 steps into a 6-step Kogge-Stone fill, and 32 rows per warp turn a
+// column march into a 5-step shuffle scan.
+struct BitPlanes {
+    unsigned long long *ar[4];   // arrows N,E,S,W
+    unsigned long long *fw, *bw; // reachable from the pivot / reaches the pivot
+    int wp;                      // words per row
+};
+
+__global__ void __launch_bounds__(256) pack_arrows_kernel(int W, int H, const uint16_t *__restrict__ D, BitPlanes bp) {
+    // one warp per 64 cells of a row: two ballots per direction
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)bp.wp * H) return;
+    const int y = (int)(gw / bp.wp), wx = (int)(gw % bp.wp), x0 = wx * 64;
+    const uint32_t d0 = (x0 + lane < W) ? D[(size_t)y * W + x0 + lane] : 0u;
+    const uint32_t d1 = (x0 + 32 + lane < W) ? D[(size_t)y * W + x0 + 32 + lane] : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned long long lo = __ballot_sync(0xffffffffu, (d0 >> k) & 1u), hi = __ballot_sync(0xffffffffu, (d1 >> k) & 1u);
+        if (lane == 0) bp.ar[k][(size_t)y * bp.wp + wx] = lo | (hi << 32);
+    }
+    if (lane == 0) { bp.fw[(size_t)y * bp.wp + wx] = 0ull; bp.bw[(size_t)y * bp.wp + wx] = 0ull; }
+}
+
+constexpr int RTH = 32;   // rows per warp tile (tile = 64 x 32 cells)
+
+__global__ void reach_seed_kernel(int W, int32_t *piv, BitPlanes bp, uint8_t *dirty) {
     int p = piv[0] != 0x7fffffff ? piv[0] : piv[1];
     if (p == 0x7fffffff) { piv[0] = -1; return; }   // no intersection at all: every query goes to the exact search
     piv[0] = p;
-    R[p] = 3;
-    const int tilesx = (W + RT - 1) / RT;
-    dirty[((p / W) / RT) * tilesx + (p % W) / RT] = 1;
+    const int x = p % W, y = p / W;
+    bp.fw[(size_t)y * bp.wp + (x >> 6)] = 1ull << (x & 63);
+    bp.bw[(size_t)y * bp.wp + (x >> 6)] = 1ull << (x & 63);
+    dirty[(y / RTH) * bp.wp + (x >> 6)] = 1;
+}
+
+// occluded fills inside a 64-bit row word (Kogge-Stone): `p` = cells that may be entered from the
+// lower (up-fill) / higher (down-fill) neighbour
+__device__ __forceinline__ unsigned long long fill_up(unsigned long long f, unsigned long long p) {
+    f |= p & (f << 1);  p &= p << 1;
+    f |= p & (f << 2);  p &= p << 2;
+    f |= p & (f << 4);  p &= p << 4;
+    f |= p & (f << 8);  p &= p << 8;
+    f |= p & (f << 16); p &= p << 16;
+    f |= p & (f << 32);
+    return f;
+}
+__device__ __forceinline__ unsigned long long fill_down(unsigned long long f, unsigned long long p) {
+    f |= p & (f >> 1);  p &= p >> 1;
+    f |= p & (f >> 2);  p &= p >> 2;
+    f |= p & (f >> 4);  p &= p >> 4;
+    f |= p & (f >> 8);  p &= p >> 8;
+    f |= p & (f >> 16); p &= p >> 16;
+    f |= p & (f >> 32);
+    return f;
+}
+// the same fills across the 32 rows of a warp tile (lane = row): row y may be entered from row y-1
+// (lane_up) / y+1 (lane_down) at the columns of `p`
+__device__ __forceinline__ unsigned long long lanes_up(unsigned long long f, unsigned long long p, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long ff = __shfl_up_sync(0xffffffffu, f, d), pp = __shfl_up_sync(0xffffffffu, p, d);
+        if (lane < d) { ff = 0ull; pp = 0ull; }
+        f |= p & ff;
+        p &= pp;
+    }
+    return f;
+}
+__device__ __forceinline__ unsigned long long lanes_down(unsigned long long f, unsigned long long p, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long ff = __shfl_down_sync(0xffffffffu, f, d), pp = __shfl_down_sync(0xffffffffu, p, d);
+        if (lane + d > 31) { ff = 0ull; pp = 0ull; }
+        f |= p & ff;
+        p &= pp;
+    }
+    return f;
 }
 
 // ---------------------------------------------------------------- reach (FW/BW from the pivot)
-// Persistent cooperative kernel.  A tile is (re)processed only when a neighbouring tile changed one
-// of its border cells; inside a tile the closure is iterated in shared memory.
-__global__ void __launch_bounds__(256) reach_kernel(int W, int H, const uint16_t *__restrict__ D, uint8_t *R, uint8_t *dirty0, uint8_t *dirty1,
-                                                    int32_t *counter /* [2] */) {
+// Persistent cooperative kernel, one WARP per 64x32 tile.  A tile is (re)processed only when a
+// neighbouring tile changed one of its border cells; inside a tile the closure is a handful of
+// bit-parallel fills instead of a cell-by-cell march.
+__global__ void __launch_bounds__(256) reach_kernel(int W, int H, BitPlanes bp, uint8_t *dirty0, uint8_t *dirty1, int32_t *counter /* [0..1] wave counters, [2] waves */) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ uint16_t sD[(RT + 2) * (RT + 2)];
-    __shared__ uint8_t sR[(RT + 2) * (RT + 2)];
-    __shared__ int s_flag;
-    const int tilesx = (W + RT - 1) / RT, tilesy = (H + RT - 1) / RT, ntiles = tilesx * tilesy;
-    constexpr int P = RT + 2;
-    for (int wave = 0;; wave++) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int wp = bp.wp, tilesy = (H + RTH - 1) / RTH, ntiles = wp * tilesy;
+    int wave = 0;
+    for (;; wave++) {
         uint8_t *cur = (wave & 1) ? dirty1 : dirty0, *nxt = (wave & 1) ? dirty0 : dirty1;
         int32_t *cnt = counter + (wave & 1);
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            __syncthreads();
-            if (threadIdx.x == 0) { s_flag = __ldcg(cur + tile); cur[tile] = 0; }
-            __syncthreads();
-            if (!s_flag) continue;
-            const int tx0 = (tile % tilesx) * RT, ty0 = (tile / tilesx) * RT;
-            for (int i = threadIdx.x; i < P * P; i += blockDim.x) {
-                const int x = tx0 - 1 + i % P, y = ty0 - 1 + i / P;
-                const bool ok = x >= 0 && x < W && y >= 0 && y < H;
-                sD[i] = ok ? D[(size_t)y * W + x] : (uint16_t)0;
-                sR[i] = ok ? __ldcg(R + (size_t)y * W + x) : (uint8_t)0;
-            }
-            __syncthreads();
-            for (;;) {
-                bool ch = false;
-                for (int i = threadIdx.x; i < RT * RT; i += blockDim.x) {
-                    const int j = (i / RT + 1) * P + (i % RT + 1);
-                    const uint32_t d = sD[j];
-                    if (!d) continue;
-                    uint32_t r = sR[j];
-                    if (r == 3) continue;
-                    uint32_t nr = r;
-                    // FW: a neighbour that points at me and is reachable
-                    if ((sR[j - P] & 1) && dl_has(sD[j - P], DN)) nr |= 1;   // cell below points north
-                    if ((sR[j + P] & 1) && dl_has(sD[j + P], DS)) nr |= 1;
-                    if ((sR[j - 1] & 1) && dl_has(sD[j - 1], DE)) nr |= 1;
-                    if ((sR[j + 1] & 1) && dl_has(sD[j + 1], DW)) nr |= 1;
-                    // BW: one of my arrows leads to a cell that reaches the pivot
-                    if ((dl_has(d, DN) && (sR[j + P] & 2)) || (dl_has(d, DS) && (sR[j - P] & 2)) ||
-                        (dl_has(d, DE) && (sR[j + 1] & 2)) || (dl_has(d, DW) && (sR[j - 1] & 2))) nr |= 2;
-                    if (nr != r) { sR[j] = (uint8_t)nr; ch = true; }
+        for (int tile = warp; tile < ntiles; tile += nwarps) {
+            int flag = 0;
+            if (lane == 0) { flag = __ldcg(cur + tile); if (flag) cur[tile] = 0; }
+            flag = __shfl_sync(0xffffffffu, flag, 0);
+            if (!flag) continue;
+            const int wx = tile % wp, ty = tile / wp, y = ty * RTH + lane;
+            const bool in = y < H;
+            const size_t o = (size_t)y * wp + wx;
+            auto ld = [&](const unsigned long long *pl, bool ok, size_t off) { return ok ? __ldcg(pl + off) : 0ull; };
+            const unsigned long long aN = ld(bp.ar[DN], in, o), aE = ld(bp.ar[DE], in, o), aS = ld(bp.ar[DS], in, o), aW = ld(bp.ar[DW], in, o);
+            unsigned long long f = ld(bp.fw, in, o), b = ld(bp.bw, in, o);
+            const unsigned long long f0 = f, b0 = b;
+            // halos: west / east words of my row, rows just below / above the tile
+            const bool hw = in && wx > 0, he = in && wx + 1 < wp;
+            const unsigned long long fW = ld(bp.fw, hw, o - 1), bW = ld(bp.bw, hw, o - 1), eW = ld(bp.ar[DE], hw, o - 1);
+            const unsigned long long fE = ld(bp.fw, he, o + 1), bE = ld(bp.bw, he, o + 1), wE = ld(bp.ar[DW], he, o + 1);
+            const int yb = ty * RTH - 1, yt = ty * RTH + RTH;
+            const bool hb = yb >= 0, ht = yt < H;
+            const size_t ob = (size_t)yb * wp + wx, ot = (size_t)yt * wp + wx;
+            // (loaded by every lane: same address, one transaction)
+            const unsigned long long fB = ld(bp.fw, hb, ob), bB = ld(bp.bw, hb, ob), nB = ld(bp.ar[DN], hb, ob);
+            const unsigned long long fT = ld(bp.fw, ht, ot), bT = ld(bp.bw, ht, ot), sT = ld(bp.ar[DS], ht, ot);
+            // inflow that never changes while the tile iterates
+            const unsigned long long f_in = (((fW & eW) >> 63) & 1ull) | ((((fE & wE) & 1ull)) << 63) |
+                                            (lane == 0 ? (fB & nB) : 0ull) | (lane == 31 ? (fT & sT) : 0ull);
+            const unsigned long long b_in = (aW & ((bW >> 63) & 1ull)) | (aE & ((bE & 1ull) << 63)) |
+                                            (lane == 0 ? (aS & bB) : 0ull) | (lane == 31 ? (aN & bT) : 0ull);
+            f |= f_in; b |= b_in;
+            for (int it = 0; it < 4096; it++) {
+                const unsigned long long pf = f, pb = b;
+                // FW moves WITH the arrows
+                f = fill_up(f, aE << 1);                 // east:  x entered from x-1 if (x-1) has E
+                f = fill_down(f, aW >> 1);               // west
+                {   // north: row y entered from y-1 where row y-1 has N
+                    unsigned long long pn = __shfl_up_sync(0xffffffffu, aN, 1); if (lane == 0) pn = 0ull;
+                    f = lanes_up(f, pn, lane);
+                    unsigned long long ps = __shfl_down_sync(0xffffffffu, aS, 1); if (lane == 31) ps = 0ull;
+                    f = lanes_down(f, ps, lane);
                 }
-                if (!__syncthreads_or(ch)) break;
+                // BW moves AGAINST the arrows: a cell with arrow d inherits from its d-neighbour
+                b = fill_down(b, aE);                    // cell x takes from x+1 if x has E
+                b = fill_up(b, aW);                      // cell x takes from x-1 if x has W
+                b = lanes_down(b, aN, lane);             // row y takes from y+1 where row y has N
+                b = lanes_up(b, aS, lane);               // row y takes from y-1 where row y has S
+                if (!__any_sync(0xffffffffu, f != pf || b != pb)) break;
             }
-            // write back; a changed border cell wakes the tile across that border
-            bool woke = false;
-            for (int i = threadIdx.x; i < RT * RT; i += blockDim.x) {
-                const int lx = i % RT, ly = i / RT, x = tx0 + lx, y = ty0 + ly;
-                if (x >= W || y >= H) continue;
-                const uint8_t r = sR[(ly + 1) * P + lx + 1];
-                const size_t g = (size_t)y * W + x;
-                if (r != __ldcg(R + g)) {
-                    R[g] = r;
-                    if (lx == 0 && x > 0) { nxt[tile - 1] = 1; woke = true; }
-                    if (lx == RT - 1 && x + 1 < W) { nxt[tile + 1] = 1; woke = true; }
-                    if (ly == 0 && y > 0) { nxt[tile - tilesx] = 1; woke = true; }
-                    if (ly == RT - 1 && y + 1 < H) { nxt[tile + tilesx] = 1; woke = true; }
-                }
+            const bool chf = f != f0, chb = b != b0;
+            if (in && chf) bp.fw[o] = f;
+            if (in && chb) bp.bw[o] = b;
+            // wake the neighbours whose halo I changed
+            const unsigned long long ch = (f ^ f0) | (b ^ b0);
+            const bool wW = __any_sync(0xffffffffu, in && (ch & 1ull)) && wx > 0;
+            const bool wEe = __any_sync(0xffffffffu, in && (ch >> 63)) && wx + 1 < wp;
+            const bool wB = __shfl_sync(0xffffffffu, ch != 0ull, 0) && ty > 0;
+            const int last = min(RTH, H - ty * RTH) - 1;
+            const bool wT = __shfl_sync(0xffffffffu, ch != 0ull, last) && ty + 1 < tilesy;
+            if (lane == 0) {
+                int woke = 0;
+                if (wW) { nxt[tile - 1] = 1; woke = 1; }
+                if (wEe) { nxt[tile + 1] = 1; woke = 1; }
+                if (wB) { nxt[tile - wp] = 1; woke = 1; }
+                if (wT) { nxt[tile + wp] = 1; woke = 1; }
+                if (woke) atomicAdd(cnt, 1);
             }
-            if (woke) atomicAdd(cnt, 1);
         }
         __threadfence();
         grid.sync();
         const int any = *((volatile int32_t *)cnt);
-        if (blockIdx.x == 0 && threadIdx.x == 0) counter[(wave + 1) & 1] = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { counter[(wave + 1) & 1] = 0; counter[2] = wave + 1; }
         if (!any) break;
         grid.sync();
     }
@@ -184,9 +268,11 @@ __device__ bool bfs_backward(const LightsCtx &L, int from, int to) {   // does `
 // cell.py:201-227 `a.leads_to(b)`
 __device__ __forceinline__ bool leads_to(const LightsCtx &L, int a, int b) {
     if (a == b) return true;
-    const uint8_t ra = L.R[a], rb = L.R[b];
-    if ((ra & 2) && (rb & 1)) return true;
-    if (!(ra & 2)) return bfs_forward(L, a, b);
+    const int ax = a % L.W, ay = a / L.W, bx = b % L.W, by = b / L.W;
+    const bool a_bw = (L.bw[(size_t)ay * L.wp + (ax >> 6)] >> (ax & 63)) & 1ull;
+    const bool b_fw = (L.fw[(size_t)by * L.wp + (bx >> 6)] >> (bx & 63)) & 1ull;
+    if (a_bw && b_fw) return true;
+    if (!a_bw) return bfs_forward(L, a, b);
     return bfs_backward(L, a, b);
 }
 
@@ -392,13 +478,18 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
     const int W = cfg->width, H = cfg->height;
     const long long n = (long long)W * H;
     const int ntiles = div_up(n, SCAN_TILE);
-    const int rtiles = div_up(W, RT) * div_up(H, RT);
+    const int rtiles = div_up(W, 64) * div_up(H, RTH);
     // workspace layout
     char *w = (char *)workspace;
     size_t o = 0;
     auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
-    int32_t *scal = (int32_t *)take(64 * 4);   // [0..1] pivot, [2..3] wave counters, [4..5] link totals
-    uint8_t *R = (uint8_t *)take(n);
+    int32_t *scal = (int32_t *)take(64 * 4);   // [0..1] pivot, [4..5] link totals, [8..9] wave counters, [10] waves
+    const int wp = div_up(W, 64);
+    BitPlanes bp;
+    for (int k = 0; k < 4; k++) bp.ar[k] = (unsigned long long *)take((size_t)wp * H * 8);
+    bp.fw = (unsigned long long *)take((size_t)wp * H * 8);
+    bp.bw = (unsigned long long *)take((size_t)wp * H * 8);
+    bp.wp = wp;
     uint8_t *F = (uint8_t *)take(n);
     int32_t *lid = (int32_t *)take(n * 4);
     int32_t *tile_cnt = (int32_t *)take((size_t)ntiles * 4);
@@ -410,12 +501,13 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
     TSIM_CUDA(cudaMemsetAsync(scal, 0, 64 * 4, cs));
     init_pivot_kernel<<<1, 1, 0, cs>>>(scal);
     TSIM_LAUNCH_CHECK();
-    TSIM_CUDA(cudaMemsetAsync(R, 0, n, cs));
     TSIM_CUDA(cudaMemsetAsync(dirty0, 0, rtiles, cs));
     TSIM_CUDA(cudaMemsetAsync(dirty1, 0, rtiles, cs));
     pivot_kernel<<<div_up(n, 256), 256, 0, cs>>>(n, (long long)(H / 2) * W, p->cell_type, p->dirs, scal);
     TSIM_LAUNCH_CHECK();
-    reach_seed_kernel<<<1, 1, 0, cs>>>(W, scal, R, dirty0);
+    pack_arrows_kernel<<<div_up((long long)wp * H * 32, 256), 256, 0, cs>>>(W, H, p->dirs, bp);
+    TSIM_LAUNCH_CHECK();
+    reach_seed_kernel<<<1, 1, 0, cs>>>(W, scal, bp, dirty0);
     TSIM_LAUNCH_CHECK();
     {
         int dev = 0, sms = 0, per_sm = 0;
@@ -423,16 +515,15 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
         TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reach_kernel, 256, 0));
         int grid = sms * (per_sm < 1 ? 1 : per_sm);
-        if (grid > rtiles) grid = rtiles;
+        if (grid > div_up(rtiles, 8)) grid = div_up(rtiles, 8);
         int Wv = W, Hv = H;
-        const uint16_t *Dp = p->dirs;
-        int32_t *counter = scal + 2;
-        void *args[] = {&Wv, &Hv, &Dp, &R, &dirty0, &dirty1, &counter};
+        int32_t *counter = scal + 8;
+        void *args[] = {&Wv, &Hv, &bp, &dirty0, &dirty1, &counter};
         TSIM_CUDA(cudaLaunchCooperativeKernel((const void *)reach_kernel, dim3(grid), dim3(256), args, 0, cs));
     }
     mark_cr_kernel<<<div_up(n, 256), 256, 0, cs>>>(W, H, p->cell_type, p->dirs, F);
     TSIM_LAUNCH_CHECK();
-    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, p->cell_type, p->dirs, R, F, err_flag};
+    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, p->cell_type, p->dirs, bp.fw, bp.bw, wp, F, err_flag};
     lights_pass_kernel<0><<<div_up(n, 128), 128, 0, cs>>>(L, F, p->aux, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0);
     TSIM_LAUNCH_CHECK();
     // compact the lights in ascending cell order
