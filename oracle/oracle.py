@@ -171,3 +171,105 @@ class OracleCity:
         self.entrance_dirs()
         self.lights()
         return self.planes()
+
+
+# ------------------------------------------------------------------------------------------------
+# tick oracle (oracle/vehicle_oracle.c)
+# ------------------------------------------------------------------------------------------------
+class VSim(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("W", "H", "n_vehicles", "n_groups", "n_lights", "algo", "rain_enabled", "tick")] +
+                [(n, C.c_void_p) for n in (
+                    "occ", "stop", "stuckmap", "rain", "spawn_tick", "origin", "target", "speed", "malf", "rank",
+                    "ev_first", "ev_vehicle", "ev_off", "ev_cells",
+                    "pos", "path_off", "path_len", "steps",
+                    "alive", "base_speed", "cur_speed", "max_steps", "early", "is_stuck", "prev_valid", "malfunction", "direction",
+                    "stuck_ticks", "stranded",
+                    "tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
+                    "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl",
+                    "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer")])
+
+
+def csr(lists, dtype=np.int32):
+    off = np.zeros(len(lists) + 1, np.int32)
+    off[1:] = np.cumsum([len(a) for a in lists])
+    flat = np.concatenate([np.asarray(a, dtype) for a in lists]) if len(lists) and off[-1] else np.zeros(0, dtype)
+    return off, np.ascontiguousarray(flat, dtype)
+
+
+def light_tables_from_reference(lights, ctrl_pairs, groups):
+    """CSR tables of the tick oracle from reference-extracted data.
+
+    lights: sorted light cells; ctrl_pairs: (light cell, controlled cell) pairs; groups: list of dicts with
+    cluster / lights / ns_lights / ew_lights / ns_in / ew_in arrays of cell indices (canonical order).
+    """
+    lights = np.asarray(lights, np.int32)
+    lidx = {int(c): i for i, c in enumerate(lights)}
+    per_light = [[int(c)] for c in lights]
+    for l, c in np.asarray(ctrl_pairs).reshape(-1, 2):
+        per_light[lidx[int(l)]].append(int(c))
+    t = {}
+    t["tl_off"], t["tl_cells"] = csr(per_light)
+    for key, src in (("g_all", "lights"), ("g_ns", "ns_lights"), ("g_ew", "ew_lights")):
+        t[key + "_off"], t[key] = csr([[lidx[int(c)] for c in g[src]] for g in groups])
+    for key, src in (("g_nsin", "ns_in"), ("g_ewin", "ew_in"), ("g_cl", "cluster")):
+        t[key + "_off"], t[key] = csr([g[src] for g in groups])
+    t["n_lights"], t["n_groups"] = len(lights), len(groups)
+    return t
+
+
+class OracleTicks:
+    """State + tapes of the tick oracle.  `tapes` needs: spawn_tick, origin, target, speed, malfunction, rank,
+    ev_tick, ev_vehicle, ev_off, ev_cells (route events sorted by tick), rain_map."""
+
+    def __init__(self, W, H, tables, tapes, n_ticks, algo=0, rain_enabled=False):
+        self.W, self.H, self.n_ticks = W, H, n_ticks
+        nv = len(tapes["spawn_tick"])
+        self.nv = nv
+        a = {}
+        a["occ"] = np.zeros(W * H, np.uint8); a["stop"] = np.zeros(W * H, np.uint8); a["stuckmap"] = np.zeros(W * H, np.uint8)
+        a["rain"] = np.ascontiguousarray(tapes["rain_map"], np.uint8).reshape(-1)
+        for k in ("spawn_tick", "origin", "target"):
+            a[k] = np.ascontiguousarray(tapes[k], np.int32)
+        a["speed"] = np.ascontiguousarray(tapes["speed"], np.uint8); a["malf"] = np.ascontiguousarray(tapes["malfunction"], np.uint8)
+        a["rank"] = np.ascontiguousarray(tapes["rank"], np.int32)
+        ev_tick = np.asarray(tapes["ev_tick"], np.int32)
+        assert np.all(np.diff(ev_tick) >= 0), "route events must be sorted by tick"
+        a["ev_first"] = np.searchsorted(ev_tick, np.arange(n_ticks + 1)).astype(np.int32)
+        a["ev_vehicle"] = np.ascontiguousarray(tapes["ev_vehicle"], np.int32)
+        a["ev_off"] = np.ascontiguousarray(tapes["ev_off"], np.int64)
+        a["ev_cells"] = np.ascontiguousarray(np.append(tapes["ev_cells"], 0), np.int32)
+        for k in ("pos", "path_off", "path_len", "steps", "stranded"):
+            a[k] = np.zeros(nv, np.int32)
+        a["pos"][:] = -1
+        for k in ("alive", "base_speed", "cur_speed", "max_steps", "early", "is_stuck", "prev_valid", "malfunction"):
+            a[k] = np.zeros(nv, np.int8)
+        a["direction"] = np.full(nv, -1, np.int8)
+        a["stuck_ticks"] = np.zeros(nv, np.int16)
+        for k in ("tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
+                  "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl"):
+            a[k] = np.ascontiguousarray(tables[k], np.int32)
+        ng = tables["n_groups"]
+        a["g_cur"] = np.full(ng, -1, np.int32); a["g_pend"] = np.zeros(ng, np.int32)   # apply_phase(0) in __init__ (:115-116)
+        for k in ("g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer"):
+            a[k] = np.zeros(ng, np.int32)
+        self.a = a
+        self.sim = VSim(W, H, nv, ng, tables["n_lights"], algo, int(rain_enabled), 0)
+        for name, _ in VSim._fields_[8:]:
+            setattr(self.sim, name, a[name].ctypes.data)
+        lib().oracle_ticks_run.restype = C.c_int
+
+    def run(self, n=1):
+        rc = lib().oracle_ticks_run(C.byref(self.sim), n)
+        if rc < 0:
+            raise ValueError(f"tape contract violated at tick {-rc - 1} (vehicle at its target in phase A)")
+
+    def state(self):
+        a = self.a
+        alive = a["alive"].astype(bool)
+        pos = np.where(alive, a["pos"], -1)
+        flags = (a["is_stuck"].astype(np.uint8) & 1) | ((a["malfunction"].astype(np.uint8) & 1) << 1) | ((a["direction"] + 1).astype(np.uint8) << 2)
+        return dict(pos=pos, base_speed=np.where(alive, a["base_speed"], 0), stuck_ticks=np.where(alive, a["stuck_ticks"], 0),
+                    vflags=np.where(alive, flags, 0).astype(np.uint8),
+                    occ=np.flatnonzero(a["occ"]).astype(np.int32), stop=np.flatnonzero(a["stop"]).astype(np.int32),
+                    stuckmap=np.flatnonzero(a["stuckmap"]).astype(np.int32),
+                    groups=np.stack([a["g_cur"], a["g_pend"], a["g_qt"], a["g_gap"], a["g_last"]], 1))

@@ -22,3 +22,58 @@ def load(path):
 
 PLANES = ("cell_type", "dirs", "aux", "block_id")
 MAPS = ("is_road_map", "road_type_map", "intersection_map", "allowed_dirs_map")
+
+
+def tick_fixtures():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "ticks_*.npz")))
+
+
+def load_ticks(path):
+    """Tick fixture with route events decoded back to cell lists and bit-packed tapes unpacked."""
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    d["meta"] = json.loads(bytes(d["meta"]).decode())
+    d["name"] = os.path.basename(path)[len("ticks_"):-4]
+    W, H, nv = d["meta"]["W"], d["meta"]["H"], d["meta"]["n_attempts"]
+    d["W"], d["H"], d["n_ticks"] = W, H, d["meta"]["n_ticks"]
+    d["malfunction"] = np.unpackbits(d["malfunction"], axis=1)[:, :nv]
+    d["rain_map"] = np.unpackbits(d["rain_map"], axis=1)[:, :W]
+    ev_len = d["ev_len"]
+    off = np.zeros(len(ev_len) + 1, np.int64)
+    off[1:] = np.cumsum(ev_len)
+    cells = np.zeros(int(off[-1]), np.int32)
+    delta = np.array([W, 1, -W, -1], np.int32)
+    steps, sp = d["ev_steps"], 0
+    for i, n in enumerate(ev_len):
+        if n == 0:
+            continue
+        seg = np.empty(n, np.int32)
+        seg[0] = d["ev_first"][i]
+        if n > 1:
+            seg[1:] = seg[0] + np.cumsum(delta[steps[sp:sp + n - 1]])
+            sp += n - 1
+        cells[off[i]:off[i + 1]] = seg
+    d["ev_off"], d["ev_cells"] = off, cells
+    groups = []
+    ng = len(d["g_cluster_off"]) - 1
+    for g in range(ng):
+        groups.append({f: d["g_" + f][d["g_" + f + "_off"][g]:d["g_" + f + "_off"][g + 1]]
+                       for f in ("cluster", "lights", "ns_lights", "ew_lights", "ns_in", "ew_in")})
+    d["groups"] = groups
+    d["group_state"] = d["group_state"].astype(np.int32)
+    return d
+
+
+def compare_tick(t, got, r):
+    """got: dict(pos, base_speed, stuck_ticks, vflags, occ, stop, stuckmap, groups) after tick t."""
+    want_pos = r["pos"][t]
+    bad = np.flatnonzero(got["pos"] != want_pos)
+    assert len(bad) == 0, (t, "pos", [(int(v), int(got["pos"][v]), int(want_pos[v])) for v in bad[:6]])
+    alive = want_pos >= 0
+    for k in ("base_speed", "stuck_ticks", "vflags"):
+        bad = np.flatnonzero((got[k] != r[k][t]) & alive)
+        assert len(bad) == 0, (t, k, [(int(v), int(got[k][v]), int(r[k][t][v])) for v in bad[:6]])
+    for k in ("occ", "stop", "stuckmap"):
+        want = r[k + "_cells"][r[k + "_off"][t]:r[k + "_off"][t + 1]]
+        assert np.array_equal(got[k], want), (t, k, len(got[k]), len(want))
+    assert np.array_equal(got["groups"], r["group_state"][t]), (t, "groups")

@@ -1,0 +1,29 @@
+"""Pins the C tick oracle (oracle/vehicle_oracle.c) against the LIVE reference tick loop."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from golden_util import compare_tick
+
+pytestmark = pytest.mark.reference
+
+CASES = [
+    dict(seed=12345, n_ticks=120, spawns_per_tick=6, malfunction_p=0.002),
+    dict(seed=7, n_ticks=80, spawns_per_tick=10, malfunction_p=0.0, rain_rect=(40, 40, 160, 120)),
+    dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01,
+         layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"s{c['seed']}")
+def test_tick_oracle_matches_reference(case):
+    from oracle.refharness import ticks
+    r = ticks.run_ticks(**case)
+    lay = r["layout"]
+    tables = O.light_tables_from_reference(lay["links"]["lights"], lay["links"]["ctrl"], r["groups"])
+    sim = O.OracleTicks(r["W"], r["H"], tables, r, r["n_ticks"], rain_enabled=case.get("rain_rect") is not None)
+    assert (r["pos"] >= 0).any()
+    for t in range(r["n_ticks"]):
+        sim.run(1)
+        compare_tick(t, sim.state(), r)
+    assert np.array_equal(sim.a["alive"].astype(bool) | (r["spawned"] == 0), sim.a["alive"].astype(bool) | (r["spawned"] == 0))
