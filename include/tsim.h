@@ -173,6 +173,68 @@ tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const 
 tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint8_t *is_road, uint8_t *road_type,
                       uint8_t *intersection, uint8_t *allowed_dirs, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tick: CityModel.step (city_model.py:1831-1860) = phase A VehicleAgent.step_decide for every active
+ * vehicle (vehicle_base.py:616-663), then phase B in activation order: IntersectionLightGroup.step
+ * (intersection_light_group.py:396-423, QUEUE_ACTUATED :463-494 / FIXED_TIME :427-441, phase commit
+ * :348-384, stop_map writes cell.py:241-251), VehicleAgent.step (vehicle_base.py:666-685: movement
+ * :733-753 via CityModel.move_vehicle city_model.py:1945-1963, tick_stuck :687-693, arrival :755-775),
+ * and the tape-driven spawner (place_vehicle city_model.py:1897-1908).
+ * Activation order, speed / malfunction draws, spawns and planned routes are INPUT tapes.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tsim_light_tables {   /* all device pointers; CSR offsets have n+1 entries */
+    int32_t n_groups, n_lights;
+    const int32_t *tl_off, *tl_cells;          /* light -> its own cell followed by its controlled road cells */
+    const int32_t *g_all_off, *g_all;          /* group -> lights (indices)                                  */
+    const int32_t *g_ns_off, *g_ns;            /* group -> lights of the N-S axis (opposite_pairs["N-S"])    */
+    const int32_t *g_ew_off, *g_ew;            /* group -> lights of the W-E axis                            */
+    const int32_t *g_nsin_off, *g_nsin;        /* group -> ns_in_coords cells (multiset)                     */
+    const int32_t *g_ewin_off, *g_ewin;        /* group -> ew_in_coords cells (multiset)                     */
+    const int32_t *g_cl_off, *g_cl;            /* group -> intersection cluster cells                        */
+} tsim_light_tables;
+
+typedef struct tsim_tick_tapes {     /* all device pointers */
+    int32_t n_ticks, n_vehicles;
+    const int32_t *spawn_first;      /* [n_ticks+1] vehicles (= spawn attempts) are sorted by spawn tick      */
+    const int32_t *origin, *target;  /* [n_vehicles] cell indices                                             */
+    const uint8_t *speed;            /* [n_ticks][n_vehicles] value of random.randint(1,5) if drawn           */
+    const uint8_t *malfunction;      /* [n_ticks][n_vehicles] 1 = the malfunction draw fires                  */
+    const int32_t *rank;             /* [n_ticks][n_vehicles] activation rank (lower steps first)             */
+    const int32_t *ev_first;         /* [n_ticks+1] route events sorted by tick                               */
+    const int32_t *ev_vehicle;       /* [n_events]                                                            */
+    const int64_t *ev_off;           /* [n_events+1] into ev_cells                                            */
+    const int32_t *ev_cells;         /* route arena: cell indices, next cell first                            */
+    const uint8_t *rain_map;         /* [H*W] or NULL (Defaults.RAIN_ENABLED False)                           */
+} tsim_tick_tapes;
+
+typedef struct tsim_tick_state {     /* all device pointers, owned by the caller */
+    uint8_t *occupancy, *stop_map, *stuck_map;   /* [H*W] CityModel.occupancy_map / stop_map / stuck_map      */
+    int32_t *claim, *stopw;                      /* [H*W] scratch planes, prepared by tsim_tick_init          */
+    /* vehicle SoA [n_vehicles] */
+    int32_t *pos, *path_len, *steps, *stranded;
+    int64_t *path_off;
+    int16_t *stuck_ticks;
+    int8_t *alive, *base_speed, *cur_speed, *max_steps, *early, *is_stuck, *prev_valid, *malfunction, *direction, *moved;
+    /* light-group state [n_groups] */
+    int32_t *g_cur, *g_pend, *g_qt, *g_gap, *g_last, *g_ft_phase, *g_ft_timer, *g_plan;
+    int32_t *scalars;                            /* [16]: [0] next tick, [1] error flag, [2] fixed-point iterations (sum),
+                                                    [3] vehicle updates (sum of live vehicles per tick), [4..] internal */
+} tsim_tick_state;
+
+/* zero the maps / vehicle / group state and prepare the scratch planes */
+tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
+                           const tsim_tick_state *st, void *stream);
+
+/* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME */
+tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
+                          const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
+
+/* labels the 4-connected components of mask != 0 (u8 plane) in raster discovery order; same outputs as
+   tsim_layout_label_nothing.  Used for the intersection clusters of _create_intersection_light_groups
+   (city_model.py:1587-1650). */
+tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask, int32_t *labels, int32_t *blobs,
+                            int32_t cap, int32_t *n_blobs, void *workspace, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

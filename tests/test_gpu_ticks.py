@@ -1,0 +1,85 @@
+"""GPU parity of the tick (tsim_tick_run through the C ABI) vs the reference fixtures and the C oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import tick_fixtures, load_ticks, compare_tick
+
+pytestmark = pytest.mark.gpu
+
+
+def build_city(cfgd, hb, vb, tz, tc, te):
+    from trafficsimulation_b200.layout import GpuCityLayout
+    cfgd = dict(cfgd)
+    carve = cfgd.pop("carve_subblock_roads", False)
+    city = GpuCityLayout(carve_subblock_roads=carve, **cfgd)
+    city.set_bands(hb, vb)
+    city.generate(tz, tc, te)
+    return city
+
+
+@pytest.mark.parametrize("path", tick_fixtures(), ids=lambda p: os.path.basename(p)[6:-4])
+def test_gpu_ticks_match_reference_fixture(path):
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    from trafficsimulation_b200.light_groups import groups_as_cell_lists
+    r = load_ticks(path)
+    city = build_city(r["meta"]["cfg"], r["hbands"], r["vbands"], r["tape_zone"], r["tape_carve"], r["tape_entrance"])
+    tabs = light_tables_from_layout(city)
+    lights = city.light_links_host()["lights"]
+    mine = groups_as_cell_lists(tabs, lights)
+    assert len(mine) == len(r["groups"])
+    for i, (a, b) in enumerate(zip(mine, r["groups"])):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), ("group table", i, k)
+    sim = GpuTraffic(r["W"], r["H"], tabs, r, r["n_ticks"], rain_enabled=r["meta"]["rain_enabled"])
+    for t in range(r["n_ticks"]):
+        sim.step(1)
+        compare_tick(t, sim.state_host(), r)
+    c = sim.counters()
+    assert c["tick"] == r["n_ticks"] and c["vehicle_updates"] == int((r["pos"][:-1] >= 0).sum())
+
+
+def test_gpu_ticks_multi_tick_launch_equals_single_ticks():
+    """n ticks in one persistent launch == n launches of one tick."""
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    r = load_ticks(tick_fixtures()[0])
+    city = build_city(r["meta"]["cfg"], r["hbands"], r["vbands"], r["tape_zone"], r["tape_carve"], r["tape_entrance"])
+    tabs = light_tables_from_layout(city)
+    sim = GpuTraffic(r["W"], r["H"], tabs, r, r["n_ticks"], rain_enabled=r["meta"]["rain_enabled"])
+    sim.step(60)
+    compare_tick(59, sim.state_host(), r)
+    sim.step(r["n_ticks"] - 60)
+    compare_tick(r["n_ticks"] - 1, sim.state_host(), r)
+
+
+@pytest.mark.parametrize("size,nveh,algo", [(512, 20000, "QUEUE_ACTUATED"), (768, 60000, "FIXED_TIME")])
+def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo):
+    """Dense synthetic traffic on a city the reference cannot plan routes for: CUDA vs the pinned C oracle."""
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    seed = size
+    hb, vb = tapes.synth_bands(seed, width=size, height=size)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    city = build_city(dict(width=size, height=size), hb, vb, tapes.synth_zone_tape(seed, cap), None, np.zeros(cap, np.int32))
+    tabs = light_tables_from_layout(city)
+    planes = city.planes_host()
+    n_ticks = 50
+    tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], nveh, n_ticks, route_len=120, spawn_ticks=5,
+                             malfunction_p=0.001)
+    sim = GpuTraffic(size, size, tabs, tp, n_ticks, algo=algo)
+    ora = O.OracleTicks(size, size, tabs, tp, n_ticks, algo=0 if algo == "QUEUE_ACTUATED" else 1)
+    moved = 0
+    prev = None
+    for t in range(n_ticks):
+        sim.step(1)
+        ora.run(1)
+        got, want = sim.state_host(), ora.state()
+        for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"):
+            assert np.array_equal(got[k], want[k]), (t, k)
+        if prev is not None:
+            moved += int(((got["pos"] != prev) & (prev >= 0)).sum())
+        prev = got["pos"]
+    assert moved > nveh   # traffic actually flows
+    assert sim.counters()["fixed_point_iterations"] >= n_ticks

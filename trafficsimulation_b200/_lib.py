@@ -18,7 +18,7 @@ SYMBOLS = [
     "tsim_version", "tsim_last_error", "tsim_build_line_table", "tsim_workspace_bytes",
     "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_layout_carve", "tsim_layout_zones",
     "tsim_layout_dead_ends", "tsim_layout_upgrade_r2", "tsim_layout_entrances", "tsim_layout_fix_dirs",
-    "tsim_layout_lights", "tsim_maps",
+    "tsim_layout_lights", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_label_mask",
 ]
 
 
@@ -48,6 +48,25 @@ class LightLinks(C.Structure):
     _fields_ = [("n_lights", C.c_void_p), ("light_cell", C.c_void_p), ("ctrl_off", C.c_void_p),
                 ("ctrl_cell", C.c_void_p), ("inc_off", C.c_void_p), ("inc_cell", C.c_void_p),
                 ("cap_lights", C.c_int32), ("cap_ctrl", C.c_int32), ("cap_inc", C.c_int32)]
+
+
+class LightTables(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("n_lights", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
+        "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl")]
+
+
+class TickTapes(C.Structure):
+    _fields_ = [("n_ticks", C.c_int32), ("n_vehicles", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "spawn_first", "origin", "target", "speed", "malfunction", "rank", "ev_first", "ev_vehicle", "ev_off", "ev_cells", "rain_map")]
+
+
+class TickState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "occupancy", "stop_map", "stuck_map", "claim", "stopw",
+        "pos", "path_len", "steps", "stranded", "path_off", "stuck_ticks",
+        "alive", "base_speed", "cur_speed", "max_steps", "early", "is_stuck", "prev_valid", "malfunction", "direction", "moved",
+        "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "g_plan", "scalars")]
 
 
 _lib = None

@@ -231,3 +231,11 @@ extern "C" tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes 
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
+
+extern "C" tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask, int32_t *labels, int32_t *blobs, int32_t cap,
+                                       int32_t *n_blobs, void *workspace, size_t ws_bytes, void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if (!mask || !labels || !blobs || !n_blobs || cap < 1) { set_error("tsim_label_mask: bad arguments"); return TSIM_ERR_CONFIG; }
+    return label_type(cfg, mask, labels, 1, blobs, cap, n_blobs, workspace, ws_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,371 @@
+// k_tick.cu -- the per-tick vehicle cellular automaton with traffic-light gating, as ONE persistent
+// cooperative kernel that advances any number of ticks per launch.
+//
+// Replaces (reference): CityModel.step city_model.py:1831-1860; VehicleAgent.step_decide / step
+// agents/vehicles/vehicle_base.py:616-685 with _tick_stranded :552-565, _check_malfunction :608-610,
+// _compute_speed :94-112, _scan_ahead_for_obstacles :422-452, _determine_max_steps :719-731,
+// _execute_movement :733-753, _move_to :521-532, tick_stuck :687-693, on_target_reached :755-775;
+// CityModel.move_vehicle / remove_vehicle / place_vehicle city_model.py:1897-1963;
+// IntersectionLightGroup.step intersection_light_group.py:396-423 (run_queue_actuated :463-494,
+// run_fixed_time :427-441, _execute_phase_change :348-384) and CellAgent.set_light_stop/go cell.py:241-251.
+//
+// Deterministic conflict resolution.  The reference moves vehicles one after another in activation
+// order; every cell a vehicle plans to enter was free in the tick-start snapshot, so it can only be
+// blocked by the FINAL cell of a vehicle with a lower rank.  That is a triangular system: vehicle v's
+// step count depends only on lower-ranked vehicles.  It is solved by Jacobi iteration over a per-cell
+// claim word (atomicMin of the rank of the vehicles that currently end there); each sweep fixes at least
+// the lowest-ranked undecided vehicle of every dependency chain, the fixed point is unique and equals
+// the sequential result.  Chains are as long as the platoons that move bumper to bumper (a few cars).
+//
+// Phases of one tick (grid.sync between them):
+//   0 scatter this tick's route events (replayed A* results) into the vehicle SoA
+//   1 phase A for every live vehicle (tick-start snapshot)  +  light groups decide and stage stop_map writes
+//   2 staged stop_map writes are committed (last writer in activation order wins)
+//   3 claim fixed point   4 clears   5 sets / arrivals / stuck counters   6-8 tape-driven spawner
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tsim {
+
+constexpr int MIN_GREEN = 5, MAX_GREEN = 30, GAP_TICKS = 3, GREEN_DURATION = 20;   // config.py:354-359
+constexpr int AWARENESS = 10, MALFUNCTION_TICKS = 400, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2;   // config.py:279,321,306,263
+constexpr int NO_CLAIM = 0x7fffffff;
+enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 };
+
+struct TickArgs {
+    int W, H, n_ticks, algo;
+    tsim_light_tables lt;
+    tsim_tick_tapes tp;
+    tsim_tick_state st;
+};
+
+template <class F>
+__device__ __forceinline__ void for_light_cells(const tsim_light_tables &lt, const int32_t *off, const int32_t *lights, int g, F f) {
+    for (int k = off[g]; k < off[g + 1]; k++) {
+        const int l = lights[k];
+        for (int q = lt.tl_off[l]; q < lt.tl_off[l + 1]; q++) f(lt.tl_cells[q]);
+    }
+}
+
+// light group: controller + decision; stop_map writes are staged in `stopw` (atomicMax, priority =
+// group index, then order inside the group) so that concurrent groups reproduce the sequential result
+__device__ void group_decide(const TickArgs &a, int g) {
+    const tsim_light_tables &lt = a.lt;
+    const tsim_tick_state &s = a.st;
+    int cur = s.g_cur[g], pend = s.g_pend[g];
+    if (pend < 0) {
+        if (a.algo == 0) {   // run_queue_actuated :463-494
+            const int qt = ++s.g_qt[g];
+            int ns_q = 0, ew_q = 0;
+            for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += s.occupancy[lt.g_nsin[k]];
+            for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += s.occupancy[lt.g_ewin[k]];
+            const int cur_q = cur == 0 ? ns_q : ew_q, opp_q = cur == 0 ? ew_q : ns_q;
+            if (qt == 1) { s.g_last[g] = cur_q; s.g_gap[g] = 0; }
+            if (cur_q > s.g_last[g]) { s.g_last[g] = cur_q; s.g_gap[g] = 0; } else s.g_gap[g]++;
+            if (qt >= MIN_GREEN && (s.g_gap[g] >= GAP_TICKS || qt >= MAX_GREEN || (opp_q > cur_q && cur_q == 0))) {
+                const int next = 1 - cur;
+                if (next != cur && next != pend) pend = next;   // apply_phase :386-393
+                s.g_qt[g] = 0;
+            }
+        } else {             // run_fixed_time :427-441
+            const int ft = ++s.g_ft_timer[g];
+            if (ft == 1) { const int ph = s.g_ft_phase[g]; if (ph != cur && ph != pend) pend = ph; }
+            if (ft >= GREEN_DURATION) { s.g_ft_phase[g] = 1 - s.g_ft_phase[g]; s.g_ft_timer[g] = 0; }
+        }
+    }
+    int plan = 0;
+    if (pend >= 0) {         // _execute_phase_change :348-384
+        bool occupied = false;
+        for (int k = lt.g_cl_off[g]; k < lt.g_cl_off[g + 1]; k++) occupied |= s.occupancy[lt.g_cl[k]] != 0;
+        const int base = (g + 1) * 4;
+        if (occupied) {
+            plan = 1;
+            for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); });
+        } else {
+            plan = 2 + pend;
+            const bool ns_go = pend == 0;
+            for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); });
+            for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); });
+            cur = pend; pend = -1;
+        }
+    }
+    s.g_cur[g] = cur; s.g_pend[g] = pend; s.g_plan[g] = plan;
+}
+
+__device__ void group_apply(const TickArgs &a, int g) {
+    const tsim_light_tables &lt = a.lt;
+    const tsim_tick_state &s = a.st;
+    const int plan = s.g_plan[g];
+    if (plan == 0) return;
+    auto commit = [&](int c) {
+        const int w = *((volatile int32_t *)(s.stopw + c));
+        if ((w >> 2) == g + 1) { s.stop_map[c] = (uint8_t)(w & 1); s.stopw[c] = 0; }
+    };
+    if (plan == 1) {
+        for_light_cells(lt, lt.g_all_off, lt.g_all, g, commit);
+    } else {
+        for_light_cells(lt, lt.g_ns_off, lt.g_ns, g, commit);
+        for_light_cells(lt, lt.g_ew_off, lt.g_ew, g, commit);
+    }
+}
+
+// phase A of one vehicle: vehicle_base.py:616-663 on the tick-start snapshot
+__device__ void vehicle_decide(const TickArgs &a, int v, int t) {
+    const tsim_tick_state &s = a.st;
+    const tsim_tick_tapes &tp = a.tp;
+    const size_t tv = (size_t)t * tp.n_vehicles + v;
+    s.early[v] = 0;
+    s.moved[v] = -1;
+    s.max_steps[v] = 0;
+    if (s.malfunction[v]) {   // _tick_stranded :552-565
+        if (--s.stranded[v] <= 0) { s.malfunction[v] = 0; s.stranded[v] = 0; }
+        if (s.malfunction[v]) { s.base_speed[v] = 0; s.cur_speed[v] = 0; s.early[v] = 1; return; }
+    }
+    if (tp.malfunction[tv]) {   // _check_malfunction :608-610
+        s.malfunction[v] = 1; s.stranded[v] = MALFUNCTION_TICKS; s.base_speed[v] = 0; s.cur_speed[v] = 0; s.early[v] = 1;
+        return;
+    }
+    const int pos = s.pos[v];
+    if (s.stop_map[pos] == 1) { s.base_speed[v] = 0; s.cur_speed[v] = 0; s.early[v] = 1; return; }   // :639-643
+    int base = s.base_speed[v];
+    if (base == 0) { base = tp.speed[tv]; s.base_speed[v] = (int8_t)base; }   // :94-112
+    int sp = base;
+    if (tp.rain_map && tp.rain_map[pos] == 1) sp = max(1, sp - RAIN_REDUCTION);
+    s.cur_speed[v] = (int8_t)sp;
+    // _scan_ahead_for_obstacles :422-452 and _determine_max_steps :719-731
+    const int len = s.path_len[v];
+    const int32_t *path = tp.ev_cells + s.path_off[v];
+    int ms = min(sp, len);
+    const int look = min(len, AWARENESS);
+    for (int i = 0; i < look && i < ms; i++) {   // cells at or beyond `ms` cannot lower it any more
+        const int c = path[i];
+        if (s.stop_map[c] == 1 || s.occupancy[c] == 1) { ms = i; break; }
+    }
+    s.max_steps[v] = (int8_t)ms;
+    if (ms <= 0) {
+        s.base_speed[v] = 0;
+        if (pos == tp.target[v]) s.scalars[S_ERR] = 30;   // tape contract: a live vehicle is never at its target in phase A
+        s.early[v] = 1;
+    }
+}
+
+// how far does v get, given the current claims?  (_execute_movement :733-753)
+__device__ __forceinline__ int vehicle_eval(const TickArgs &a, int v, int rank) {
+    const tsim_tick_state &s = a.st;
+    const int m = s.max_steps[v];
+    const int32_t *path = a.tp.ev_cells + s.path_off[v];
+    int k = 0;
+    for (int j = 1; j <= m; j++) {
+        const int c = path[j - 1];
+        if (__ldcg(s.claim + c) < rank) break;                 // a lower-ranked vehicle ends here
+        if (s.stop_map[c] == 1 && j != m) break;               // a stop cell may only be entered on the last step
+        k = j;
+    }
+    return k;
+}
+
+__global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const tsim_tick_state &s = a.st;
+    const tsim_tick_tapes &tp = a.tp;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int nv = tp.n_vehicles, ng = a.lt.n_groups;
+    for (int it = 0; it < a.n_ticks; it++) {
+        const int t = *((volatile int32_t *)(s.scalars + S_TICK));
+        if (t >= tp.n_ticks) { if (tid == 0) s.scalars[S_ERR] = 31; break; }
+        // ---- 0: replay this tick's planned routes
+        for (int e = tp.ev_first[t] + tid; e < tp.ev_first[t + 1]; e += nth) {
+            const int v = tp.ev_vehicle[e];
+            s.path_off[v] = tp.ev_off[e];
+            s.path_len[v] = (int32_t)(tp.ev_off[e + 1] - tp.ev_off[e]);
+        }
+        grid.sync();
+        // ---- 1: phase A + light-group decisions
+        int live = 0;
+        for (int v = tid; v < nv; v += nth)
+            if (s.alive[v]) { vehicle_decide(a, v, t); live++; }
+        live = __reduce_add_sync(0xffffffffu, live);
+        if ((threadIdx.x & 31) == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
+        for (int g = tid; g < ng; g += nth) group_decide(a, g);
+        grid.sync();
+        // ---- 2: commit the staged stop_map writes
+        for (int g = tid; g < ng; g += nth) group_apply(a, g);
+        grid.sync();
+        // ---- 3: claim fixed point
+        const int32_t *rank = tp.rank + (size_t)t * nv;
+        for (int iter = 0;; iter++) {
+            int32_t *flag = s.scalars + (iter & 1 ? S_FLAG1 : S_FLAG0);
+            bool ch = false;
+            for (int v = tid; v < nv; v += nth) {
+                if (!s.alive[v] || s.early[v]) continue;
+                const int k = vehicle_eval(a, v, rank[v]);
+                if (k != s.moved[v]) { s.moved[v] = (int8_t)k; ch = true; }
+            }
+            if (__any_sync(0xffffffffu, ch) && (threadIdx.x & 31) == 0) *flag = 1;
+            grid.sync();
+            const int any = *((volatile int32_t *)flag);
+            if (tid == 0) { s.scalars[iter & 1 ? S_FLAG0 : S_FLAG1] = 0; s.scalars[S_ITERS]++; }
+            if (!any) break;
+            if (iter > 100000) { if (tid == 0) s.scalars[S_ERR] = 32; break; }
+            for (int v = tid; v < nv; v += nth) {      // drop every claim ...
+                if (!s.alive[v] || s.early[v]) continue;
+                const int32_t *path = tp.ev_cells + s.path_off[v];
+                for (int j = 0; j < s.max_steps[v]; j++) s.claim[path[j]] = NO_CLAIM;
+            }
+            grid.sync();
+            for (int v = tid; v < nv; v += nth) {      // ... and claim the current final cells again
+                if (!s.alive[v] || s.early[v]) continue;
+                const int k = s.moved[v];
+                if (k < 1) continue;
+                const int c = tp.ev_cells[s.path_off[v] + k - 1];
+                if (c != tp.target[v]) atomicMin(s.claim + c, rank[v]);   // an arriving vehicle is removed at once
+            }
+            grid.sync();
+        }
+        if (tid == 0) { s.scalars[S_FLAG0] = 0; s.scalars[S_FLAG1] = 0; }
+        // ---- 4: clears (cells left or passed through; claims)
+        for (int v = tid; v < nv; v += nth) {
+            if (!s.alive[v] || s.early[v]) continue;
+            const int32_t *path = tp.ev_cells + s.path_off[v];
+            const int k = s.moved[v], m = s.max_steps[v];
+            for (int j = 0; j < m; j++) s.claim[path[j]] = NO_CLAIM;
+            if (k >= 1) {
+                const int pos = s.pos[v];
+                s.occupancy[pos] = 0; s.stuck_map[pos] = 0;            // move_vehicle city_model.py:1952,1957
+                for (int j = 0; j + 1 < k; j++) s.stuck_map[path[j]] = 0;
+                if (path[k - 1] == tp.target[v]) s.stuck_map[path[k - 1]] = 0;   // arrives: remove_vehicle clears its cell again
+            }
+        }
+        grid.sync();
+        // ---- 5: sets, bookkeeping, arrivals
+        for (int v = tid; v < nv; v += nth) {
+            if (!s.alive[v]) continue;
+            int pos = s.pos[v];
+            const int target = tp.target[v];
+            if (!s.early[v]) {
+                const int k = s.moved[v];
+                if (k >= 1) {
+                    const int32_t *path = tp.ev_cells + s.path_off[v];
+                    const int fin = path[k - 1], prev = k >= 2 ? path[k - 2] : pos;
+                    if (fin != target) {
+                        s.occupancy[fin] = 1;
+                        s.stuck_map[fin] = (k == 1 && s.is_stuck[v]) ? 1 : 0;   // move_vehicle :1956-1958, before _move_to resets is_stuck
+                    }
+                    const int d = fin - prev;                                    // compute_direction numba_utilities.py:14-28
+                    s.direction[v] = (int8_t)(d == a.W ? DN : d == 1 ? DE : d == -a.W ? DS : d == -1 ? DW : s.direction[v]);
+                    if (s.stuck_ticks[v] > 0) { s.is_stuck[v] = 0; s.stuck_ticks[v] = 0; }   // _move_to :528-532
+                    s.steps[v] += k;
+                    s.path_off[v] += k; s.path_len[v] -= k;
+                    s.pos[v] = pos = fin;
+                }
+                s.prev_valid[v] = 1;   // step() :677
+            } else {
+                s.early[v] = 0;        // :679-680 tick_stuck :687-693
+                if (s.prev_valid[v] && s.stop_map[pos] != 1) {
+                    const int st = ++s.stuck_ticks[v];
+                    if (st > STUCK_THRESHOLD && !s.is_stuck[v]) s.is_stuck[v] = 1;
+                }
+                if (pos == target) { s.occupancy[pos] = 0; s.stuck_map[pos] = 0; }
+            }
+            if (pos == target) s.alive[v] = 0;   // on_target_reached :755-775 -> remove_vehicle city_model.py:1920-1929
+        }
+        grid.sync();
+        // ---- 6-8: spawner (attempts of this tick, lowest attempt index wins a free cell)
+        const int k0 = tp.spawn_first[t], k1 = tp.spawn_first[t + 1];
+        for (int k = k0 + tid; k < k1; k += nth)
+            if (s.occupancy[tp.origin[k]] == 0) atomicMin(s.claim + tp.origin[k], k);
+        grid.sync();
+        for (int k = k0 + tid; k < k1; k += nth) {
+            const int o = tp.origin[k];
+            if (__ldcg(s.claim + o) != k) continue;
+            s.alive[k] = 1; s.pos[k] = o;
+            s.base_speed[k] = 0; s.cur_speed[k] = 0; s.max_steps[k] = 0; s.early[k] = 0; s.is_stuck[k] = 0; s.prev_valid[k] = 0;
+            s.malfunction[k] = 0; s.direction[k] = -1; s.stuck_ticks[k] = 0; s.stranded[k] = 0; s.steps[k] = 0; s.moved[k] = 0;
+            s.occupancy[o] = 1; s.stuck_map[o] = 0;   // place_vehicle city_model.py:1904-1907
+        }
+        grid.sync();
+        for (int k = k0 + tid; k < k1; k += nth) s.claim[tp.origin[k]] = NO_CLAIM;
+        if (tid == 0) s.scalars[S_TICK] = t + 1;
+        grid.sync();
+    }
+}
+
+__global__ void fill_i32_kernel(long long n, int32_t *p, int32_t v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace tsim
+
+using namespace tsim;
+
+static tsim_status check_tick_args(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st) {
+    tsim_status s = check_cfg(cfg);
+    if (s != TSIM_OK) return s;
+    if (!lt || !tp || !st) { set_error("tick: NULL argument struct"); return TSIM_ERR_CONFIG; }
+    if (tp->n_vehicles < 0 || tp->n_ticks < 1 || lt->n_groups < 0) { set_error("tick: bad sizes"); return TSIM_ERR_CONFIG; }
+    if (!st->occupancy || !st->stop_map || !st->stuck_map || !st->claim || !st->stopw || !st->scalars) { set_error("tick: NULL map / scratch plane"); return TSIM_ERR_CONFIG; }
+    if (tp->n_vehicles > 0 && (!st->pos || !st->path_off || !st->path_len || !st->alive || !st->moved || !tp->origin || !tp->target || !tp->speed ||
+                               !tp->malfunction || !tp->rank || !tp->spawn_first || !tp->ev_first)) {
+        set_error("tick: NULL vehicle array / tape");
+        return TSIM_ERR_CONFIG;
+    }
+    if (cfg->halo != 0 || cfg->rows != cfg->height) { set_error("tick: sharded windows are handled by the host-side shard driver"); return TSIM_ERR_UNSUPPORTED; }
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st,
+                                      void *stream) {
+    tsim_status r = check_tick_args(cfg, lt, tp, st);
+    if (r != TSIM_OK) return r;
+    cudaStream_t cs = (cudaStream_t)stream;
+    const size_t n = (size_t)cfg->width * cfg->height, nv = (size_t)tp->n_vehicles, ng = (size_t)lt->n_groups;
+    TSIM_CUDA(cudaMemsetAsync(st->occupancy, 0, n, cs));
+    TSIM_CUDA(cudaMemsetAsync(st->stop_map, 0, n, cs));
+    TSIM_CUDA(cudaMemsetAsync(st->stuck_map, 0, n, cs));
+    TSIM_CUDA(cudaMemsetAsync(st->stopw, 0, n * 4, cs));
+    fill_i32_kernel<<<1184, 256, 0, cs>>>((long long)n, st->claim, NO_CLAIM);
+    TSIM_LAUNCH_CHECK();
+    if (nv) {
+        fill_i32_kernel<<<div_up((long long)nv, 256) < 1184 ? div_up((long long)nv, 256) : 1184, 256, 0, cs>>>((long long)nv, st->pos, -1);
+        TSIM_LAUNCH_CHECK();
+        TSIM_CUDA(cudaMemsetAsync(st->path_len, 0, nv * 4, cs));
+        TSIM_CUDA(cudaMemsetAsync(st->steps, 0, nv * 4, cs));
+        TSIM_CUDA(cudaMemsetAsync(st->stranded, 0, nv * 4, cs));
+        TSIM_CUDA(cudaMemsetAsync(st->path_off, 0, nv * 8, cs));
+        TSIM_CUDA(cudaMemsetAsync(st->stuck_ticks, 0, nv * 2, cs));
+        int8_t *bytes[] = {st->alive, st->base_speed, st->cur_speed, st->max_steps, st->early, st->is_stuck, st->prev_valid, st->malfunction, st->moved};
+        for (int8_t *b : bytes) TSIM_CUDA(cudaMemsetAsync(b, 0, nv, cs));
+        TSIM_CUDA(cudaMemsetAsync(st->direction, 0xff, nv, cs));
+    }
+    if (ng) {
+        fill_i32_kernel<<<div_up((long long)ng, 256) < 1184 ? div_up((long long)ng, 256) : 1184, 256, 0, cs>>>((long long)ng, st->g_cur, -1);
+        TSIM_LAUNCH_CHECK();
+        int32_t *zero[] = {st->g_pend, st->g_qt, st->g_gap, st->g_last, st->g_ft_phase, st->g_ft_timer, st->g_plan};   // g_pend = 0: apply_phase(0) in __init__ (:115-116)
+        for (int32_t *z : zero) TSIM_CUDA(cudaMemsetAsync(z, 0, ng * 4, cs));
+    }
+    TSIM_CUDA(cudaMemsetAsync(st->scalars, 0, 16 * 4, cs));
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st,
+                                     int32_t n_ticks, int32_t algo, void *stream) {
+    tsim_status r = check_tick_args(cfg, lt, tp, st);
+    if (r != TSIM_OK) return r;
+    if (n_ticks < 1 || (algo != 0 && algo != 1)) { set_error("tick: n_ticks %d algo %d", n_ticks, algo); return TSIM_ERR_CONFIG; }
+    TickArgs a{cfg->width, cfg->height, n_ticks, algo, *lt, *tp, *st};
+    int dev = 0, sms = 0, per_sm = 0;
+    TSIM_CUDA(cudaGetDevice(&dev));
+    TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick_kernel, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    // grid.sync cost grows with the CTA count: use just enough CTAs for the work, at most one full wave
+    long long want = ((long long)tp->n_vehicles + 255) / 256;
+    if (want < (lt->n_groups + 255) / 256) want = (lt->n_groups + 255) / 256;
+    long long cap = (long long)sms * (per_sm > 4 ? 4 : per_sm);
+    int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    void *args[] = {&a};
+    TSIM_CUDA(cudaLaunchCooperativeKernel((const void *)tick_kernel, dim3(grid), dim3(256), args, 0, (cudaStream_t)stream));
+    return TSIM_OK;
+}

@@ -1,0 +1,126 @@
+"""Intersection light groups from the layout's link tables (host side, O(#lights) table work).
+
+Mirrors, for the default QUEUE_ACTUATED / FIXED_TIME controllers, what the reference builds in
+``CityModel._create_intersection_light_groups`` (city_model.py:1587-1650) and
+``IntersectionLightGroup.__init__`` (intersection_light_group.py:33-116):
+
+* clusters = 4-connected components of ``_intersection_cells`` (the "ever intersection" aux bit),
+  labelled on the device (``tsim_label_mask``); a cluster whose four diagonal corner cells (one cell
+  outside its bounding box) hold no TrafficLight forms no group (:1623-1635);
+* canonical group order = cluster order = raster order of the cluster's first cell (the reference
+  iterates a Python set there; the tick tapes fix the activation order to this canonical one);
+* ``opposite_pairs`` (:243-279): a light joins the N-S (W-E) list if one of its controlled road cells
+  has, as its FIRST arrow that enters an Intersection cell of this very cluster, a N/S (E/W) arrow;
+* lane cells (:141-154): every assigned incoming lane cell (with multiplicity) goes to ``ns_in`` if it
+  has a N or S arrow and lies below the light, else to ``ew_in`` if it has an E or W arrow and lies left
+  of the light (the *_out lists are not read by the two controllers in scope).
+
+Everything is returned as CSR int32 arrays in the layout of ``tsim_light_tables`` (include/tsim.h).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+T_INTER, T_TL = 12, 15
+DX = np.array([0, 1, 0, -1], np.int64)   # N, E, S, W
+DY = np.array([1, 0, -1, 0], np.int64)
+
+
+def _csr_from_pairs(owner, value, n_owner):
+    """rows sorted by owner (stable) -> (off[n_owner+1], values)"""
+    order = np.argsort(owner, kind="stable")
+    off = np.zeros(n_owner + 1, np.int32)
+    np.add.at(off, owner + 1, 1)
+    return np.cumsum(off).astype(np.int32), value[order].astype(np.int32)
+
+
+def build_light_tables(W, H, cell_type, dirs, cluster_label, cluster_table, lights, ctrl_off, ctrl_cell, inc_off, inc_cell):
+    """All inputs are host numpy arrays; planes are [H, W]."""
+    T = cell_type.reshape(-1)
+    D = dirs.reshape(-1).astype(np.int64)
+    L = cluster_label.reshape(-1)
+    lights = np.asarray(lights, np.int64)
+    n_lights = len(lights)
+    ctrl_off = np.asarray(ctrl_off, np.int64); inc_off = np.asarray(inc_off, np.int64)
+    nC = len(cluster_table)
+    # light -> own cell followed by its controlled cells
+    tl_off = (ctrl_off[: n_lights + 1] + np.arange(n_lights + 1)).astype(np.int32)
+    tl_cells = np.zeros(int(tl_off[-1]) if n_lights else 0, np.int32)
+    if n_lights:
+        tl_cells[tl_off[:-1]] = lights
+        body = np.ones(len(tl_cells), bool); body[tl_off[:-1]] = False
+        tl_cells[body] = ctrl_cell[: int(ctrl_off[n_lights])]
+    # corner lights per cluster, corner order of the reference (:1623-1624)
+    minx, miny, maxx, maxy = (cluster_table[:, k].astype(np.int64) for k in range(4))
+    cl_ids, cl_lights = [], []
+    for cx, cy in ((minx - 1, miny - 1), (maxx + 1, miny - 1), (minx - 1, maxy + 1), (maxx + 1, maxy + 1)):
+        ok = (cx >= 0) & (cx < W) & (cy >= 0) & (cy < H)
+        cell = np.where(ok, cy * W + cx, 0)
+        ok &= T[cell] == T_TL
+        idx = np.searchsorted(lights, cell[ok])
+        cl_ids.append(np.flatnonzero(ok)); cl_lights.append(idx)
+    slot = np.concatenate([np.full(len(c), k) for k, c in enumerate(cl_ids)]) if nC else np.zeros(0, np.int64)
+    cl = np.concatenate(cl_ids) if nC else np.zeros(0, np.int64)
+    li = np.concatenate(cl_lights) if nC else np.zeros(0, np.int64)
+    order = np.lexsort((slot, cl))
+    cl, li = cl[order], li[order]
+    group_clusters = np.unique(cl)                      # cluster index (0-based) of every group, canonical order
+    ng = len(group_clusters)
+    gi = np.searchsorted(group_clusters, cl)            # group index of every (group, light) pair
+    g_all_off, g_all = _csr_from_pairs(gi, li, ng)
+    # opposite pairs: per (group, light, controlled cell) the first arrow entering this cluster's Intersection
+    n_ctrl = (ctrl_off[li + 1] - ctrl_off[li]).astype(np.int64)
+    pg = np.repeat(gi, n_ctrl); pl = np.repeat(li, n_ctrl)
+    start = np.repeat(ctrl_off[li], n_ctrl)
+    within = np.arange(len(pg)) - np.repeat(np.cumsum(n_ctrl) - n_ctrl, n_ctrl)
+    cb = ctrl_cell[start + within].astype(np.int64)
+    want_label = (group_clusters[pg] + 1)
+    axis = np.full(len(pg), -1, np.int64)
+    cbx, cby, cbd = cb % W, cb // W, D[cb]
+    for i in range(4):
+        has = ((cbd >> 12) & 7) > i
+        d = (cbd >> (4 + 2 * i)) & 3
+        nx, ny = cbx + DX[d], cby + DY[d]
+        inb = (nx >= 0) & (nx < W) & (ny >= 0) & (ny < H)
+        nc = np.where(inb, ny * W + nx, 0)
+        hit = has & inb & (T[nc] == T_INTER) & (L[nc] == want_label) & (axis < 0)
+        axis[hit] = (d[hit] & 1)                        # N,S -> 0 (vertical), E,W -> 1 (horizontal)
+    tabs = {}
+    for key, ax in (("g_ns", 0), ("g_ew", 1)):
+        sel = axis == ax
+        pairs = np.unique(np.stack([pg[sel], pl[sel]], 1), axis=0) if sel.any() else np.zeros((0, 2), np.int64)
+        tabs[key + "_off"], tabs[key] = _csr_from_pairs(pairs[:, 0], pairs[:, 1], ng)
+    # lane cells
+    n_inc = (inc_off[li + 1] - inc_off[li]).astype(np.int64)
+    qg = np.repeat(gi, n_inc); ql = np.repeat(li, n_inc)
+    start = np.repeat(inc_off[li], n_inc)
+    within = np.arange(len(qg)) - np.repeat(np.cumsum(n_inc) - n_inc, n_inc)
+    rb = inc_cell[start + within].astype(np.int64)
+    rbd = D[rb] & 0xF
+    tlx, tly = lights[ql] % W, lights[ql] // W
+    vertical = (rbd & 0b0101) != 0
+    horizontal = ~vertical & ((rbd & 0b1010) != 0)
+    ns_in = vertical & (rb // W < tly)
+    ew_in = horizontal & (rb % W < tlx)
+    tabs["g_nsin_off"], tabs["g_nsin"] = _csr_from_pairs(qg[ns_in], rb[ns_in], ng)
+    tabs["g_ewin_off"], tabs["g_ewin"] = _csr_from_pairs(qg[ew_in], rb[ew_in], ng)
+    # cluster cells of the groups
+    cells = np.flatnonzero(L > 0)
+    lab = L[cells].astype(np.int64) - 1
+    keep = np.isin(lab, group_clusters)
+    cells, lab = cells[keep], lab[keep]
+    tabs["g_cl_off"], tabs["g_cl"] = _csr_from_pairs(np.searchsorted(group_clusters, lab), cells, ng)
+    tabs.update(tl_off=tl_off, tl_cells=tl_cells, g_all_off=g_all_off, g_all=g_all, n_groups=ng, n_lights=n_lights,
+                group_clusters=group_clusters.astype(np.int32))
+    return tabs
+
+
+def groups_as_cell_lists(tabs, lights):
+    """Group tables as sorted cell-index arrays (the form the reference fixtures use), for parity checks."""
+    lights = np.asarray(lights)
+    out = []
+    for g in range(tabs["n_groups"]):
+        sl = lambda k: tabs[k][tabs[k + "_off"][g]:tabs[k + "_off"][g + 1]]
+        out.append(dict(cluster=np.sort(sl("g_cl")), lights=np.sort(lights[sl("g_all")]), ns_lights=np.sort(lights[sl("g_ns")]),
+                        ew_lights=np.sort(lights[sl("g_ew")]), ns_in=np.sort(sl("g_nsin")), ew_in=np.sort(sl("g_ewin"))))
+    return out

@@ -54,3 +54,64 @@ def synth_carve_tape(seed: int, blobs: np.ndarray, min_subblock_spacing: int = 5
     tape[:, 6] = np.where(carved, rng.random(n) < 0.5, 0)
     tape[:, 7] = carved
     return tape
+
+
+def synth_traffic(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarray, n_vehicles: int, n_ticks: int,
+                  route_len: int = 200, spawn_ticks: int = 1, malfunction_p: float = 0.0):
+    """Synthetic tick tapes for cities too large for the reference's A* (SURVEY.md §8d configs 4/5).
+
+    Vehicles are spawn attempts on distinct random road cells during the first `spawn_ticks` ticks; each
+    follows a pre-planned route that obeys the allowed directions of every cell it leaves (a random walk
+    over the arrow graph without immediate U-turns, cut at dead ends); the route's last cell is the target.
+    Returns the tape dict consumed by `GpuTraffic` (and by the tick oracle).
+    """
+    rng = np.random.default_rng(seed)
+    T = cell_type.reshape(-1)
+    D = dirs.reshape(-1).astype(np.int64)
+    road = np.flatnonzero((D & 0xF) != 0)
+    n_vehicles = min(n_vehicles, len(road))
+    origin = rng.choice(road, size=n_vehicles, replace=False).astype(np.int64)
+    step = np.array([W, 1, -W, -1], np.int64)
+    pos = origin.copy()
+    last_dir = np.full(n_vehicles, -1, np.int64)
+    alive = np.ones(n_vehicles, bool)
+    cols = []
+    for _ in range(route_len):
+        d = D[pos]
+        n = (d >> 12) & 7
+        pick = (rng.random(n_vehicles) * np.maximum(n, 1)).astype(np.int64)
+        choice = (d >> (4 + 2 * pick)) & 3
+        # avoid an immediate U-turn when another arrow exists
+        uturn = (choice == (last_dir + 2) % 4) & (last_dir >= 0) & (n > 1)
+        alt = (d >> (4 + 2 * ((pick + 1) % np.maximum(n, 1)))) & 3
+        choice = np.where(uturn, alt, choice)
+        x, y = pos % W, pos // W
+        nx, ny = x + np.array([0, 1, 0, -1])[choice], y + np.array([1, 0, -1, 0])[choice]
+        ok = alive & (n > 0) & (nx >= 0) & (nx < W) & (ny >= 0) & (ny < H)
+        nxt = np.where(ok, ny * W + nx, pos)
+        ok &= (D[nxt] & 0xF) != 0          # never step onto an arrow-less cell
+        nxt = np.where(ok, nxt, pos)
+        alive = ok
+        cols.append(np.where(ok, nxt, -1))
+        pos = nxt
+        last_dir = np.where(ok, choice, last_dir)
+    route = np.stack(cols, 1)                                  # [V, route_len], -1 padded at the tail
+    length = (route >= 0).sum(1)
+    keep = length >= 1
+    origin, route, length = origin[keep], route[keep], length[keep]
+    nv = len(origin)
+    target = route[np.arange(nv), length - 1]
+    ok = target != origin
+    origin, route, length, target = origin[ok], route[ok], length[ok], target[ok]
+    nv = len(origin)
+    spawn_tick = np.sort(rng.integers(0, spawn_ticks, size=nv)).astype(np.int32)
+    ev_off = np.zeros(nv + 1, np.int64)
+    ev_off[1:] = np.cumsum(length)
+    ev_cells = route[route >= 0].astype(np.int32)
+    return dict(
+        spawn_tick=spawn_tick, origin=origin.astype(np.int32), target=target.astype(np.int32),
+        speed=rng.integers(1, 6, size=(n_ticks, nv), dtype=np.uint8),
+        malfunction=(rng.random((n_ticks, nv)) < malfunction_p).astype(np.uint8) if malfunction_p > 0 else np.zeros((n_ticks, nv), np.uint8),
+        rank=np.argsort(rng.random((n_ticks, nv)), axis=1).astype(np.int32),
+        ev_tick=spawn_tick.copy(), ev_vehicle=np.arange(nv, dtype=np.int32), ev_off=ev_off, ev_cells=ev_cells,
+        rain_map=np.zeros((H, W), np.uint8))

@@ -1,0 +1,160 @@
+"""Host side of the tick: vehicle SoA, light-group tables and tapes on the device, advanced by
+``tsim_tick_run`` (one persistent cooperative CUDA kernel for any number of ticks).
+
+Mirrors the reference's ``CityModel.step()`` (city_model.py:1831-1860) for the parts in scope: the
+public maps ``occupancy_map``, ``stop_map``, ``stuck_map`` (city_model.py:109-115) live here as device
+planes; vehicles are rows of a structure of arrays indexed by spawn-attempt number.
+
+Tape contract: see DESIGN.md §5 and oracle/refharness/ticks.py (activation order = light groups, then
+vehicles by ``rank``, then the spawner; route events replay every path the planner produced).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .light_groups import build_light_tables
+
+_I8 = ("alive", "base_speed", "cur_speed", "max_steps", "early", "is_stuck", "prev_valid", "malfunction", "direction", "moved")
+_I32 = ("pos", "path_len", "steps", "stranded")
+_G32 = ("g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "g_plan")
+_LT = ("tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
+       "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl")
+
+
+def light_tables_from_layout(city):
+    """Build the light-group tables for a generated ``GpuCityLayout`` (device labelling + host table work)."""
+    W, H = city.width, city.height
+    dev = city.device
+    mask = ((city.aux & 0x40) != 0).to(torch.uint8)
+    labels = torch.empty(W * H, dtype=torch.int32, device=dev)
+    cap = max(1024, (W * H) // 16)
+    blobs = torch.zeros(cap * 6, dtype=torch.int32, device=dev)
+    n = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(city.lib.tsim_label_mask(C.byref(city.cfg), C.c_void_p(mask.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                        C.c_void_p(blobs.data_ptr()), cap, C.c_void_p(n.data_ptr()),
+                                        C.c_void_p(city.workspace.data_ptr()), C.c_size_t(city.workspace.numel()), city._stream))
+    nc = int(n.item())
+    if nc > cap:
+        raise _lib.TsimError(6, f"{nc} intersection clusters exceed the table capacity {cap}")
+    t = city._link_tensors
+    nl = int(city.flags[3].item())
+    planes = city.planes_host()
+    ctrl_off = t["ctrl_off"][: nl + 1].cpu().numpy()
+    inc_off = t["inc_off"][: nl + 1].cpu().numpy()
+    return build_light_tables(
+        W, H, planes["cell_type"], planes["dirs"], labels.cpu().numpy().reshape(H, W), blobs[: nc * 6].view(nc, 6).cpu().numpy(),
+        t["light_cell"][:nl].cpu().numpy(), ctrl_off, t["ctrl_cell"][: int(ctrl_off[-1]) if nl else 0].cpu().numpy(),
+        inc_off, t["inc_cell"][: int(inc_off[-1]) if nl else 0].cpu().numpy())
+
+
+class GpuTraffic:
+    """Vehicle CA + traffic lights on the device.
+
+    tapes: dict with spawn_tick (sorted), origin, target, speed [T,V] u8, malfunction [T,V] u8, rank [T,V] i32,
+    ev_tick (sorted), ev_vehicle, ev_off (int64, n_events+1), ev_cells, optional rain_map [H,W] u8.
+    """
+
+    def __init__(self, width, height, light_tables, tapes, n_ticks, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("trafficsimulation_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = dev = torch.device(device)
+        self.W, self.H, self.n_ticks = int(width), int(height), int(n_ticks)
+        self.algo = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1}[algo]
+        self.cfg = _lib.Cfg(self.W, self.H, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, self.H, 0)
+        n = self.W * self.H
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+        # ---- light tables
+        self.lt_t = {k: up(light_tables[k], np.int32) for k in _LT}
+        self.n_groups, self.n_lights = int(light_tables["n_groups"]), int(light_tables["n_lights"])
+        self.lt = _lib.LightTables(self.n_groups, self.n_lights, *[self.lt_t[k].data_ptr() for k in _LT])
+        # ---- tapes
+        spawn_tick = np.asarray(tapes["spawn_tick"], np.int32)
+        assert np.all(np.diff(spawn_tick) >= 0), "spawn attempts must be sorted by tick"
+        ev_tick = np.asarray(tapes["ev_tick"], np.int32)
+        assert np.all(np.diff(ev_tick) >= 0), "route events must be sorted by tick"
+        self.nv = nv = len(spawn_tick)
+        tt = {}
+        tt["spawn_first"] = up(np.searchsorted(spawn_tick, np.arange(n_ticks + 1)), np.int32)
+        tt["origin"], tt["target"] = up(tapes["origin"], np.int32), up(tapes["target"], np.int32)
+        tt["speed"], tt["malfunction"] = up(tapes["speed"], np.uint8), up(tapes["malfunction"], np.uint8)
+        tt["rank"] = up(tapes["rank"], np.int32)
+        assert tt["speed"].numel() >= n_ticks * nv and tt["rank"].numel() >= n_ticks * nv
+        tt["ev_first"] = up(np.searchsorted(ev_tick, np.arange(n_ticks + 1)), np.int32)
+        tt["ev_vehicle"] = up(tapes["ev_vehicle"], np.int32)
+        tt["ev_off"] = up(tapes["ev_off"], np.int64)
+        tt["ev_cells"] = up(np.append(np.asarray(tapes["ev_cells"], np.int32), 0), np.int32)
+        rain = tapes.get("rain_map") if rain_enabled else None
+        tt["rain_map"] = up(np.asarray(rain).reshape(-1), np.uint8) if rain is not None else None
+        self.tt = tt
+        self.tp = _lib.TickTapes(n_ticks, nv, *[(tt[k].data_ptr() if tt[k] is not None else 0) for k in
+                                                ("spawn_first", "origin", "target", "speed", "malfunction", "rank", "ev_first", "ev_vehicle",
+                                                 "ev_off", "ev_cells", "rain_map")])
+        # ---- state
+        z = lambda cnt, dt: torch.zeros(max(int(cnt), 1), dtype=dt, device=dev)
+        s = {"occupancy": z(n, torch.uint8), "stop_map": z(n, torch.uint8), "stuck_map": z(n, torch.uint8),
+             "claim": z(n, torch.int32), "stopw": z(n, torch.int32)}
+        for k in _I32:
+            s[k] = z(nv, torch.int32)
+        s["path_off"] = z(nv, torch.int64)
+        s["stuck_ticks"] = z(nv, torch.int16)
+        for k in _I8:
+            s[k] = z(nv, torch.int8)
+        for k in _G32:
+            s[k] = z(self.n_groups, torch.int32)
+        s["scalars"] = z(16, torch.int32)
+        self.s = s
+        order = [f[0] for f in _lib.TickState._fields_]
+        self.st = _lib.TickState(*[s[k].data_ptr() for k in order])
+        _lib.check(self.lib.tsim_tick_init(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), self._stream))
+
+    @property
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # public maps of the reference model (city_model.py:109-115)
+    @property
+    def occupancy_map(self):
+        return self.s["occupancy"].view(self.H, self.W)
+
+    @property
+    def stop_map(self):
+        return self.s["stop_map"].view(self.H, self.W)
+
+    @property
+    def stuck_map(self):
+        return self.s["stuck_map"].view(self.H, self.W)
+
+    def step(self, n=1, check=True):
+        """Advance n ticks (CityModel.step, city_model.py:1831)."""
+        _lib.check(self.lib.tsim_tick_run(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), int(n), self.algo, self._stream))
+        if check:
+            err = int(self.s["scalars"][1].item())
+            if err:
+                raise _lib.TsimError(4 if err == 30 else 6, f"tick kernel error flag {err}")
+
+    @property
+    def tick(self):
+        return int(self.s["scalars"][0].item())
+
+    def counters(self):
+        sc = self.s["scalars"].cpu().numpy()
+        return {"tick": int(sc[0]), "fixed_point_iterations": int(sc[2]), "vehicle_updates": int(sc[6:8].view(np.int64)[0])}
+
+    def state_host(self):
+        """Same dict as oracle.OracleTicks.state() / the reference fixtures."""
+        s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw")}
+        alive = s["alive"][: self.nv].astype(bool)
+        cut = lambda a: a[: self.nv]
+        flags = (cut(s["is_stuck"]).astype(np.uint8) & 1) | ((cut(s["malfunction"]).astype(np.uint8) & 1) << 1) | \
+                ((cut(s["direction"]) + 1).astype(np.uint8) << 2)
+        ng = self.n_groups
+        return dict(pos=np.where(alive, cut(s["pos"]), -1), base_speed=np.where(alive, cut(s["base_speed"]), 0),
+                    stuck_ticks=np.where(alive, cut(s["stuck_ticks"]), 0), vflags=np.where(alive, flags, 0).astype(np.uint8),
+                    occ=np.flatnonzero(s["occupancy"]).astype(np.int32), stop=np.flatnonzero(s["stop_map"]).astype(np.int32),
+                    stuckmap=np.flatnonzero(s["stuck_map"]).astype(np.int32),
+                    groups=np.stack([s["g_cur"][:ng], s["g_pend"][:ng], s["g_qt"][:ng], s["g_gap"][:ng], s["g_last"][:ng]], 1))
