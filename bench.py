@@ -115,6 +115,71 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons)}
 
 
+def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20):
+    """Second headline metric: agent-updates/s of the vehicle CA tick (BASELINE.json configs[3], in the
+    simultaneous-occupancy form SURVEY.md §8d defines: 100k vehicles live at once on a 2048^2 city)."""
+    import torch
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    seed = 2048
+    hb, vb, cap, tz, te = synth_inputs(size, seed)
+    city = GpuCityLayout(width=size, height=size, device=dev)
+    city.set_bands(hb, vb)
+    city.generate(tz, None, te)
+    tabs = light_tables_from_layout(city)
+    planes = city.planes_host()
+    tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], n_vehicles, n_ticks, route_len=400, spawn_ticks=1)
+    nv = len(tp["origin"])
+    sim = GpuTraffic(size, size, tabs, tp, n_ticks, device=dev)
+    sim.step(5)           # warm-up ticks (also spawns everybody)
+    torch.cuda.synchronize()
+    c0 = sim.counters()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    sim.step(n_ticks - 5, check=False)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    c1 = sim.counters()
+    updates = c1["vehicle_updates"] - c0["vehicle_updates"]
+    ticks = c1["tick"] - c0["tick"]
+    peak, peak_src = measured_peaks()
+    ups = updates / (ms * 1e-3)
+    # end to end: one launch per tick with a host read of the tick counters after every tick
+    sim2 = GpuTraffic(size, size, tabs, tp, n_ticks, device=dev)
+    sim2.step(5)
+    torch.cuda.synchronize()
+    e0 = sim2.counters()["vehicle_updates"]
+    t0 = time.perf_counter()
+    for _ in range(50):
+        sim2.step(1, check=True)
+    t1 = time.perf_counter()
+    e2e = (sim2.counters()["vehicle_updates"] - e0) / (t1 - t0)
+    # CPU port on the same tapes
+    ora = O.OracleTicks(size, size, tabs, tp, n_ticks)
+    ora.run(5)
+    live0 = int(ora.a["alive"].sum())
+    t0 = time.perf_counter()
+    upd_cpu = 0
+    for _ in range(cpu_ticks):
+        upd_cpu += int(ora.a["alive"].sum())
+        ora.run(1)
+    cpu_s = time.perf_counter() - t0
+    return {"metric": "agent-updates/sec (vehicle CA tick with traffic-light gating)", "value": ups, "unit": "agent-updates/s",
+            "config": {"workload": f"{size}x{size} city, {nv} vehicles spawned at tick 0, {ticks} timed ticks in one persistent launch",
+                       "groups": sim.n_groups, "lights": sim.n_lights},
+            "ms_per_tick": ms / ticks, "vehicle_updates": updates,
+            "fixed_point_iterations_per_tick": (c1["fixed_point_iterations"] - c0["fixed_point_iterations"]) / ticks,
+            "e2e": {"value": e2e, "unit": "agent-updates/s", "note": "one launch per tick + host read of the counters"},
+            "roofline": {"bound": "hbm", "alg_bytes_per_update": 84, "achieved": round(ups * 84 / 1e9, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(ups * 84 / 1e9 / peak, 5), "peak_source": peak_src,
+                         "note": "latency-bound at this size: ~10 grid-wide barriers per tick dominate (DESIGN.md §6)"},
+            "cpu_baseline": {"value": upd_cpu / cpu_s, "unit": "agent-updates/s", "cores": 1, "kind": "port",
+                             "sample": f"oracle/vehicle_oracle.c, same tapes, {cpu_ticks} ticks, {live0} live vehicles"}}
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -247,6 +312,7 @@ def ours(args):
         total_alg = sum(cells * p["alg_bytes_per_cell"] for p in passes.values())
         pipeline_gbs = total_alg * args.steps / (ms * 1e-3) / 1e9 / world
         cpu_val, cpu_s = cpu_arm(CPU_SAMPLE, 2, 1)
+        vehicle = vehicle_bench(dev)
         line = {
             "metric": "grid cells/sec, full layout generation (all passes)", "value": value, "unit": "cells/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -262,6 +328,7 @@ def ours(args):
             "pipeline": {"algorithmic_bytes_per_cell": total_alg / cells, "achieved_gbs": round(pipeline_gbs, 1),
                          "frac_of_measured_peak": round(pipeline_gbs / peak, 4)},
             "passes": passes,
+            "vehicle_step": vehicle,
             "cpu_baseline": {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                              "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"},
         }
