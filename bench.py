@@ -72,19 +72,33 @@ def cpu_arm(size, steps, warmup, seed=4096):
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms by a reader thread (the recipe's clocks
+    line, B200_PROFILING.md).  Rows are time-stamped; `summary(t0, t1)` uses the rows inside the window."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
     def __init__(self, index=0):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
         self.proc = None
+        self.thread = None
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7 and parts[0].isdigit():
+                self.rows.append((time.monotonic(), parts))
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}",
-                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.thread = threading.Thread(target=self._reader, daemon=True)
+            self.thread.start()
+            t_end = time.monotonic() + 5.0
+            while not self.rows and time.monotonic() < t_end and self.proc.poll() is None:
+                time.sleep(0.02)   # first sample in hand before the timed region starts
         except OSError:
             self.proc = None
         return self
@@ -94,25 +108,26 @@ class ClockSampler:
             return
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-            out, _ = self.proc.communicate()
-        for line in out.strip().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) >= 6 and parts[0].isdigit():
-                self.rows.append(parts)
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
-    def summary(self):
-        if not self.rows:
+    def summary(self, t0=None, t1=None):
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0 - 0.06) and (t1 is None or t <= t1 + 0.06)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows)
+        sm = sorted(int(r[0]) for r in rows)
         reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()) if any(r[2].replace(".", "", 1).isdigit() for r in rows) else None}
 
 
 def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20):
@@ -222,13 +237,14 @@ def ours(args):
     # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events on the launch stream
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    with ClockSampler(local) as clocks:
-        for a, b in ev:
-            flush.fill_(1)
-            a.record()
-            step()
-            b.record()
-        barrier()
+    clocks = ClockSampler(local).__enter__()   # keeps sampling through the per-pass breakdown below (same workload)
+    t_clk0 = time.monotonic()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     city._check_flag("timed steps")
     t_dev = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -266,6 +282,9 @@ def ours(args):
             gbs = cells * bpc / (t * 1e-3) / 1e9
             passes[n] = {"ms": round(t, 4), "cells_per_s": cells / (t * 1e-3), "alg_bytes_per_cell": bpc,
                          "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4)}
+
+    t_clk1 = time.monotonic()
+    clocks.__exit__(None, None, None)
 
     # ---- end to end through the public API with host buffers
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -321,7 +340,7 @@ def ours(args):
                        "cells_per_gpu": cells, "parallelism": "one city per GPU" if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write)", "seed": 4096,
                        "blocks": int(city.flags[2].item()), "lights": int(city.flags[3].item()), "dead_end_sweeps": city.sweeps()},
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(t_clk0, t_clk1),
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": sum(KERNELS_PER_STEP.values()) * args.steps,
             "roofline": roof,
