@@ -100,6 +100,8 @@ typedef struct tsim_lines {
 
 int         tsim_version(void);
 const char *tsim_last_error(void);
+/* number of CUDA kernels this library has launched in this process (benchmarks report it) */
+long long   tsim_launch_count(void);
 
 /* host-side helper: band list (n rows of start,end,type,dir) -> line table of `len` entries.
    Restates _find_band_covering (city_model.py:1269-1273: first band in list order wins) and the

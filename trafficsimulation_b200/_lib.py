@@ -15,7 +15,7 @@ STATUS_NAMES = {0: "TSIM_OK", 1: "TSIM_ERR_CONFIG", 2: "TSIM_ERR_WORKSPACE", 3: 
 
 # every symbol include/tsim.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "tsim_version", "tsim_last_error", "tsim_build_line_table", "tsim_workspace_bytes",
+    "tsim_version", "tsim_last_error", "tsim_launch_count", "tsim_build_line_table", "tsim_workspace_bytes",
     "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_layout_carve", "tsim_layout_zones",
     "tsim_layout_dead_ends", "tsim_layout_upgrade_r2", "tsim_layout_entrances", "tsim_layout_fix_dirs",
     "tsim_layout_lights", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_label_mask",
@@ -83,6 +83,7 @@ def load():
             "trafficsimulation_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     lib.tsim_last_error.restype = C.c_char_p
+    lib.tsim_launch_count.restype = C.c_longlong
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError if the library does not export a declared symbol
     _lib = lib

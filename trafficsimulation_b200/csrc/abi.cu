@@ -3,11 +3,15 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include "common.cuh"
 
 namespace tsim {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -45,6 +49,8 @@ using namespace tsim;
 extern "C" int tsim_version(void) { return TSIM_ABI_VERSION; }
 
 extern "C" const char *tsim_last_error(void) { return g_err; }
+
+extern "C" long long tsim_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // Restates _find_band_covering (city_model.py:1269-1273): the FIRST band in list order that covers
 // an index wins; plus membership in bands[0] / bands[-1], which _override_corner_lane_dirs (:519-527)

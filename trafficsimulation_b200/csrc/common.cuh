@@ -76,7 +76,17 @@ tsim_status check_cfg(const tsim_cfg *cfg);
         if (_s != TSIM_OK) return _s;                                \
     } while (0)
 
-#define TSIM_LAUNCH_CHECK() TSIM_CUDA(cudaGetLastError())
+void count_launch();   // every kernel launch of the library is counted (tsim_launch_count)
+#define TSIM_LAUNCH_CHECK()             \
+    do {                                \
+        ::tsim::count_launch();         \
+        TSIM_CUDA(cudaGetLastError());  \
+    } while (0)
+#define TSIM_COOP_LAUNCH(kernel, grid, block, args, stream)                                              \
+    do {                                                                                                 \
+        ::tsim::count_launch();                                                                          \
+        TSIM_CUDA(cudaLaunchCooperativeKernel((const void *)(kernel), (grid), (block), (args), 0, (stream))); \
+    } while (0)
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

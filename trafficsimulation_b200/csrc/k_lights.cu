@@ -7,16 +7,31 @@
 //     itself points into an Intersection) no longer has its original type -- `type_at_time`;
 //   * Sidewalk -> TrafficLight conversions never influence a test (both are accepted), so they commute;
 //   * `nb.light` of a cell that is converted later is reset by the conversion (a fresh CellAgent).
-// `leads_to` is a BFS over the whole directed arrow graph.  It is answered in O(1) for almost every
-// query from two reachability planes computed once: FW = reachable from a pivot intersection, BW = can
-// reach the pivot; BW(a) && FW(b) implies a -> pivot -> b.  The remaining queries have a source that
-// cannot reach the pivot (a sink region, e.g. highway exit lanes) or a target the pivot cannot reach (a
-// source region); their forward / backward closures are tiny and are searched exactly, with a bounded
-// visited list that raises TSIM_ERR_CAPACITY rather than guessing.
 //
-// Kernel sequence (all on the caller's stream):
-//   pivot -> reach (cooperative, tile wavefront) -> mark ControlledRoad candidates -> mark lights ->
-//   compact lights (scan) -> count links -> scan -> fill links + has-light bits -> apply types.
+// Everything except the first kernel works on BIT-PLANES (64 cells per 64-bit word, 1/8 B per cell):
+//   1. bits    : one streaming read of T and D (3 B/cell) -> arrow planes N/E/S/W, Intersection plane,
+//                road-without-intersection plane; picks the pivot intersection;
+//   2. cr      : ControlledRoad candidates = R & (arrow planes & shifted Intersection plane): pure word
+//                logic; popcount -> scan -> compact list of the (~2.5 % of all) candidate cells;
+//   3. reach   : `leads_to` is a BFS over the whole directed arrow graph.  It is answered in O(1) from
+//                two reachability planes, FW = reachable from the pivot, BW = can reach the pivot
+//                (BW(a) && FW(b) implies a -> pivot -> b).  The planes are the fixed point of alternating
+//                LINE closures: a row sweep closes every row under its E/W arrows (64 cells per
+//                Kogge-Stone fill, carries across the words of a row resolved like an adder's carry chain
+//                from two warp ballots), a column sweep closes every column under its N/S arrows (64
+//                columns per word in parallel, rows chunked over the threads of a CTA with a
+//                generate/propagate scan).  A path with k turns is covered after k sweeps, and a grid
+//                city needs a handful; the loop runs until a whole alternation changes nothing, so the
+//                result is the exact closure whatever the number of turns.  Queries whose source cannot
+//                reach the pivot or whose target the pivot cannot reach (sink / source regions such as
+//                highway exit lanes) are searched exactly with a bounded visited list that raises
+//                TSIM_ERR_CAPACITY rather than guessing;
+//   4. eval    : ONE thread per candidate evaluates the reference's per-road logic once and keeps the
+//                result as a 64-bit record (light cells as 5-bit offsets, reverse-scan lengths per
+//                direction); lights are marked in a bit-plane with atomicOr;
+//   5. lights in ascending cell order = popcount scan of that plane; CSR link tables by
+//      count -> scan -> fill from the records; type / aux updates are written for the candidate and
+//      light cells only (sparse), never as a full-plane sweep.
 #include <cooperative_groups.h>
 #include "scan.cuh"
 
@@ -24,72 +39,147 @@ namespace cg = cooperative_groups;
 
 namespace tsim {
 
-constexpr int F_CR = 1, F_TL = 2;   // flag plane bits
+typedef unsigned long long u64;
+
 constexpr int BFS_CAP = 160;        // visited cells of an exact fallback search
+constexpr int MAX_TL_RANGE = 30;    // reverse-scan lengths are kept in 5 bits
+
+struct Bits {
+    u64 *aN, *aE, *aS, *aW;   // arrow planes
+    u64 *I, *R;               // Intersection / road-like-without-intersection
+    u64 *fw, *bw;             // reachable from the pivot / reaches the pivot
+    u64 *cr, *tl;             // ControlledRoad candidates / TrafficLight cells
+    int wp;                   // words per row
+};
 
 struct LightsCtx {
     int W, H, tl_range, cap_lights;
     const uint8_t *T; const uint16_t *D;
-    const unsigned long long *fw, *bw; int wp;   // reach bit-planes: FW = reachable from the pivot, BW = reaches it
-    const uint8_t *F;   // F_CR / F_TL
+    Bits b;
     int32_t *err;
     __device__ __forceinline__ bool has(int x, int y) const { return x >= 0 && x < W && y >= 0 && y < H; }
     __device__ __forceinline__ int at(int x, int y) const { return y * W + x; }
+    __device__ __forceinline__ bool bit(const u64 *pl, int x, int y) const { return (pl[(size_t)y * b.wp + (x >> 6)] >> (x & 63)) & 1ull; }
 };
 
-// ---------------------------------------------------------------- pivot
-__global__ void __launch_bounds__(256) pivot_kernel(long long n, long long mid, const uint8_t *__restrict__ T, const uint16_t *__restrict__ D, int32_t *piv /* [2] */) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (T[i] == T_INTER && D[i] != 0) {
-        if (i >= mid) atomicMin(piv + 0, (int)i);
-        atomicMin(piv + 1, (int)i);
+// ---------------------------------------------------------------- 1. bit-planes from T and D
+__global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const uint8_t *__restrict__ T, const uint16_t *__restrict__ D, Bits bp,
+                                                          long long mid, int32_t *piv /* [0] first >= mid, [1] first */) {
+    const int spr = bp.wp * 4;   // 16-cell strips per row (a quad of lanes = one word)
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    const long long y_ll = g / spr;
+    const int s = (int)(g % spr), x0 = s * 16;
+    const bool row_ok = y_ll < H;
+    const int y = (int)y_ll;
+    uint32_t mN = 0, mE = 0, mS = 0, mW = 0, mI = 0, mR = 0;
+    int p_all = 0x7fffffff, p_mid = 0x7fffffff;
+    if (row_ok && x0 < W) {
+        const size_t base = (size_t)y * W + x0;
+        uint32_t tw[4], dw[8];
+        if ((W & 15) == 0) {
+            const uint4 tq = __ldg(reinterpret_cast<const uint4 *>(T + base));
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(D + base)), d1 = __ldg(reinterpret_cast<const uint4 *>(D + base + 8));
+            tw[0] = tq.x; tw[1] = tq.y; tw[2] = tq.z; tw[3] = tq.w;
+            dw[0] = d0.x; dw[1] = d0.y; dw[2] = d0.z; dw[3] = d0.w; dw[4] = d1.x; dw[5] = d1.y; dw[6] = d1.z; dw[7] = d1.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) tw[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) dw[k] = 0;
+            for (int k = 0; k < 16 && x0 + k < W; k++) {
+                tw[k >> 2] |= (uint32_t)T[base + k] << (8 * (k & 3));
+                dw[k >> 1] |= (uint32_t)D[base + k] << (16 * (k & 1));
+            }
+            for (int k = W - x0; k < 16; k++) if (k >= 0) tw[k >> 2] |= (uint32_t)T_WALL << (8 * (k & 3));
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int t = (tw[k >> 2] >> (8 * (k & 3))) & 0xff;
+            const uint32_t d = (dw[k >> 1] >> (16 * (k & 1))) & 0xffff;
+            mN |= ((d >> DN) & 1u) << k; mE |= ((d >> DE) & 1u) << k; mS |= ((d >> DS) & 1u) << k; mW |= ((d >> DW) & 1u) << k;
+            mI |= (uint32_t)(t == T_INTER) << k;
+            mR |= ((SET_ROAD_NO_INT >> (t & 31)) & 1u) << k;
+            if (t == T_INTER && d != 0) {
+                const long long i = (long long)base + k;
+                if (i < p_all) p_all = (int)i;
+                if (i >= mid && i < p_mid) p_mid = (int)i;
+            }
+        }
+    }
+    // quad of lanes -> one 64-bit word per plane
+    auto pack = [&](uint32_t m) {
+        u64 v = (u64)m << (16 * q);
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        return v;
+    };
+    const u64 wN = pack(mN), wE = pack(mE), wS = pack(mS), wW = pack(mW), wI = pack(mI), wR = pack(mR);
+    if (row_ok && q == 0) {
+        const size_t o = (size_t)y * bp.wp + (s >> 2);
+        bp.aN[o] = wN; bp.aE[o] = wE; bp.aS[o] = wS; bp.aW[o] = wW; bp.I[o] = wI; bp.R[o] = wR;
+        bp.fw[o] = 0ull; bp.bw[o] = 0ull; bp.tl[o] = 0ull;
+    }
+    p_all = __reduce_min_sync(0xffffffffu, p_all);
+    p_mid = __reduce_min_sync(0xffffffffu, p_mid);
+    if (lane == 0) {
+        if (p_all != 0x7fffffff) atomicMin(piv + 1, p_all);
+        if (p_mid != 0x7fffffff) atomicMin(piv + 0, p_mid);
     }
 }
 
 __global__ void init_pivot_kernel(int32_t *piv) { piv[0] = 0x7fffffff; piv[1] = 0x7fffffff; }
 
-// ---------------------------------------------------------------- arrow bit-planes
-// One bit per cell and direction: AR[d][y][wx] bit (x & 63) = cell (x,y) has arrow d.  64 cells per
-// word turn a lane march of 64 steps into a 6-step Kogge-Stone fill, and 32 rows per warp turn a
-// column march into a 5-step shuffle scan.
-struct BitPlanes {
-    unsigned long long *ar[4];   // arrows N,E,S,W
-    unsigned long long *fw, *bw; // reachable from the pivot / reaches the pivot
-    int wp;                      // words per row
-};
-
-__global__ void __launch_bounds__(256) pack_arrows_kernel(int W, int H, const uint16_t *__restrict__ D, BitPlanes bp) {
-    // one warp per 64 cells of a row: two ballots per direction
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= (long long)bp.wp * H) return;
-    const int y = (int)(gw / bp.wp), wx = (int)(gw % bp.wp), x0 = wx * 64;
-    const uint32_t d0 = (x0 + lane < W) ? D[(size_t)y * W + x0 + lane] : 0u;
-    const uint32_t d1 = (x0 + 32 + lane < W) ? D[(size_t)y * W + x0 + 32 + lane] : 0u;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const unsigned long long lo = __ballot_sync(0xffffffffu, (d0 >> k) & 1u), hi = __ballot_sync(0xffffffffu, (d1 >> k) & 1u);
-        if (lane == 0) bp.ar[k][(size_t)y * bp.wp + wx] = lo | (hi << 32);
-    }
-    if (lane == 0) { bp.fw[(size_t)y * bp.wp + wx] = 0ull; bp.bw[(size_t)y * bp.wp + wx] = 0ull; }
+// ---------------------------------------------------------------- 2. ControlledRoad candidates (:1439-1452)
+__global__ void __launch_bounds__(256) cr_bits_kernel(int H, Bits bp, int32_t *__restrict__ cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nw = (long long)bp.wp * H;
+    if (i >= nw) return;
+    const int y = (int)(i / bp.wp), wx = (int)(i % bp.wp);
+    const u64 I0 = bp.I[i];
+    const u64 Iup = y + 1 < H ? bp.I[i + bp.wp] : 0ull, Idn = y > 0 ? bp.I[i - bp.wp] : 0ull;
+    const u64 Inx = wx + 1 < bp.wp ? bp.I[i + 1] : 0ull, Ipv = wx > 0 ? bp.I[i - 1] : 0ull;
+    const u64 cr = bp.R[i] & ((bp.aN[i] & Iup) | (bp.aS[i] & Idn) | (bp.aE[i] & ((I0 >> 1) | (Inx << 63))) | (bp.aW[i] & ((I0 << 1) | (Ipv >> 63))));
+    bp.cr[i] = cr;
+    cnt[i] = __popcll(cr);
 }
 
-constexpr int RTH = 32;   // rows per warp tile (tile = 64 x 32 cells)
+__global__ void __launch_bounds__(256) bit_count_kernel(long long nw, const u64 *__restrict__ plane, int32_t *__restrict__ cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) cnt[i] = __popcll(plane[i]);
+}
 
-__global__ void reach_seed_kernel(int W, int32_t *piv, BitPlanes bp, uint8_t *dirty) {
+// cells of the set bits, ascending cell index; prefix = exclusive scan of the word popcounts
+__global__ void __launch_bounds__(256) bit_list_kernel(int W, int H, int wp, const u64 *__restrict__ plane, const int32_t *__restrict__ prefix,
+                                                       int32_t *__restrict__ list, int cap, int32_t *err, int err_code) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)wp * H) return;
+    u64 m = plane[i];
+    if (!m) return;
+    const int y = (int)(i / wp), wx = (int)(i % wp);
+    int k = prefix[i];
+    const int base = y * W + wx * 64;
+    while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (k < cap) list[k] = base + b; else *err = err_code;
+        k++;
+    }
+}
+
+// ---------------------------------------------------------------- 3. reach
+__global__ void reach_seed_kernel(int W, int32_t *piv, Bits bp) {
     int p = piv[0] != 0x7fffffff ? piv[0] : piv[1];
     if (p == 0x7fffffff) { piv[0] = -1; return; }   // no intersection at all: every query goes to the exact search
     piv[0] = p;
     const int x = p % W, y = p / W;
     bp.fw[(size_t)y * bp.wp + (x >> 6)] = 1ull << (x & 63);
     bp.bw[(size_t)y * bp.wp + (x >> 6)] = 1ull << (x & 63);
-    dirty[(y / RTH) * bp.wp + (x >> 6)] = 1;
 }
 
-// occluded fills inside a 64-bit row word (Kogge-Stone): `p` = cells that may be entered from the
-// lower (up-fill) / higher (down-fill) neighbour
-__device__ __forceinline__ unsigned long long fill_up(unsigned long long f, unsigned long long p) {
+// occluded fills inside a 64-bit word (Kogge-Stone): `p` = cells that may be entered from the lower
+// (up-fill) / higher (down-fill) neighbour
+__device__ __forceinline__ u64 fill_up(u64 f, u64 p) {
     f |= p & (f << 1);  p &= p << 1;
     f |= p & (f << 2);  p &= p << 2;
     f |= p & (f << 4);  p &= p << 4;
@@ -98,7 +188,7 @@ __device__ __forceinline__ unsigned long long fill_up(unsigned long long f, unsi
     f |= p & (f << 32);
     return f;
 }
-__device__ __forceinline__ unsigned long long fill_down(unsigned long long f, unsigned long long p) {
+__device__ __forceinline__ u64 fill_down(u64 f, u64 p) {
     f |= p & (f >> 1);  p &= p >> 1;
     f |= p & (f >> 2);  p &= p >> 2;
     f |= p & (f >> 4);  p &= p >> 4;
@@ -107,113 +197,149 @@ __device__ __forceinline__ unsigned long long fill_down(unsigned long long f, un
     f |= p & (f >> 32);
     return f;
 }
-// the same fills across the 32 rows of a warp tile (lane = row): row y may be entered from row y-1
-// (lane_up) / y+1 (lane_down) at the columns of `p`
-__device__ __forceinline__ unsigned long long lanes_up(unsigned long long f, unsigned long long p, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long ff = __shfl_up_sync(0xffffffffu, f, d), pp = __shfl_up_sync(0xffffffffu, p, d);
-        if (lane < d) { ff = 0ull; pp = 0ull; }
-        f |= p & ff;
-        p &= pp;
-    }
-    return f;
-}
-__device__ __forceinline__ unsigned long long lanes_down(unsigned long long f, unsigned long long p, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long ff = __shfl_down_sync(0xffffffffu, f, d), pp = __shfl_down_sync(0xffffffffu, p, d);
-        if (lane + d > 31) { ff = 0ull; pp = 0ull; }
-        f |= p & ff;
-        p &= pp;
-    }
-    return f;
+
+// carry chain over the 32 words of a warp: c[0] = cin, c[i+1] = g[i] | (p[i] & c[i]) -- exactly a binary
+// adder's carries, so one 64-bit add resolves all of them.  Returns the carry INTO every lane.
+__device__ __forceinline__ uint32_t carry_chain(uint32_t g, uint32_t p, uint32_t cin, uint32_t &cout) {
+    const u64 X = (u64)(g | (p & ~g)), Y = (u64)g;
+    const u64 C = (X + Y + cin) ^ X ^ Y;
+    cout = (uint32_t)(C >> 32) & 1u;
+    return (uint32_t)C;
 }
 
-// ---------------------------------------------------------------- reach (FW/BW from the pivot)
-// Persistent cooperative kernel, one WARP per 64x32 tile.  A tile is (re)processed only when a
-// neighbouring tile changed one of its border cells; inside a tile the closure is a handful of
-// bit-parallel fills instead of a cell-by-cell march.
-__global__ void __launch_bounds__(256) reach_kernel(int W, int H, BitPlanes bp, uint8_t *dirty0, uint8_t *dirty1, int32_t *counter /* [0..1] wave counters, [2] waves */) {
+// closes row y under its E / W arrows (both planes); returns true if anything changed
+__device__ bool row_closure(const Bits &bp, int y, int lane) {
+    const int wp = bp.wp;
+    const size_t base = (size_t)y * wp;
+    bool any = false;
+    for (int round = 0; round < 64; round++) {
+        bool ch = false;
+        // ---- left -> right: FW along E arrows, BW against W arrows
+        uint32_t cf = 0, cb = 0;
+        for (int c0 = 0; c0 < wp; c0 += 32) {
+            const int w = c0 + lane;
+            const bool in = w < wp;
+            const u64 aE = in ? bp.aE[base + w] : 0ull, aW = in ? bp.aW[base + w] : 0ull;
+            const u64 f = in ? __ldcg(bp.fw + base + w) : 0ull, b = in ? __ldcg(bp.bw + base + w) : 0ull;
+            u64 f1 = fill_up(f, aE << 1), b1 = fill_up(b, aW);
+            const uint32_t gf = __ballot_sync(0xffffffffu, (f1 & aE) >> 63), pf = __ballot_sync(0xffffffffu, aE == ~0ull);
+            const uint32_t gb = __ballot_sync(0xffffffffu, b1 >> 63), pb = __ballot_sync(0xffffffffu, aW == ~0ull);
+            uint32_t nf, nb;
+            const uint32_t inf = carry_chain(gf, pf, cf, nf), inb = carry_chain(gb, pb, cb, nb);
+            cf = nf; cb = nb;
+            if ((inf >> lane) & 1u) f1 = fill_up(f1 | 1ull, aE << 1);
+            if ((inb >> lane) & 1u) b1 = fill_up(b1 | (aW & 1ull), aW);
+            if (in && f1 != f) { bp.fw[base + w] = f1; ch = true; }
+            if (in && b1 != b) { bp.bw[base + w] = b1; ch = true; }
+        }
+        // ---- right -> left: FW along W arrows, BW against E arrows
+        cf = 0; cb = 0;
+        for (int c0 = ((wp - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+            const int w = c0 + lane;
+            const bool in = w < wp;
+            const u64 aE = in ? bp.aE[base + w] : 0ull, aW = in ? bp.aW[base + w] : 0ull;
+            const u64 f = in ? __ldcg(bp.fw + base + w) : 0ull, b = in ? __ldcg(bp.bw + base + w) : 0ull;
+            u64 f1 = fill_down(f, aW >> 1), b1 = fill_down(b, aE);
+            const uint32_t gf = __brev(__ballot_sync(0xffffffffu, f1 & aW & 1ull)), pf = __brev(__ballot_sync(0xffffffffu, aW == ~0ull));
+            const uint32_t gb = __brev(__ballot_sync(0xffffffffu, b1 & 1ull)), pb = __brev(__ballot_sync(0xffffffffu, aE == ~0ull));
+            uint32_t nf, nb;
+            const uint32_t inf = __brev(carry_chain(gf, pf, cf, nf)), inb = __brev(carry_chain(gb, pb, cb, nb));
+            cf = nf; cb = nb;
+            if ((inf >> lane) & 1u) f1 = fill_down(f1 | (1ull << 63), aW >> 1);
+            if ((inb >> lane) & 1u) b1 = fill_down(b1 | (aE & (1ull << 63)), aE);
+            if (in && f1 != f) { bp.fw[base + w] = f1; ch = true; }
+            if (in && b1 != b) { bp.bw[base + w] = b1; ch = true; }
+        }
+        if (!__any_sync(0xffffffffu, ch)) break;
+        any = true;
+    }
+    return any;
+}
+
+// Column closure of ONE word column (64 grid columns in parallel) by one CTA: thread k owns rows
+// [k*R, k*R+R).  UP = true: FW along N arrows and BW against S arrows (carries move up);
+// UP = false: FW along S arrows and BW against N arrows (carries move down).
+struct GP { u64 gf, pf, gb, pb; };
+
+template <bool UP>
+__device__ bool col_closure(const Bits &bp, int H, int wx, GP *s_gp) {
+    const int nt = blockDim.x, k = threadIdx.x;
+    const int R = (H + nt - 1) / nt;
+    const int ylo = min(H, k * R), yhi = min(H, ylo + R);
+    const int wp = bp.wp;
+    const u64 *arrF = UP ? bp.aN : bp.aS;   // FW: leaving row y along this arrow
+    const u64 *arrB = UP ? bp.aS : bp.aN;   // BW: row y inherits from the previous row of the sweep if it has this arrow
+    // phase 1: generate / propagate of my chunk
+    u64 cf = 0, pf = ~0ull, cb = 0, pb = ~0ull;
+    for (int j = 0; j < yhi - ylo; j++) {
+        const int y = UP ? ylo + j : yhi - 1 - j;
+        const size_t o = (size_t)y * wp + wx;
+        const u64 aF = arrF[o], aB = arrB[o];
+        const u64 f = __ldcg(bp.fw + o) | cf, b = __ldcg(bp.bw + o) | (aB & cb);
+        cf = f & aF; pf &= aF;
+        cb = b; pb &= aB;
+    }
+    // inclusive scan over the chunks in sweep order: out[k] = g[k] | (p[k] & out[k-1])
+    const int pos = UP ? k : nt - 1 - k;   // position in sweep order
+    GP me{cf, pf, cb, pb};
+    s_gp[pos] = me;
+    __syncthreads();
+    for (int d = 1; d < nt; d <<= 1) {
+        GP lo;
+        const bool take = pos >= d;
+        if (take) lo = s_gp[pos - d];
+        __syncthreads();
+        if (take) {
+            me.gf |= me.pf & lo.gf; me.pf &= lo.pf;
+            me.gb |= me.pb & lo.gb; me.pb &= lo.pb;
+            s_gp[pos] = me;
+        }
+        __syncthreads();
+    }
+    cf = pos > 0 ? s_gp[pos - 1].gf : 0ull;
+    cb = pos > 0 ? s_gp[pos - 1].gb : 0ull;
+    __syncthreads();
+    // phase 2: apply with the carry-in
+    bool ch = false;
+    for (int j = 0; j < yhi - ylo; j++) {
+        const int y = UP ? ylo + j : yhi - 1 - j;
+        const size_t o = (size_t)y * wp + wx;
+        const u64 aF = arrF[o], aB = arrB[o];
+        const u64 f0 = __ldcg(bp.fw + o), b0 = __ldcg(bp.bw + o);
+        const u64 f = f0 | cf, b = b0 | (aB & cb);
+        if (f != f0) { bp.fw[o] = f; ch = true; }
+        if (b != b0) { bp.bw[o] = b; ch = true; }
+        cf = f & aF;
+        cb = b;
+    }
+    return ch;
+}
+
+// Persistent cooperative kernel: alternate row and column closures until an alternation changes nothing.
+__global__ void __launch_bounds__(256) reach_kernel(int H, Bits bp, int32_t *flags /* [0..2] change flags, [3] alternations */, int32_t *err) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ GP s_gp[256];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int wp = bp.wp, tilesy = (H + RTH - 1) / RTH, ntiles = wp * tilesy;
-    int wave = 0;
-    for (;; wave++) {
-        uint8_t *cur = (wave & 1) ? dirty1 : dirty0, *nxt = (wave & 1) ? dirty0 : dirty1;
-        int32_t *cnt = counter + (wave & 1);
-        for (int tile = warp; tile < ntiles; tile += nwarps) {
-            int flag = 0;
-            if (lane == 0) { flag = __ldcg(cur + tile); if (flag) cur[tile] = 0; }
-            flag = __shfl_sync(0xffffffffu, flag, 0);
-            if (!flag) continue;
-            const int wx = tile % wp, ty = tile / wp, y = ty * RTH + lane;
-            const bool in = y < H;
-            const size_t o = (size_t)y * wp + wx;
-            auto ld = [&](const unsigned long long *pl, bool ok, size_t off) { return ok ? __ldcg(pl + off) : 0ull; };
-            const unsigned long long aN = ld(bp.ar[DN], in, o), aE = ld(bp.ar[DE], in, o), aS = ld(bp.ar[DS], in, o), aW = ld(bp.ar[DW], in, o);
-            unsigned long long f = ld(bp.fw, in, o), b = ld(bp.bw, in, o);
-            const unsigned long long f0 = f, b0 = b;
-            // halos: west / east words of my row, rows just below / above the tile
-            const bool hw = in && wx > 0, he = in && wx + 1 < wp;
-            const unsigned long long fW = ld(bp.fw, hw, o - 1), bW = ld(bp.bw, hw, o - 1), eW = ld(bp.ar[DE], hw, o - 1);
-            const unsigned long long fE = ld(bp.fw, he, o + 1), bE = ld(bp.bw, he, o + 1), wE = ld(bp.ar[DW], he, o + 1);
-            const int yb = ty * RTH - 1, yt = ty * RTH + RTH;
-            const bool hb = yb >= 0, ht = yt < H;
-            const size_t ob = (size_t)yb * wp + wx, ot = (size_t)yt * wp + wx;
-            // (loaded by every lane: same address, one transaction)
-            const unsigned long long fB = ld(bp.fw, hb, ob), bB = ld(bp.bw, hb, ob), nB = ld(bp.ar[DN], hb, ob);
-            const unsigned long long fT = ld(bp.fw, ht, ot), bT = ld(bp.bw, ht, ot), sT = ld(bp.ar[DS], ht, ot);
-            // inflow that never changes while the tile iterates
-            const unsigned long long f_in = (((fW & eW) >> 63) & 1ull) | ((((fE & wE) & 1ull)) << 63) |
-                                            (lane == 0 ? (fB & nB) : 0ull) | (lane == 31 ? (fT & sT) : 0ull);
-            const unsigned long long b_in = (aW & ((bW >> 63) & 1ull)) | (aE & ((bE & 1ull) << 63)) |
-                                            (lane == 0 ? (aS & bB) : 0ull) | (lane == 31 ? (aN & bT) : 0ull);
-            f |= f_in; b |= b_in;
-            for (int it = 0; it < 4096; it++) {
-                const unsigned long long pf = f, pb = b;
-                // FW moves WITH the arrows
-                f = fill_up(f, aE << 1);                 // east:  x entered from x-1 if (x-1) has E
-                f = fill_down(f, aW >> 1);               // west
-                {   // north: row y entered from y-1 where row y-1 has N
-                    unsigned long long pn = __shfl_up_sync(0xffffffffu, aN, 1); if (lane == 0) pn = 0ull;
-                    f = lanes_up(f, pn, lane);
-                    unsigned long long ps = __shfl_down_sync(0xffffffffu, aS, 1); if (lane == 31) ps = 0ull;
-                    f = lanes_down(f, ps, lane);
-                }
-                // BW moves AGAINST the arrows: a cell with arrow d inherits from its d-neighbour
-                b = fill_down(b, aE);                    // cell x takes from x+1 if x has E
-                b = fill_up(b, aW);                      // cell x takes from x-1 if x has W
-                b = lanes_down(b, aN, lane);             // row y takes from y+1 where row y has N
-                b = lanes_up(b, aS, lane);               // row y takes from y-1 where row y has S
-                if (!__any_sync(0xffffffffu, f != pf || b != pb)) break;
-            }
-            const bool chf = f != f0, chb = b != b0;
-            if (in && chf) bp.fw[o] = f;
-            if (in && chb) bp.bw[o] = b;
-            // wake the neighbours whose halo I changed
-            const unsigned long long ch = (f ^ f0) | (b ^ b0);
-            const bool wW = __any_sync(0xffffffffu, in && (ch & 1ull)) && wx > 0;
-            const bool wEe = __any_sync(0xffffffffu, in && (ch >> 63)) && wx + 1 < wp;
-            const bool wB = __shfl_sync(0xffffffffu, ch != 0ull, 0) && ty > 0;
-            const int last = min(RTH, H - ty * RTH) - 1;
-            const bool wT = __shfl_sync(0xffffffffu, ch != 0ull, last) && ty + 1 < tilesy;
-            if (lane == 0) {
-                int woke = 0;
-                if (wW) { nxt[tile - 1] = 1; woke = 1; }
-                if (wEe) { nxt[tile + 1] = 1; woke = 1; }
-                if (wB) { nxt[tile - wp] = 1; woke = 1; }
-                if (wT) { nxt[tile + wp] = 1; woke = 1; }
-                if (woke) atomicAdd(cnt, 1);
-            }
-        }
+    for (int it = 0;; it++) {
+        int32_t *flag = flags + it % 3;
+        bool ch = false;
+        for (int y = warp; y < H; y += nwarps) ch |= row_closure(bp, y, lane);
         __threadfence();
         grid.sync();
-        const int any = *((volatile int32_t *)cnt);
-        if (blockIdx.x == 0 && threadIdx.x == 0) { counter[(wave + 1) & 1] = 0; counter[2] = wave + 1; }
-        if (!any) break;
+        for (int wx = blockIdx.x; wx < bp.wp; wx += gridDim.x) {
+            ch |= col_closure<true>(bp, H, wx, s_gp);
+            __syncthreads();
+            ch |= col_closure<false>(bp, H, wx, s_gp);
+            __syncthreads();
+        }
+        if (__syncthreads_or(ch) && threadIdx.x == 0) *flag = 1;
+        __threadfence();
         grid.sync();
+        const int any = *((volatile int32_t *)flag);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { flags[(it + 2) % 3] = 0; flags[3] = it + 1; }
+        if (!any) break;
+        if (it > 100000) { if (blockIdx.x == 0 && threadIdx.x == 0) *err = 12; break; }
     }
 }
 
@@ -269,45 +395,31 @@ __device__ bool bfs_backward(const LightsCtx &L, int from, int to) {   // does `
 __device__ __forceinline__ bool leads_to(const LightsCtx &L, int a, int b) {
     if (a == b) return true;
     const int ax = a % L.W, ay = a / L.W, bx = b % L.W, by = b / L.W;
-    const bool a_bw = (L.bw[(size_t)ay * L.wp + (ax >> 6)] >> (ax & 63)) & 1ull;
-    const bool b_fw = (L.fw[(size_t)by * L.wp + (bx >> 6)] >> (bx & 63)) & 1ull;
+    const bool a_bw = L.bit(L.b.bw, ax, ay), b_fw = L.bit(L.b.fw, bx, by);
     if (a_bw && b_fw) return true;
     if (!a_bw) return bfs_forward(L, a, b);
     return bfs_backward(L, a, b);
 }
 
-// ---------------------------------------------------------------- per ControlledRoad evaluation
+// ---------------------------------------------------------------- 4. per ControlledRoad evaluation
 __device__ __forceinline__ bool before_cm(int sx, int sy, int cx, int cy) { return sx < cx || (sx == cx && sy < cy); }   // column-major order
 
 // cell type as the reference sees it when it visits (cx,cy)
 __device__ __forceinline__ int type_at_time(const LightsCtx &L, int sx, int sy, int cx, int cy) {
-    const int s = L.at(sx, sy);
-    if ((L.F[s] & F_CR) && before_cm(sx, sy, cx, cy)) return T_CR;
-    return L.T[s];
+    if (before_cm(sx, sy, cx, cy) && L.bit(L.b.cr, sx, sy)) return T_CR;
+    return L.T[L.at(sx, sy)];
 }
 
-// is (x,y) converted to ControlledRoad?  (:1439-1452)
-__device__ __forceinline__ bool is_controlled(int W, int H, const uint8_t *T, const uint16_t *D, int x, int y) {
-    const int i = y * W + x;
-    if (!in_set(SET_ROAD_NO_INT, T[i])) return false;
-    const uint32_t d = D[i];
-    for (int q = 0; q < dl_len(d); q++) {
-        const int k = dl_get(d, q), nx = x + dx_of(k), ny = y + dy_of(k);
-        if (nx >= 0 && nx < W && ny >= 0 && ny < H && T[ny * W + nx] == T_INTER) return true;
-    }
-    return false;
-}
-
-struct Eval {
-    int acc[8], nacc;    // Sidewalk cells that become / are this road's lights
-    int sc[12], nsc;     // reverse-scan cells (assigned incoming lane cells), in scan order
-};
-
-__device__ void lights_eval(const LightsCtx &L, int cx, int cy, Eval &e) {
+// Result record of one ControlledRoad: bits 0..39 up to 8 light cells as 5-bit offsets (dy+2)*5+(dx+2),
+// bits 40..59 reverse-scan length per entry of the ordered direction list (5 bits each), bits 60..63 the
+// number of light cells.
+__device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
     const int c = L.at(cx, cy);
     const int t = L.T[c];
     const uint32_t rd = L.D[c];
-    e.nacc = 0; e.nsc = 0;
+    u64 rec = 0;
+    int nacc = 0;
+    auto push = [&](int ax, int ay) { rec |= (u64)((ay - cy + 2) * 5 + (ax - cx + 2)) << (5 * nacc); nacc++; };
     int vx[4], vy[4], nv = 0;
     for (int r = 0; r < dl_len(rd); r++) {   // cells to the right of every arrow, de-duplicated (:1465-1474)
         const int k = right_of(dl_get(rd, r)), bx = cx + dx_of(k), by = cy + dy_of(k);
@@ -321,132 +433,152 @@ __device__ void lights_eval(const LightsCtx &L, int cx, int cy, Eval &e) {
         if (st == T_CR || st == t) {
             if (!(L.D[L.at(vx[u], vy[u])] & rd & 0xf)) continue;   // shares no arrow (:1483)
             const int fx = 2 * vx[u] - cx, fy = 2 * vy[u] - cy;
-            if (L.has(fx, fy) && L.T[L.at(fx, fy)] == T_SIDEWALK) e.acc[e.nacc++] = L.at(fx, fy);
+            if (L.has(fx, fy) && L.T[L.at(fx, fy)] == T_SIDEWALK) push(fx, fy);
         }
-        if (L.T[L.at(vx[u], vy[u])] == T_SIDEWALK) e.acc[e.nacc++] = L.at(vx[u], vy[u]);
+        if (L.T[L.at(vx[u], vy[u])] == T_SIDEWALK) push(vx[u], vy[u]);
     }
-    if (e.nacc == 0) return;
+    if (nacc == 0) return 0;
+    rec |= (u64)nacc << 60;
     int depth = 0;   // budget shared by all directions (:1528-1548)
     for (int i = 0; i < dl_len(rd); i++) {
         const int k = opp_of(dl_get(rd, i));
-        int bx = cx + dx_of(k), by = cy + dy_of(k);
+        int bx = cx + dx_of(k), by = cy + dy_of(k), cnt = 0;
         while (depth <= L.tl_range) {
             if (!L.has(bx, by)) break;
             if (type_at_time(L, bx, by, cx, cy) != t) break;
-            const int nb = L.at(bx, by);
-            if (!leads_to(L, nb, c)) break;
-            e.sc[e.nsc++] = nb;
+            if (!leads_to(L, L.at(bx, by), c)) break;
+            cnt++;
             bx += dx_of(k); by += dy_of(k); depth++;
         }
+        rec |= (u64)cnt << (40 + 5 * i);
     }
+    return rec;
 }
+
+__device__ __forceinline__ int rec_nacc(u64 r) { return (int)(r >> 60); }
+__device__ __forceinline__ int rec_acc(u64 r, int u, int c, int W) {
+    const int code = (int)(r >> (5 * u)) & 31;
+    return c + (code / 5 - 2) * W + (code % 5 - 2);
+}
+__device__ __forceinline__ int rec_cnt(u64 r, int i) { return (int)(r >> (40 + 5 * i)) & 31; }
+__device__ __forceinline__ int rec_nsc(u64 r) { return rec_cnt(r, 0) + rec_cnt(r, 1) + rec_cnt(r, 2) + rec_cnt(r, 3); }
 
 __device__ __forceinline__ void or_byte(uint8_t *p, uint32_t bits) {
     uint32_t *w = (uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
     atomicOr(w, bits << (8 * ((uintptr_t)p & 3)));
 }
 
-__global__ void __launch_bounds__(256) mark_cr_kernel(int W, int H, const uint8_t *__restrict__ T, const uint16_t *__restrict__ D, uint8_t *F) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)W * H) return;
-    uint8_t f = 0;
-    if (in_set(SET_ROAD_NO_INT, T[i]) && is_controlled(W, H, T, D, (int)(i % W), (int)(i / W))) f = F_CR;
-    F[i] = f;
+__global__ void __launch_bounds__(128) lights_eval_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
+                                                          u64 *__restrict__ rec) {
+    const int n = *n_cr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cr_cell[i];
+        const u64 r = lights_eval(L, c % L.W, c / L.W);
+        rec[i] = r;
+        for (int u = 0; u < rec_nacc(r); u++) {
+            const int a = rec_acc(r, u, c, L.W);
+            const int ax = a % L.W, ay = a / L.W;
+            atomicOr(L.b.tl + (size_t)ay * L.b.wp + (ax >> 6), 1ull << (ax & 63));
+        }
+    }
 }
 
-// mode 0: mark lights; 1: count links per light; 2: fill links and set has-light bits
-template <int MODE>
-__global__ void __launch_bounds__(128) lights_pass_kernel(LightsCtx L, uint8_t *F, uint8_t *A, const int32_t *__restrict__ lid,
-                                                          int32_t *ctrl_cnt, int32_t *inc_cnt, const int32_t *__restrict__ ctrl_off,
-                                                          const int32_t *__restrict__ inc_off, int32_t *ctrl_cell, int32_t *inc_cell,
-                                                          int cap_ctrl, int cap_inc) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)L.W * L.H) return;
-    if (!(L.F[i] & F_CR)) return;
-    Eval e;
-    lights_eval(L, (int)(i % L.W), (int)(i / L.W), e);
-    if (e.nacc == 0) return;
-    if (MODE == 0) {
-        for (int u = 0; u < e.nacc; u++) or_byte(F + e.acc[u], F_TL);
-    } else if (MODE == 1) {
-        for (int u = 0; u < e.nacc; u++) {
-            const int l = lid[e.acc[u]];
+// light index of a TrafficLight cell: lights are numbered in ascending cell order
+__device__ __forceinline__ int light_id(const LightsCtx &L, const int32_t *__restrict__ tl_prefix, int cell) {
+    const int x = cell % L.W, y = cell / L.W;
+    const size_t o = (size_t)y * L.b.wp + (x >> 6);
+    return tl_prefix[o] + __popcll(L.b.tl[o] & ((1ull << (x & 63)) - 1ull));
+}
+
+// 5a. count links per light
+__global__ void __launch_bounds__(128) lights_count_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
+                                                           const u64 *__restrict__ rec, const int32_t *__restrict__ tl_prefix,
+                                                           int32_t *ctrl_cnt, int32_t *inc_cnt) {
+    const int n = *n_cr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 r = rec[i];
+        const int na = rec_nacc(r);
+        if (!na) continue;
+        const int c = cr_cell[i], nsc = rec_nsc(r);
+        for (int u = 0; u < na; u++) {
+            const int l = light_id(L, tl_prefix, rec_acc(r, u, c, L.W));
             if (l >= L.cap_lights) continue;
             atomicAdd(ctrl_cnt + l, 1);
-            if (e.nsc) atomicAdd(inc_cnt + l, e.nsc);
+            if (nsc) atomicAdd(inc_cnt + l, nsc);
         }
-    } else {
-        for (int u = 0; u < e.nacc; u++) {
-            const int l = lid[e.acc[u]];
-            if (l >= L.cap_lights) continue;
-            const int pc = ctrl_off[l] + atomicAdd(ctrl_cnt + l, 1);
-            if (pc < cap_ctrl) ctrl_cell[pc] = (int32_t)i; else *L.err = 20;
-            if (e.nsc) {
-                const int pi = inc_off[l] + atomicAdd(inc_cnt + l, e.nsc);
-                for (int s = 0; s < e.nsc; s++) { if (pi + s < cap_inc) inc_cell[pi + s] = e.sc[s]; else *L.err = 21; }
+    }
+}
+
+// 5b. fill links, set has-light bits, convert the cell (place_cell(..., "ControlledRoad") keeps the
+// arrows and remembers the original type, :1455-1459)
+__global__ void __launch_bounds__(128) lights_fill_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
+                                                          const u64 *__restrict__ rec, const int32_t *__restrict__ tl_prefix, uint8_t *T, uint8_t *A,
+                                                          int32_t *B, int32_t *ctrl_cur, int32_t *inc_cur, const int32_t *__restrict__ ctrl_off,
+                                                          const int32_t *__restrict__ inc_off, int32_t *ctrl_cell, int32_t *inc_cell, int cap_ctrl,
+                                                          int cap_inc) {
+    const int n = *n_cr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 r = rec[i];
+        const int c = cr_cell[i];
+        const int na = rec_nacc(r);
+        const int t = T[c];
+        const uint32_t rd = L.D[c];
+        if (na) {
+            const int nsc = rec_nsc(r);
+            for (int u = 0; u < na; u++) {
+                const int l = light_id(L, tl_prefix, rec_acc(r, u, c, L.W));
+                if (l >= L.cap_lights) continue;
+                const int pc = ctrl_off[l] + atomicAdd(ctrl_cur + l, 1);
+                if (pc < cap_ctrl) ctrl_cell[pc] = c; else *L.err = 20;
+                if (nsc) {
+                    int pi = inc_off[l] + atomicAdd(inc_cur + l, nsc);
+                    for (int d = 0; d < dl_len(rd); d++) {
+                        const int k = opp_of(dl_get(rd, d)), step = dy_of(k) * L.W + dx_of(k);
+                        for (int s = 1; s <= rec_cnt(r, d); s++, pi++) { if (pi < cap_inc) inc_cell[pi] = c + s * step; else *L.err = 21; }
+                    }
+                }
+            }
+            // nb.light = tl (:1542); lost again if nb itself is converted later (a fresh CellAgent)
+            const int cx = c % L.W, cy = c / L.W;
+            for (int d = 0; d < dl_len(rd); d++) {
+                const int k = opp_of(dl_get(rd, d));
+                for (int s = 1; s <= rec_cnt(r, d); s++) {
+                    const int sx = cx + s * dx_of(k), sy = cy + s * dy_of(k);
+                    if (!L.bit(L.b.cr, sx, sy)) or_byte(A + L.at(sx, sy), AUX_LIGHT);
+                }
             }
         }
-        or_byte(A + i, AUX_LIGHT);                                   // controlled_road.light = tl (:1517)
-        for (int s = 0; s < e.nsc; s++)                              // nb.light = tl (:1542), lost again if nb is converted later
-            if (!(L.F[e.sc[s]] & F_CR)) or_byte(A + e.sc[s], AUX_LIGHT);
+        T[c] = T_CR;
+        A[c] = (uint8_t)((A[c] & (AUX_RING | AUX_EVER)) | (na ? AUX_LIGHT : 0) | t);   // controlled_road.light = tl (:1517)
+        if (t == T_BE) B[c] = 0;
     }
 }
 
-// lights in ascending cell order: count flags per tile / rank
-__global__ void __launch_bounds__(256) flag_count_kernel(long long n, const uint8_t *__restrict__ F, int bit, int32_t *tile_count) {
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    const long long base = (long long)blockIdx.x * SCAN_TILE;
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_TILE / 256; k++) {
-        const long long i = base + k * 256 + threadIdx.x;
-        if (i < n && (F[i] & bit)) c++;
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_count[blockIdx.x] = s_cnt;
-}
-
-__global__ void __launch_bounds__(256) flag_rank_kernel(long long n, const uint8_t *__restrict__ F, int bit, const int32_t *__restrict__ tile_off,
-                                                        int32_t *__restrict__ lid, int32_t *__restrict__ cells, int cap, int32_t *err) {
-    __shared__ int s_warp[8];
-    const long long base = (long long)blockIdx.x * SCAN_TILE;
-    int running = tile_off[blockIdx.x];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int k = 0; k < SCAN_TILE / 256; k++) {
-        const long long i = base + k * 256 + threadIdx.x;
-        const bool f = i < n && (F[i] & bit);
-        const uint32_t m = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) s_warp[w] = __popc(m);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < w) before += c; total += c; }
-        if (f) {
-            const int id = running + before + __popc(m & ((1u << lane) - 1u));
-            lid[i] = id;
-            if (id < cap) cells[id] = (int32_t)i; else *err = 22;
-        }
-        running += total;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(256) lights_apply_kernel(long long n, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B, const uint8_t *__restrict__ F) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// Sidewalk -> TrafficLight (:1506-1509)
+__global__ void __launch_bounds__(256) tl_apply_kernel(const int32_t *__restrict__ n_lights, const int32_t *__restrict__ light_cell, int cap,
+                                                       uint8_t *T, uint16_t *D, uint8_t *A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(*n_lights, cap);
     if (i >= n) return;
-    const uint8_t f = F[i];
-    if (f & F_CR) {   // place_cell(..., "ControlledRoad") keeps the arrows, remembers the original type (:1455-1459)
-        const int t = T[i];
-        T[i] = T_CR;
-        A[i] = (uint8_t)((A[i] & (AUX_RING | AUX_EVER | AUX_LIGHT)) | t);
-        if (t == T_BE) B[i] = 0;
-    } else if (f & F_TL) {   // :1506-1509
-        T[i] = T_TL; D[i] = 0; A[i] &= (AUX_RING | AUX_EVER);
-    }
+    const int c = light_cell[i];
+    T[c] = T_TL; D[c] = 0; A[c] &= (AUX_RING | AUX_EVER);
+}
+
+// canonical order inside every light's segments (the fill order above depends on atomics)
+__global__ void __launch_bounds__(256) links_sort_kernel(const int32_t *__restrict__ n_lights, int cap, const int32_t *__restrict__ ctrl_off,
+                                                         int32_t *ctrl_cell, const int32_t *__restrict__ inc_off, int32_t *inc_cell) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= min(*n_lights, cap)) return;
+    auto isort = [](int32_t *a, int n) {
+        for (int i = 1; i < n; i++) {
+            const int32_t v = a[i];
+            int j = i - 1;
+            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+            a[j + 1] = v;
+        }
+    };
+    isort(ctrl_cell + ctrl_off[l], ctrl_off[l + 1] - ctrl_off[l]);
+    isort(inc_cell + inc_off[l], inc_off[l + 1] - inc_off[l]);
 }
 
 __global__ void close_offsets_kernel(const int32_t *n_lights, int32_t *ctrl_off, int32_t *inc_off, const int32_t *totals, int cap_lights,
@@ -473,41 +605,48 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
         return TSIM_ERR_CONFIG;
     }
     if (cfg->forward_traffic_light_range) { set_error("forward_traffic_light_range is not implemented on the GPU path"); return TSIM_ERR_UNSUPPORTED; }
+    if (cfg->traffic_light_range < 0 || cfg->traffic_light_range > MAX_TL_RANGE) {
+        set_error("traffic_light_range %d outside 0..%d", cfg->traffic_light_range, MAX_TL_RANGE);
+        return TSIM_ERR_UNSUPPORTED;
+    }
     if (cfg->halo != 0 || cfg->rows != cfg->height) { set_error("tsim_layout_lights: run on the gathered grid"); return TSIM_ERR_UNSUPPORTED; }
     cudaStream_t cs = (cudaStream_t)stream;
     const int W = cfg->width, H = cfg->height;
     const long long n = (long long)W * H;
-    const int ntiles = div_up(n, SCAN_TILE);
-    const int rtiles = div_up(W, 64) * div_up(H, RTH);
+    const int wp = div_up(W, 64);
+    const long long nw = (long long)wp * H;
+    const int cap_cr = (int)(n / 4 + 1024);
     // workspace layout
     char *w = (char *)workspace;
     size_t o = 0;
     auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
-    int32_t *scal = (int32_t *)take(64 * 4);   // [0..1] pivot, [4..5] link totals, [8..9] wave counters, [10] waves
-    const int wp = div_up(W, 64);
-    BitPlanes bp;
-    for (int k = 0; k < 4; k++) bp.ar[k] = (unsigned long long *)take((size_t)wp * H * 8);
-    bp.fw = (unsigned long long *)take((size_t)wp * H * 8);
-    bp.bw = (unsigned long long *)take((size_t)wp * H * 8);
+    int32_t *scal = (int32_t *)take(64 * 4);   // [0..1] pivot, [4..5] link totals, [8..11] reach flags, [12] n_cr
+    Bits bp;
+    u64 **planes[] = {&bp.aN, &bp.aE, &bp.aS, &bp.aW, &bp.I, &bp.R, &bp.fw, &bp.bw, &bp.cr, &bp.tl};
+    for (u64 **pl : planes) *pl = (u64 *)take((size_t)nw * 8);
     bp.wp = wp;
-    uint8_t *F = (uint8_t *)take(n);
-    int32_t *lid = (int32_t *)take(n * 4);
-    int32_t *tile_cnt = (int32_t *)take((size_t)ntiles * 4);
-    uint8_t *dirty0 = (uint8_t *)take(rtiles), *dirty1 = (uint8_t *)take(rtiles);
-    int32_t *cnt_ctrl = (int32_t *)take((size_t)lk->cap_lights * 4), *cnt_inc = (int32_t *)take((size_t)lk->cap_lights * 4);
-    int32_t *scan_tmp = (int32_t *)take((size_t)(div_up(lk->cap_lights, SCAN_TILE) + 1) * 4);
+    int32_t *cr_prefix = (int32_t *)take((size_t)nw * 4), *tl_prefix = (int32_t *)take((size_t)nw * 4);
+    int32_t *scan_tmp = (int32_t *)take((size_t)(div_up(nw > lk->cap_lights ? nw : lk->cap_lights, SCAN_TILE) + 1) * 4);
+    int32_t *cr_cell = (int32_t *)take((size_t)cap_cr * 4);
+    u64 *rec = (u64 *)take((size_t)cap_cr * 8);
+    int32_t *cur_ctrl = (int32_t *)take((size_t)lk->cap_lights * 4), *cur_inc = (int32_t *)take((size_t)lk->cap_lights * 4);
     if (!workspace || o > ws_bytes) { set_error("tsim_layout_lights needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
+    int32_t *n_cr = scal + 12;
 
     TSIM_CUDA(cudaMemsetAsync(scal, 0, 64 * 4, cs));
     init_pivot_kernel<<<1, 1, 0, cs>>>(scal);
     TSIM_LAUNCH_CHECK();
-    TSIM_CUDA(cudaMemsetAsync(dirty0, 0, rtiles, cs));
-    TSIM_CUDA(cudaMemsetAsync(dirty1, 0, rtiles, cs));
-    pivot_kernel<<<div_up(n, 256), 256, 0, cs>>>(n, (long long)(H / 2) * W, p->cell_type, p->dirs, scal);
+    // 1. bit-planes + pivot
+    lights_bits_kernel<<<div_up(nw * 4, 256), 256, 0, cs>>>(W, H, p->cell_type, p->dirs, bp, (long long)(H / 2) * W, scal);
     TSIM_LAUNCH_CHECK();
-    pack_arrows_kernel<<<div_up((long long)wp * H * 32, 256), 256, 0, cs>>>(W, H, p->dirs, bp);
+    // 2. candidates -> compact list
+    cr_bits_kernel<<<div_up(nw, 256), 256, 0, cs>>>(H, bp, cr_prefix);
     TSIM_LAUNCH_CHECK();
-    reach_seed_kernel<<<1, 1, 0, cs>>>(W, scal, bp, dirty0);
+    if ((st = exclusive_scan_i32(cr_prefix, nw, scan_tmp, n_cr, cs)) != TSIM_OK) return st;
+    bit_list_kernel<<<div_up(nw, 256), 256, 0, cs>>>(W, H, wp, bp.cr, cr_prefix, cr_cell, cap_cr, err_flag, 23);
+    TSIM_LAUNCH_CHECK();
+    // 3. reach
+    reach_seed_kernel<<<1, 1, 0, cs>>>(W, scal, bp);
     TSIM_LAUNCH_CHECK();
     {
         int dev = 0, sms = 0, per_sm = 0;
@@ -515,41 +654,41 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
         TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reach_kernel, 256, 0));
         int grid = sms * (per_sm < 1 ? 1 : per_sm);
-        if (grid > div_up(rtiles, 8)) grid = div_up(rtiles, 8);
-        int Wv = W, Hv = H;
-        int32_t *counter = scal + 8;
-        void *args[] = {&Wv, &Hv, &bp, &dirty0, &dirty1, &counter};
-        TSIM_CUDA(cudaLaunchCooperativeKernel((const void *)reach_kernel, dim3(grid), dim3(256), args, 0, cs));
+        const int want = div_up(H, 8) > wp ? div_up(H, 8) : wp;   // 8 rows per CTA in the row sweep, one word column per CTA in the column sweep
+        if (grid > want) grid = want;
+        int Hv = H;
+        int32_t *flags = scal + 8;
+        void *args[] = {&Hv, &bp, &flags, &err_flag};
+        TSIM_COOP_LAUNCH(reach_kernel, dim3(grid), dim3(256), args, cs);
     }
-    mark_cr_kernel<<<div_up(n, 256), 256, 0, cs>>>(W, H, p->cell_type, p->dirs, F);
+    // 4. evaluate every candidate once (launch covers the capacity; threads beyond *n_cr exit)
+    const int list_grid = div_up(cap_cr, 128) < 148 * 16 ? div_up(cap_cr, 128) : 148 * 16;   // grid-stride over the compact list
+    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, p->cell_type, p->dirs, bp, err_flag};
+    lights_eval_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec);
     TSIM_LAUNCH_CHECK();
-    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, p->cell_type, p->dirs, bp.fw, bp.bw, wp, F, err_flag};
-    lights_pass_kernel<0><<<div_up(n, 128), 128, 0, cs>>>(L, F, p->aux, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0);
+    // 5. lights in ascending cell order
+    bit_count_kernel<<<div_up(nw, 256), 256, 0, cs>>>(nw, bp.tl, tl_prefix);
     TSIM_LAUNCH_CHECK();
-    // compact the lights in ascending cell order
-    flag_count_kernel<<<ntiles, 256, 0, cs>>>(n, F, F_TL, tile_cnt);
-    TSIM_LAUNCH_CHECK();
-    scan_tiles_kernel<<<1, 1024, 0, cs>>>(ntiles, tile_cnt, lk->n_lights);
-    TSIM_LAUNCH_CHECK();
-    flag_rank_kernel<<<ntiles, 256, 0, cs>>>(n, F, F_TL, tile_cnt, lid, lk->light_cell, lk->cap_lights, err_flag);
+    if ((st = exclusive_scan_i32(tl_prefix, nw, scan_tmp, lk->n_lights, cs)) != TSIM_OK) return st;
+    bit_list_kernel<<<div_up(nw, 256), 256, 0, cs>>>(W, H, wp, bp.tl, tl_prefix, lk->light_cell, lk->cap_lights, err_flag, 22);
     TSIM_LAUNCH_CHECK();
     // count -> offsets -> fill
-    TSIM_CUDA(cudaMemsetAsync(cnt_ctrl, 0, (size_t)lk->cap_lights * 4, cs));
-    TSIM_CUDA(cudaMemsetAsync(cnt_inc, 0, (size_t)lk->cap_lights * 4, cs));
-    lights_pass_kernel<1><<<div_up(n, 128), 128, 0, cs>>>(L, F, p->aux, lid, cnt_ctrl, cnt_inc, nullptr, nullptr, nullptr, nullptr, 0, 0);
+    TSIM_CUDA(cudaMemsetAsync(lk->ctrl_off, 0, (size_t)(lk->cap_lights + 1) * 4, cs));
+    TSIM_CUDA(cudaMemsetAsync(lk->inc_off, 0, (size_t)(lk->cap_lights + 1) * 4, cs));
+    lights_count_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, tl_prefix, lk->ctrl_off, lk->inc_off);
     TSIM_LAUNCH_CHECK();
-    TSIM_CUDA(cudaMemcpyAsync(lk->ctrl_off, cnt_ctrl, (size_t)lk->cap_lights * 4, cudaMemcpyDeviceToDevice, cs));
-    TSIM_CUDA(cudaMemcpyAsync(lk->inc_off, cnt_inc, (size_t)lk->cap_lights * 4, cudaMemcpyDeviceToDevice, cs));
     if ((st = exclusive_scan_i32(lk->ctrl_off, lk->cap_lights, scan_tmp, scal + 4, cs)) != TSIM_OK) return st;
     if ((st = exclusive_scan_i32(lk->inc_off, lk->cap_lights, scan_tmp, scal + 5, cs)) != TSIM_OK) return st;
     close_offsets_kernel<<<1, 1, 0, cs>>>(lk->n_lights, lk->ctrl_off, lk->inc_off, scal + 4, lk->cap_lights, lk->cap_ctrl, lk->cap_inc, err_flag);
     TSIM_LAUNCH_CHECK();
-    TSIM_CUDA(cudaMemsetAsync(cnt_ctrl, 0, (size_t)lk->cap_lights * 4, cs));
-    TSIM_CUDA(cudaMemsetAsync(cnt_inc, 0, (size_t)lk->cap_lights * 4, cs));
-    lights_pass_kernel<2><<<div_up(n, 128), 128, 0, cs>>>(L, F, p->aux, lid, cnt_ctrl, cnt_inc, lk->ctrl_off, lk->inc_off, lk->ctrl_cell,
-                                                          lk->inc_cell, lk->cap_ctrl, lk->cap_inc);
+    TSIM_CUDA(cudaMemsetAsync(cur_ctrl, 0, (size_t)lk->cap_lights * 4, cs));
+    TSIM_CUDA(cudaMemsetAsync(cur_inc, 0, (size_t)lk->cap_lights * 4, cs));
+    lights_fill_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, tl_prefix, p->cell_type, p->aux, p->block_id, cur_ctrl, cur_inc,
+                                                            lk->ctrl_off, lk->inc_off, lk->ctrl_cell, lk->inc_cell, lk->cap_ctrl, lk->cap_inc);
     TSIM_LAUNCH_CHECK();
-    lights_apply_kernel<<<div_up(n, 256), 256, 0, cs>>>(n, p->cell_type, p->dirs, p->aux, p->block_id, F);
+    tl_apply_kernel<<<div_up(lk->cap_lights, 256), 256, 0, cs>>>(lk->n_lights, lk->light_cell, lk->cap_lights, p->cell_type, p->dirs, p->aux);
+    TSIM_LAUNCH_CHECK();
+    links_sort_kernel<<<div_up(lk->cap_lights, 256), 256, 0, cs>>>(lk->n_lights, lk->cap_lights, lk->ctrl_off, lk->ctrl_cell, lk->inc_off, lk->inc_cell);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

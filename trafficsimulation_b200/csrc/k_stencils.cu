@@ -232,7 +232,7 @@ extern "C" tsim_status tsim_layout_dead_ends(const tsim_cfg *cfg, const tsim_pla
     int grid = coop_grid((const void *)dead_ends_kernel, 256);
     uint8_t *T = p->cell_type; uint16_t *D = p->dirs; uint8_t *A = p->aux;
     void *args[] = {&s, &T, &D, &A, &flags};
-    TSIM_CUDA(cudaLaunchCooperativeKernel((const void *)dead_ends_kernel, dim3(grid), dim3(256), args, 0, cs));
+    TSIM_COOP_LAUNCH(dead_ends_kernel, dim3(grid), dim3(256), args, cs);
     if (sweeps) TSIM_CUDA(cudaMemcpyAsync(sweeps, flags + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
     return TSIM_OK;
 }

@@ -366,6 +366,6 @@ extern "C" tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_table
     long long cap = (long long)sms * (per_sm > 4 ? 4 : per_sm);
     int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     void *args[] = {&a};
-    TSIM_CUDA(cudaLaunchCooperativeKernel((const void *)tick_kernel, dim3(grid), dim3(256), args, 0, (cudaStream_t)stream));
+    TSIM_COOP_LAUNCH(tick_kernel, dim3(grid), dim3(256), args, (cudaStream_t)stream);
     return TSIM_OK;
 }
