@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TSIM_ABI_VERSION 1
+#define TSIM_ABI_VERSION 2
 
 /* cell_type codes = index into Defaults.ZONES (Simulation/config.py:74-95) */
 enum tsim_cell_type {
@@ -76,9 +76,11 @@ typedef struct tsim_cfg {
     int32_t forward_traffic_light_range;       /* must be 0 on the GPU path (TSIM_ERR_UNSUPPORTED) */
     int32_t forward_intersections_mode;
     int32_t block_entrance_road_level;         /* Defaults.BLOCK_ENTRANCE_ROAD_LEVEL, config.py:26 */
-    /* row-band shard window: this device holds global rows [row0, row0 + rows) plus `halo`
-       rows above and below inside the same allocation; single device: row0=0, rows=height, halo=0 */
-    int32_t row0, rows, halo;
+    /* row-band shard window: the planes passed with this cfg hold global rows
+       [win_y0, win_y0 + win_rows) of the width x height grid, row-major, nothing else.  Every cell
+       index a call takes or returns (component roots, light cells, link tables) is an index into THIS
+       window; rows outside it do not exist for the call.  Single device: win_y0 = 0, win_rows = height. */
+    int32_t win_y0, win_rows, reserved0;
 } tsim_cfg;
 
 typedef struct tsim_planes {
@@ -94,9 +96,19 @@ typedef struct tsim_lines {
     const uint32_t *col;   /* [width]  */
 } tsim_lines;
 
-/* component table produced by the labelling passes, one row per component in raster
-   discovery order (id = row + 1): minx, miny, maxx, maxy, size, root cell index */
+/* component table produced by the labelling passes, one row per component of the window in raster
+   discovery order: minx, miny (global y), maxx, maxy (global y), size, root cell (window index) */
 #define TSIM_BLOB_STRIDE 6
+
+typedef struct tsim_blobs {
+    int32_t *table;          /* [cap][TSIM_BLOB_STRIDE], device                                          */
+    int32_t  cap;
+    int32_t *count;          /* device scalar: components found in the window                            */
+    const int32_t *id_base;  /* device scalar or NULL (= 0): id of table row k is k + 1 + *id_base.  Shards
+                                set it from the all-gathered root counts so that ids -- the index into
+                                every per-block tape and the value stored in block_id -- are the global
+                                raster discovery ranks                                     */
+} tsim_blobs;
 
 int         tsim_version(void);
 const char *tsim_last_error(void);
@@ -120,24 +132,25 @@ tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_planes *p, c
                                     void *stream);
 
 /* 4-connected components of `Nothing` in raster discovery order (the flood fills at
-   city_model.py:632-647 and :746-763).  Writes labels (1-based id, 0 elsewhere) into p->block_id,
-   the component table into blobs[cap][TSIM_BLOB_STRIDE] and the count into *n_blobs (device). */
-tsim_status tsim_layout_label_nothing(const tsim_cfg *cfg, const tsim_planes *p, int32_t *blobs,
-                                      int32_t cap, int32_t *n_blobs, void *workspace, size_t ws_bytes,
-                                      void *stream);
+   city_model.py:632-647 and :746-763): fills the component table and the count.  The run structure
+   of the labelling stays in `workspace`; tsim_layout_zones (same workspace, no other libtsim call in
+   between) turns it into the block_id plane.  block_id itself is not touched here. */
+tsim_status tsim_layout_label_nothing(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs,
+                                      int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
 
-/* _carve_subblock_roads (city_model.py:563-737) given the labels of tsim_layout_label_nothing and
-   the carve tape: one row of 8 int32 per blob (drawn, carved, px, py, hor_dir, ver_dir,
+/* _carve_subblock_roads (city_model.py:563-737) given the table of tsim_layout_label_nothing and
+   the carve tape: one row of 8 int32 per blob id (drawn, carved, px, py (global), hor_dir, ver_dir,
    inbound_is_horizontal, tries).  err_flag (device int32) is set non-zero on an illegal row. */
 tsim_status tsim_layout_carve(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines,
-                              const int32_t *blobs, const int32_t *n_blobs, const int32_t *tape,
-                              int32_t n_tape, int32_t *err_flag, void *stream);
-
-/* _flood_fill_blocks_storing_data (city_model.py:742-806) given fresh labels: fills each block with
-   Empty (bbox < 3) or the zone zone_by_block[id-1]; block_id keeps the labels. */
-tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes *p, const int32_t *blobs,
-                              const int32_t *n_blobs, const uint8_t *zone_by_block, int32_t n_tape,
+                              const tsim_blobs *blobs, const int32_t *tape, int32_t n_tape,
                               int32_t *err_flag, void *stream);
+
+/* _flood_fill_blocks_storing_data (city_model.py:742-806) right after tsim_layout_label_nothing:
+   writes block_id (id of the cell's block, 0 elsewhere) and fills each block with Empty (bbox < 3)
+   or the zone zone_by_block[id-1]. */
+tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs,
+                              const uint8_t *zone_by_block, int32_t n_tape, int32_t *err_flag,
+                              void *workspace, size_t ws_bytes, void *stream);
 
 /* _eliminate_dead_ends (city_model.py:811-840); *sweeps (device) receives the sweep count */
 tsim_status tsim_layout_dead_ends(const tsim_cfg *cfg, const tsim_planes *p, int32_t *sweeps,
@@ -148,10 +161,10 @@ tsim_status tsim_layout_upgrade_r2(const tsim_cfg *cfg, const tsim_planes *p, co
                                    int32_t *err_flag, void *stream);
 
 /* _final_place_block_entrances (city_model.py:884-963); run_by_block[id-1] = canonical index of the
-   chosen run among the longest ones; entrances[id-1] receives the cell index or -1 */
-tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_planes *p, const int32_t *blobs,
-                                  const int32_t *n_blobs, const int32_t *run_by_block, int32_t n_tape,
-                                  int32_t *entrances, int32_t *err_flag, void *stream);
+   chosen run among the longest ones; entrances[k] (k = table row) receives the cell index or -1 */
+tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs,
+                                  const int32_t *run_by_block, int32_t n_tape, int32_t *entrances,
+                                  int32_t *err_flag, void *stream);
 
 /* _remove_invalid_intersection_directions + _add_entrance_directions (city_model.py:969-1070), fused */
 tsim_status tsim_layout_fix_dirs(const tsim_cfg *cfg, const tsim_planes *p, void *stream);
@@ -231,11 +244,11 @@ tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, con
 tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                           const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
 
-/* labels the 4-connected components of mask != 0 (u8 plane) in raster discovery order; same outputs as
-   tsim_layout_label_nothing.  Used for the intersection clusters of _create_intersection_light_groups
-   (city_model.py:1587-1650). */
-tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask, int32_t *labels, int32_t *blobs,
-                            int32_t cap, int32_t *n_blobs, void *workspace, size_t ws_bytes, void *stream);
+/* labels the 4-connected components of mask == 1 (u8 plane) in raster discovery order: component
+   table as tsim_layout_label_nothing, plus the label plane (id, 0 elsewhere).  Used for the
+   intersection clusters of _create_intersection_light_groups (city_model.py:1587-1650). */
+tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask, int32_t *labels, const tsim_blobs *blobs,
+                            int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -33,11 +33,15 @@ class Cfg(C.Structure):
         "width", "height", "wall_thickness", "sidewalk_ring_width", "ring_road_type",
         "optimized_intersections", "subblock_roads_have_intersections", "subblock_road_type",
         "min_subblock_spacing", "traffic_light_range", "forward_traffic_light_range",
-        "forward_intersections_mode", "block_entrance_road_level", "row0", "rows", "halo")]
+        "forward_intersections_mode", "block_entrance_road_level", "win_y0", "win_rows", "reserved0")]
 
 
 class Planes(C.Structure):
     _fields_ = [("cell_type", C.c_void_p), ("dirs", C.c_void_p), ("aux", C.c_void_p), ("block_id", C.c_void_p)]
+
+
+class Blobs(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("cap", C.c_int32), ("count", C.c_void_p), ("id_base", C.c_void_p)]
 
 
 class Lines(C.Structure):

@@ -28,17 +28,26 @@ tsim_status check_cuda(cudaError_t e, const char *what) {
 
 tsim_status check_cfg(const tsim_cfg *c) {
     if (!c) { set_error("cfg is NULL"); return TSIM_ERR_CONFIG; }
-    if (c->width < 1 || c->height < 1 || (long long)c->width * c->height > 0x7fffffffLL) {
-        set_error("grid %d x %d out of range (cell indices are int32)", c->width, c->height);
+    if (c->width < 1 || c->height < 1) {
+        set_error("grid %d x %d out of range", c->width, c->height);
         return TSIM_ERR_CONFIG;
     }
     if (c->wall_thickness < 0 || c->sidewalk_ring_width < 0) { set_error("negative frame widths"); return TSIM_ERR_CONFIG; }
     if (c->ring_road_type < 0 || c->ring_road_type > 3) { set_error("ring_road_type %d", c->ring_road_type); return TSIM_ERR_CONFIG; }
     if (c->subblock_road_type < 1 || c->subblock_road_type > 3) { set_error("subblock_road_type %d", c->subblock_road_type); return TSIM_ERR_CONFIG; }
-    if (c->rows < 1 || c->row0 < 0 || c->row0 + c->rows > c->height || c->halo < 0) {
-        set_error("bad shard window row0=%d rows=%d halo=%d height=%d", c->row0, c->rows, c->halo, c->height);
+    if (c->win_rows < 1 || c->win_y0 < 0 || c->win_y0 + c->win_rows > c->height) {
+        set_error("bad shard window win_y0=%d win_rows=%d height=%d", c->win_y0, c->win_rows, c->height);
         return TSIM_ERR_CONFIG;
     }
+    if ((long long)c->width * c->win_rows > 0x7fffffffLL) {
+        set_error("window %d x %d out of range (cell indices are int32)", c->width, c->win_rows);
+        return TSIM_ERR_CONFIG;
+    }
+    return TSIM_OK;
+}
+
+tsim_status check_blobs(const tsim_blobs *b, const char *who) {
+    if (!b || !b->table || !b->count || b->cap < 1) { set_error("%s: bad tsim_blobs", who); return TSIM_ERR_CONFIG; }
     return TSIM_OK;
 }
 
@@ -88,7 +97,7 @@ extern "C" tsim_status tsim_workspace_bytes(const tsim_cfg *cfg, size_t *out) {
     tsim_status s = check_cfg(cfg);
     if (s != TSIM_OK) return s;
     if (!out) { set_error("out is NULL"); return TSIM_ERR_CONFIG; }
-    size_t cells = (size_t)cfg->width * (size_t)(cfg->rows + 2 * cfg->halo);
+    size_t cells = (size_t)cfg->width * (size_t)cfg->win_rows;
     // largest user: tsim_layout_lights (reach bits 1 B + per-cell scratch 4 B) and the labelling
     // passes (scan partials); see each pass for its own layout.  16 B per cell + 1 MiB covers all.
     *out = cells * 16 + (1u << 20);

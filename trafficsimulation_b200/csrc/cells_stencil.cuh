@@ -11,7 +11,7 @@ struct PlaneView {
     const uint16_t *D;
     const uint8_t *A;
     int W, H, y0, nrows;
-    __host__ __device__ __forceinline__ bool has(int x, int y) const { return x >= 0 && x < W && y >= 0 && y < H; }
+    __host__ __device__ __forceinline__ bool has(int x, int y) const { return x >= 0 && x < W && y >= y0 && y < y0 + nrows; }
     __host__ __device__ __forceinline__ size_t at(int x, int y) const { return (size_t)(y - y0) * W + x; }
     __host__ __device__ __forceinline__ int t(int x, int y) const { return has(x, y) ? (int)T[at(x, y)] : -1; }
     __host__ __device__ __forceinline__ uint32_t d(int x, int y) const { return D[at(x, y)]; }

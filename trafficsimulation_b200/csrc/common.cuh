@@ -66,7 +66,16 @@ struct Geo {   // derived geometry of a cfg
     __host__ __device__ bool inside(int x, int y) const { return x >= ixmin && x <= ixmax && y >= iymin && y <= iymax; }
 };
 
+// window of a shard allocation: local row ly holds global row y0 + ly
+struct Win {
+    int W, LH, y0, Hg;
+    __host__ __device__ explicit Win(const tsim_cfg &c) : W(c.width), LH(c.win_rows), y0(c.win_y0), Hg(c.height) {}
+    __host__ __device__ long long cells() const { return (long long)W * LH; }
+    __host__ __device__ bool full() const { return y0 == 0 && LH == Hg; }
+};
+
 void set_error(const char *fmt, ...);
+tsim_status check_blobs(const tsim_blobs *b, const char *who);
 tsim_status check_cuda(cudaError_t e, const char *what);
 tsim_status check_cfg(const tsim_cfg *cfg);
 

@@ -9,9 +9,9 @@
 
 namespace tsim {
 
-struct LiveGrid {   // read/write access to the live planes (own writes are visible to the thread)
+struct LiveGrid {   // read/write access to the live planes of the window, LOCAL row numbers (own writes are visible to the thread)
     uint8_t *T; uint16_t *D; uint8_t *A;
-    int W, H;
+    int W, H;       // H = rows of the window
     __device__ __forceinline__ bool has(int x, int y) const { return x >= 0 && x < W && y >= 0 && y < H; }
     __device__ __forceinline__ size_t at(int x, int y) const { return (size_t)y * W + x; }
     __device__ __forceinline__ int t(int x, int y) const { return has(x, y) ? (int)((volatile uint8_t *)T)[at(x, y)] : -1; }
@@ -36,7 +36,7 @@ __device__ __forceinline__ void lay_cell(const LiveGrid &g, int sub_t, int x, in
 }
 
 // extend_to_road (:603-627)
-__device__ void extend(const tsim_cfg &c, const LiveGrid &g, const uint32_t *rowt, const uint32_t *colt, int sub_t, int sx, int sy,
+__device__ void extend(const tsim_cfg &c, const LiveGrid &g, const uint32_t *rowt /* + win_y0 */, const uint32_t *colt, int sub_t, int sx, int sy,
                        int march, int arrow, int32_t *err) {
     int cx = sx, cy = sy;
     while (g.has(cx, cy)) {
@@ -74,25 +74,31 @@ __device__ void extend(const tsim_cfg &c, const LiveGrid &g, const uint32_t *row
 
 __global__ void __launch_bounds__(128) carve_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, const uint32_t *__restrict__ rowt,
                                                     const uint32_t *__restrict__ colt, const int32_t *__restrict__ blobs,
-                                                    const int32_t *__restrict__ n_blobs, const int32_t *__restrict__ tape, int n_tape,
-                                                    int32_t *err) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nb = *n_blobs;
-    if (b == 0 && nb > n_tape) *err = 1;
-    if (b >= nb) return;
-    const int32_t *row = tape + (size_t)b * 8;
-    if (!row[1]) return;
+                                                    const int32_t *__restrict__ n_blobs, int cap_blobs, const int32_t *__restrict__ id_base,
+                                                    const int32_t *__restrict__ tape, int n_tape, int32_t *err) {
+    const int nb = min(*n_blobs, cap_blobs);
+    const int base = id_base ? *id_base : 0;
+    const int y0 = c.win_y0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+    const int gid = b + base;            // 0-based global blob id = tape row
+    if (gid < 0) continue;               // cut by the window's lower edge: owned (and carved) by the shard below
+    if (gid >= n_tape) { *err = 1; continue; }
+    const int32_t *row = tape + (size_t)gid * 8;
+    if (!row[1]) continue;
     const int32_t *bl = blobs + (size_t)b * TSIM_BLOB_STRIDE;
-    const int minx = bl[0], miny = bl[1], maxx = bl[2], maxy = bl[3];
-    const int px = row[2], py = row[3], hd = row[4], vd = row[5], inb_h = row[6];
+    const int minx = bl[0], miny = bl[1] - y0, maxx = bl[2], maxy = bl[3] - y0;   // window-local rows from here on
+    // a blob cut by a window edge that is not a grid edge lies in the halo: the shard that owns its rows sees it whole and carves it
+    if ((miny == 0 && y0 > 0) || (maxy == c.win_rows - 1 && y0 + c.win_rows < c.height)) continue;
+    const int px = row[2], py = row[3] - y0, hd = row[4], vd = row[5], inb_h = row[6];
     const int ms = c.min_subblock_spacing;
     // the tape must hold a decision the reference could have drawn (:659-675)
     if (!((hd == DW || hd == DE) && (vd == DN || vd == DS)) || px < minx + ms || px > maxx - ms || py < miny + ms || py > maxy - ms ||
         (long long)(maxx - minx + 1) * (maxy - miny + 1) != bl[4] /* non-rectangular blob: carve footprints may interact */) {
         *err = 2;
-        return;
+        continue;
     }
-    const LiveGrid g{T, D, A, c.width, c.height};
+    const LiveGrid g{T, D, A, c.width, c.win_rows};
+    const uint32_t *rowl = rowt + y0;   // line table of local row ly = rowl[ly]
     const int sub_t = T_R1 - 1 + c.subblock_road_type;
     const int h_arrow = inb_h ? opp_of(hd) : hd;   // :683-696
     const int v_arrow = inb_h ? vd : opp_of(vd);   // :707-708
@@ -102,32 +108,34 @@ __global__ void __launch_bounds__(128) carve_kernel(tsim_cfg c, uint8_t *T, uint
     if (vd == DS) { for (int vy = py; vy >= miny; vy--) lay_cell(g, sub_t, px, vy, v_arrow); vy_end = miny; }
     else { for (int vy = py; vy <= maxy; vy++) lay_cell(g, sub_t, px, vy, v_arrow); vy_end = maxy; }
     g.D[g.at(px, py)] = (uint16_t)dl_one(inb_h ? v_arrow : h_arrow);   // pivot shows the outbound arrow only (:713-715)
-    extend(c, g, rowt, colt, sub_t, hx_end + dx_of(hd), py, hd, h_arrow, err);
-    extend(c, g, rowt, colt, sub_t, px, vy_end + dy_of(vd), vd, v_arrow, err);
+    extend(c, g, rowl, colt, sub_t, hx_end + dx_of(hd), py, hd, h_arrow, err);
+    extend(c, g, rowl, colt, sub_t, px, vy_end + dy_of(vd), vd, v_arrow, err);
     for (int dy = -1; dy <= 1; dy++)   // :731-737
         for (int dx = -1; dx <= 1; dx++) {
             if (!dx && !dy) continue;
             const int t = g.t(px + dx, py + dy);
             if (t >= 0 && !is_road_like(t) && t != T_WALL) g.place(px + dx, py + dy, T_SIDEWALK);
         }
+    }
 }
 
 }  // namespace tsim
 
 using namespace tsim;
 
-extern "C" tsim_status tsim_layout_carve(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines, const int32_t *blobs,
-                                         const int32_t *n_blobs, const int32_t *tape, int32_t n_tape, int32_t *err_flag, void *stream) {
+extern "C" tsim_status tsim_layout_carve(const tsim_cfg *cfg, const tsim_planes *p, const tsim_lines *lines, const tsim_blobs *blobs,
+                                         const int32_t *tape, int32_t n_tape, int32_t *err_flag, void *stream) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
-    if (!p || !p->cell_type || !p->dirs || !p->aux || !lines || !lines->row || !lines->col || !blobs || !n_blobs || !tape || !err_flag || n_tape < 0) {
+    if ((st = check_blobs(blobs, "tsim_layout_carve")) != TSIM_OK) return st;
+    if (!p || !p->cell_type || !p->dirs || !p->aux || !lines || !lines->row || !lines->col || !tape || !err_flag || n_tape < 0) {
         set_error("tsim_layout_carve: bad arguments");
         return TSIM_ERR_CONFIG;
     }
-    if (cfg->halo != 0 || cfg->rows != cfg->height) { set_error("tsim_layout_carve: run on the gathered grid (shards carve after the blob merge)"); return TSIM_ERR_UNSUPPORTED; }
     if (n_tape == 0) return TSIM_OK;
-    carve_kernel<<<div_up(n_tape, 128), 128, 0, (cudaStream_t)stream>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, blobs,
-                                                                        n_blobs, tape, n_tape, err_flag);
+    const int grid = div_up(blobs->cap, 128) < 148 * 16 ? div_up(blobs->cap, 128) : 148 * 16;
+    carve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, blobs->table,
+                                                         blobs->count, blobs->cap, blobs->id_base, tape, n_tape, err_flag);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

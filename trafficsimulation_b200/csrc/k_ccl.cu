@@ -1,27 +1,125 @@
-// k_ccl.cu -- union-find connected-component labelling of one cell type, in raster discovery order.
+// k_ccl.cu -- connected-component labelling of one cell type in raster discovery order, as a
+// union-find over ROW RUNS of a bit-plane.
 //
-// Replaces the DFS flood fills of _carve_subblock_roads (city_model.py:632-647) and
-// _flood_fill_blocks_storing_data (:746-763), and the zone fill of the latter (:768-806).
+// Replaces the DFS flood fills of _carve_subblock_roads (city_model.py:632-647),
+// _flood_fill_blocks_storing_data (:746-763) with its zone fill (:768-806), and the cluster fill of
+// _create_intersection_light_groups (:1595-1611).
 //
 // The reference numbers components by the raster position (y outer, x inner) of their first cell.
-// Union-find with "smaller index wins" makes every component's root its minimum raster index, so
-// id = 1 + (number of roots before it) -- an exclusive scan over root flags.
+// Union-find with "smaller index wins" over runs numbered in raster order makes every component's
+// root its first run, whose first cell is the component's minimum raster cell; so
+// id = 1 + (number of root runs before it) -- an exclusive scan over root flags.
 //
-//   1. init    : label = raster index of the start of the cell's horizontal run inside its warp's
-//                32-cell segment (warp ballot -- the run pre-merge costs no memory traffic);
-//   2. merge   : union with the cell above where the column adjacency is not already implied by the
-//                left neighbours, and across warp-segment seams; lock-free atomicMin hooking;
-//   3. flatten + count roots per tile -> single-CTA scan of tile counts -> ranks at roots;
-//   4. relabel : label -> id, per-run atomics for bbox / size into the component table.
+//   1. bits    : ONE streaming read of the type plane (1 B/cell): target cells -> bit-plane, 64 cells
+//                per word (a quad of lanes packs a word with two shuffles);
+//   2. runs    : run starts = bit & ~previous bit; popcount -> scan numbers the runs in raster order;
+//                per run: parent, first cell, length (dense arrays, ~1 run per 50 cells of a city);
+//   3. merge   : per word, the overlap segments of row y and row y-1 (one AND) -> one lock-free
+//                atomicMin union per segment;
+//   4. flatten : parent -> root, root flags -> scan -> component ids; table rows initialised at roots;
+//   5. bbox    : per run atomics (min/max x, y, size) into the component table;
+//   6. labels  : only when a label plane is wanted (zoning, clusters): one coalesced 4 B/cell write of
+//                the ids, fused with the zone fill of the type plane.
 //
-// The label plane IS the caller's block_id plane (int32), so no extra 4 B/cell scratch is needed
-// besides the per-root rank (workspace, 4 B/cell, written only at roots).
+// Carving needs steps 1-5 only (no per-cell label traffic at all); zoning adds step 6, which is the
+// compulsory 4 B/cell write of block_id + the 1 B/cell type update.
 #include "scan.cuh"
 
 namespace tsim {
 
-constexpr int CCL_TILE = SCAN_TILE;   // cells per CTA in the counting / ranking kernels (256 threads x 8)
+typedef unsigned long long u64;
 
+struct Runs {            // lives in the caller's workspace between the label call and the zoning call
+    u64 *M;              // [wp * LH] target bit-plane
+    int32_t *sprefix;    // [wp * LH] runs started before this word (raster order)
+    int32_t *parent;     // [cap] union-find parent; after flatten: the root run
+    int32_t *start;      // [cap] first cell of the run (window index)
+    int32_t *len;        // [cap]
+    int32_t *rank;       // [cap] root flag, then (scan) roots before this run
+    int32_t *n_runs;     // device scalar
+    int32_t *err;        // the caller's error flag: 24 = run capacity, 25 = component capacity
+    int wp, cap;
+};
+
+// ---------------------------------------------------------------- 1. bit-plane of the target type
+__global__ void __launch_bounds__(256) ccl_bits_kernel(int W, int LH, int wp, const uint8_t *__restrict__ T, int target, u64 *__restrict__ M) {
+    const int spr = wp * 4;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = threadIdx.x & 3;
+    const long long y_ll = g / spr;
+    const int s = (int)(g % spr), x0 = s * 16;
+    const bool row_ok = y_ll < LH;
+    uint32_t m = 0;
+    if (row_ok && x0 < W) {
+        const size_t base = (size_t)y_ll * W + x0;
+        if ((W & 15) == 0) {
+            const uint4 tq = __ldg(reinterpret_cast<const uint4 *>(T + base));
+            const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) m |= (uint32_t)(((tw[k >> 2] >> (8 * (k & 3))) & 0xffu) == (uint32_t)target) << k;
+        } else {
+            for (int k = 0; k < 16 && x0 + k < W; k++) m |= (uint32_t)(T[base + k] == target) << k;
+        }
+    }
+    u64 v = (u64)m << (16 * q);
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    if (row_ok && q == 0) M[(size_t)y_ll * wp + (s >> 2)] = v;
+}
+
+// run starts of word (y, wx): set bit whose left neighbour (previous bit, or bit 63 of the previous word of the row) is clear
+__device__ __forceinline__ u64 run_starts(const u64 *__restrict__ M, size_t i, int wx) {
+    const u64 m = M[i];
+    const u64 prev = wx > 0 ? M[i - 1] >> 63 : 0ull;
+    return m & ~((m << 1) | prev);
+}
+
+// index of the run that contains bit p of word i
+__device__ __forceinline__ int run_of(const u64 *__restrict__ M, const int32_t *__restrict__ sprefix, size_t i, int wx, int p) {
+    return sprefix[i] + __popcll(run_starts(M, i, wx) & ((2ull << p) - 1ull)) - 1;
+}
+
+// ---------------------------------------------------------------- 2. runs
+__global__ void __launch_bounds__(256) ccl_count_kernel(long long nw, int wp, const u64 *__restrict__ M, int32_t *__restrict__ cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) cnt[i] = __popcll(run_starts(M, (size_t)i, (int)(i % wp)));
+}
+
+__global__ void __launch_bounds__(256) ccl_runs_kernel(int W, long long nw, Runs r) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nw) return;
+    const int wp = r.wp, wx = (int)(i % wp);
+    const long long y = i / wp;
+    u64 st = run_starts(r.M, (size_t)i, wx);
+    if (!st) return;
+    const u64 m = r.M[i];
+    int k = r.sprefix[i];
+    while (st) {
+        const int p = __ffsll((long long)st) - 1;
+        st &= st - 1;
+        // length: ones from p upwards, continuing into the following words of the row
+        const u64 rest = ~(m >> p);
+        int len = rest ? __ffsll((long long)rest) - 1 : 64;
+        if (p + len == 64) {
+            for (int w2 = wx + 1; w2 < wp; w2++) {
+                const u64 inv = ~r.M[i + (w2 - wx)];
+                const int l = inv ? __ffsll((long long)inv) - 1 : 64;
+                len += l;
+                if (l < 64) break;
+            }
+        }
+        if (k < r.cap) {
+            r.parent[k] = k;
+            r.start[k] = (int32_t)(y * W + wx * 64 + p);
+            r.len[k] = len;
+        } else {
+            *r.err = 24;
+        }
+        k++;
+    }
+}
+
+// ---------------------------------------------------------------- 3. merge
 __device__ __forceinline__ int uf_find(const int32_t *L, int i) {
     int p = __ldcg(L + i);
     while (p != i) { i = p; p = __ldcg(L + i); }
@@ -40,166 +138,194 @@ __device__ __forceinline__ void uf_union(int32_t *L, int a, int b) {
     }
 }
 
-// one thread per cell of the OWNED rows; warp = 32 consecutive x of one row (W padded to 32)
-__global__ void __launch_bounds__(256) ccl_init_kernel(int W, int nrows, const uint8_t *__restrict__ T, int32_t *__restrict__ L, int target) {
-    const int wpr = (W + 31) >> 5;   // warps per row
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= (long long)wpr * nrows) return;
-    const int y = (int)(gw / wpr), x = (int)(gw % wpr) * 32 + lane;
-    const bool in = x < W;
-    const size_t i = (size_t)y * W + x;
-    const bool tg = in && T[i] == target;
-    const uint32_t mask = __ballot_sync(0xffffffffu, tg);
-    if (!in) return;
-    if (!tg) { L[i] = -1; return; }
-    // start of my run inside this warp segment: one past the highest clear bit below my lane
-    const uint32_t below = ~mask & ((1u << lane) - 1u);
-    const int start = below ? 32 - __clz(below) : 0;
-    L[i] = (int32_t)(i - (lane - start));
-}
-
-__global__ void __launch_bounds__(256) ccl_merge_kernel(int W, int nrows, const uint8_t *__restrict__ T, int32_t *L, int target) {
-    const long long n = (long long)W * nrows;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (T[i] != target) return;
-    const int y = (int)(i / W), x = (int)(i % W);
-    const bool left = x > 0 && T[i - 1] == target;
-    if (left && (x & 31) == 0) uf_union(L, (int)i, (int)i - 1);            // seam between warp segments
-    if (y > 0 && T[i - W] == target) {
-        const bool upleft = x > 0 && T[i - W - 1] == target;
-        if (!(left && upleft)) uf_union(L, (int)i, (int)(i - W));          // else implied by the left pair
+__global__ void __launch_bounds__(256) ccl_merge_kernel(long long nw, Runs r) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + r.wp;   // rows 1..
+    if (i >= nw) return;
+    const int wp = r.wp, wx = (int)(i % wp);
+    const u64 ov = r.M[i] & r.M[i - wp];
+    if (!ov) return;
+    const u64 ovprev = wx > 0 ? (r.M[i - 1] & r.M[i - wp - 1]) >> 63 : 0ull;
+    u64 seg = ov & ~((ov << 1) | ovprev);   // first cell of every overlap segment (a segment continuing from the previous word was merged there)
+    while (seg) {
+        const int p = __ffsll((long long)seg) - 1;
+        seg &= seg - 1;
+        const int a = run_of(r.M, r.sprefix, (size_t)i, wx, p), b = run_of(r.M, r.sprefix, (size_t)(i - wp), wx, p);
+        if (a < r.cap && b < r.cap) uf_union(r.parent, a, b);
     }
 }
 
-// flatten labels and count roots per tile
-__global__ void __launch_bounds__(256) ccl_flatten_count_kernel(long long n, int32_t *L, int32_t *tile_count) {
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    const long long base = (long long)blockIdx.x * CCL_TILE;
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < CCL_TILE / 256; k++) {
-        const long long i = base + k * 256 + threadIdx.x;
-        if (i < n) {
-            const int l = __ldcg(L + i);
-            if (l >= 0) {
-                const int r = uf_find(L, l);
-                if (r != l) L[i] = r;
-                c += (r == (int)i);
-            }
+// ---------------------------------------------------------------- 4. flatten, rank, table rows
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(Runs r) {
+    const int n = min(*r.n_runs, r.cap);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int root = uf_find(r.parent, k);
+        r.rank[k] = (root == k);
+        if (root != k) r.parent[k] = root;   // roots keep pointing at themselves, so concurrent finds stay correct
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_roots_kernel(Runs r, int32_t *__restrict__ blobs, int cap_blobs, int32_t *err) {
+    const int n = min(*r.n_runs, r.cap);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        if (r.parent[k] != k) continue;
+        const int id = r.rank[k];   // 0-based
+        if (id < cap_blobs) {
+            int32_t *b = blobs + (size_t)id * TSIM_BLOB_STRIDE;
+            b[0] = 0x7fffffff; b[1] = 0x7fffffff; b[2] = -1; b[3] = -1; b[4] = 0; b[5] = r.start[k];
+        } else {
+            *err = 25;
         }
     }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_count[blockIdx.x] = s_cnt;
 }
 
-// rank roots inside each tile (raster order) and initialise their component-table rows
-__global__ void __launch_bounds__(256) ccl_rank_kernel(long long n, const int32_t *__restrict__ L, const int32_t *__restrict__ tile_off,
-                                                       int32_t *__restrict__ rank, int32_t *__restrict__ blobs, int cap, int32_t *err) {
-    __shared__ int s_warp[8];
-    const long long base = (long long)blockIdx.x * CCL_TILE;
-    int running = tile_off[blockIdx.x];
-    for (int k = 0; k < CCL_TILE / 256; k++) {
-        const long long i = base + k * 256 + threadIdx.x;
-        const bool root = i < n && L[i] == (int)i;
-        const uint32_t m = __ballot_sync(0xffffffffu, root);
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        if (lane == 0) s_warp[w] = __popc(m);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < w) before += c; total += c; }
-        if (root) {
-            const int id = running + before + __popc(m & ((1u << lane) - 1u)) + 1;   // 1-based
-            rank[i] = id;
-            if (id <= cap) {
-                int32_t *b = blobs + (size_t)(id - 1) * TSIM_BLOB_STRIDE;
-                b[0] = 0x7fffffff; b[1] = 0x7fffffff; b[2] = -1; b[3] = -1; b[4] = 0; b[5] = (int32_t)i;
-            } else {
-                *err = 1;
-            }
-        }
-        running += total;
-        __syncthreads();
-    }
-}
-
-// label -> id, bbox / size by per-run atomics
-__global__ void __launch_bounds__(256) ccl_relabel_kernel(int W, int nrows, int y_global0, int32_t *L, const int32_t *__restrict__ rank,
-                                                          int32_t *blobs, int cap) {
-    const int wpr = (W + 31) >> 5;
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= (long long)wpr * nrows) return;
-    const int y = (int)(gw / wpr), x = (int)(gw % wpr) * 32 + lane;
-    const bool in = x < W;
-    const size_t i = (size_t)y * W + x;
-    const int l = in ? L[i] : -1;
-    const int id = l >= 0 ? rank[l] : 0;
-    if (in) L[i] = id;
-    // runs of equal id inside the warp segment
-    const int left_id = __shfl_up_sync(0xffffffffu, id, 1);
-    const bool start = id > 0 && (lane == 0 || left_id != id);
-    const uint32_t smask = __ballot_sync(0xffffffffu, start || id == 0);   // boundaries (run starts and gaps)
-    if (start && id <= cap) {
-        const uint32_t after = smask & ~((2u << lane) - 1u);               // next boundary after my lane
-        const int end = after ? __ffs(after) - 1 : 32;                     // exclusive lane
-        const int len = end - lane;
-        int32_t *b = blobs + (size_t)(id - 1) * TSIM_BLOB_STRIDE;
+// ---------------------------------------------------------------- 5. bbox / size; parent[] becomes the 0-based component id of the run
+__global__ void __launch_bounds__(256) ccl_bbox_kernel(int W, int y_global0, Runs r, int32_t *blobs, int cap_blobs) {
+    const int n = min(*r.n_runs, r.cap);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int id = r.rank[r.parent[k]];
+        if (id >= cap_blobs) continue;
+        const int s = r.start[k], len = r.len[k];
+        const int x = s % W, y = s / W + y_global0;
+        int32_t *b = blobs + (size_t)id * TSIM_BLOB_STRIDE;
         atomicMin(b + 0, x); atomicMax(b + 2, x + len - 1);
-        atomicMin(b + 1, y + y_global0); atomicMax(b + 3, y + y_global0);
+        atomicMin(b + 1, y); atomicMax(b + 3, y);
         atomicAdd(b + 4, len);
     }
 }
 
-// zone fill (city_model.py:768-786): Empty when the bbox is thinner than 3, else the taped zone
-__global__ void __launch_bounds__(256) zones_fill_kernel(long long n, uint8_t *T, uint16_t *D, uint8_t *A, const int32_t *__restrict__ B,
-                                                         const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs,
-                                                         const uint8_t *__restrict__ zone, int n_tape, int32_t *err) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int id = B[i];
-    if (id <= 0) return;
-    if (id > n_tape || id > *n_blobs) { *err = 1; return; }
-    const int32_t *b = blobs + (size_t)(id - 1) * TSIM_BLOB_STRIDE;
-    const bool thin = (b[2] - b[0] + 1 < 3) || (b[3] - b[1] + 1 < 3);
-    int t = T_EMPTY;
-    if (!thin) { t = zone[id - 1]; if (t > T_OTH) { *err = 2; return; } }
-    T[i] = (uint8_t)t; D[i] = 0; A[i] &= (AUX_RING | AUX_EVER);
+__global__ void __launch_bounds__(256) ccl_ids_kernel(Runs r) {   // separate pass: bbox reads parent[] of OTHER runs' roots
+    const int n = min(*r.n_runs, r.cap);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) r.len[k] = r.rank[r.parent[k]];   // len[] := component id
 }
 
-tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int32_t *L, int target, int32_t *blobs, int32_t cap, int32_t *n_blobs,
-                       void *workspace, size_t ws_bytes, cudaStream_t cs) {
-    // single-device labelling works on the owned rows; shards call it per device and merge afterwards
-    const int W = cfg->width, nrows = cfg->rows;
-    const long long n = (long long)W * nrows;
-    const int ntiles = div_up(n, CCL_TILE);
-    const size_t need = 256 + (size_t)n * 4 + (size_t)ntiles * 4;
-    if (!workspace || ws_bytes < need) { set_error("labelling needs %zu workspace bytes, got %zu", need, ws_bytes); return TSIM_ERR_WORKSPACE; }
-    int32_t *err = (int32_t *)workspace;                             // [0] capacity flag
-    int32_t *rank = (int32_t *)((char *)workspace + 256);
-    int32_t *tile_count = rank + n;
-    const size_t off = (size_t)cfg->halo * W;
-    const uint8_t *To = T + off;
-    int32_t *Lo = L + off;
-    TSIM_CUDA(cudaMemsetAsync(err, 0, 4, cs));
-    const long long warps = (long long)((W + 31) >> 5) * nrows;
-    ccl_init_kernel<<<div_up(warps * 32, 256), 256, 0, cs>>>(W, nrows, To, Lo, target);
+// ---------------------------------------------------------------- 6. label plane (+ zone fill)
+// fill[id] (u8): new type of the component's cells, or 0xff = leave the type plane alone
+__global__ void __launch_bounds__(256) zones_table_kernel(const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs, int cap_blobs,
+                                                          const int32_t *__restrict__ id_base, const uint8_t *__restrict__ zone, int n_tape,
+                                                          uint8_t *__restrict__ fill, int32_t *err) {
+    const int n = min(*n_blobs, cap_blobs);
+    const int base = id_base ? *id_base : 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int32_t *b = blobs + (size_t)k * TSIM_BLOB_STRIDE;
+        const bool thin = (b[2] - b[0] + 1 < 3) || (b[3] - b[1] + 1 < 3);   // :768-770
+        int t = T_EMPTY;
+        if (!thin) {
+            const int gid = k + base;   // 0-based global id
+            if (gid < 0) { t = T_EMPTY; }                       // a component cut by the window's lower edge: its rows are not owned here
+            else if (gid >= n_tape) { *err = 1; }
+            else { t = zone[gid]; if (t > T_OTH) { *err = 2; t = T_EMPTY; } }
+        }
+        fill[k] = (uint8_t)t;
+    }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Runs r, const int32_t *__restrict__ id_base, int cap_blobs,
+                                                         int32_t *__restrict__ L, uint8_t *__restrict__ T, const uint8_t *__restrict__ fill) {
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    const int base = (id_base ? *id_base : 0) + 1;
+    const int wp = r.wp;
+    if ((W & 3) == 0) {
+        const long long y = i0 / W;
+        const int x = (int)(i0 % W), wx = x >> 6, sh = x & 63;
+        const size_t wi = (size_t)y * wp + wx;
+        const uint32_t bits = (uint32_t)(r.M[wi] >> sh) & 0xfu;
+        int4 out = make_int4(0, 0, 0, 0);
+        if (bits) {
+            const u64 st = run_starts(r.M, wi, wx);
+            const int sp = r.sprefix[wi];
+            int ids[4] = {0, 0, 0, 0};
+            int last_run = -1, last_id = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!((bits >> k) & 1u)) continue;
+                const int run = sp + __popcll(st & ((2ull << (sh + k)) - 1ull)) - 1;
+                if (run != last_run) { last_run = run; last_id = run < r.cap ? r.len[run] : 0; }
+                ids[k] = last_id + base;
+                if (FILL && last_id < cap_blobs) { const uint8_t f = fill[last_id]; if (f != 0xff) T[i0 + k] = f; }
+            }
+            out = make_int4(ids[0], ids[1], ids[2], ids[3]);
+        }
+        *reinterpret_cast<int4 *>(L + i0) = out;
+    } else {
+        for (int k = 0; k < 4 && i0 + k < n; k++) {
+            const long long i = i0 + k, y = i / W;
+            const int x = (int)(i % W), wx = x >> 6, p = x & 63;
+            const size_t wi = (size_t)y * wp + wx;
+            int id = 0;
+            if ((r.M[wi] >> p) & 1ull) {
+                const int run = run_of(r.M, r.sprefix, wi, wx, p);
+                const int cid = run < r.cap ? r.len[run] : 0;
+                id = cid + base;
+                if (FILL && cid < cap_blobs) { const uint8_t f = fill[cid]; if (f != 0xff) T[i] = f; }
+            }
+            L[i] = id;
+        }
+    }
+}
+
+// workspace layout shared by the label call and the calls that materialise its result
+static tsim_status runs_layout(const tsim_cfg *cfg, void *workspace, size_t ws_bytes, Runs &r, int32_t *&scan_tmp, uint8_t *&fill, int cap_blobs) {
+    const Win win(*cfg);
+    const long long n = win.cells();
+    const int wp = div_up(win.W, 64);
+    const long long nw = (long long)wp * win.LH;
+    const int cap = (int)(n / 4 + 1024);
+    char *w = (char *)workspace;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
+    int32_t *scal = (int32_t *)take(64 * 4);
+    r.n_runs = scal; r.err = nullptr;
+    r.M = (u64 *)take((size_t)nw * 8);
+    r.sprefix = (int32_t *)take((size_t)nw * 4);
+    r.parent = (int32_t *)take((size_t)cap * 4);
+    r.start = (int32_t *)take((size_t)cap * 4);
+    r.len = (int32_t *)take((size_t)cap * 4);
+    r.rank = (int32_t *)take((size_t)cap * 4);
+    scan_tmp = (int32_t *)take((size_t)(div_up(nw > cap ? nw : cap, SCAN_TILE) + 1) * 4);
+    fill = (uint8_t *)take((size_t)(cap_blobs > 0 ? cap_blobs : 1));
+    r.wp = wp; r.cap = cap;
+    if (!workspace || o > ws_bytes) { set_error("labelling needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
+    return TSIM_OK;
+}
+
+static int list_grid(long long n) {
+    long long b = (n + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    return (int)(b < 1 ? 1 : b);
+}
+
+// steps 1-5
+tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int target, const tsim_blobs *blobs, int32_t *err_flag, void *workspace,
+                       size_t ws_bytes, cudaStream_t cs) {
+    Runs r; int32_t *scan_tmp; uint8_t *fill;
+    tsim_status st = runs_layout(cfg, workspace, ws_bytes, r, scan_tmp, fill, blobs->cap);
+    if (st != TSIM_OK) return st;
+    r.err = err_flag;
+    const Win win(*cfg);
+    const long long nw = (long long)r.wp * win.LH;
+    TSIM_CUDA(cudaMemsetAsync(r.n_runs, 0, 64 * 4, cs));
+    ccl_bits_kernel<<<div_up(nw * 4, 256), 256, 0, cs>>>(win.W, win.LH, r.wp, T, target, r.M);
     TSIM_LAUNCH_CHECK();
-    ccl_merge_kernel<<<div_up(n, 256), 256, 0, cs>>>(W, nrows, To, Lo, target);
+    ccl_count_kernel<<<div_up(nw, 256), 256, 0, cs>>>(nw, r.wp, r.M, r.sprefix);
     TSIM_LAUNCH_CHECK();
-    ccl_flatten_count_kernel<<<ntiles, 256, 0, cs>>>(n, Lo, tile_count);
+    if ((st = exclusive_scan_i32(r.sprefix, nw, scan_tmp, r.n_runs, cs)) != TSIM_OK) return st;
+    ccl_runs_kernel<<<div_up(nw, 256), 256, 0, cs>>>(win.W, nw, r);
     TSIM_LAUNCH_CHECK();
-    scan_tiles_kernel<<<1, 1024, 0, cs>>>(ntiles, tile_count, n_blobs);
+    if (win.LH > 1) {
+        ccl_merge_kernel<<<div_up(nw - r.wp, 256), 256, 0, cs>>>(nw, r);
+        TSIM_LAUNCH_CHECK();
+    }
+    const int g = list_grid(r.cap);
+    ccl_flatten_kernel<<<g, 256, 0, cs>>>(r);
     TSIM_LAUNCH_CHECK();
-    ccl_rank_kernel<<<ntiles, 256, 0, cs>>>(n, Lo, tile_count, rank, blobs, cap, err);
+    if ((st = exclusive_scan_i32(r.rank, r.cap, scan_tmp, blobs->count, cs, r.n_runs)) != TSIM_OK) return st;
+    ccl_roots_kernel<<<g, 256, 0, cs>>>(r, blobs->table, blobs->cap, r.err);
     TSIM_LAUNCH_CHECK();
-    ccl_relabel_kernel<<<div_up(warps * 32, 256), 256, 0, cs>>>(W, nrows, cfg->row0, Lo, rank, blobs, cap);
+    ccl_bbox_kernel<<<g, 256, 0, cs>>>(win.W, win.y0, r, blobs->table, blobs->cap);
+    TSIM_LAUNCH_CHECK();
+    ccl_ids_kernel<<<g, 256, 0, cs>>>(r);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
@@ -208,34 +334,48 @@ tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int32_t *L, int ta
 
 using namespace tsim;
 
-extern "C" tsim_status tsim_layout_label_nothing(const tsim_cfg *cfg, const tsim_planes *p, int32_t *blobs, int32_t cap, int32_t *n_blobs,
+extern "C" tsim_status tsim_layout_label_nothing(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs, int32_t *err_flag,
                                                  void *workspace, size_t ws_bytes, void *stream) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
-    if (!p || !p->cell_type || !p->block_id || !blobs || !n_blobs || cap < 1) { set_error("tsim_layout_label_nothing: bad arguments"); return TSIM_ERR_CONFIG; }
-    return label_type(cfg, p->cell_type, p->block_id, T_NOTHING, blobs, cap, n_blobs, workspace, ws_bytes, (cudaStream_t)stream);
+    if ((st = check_blobs(blobs, "tsim_layout_label_nothing")) != TSIM_OK) return st;
+    if (!p || !p->cell_type || !err_flag) { set_error("tsim_layout_label_nothing: NULL plane or err_flag"); return TSIM_ERR_CONFIG; }
+    return label_type(cfg, p->cell_type, T_NOTHING, blobs, err_flag, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
-extern "C" tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes *p, const int32_t *blobs, const int32_t *n_blobs,
-                                         const uint8_t *zone_by_block, int32_t n_tape, int32_t *err_flag, void *stream) {
+extern "C" tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs, const uint8_t *zone_by_block,
+                                         int32_t n_tape, int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
-    if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id || !blobs || !n_blobs || !zone_by_block || !err_flag) {
-        set_error("tsim_layout_zones: bad arguments");
-        return TSIM_ERR_CONFIG;
-    }
-    const long long n = (long long)cfg->width * cfg->rows;
-    const size_t off = (size_t)cfg->halo * cfg->width;
-    zones_fill_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(n, p->cell_type + off, p->dirs + off, p->aux + off, p->block_id + off,
-                                                                        blobs, n_blobs, zone_by_block, n_tape, err_flag);
+    if ((st = check_blobs(blobs, "tsim_layout_zones")) != TSIM_OK) return st;
+    if (!p || !p->cell_type || !p->block_id || !zone_by_block || !err_flag || n_tape < 0) { set_error("tsim_layout_zones: bad arguments"); return TSIM_ERR_CONFIG; }
+    if (((uintptr_t)p->block_id & 15) != 0) { set_error("tsim_layout_zones: block_id must be 16-byte aligned"); return TSIM_ERR_CONFIG; }
+    Runs r; int32_t *scan_tmp; uint8_t *fill;
+    if ((st = runs_layout(cfg, workspace, ws_bytes, r, scan_tmp, fill, blobs->cap)) != TSIM_OK) return st;
+    cudaStream_t cs = (cudaStream_t)stream;
+    const Win win(*cfg);
+    const long long n = win.cells();
+    zones_table_kernel<<<list_grid(blobs->cap), 256, 0, cs>>>(blobs->table, blobs->count, blobs->cap, blobs->id_base, zone_by_block, n_tape, fill, err_flag);
+    TSIM_LAUNCH_CHECK();
+    // Nothing cells carry no arrows and no aux bits (frame pass / place_cell), so only the type changes
+    ccl_labels_kernel<true><<<div_up(div_up(n, 4), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, p->block_id, p->cell_type, fill);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
 
-extern "C" tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask, int32_t *labels, int32_t *blobs, int32_t cap,
-                                       int32_t *n_blobs, void *workspace, size_t ws_bytes, void *stream) {
+extern "C" tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask, int32_t *labels, const tsim_blobs *blobs, int32_t *err_flag,
+                                       void *workspace, size_t ws_bytes, void *stream) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
-    if (!mask || !labels || !blobs || !n_blobs || cap < 1) { set_error("tsim_label_mask: bad arguments"); return TSIM_ERR_CONFIG; }
-    return label_type(cfg, mask, labels, 1, blobs, cap, n_blobs, workspace, ws_bytes, (cudaStream_t)stream);
+    if ((st = check_blobs(blobs, "tsim_label_mask")) != TSIM_OK) return st;
+    if (!mask || !labels || !err_flag || ((uintptr_t)labels & 15)) { set_error("tsim_label_mask: bad arguments"); return TSIM_ERR_CONFIG; }
+    cudaStream_t cs = (cudaStream_t)stream;
+    if ((st = label_type(cfg, mask, 1, blobs, err_flag, workspace, ws_bytes, cs)) != TSIM_OK) return st;
+    Runs r; int32_t *scan_tmp; uint8_t *fill;
+    if ((st = runs_layout(cfg, workspace, ws_bytes, r, scan_tmp, fill, blobs->cap)) != TSIM_OK) return st;
+    const Win win(*cfg);
+    const long long n = win.cells();
+    ccl_labels_kernel<false><<<div_up(div_up(n, 4), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
 }

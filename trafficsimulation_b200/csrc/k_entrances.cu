@@ -30,22 +30,28 @@ __device__ __forceinline__ void s_union(int *lab, int a, int b) {
 }
 
 __global__ void __launch_bounds__(128) entrances_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B,
-                                                        const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs,
-                                                        const int32_t *__restrict__ run_by_block, int n_tape, int32_t *entrances, int32_t *err) {
+                                                        const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs, int cap_blobs,
+                                                        const int32_t *__restrict__ id_base, const int32_t *__restrict__ run_by_block, int n_tape,
+                                                        int32_t *entrances, int32_t *err) {
     __shared__ uint8_t s_mark[ENT_CAP];
     __shared__ int s_lab[ENT_CAP];
     __shared__ int s_cnt[ENT_CAP];
     __shared__ int s_max, s_pref, s_chosen, s_warp[4], s_seen;
-    const int nb = *n_blobs;
-    const int W = c.width, H = c.height;
-    for (int b = blockIdx.x + 1; b <= nb; b += gridDim.x) {
+    const int nb = min(*n_blobs, cap_blobs);
+    const int W = c.width, H = c.win_rows;   // window-local rows throughout
+    const int base = id_base ? *id_base : 0;
+    for (int bk = blockIdx.x; bk < nb; bk += gridDim.x) {
         __syncthreads();
-        const int32_t *bl = blobs + (size_t)(b - 1) * TSIM_BLOB_STRIDE;
+        const int b = bk + 1 + base;         // block id as stored in block_id
+        const int32_t *bl = blobs + (size_t)bk * TSIM_BLOB_STRIDE;
         const int root = bl[5];
-        if (threadIdx.x == 0) entrances[b - 1] = -1;
+        if (threadIdx.x == 0) entrances[bk] = -1;
+        if (b < 1) continue;                 // cut by the window's lower edge: not owned here
         if (T[root] > T_OTH) continue;   // Empty blocks get no entrance (:902)
+        const int by0 = bl[1] - c.win_y0, by1 = bl[3] - c.win_y0;
+        if ((by0 == 0 && c.win_y0 > 0) || (by1 == H - 1 && c.win_y0 + H < c.height)) continue;   // cut by a window edge: the owner sees it whole
         if (b > n_tape) { if (threadIdx.x == 0) *err = 1; continue; }
-        const int x0 = max(bl[0] - 1, 0), y0 = max(bl[1] - 1, 0), x1 = min(bl[2] + 1, W - 1), y1 = min(bl[3] + 1, H - 1);
+        const int x0 = max(bl[0] - 1, 0), y0 = max(by0 - 1, 0), x1 = min(bl[2] + 1, W - 1), y1 = min(by1 + 1, H - 1);
         const int tw = x1 - x0 + 1, th = y1 - y0 + 1, n = tw * th;
         if (n > ENT_CAP) { if (threadIdx.x == 0) *err = 2; continue; }
         if (threadIdx.x == 0) { s_max = 0; s_pref = 0; s_chosen = -1; s_seen = 0; }
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(128) entrances_kernel(tsim_cfg c, uint8_t *T, 
             // reference's later place_cell would
             const int prev = atomicMax(B + g, b);
             if (prev <= b) { T[g] = T_BE; D[g] = 0; A[g] &= (AUX_RING | AUX_EVER); }
-            entrances[b - 1] = (int32_t)g;
+            entrances[bk] = (int32_t)g;
         }
     }
 }
@@ -141,19 +147,19 @@ __global__ void __launch_bounds__(128) entrances_kernel(tsim_cfg c, uint8_t *T, 
 
 using namespace tsim;
 
-extern "C" tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_planes *p, const int32_t *blobs, const int32_t *n_blobs,
-                                             const int32_t *run_by_block, int32_t n_tape, int32_t *entrances, int32_t *err_flag, void *stream) {
+extern "C" tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs, const int32_t *run_by_block,
+                                             int32_t n_tape, int32_t *entrances, int32_t *err_flag, void *stream) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
-    if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id || !blobs || !n_blobs || !run_by_block || !entrances || !err_flag) {
+    if ((st = check_blobs(blobs, "tsim_layout_entrances")) != TSIM_OK) return st;
+    if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id || !run_by_block || !entrances || !err_flag) {
         set_error("tsim_layout_entrances: bad arguments");
         return TSIM_ERR_CONFIG;
     }
-    if (cfg->halo != 0 || cfg->rows != cfg->height) { set_error("tsim_layout_entrances: run on the gathered grid"); return TSIM_ERR_UNSUPPORTED; }
     if (n_tape <= 0) return TSIM_OK;
-    int grid = n_tape < 148 * 64 ? n_tape : 148 * 64;
-    entrances_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs, n_blobs, run_by_block,
-                                                             n_tape, entrances, err_flag);
+    int grid = blobs->cap < 148 * 64 ? blobs->cap : 148 * 64;
+    entrances_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, blobs->count,
+                                                             blobs->cap, blobs->id_base, run_by_block, n_tape, entrances, err_flag);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

@@ -8,8 +8,8 @@
 //
 // Every one of those passes is a function of (x, y), the two band descriptors covering the cell and
 // the descriptors of its 4 neighbours, so the 13 in-place sweeps of the reference collapse into a
-// single pass that only WRITES the planes: 1 (type) + 2 (dirs) + 1 (aux) + 4 (block_id) B/cell,
-// no reads except the O(W+H) line tables (L1/L2 resident).
+// single pass that only WRITES the planes: 1 (type) + 2 (dirs) + 1 (aux) B/cell, no reads except
+// the O(W+H) line tables (L1/L2 resident).  block_id is written as a whole by the zoning pass.
 #include "cells_frame.cuh"
 
 namespace tsim {
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) frame_roads_kernel(tsim_cfg c, uint8_t *_
     const int xblocks = (W + VEC * 256 - 1) / (VEC * 256);
     const int xv = ((blockIdx.x % xblocks) * blockDim.x + threadIdx.x) * VEC;
     const int ly = blockIdx.x / xblocks;            // local row inside the shard allocation
-    const int y = c.row0 - c.halo + ly;
+    const int y = c.win_y0 + ly;
     if (xv >= W || y < 0 || y >= H) return;
     const uint32_t r0 = y > 0 ? __ldg(rowt + y - 1) : 0u, r1 = __ldg(rowt + y), r2 = y + 1 < H ? __ldg(rowt + y + 1) : 0u;
     uint32_t ce[VEC + 2];
@@ -47,11 +47,10 @@ __global__ void __launch_bounds__(256) frame_roads_kernel(tsim_cfg c, uint8_t *_
         *reinterpret_cast<uchar4 *>(T + base) = make_uchar4(tt[0], tt[1], tt[2], tt[3]);
         *reinterpret_cast<ushort4 *>(D + base) = make_ushort4(dd[0], dd[1], dd[2], dd[3]);
         *reinterpret_cast<uchar4 *>(A + base) = make_uchar4(aa[0], aa[1], aa[2], aa[3]);
-        *reinterpret_cast<int4 *>(B + base) = make_int4(0, 0, 0, 0);
     } else {
 #pragma unroll
         for (int i = 0; i < VEC; i++)
-            if (xv + i < W) { T[base + i] = tt[i]; D[base + i] = dd[i]; A[base + i] = aa[i]; B[base + i] = 0; }
+            if (xv + i < W) { T[base + i] = tt[i]; D[base + i] = dd[i]; A[base + i] = aa[i]; }
     }
 }
 
@@ -67,7 +66,7 @@ extern "C" tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_p
         return TSIM_ERR_CONFIG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int W = cfg->width, rows = cfg->rows + 2 * cfg->halo;
+    const int W = cfg->width, rows = cfg->win_rows;
     if (W % 4 == 0) {
         dim3 grid((unsigned)div_up(W, 4 * 256) * rows);
         frame_roads_kernel<4><<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, lines->row, lines->col);

@@ -609,9 +609,10 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
         set_error("traffic_light_range %d outside 0..%d", cfg->traffic_light_range, MAX_TL_RANGE);
         return TSIM_ERR_UNSUPPORTED;
     }
-    if (cfg->halo != 0 || cfg->rows != cfg->height) { set_error("tsim_layout_lights: run on the gathered grid"); return TSIM_ERR_UNSUPPORTED; }
     cudaStream_t cs = (cudaStream_t)stream;
-    const int W = cfg->width, H = cfg->height;
+    const int W = cfg->width, H = cfg->win_rows;   // window-local rows throughout
+    int mid_row = cfg->height / 2 - cfg->win_y0;   // the pivot is the first intersection at or after the grid's middle row
+    mid_row = mid_row < 0 ? 0 : (mid_row > H ? H : mid_row);
     const long long n = (long long)W * H;
     const int wp = div_up(W, 64);
     const long long nw = (long long)wp * H;
@@ -637,7 +638,7 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
     init_pivot_kernel<<<1, 1, 0, cs>>>(scal);
     TSIM_LAUNCH_CHECK();
     // 1. bit-planes + pivot
-    lights_bits_kernel<<<div_up(nw * 4, 256), 256, 0, cs>>>(W, H, p->cell_type, p->dirs, bp, (long long)(H / 2) * W, scal);
+    lights_bits_kernel<<<div_up(nw * 4, 256), 256, 0, cs>>>(W, H, p->cell_type, p->dirs, bp, (long long)mid_row * W, scal);
     TSIM_LAUNCH_CHECK();
     // 2. candidates -> compact list
     cr_bits_kernel<<<div_up(nw, 256), 256, 0, cs>>>(H, bp, cr_prefix);
@@ -677,8 +678,8 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
     TSIM_CUDA(cudaMemsetAsync(lk->inc_off, 0, (size_t)(lk->cap_lights + 1) * 4, cs));
     lights_count_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, tl_prefix, lk->ctrl_off, lk->inc_off);
     TSIM_LAUNCH_CHECK();
-    if ((st = exclusive_scan_i32(lk->ctrl_off, lk->cap_lights, scan_tmp, scal + 4, cs)) != TSIM_OK) return st;
-    if ((st = exclusive_scan_i32(lk->inc_off, lk->cap_lights, scan_tmp, scal + 5, cs)) != TSIM_OK) return st;
+    if ((st = exclusive_scan_i32(lk->ctrl_off, lk->cap_lights, scan_tmp, scal + 4, cs, lk->n_lights)) != TSIM_OK) return st;
+    if ((st = exclusive_scan_i32(lk->inc_off, lk->cap_lights, scan_tmp, scal + 5, cs, lk->n_lights)) != TSIM_OK) return st;
     close_offsets_kernel<<<1, 1, 0, cs>>>(lk->n_lights, lk->ctrl_off, lk->inc_off, scal + 4, lk->cap_lights, lk->cap_ctrl, lk->cap_inc, err_flag);
     TSIM_LAUNCH_CHECK();
     TSIM_CUDA(cudaMemsetAsync(cur_ctrl, 0, (size_t)lk->cap_lights * 4, cs));

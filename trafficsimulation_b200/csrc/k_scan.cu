@@ -33,11 +33,14 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(int ntiles, int32_t *t
     if (threadIdx.x == 0) *n_out = s_carry;
 }
 
-__global__ void __launch_bounds__(256) tile_sum_kernel(long long n, const int32_t *__restrict__ data, int32_t *__restrict__ tile_sum) {
+__global__ void __launch_bounds__(256) tile_sum_kernel(long long n, const int32_t *__restrict__ n_dev, const int32_t *__restrict__ data,
+                                                       int32_t *__restrict__ tile_sum) {
     __shared__ int s_sum;
+    if (n_dev && *n_dev < n) n = *n_dev;   // the live prefix of a capacity-sized array
+    const long long base = (long long)blockIdx.x * SCAN_TILE;
+    if (base >= n) { if (threadIdx.x == 0) tile_sum[blockIdx.x] = 0; return; }
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
-    const long long base = (long long)blockIdx.x * SCAN_TILE;
     int c = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_TILE / 256; k++) {
@@ -50,9 +53,12 @@ __global__ void __launch_bounds__(256) tile_sum_kernel(long long n, const int32_
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = s_sum;
 }
 
-__global__ void __launch_bounds__(256) tile_scan_kernel(long long n, int32_t *data, const int32_t *__restrict__ tile_off) {
+__global__ void __launch_bounds__(256) tile_scan_kernel(long long n, const int32_t *__restrict__ n_dev, int32_t *data,
+                                                        const int32_t *__restrict__ tile_off) {
     __shared__ int s_warp[8];
+    if (n_dev && *n_dev < n) n = *n_dev;
     const long long base = (long long)blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
     int running = tile_off[blockIdx.x];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int k = 0; k < SCAN_TILE / 256; k++) {
@@ -72,14 +78,14 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(long long n, int32_t *da
     }
 }
 
-tsim_status exclusive_scan_i32(int32_t *data, long long n, int32_t *tmp, int32_t *total_out, cudaStream_t cs) {
+tsim_status exclusive_scan_i32(int32_t *data, long long n, int32_t *tmp, int32_t *total_out, cudaStream_t cs, const int32_t *n_dev) {
     if (n <= 0) { TSIM_CUDA(cudaMemsetAsync(total_out, 0, 4, cs)); return TSIM_OK; }
     const int ntiles = div_up(n, SCAN_TILE);
-    tile_sum_kernel<<<ntiles, 256, 0, cs>>>(n, data, tmp);
+    tile_sum_kernel<<<ntiles, 256, 0, cs>>>(n, n_dev, data, tmp);
     TSIM_LAUNCH_CHECK();
     scan_tiles_kernel<<<1, 1024, 0, cs>>>(ntiles, tmp, total_out);
     TSIM_LAUNCH_CHECK();
-    tile_scan_kernel<<<ntiles, 256, 0, cs>>>(n, data, tmp);
+    tile_scan_kernel<<<ntiles, 256, 0, cs>>>(n, n_dev, data, tmp);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

@@ -17,10 +17,10 @@ namespace cg = cooperative_groups;
 
 namespace tsim {
 
-struct Shard {   // local row window of a shard allocation
-    int W, H, y0, nrows, ylo, yhi;   // allocation holds rows [y0, y0+nrows); this device OWNS [ylo, yhi)
+struct Shard {   // row window of a shard allocation (global row numbers)
+    int W, H, y0, nrows, ylo, yhi;   // allocation holds rows [y0, y0+nrows) = [ylo, yhi); rows outside do not exist for the call
     __host__ explicit Shard(const tsim_cfg &c) {
-        W = c.width; H = c.height; y0 = c.row0 - c.halo; nrows = c.rows + 2 * c.halo; ylo = c.row0; yhi = c.row0 + c.rows;
+        W = c.width; H = c.height; y0 = c.win_y0; nrows = c.win_rows; ylo = y0; yhi = y0 + nrows;
     }
 };
 
@@ -73,16 +73,16 @@ __device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, u
 // removal, never cause a wrong one.  A thread that removes a cell follows the stub it just exposed.
 // ------------------------------------------------------------------------------------------------
 struct CoherentView {   // L2-coherent reads (bypass L1) for planes that other SMs modify in this kernel
-    uint8_t *T; int W, H, y0;
+    uint8_t *T; int W, y0, y1;
     __device__ __forceinline__ int t(int x, int y) const {
-        return (x >= 0 && x < W && y >= 0 && y < H) ? (int)__ldcg(T + (size_t)(y - y0) * W + x) : -1;
+        return (x >= 0 && x < W && y >= y0 && y < y1) ? (int)__ldcg(T + (size_t)(y - y0) * W + x) : -1;
     }
 };
 
 __global__ void __launch_bounds__(256) dead_ends_kernel(Shard s, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *flags /* [0]=changed, [1]=sweeps */) {
     cg::grid_group grid = cg::this_grid();
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-    CoherentView v{T, s.W, s.H, s.y0};
+    CoherentView v{T, s.W, s.y0, s.y0 + s.nrows};
     int sweeps = 0;
     for (;;) {
         sweeps++;
@@ -271,9 +271,9 @@ extern "C" tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint
     if ((st = check_planes(p, "tsim_maps")) != TSIM_OK) return st;
     if (!is_road || !road_type || !intersection || !allowed_dirs) { set_error("tsim_maps: NULL output"); return TSIM_ERR_CONFIG; }
     cudaStream_t cs = (cudaStream_t)stream;
-    // maps are produced for the rows this device owns; outputs are [rows][W] starting at row0
-    const long long n = (long long)cfg->width * cfg->rows;
-    const size_t off = (size_t)cfg->halo * cfg->width;
+    // maps are produced for the whole window; outputs are [win_rows][W]
+    const long long n = (long long)cfg->width * cfg->win_rows;
+    const size_t off = 0;
     const bool aligned = (n % 16 == 0) && (off % 16 == 0) &&
                          !(((uintptr_t)is_road | (uintptr_t)road_type | (uintptr_t)intersection | (uintptr_t)allowed_dirs) & 15);
     if (aligned)

@@ -311,7 +311,7 @@ static tsim_status check_tick_args(const tsim_cfg *cfg, const tsim_light_tables 
         set_error("tick: NULL vehicle array / tape");
         return TSIM_ERR_CONFIG;
     }
-    if (cfg->halo != 0 || cfg->rows != cfg->height) { set_error("tick: sharded windows are handled by the host-side shard driver"); return TSIM_ERR_UNSUPPORTED; }
+    if (cfg->win_y0 != 0 || cfg->win_rows != cfg->height) { set_error("tick: sharded windows are handled by the host-side shard driver"); return TSIM_ERR_UNSUPPORTED; }
     return TSIM_OK;
 }
 

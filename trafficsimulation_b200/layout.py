@@ -58,7 +58,7 @@ class GpuCityLayout:
         self.cell_type = torch.empty(n, dtype=torch.uint8, device=dev)
         self.dirs = torch.empty(n, dtype=torch.int16, device=dev)      # u16 bit patterns
         self.aux = torch.empty(n, dtype=torch.uint8, device=dev)
-        self.block_id = torch.empty(n, dtype=torch.int32, device=dev)
+        self.block_id = torch.zeros(n, dtype=torch.int32, device=dev)   # written as a whole by the zoning pass
         self._planes = _lib.Planes(self.cell_type.data_ptr(), self.dirs.data_ptr(), self.aux.data_ptr(), self.block_id.data_ptr())
         ws = C.c_size_t(0)
         _lib.check(self.lib.tsim_workspace_bytes(C.byref(self.cfg), C.byref(ws)))
@@ -84,7 +84,7 @@ class GpuCityLayout:
         v = int(self.flags[0].item())
         if v:
             self.flags[0] = 0
-            raise _lib.TsimError(4 if v < 10 else 6, f"{what}: device error flag {v}")
+            raise _lib.TsimError(4 if v < 10 else 6, f"{what}: device error flag {v} (DESIGN.md §9 lists the codes)")
 
     def set_bands(self, hbands, vbands):
         """Band lists as int32 [n,4] (start, end, type 1..3, dir 0..3 or -1); city_model.py:380-394."""
@@ -102,6 +102,7 @@ class GpuCityLayout:
         cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
         self.blob_cap = cap
         self.blobs = torch.zeros(cap * BLOB_STRIDE, dtype=torch.int32, device=self.device)
+        self._blobs = _lib.Blobs(self.blobs.data_ptr(), cap, self.flags.data_ptr() + 4 * 2, 0)   # count = flags[2], id_base = NULL
         self._frame_done = False
 
     # ------------------------------------------------------------------ passes (reference names)
@@ -121,26 +122,24 @@ class GpuCityLayout:
 
     def label_nothing(self):
         """Label the current `Nothing` components; returns (n, table[n,6]) on the host (synchronises)."""
-        _lib.check(self.lib.tsim_layout_label_nothing(C.byref(self.cfg), C.byref(self._planes), _ptr(self.blobs), self.blob_cap,
-                                                      self._flag_ptr(2), _ptr(self.workspace), C.c_size_t(self.workspace.numel()),
-                                                      self._stream))
+        self._label_async()
         n = int(self.flags[2].item())
+        self._check_flag("label_nothing")
         if n > self.blob_cap:
             raise _lib.TsimError(6, f"{n} components exceed the table capacity {self.blob_cap}")
         return n, self.blobs[: n * BLOB_STRIDE].view(n, BLOB_STRIDE)
 
     def _label_async(self):
-        _lib.check(self.lib.tsim_layout_label_nothing(C.byref(self.cfg), C.byref(self._planes), _ptr(self.blobs), self.blob_cap,
-                                                      self._flag_ptr(2), _ptr(self.workspace), C.c_size_t(self.workspace.numel()),
-                                                      self._stream))
+        _lib.check(self.lib.tsim_layout_label_nothing(C.byref(self.cfg), C.byref(self._planes), C.byref(self._blobs), self._flag_ptr(0),
+                                                      _ptr(self.workspace), C.c_size_t(self.workspace.numel()), self._stream))
 
     def _carve_subblock_roads(self, tape_carve, check=True):   # city_model.py:563
         tape = tape_carve if isinstance(tape_carve, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(tape_carve, np.int32)).to(self.device)
         tape = tape.contiguous().view(-1)
         self._label_async()
         self._carve_tape = tape
-        _lib.check(self.lib.tsim_layout_carve(C.byref(self.cfg), C.byref(self._planes), C.byref(self._lines), _ptr(self.blobs),
-                                              self._flag_ptr(2), _ptr(tape), tape.numel() // 8, self._flag_ptr(0), self._stream))
+        _lib.check(self.lib.tsim_layout_carve(C.byref(self.cfg), C.byref(self._planes), C.byref(self._lines), C.byref(self._blobs),
+                                              _ptr(tape), tape.numel() // 8, self._flag_ptr(0), self._stream))
         if check:
             self._check_flag("_carve_subblock_roads")
 
@@ -148,8 +147,8 @@ class GpuCityLayout:
         z = tape_zone if isinstance(tape_zone, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(tape_zone, np.uint8)).to(self.device)
         self._zone_tape = z
         self._label_async()
-        _lib.check(self.lib.tsim_layout_zones(C.byref(self.cfg), C.byref(self._planes), _ptr(self.blobs), self._flag_ptr(2), _ptr(z),
-                                              z.numel(), self._flag_ptr(0), self._stream))
+        _lib.check(self.lib.tsim_layout_zones(C.byref(self.cfg), C.byref(self._planes), C.byref(self._blobs), _ptr(z), z.numel(),
+                                              self._flag_ptr(0), _ptr(self.workspace), C.c_size_t(self.workspace.numel()), self._stream))
         if check:
             self.n_blocks = int(self.flags[2].item())
             self._check_flag("_flood_fill_blocks_storing_data")
@@ -172,8 +171,8 @@ class GpuCityLayout:
         else:
             run = torch.from_numpy(np.ascontiguousarray(tape_entrance, np.int32)).to(self.device)
         self._run_tape = run
-        self.entrances = torch.full((max(n_tape, 1),), -1, dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.tsim_layout_entrances(C.byref(self.cfg), C.byref(self._planes), _ptr(self.blobs), self._flag_ptr(2), _ptr(run),
+        self.entrances = torch.full((self.blob_cap,), -1, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.tsim_layout_entrances(C.byref(self.cfg), C.byref(self._planes), C.byref(self._blobs), _ptr(run),
                                                   n_tape, _ptr(self.entrances), self._flag_ptr(0), self._stream))
         if check:
             self._check_flag("_final_place_block_entrances")

@@ -34,10 +34,12 @@ def light_tables_from_layout(city):
     cap = max(1024, (W * H) // 16)
     blobs = torch.zeros(cap * 6, dtype=torch.int32, device=dev)
     n = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(city.lib.tsim_label_mask(C.byref(city.cfg), C.c_void_p(mask.data_ptr()), C.c_void_p(labels.data_ptr()),
-                                        C.c_void_p(blobs.data_ptr()), cap, C.c_void_p(n.data_ptr()),
-                                        C.c_void_p(city.workspace.data_ptr()), C.c_size_t(city.workspace.numel()), city._stream))
+    bl = _lib.Blobs(blobs.data_ptr(), cap, n.data_ptr(), 0)
+    _lib.check(city.lib.tsim_label_mask(C.byref(city.cfg), C.c_void_p(mask.data_ptr()), C.c_void_p(labels.data_ptr()), C.byref(bl),
+                                        city._flag_ptr(0), C.c_void_p(city.workspace.data_ptr()), C.c_size_t(city.workspace.numel()),
+                                        city._stream))
     nc = int(n.item())
+    city._check_flag("tsim_label_mask")
     if nc > cap:
         raise _lib.TsimError(6, f"{nc} intersection clusters exceed the table capacity {cap}")
     t = city._link_tensors
@@ -65,7 +67,7 @@ class GpuTraffic:
         self.device = dev = torch.device(device)
         self.W, self.H, self.n_ticks = int(width), int(height), int(n_ticks)
         self.algo = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1}[algo]
-        self.cfg = _lib.Cfg(self.W, self.H, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, self.H, 0)
+        self.cfg = _lib.Cfg(self.W, self.H, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, self.H, 0)   # win_y0 = 0, win_rows = H
         n = self.W * self.H
         up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
         # ---- light tables
