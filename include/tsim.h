@@ -94,6 +94,11 @@ typedef struct tsim_planes {
 typedef struct tsim_lines {
     const uint32_t *row;   /* [height] */
     const uint32_t *col;   /* [width]  */
+    /* optional class tables of tsim_build_class_tables (all NULL / 0 = closed-form evaluation per cell) */
+    const uint8_t  *row_class;   /* [height] class of the descriptor triple of rows y-1, y, y+1 */
+    const uint8_t  *col_class;   /* [width]                                                     */
+    const uint32_t *lut;         /* [n_row_classes][n_col_classes]: type | aux << 8 | dirs << 16 */
+    int32_t n_row_classes, n_col_classes;
 } tsim_lines;
 
 /* component table produced by the labelling passes, one row per component of the window in raster
@@ -120,6 +125,15 @@ long long   tsim_launch_count(void);
    forced-band membership used by _override_corner_lane_dirs (:519-527) and
    _upgrade_r2_to_intersections (:859-866). */
 tsim_status tsim_build_line_table(const int32_t *bands, int32_t n_bands, int32_t len, uint32_t *out_host);
+
+/* host-side helper: away from the frame every output of tsim_layout_frame_roads is a function of the
+   band descriptors of the cell's row/column and of their two neighbours only.  This groups rows and
+   columns into classes of equal descriptor triples and tabulates the cell for every (row class, column
+   class) pair, so the kernel's bulk path is one table look-up per cell.  TSIM_ERR_CAPACITY when an axis
+   has more than 255 classes or the table exceeds lut_cap entries (the caller then passes no tables). */
+tsim_status tsim_build_class_tables(const tsim_cfg *cfg, const uint32_t *row_host, const uint32_t *col_host,
+                                    uint8_t *row_class_host, uint8_t *col_class_host, uint32_t *lut_host,
+                                    int32_t lut_cap, int32_t *n_row_classes, int32_t *n_col_classes);
 
 /* bytes of device workspace every tsim_layout_* / tsim_maps call may use */
 tsim_status tsim_workspace_bytes(const tsim_cfg *cfg, size_t *out_bytes);
@@ -164,7 +178,7 @@ tsim_status tsim_layout_upgrade_r2(const tsim_cfg *cfg, const tsim_planes *p, co
    chosen run among the longest ones; entrances[k] (k = table row) receives the cell index or -1 */
 tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs,
                                   const int32_t *run_by_block, int32_t n_tape, int32_t *entrances,
-                                  int32_t *err_flag, void *stream);
+                                  int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
 
 /* _remove_invalid_intersection_directions + _add_entrance_directions (city_model.py:969-1070), fused */
 tsim_status tsim_layout_fix_dirs(const tsim_cfg *cfg, const tsim_planes *p, void *stream);

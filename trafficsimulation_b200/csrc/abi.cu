@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
-#include "common.cuh"
+#include <map>
+#include <tuple>
+#include "cells_frame.cuh"
 
 namespace tsim {
 
@@ -90,6 +92,46 @@ extern "C" tsim_status tsim_build_line_table(const int32_t *bands, int32_t n, in
         }
         out[idx] = e;
     }
+    return TSIM_OK;
+}
+
+// classes of equal (previous, own, next) descriptor triples along one axis
+static int axis_classes(const uint32_t *tab, int len, uint8_t *cls, std::map<std::tuple<uint32_t, uint32_t, uint32_t>, int> &ids,
+                        std::tuple<uint32_t, uint32_t, uint32_t> *reps) {
+    for (int i = 0; i < len; i++) {
+        const auto key = std::make_tuple(i > 0 ? tab[i - 1] : 0u, tab[i], i + 1 < len ? tab[i + 1] : 0u);
+        auto it = ids.find(key);
+        if (it == ids.end()) {
+            if (ids.size() >= 255) return -1;
+            const int id = (int)ids.size();
+            reps[id] = key;
+            it = ids.emplace(key, id).first;
+        }
+        cls[i] = (uint8_t)it->second;
+    }
+    return (int)ids.size();
+}
+
+extern "C" tsim_status tsim_build_class_tables(const tsim_cfg *cfg, const uint32_t *row, const uint32_t *col, uint8_t *row_class,
+                                               uint8_t *col_class, uint32_t *lut, int32_t lut_cap, int32_t *n_row, int32_t *n_col) {
+    tsim_status s = check_cfg(cfg);
+    if (s != TSIM_OK) return s;
+    if (!row || !col || !row_class || !col_class || !lut || !n_row || !n_col) { set_error("tsim_build_class_tables: NULL argument"); return TSIM_ERR_CONFIG; }
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t>, int> rid, cid;
+    std::tuple<uint32_t, uint32_t, uint32_t> rrep[256], crep[256];
+    const int nr = axis_classes(row, cfg->height, row_class, rid, rrep), nc = axis_classes(col, cfg->width, col_class, cid, crep);
+    if (nr < 0 || nc < 0 || (long long)nr * nc > lut_cap) { set_error("too many band classes for the look-up table"); return TSIM_ERR_CAPACITY; }
+    const Geo g(*cfg);
+    // any cell of the bulk region stands for all of them (see bulk_* in k_frame_roads.cu)
+    const int x = g.ixmin + 6, y = g.iymin + 6;
+    for (int a = 0; a < nr; a++)
+        for (int b = 0; b < nc; b++) {
+            int t; uint32_t d, au;
+            frame_roads_cell(*cfg, g, std::get<0>(rrep[a]), std::get<1>(rrep[a]), std::get<2>(rrep[a]), std::get<0>(crep[b]), std::get<1>(crep[b]),
+                             std::get<2>(crep[b]), x, y, t, d, au);
+            lut[a * nc + b] = (uint32_t)t | (au << 8) | (d << 16);
+        }
+    *n_row = nr; *n_col = nc;
     return TSIM_OK;
 }
 

@@ -29,28 +29,24 @@ __device__ __forceinline__ void s_union(int *lab, int a, int b) {
     }
 }
 
+// big blocks (tile beyond the warp kernel's capacity): one CTA per block, from the list the warp kernel wrote
 __global__ void __launch_bounds__(128) entrances_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B,
-                                                        const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs, int cap_blobs,
-                                                        const int32_t *__restrict__ id_base, const int32_t *__restrict__ run_by_block, int n_tape,
-                                                        int32_t *entrances, int32_t *err) {
+                                                        const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_big,
+                                                        const int32_t *__restrict__ big_list, const int32_t *__restrict__ id_base,
+                                                        const int32_t *__restrict__ run_by_block, int n_tape, int32_t *entrances, int32_t *err) {
     __shared__ uint8_t s_mark[ENT_CAP];
     __shared__ int s_lab[ENT_CAP];
     __shared__ int s_cnt[ENT_CAP];
     __shared__ int s_max, s_pref, s_chosen, s_warp[4], s_seen;
-    const int nb = min(*n_blobs, cap_blobs);
+    const int nbig = *n_big;
     const int W = c.width, H = c.win_rows;   // window-local rows throughout
     const int base = id_base ? *id_base : 0;
-    for (int bk = blockIdx.x; bk < nb; bk += gridDim.x) {
+    for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
         __syncthreads();
+        const int bk = big_list[q];          // the warp kernel already applied the skip rules (:902, window cuts, tape length)
         const int b = bk + 1 + base;         // block id as stored in block_id
         const int32_t *bl = blobs + (size_t)bk * TSIM_BLOB_STRIDE;
-        const int root = bl[5];
-        if (threadIdx.x == 0) entrances[bk] = -1;
-        if (b < 1) continue;                 // cut by the window's lower edge: not owned here
-        if (T[root] > T_OTH) continue;   // Empty blocks get no entrance (:902)
         const int by0 = bl[1] - c.win_y0, by1 = bl[3] - c.win_y0;
-        if ((by0 == 0 && c.win_y0 > 0) || (by1 == H - 1 && c.win_y0 + H < c.height)) continue;   // cut by a window edge: the owner sees it whole
-        if (b > n_tape) { if (threadIdx.x == 0) *err = 1; continue; }
         const int x0 = max(bl[0] - 1, 0), y0 = max(by0 - 1, 0), x1 = min(bl[2] + 1, W - 1), y1 = min(by1 + 1, H - 1);
         const int tw = x1 - x0 + 1, th = y1 - y0 + 1, n = tw * th;
         if (n > ENT_CAP) { if (threadIdx.x == 0) *err = 2; continue; }
@@ -143,12 +139,175 @@ __global__ void __launch_bounds__(128) entrances_kernel(tsim_cfg c, uint8_t *T, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small blocks (the bounding box grown by 2 cells holds at most ENT_WCAP cells -- every block of a
+// carved city): ONE WARP per block, no CTA-wide barriers.  The tile is staged once as a 3-bit code per
+// cell (member of this block / a type _touches_road accepts / a type the road-level filter prefers), so
+// global memory is read once per tile cell; marks, run union-find, run lengths, the taped choice and the
+// median all work on the warp's shared-memory slice.
+constexpr int ENT_WCAP = 768;    // tile cells a warp can stage
+constexpr int ENT_LCAP = 384;    // marked (ring and road) cells of a tile
+constexpr int ENT_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * ENT_WARPS) entrances_warp_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B,
+                                                                        const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs,
+                                                                        int cap_blobs, const int32_t *__restrict__ id_base,
+                                                                        const int32_t *__restrict__ run_by_block, int n_tape, int32_t *entrances,
+                                                                        int32_t *n_big, int32_t *big_list, int32_t *err) {
+    __shared__ uint8_t s_code_all[ENT_WARPS][ENT_WCAP];
+    __shared__ uint8_t s_mark_all[ENT_WARPS][ENT_WCAP];
+    __shared__ int s_lab_all[ENT_WARPS][ENT_WCAP];
+    __shared__ int s_cnt_all[ENT_WARPS][ENT_WCAP];
+    __shared__ uint32_t s_list_all[ENT_WARPS][ENT_LCAP];   // marked cells in tile order: index | lx << 10 | ly << 20
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t *s_code = s_code_all[wid], *s_mark = s_mark_all[wid];
+    int *s_lab = s_lab_all[wid], *s_cnt = s_cnt_all[wid];
+    uint32_t *s_list = s_list_all[wid];
+    const int nb = min(*n_blobs, cap_blobs);
+    const int W = c.width, H = c.win_rows;   // window-local rows throughout
+    const int base = id_base ? *id_base : 0;
+    const int level = c.block_entrance_road_level;
+    const int gw = blockIdx.x * ENT_WARPS + wid, nwarps = gridDim.x * ENT_WARPS;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int bk = gw; bk < nb; bk += nwarps) {
+        __syncwarp();
+        const int b = bk + 1 + base;         // block id as stored in block_id
+        const int32_t *bl = blobs + (size_t)bk * TSIM_BLOB_STRIDE;
+        const int root = bl[5];
+        if (lane == 0) entrances[bk] = -1;
+        if (b < 1) continue;                 // cut by the window's lower edge: not owned here
+        if (T[root] > T_OTH) continue;       // Empty blocks get no entrance (:902)
+        const int by0 = bl[1] - c.win_y0, by1 = bl[3] - c.win_y0;
+        if ((by0 == 0 && c.win_y0 > 0) || (by1 == H - 1 && c.win_y0 + H < c.height)) continue;   // cut by a window edge: the owner sees it whole
+        if (b > n_tape) { if (lane == 0) *err = 1; continue; }
+        const int x0 = max(bl[0] - 2, 0), y0 = max(by0 - 2, 0), x1 = min(bl[2] + 2, W - 1), y1 = min(by1 + 2, H - 1);
+        const int tw = x1 - x0 + 1, th = y1 - y0 + 1, n = tw * th;
+        if (n > ENT_WCAP) { if (lane == 0) big_list[atomicAdd(n_big, 1)] = bk; continue; }
+        // 0. stage the tile: bit0 member of the block, bit1 _touches_road type, bit2 preferred road level
+        {
+            int ly = lane / tw, lx = lane - ly * tw;
+            for (int i = lane; i < n; i += 32) {
+                const size_t g = (size_t)(y0 + ly) * W + x0 + lx;
+                const int t = T[g];
+                uint8_t code = 0;
+                if (in_set(SET_ZONE, t)) code = (B[g] == b) ? 1 : 0;
+                else code = (in_set(SET_TOUCH_ROAD, t) ? 2 : 0) | (((t == T_R1) || (t == T_R2 && level < 2)) ? 4 : 0);
+                s_code[i] = code;
+                lx += 32;
+                while (lx >= tw) { lx -= tw; ly++; }
+            }
+        }
+        __syncwarp();
+        // 1. ring cells that touch a road (:906); bit1 = preferred by the road-level filter (:911-923); compacted in tile order
+        int nl = 0;
+        bool pref_any = false;
+        {
+            int ly = lane / tw, lx = lane - ly * tw;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                uint8_t m = 0;
+                if (i < n && !(s_code[i] & 1)) {
+                    uint8_t acc = 0;
+                    if (lx + 1 < tw) acc |= s_code[i + 1];
+                    if (lx > 0) acc |= s_code[i - 1];
+                    if (ly + 1 < th) acc |= s_code[i + tw];
+                    if (ly > 0) acc |= s_code[i - tw];
+                    if ((acc & 3) == 3) m = 1 | ((acc & 4) ? 2 : 0);
+                }
+                if (i < n) s_mark[i] = m;
+                const uint32_t bal = __ballot_sync(0xffffffffu, m != 0);
+                if (m) {
+                    const int p = nl + __popc(bal & lt_mask);
+                    if (p < ENT_LCAP) s_list[p] = (uint32_t)i | ((uint32_t)lx << 10) | ((uint32_t)ly << 20);
+                    s_lab[i] = i; s_cnt[i] = 0;
+                    pref_any |= (m & 2) != 0;
+                }
+                nl += __popc(bal);
+                lx += 32;
+                while (lx >= tw) { lx -= tw; ly++; }
+            }
+        }
+        if (nl == 0) continue;               // land-locked block (:907-908)
+        if (nl > ENT_LCAP) { if (lane == 0) big_list[atomicAdd(n_big, 1)] = bk; continue; }
+        pref_any = __any_sync(0xffffffffu, pref_any);
+        __syncwarp();
+        const uint8_t need = (level > 0 && pref_any) ? 3 : 1;
+        // 2. runs = 4-connected components of the marked cells
+        for (int p = lane; p < nl; p += 32) {
+            const uint32_t e = s_list[p];
+            const int i = e & 1023, lx = (e >> 10) & 1023, ly = e >> 20;
+            if ((s_mark[i] & need) != need) continue;
+            if (lx + 1 < tw && (s_mark[i + 1] & need) == need) s_union(s_lab, i, i + 1);
+            if (ly + 1 < th && (s_mark[i + tw] & need) == need) s_union(s_lab, i, i + tw);
+        }
+        __syncwarp();
+        for (int p = lane; p < nl; p += 32) {
+            const int i = s_list[p] & 1023;
+            if ((s_mark[i] & need) != need) continue;
+            const int r = s_find(s_lab, i);
+            s_lab[i] = r;
+            atomicAdd(s_cnt + r, 1);
+        }
+        __syncwarp();
+        int maxlen = 0;
+        for (int p = lane; p < nl; p += 32) {
+            const int i = s_list[p] & 1023;
+            if ((s_mark[i] & need) == need && s_lab[i] == i) maxlen = max(maxlen, s_cnt[i]);
+        }
+        maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+        if (maxlen == 0) continue;           // no ring cell passes the road-level filter
+        // 3. the tape's choice among the longest runs, runs ordered by their root (min (y,x) cell)
+        const int want = run_by_block[b - 1];
+        int chosen = -1, seen = 0;
+        for (int p0 = 0; p0 < nl; p0 += 32) {
+            const int p = p0 + lane;
+            const int i = p < nl ? (int)(s_list[p] & 1023) : 0;
+            const bool cand = p < nl && (s_mark[i] & need) == need && s_lab[i] == i && s_cnt[i] == maxlen;
+            const uint32_t m = __ballot_sync(0xffffffffu, cand);
+            const int k = want - seen;
+            if (k >= 0 && k < __popc(m)) {
+                uint32_t mm = m;
+                for (int j = 0; j < k; j++) mm &= mm - 1;
+                chosen = (int)(s_list[p0 + __ffs(mm) - 1] & 1023);
+                break;
+            }
+            seen += __popc(m);
+        }
+        if (chosen < 0) { if (lane == 0) *err = 3; continue; }
+        // 4. (x,y)-lexicographic element len/2 of the chosen run (:949-956): column histogram, then walk
+        __syncwarp();
+        for (int i = lane; i < tw; i += 32) s_cnt[i] = 0;   // roots' counts no longer needed
+        __syncwarp();
+        for (int p = lane; p < nl; p += 32) {
+            const uint32_t e = s_list[p];
+            const int i = e & 1023;
+            if ((s_mark[i] & need) == need && s_lab[i] == chosen) atomicAdd(s_cnt + ((e >> 10) & 1023), 1);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int k = maxlen / 2, col = 0;
+            while (k >= s_cnt[col]) { k -= s_cnt[col]; col++; }
+            int cell = -1;
+            for (int ly = 0; ly < th; ly++) {
+                const int i = ly * tw + col;
+                if ((s_mark[i] & need) == need && s_lab[i] == chosen) { if (k == 0) { cell = i; break; } k--; }
+            }
+            const size_t g = (size_t)(y0 + cell / tw) * W + x0 + cell % tw;
+            // place_cell(..., "BlockEntrance") (:959-962); the highest block id wins a shared cell, as the
+            // reference's later place_cell would
+            const int prev = atomicMax(B + g, b);
+            if (prev <= b) { T[g] = T_BE; D[g] = 0; A[g] &= (AUX_RING | AUX_EVER); }
+            entrances[bk] = (int32_t)g;
+        }
+    }
+}
+
 }  // namespace tsim
 
 using namespace tsim;
 
 extern "C" tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs, const int32_t *run_by_block,
-                                             int32_t n_tape, int32_t *entrances, int32_t *err_flag, void *stream) {
+                                             int32_t n_tape, int32_t *entrances, int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
     if ((st = check_blobs(blobs, "tsim_layout_entrances")) != TSIM_OK) return st;
@@ -156,10 +315,19 @@ extern "C" tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_pla
         set_error("tsim_layout_entrances: bad arguments");
         return TSIM_ERR_CONFIG;
     }
+    const size_t need = 256 + (size_t)blobs->cap * 4;
+    if (!workspace || ws_bytes < need) { set_error("tsim_layout_entrances needs %zu workspace bytes, got %zu", need, ws_bytes); return TSIM_ERR_WORKSPACE; }
     if (n_tape <= 0) return TSIM_OK;
-    int grid = blobs->cap < 148 * 64 ? blobs->cap : 148 * 64;
-    entrances_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, blobs->count,
-                                                             blobs->cap, blobs->id_base, run_by_block, n_tape, entrances, err_flag);
+    cudaStream_t cs = (cudaStream_t)stream;
+    int32_t *n_big = (int32_t *)workspace, *big_list = (int32_t *)((char *)workspace + 256);
+    TSIM_CUDA(cudaMemsetAsync(n_big, 0, 4, cs));
+    const int wgrid = div_up(blobs->cap, ENT_WARPS) < 148 * 6 ? div_up(blobs->cap, ENT_WARPS) : 148 * 6;   // 6 CTAs of 37 KB shared memory per SM
+    entrances_warp_kernel<<<wgrid, 32 * ENT_WARPS, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, blobs->count, blobs->cap,
+                                                            blobs->id_base, run_by_block, n_tape, entrances, n_big, big_list, err_flag);
+    TSIM_LAUNCH_CHECK();
+    const int grid = blobs->cap < 148 * 6 ? blobs->cap : 148 * 6;
+    entrances_kernel<<<grid, 128, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, n_big, big_list, blobs->id_base,
+                                           run_by_block, n_tape, entrances, err_flag);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

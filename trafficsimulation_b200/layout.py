@@ -173,7 +173,8 @@ class GpuCityLayout:
         self._run_tape = run
         self.entrances = torch.full((self.blob_cap,), -1, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.tsim_layout_entrances(C.byref(self.cfg), C.byref(self._planes), C.byref(self._blobs), _ptr(run),
-                                                  n_tape, _ptr(self.entrances), self._flag_ptr(0), self._stream))
+                                                  n_tape, _ptr(self.entrances), self._flag_ptr(0), _ptr(self.workspace),
+                                                  C.c_size_t(self.workspace.numel()), self._stream))
         if check:
             self._check_flag("_final_place_block_entrances")
 
