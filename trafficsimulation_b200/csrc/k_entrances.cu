@@ -140,6 +140,116 @@ __global__ void __launch_bounds__(128) entrances_kernel(tsim_cfg c, uint8_t *T, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Rectangular blocks (size == bounding-box area: almost every block of a city).  Their ring is the four
+// sides just outside the box, without the corners, and cells of different sides are never 4-adjacent,
+// so the runs are simply the maximal segments of road-touching cells on each side: no tile, no
+// union-find, no block_id reads.  One warp per block: lanes test the ring cells (three type loads
+// each), four ballots give the sides as bit-strings, lane 0 walks the handful of runs.
+// Anything else (non-rectangular, or a side longer than 64) goes to `gen_list` for the tile kernel.
+__device__ __forceinline__ int run_len_at(unsigned long long m, int s) {   // length of the run of ones starting at bit s
+    const unsigned long long inv = ~(m >> s);
+    const int l = inv ? __ffsll((long long)inv) - 1 : 64;
+    return min(l, 64 - s);
+}
+
+__global__ void __launch_bounds__(256) entrances_rect_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B,
+                                                             const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs, int cap_blobs,
+                                                             const int32_t *__restrict__ id_base, const int32_t *__restrict__ run_by_block, int n_tape,
+                                                             int32_t *entrances, int32_t *n_gen, int32_t *gen_list, int32_t *err) {
+    typedef unsigned long long u64;
+    const int lane = threadIdx.x & 31;
+    const int nb = min(*n_blobs, cap_blobs);
+    const int W = c.width, H = c.win_rows;   // window-local rows throughout
+    const int base = id_base ? *id_base : 0;
+    const int level = c.block_entrance_road_level;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int bk = gw; bk < nb; bk += nwarps) {
+        const int b = bk + 1 + base;         // block id as stored in block_id
+        const int32_t *bl = blobs + (size_t)bk * TSIM_BLOB_STRIDE;
+        const int root = bl[5];
+        if (lane == 0) entrances[bk] = -1;
+        if (b < 1) continue;                 // cut by the window's lower edge: not owned here
+        if (T[root] > T_OTH) continue;       // Empty blocks get no entrance (:902)
+        const int bx0 = bl[0], bx1 = bl[2], by0 = bl[1] - c.win_y0, by1 = bl[3] - c.win_y0;
+        if ((by0 == 0 && c.win_y0 > 0) || (by1 == H - 1 && c.win_y0 + H < c.height)) continue;   // cut by a window edge: the owner sees it whole
+        if (b > n_tape) { if (lane == 0) *err = 1; continue; }
+        const int w = bx1 - bx0 + 1, h = by1 - by0 + 1;
+        if ((long long)w * h != bl[4] || w > 64 || h > 64) { if (lane == 0) gen_list[atomicAdd(n_gen, 1)] = bk; continue; }
+        // sides: 0 bottom (y = by0-1), 1 left (x = bx0-1), 2 right (x = bx1+1), 3 top (y = by1+1); bit j = j-th cell from the low end
+        u64 mk[4] = {0, 0, 0, 0}, pf[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const bool horiz = (s == 0 || s == 3);
+            const int len = horiz ? w : h;
+            const int fx = s == 1 ? bx0 - 1 : (s == 2 ? bx1 + 1 : bx0), fy = s == 0 ? by0 - 1 : (s == 3 ? by1 + 1 : by0);
+            if (fx < 0 || fx >= W || fy < 0 || fy >= H) continue;   // the side lies outside the window
+            for (int j0 = 0; j0 < len; j0 += 32) {
+                const int j = j0 + lane;
+                bool touch = false, pref = false;
+                if (j < len) {
+                    const int x = horiz ? fx + j : fx, y = horiz ? fy : fy + j;
+                    // the three neighbours that are not the block itself (a zone cell is never a road)
+                    const int ox[3] = {horiz ? -1 : 0, horiz ? 1 : 0, s == 1 ? -1 : (s == 2 ? 1 : 0)};
+                    const int oy[3] = {horiz ? 0 : -1, horiz ? 0 : 1, s == 0 ? -1 : (s == 3 ? 1 : 0)};
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const int nx = x + ox[k], ny = y + oy[k];
+                        if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
+                        const int t = T[(size_t)ny * W + nx];
+                        touch |= in_set(SET_TOUCH_ROAD, t);
+                        pref |= (t == T_R1) || (t == T_R2 && level < 2);
+                    }
+                }
+                const u64 bm = __ballot_sync(0xffffffffu, touch), bp = __ballot_sync(0xffffffffu, touch && pref);
+                mk[s] |= bm << j0; pf[s] |= bp << j0;
+            }
+        }
+        if (level > 0 && (pf[0] | pf[1] | pf[2] | pf[3])) { mk[0] &= pf[0]; mk[1] &= pf[1]; mk[2] &= pf[2]; mk[3] &= pf[3]; }   // :911-923
+        if (!(mk[0] | mk[1] | mk[2] | mk[3])) continue;   // land-locked block (:907-908)
+        if (lane != 0) continue;
+        int maxlen = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            u64 m = mk[s];
+            while (m) {
+                const int st = __ffsll((long long)m) - 1, l = run_len_at(m, st);
+                maxlen = max(maxlen, l);
+                m &= ~(((l == 64) ? ~0ull : ((1ull << l) - 1ull)) << st);
+            }
+        }
+        // the tape's choice among the longest runs, in the order of their first (lowest (y, x)) cell:
+        // bottom side by x, then left / right runs by their first row (left before right), then the top side
+        const int want = run_by_block[b - 1];
+        int seen = 0, cs = -1, cst = 0;
+        auto visit = [&](int side, int st, int l) {
+            if (l == maxlen) { if (seen == want) { cs = side; cst = st; } seen++; }
+        };
+        {
+            u64 m = mk[0];
+            while (m && cs < 0) { const int st = __ffsll((long long)m) - 1, l = run_len_at(m, st); visit(0, st, l); m &= ~(((l == 64) ? ~0ull : ((1ull << l) - 1ull)) << st); }
+            u64 ml = mk[1], mr = mk[2];
+            while ((ml | mr) && cs < 0) {
+                const int sl = ml ? __ffsll((long long)ml) - 1 : 64, sr = mr ? __ffsll((long long)mr) - 1 : 64;
+                if (sl <= sr) { const int l = run_len_at(ml, sl); visit(1, sl, l); ml &= ~(((l == 64) ? ~0ull : ((1ull << l) - 1ull)) << sl); }
+                else { const int l = run_len_at(mr, sr); visit(2, sr, l); mr &= ~(((l == 64) ? ~0ull : ((1ull << l) - 1ull)) << sr); }
+            }
+            m = mk[3];
+            while (m && cs < 0) { const int st = __ffsll((long long)m) - 1, l = run_len_at(m, st); visit(3, st, l); m &= ~(((l == 64) ? ~0ull : ((1ull << l) - 1ull)) << st); }
+        }
+        if (cs < 0) { *err = 3; continue; }
+        // element len/2 of the run sorted by x (horizontal) or y (vertical) (:949-956)
+        const int off = cst + maxlen / 2;
+        const int ex = cs == 1 ? bx0 - 1 : (cs == 2 ? bx1 + 1 : bx0 + off), ey = cs == 0 ? by0 - 1 : (cs == 3 ? by1 + 1 : by0 + off);
+        const size_t g = (size_t)ey * W + ex;
+        // place_cell(..., "BlockEntrance") (:959-962); the highest block id wins a shared cell, as the
+        // reference's later place_cell would
+        const int prev = atomicMax(B + g, b);
+        if (prev <= b) { T[g] = T_BE; D[g] = 0; A[g] &= (AUX_RING | AUX_EVER); }
+        entrances[bk] = (int32_t)g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small blocks (the bounding box grown by 2 cells holds at most ENT_WCAP cells -- every block of a
 // carved city): ONE WARP per block, no CTA-wide barriers.  The tile is staged once as a 3-bit code per
 // cell (member of this block / a type _touches_road accepts / a type the road-level filter prefers), so
@@ -150,8 +260,8 @@ constexpr int ENT_LCAP = 384;    // marked (ring and road) cells of a tile
 constexpr int ENT_WARPS = 4;
 
 __global__ void __launch_bounds__(32 * ENT_WARPS) entrances_warp_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B,
-                                                                        const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs,
-                                                                        int cap_blobs, const int32_t *__restrict__ id_base,
+                                                                        const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_gen,
+                                                                        const int32_t *__restrict__ gen_list, const int32_t *__restrict__ id_base,
                                                                         const int32_t *__restrict__ run_by_block, int n_tape, int32_t *entrances,
                                                                         int32_t *n_big, int32_t *big_list, int32_t *err) {
     __shared__ uint8_t s_code_all[ENT_WARPS][ENT_WCAP];
@@ -163,23 +273,18 @@ __global__ void __launch_bounds__(32 * ENT_WARPS) entrances_warp_kernel(tsim_cfg
     uint8_t *s_code = s_code_all[wid], *s_mark = s_mark_all[wid];
     int *s_lab = s_lab_all[wid], *s_cnt = s_cnt_all[wid];
     uint32_t *s_list = s_list_all[wid];
-    const int nb = min(*n_blobs, cap_blobs);
+    const int ngen = *n_gen;
     const int W = c.width, H = c.win_rows;   // window-local rows throughout
     const int base = id_base ? *id_base : 0;
     const int level = c.block_entrance_road_level;
     const int gw = blockIdx.x * ENT_WARPS + wid, nwarps = gridDim.x * ENT_WARPS;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int bk = gw; bk < nb; bk += nwarps) {
+    for (int q = gw; q < ngen; q += nwarps) {
         __syncwarp();
+        const int bk = gen_list[q];          // the rectangle kernel already applied the skip rules (:902, window cuts, tape length)
         const int b = bk + 1 + base;         // block id as stored in block_id
         const int32_t *bl = blobs + (size_t)bk * TSIM_BLOB_STRIDE;
-        const int root = bl[5];
-        if (lane == 0) entrances[bk] = -1;
-        if (b < 1) continue;                 // cut by the window's lower edge: not owned here
-        if (T[root] > T_OTH) continue;       // Empty blocks get no entrance (:902)
         const int by0 = bl[1] - c.win_y0, by1 = bl[3] - c.win_y0;
-        if ((by0 == 0 && c.win_y0 > 0) || (by1 == H - 1 && c.win_y0 + H < c.height)) continue;   // cut by a window edge: the owner sees it whole
-        if (b > n_tape) { if (lane == 0) *err = 1; continue; }
         const int x0 = max(bl[0] - 2, 0), y0 = max(by0 - 2, 0), x1 = min(bl[2] + 2, W - 1), y1 = min(by1 + 2, H - 1);
         const int tw = x1 - x0 + 1, th = y1 - y0 + 1, n = tw * th;
         if (n > ENT_WCAP) { if (lane == 0) big_list[atomicAdd(n_big, 1)] = bk; continue; }
@@ -315,14 +420,19 @@ extern "C" tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_pla
         set_error("tsim_layout_entrances: bad arguments");
         return TSIM_ERR_CONFIG;
     }
-    const size_t need = 256 + (size_t)blobs->cap * 4;
+    const size_t need = 256 + 2 * (((size_t)blobs->cap * 4 + 255) & ~(size_t)255);
     if (!workspace || ws_bytes < need) { set_error("tsim_layout_entrances needs %zu workspace bytes, got %zu", need, ws_bytes); return TSIM_ERR_WORKSPACE; }
     if (n_tape <= 0) return TSIM_OK;
     cudaStream_t cs = (cudaStream_t)stream;
-    int32_t *n_big = (int32_t *)workspace, *big_list = (int32_t *)((char *)workspace + 256);
-    TSIM_CUDA(cudaMemsetAsync(n_big, 0, 4, cs));
+    int32_t *n_big = (int32_t *)workspace, *n_gen = n_big + 1, *big_list = (int32_t *)((char *)workspace + 256);
+    int32_t *gen_list = (int32_t *)((char *)big_list + (((size_t)blobs->cap * 4 + 255) & ~(size_t)255));
+    TSIM_CUDA(cudaMemsetAsync(n_big, 0, 8, cs));
+    const int rgrid = div_up(blobs->cap, 8) < 148 * 8 ? div_up(blobs->cap, 8) : 148 * 8;
+    entrances_rect_kernel<<<rgrid, 256, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, blobs->count, blobs->cap,
+                                                 blobs->id_base, run_by_block, n_tape, entrances, n_gen, gen_list, err_flag);
+    TSIM_LAUNCH_CHECK();
     const int wgrid = div_up(blobs->cap, ENT_WARPS) < 148 * 6 ? div_up(blobs->cap, ENT_WARPS) : 148 * 6;   // 6 CTAs of 37 KB shared memory per SM
-    entrances_warp_kernel<<<wgrid, 32 * ENT_WARPS, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, blobs->count, blobs->cap,
+    entrances_warp_kernel<<<wgrid, 32 * ENT_WARPS, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, n_gen, gen_list,
                                                             blobs->id_base, run_by_block, n_tape, entrances, n_big, big_list, err_flag);
     TSIM_LAUNCH_CHECK();
     const int grid = blobs->cap < 148 * 6 ? blobs->cap : 148 * 6;

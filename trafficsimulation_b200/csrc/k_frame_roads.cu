@@ -54,6 +54,66 @@ __global__ void __launch_bounds__(256) frame_roads_kernel(tsim_cfg c, uint8_t *_
     }
 }
 
+// Bulk region: cells whose 3x3 neighbourhood lies inside the interior and outside the forced ring-corner
+// squares (thickness <= 4) and the frame.  There the cell is a function of the descriptor triples only.
+struct Bulk {
+    int x0, x1, y0, y1;
+    __host__ __device__ explicit Bulk(const Geo &g) : x0(g.ixmin + 5), x1(g.ixmax - 5), y0(g.iymin + 5), y1(g.iymax - 5) {}
+};
+
+// 16 cells per thread.  Bulk strips: one class look-up per cell from the CTA's shared copy of the row's
+// table line, three 128-bit stores.  Everything else (the frame, ~0.5 % of a large city): closed form.
+__global__ void __launch_bounds__(256) frame_roads_lut_kernel(tsim_cfg c, uint8_t *__restrict__ T, uint16_t *__restrict__ D, uint8_t *__restrict__ A,
+                                                              const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt,
+                                                              const uint8_t *__restrict__ rowc, const uint8_t *__restrict__ colc,
+                                                              const uint32_t *__restrict__ lut, int ncc) {
+    __shared__ uint32_t s_lut[256];
+    const Geo g(c);
+    const Bulk bk(g);
+    const int W = g.W, H = g.H;
+    const int xblocks = (W + 16 * 256 - 1) / (16 * 256);
+    const int ly = blockIdx.x / xblocks;
+    const int y = c.win_y0 + ly;
+    const bool row_bulk = y >= bk.y0 && y <= bk.y1;
+    if (row_bulk) {
+        const uint32_t *line = lut + (size_t)rowc[y] * ncc;
+        for (int i = threadIdx.x; i < ncc; i += blockDim.x) s_lut[i] = line[i];
+    }
+    __syncthreads();
+    const int xv = ((blockIdx.x % xblocks) * blockDim.x + threadIdx.x) * 16;
+    if (xv >= W) return;
+    uint32_t tw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0}, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (row_bulk && xv >= bk.x0 && xv + 15 <= bk.x1) {
+        const uint4 cq = __ldg(reinterpret_cast<const uint4 *>(colc + xv));
+        const uint32_t cw[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t e = s_lut[(cw[k >> 2] >> (8 * (k & 3))) & 0xffu];
+            tw[k >> 2] |= (e & 0xffu) << (8 * (k & 3));
+            aw[k >> 2] |= ((e >> 8) & 0xffu) << (8 * (k & 3));
+            dw[k >> 1] |= (e >> 16) << (16 * (k & 1));
+        }
+    } else {
+        const uint32_t r0 = y > 0 ? __ldg(rowt + y - 1) : 0u, r1 = __ldg(rowt + y), r2 = y + 1 < H ? __ldg(rowt + y + 1) : 0u;
+        uint32_t cprev = xv > 0 ? __ldg(colt + xv - 1) : 0u, ccur = __ldg(colt + xv);
+        for (int k = 0; k < 16; k++) {   // W % 16 == 0: the strip is inside the row
+            const int x = xv + k;
+            const uint32_t cnext = x + 1 < W ? __ldg(colt + x + 1) : 0u;
+            int t; uint32_t d, a;
+            frame_roads_cell(c, g, r0, r1, r2, cprev, ccur, cnext, x, y, t, d, a);
+            tw[k >> 2] |= (uint32_t)t << (8 * (k & 3));
+            aw[k >> 2] |= a << (8 * (k & 3));
+            dw[k >> 1] |= d << (16 * (k & 1));
+            cprev = ccur; ccur = cnext;
+        }
+    }
+    const size_t base = (size_t)ly * W + xv;
+    *reinterpret_cast<uint4 *>(T + base) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+    *reinterpret_cast<uint4 *>(A + base) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+    *reinterpret_cast<uint4 *>(D + base) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+    *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+}
+
 }  // namespace tsim
 
 using namespace tsim;
@@ -67,7 +127,13 @@ extern "C" tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_p
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int W = cfg->width, rows = cfg->win_rows;
-    if (W % 4 == 0) {
+    const bool aligned = !(((uintptr_t)p->cell_type | (uintptr_t)p->dirs | (uintptr_t)p->aux) & 15);
+    if (W % 16 == 0 && aligned && lines->lut && lines->row_class && lines->col_class && lines->n_col_classes > 0 && lines->n_col_classes <= 256 &&
+        !((uintptr_t)lines->col_class & 15)) {
+        dim3 grid((unsigned)div_up(W, 16 * 256) * rows);
+        frame_roads_lut_kernel<<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, lines->row_class, lines->col_class,
+                                                     lines->lut, lines->n_col_classes);
+    } else if (W % 4 == 0) {
         dim3 grid((unsigned)div_up(W, 4 * 256) * rows);
         frame_roads_kernel<4><<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, lines->row, lines->col);
     } else {

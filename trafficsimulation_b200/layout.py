@@ -97,7 +97,23 @@ class GpuCityLayout:
         self.hbands, self.vbands = hb, vb
         self.row_table = torch.from_numpy(row.view(np.int32)).to(self.device)
         self.col_table = torch.from_numpy(col.view(np.int32)).to(self.device)
-        self._lines = _lib.Lines(self.row_table.data_ptr(), self.col_table.data_ptr())
+        # class tables for the bulk path of the frame pass (optional: too many classes -> closed form everywhere)
+        rc, cc = np.zeros(self.height, np.uint8), np.zeros(self.width, np.uint8)
+        lut = np.zeros(256 * 256, np.uint32)
+        nr, nc = C.c_int32(0), C.c_int32(0)
+        st = self.lib.tsim_build_class_tables(C.byref(self.cfg), row.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p),
+                                              rc.ctypes.data_as(C.c_void_p), cc.ctypes.data_as(C.c_void_p), lut.ctypes.data_as(C.c_void_p),
+                                              len(lut), C.byref(nr), C.byref(nc))
+        if st == 0:
+            self.row_class = torch.from_numpy(rc).to(self.device)
+            self.col_class = torch.from_numpy(cc).to(self.device)
+            self.class_lut = torch.from_numpy(lut[: nr.value * nc.value].view(np.int32)).to(self.device)
+            self._lines = _lib.Lines(self.row_table.data_ptr(), self.col_table.data_ptr(), self.row_class.data_ptr(), self.col_class.data_ptr(),
+                                     self.class_lut.data_ptr(), nr.value, nc.value)
+        elif st == 6:   # TSIM_ERR_CAPACITY: not an error, just no tables
+            self._lines = _lib.Lines(self.row_table.data_ptr(), self.col_table.data_ptr(), 0, 0, 0, 0, 0)
+        else:
+            _lib.check(st)
         # capacity of the component tables: every rectangle of the band grid can split in at most 3
         cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
         self.blob_cap = cap
