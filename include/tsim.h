@@ -198,6 +198,27 @@ typedef struct tsim_light_links {
 tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *links,
                                int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
 
+/* The stages of tsim_layout_lights, for row-band shards: `leads_to` needs reachability over the WHOLE grid, so
+   shards run prepare, agree on one pivot, then alternate tsim_lights_reach with an exchange (bitwise OR) of the
+   halo rows of the two reachability planes until no shard reports a change, then finish.
+     prepare : bit-planes + candidate list; pivot_out (device int32[2], optional) receives this window's pivot
+               candidates as window cell indices: [0] first intersection at or after the grid's middle row,
+               [1] first intersection at all (0x7fffffff = none)
+     seed    : pivot = device scalar with the window cell index of the agreed pivot (negative: outside this
+               window); NULL = use this window's own candidate
+     reach   : closure inside the window; *changed (device, optional) is set to 1 when a bit was added
+     reach_planes : byte offsets of the planes inside the workspace ([win_rows][words_per_row] uint64)
+     finish  : evaluation, light numbering, link tables, cell conversion */
+tsim_status tsim_lights_prepare(const tsim_cfg *cfg, const tsim_planes *p, int32_t *pivot_out, int32_t *err_flag,
+                                void *workspace, size_t ws_bytes, void *stream);
+tsim_status tsim_lights_seed(const tsim_cfg *cfg, const int32_t *pivot, void *workspace, size_t ws_bytes, void *stream);
+tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes,
+                              void *stream);
+tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_bytes, size_t *fw_off, size_t *bw_off,
+                                     int32_t *words_per_row);
+tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *links,
+                               int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
+
 /* _build_simple_maps (city_model.py:2151-2199) */
 tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint8_t *is_road, uint8_t *road_type,
                       uint8_t *intersection, uint8_t *allowed_dirs, void *stream);

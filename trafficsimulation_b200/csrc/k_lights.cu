@@ -168,10 +168,12 @@ __global__ void __launch_bounds__(256) bit_list_kernel(int W, int H, int wp, con
 }
 
 // ---------------------------------------------------------------- 3. reach
-__global__ void reach_seed_kernel(int W, int32_t *piv, Bits bp) {
-    int p = piv[0] != 0x7fffffff ? piv[0] : piv[1];
-    if (p == 0x7fffffff) { piv[0] = -1; return; }   // no intersection at all: every query goes to the exact search
-    piv[0] = p;
+// pivot: device scalar(s).  own == true: the candidates of lights_bits_kernel ([0] first at or after the middle row,
+// [1] first overall); own == false: one window cell index chosen by the caller (negative: the pivot lies outside this window)
+__global__ void reach_seed_kernel(int W, const int32_t *piv, bool own, Bits bp) {
+    int p = piv[0];
+    if (own) { if (p == 0x7fffffff) p = piv[1]; if (p == 0x7fffffff) return; }   // no intersection at all: every query goes to the exact search
+    if (p < 0) return;
     const int x = p % W, y = p / W;
     bp.fw[(size_t)y * bp.wp + (x >> 6)] = 1ull << (x & 63);
     bp.bw[(size_t)y * bp.wp + (x >> 6)] = 1ull << (x & 63);
@@ -316,7 +318,8 @@ __device__ bool col_closure(const Bits &bp, int H, int wx, GP *s_gp) {
 }
 
 // Persistent cooperative kernel: alternate row and column closures until an alternation changes nothing.
-__global__ void __launch_bounds__(256) reach_kernel(int H, Bits bp, int32_t *flags /* [0..2] change flags, [3] alternations */, int32_t *err) {
+__global__ void __launch_bounds__(256) reach_kernel(int H, Bits bp, int32_t *flags /* [0..2] change flags, [3] alternations */, int32_t *changed,
+                                                    int32_t *err) {
     cg::grid_group grid = cg::this_grid();
     __shared__ GP s_gp[256];
     const int lane = threadIdx.x & 31;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(256) reach_kernel(int H, Bits bp, int32_t *fla
         __threadfence();
         grid.sync();
         const int any = *((volatile int32_t *)flag);
-        if (blockIdx.x == 0 && threadIdx.x == 0) { flags[(it + 2) % 3] = 0; flags[3] = it + 1; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { flags[(it + 2) % 3] = 0; flags[3] = it + 1; if (any && changed) *changed = 1; }
         if (!any) break;
         if (it > 100000) { if (blockIdx.x == 0 && threadIdx.x == 0) *err = 12; break; }
     }
@@ -557,28 +560,45 @@ __global__ void __launch_bounds__(128) lights_fill_kernel(LightsCtx L, const int
 // Sidewalk -> TrafficLight (:1506-1509)
 __global__ void __launch_bounds__(256) tl_apply_kernel(const int32_t *__restrict__ n_lights, const int32_t *__restrict__ light_cell, int cap,
                                                        uint8_t *T, uint16_t *D, uint8_t *A) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(*n_lights, cap);
-    if (i >= n) return;
-    const int c = light_cell[i];
-    T[c] = T_TL; D[c] = 0; A[c] &= (AUX_RING | AUX_EVER);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = light_cell[i];
+        T[c] = T_TL; D[c] = 0; A[c] &= (AUX_RING | AUX_EVER);
+    }
 }
 
-// canonical order inside every light's segments (the fill order above depends on atomics)
-__global__ void __launch_bounds__(256) links_sort_kernel(const int32_t *__restrict__ n_lights, int cap, const int32_t *__restrict__ ctrl_off,
-                                                         int32_t *ctrl_cell, const int32_t *__restrict__ inc_off, int32_t *inc_cell) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= min(*n_lights, cap)) return;
-    auto isort = [](int32_t *a, int n) {
+// canonical order inside every light's segments (the fill order above depends on atomics): each thread
+// pulls its light's segment into a local array, sorts it there and writes it back once
+__device__ __forceinline__ void sort_segment(int32_t *a, int n) {
+    constexpr int LOCAL = 48;
+    if (n < 2) return;
+    if (n <= LOCAL) {
+        int32_t v[LOCAL];
+        for (int i = 0; i < n; i++) v[i] = a[i];
         for (int i = 1; i < n; i++) {
-            const int32_t v = a[i];
+            const int32_t x = v[i];
             int j = i - 1;
-            while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
-            a[j + 1] = v;
+            while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; j--; }
+            v[j + 1] = x;
         }
-    };
-    isort(ctrl_cell + ctrl_off[l], ctrl_off[l + 1] - ctrl_off[l]);
-    isort(inc_cell + inc_off[l], inc_off[l + 1] - inc_off[l]);
+        for (int i = 0; i < n; i++) a[i] = v[i];
+    } else {
+        for (int i = 1; i < n; i++) {
+            const int32_t x = a[i];
+            int j = i - 1;
+            while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; j--; }
+            a[j + 1] = x;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) links_sort_kernel(const int32_t *__restrict__ n_lights, int cap, const int32_t *__restrict__ ctrl_off,
+                                                         int32_t *ctrl_cell, const int32_t *__restrict__ inc_off, int32_t *inc_cell) {
+    const int n = min(*n_lights, cap);
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
+        sort_segment(ctrl_cell + ctrl_off[l], ctrl_off[l + 1] - ctrl_off[l]);
+        sort_segment(inc_cell + inc_off[l], inc_off[l + 1] - inc_off[l]);
+    }
 }
 
 __global__ void close_offsets_kernel(const int32_t *n_lights, int32_t *ctrl_off, int32_t *inc_off, const int32_t *totals, int cap_lights,
@@ -595,73 +615,145 @@ __global__ void close_offsets_kernel(const int32_t *n_lights, int32_t *ctrl_off,
 
 using namespace tsim;
 
-extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag,
-                                          void *workspace, size_t ws_bytes, void *stream) {
+struct LightsWs {   // fixed part of the workspace, shared by the three stages
+    int32_t *scal;   // [0..1] pivot candidates, [4..5] link totals, [8..11] reach flags, [12] n_cr
+    Bits bp;
+    int32_t *cr_prefix, *tl_prefix, *scan_tmp, *cr_cell;
+    u64 *rec;
+    int W, H, wp, cap_cr;
+    long long n, nw;
+    size_t end;      // first free byte after the fixed part
+};
+
+static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_bytes, LightsWs &L) {
+    L.W = cfg->width; L.H = cfg->win_rows;   // window-local rows throughout
+    L.n = (long long)L.W * L.H;
+    L.wp = div_up(L.W, 64);
+    L.nw = (long long)L.wp * L.H;
+    L.cap_cr = (int)(L.n / 4 + 1024);
+    char *w = (char *)workspace;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
+    L.scal = (int32_t *)take(64 * 4);
+    u64 **planes[] = {&L.bp.aN, &L.bp.aE, &L.bp.aS, &L.bp.aW, &L.bp.I, &L.bp.R, &L.bp.fw, &L.bp.bw, &L.bp.cr, &L.bp.tl};
+    for (u64 **pl : planes) *pl = (u64 *)take((size_t)L.nw * 8);
+    L.bp.wp = L.wp;
+    L.cr_prefix = (int32_t *)take((size_t)L.nw * 4);
+    L.tl_prefix = (int32_t *)take((size_t)L.nw * 4);
+    L.scan_tmp = (int32_t *)take((size_t)(div_up(L.nw, SCAN_TILE) + 1) * 4);
+    L.cr_cell = (int32_t *)take((size_t)L.cap_cr * 4);
+    L.rec = (u64 *)take((size_t)L.cap_cr * 8);
+    L.end = o;
+    if (!workspace || o > ws_bytes) { set_error("the lights pass needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
+    return TSIM_OK;
+}
+
+static tsim_status lights_check(const tsim_cfg *cfg) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
-    if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id || !lk || !err_flag || !lk->n_lights || !lk->light_cell || !lk->ctrl_off ||
-        !lk->ctrl_cell || !lk->inc_off || !lk->inc_cell) {
-        set_error("tsim_layout_lights: bad arguments");
-        return TSIM_ERR_CONFIG;
-    }
     if (cfg->forward_traffic_light_range) { set_error("forward_traffic_light_range is not implemented on the GPU path"); return TSIM_ERR_UNSUPPORTED; }
     if (cfg->traffic_light_range < 0 || cfg->traffic_light_range > MAX_TL_RANGE) {
         set_error("traffic_light_range %d outside 0..%d", cfg->traffic_light_range, MAX_TL_RANGE);
         return TSIM_ERR_UNSUPPORTED;
     }
-    cudaStream_t cs = (cudaStream_t)stream;
-    const int W = cfg->width, H = cfg->win_rows;   // window-local rows throughout
-    int mid_row = cfg->height / 2 - cfg->win_y0;   // the pivot is the first intersection at or after the grid's middle row
-    mid_row = mid_row < 0 ? 0 : (mid_row > H ? H : mid_row);
-    const long long n = (long long)W * H;
-    const int wp = div_up(W, 64);
-    const long long nw = (long long)wp * H;
-    const int cap_cr = (int)(n / 4 + 1024);
-    // workspace layout
-    char *w = (char *)workspace;
-    size_t o = 0;
-    auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
-    int32_t *scal = (int32_t *)take(64 * 4);   // [0..1] pivot, [4..5] link totals, [8..11] reach flags, [12] n_cr
-    Bits bp;
-    u64 **planes[] = {&bp.aN, &bp.aE, &bp.aS, &bp.aW, &bp.I, &bp.R, &bp.fw, &bp.bw, &bp.cr, &bp.tl};
-    for (u64 **pl : planes) *pl = (u64 *)take((size_t)nw * 8);
-    bp.wp = wp;
-    int32_t *cr_prefix = (int32_t *)take((size_t)nw * 4), *tl_prefix = (int32_t *)take((size_t)nw * 4);
-    int32_t *scan_tmp = (int32_t *)take((size_t)(div_up(nw > lk->cap_lights ? nw : lk->cap_lights, SCAN_TILE) + 1) * 4);
-    int32_t *cr_cell = (int32_t *)take((size_t)cap_cr * 4);
-    u64 *rec = (u64 *)take((size_t)cap_cr * 8);
-    int32_t *cur_ctrl = (int32_t *)take((size_t)lk->cap_lights * 4), *cur_inc = (int32_t *)take((size_t)lk->cap_lights * 4);
-    if (!workspace || o > ws_bytes) { set_error("tsim_layout_lights needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
-    int32_t *n_cr = scal + 12;
+    return TSIM_OK;
+}
 
-    TSIM_CUDA(cudaMemsetAsync(scal, 0, 64 * 4, cs));
-    init_pivot_kernel<<<1, 1, 0, cs>>>(scal);
+// stage 1: bit-planes, pivot candidates, compact candidate list
+extern "C" tsim_status tsim_lights_prepare(const tsim_cfg *cfg, const tsim_planes *p, int32_t *pivot_out, int32_t *err_flag, void *workspace,
+                                           size_t ws_bytes, void *stream) {
+    tsim_status st = lights_check(cfg);
+    if (st != TSIM_OK) return st;
+    if (!p || !p->cell_type || !p->dirs || !err_flag) { set_error("tsim_lights_prepare: bad arguments"); return TSIM_ERR_CONFIG; }
+    LightsWs L;
+    if ((st = lights_ws(cfg, workspace, ws_bytes, L)) != TSIM_OK) return st;
+    cudaStream_t cs = (cudaStream_t)stream;
+    int mid_row = cfg->height / 2 - cfg->win_y0;   // the pivot is the first intersection at or after the grid's middle row
+    mid_row = mid_row < 0 ? 0 : (mid_row > L.H ? L.H : mid_row);
+    TSIM_CUDA(cudaMemsetAsync(L.scal, 0, 64 * 4, cs));
+    init_pivot_kernel<<<1, 1, 0, cs>>>(L.scal);
     TSIM_LAUNCH_CHECK();
-    // 1. bit-planes + pivot
-    lights_bits_kernel<<<div_up(nw * 4, 256), 256, 0, cs>>>(W, H, p->cell_type, p->dirs, bp, (long long)mid_row * W, scal);
+    lights_bits_kernel<<<div_up(L.nw * 4, 256), 256, 0, cs>>>(L.W, L.H, p->cell_type, p->dirs, L.bp, (long long)mid_row * L.W, L.scal);
     TSIM_LAUNCH_CHECK();
-    // 2. candidates -> compact list
-    cr_bits_kernel<<<div_up(nw, 256), 256, 0, cs>>>(H, bp, cr_prefix);
+    cr_bits_kernel<<<div_up(L.nw, 256), 256, 0, cs>>>(L.H, L.bp, L.cr_prefix);
     TSIM_LAUNCH_CHECK();
-    if ((st = exclusive_scan_i32(cr_prefix, nw, scan_tmp, n_cr, cs)) != TSIM_OK) return st;
-    bit_list_kernel<<<div_up(nw, 256), 256, 0, cs>>>(W, H, wp, bp.cr, cr_prefix, cr_cell, cap_cr, err_flag, 23);
+    if ((st = exclusive_scan_i32(L.cr_prefix, L.nw, L.scan_tmp, L.scal + 12, cs)) != TSIM_OK) return st;
+    bit_list_kernel<<<div_up(L.nw, 256), 256, 0, cs>>>(L.W, L.H, L.wp, L.bp.cr, L.cr_prefix, L.cr_cell, L.cap_cr, err_flag, 23);
     TSIM_LAUNCH_CHECK();
-    // 3. reach
-    reach_seed_kernel<<<1, 1, 0, cs>>>(W, scal, bp);
+    if (pivot_out) TSIM_CUDA(cudaMemcpyAsync(pivot_out, L.scal, 8, cudaMemcpyDeviceToDevice, cs));
+    return TSIM_OK;
+}
+
+// stage 2a: seed the reachability planes.  pivot == NULL: this window's own candidate (single device).
+extern "C" tsim_status tsim_lights_seed(const tsim_cfg *cfg, const int32_t *pivot, void *workspace, size_t ws_bytes, void *stream) {
+    tsim_status st = lights_check(cfg);
+    if (st != TSIM_OK) return st;
+    LightsWs L;
+    if ((st = lights_ws(cfg, workspace, ws_bytes, L)) != TSIM_OK) return st;
+    reach_seed_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(L.W, pivot ? pivot : L.scal, pivot == nullptr, L.bp);
     TSIM_LAUNCH_CHECK();
-    {
-        int dev = 0, sms = 0, per_sm = 0;
-        TSIM_CUDA(cudaGetDevice(&dev));
-        TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reach_kernel, 256, 0));
-        int grid = sms * (per_sm < 1 ? 1 : per_sm);
-        const int want = div_up(H, 8) > wp ? div_up(H, 8) : wp;   // 8 rows per CTA in the row sweep, one word column per CTA in the column sweep
-        if (grid > want) grid = want;
-        int Hv = H;
-        int32_t *flags = scal + 8;
-        void *args[] = {&Hv, &bp, &flags, &err_flag};
-        TSIM_COOP_LAUNCH(reach_kernel, dim3(grid), dim3(256), args, cs);
+    return TSIM_OK;
+}
+
+// stage 2b: closure of the planes inside this window; *changed (device, optional) is set to 1 if a bit was added
+extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream) {
+    tsim_status st = lights_check(cfg);
+    if (st != TSIM_OK) return st;
+    if (!err_flag) { set_error("tsim_lights_reach: NULL err_flag"); return TSIM_ERR_CONFIG; }
+    LightsWs L;
+    if ((st = lights_ws(cfg, workspace, ws_bytes, L)) != TSIM_OK) return st;
+    cudaStream_t cs = (cudaStream_t)stream;
+    int dev = 0, sms = 0, per_sm = 0;
+    TSIM_CUDA(cudaGetDevice(&dev));
+    TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reach_kernel, 256, 0));
+    int grid = sms * (per_sm < 1 ? 1 : per_sm);
+    const int want = div_up(L.H, 8) > L.wp ? div_up(L.H, 8) : L.wp;   // 8 rows per CTA in the row sweep, one word column per CTA in the column sweep
+    if (grid > want) grid = want;
+    int32_t *flags = L.scal + 8;
+    TSIM_CUDA(cudaMemsetAsync(flags, 0, 16, cs));
+    void *args[] = {&L.H, &L.bp, &flags, &changed, &err_flag};
+    TSIM_COOP_LAUNCH(reach_kernel, dim3(grid), dim3(256), args, cs);
+    return TSIM_OK;
+}
+
+// byte offsets of the two reachability planes inside the workspace ([win_rows][words_per_row] uint64, bit x & 63 of
+// word x >> 6 = cell x), so that shards can exchange (OR) their halo rows between tsim_lights_reach calls
+extern "C" tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_bytes, size_t *fw_off, size_t *bw_off, int32_t *words_per_row) {
+    tsim_status st = lights_check(cfg);
+    if (st != TSIM_OK) return st;
+    if (!fw_off || !bw_off || !words_per_row) { set_error("tsim_lights_reach_planes: NULL output"); return TSIM_ERR_CONFIG; }
+    LightsWs L;
+    char dummy;
+    if ((st = lights_ws(cfg, &dummy, ws_bytes, L)) != TSIM_OK) return st;
+    *fw_off = (size_t)((char *)L.bp.fw - &dummy); *bw_off = (size_t)((char *)L.bp.bw - &dummy); *words_per_row = L.wp;
+    return TSIM_OK;
+}
+
+// stage 3: evaluate the candidates, number the lights, build the link tables, convert the cells
+extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
+                                          size_t ws_bytes, void *stream) {
+    tsim_status st = lights_check(cfg);
+    if (st != TSIM_OK) return st;
+    if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id || !lk || !err_flag || !lk->n_lights || !lk->light_cell || !lk->ctrl_off ||
+        !lk->ctrl_cell || !lk->inc_off || !lk->inc_cell) {
+        set_error("tsim_lights_finish: bad arguments");
+        return TSIM_ERR_CONFIG;
     }
+    LightsWs ws;
+    if ((st = lights_ws(cfg, workspace, ws_bytes, ws)) != TSIM_OK) return st;
+    char *w = (char *)workspace;
+    size_t o = ws.end;
+    auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
+    int32_t *scan_tmp = (int32_t *)take((size_t)(div_up(ws.nw > lk->cap_lights ? ws.nw : lk->cap_lights, SCAN_TILE) + 1) * 4);
+    int32_t *cur_ctrl = (int32_t *)take((size_t)lk->cap_lights * 4), *cur_inc = (int32_t *)take((size_t)lk->cap_lights * 4);
+    if (o > ws_bytes) { set_error("tsim_lights_finish needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
+    cudaStream_t cs = (cudaStream_t)stream;
+    const int W = ws.W, H = ws.H, wp = ws.wp, cap_cr = ws.cap_cr;
+    const long long nw = ws.nw;
+    const Bits &bp = ws.bp;
+    int32_t *scal = ws.scal, *n_cr = ws.scal + 12, *cr_cell = ws.cr_cell, *tl_prefix = ws.tl_prefix;
+    u64 *rec = ws.rec;
     // 4. evaluate every candidate once (launch covers the capacity; threads beyond *n_cr exit)
     const int list_grid = div_up(cap_cr, 128) < 148 * 16 ? div_up(cap_cr, 128) : 148 * 16;   // grid-stride over the compact list
     LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, p->cell_type, p->dirs, bp, err_flag};
@@ -687,9 +779,18 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
     lights_fill_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, tl_prefix, p->cell_type, p->aux, p->block_id, cur_ctrl, cur_inc,
                                                             lk->ctrl_off, lk->inc_off, lk->ctrl_cell, lk->inc_cell, lk->cap_ctrl, lk->cap_inc);
     TSIM_LAUNCH_CHECK();
-    tl_apply_kernel<<<div_up(lk->cap_lights, 256), 256, 0, cs>>>(lk->n_lights, lk->light_cell, lk->cap_lights, p->cell_type, p->dirs, p->aux);
+    tl_apply_kernel<<<(div_up(lk->cap_lights, 256) < 148 * 8 ? div_up(lk->cap_lights, 256) : 148 * 8), 256, 0, cs>>>(lk->n_lights, lk->light_cell, lk->cap_lights, p->cell_type, p->dirs, p->aux);
     TSIM_LAUNCH_CHECK();
-    links_sort_kernel<<<div_up(lk->cap_lights, 256), 256, 0, cs>>>(lk->n_lights, lk->cap_lights, lk->ctrl_off, lk->ctrl_cell, lk->inc_off, lk->inc_cell);
+    links_sort_kernel<<<(div_up(lk->cap_lights, 128) < 148 * 16 ? div_up(lk->cap_lights, 128) : 148 * 16), 128, 0, cs>>>(lk->n_lights, lk->cap_lights, lk->ctrl_off, lk->ctrl_cell, lk->inc_off, lk->inc_cell);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag,
+                                          void *workspace, size_t ws_bytes, void *stream) {
+    tsim_status st;
+    if ((st = tsim_lights_prepare(cfg, p, nullptr, err_flag, workspace, ws_bytes, stream)) != TSIM_OK) return st;
+    if ((st = tsim_lights_seed(cfg, nullptr, workspace, ws_bytes, stream)) != TSIM_OK) return st;
+    if ((st = tsim_lights_reach(cfg, nullptr, err_flag, workspace, ws_bytes, stream)) != TSIM_OK) return st;
+    return tsim_lights_finish(cfg, p, lk, err_flag, workspace, ws_bytes, stream);
 }

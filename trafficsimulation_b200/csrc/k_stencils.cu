@@ -73,16 +73,21 @@ __device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, u
 // removal, never cause a wrong one.  A thread that removes a cell follows the stub it just exposed.
 // ------------------------------------------------------------------------------------------------
 struct CoherentView {   // L2-coherent reads (bypass L1) for planes that other SMs modify in this kernel
-    uint8_t *T; int W, y0, y1;
+    uint8_t *T; int W, H, y0, y1;
+    // A row outside the window but inside the grid is UNKNOWN here: it counts as a (non-removable) road, so a
+    // cell next to a shard cut is never removed on missing information -- at worst its removal waits for the
+    // halo exchange (removal is monotone, so waiting never changes the fixed point).
     __device__ __forceinline__ int t(int x, int y) const {
-        return (x >= 0 && x < W && y >= y0 && y < y1) ? (int)__ldcg(T + (size_t)(y - y0) * W + x) : -1;
+        if (x < 0 || x >= W || y < 0 || y >= H) return -1;
+        if (y < y0 || y >= y1) return T_R1;
+        return (int)__ldcg(T + (size_t)(y - y0) * W + x);
     }
 };
 
 __global__ void __launch_bounds__(256) dead_ends_kernel(Shard s, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *flags /* [0]=changed, [1]=sweeps */) {
     cg::grid_group grid = cg::this_grid();
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-    CoherentView v{T, s.W, s.y0, s.y0 + s.nrows};
+    CoherentView v{T, s.W, s.H, s.y0, s.y0 + s.nrows};
     int sweeps = 0;
     for (;;) {
         sweeps++;

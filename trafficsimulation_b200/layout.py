@@ -41,19 +41,23 @@ class GpuCityLayout:
                  optimized_intersections=True, carve_subblock_roads=False, subblock_roads_have_intersections=True,
                  subblock_road_type="R3", min_subblock_spacing=5, traffic_light_range=10,
                  forward_traffic_light_range=False, forward_traffic_light_range_intersections="Skip",
-                 block_entrance_road_level=0, device="cuda:0", **_unused_reference_kwargs):
+                 block_entrance_road_level=0, device="cuda:0", win_y0=0, win_rows=None, **_unused_reference_kwargs):
+        """``win_y0`` / ``win_rows``: this object holds only the global rows [win_y0, win_y0 + win_rows) of the
+        width x height city (a row-band shard window, see sharded.py); default = the whole grid."""
         if not torch.cuda.is_available():
             raise RuntimeError("trafficsimulation_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.width, self.height = int(width), int(height)
+        self.win_y0 = int(win_y0)
+        self.win_rows = int(self.height - self.win_y0 if win_rows is None else win_rows)
         self.carve_subblock_roads = bool(carve_subblock_roads)
         self.cfg = _lib.Cfg(self.width, self.height, wall_thickness, sidewalk_ring_width, ROAD_CODE[ring_road_type],
                             int(optimized_intersections), int(subblock_roads_have_intersections),
                             ROAD_CODE[subblock_road_type], min_subblock_spacing, traffic_light_range,
                             int(forward_traffic_light_range), FORWARD_MODES.index(forward_traffic_light_range_intersections),
-                            block_entrance_road_level, 0, self.height, 0)
-        n = self.width * self.height
+                            block_entrance_road_level, self.win_y0, self.win_rows, 0)
+        n = self.width * self.win_rows
         dev = self.device
         self.cell_type = torch.empty(n, dtype=torch.uint8, device=dev)
         self.dirs = torch.empty(n, dtype=torch.int16, device=dev)      # u16 bit patterns
@@ -63,7 +67,8 @@ class GpuCityLayout:
         ws = C.c_size_t(0)
         _lib.check(self.lib.tsim_workspace_bytes(C.byref(self.cfg), C.byref(ws)))
         self.workspace = torch.empty(ws.value, dtype=torch.uint8, device=dev)
-        self.flags = torch.zeros(16, dtype=torch.int32, device=dev)   # [0] err flag, [1] sweeps, [2] n_blobs, [3] n_lights
+        # [0] err flag, [1] sweeps, [2] n_blobs, [3] n_lights, [4] id_base, [8..9] pivot candidates, [10] pivot, [11] reach changed
+        self.flags = torch.zeros(16, dtype=torch.int32, device=dev)
         self.blobs = None
         self.n_blocks = 0
         self.entrances = None
@@ -116,9 +121,11 @@ class GpuCityLayout:
             _lib.check(st)
         # capacity of the component tables: every rectangle of the band grid can split in at most 3
         cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+        if self.win_rows < self.height:   # a window sees its share of the band grid (plus slack for cut components)
+            cap = int(cap * min(1.0, 1.5 * self.win_rows / self.height)) + 4 * (len(vb) + 2) + 64
         self.blob_cap = cap
         self.blobs = torch.zeros(cap * BLOB_STRIDE, dtype=torch.int32, device=self.device)
-        self._blobs = _lib.Blobs(self.blobs.data_ptr(), cap, self.flags.data_ptr() + 4 * 2, 0)   # count = flags[2], id_base = NULL
+        self._blobs = _lib.Blobs(self.blobs.data_ptr(), cap, self.flags.data_ptr() + 4 * 2, self.flags.data_ptr() + 4 * 4)   # count = flags[2], id_base = flags[4]
         self._frame_done = False
 
     # ------------------------------------------------------------------ passes (reference names)
@@ -149,20 +156,22 @@ class GpuCityLayout:
         _lib.check(self.lib.tsim_layout_label_nothing(C.byref(self.cfg), C.byref(self._planes), C.byref(self._blobs), self._flag_ptr(0),
                                                       _ptr(self.workspace), C.c_size_t(self.workspace.numel()), self._stream))
 
-    def _carve_subblock_roads(self, tape_carve, check=True):   # city_model.py:563
+    def _carve_subblock_roads(self, tape_carve, check=True, relabel=True):   # city_model.py:563
         tape = tape_carve if isinstance(tape_carve, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(tape_carve, np.int32)).to(self.device)
         tape = tape.contiguous().view(-1)
-        self._label_async()
+        if relabel:
+            self._label_async()
         self._carve_tape = tape
         _lib.check(self.lib.tsim_layout_carve(C.byref(self.cfg), C.byref(self._planes), C.byref(self._lines), C.byref(self._blobs),
                                               _ptr(tape), tape.numel() // 8, self._flag_ptr(0), self._stream))
         if check:
             self._check_flag("_carve_subblock_roads")
 
-    def _flood_fill_blocks_storing_data(self, tape_zone, check=True):   # city_model.py:742
+    def _flood_fill_blocks_storing_data(self, tape_zone, check=True, relabel=True):   # city_model.py:742
         z = tape_zone if isinstance(tape_zone, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(tape_zone, np.uint8)).to(self.device)
         self._zone_tape = z
-        self._label_async()
+        if relabel:
+            self._label_async()
         _lib.check(self.lib.tsim_layout_zones(C.byref(self.cfg), C.byref(self._planes), C.byref(self._blobs), _ptr(z), z.numel(),
                                               self._flag_ptr(0), _ptr(self.workspace), C.c_size_t(self.workspace.numel()), self._stream))
         if check:
@@ -187,7 +196,8 @@ class GpuCityLayout:
         else:
             run = torch.from_numpy(np.ascontiguousarray(tape_entrance, np.int32)).to(self.device)
         self._run_tape = run
-        self.entrances = torch.full((self.blob_cap,), -1, dtype=torch.int32, device=self.device)
+        if self.entrances is None or self.entrances.numel() != self.blob_cap:   # rows < n_blocks are rewritten by every call
+            self.entrances = torch.full((self.blob_cap,), -1, dtype=torch.int32, device=self.device)
         _lib.check(self.lib.tsim_layout_entrances(C.byref(self.cfg), C.byref(self._planes), C.byref(self._blobs), _ptr(run),
                                                   n_tape, _ptr(self.entrances), self._flag_ptr(0), _ptr(self.workspace),
                                                   C.c_size_t(self.workspace.numel()), self._stream))
@@ -201,23 +211,54 @@ class GpuCityLayout:
         _lib.check(self.lib.tsim_layout_fix_dirs(C.byref(self.cfg), C.byref(self._planes), self._stream))
         self._fix_pending = False
 
-    def _add_traffic_lights(self, check=True):   # city_model.py:1422
-        n = self.width * self.height
-        cap_l, cap_c, cap_i = max(1024, n // 12), max(1024, n // 8), max(4096, n)
+    def _lights_prepare(self):
+        _lib.check(self.lib.tsim_lights_prepare(C.byref(self.cfg), C.byref(self._planes), self._flag_ptr(8), self._flag_ptr(0), _ptr(self.workspace),
+                                                C.c_size_t(self.workspace.numel()), self._stream))
+
+    def _lights_seed(self):   # flags[10] = window cell of the agreed pivot (negative: outside)
+        _lib.check(self.lib.tsim_lights_seed(C.byref(self.cfg), self._flag_ptr(10), _ptr(self.workspace), C.c_size_t(self.workspace.numel()), self._stream))
+
+    def _lights_reach(self):  # flags[11] is set when a bit was added
+        _lib.check(self.lib.tsim_lights_reach(C.byref(self.cfg), self._flag_ptr(11), self._flag_ptr(0), _ptr(self.workspace),
+                                              C.c_size_t(self.workspace.numel()), self._stream))
+
+    def reach_planes(self):
+        """The two reachability bit-planes inside the workspace as int64 tensors [win_rows, words_per_row]."""
+        fw, bw, wp = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
+        _lib.check(self.lib.tsim_lights_reach_planes(C.byref(self.cfg), C.c_size_t(self.workspace.numel()), C.byref(fw), C.byref(bw), C.byref(wp)))
+        nb = self.win_rows * wp.value * 8
+        return (self.workspace[fw.value: fw.value + nb].view(torch.int64).view(self.win_rows, wp.value),
+                self.workspace[bw.value: bw.value + nb].view(torch.int64).view(self.win_rows, wp.value))
+
+    def _lights_finish(self, check=True):
+        lk = self._links_struct()
+        _lib.check(self.lib.tsim_lights_finish(C.byref(self.cfg), C.byref(self._planes), C.byref(lk), self._flag_ptr(0), _ptr(self.workspace),
+                                               C.c_size_t(self.workspace.numel()), self._stream))
+        if check:
+            self._check_flag("_add_traffic_lights")
+
+    def _links_struct(self):
+        n = self.width * self.win_rows
+        cap_l, cap_c, cap_i = max(1024, n // 16), max(1024, n // 8), max(4096, n // 2)
         dev = self.device
-        t = dict(n_lights=self.flags[3:4], light_cell=torch.empty(cap_l, dtype=torch.int32, device=dev),
-                 ctrl_off=torch.empty(cap_l + 1, dtype=torch.int32, device=dev), ctrl_cell=torch.empty(cap_c, dtype=torch.int32, device=dev),
-                 inc_off=torch.empty(cap_l + 1, dtype=torch.int32, device=dev), inc_cell=torch.empty(cap_i, dtype=torch.int32, device=dev))
-        self._link_tensors = t
-        lk = _lib.LightLinks(self._flag_ptr(3), t["light_cell"].data_ptr(), t["ctrl_off"].data_ptr(), t["ctrl_cell"].data_ptr(),
-                             t["inc_off"].data_ptr(), t["inc_cell"].data_ptr(), cap_l, cap_c, cap_i)
+        t = getattr(self, "_link_tensors", None)
+        if t is None:   # allocated once, reused by every call
+            t = dict(n_lights=self.flags[3:4], light_cell=torch.empty(cap_l, dtype=torch.int32, device=dev),
+                     ctrl_off=torch.empty(cap_l + 1, dtype=torch.int32, device=dev), ctrl_cell=torch.empty(cap_c, dtype=torch.int32, device=dev),
+                     inc_off=torch.empty(cap_l + 1, dtype=torch.int32, device=dev), inc_cell=torch.empty(cap_i, dtype=torch.int32, device=dev))
+            self._link_tensors = t
+        return _lib.LightLinks(self._flag_ptr(3), t["light_cell"].data_ptr(), t["ctrl_off"].data_ptr(), t["ctrl_cell"].data_ptr(),
+                               t["inc_off"].data_ptr(), t["inc_cell"].data_ptr(), cap_l, cap_c, cap_i)
+
+    def _add_traffic_lights(self, check=True):   # city_model.py:1422
+        lk = self._links_struct()
         _lib.check(self.lib.tsim_layout_lights(C.byref(self.cfg), C.byref(self._planes), C.byref(lk), self._flag_ptr(0), _ptr(self.workspace),
                                                C.c_size_t(self.workspace.numel()), self._stream))
         if check:
             self._check_flag("_add_traffic_lights")
 
     def _build_simple_maps(self):   # city_model.py:2151
-        n = self.width * self.height
+        n = self.width * self.win_rows
         if self.maps is None:
             self.maps = {k: torch.empty(n, dtype=torch.uint8, device=self.device)
                          for k in ("is_road_map", "road_type_map", "intersection_map", "allowed_dirs_map")}
@@ -245,14 +286,14 @@ class GpuCityLayout:
 
     # ------------------------------------------------------------------ read-back
     def planes_host(self):
-        H, W = self.height, self.width
+        H, W = self.win_rows, self.width
         return {"cell_type": self.cell_type.cpu().numpy().reshape(H, W),
                 "dirs": self.dirs.cpu().numpy().view(np.uint16).reshape(H, W),
                 "aux": self.aux.cpu().numpy().reshape(H, W),
                 "block_id": self.block_id.cpu().numpy().reshape(H, W)}
 
     def maps_host(self):
-        H, W = self.height, self.width
+        H, W = self.win_rows, self.width
         return {k: v.cpu().numpy().reshape(H, W) for k, v in self.maps.items()}
 
     def light_links_host(self):

@@ -1,0 +1,324 @@
+"""Row-band shards of the layout pipeline across the GPUs of one box.
+
+The city's ``[H][W]`` planes are cut into ``n_shards`` contiguous row bands.  Shard ``s`` OWNS rows
+``[own_lo, own_hi)`` and holds a WINDOW ``[win_lo, win_hi)`` = its own rows plus ``halo`` rows of each
+neighbour.  Every pass runs on the whole window with the single-GPU kernels (a window is a small city whose
+out-of-window rows do not exist), then the shards refresh their halo rows from the owners:
+
+* closed-form pass (frame + roads): no communication at all, band tables are replicated;
+* stencil and per-block passes: one neighbour exchange of ``halo`` rows per plane after the pass.  A pass is
+  exact on a shard's own rows when everything those rows depend on lies inside the window: 1 row for the
+  stencils, ``traffic_light_range + 2`` for the lights, one block height for carving / zoning / entrances.
+  ``halo`` (default 64) must exceed the tallest block (``max_block_spacing`` = 18 by default); a component
+  that touches both a shard's own rows and a non-grid window edge raises ``TSIM_ERR_CAPACITY`` -- never a
+  silent wrong answer;
+* labelling: ids are global raster discovery ranks.  A component that meets a shard's own rows lies inside
+  its window, so its window root is its true root; every shard counts the roots in its own rows, one
+  all-gather + prefix gives ``id_base`` (device scalar consumed by the kernels through ``tsim_blobs``);
+* fixed points (dead ends, reachability for ``leads_to``): local fixed point, halo exchange, all-reduce of
+  the "changed" flags, repeat until no shard changed.  Dead-end removal treats rows beyond a shard cut as
+  unknown (= road), so missing information can only delay a removal (the pass is monotone).
+
+Two deployments share this code: one process per GPU under ``torch.distributed`` (NCCL; gloo on CPU for
+the host-logic tests) with one local shard each, or ONE process holding all shards on one device (how the
+``-m gpu`` tests check N-shard == 1-shard on a single GPU).  The data path has no other collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+INF32 = 0x7FFFFFFF
+ERR_HALO = 26   # a component meets both a shard's own rows and a cut edge of its window: halo too small
+
+
+class ShardPlan:
+    """Row ranges of every shard: own rows (even split) and window (own rows + halo, clipped to the grid)."""
+
+    def __init__(self, height: int, n_shards: int, halo: int):
+        if n_shards < 1 or height < n_shards:
+            raise ValueError(f"cannot cut {height} rows into {n_shards} shards")
+        self.height, self.n, self.halo = int(height), int(n_shards), int(halo)
+        self.own_lo = [s * height // n_shards for s in range(n_shards)]
+        self.own_hi = [(s + 1) * height // n_shards for s in range(n_shards)]
+        if n_shards > 1 and min(h - l for l, h in zip(self.own_lo, self.own_hi)) < halo:
+            raise ValueError(f"halo {halo} exceeds the rows of a shard ({height} rows / {n_shards} shards)")
+        self.win_lo = [max(0, l - halo) for l in self.own_lo]
+        self.win_hi = [min(height, h + halo) for h in self.own_hi]
+
+    def up_rows(self, s):
+        """(global row range) shard s sends UP to s+1 = the lower halo of s+1 (rows s owns)."""
+        return self.win_lo[s + 1], self.own_lo[s + 1]
+
+    def down_rows(self, s):
+        """(global row range) shard s sends DOWN to s-1 = the upper halo of s-1 (rows s owns)."""
+        return self.own_hi[s - 1], self.win_hi[s - 1]
+
+
+class Comm:
+    """Neighbour exchange and the two tiny collectives, for shards that are all local (``group is None`` and
+    world size 1) or spread one per rank over a ``torch.distributed`` group."""
+
+    def __init__(self, n_shards: int, dist_enabled: bool, group=None):
+        self.n = n_shards
+        self.dist = None
+        if dist_enabled:
+            import torch.distributed as dist
+            self.dist = dist
+            self.group = group
+            self.rank = dist.get_rank(group)
+            if dist.get_world_size(group) != n_shards:
+                raise ValueError("one shard per rank: world size must equal n_shards")
+            self.local = [self.rank]
+        else:
+            self.local = list(range(n_shards))
+
+    # halo exchange: get(s, lo, hi) -> view of shard s's rows [lo, hi) (global row numbers); put(s, lo, hi, src)
+    def exchange(self, plan: ShardPlan, get, put):
+        if self.n == 1:
+            return
+        if self.dist is None:
+            staged = []
+            for s in range(self.n - 1):
+                lo, hi = plan.up_rows(s)
+                staged.append((s + 1, lo, hi, get(s, lo, hi).clone()))
+                lo, hi = plan.down_rows(s + 1)
+                staged.append((s, lo, hi, get(s + 1, lo, hi).clone()))
+            for dst, lo, hi, src in staged:
+                put(dst, lo, hi, src)
+            return
+        dist, s = self.dist, self.rank
+        ops, recvs = [], []
+        if s + 1 < self.n:
+            lo, hi = plan.up_rows(s)
+            ops.append(dist.P2POp(dist.isend, get(s, lo, hi).contiguous(), s + 1, self.group))
+            lo, hi = plan.down_rows(s + 1)
+            buf = torch.empty_like(get(s, lo, hi).contiguous())
+            ops.append(dist.P2POp(dist.irecv, buf, s + 1, self.group))
+            recvs.append((lo, hi, buf))
+        if s > 0:
+            lo, hi = plan.down_rows(s)
+            ops.append(dist.P2POp(dist.isend, get(s, lo, hi).contiguous(), s - 1, self.group))
+            lo, hi = plan.up_rows(s - 1)
+            buf = torch.empty_like(get(s, lo, hi).contiguous())
+            ops.append(dist.P2POp(dist.irecv, buf, s - 1, self.group))
+            recvs.append((lo, hi, buf))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for lo, hi, buf in recvs:
+            put(s, lo, hi, buf)
+
+    def all_gather(self, vals: dict):
+        """vals: {local shard -> 1-D tensor[k]} -> {local shard -> tensor [n_shards, k]} (same device / dtype)."""
+        if self.dist is None:
+            return {s: torch.stack([vals[r].to(vals[s].device) for r in range(self.n)]) for s in self.local}
+        v = vals[self.rank].contiguous().reshape(-1)
+        out = torch.empty(self.n * v.numel(), dtype=v.dtype, device=v.device)
+        self.dist.all_gather_into_tensor(out, v, group=self.group)
+        return {self.rank: out.view(self.n, v.numel())}
+
+    def any(self, flags: dict) -> bool:
+        """flags: {local shard -> 0-d / 1-element integer tensor}; True if any shard's flag is non-zero (host sync)."""
+        if self.dist is None:
+            return any(bool(int(f.reshape(-1)[0].item())) for f in flags.values())
+        f = flags[self.rank].reshape(-1)[:1].to(torch.int32).clone()
+        self.dist.all_reduce(f, op=self.dist.ReduceOp.MAX, group=self.group)
+        return bool(int(f.item()))
+
+
+def id_bases(own_counts: torch.Tensor, n_lo: torch.Tensor, shard: int) -> torch.Tensor:
+    """Global id base of a shard's window-local component numbering (0-d int32 tensor).
+
+    own_counts[r] = roots in the own rows of shard r (all-gathered), n_lo = roots of THIS window below its
+    own rows.  Window component k (0-based, raster order) has global 0-based id k + base with
+    base = sum(own_counts[:shard]) - n_lo: the roots between the window's first owned root and any root that
+    matters are all true roots (module docstring).
+    """
+    before = own_counts[:shard].sum() if shard > 0 else torch.zeros((), dtype=own_counts.dtype, device=own_counts.device)
+    return (before - n_lo).to(torch.int32)
+
+
+class ShardedCityLayout:
+    """``GpuCityLayout`` over row-band shards.  Same constructor kwargs as the reference ``CityModel`` plus the
+    shard geometry; ``generate`` runs the reference's pass sequence (city_model.py:125-139, 148)."""
+
+    def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, **city_kwargs):
+        from .layout import GpuCityLayout
+        self.kw = dict(city_kwargs)
+        self.width, self.height = int(city_kwargs.get("width", 200)), int(city_kwargs.get("height", 200))
+        self.plan = ShardPlan(self.height, n_shards, halo if n_shards > 1 else 0)
+        self.comm = Comm(n_shards, distributed, group)
+        self.carve = bool(city_kwargs.get("carve_subblock_roads", False))
+        self.shards = {}
+        for i, s in enumerate(self.comm.local):
+            dev = (devices[i] if devices else (city_kwargs.get("device", "cuda:0")))
+            kw = {k: v for k, v in city_kwargs.items() if k != "device"}
+            self.shards[s] = GpuCityLayout(device=dev, win_y0=self.plan.win_lo[s], win_rows=self.plan.win_hi[s] - self.plan.win_lo[s], **kw)
+        self.n_blocks = None
+
+    # ------------------------------------------------------------------ plumbing
+    def set_bands(self, hbands, vbands):
+        for L in self.shards.values():
+            L.set_bands(hbands, vbands)
+        self.global_cap = 3 * (len(hbands) + 2) * (len(vbands) + 2) + 64   # bound on the blocks of the whole city
+
+    def _plane(self, s, name):
+        L = self.shards[s]
+        t = getattr(L, name)
+        return t.view(L.win_rows, self.width)
+
+    def _exchange(self, *names):
+        for name in names:
+            self.comm.exchange(self.plan,
+                               lambda s, lo, hi, name=name: self._plane(s, name)[lo - self.plan.win_lo[s]: hi - self.plan.win_lo[s]],
+                               lambda s, lo, hi, src, name=name: self._plane(s, name)[lo - self.plan.win_lo[s]: hi - self.plan.win_lo[s]].copy_(src))
+
+    def _label_and_number(self):
+        """Label every window, then turn the window-local numbering into global raster ranks (id_base)."""
+        p, W = self.plan, self.width
+        counts, n_lo = {}, {}
+        for s, L in self.shards.items():
+            L._label_async()
+            tab = L.blobs.view(-1, 6)
+            valid = torch.arange(tab.shape[0], device=tab.device) < L.flags[2]
+            root = tab[:, 5].to(torch.int64)
+            lo_cell, hi_cell = (p.own_lo[s] - p.win_lo[s]) * W, (p.own_hi[s] - p.win_lo[s]) * W
+            n_lo[s] = (valid & (root < lo_cell)).sum()
+            counts[s] = (valid & (root >= lo_cell) & (root < hi_cell)).sum().reshape(1)
+            # a component that meets the own rows must not reach a cut edge of the window (ring cells need one more row)
+            miny, maxy = tab[:, 1], tab[:, 3]
+            meets = valid & (maxy >= p.own_lo[s]) & (miny < p.own_hi[s])
+            cut = ((miny <= p.win_lo[s] + 1) & (p.win_lo[s] > 0)) | ((maxy >= p.win_hi[s] - 2) & (p.win_hi[s] < self.height))
+            bad = (meets & cut).any()
+            L.flags[0] = torch.where(bad & (L.flags[0] == 0), torch.full_like(L.flags[0], ERR_HALO), L.flags[0])
+        gathered = self.comm.all_gather(counts)
+        for s, L in self.shards.items():
+            own = gathered[s].reshape(-1)
+            L.flags[4] = id_bases(own, n_lo[s], s)
+            self._total = own.sum()
+
+    def _check(self, what):
+        for L in self.shards.values():
+            L._check_flag(what)
+
+    # ------------------------------------------------------------------ the pipeline
+    def generate(self, tape_zone, tape_carve=None, tape_entrance=None, check=True, lights=True, maps=True):
+        S = self.shards
+        if tape_entrance is None:                             # per-block tapes are indexed by GLOBAL block id
+            tape_entrance = np.zeros(self.global_cap, np.int32)
+        for L in S.values():
+            L._build_roads_and_sidewalks()                    # closed form: exact on the whole window, no exchange
+        if self.carve:
+            self._label_and_number()
+            for L in S.values():
+                L._carve_subblock_roads(tape_carve, check=False, relabel=False)
+            self._exchange("cell_type", "dirs", "aux")
+        self._label_and_number()
+        for L in S.values():
+            L._flood_fill_blocks_storing_data(tape_zone, check=False, relabel=False)
+        self._exchange("cell_type", "block_id")
+        self.dead_end_rounds = 0
+        while True:                                           # monotone pruning: local fixed point, exchange, repeat
+            for L in S.values():
+                L._eliminate_dead_ends()
+            self._exchange("cell_type", "dirs", "aux")
+            self.dead_end_rounds += 1
+            if not self.comm.any({s: (L.flags[1] > 1).to(torch.int32) for s, L in S.items()}):
+                break
+        for L in S.values():
+            L._upgrade_r2_to_intersections(check=False)
+        self._exchange("cell_type", "dirs", "aux")
+        for L in S.values():
+            L._final_place_block_entrances(tape_entrance, check=False)
+        self._exchange("cell_type", "dirs", "aux", "block_id")
+        for L in S.values():
+            L._remove_invalid_intersection_directions()
+            L._add_entrance_directions()
+        self._exchange("dirs")
+        if lights:
+            self._lights()
+        if maps:
+            for L in S.values():
+                L._build_simple_maps()
+        if check:
+            self._check("generate")
+            self.n_blocks = int(self._total.item())
+
+    def _lights(self):
+        p, W, S = self.plan, self.width, self.shards
+        cands = {}
+        for s, L in S.items():
+            L._lights_prepare()
+            c = L.flags[8:10].to(torch.int64)
+            cands[s] = torch.where(c == INF32, torch.full_like(c, 2 ** 62), c + p.win_lo[s] * W)   # global raster index
+        gathered = self.comm.all_gather(cands)
+        for s, L in S.items():
+            g = gathered[s]
+            mid, first = g[:, 0].min(), g[:, 1].min()
+            piv = torch.where(mid < 2 ** 62, mid, first)
+            local = piv - p.win_lo[s] * W
+            inside = (piv < 2 ** 62) & (local >= 0) & (local < L.win_rows * W)
+            L.flags[10] = torch.where(inside, local, torch.full_like(local, -1)).to(torch.int32)
+            L._lights_seed()
+        self.reach_rounds = 0
+        planes = {s: L.reach_planes() for s, L in S.items()}
+        while True:
+            changed = {}
+            for s, L in S.items():
+                L.flags[11] = 0
+                L._lights_reach()
+                changed[s] = L.flags[11].clone()
+            for k in (0, 1):                                  # OR the owners' rows into the neighbours' halo rows
+                def get(s, lo, hi, k=k):
+                    return planes[s][k][lo - p.win_lo[s]: hi - p.win_lo[s]]
+
+                def put(s, lo, hi, src, k=k):
+                    dst = planes[s][k][lo - p.win_lo[s]: hi - p.win_lo[s]]
+                    merged = dst | src
+                    changed[s] = changed[s] | (merged != dst).any().to(torch.int32)
+                    dst.copy_(merged)
+                self.comm.exchange(p, get, put)
+            self.reach_rounds += 1
+            if not self.comm.any(changed):
+                break
+        for L in S.values():
+            L._lights_finish(check=False)
+        self._exchange("cell_type", "aux", "block_id")
+
+    # ------------------------------------------------------------------ read-back (own rows)
+    def planes_host(self):
+        """Own rows of every LOCAL shard, stacked in row order (the whole city when all shards are local)."""
+        out = {}
+        for s in sorted(self.shards):
+            L, p = self.shards[s], self.plan
+            h = L.planes_host()
+            a, b = p.own_lo[s] - p.win_lo[s], p.own_hi[s] - p.win_lo[s]
+            for k, v in h.items():
+                out.setdefault(k, []).append(v[a:b])
+        return {k: np.concatenate(v, 0) for k, v in out.items()}
+
+    def maps_host(self):
+        out = {}
+        for s in sorted(self.shards):
+            L, p = self.shards[s], self.plan
+            a, b = p.own_lo[s] - p.win_lo[s], p.own_hi[s] - p.win_lo[s]
+            for k, v in L.maps_host().items():
+                out.setdefault(k, []).append(v[a:b])
+        return {k: np.concatenate(v, 0) for k, v in out.items()}
+
+    def light_links_host(self):
+        """Link tables of the lights each local shard OWNS, as sorted (light, cell) pairs in GLOBAL cell indices."""
+        p, W = self.plan, self.width
+        lights, ctrl, inc = [], [], []
+        for s in sorted(self.shards):
+            L = self.shards[s]
+            g = L.light_links_host()
+            off = p.win_lo[s] * W
+            lo, hi = (p.own_lo[s] - p.win_lo[s]) * W, (p.own_hi[s] - p.win_lo[s]) * W
+            keep = (g["lights"] >= lo) & (g["lights"] < hi)
+            lights.append(g["lights"][keep].astype(np.int64) + off)
+            for name, acc in (("ctrl", ctrl), ("incoming", inc)):
+                pr = g[name].astype(np.int64)
+                k = (pr[:, 0] >= lo) & (pr[:, 0] < hi)
+                acc.append(pr[k] + off)
+        return {"lights": np.concatenate(lights), "ctrl": np.concatenate(ctrl, 0), "incoming": np.concatenate(inc, 0)}
