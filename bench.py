@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 PASS_BYTES = {"frame_roads": 4, "carve": 6, "zones": 6, "dead_ends": 2, "upgrade_r2": 4, "entrances": 6,
               "fix_dirs": 10, "lights": 5, "maps": 8}
 CPU_SAMPLE = 2048   # the CPU arm runs a CPU_SAMPLE x CPU_SAMPLE city per step
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), by pass
+ROOFLINE_TRAFFIC = {}
 
 
 def measured_peaks():
@@ -197,7 +199,7 @@ def ours(args):
     import torch
     import torch.distributed as dist
     from trafficsimulation_b200 import tapes
-    from trafficsimulation_b200.layout import GpuCityLayout
+    from trafficsimulation_b200.sharded import ShardedCityLayout
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,20 +208,24 @@ def ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    size, seed = args.size, 4096 + rank    # weak scaling: every rank generates its own size x size city
-    hb, vb, cap, tz, te = synth_inputs(size, seed)
-    city = GpuCityLayout(width=size, height=size, carve_subblock_roads=True, device=dev)
-    city.set_bands(hb, vb)
-    city._build_roads_and_sidewalks()
-    n_blobs, table = city.label_nothing()
-    tc = tapes.synth_carve_tape(seed, table.cpu().numpy())
+    # weak scaling: ONE city of `size` columns x `size * world` rows, cut into `world` row-band shards (one per GPU,
+    # 64 halo rows, NCCL neighbour exchange after every pass); at world == 1 this is the plain size x size city
+    size, seed = args.size, 4096
+    W, H = size, size * world
+    hb, vb = tapes.synth_bands(seed, width=W, height=H)
+    sh = ShardedCityLayout(world, halo=64, distributed=world > 1, width=W, height=H, carve_subblock_roads=True, device=dev)
+    sh.set_bands(hb, vb)
+    city = sh.shards[rank]
+    cap = sh.global_cap
+    tz, te = tapes.synth_zone_tape(seed, cap), np.zeros(cap, np.int32)
     d_tz, d_te = torch.from_numpy(tz).to(dev), torch.from_numpy(te).to(dev)
-    d_tc = torch.from_numpy(tc).to(dev)
-    cells = size * size
+    d_tc = sh.synth_carve_tapes(seed)[rank]
+    own_rows = sh.plan.own_hi[rank] - sh.plan.own_lo[rank]
+    cells = W * own_rows                                             # cells this GPU owns
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step():
-        city.generate(d_tz, d_tc, d_te, check=False)
+        sh.generate(d_tz, {rank: d_tc}, d_te, check=False)
 
     def barrier():
         torch.cuda.synchronize()
@@ -240,6 +246,8 @@ def ours(args):
     t_clk0 = time.monotonic()
     for a, b in ev:
         flush.fill_(1)
+        if world > 1:
+            dist.barrier()          # all ranks enter the step together; the step itself is timed on the device
         a.record()
         step()
         b.record()
@@ -251,11 +259,11 @@ def ours(args):
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     ms = float(t_dev.item())
-    value = cells * world * args.steps / (ms * 1e-3)
+    value = W * H * args.steps / (ms * 1e-3)
 
-    # ---- per-pass breakdown (rank 0, same stream, events between passes)
+    # ---- per-pass breakdown (single GPU only: on shards the passes interleave with the exchanges)
     passes = {}
-    if rank == 0:
+    if world == 1:
         names = ["frame_roads", "carve", "zones", "dead_ends", "upgrade_r2", "entrances", "fix_dirs", "lights", "maps"]
         calls = [city._build_roads_and_sidewalks, lambda: city._carve_subblock_roads(d_tc, check=False),
                  lambda: city._flood_fill_blocks_storing_data(d_tz, check=False), city._eliminate_dead_ends,
@@ -282,15 +290,15 @@ def ours(args):
             gbs = cells * bpc / (t * 1e-3) / 1e9
             passes[n] = {"ms": round(t, 4), "cells_per_s": cells / (t * 1e-3), "alg_bytes_per_cell": bpc,
                          "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4)}
-
     t_clk1 = time.monotonic()
     clocks.__exit__(None, None, None)
 
-    # ---- end to end through the public API with host buffers
-    pin = lambda a: torch.from_numpy(a).pin_memory()
-    h_tz, h_tc, h_te = pin(tz), pin(tc), pin(te)
+    # ---- end to end through the public API with host buffers: tapes + band tables H2D, own rows of planes + maps D2H
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_tz, h_te, h_tc = pin(tz), pin(te), d_tc.cpu().pin_memory()
     h_rows, h_cols = city.row_table.cpu().pin_memory(), city.col_table.cpu().pin_memory()
-    outs = {"cell_type": city.cell_type, "dirs": city.dirs, "aux": city.aux, "block_id": city.block_id}
+    lo = (sh.plan.own_lo[rank] - sh.plan.win_lo[rank]) * W
+    outs = {k: getattr(city, k)[lo: lo + cells] for k in ("cell_type", "dirs", "aux", "block_id")}
     h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
     h_maps = None
     h2d = sum(t.numel() * t.element_size() for t in (h_tz, h_tc, h_te, h_rows, h_cols))
@@ -299,13 +307,13 @@ def ours(args):
         nonlocal h_maps
         city.row_table.copy_(h_rows, non_blocking=True); city.col_table.copy_(h_cols, non_blocking=True)
         d_tz.copy_(h_tz, non_blocking=True); d_tc.copy_(h_tc, non_blocking=True); d_te.copy_(h_te, non_blocking=True)
-        city.generate(d_tz, d_tc, d_te, check=False)
+        step()
         if h_maps is None:
-            h_maps = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in city.maps.items()}
+            h_maps = {k: torch.empty(cells, dtype=v.dtype).pin_memory() for k, v in city.maps.items()}
         for k, v in outs.items():
             h_out[k].copy_(v, non_blocking=True)
         for k, v in city.maps.items():
-            h_maps[k].copy_(v, non_blocking=True)
+            h_maps[k].copy_(v[lo: lo + cells], non_blocking=True)
         torch.cuda.synchronize()
         city._check_flag("e2e")
 
@@ -319,38 +327,50 @@ def ours(args):
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = cells * world * args.steps / float(t_e2e.item())
+    e2e_value = W * H * args.steps / float(t_e2e.item())
+    n_blocks = int(sh._total.item())
+    n_lights = torch.tensor([int(((city._link_tensors["light_cell"][: int(city.flags[3].item())] >= lo) &
+                                  (city._link_tensors["light_cell"][: int(city.flags[3].item())] < lo + cells)).sum().item())],
+                            dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_lights)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        top = max(passes, key=lambda n: passes[n]["ms"])
-        alg_bytes = cells * passes[top]["alg_bytes_per_cell"]
-        roof = {"bound": "hbm", "kernel": top, "achieved": passes[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": passes[top]["frac_of_measured_peak"], "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes}
-        total_alg = sum(cells * p["alg_bytes_per_cell"] for p in passes.values())
-        pipeline_gbs = total_alg * args.steps / (ms * 1e-3) / 1e9 / world
-        cpu_val, cpu_s = cpu_arm(CPU_SAMPLE, 2, 1)
-        vehicle = vehicle_bench(dev)
+        total_alg_per_cell = sum(PASS_BYTES.values())
+        pipeline_gbs = cells * total_alg_per_cell * args.steps / (ms * 1e-3) / 1e9   # per GPU
+        if passes:
+            top = max(passes, key=lambda n: passes[n]["ms"])
+            roof = {"bound": "hbm", "kernel": top, "achieved": passes[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": passes[top]["frac_of_measured_peak"], "traffic": ROOFLINE_TRAFFIC.get(top), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": cells * passes[top]["alg_bytes_per_cell"]}
+        else:
+            roof = {"bound": "hbm", "kernel": "whole pipeline (per GPU)", "achieved": round(pipeline_gbs, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(pipeline_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": cells * total_alg_per_cell}
+        cpu_val, cpu_s = (cpu_arm(CPU_SAMPLE, 2, 1) if world == 1 else (None, None))
         line = {
             "metric": "grid cells/sec, full layout generation (all passes)", "value": value, "unit": "cells/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{size}x{size} synthetic city layout, all generation passes (carve + lights + maps)",
-                       "cells_per_gpu": cells, "parallelism": "one city per GPU" if world > 1 else "single GPU",
-                       "l2": "flushed between timed steps (256 MiB write)", "seed": 4096,
-                       "blocks": int(city.flags[2].item()), "lights": int(city.flags[3].item()), "dead_end_sweeps": city.sweeps()},
+            "config": {"workload": f"{W}x{H} synthetic city layout, all generation passes (carve + lights + maps)",
+                       "cells_per_gpu": cells,
+                       "parallelism": f"{world} row-band shards of {own_rows} rows (+64 halo rows), NCCL halo exchange after each pass" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB write)", "seed": seed,
+                       "blocks": n_blocks, "lights": int(n_lights.item()), "dead_end_sweeps": city.sweeps(),
+                       "shard_rounds": {"dead_ends": getattr(sh, "dead_end_rounds", 1), "reach": getattr(sh, "reach_rounds", 1)}},
             "clocks": clocks.summary(t_clk0, t_clk1),
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "pipeline": {"algorithmic_bytes_per_cell": total_alg / cells, "achieved_gbs": round(pipeline_gbs, 1),
+            "pipeline": {"algorithmic_bytes_per_cell": total_alg_per_cell, "achieved_gbs_per_gpu": round(pipeline_gbs, 1),
                          "frac_of_measured_peak": round(pipeline_gbs / peak, 4)},
             "passes": passes,
-            "vehicle_step": vehicle,
-            "cpu_baseline": {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
-                             "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"},
         }
+        if world == 1:
+            line["vehicle_step"] = vehicle_bench(dev)
+            line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
+                                    "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

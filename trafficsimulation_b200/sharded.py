@@ -176,6 +176,11 @@ class ShardedCityLayout:
     def _label_and_number(self):
         """Label every window, then turn the window-local numbering into global raster ranks (id_base)."""
         p, W = self.plan, self.width
+        if p.n == 1:                                          # one window = the whole grid: window ranks ARE global ranks
+            L = self.shards[0]
+            L._label_async()
+            self._total = L.flags[2]
+            return
         counts, n_lo = {}, {}
         for s, L in self.shards.items():
             L._label_async()
@@ -197,6 +202,21 @@ class ShardedCityLayout:
             L.flags[4] = id_bases(own, n_lo[s], s)
             self._total = own.sum()
 
+    def synth_carve_tapes(self, seed):
+        """Synthetic carve tapes for cities the reference cannot reach (tapes.synth_carve_tape_device): runs the frame
+        pass and the labelling once, returns {local shard -> int32 tape [global_cap + 1, 8]} for ``generate``."""
+        from . import tapes
+        for L in self.shards.values():
+            L._build_roads_and_sidewalks()
+        self._label_and_number()
+        uni = tapes.synth_carve_uniforms(seed, self.global_cap)
+        out = {}
+        for s, L in self.shards.items():
+            u = torch.from_numpy(uni).to(L.device)
+            t = torch.zeros((self.global_cap + 1, 8), dtype=torch.int32, device=L.device)
+            out[s] = tapes.synth_carve_tape_device(u, L.blobs.view(-1, 6), L.flags[2], L.flags[4], t)
+        return out
+
     def _check(self, what):
         for L in self.shards.values():
             L._check_flag(what)
@@ -204,14 +224,35 @@ class ShardedCityLayout:
     # ------------------------------------------------------------------ the pipeline
     def generate(self, tape_zone, tape_carve=None, tape_entrance=None, check=True, lights=True, maps=True):
         S = self.shards
+        if self.plan.n == 1:                                  # no cuts: the plain single-GPU sequence, no host round trips
+            L = S[0]
+            L._place_thick_wall(); L._place_sidewalk_inner_ring(); L._clear_interior()
+            L._build_roads_and_sidewalks()
+            if self.carve:
+                L._carve_subblock_roads(tape_carve[0] if isinstance(tape_carve, dict) else tape_carve, check=False)
+            L._flood_fill_blocks_storing_data(tape_zone, check=False)
+            self._total = L.flags[2]
+            L._eliminate_dead_ends()
+            L._upgrade_r2_to_intersections(check=False)
+            L._final_place_block_entrances(tape_entrance, check=False)
+            L._remove_invalid_intersection_directions(); L._add_entrance_directions()
+            if lights:
+                L._add_traffic_lights(check=False)
+            if maps:
+                L._build_simple_maps()
+            self.dead_end_rounds = self.reach_rounds = 1
+            if check:
+                self._check("generate")
+                self.n_blocks = int(self._total.item())
+            return
         if tape_entrance is None:                             # per-block tapes are indexed by GLOBAL block id
             tape_entrance = np.zeros(self.global_cap, np.int32)
         for L in S.values():
             L._build_roads_and_sidewalks()                    # closed form: exact on the whole window, no exchange
         if self.carve:
             self._label_and_number()
-            for L in S.values():
-                L._carve_subblock_roads(tape_carve, check=False, relabel=False)
+            for s, L in S.items():
+                L._carve_subblock_roads(tape_carve[s] if isinstance(tape_carve, dict) else tape_carve, check=False, relabel=False)
             self._exchange("cell_type", "dirs", "aux")
         self._label_and_number()
         for L in S.values():

@@ -56,6 +56,41 @@ def synth_carve_tape(seed: int, blobs: np.ndarray, min_subblock_spacing: int = 5
     return tape
 
 
+def synth_carve_uniforms(seed: int, cap: int) -> np.ndarray:
+    """Six uniforms per GLOBAL blob id: the shared randomness of ``synth_carve_tape_device`` (replicated on every shard)."""
+    return np.random.default_rng(seed).random((cap, 6), dtype=np.float32)
+
+
+def synth_carve_tape_device(uniforms, table, count, id_base, out, min_subblock_spacing: int = 5, subblock_chance: float = 0.3):
+    """Carve tape rows for the blobs of one window, written into the global-id-indexed tape ``out`` [cap, 8] (torch, on device).
+
+    ``table`` [cap_w, 6] / ``count`` / ``id_base`` are the window's component table (tsim_blobs); ``out`` has one
+    more row than there are ids (a scratch row).  A blob's row is a
+    function of its global id (through ``uniforms``) and of its bounding box only, so every shard that sees the whole
+    blob writes the same row; blobs cut by a window edge (partial bounding box) are skipped by the carve kernel.
+    Same acceptance rules as ``synth_carve_tape`` (city_model.py:649-682).
+    """
+    import torch
+    ms = min_subblock_spacing
+    k = torch.arange(table.shape[0], device=table.device)
+    gid = k + id_base.to(torch.int64)
+    ok = (k < count) & (gid >= 0) & (gid < out.shape[0] - 1)
+    g = gid.clamp(0, out.shape[0] - 2)
+    u = uniforms[g]
+    minx, miny, maxx, maxy, size = (table[:, i].to(torch.int64) for i in range(5))
+    w, h = maxx - minx + 1, maxy - miny + 1
+    carved = ok & (u[:, 0] <= subblock_chance) & (w >= 2 * ms + 1) & (h >= 2 * ms + 1) & (w * h == size)
+    px = minx + ms + (u[:, 1] * (w - 2 * ms).clamp(min=1)).to(torch.int64)
+    py = miny + ms + (u[:, 2] * (h - 2 * ms).clamp(min=1)).to(torch.int64)
+    px, py = torch.minimum(px, maxx - ms), torch.minimum(py, maxy - ms)
+    rows = torch.stack([(ok & (u[:, 0] <= subblock_chance)).to(torch.int64), carved.to(torch.int64), px, py,
+                        torch.where(u[:, 3] < 0.5, 3, 1), torch.where(u[:, 4] < 0.5, 0, 2), (u[:, 5] < 0.5).to(torch.int64),
+                        carved.to(torch.int64)], 1)
+    rows = torch.where(carved[:, None], rows, torch.zeros_like(rows)).to(torch.int32)
+    out[torch.where(ok, g, torch.full_like(g, out.shape[0] - 1))] = rows   # the last row of `out` is a scratch row (no host sync)
+    return out
+
+
 def synth_traffic(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarray, n_vehicles: int, n_ticks: int,
                   route_len: int = 200, spawn_ticks: int = 1, malfunction_p: float = 0.0):
     """Synthetic tick tapes for cities too large for the reference's A* (SURVEY.md §8d configs 4/5).
