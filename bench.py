@@ -3,8 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S]
 
-Workload (BASELINE.json configs[1]): a S x S synthetic city (default 4096 x 4096), ALL layout
-generation passes -- frame, roads, sub-block carving, flood-fill zoning, dead ends, R2 upgrade, block
+Workload: a S x S synthetic city, ALL layout generation passes.  Default S = 16384 (BASELINE.json configs[2],
+the size the north star's roofline target is quoted on); configs[1] (4096 x 4096) is timed beside it and
+reported under "config1_4096".  With --gpus N the city has S x N*S cells in N row-band shards (weak scaling).
+Passes -- frame, roads, sub-block carving, flood-fill zoning, dead ends, R2 upgrade, block
 entrances, direction fixes, traffic lights with controlled-road linking, derived maps.  One "step" is
 one full generation of the city from its band lists and tapes.
 
@@ -195,6 +197,34 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20):
                              "sample": f"oracle/vehicle_oracle.c, same tapes, {cpu_ticks} ticks, {live0} live vehicles"}}
 
 
+def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
+    """BASELINE.json configs[1] (4096 x 4096, all passes, 1 GPU) next to the headline size: device-resident cells/s."""
+    import torch
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.sharded import ShardedCityLayout
+    hb, vb = tapes.synth_bands(seed, width=size, height=size)
+    sh = ShardedCityLayout(1, width=size, height=size, carve_subblock_roads=True, device=dev)
+    sh.set_bands(hb, vb)
+    tz = torch.from_numpy(tapes.synth_zone_tape(seed, sh.global_cap)).to(dev)
+    te = torch.zeros(sh.global_cap, dtype=torch.int32, device=dev)
+    tc = sh.synth_carve_tapes(seed)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        sh.generate(tz, tc, te, check=False)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        sh.generate(tz, tc, te, check=False)
+        b.record()
+    torch.cuda.synchronize()
+    sh.shards[0]._check_flag("small_city_leg")
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    return {"workload": f"{size}x{size} synthetic city layout, all generation passes, 1 GPU (BASELINE.json configs[1])",
+            "value": size * size / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms, "steps": steps,
+            "frac_of_measured_peak": round(size * size * sum(PASS_BYTES.values()) / (ms * 1e-3) / 1e9 / measured_peaks()[0], 4)}
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -368,6 +398,7 @@ def ours(args):
             "passes": passes,
         }
         if world == 1:
+            line["config1_4096"] = small_city_leg(dev) if size != 4096 else None
             line["vehicle_step"] = vehicle_bench(dev)
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                                     "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
@@ -402,7 +433,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=16384)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -73,40 +73,43 @@ class Comm:
         else:
             self.local = list(range(n_shards))
 
-    # halo exchange: get(s, lo, hi) -> view of shard s's rows [lo, hi) (global row numbers); put(s, lo, hi, src)
-    def exchange(self, plan: ShardPlan, get, put):
+    # halo exchange.  items: list of (get, put) with get(s, lo, hi) -> view of shard s's rows [lo, hi) (global row
+    # numbers) and put(s, lo, hi, src).  All items travel in ONE batch of sends / receives per neighbour pair.
+    def exchange(self, plan: ShardPlan, get, put=None):
+        items = [(get, put)] if put is not None else list(get)
         if self.n == 1:
             return
         if self.dist is None:
-            staged = []
-            for s in range(self.n - 1):
-                lo, hi = plan.up_rows(s)
-                staged.append((s + 1, lo, hi, get(s, lo, hi).clone()))
-                lo, hi = plan.down_rows(s + 1)
-                staged.append((s, lo, hi, get(s + 1, lo, hi).clone()))
-            for dst, lo, hi, src in staged:
-                put(dst, lo, hi, src)
+            for g, p in items:
+                staged = []
+                for s in range(self.n - 1):
+                    lo, hi = plan.up_rows(s)
+                    staged.append((s + 1, lo, hi, g(s, lo, hi).clone()))
+                    lo, hi = plan.down_rows(s + 1)
+                    staged.append((s, lo, hi, g(s + 1, lo, hi).clone()))
+                for dst, lo, hi, src in staged:
+                    p(dst, lo, hi, src)
             return
         dist, s = self.dist, self.rank
         ops, recvs = [], []
-        if s + 1 < self.n:
-            lo, hi = plan.up_rows(s)
-            ops.append(dist.P2POp(dist.isend, get(s, lo, hi).contiguous(), s + 1, self.group))
-            lo, hi = plan.down_rows(s + 1)
-            buf = torch.empty_like(get(s, lo, hi).contiguous())
-            ops.append(dist.P2POp(dist.irecv, buf, s + 1, self.group))
-            recvs.append((lo, hi, buf))
-        if s > 0:
-            lo, hi = plan.down_rows(s)
-            ops.append(dist.P2POp(dist.isend, get(s, lo, hi).contiguous(), s - 1, self.group))
-            lo, hi = plan.up_rows(s - 1)
-            buf = torch.empty_like(get(s, lo, hi).contiguous())
-            ops.append(dist.P2POp(dist.irecv, buf, s - 1, self.group))
-            recvs.append((lo, hi, buf))
+
+        def add(g, p, peer, send_rows, recv_rows):   # rows travel as raw bytes (NCCL has no int16)
+            src = g(s, *send_rows).contiguous()
+            ops.append(dist.P2POp(dist.isend, src.view(torch.uint8).reshape(-1), peer, self.group))
+            like = g(s, *recv_rows)
+            buf = torch.empty(like.numel() * like.element_size(), dtype=torch.uint8, device=like.device)
+            ops.append(dist.P2POp(dist.irecv, buf, peer, self.group))
+            recvs.append((p, recv_rows, buf, like.dtype, like.shape))
+
+        for g, p in items:
+            if s + 1 < self.n:
+                add(g, p, s + 1, plan.up_rows(s), plan.down_rows(s + 1))
+            if s > 0:
+                add(g, p, s - 1, plan.down_rows(s), plan.up_rows(s - 1))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        for lo, hi, buf in recvs:
-            put(s, lo, hi, buf)
+        for p, (lo, hi), buf, dtype, shape in recvs:
+            p(s, lo, hi, buf.view(dtype).view(shape))
 
     def all_gather(self, vals: dict):
         """vals: {local shard -> 1-D tensor[k]} -> {local shard -> tensor [n_shards, k]} (same device / dtype)."""
@@ -168,10 +171,10 @@ class ShardedCityLayout:
         return t.view(L.win_rows, self.width)
 
     def _exchange(self, *names):
-        for name in names:
-            self.comm.exchange(self.plan,
-                               lambda s, lo, hi, name=name: self._plane(s, name)[lo - self.plan.win_lo[s]: hi - self.plan.win_lo[s]],
-                               lambda s, lo, hi, src, name=name: self._plane(s, name)[lo - self.plan.win_lo[s]: hi - self.plan.win_lo[s]].copy_(src))
+        wl = self.plan.win_lo
+        self.comm.exchange(self.plan, [(lambda s, lo, hi, name=name: self._plane(s, name)[lo - wl[s]: hi - wl[s]],
+                                        lambda s, lo, hi, src, name=name: self._plane(s, name)[lo - wl[s]: hi - wl[s]].copy_(src))
+                                       for name in names])
 
     def _label_and_number(self):
         """Label every window, then turn the window-local numbering into global raster ranks (id_base)."""
@@ -309,6 +312,7 @@ class ShardedCityLayout:
                 L.flags[11] = 0
                 L._lights_reach()
                 changed[s] = L.flags[11].clone()
+            items = []
             for k in (0, 1):                                  # OR the owners' rows into the neighbours' halo rows
                 def get(s, lo, hi, k=k):
                     return planes[s][k][lo - p.win_lo[s]: hi - p.win_lo[s]]
@@ -318,7 +322,8 @@ class ShardedCityLayout:
                     merged = dst | src
                     changed[s] = changed[s] | (merged != dst).any().to(torch.int32)
                     dst.copy_(merged)
-                self.comm.exchange(p, get, put)
+                items.append((get, put))
+            self.comm.exchange(p, items)
             self.reach_rounds += 1
             if not self.comm.any(changed):
                 break
