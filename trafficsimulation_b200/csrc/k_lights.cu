@@ -179,26 +179,16 @@ __global__ void reach_seed_kernel(int W, const int32_t *piv, bool own, Bits bp) 
     bp.bw[(size_t)y * bp.wp + (x >> 6)] = 1ull << (x & 63);
 }
 
-// occluded fills inside a 64-bit word (Kogge-Stone): `p` = cells that may be entered from the lower
-// (up-fill) / higher (down-fill) neighbour
+// Occluded fills inside a 64-bit word: every set bit of f spreads upwards (fill_up) / downwards (fill_down) through
+// the consecutive cells of p, p = cells that may be entered from the lower / higher neighbour.  One subtraction does
+// it: with o = blockers | sources, o - 2f lets the borrow of every source ripple up to its first blocker, so
+// o ^ (o - 2f) is the set of cells passed (the chess-engine "o ^ (o - 2r)" ray trick; checked exhaustively against the
+// Kogge-Stone form on the host).
 __device__ __forceinline__ u64 fill_up(u64 f, u64 p) {
-    f |= p & (f << 1);  p &= p << 1;
-    f |= p & (f << 2);  p &= p << 2;
-    f |= p & (f << 4);  p &= p << 4;
-    f |= p & (f << 8);  p &= p << 8;
-    f |= p & (f << 16); p &= p << 16;
-    f |= p & (f << 32);
-    return f;
+    const u64 o = ~p | f;
+    return f | ((o ^ (o - (f << 1))) & p);
 }
-__device__ __forceinline__ u64 fill_down(u64 f, u64 p) {
-    f |= p & (f >> 1);  p &= p >> 1;
-    f |= p & (f >> 2);  p &= p >> 2;
-    f |= p & (f >> 4);  p &= p >> 4;
-    f |= p & (f >> 8);  p &= p >> 8;
-    f |= p & (f >> 16); p &= p >> 16;
-    f |= p & (f >> 32);
-    return f;
-}
+__device__ __forceinline__ u64 fill_down(u64 f, u64 p) { return __brevll(fill_up(__brevll(f), __brevll(p))); }
 
 // carry chain over the 32 words of a warp: c[0] = cin, c[i+1] = g[i] | (p[i] & c[i]) -- exactly a binary
 // adder's carries, so one 64-bit add resolves all of them.  Returns the carry INTO every lane.
@@ -209,134 +199,153 @@ __device__ __forceinline__ uint32_t carry_chain(uint32_t g, uint32_t p, uint32_t
     return (uint32_t)C;
 }
 
-// closes row y under its E / W arrows (both planes); returns true if anything changed
-__device__ bool row_closure(const Bits &bp, int y, int lane) {
-    const int wp = bp.wp;
-    const size_t base = (size_t)y * wp;
+// Closes one LINE of `wp` words under the arrows along it: aUp = arrow towards the next cell (E in a row of the
+// row-major planes, N in a row of the transposed planes), aDn = arrow towards the previous cell.  `f` moves WITH the
+// arrows, `b` AGAINST them.  One warp per line; returns true if anything changed.
+__device__ bool line_closure(u64 *__restrict__ fpl, u64 *__restrict__ bpl, const u64 *__restrict__ up, const u64 *__restrict__ dn, size_t base, int wp,
+                             int nbits, int lane, uint8_t *__restrict__ dirty /* + word * dstride: the 64x64 block the word belongs to */, int dstride) {
     bool any = false;
-    for (int round = 0; round < 64; round++) {
+    const u64 tail = (nbits & 63) ? ((1ull << (nbits & 63)) - 1ull) : ~0ull;   // an arrow out of the grid must not set a padding bit
+    // Alternate low -> high and high -> low passes.  The line is closed as soon as a pass changes nothing and the
+    // opposite pass has run on the same state (so: at least two passes, stop at the first quiet one).
+    for (int pass = 0; pass < 256; pass++) {
         bool ch = false;
-        // ---- left -> right: FW along E arrows, BW against W arrows
         uint32_t cf = 0, cb = 0;
-        for (int c0 = 0; c0 < wp; c0 += 32) {
-            const int w = c0 + lane;
-            const bool in = w < wp;
-            const u64 aE = in ? bp.aE[base + w] : 0ull, aW = in ? bp.aW[base + w] : 0ull;
-            const u64 f = in ? __ldcg(bp.fw + base + w) : 0ull, b = in ? __ldcg(bp.bw + base + w) : 0ull;
-            u64 f1 = fill_up(f, aE << 1), b1 = fill_up(b, aW);
-            const uint32_t gf = __ballot_sync(0xffffffffu, (f1 & aE) >> 63), pf = __ballot_sync(0xffffffffu, aE == ~0ull);
-            const uint32_t gb = __ballot_sync(0xffffffffu, b1 >> 63), pb = __ballot_sync(0xffffffffu, aW == ~0ull);
-            uint32_t nf, nb;
-            const uint32_t inf = carry_chain(gf, pf, cf, nf), inb = carry_chain(gb, pb, cb, nb);
-            cf = nf; cb = nb;
-            if ((inf >> lane) & 1u) f1 = fill_up(f1 | 1ull, aE << 1);
-            if ((inb >> lane) & 1u) b1 = fill_up(b1 | (aW & 1ull), aW);
-            if (in && f1 != f) { bp.fw[base + w] = f1; ch = true; }
-            if (in && b1 != b) { bp.bw[base + w] = b1; ch = true; }
+        if ((pass & 1) == 0) {   // ---- low -> high: f along aUp, b against aDn
+            for (int c0 = 0; c0 < wp; c0 += 32) {
+                const int w = c0 + lane;
+                const bool in = w < wp;
+                const u64 aE = in ? up[base + w] : 0ull, aW = in ? dn[base + w] : 0ull;
+                const u64 f = in ? __ldcg(fpl + base + w) : 0ull, b = in ? __ldcg(bpl + base + w) : 0ull;
+                u64 f1 = fill_up(f, aE << 1), b1 = fill_up(b, aW);
+                const uint32_t gf = __ballot_sync(0xffffffffu, (f1 & aE) >> 63), pf = __ballot_sync(0xffffffffu, aE == ~0ull);
+                const uint32_t gb = __ballot_sync(0xffffffffu, b1 >> 63), pb = __ballot_sync(0xffffffffu, aW == ~0ull);
+                uint32_t nf, nb;
+                const uint32_t inf = carry_chain(gf, pf, cf, nf), inb = carry_chain(gb, pb, cb, nb);
+                cf = nf; cb = nb;
+                if ((inf >> lane) & 1u) f1 = fill_up(f1 | 1ull, aE << 1);
+                if ((inb >> lane) & 1u) b1 = fill_up(b1 | (aW & 1ull), aW);
+                if (w == wp - 1) { f1 &= tail; b1 &= tail; }
+                if (in && (f1 != f || b1 != b)) { fpl[base + w] = f1; bpl[base + w] = b1; dirty[(size_t)w * dstride] = 1; ch = true; }
+            }
+        } else {                 // ---- high -> low: f along aDn, b against aUp
+            for (int c0 = ((wp - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+                const int w = c0 + lane;
+                const bool in = w < wp;
+                const u64 aE = in ? up[base + w] : 0ull, aW = in ? dn[base + w] : 0ull;
+                const u64 f = in ? __ldcg(fpl + base + w) : 0ull, b = in ? __ldcg(bpl + base + w) : 0ull;
+                u64 f1 = fill_down(f, aW >> 1), b1 = fill_down(b, aE);
+                const uint32_t gf = __brev(__ballot_sync(0xffffffffu, f1 & aW & 1ull)), pf = __brev(__ballot_sync(0xffffffffu, aW == ~0ull));
+                const uint32_t gb = __brev(__ballot_sync(0xffffffffu, b1 & 1ull)), pb = __brev(__ballot_sync(0xffffffffu, aE == ~0ull));
+                uint32_t nf, nb;
+                const uint32_t inf = __brev(carry_chain(gf, pf, cf, nf)), inb = __brev(carry_chain(gb, pb, cb, nb));
+                cf = nf; cb = nb;
+                if ((inf >> lane) & 1u) f1 = fill_down(f1 | (1ull << 63), aW >> 1);
+                if ((inb >> lane) & 1u) b1 = fill_down(b1 | (aE & (1ull << 63)), aE);
+                if (w == wp - 1) { f1 &= tail; b1 &= tail; }
+                if (in && (f1 != f || b1 != b)) { fpl[base + w] = f1; bpl[base + w] = b1; dirty[(size_t)w * dstride] = 1; ch = true; }
+            }
         }
-        // ---- right -> left: FW along W arrows, BW against E arrows
-        cf = 0; cb = 0;
-        for (int c0 = ((wp - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
-            const int w = c0 + lane;
-            const bool in = w < wp;
-            const u64 aE = in ? bp.aE[base + w] : 0ull, aW = in ? bp.aW[base + w] : 0ull;
-            const u64 f = in ? __ldcg(bp.fw + base + w) : 0ull, b = in ? __ldcg(bp.bw + base + w) : 0ull;
-            u64 f1 = fill_down(f, aW >> 1), b1 = fill_down(b, aE);
-            const uint32_t gf = __brev(__ballot_sync(0xffffffffu, f1 & aW & 1ull)), pf = __brev(__ballot_sync(0xffffffffu, aW == ~0ull));
-            const uint32_t gb = __brev(__ballot_sync(0xffffffffu, b1 & 1ull)), pb = __brev(__ballot_sync(0xffffffffu, aE == ~0ull));
-            uint32_t nf, nb;
-            const uint32_t inf = __brev(carry_chain(gf, pf, cf, nf)), inb = __brev(carry_chain(gb, pb, cb, nb));
-            cf = nf; cb = nb;
-            if ((inf >> lane) & 1u) f1 = fill_down(f1 | (1ull << 63), aW >> 1);
-            if ((inb >> lane) & 1u) b1 = fill_down(b1 | (aE & (1ull << 63)), aE);
-            if (in && f1 != f) { bp.fw[base + w] = f1; ch = true; }
-            if (in && b1 != b) { bp.bw[base + w] = b1; ch = true; }
-        }
-        if (!__any_sync(0xffffffffu, ch)) break;
-        any = true;
+        ch = __any_sync(0xffffffffu, ch);
+        any |= ch;
+        if (!ch && pass >= 1) break;
     }
     return any;
 }
 
-// Column closure of ONE word column (64 grid columns in parallel) by one CTA: thread k owns rows
-// [k*R, k*R+R).  UP = true: FW along N arrows and BW against S arrows (carries move up);
-// UP = false: FW along S arrows and BW against N arrows (carries move down).
-struct GP { u64 gf, pf, gb, pb; };
-
-template <bool UP>
-__device__ bool col_closure(const Bits &bp, int H, int wx, GP *s_gp) {
-    const int nt = blockDim.x, k = threadIdx.x;
-    const int R = (H + nt - 1) / nt;
-    const int ylo = min(H, k * R), yhi = min(H, ylo + R);
-    const int wp = bp.wp;
-    const u64 *arrF = UP ? bp.aN : bp.aS;   // FW: leaving row y along this arrow
-    const u64 *arrB = UP ? bp.aS : bp.aN;   // BW: row y inherits from the previous row of the sweep if it has this arrow
-    // phase 1: generate / propagate of my chunk
-    u64 cf = 0, pf = ~0ull, cb = 0, pb = ~0ull;
-    for (int j = 0; j < yhi - ylo; j++) {
-        const int y = UP ? ylo + j : yhi - 1 - j;
-        const size_t o = (size_t)y * wp + wx;
-        const u64 aF = arrF[o], aB = arrB[o];
-        const u64 f = __ldcg(bp.fw + o) | cf, b = __ldcg(bp.bw + o) | (aB & cb);
-        cf = f & aF; pf &= aF;
-        cb = b; pb &= aB;
+// In-register transpose of a 64 x 64 bit block held by a warp as rows `lane` (a0) and `lane + 32` (a1): six
+// butterfly stages (Hacker's Delight), the five cross-lane ones with one 64-bit shuffle per word.
+__device__ __forceinline__ void t64(u64 &a0, u64 &a1, int lane) {
+    { const u64 t = ((a0 >> 32) ^ a1) & 0x00000000ffffffffull; a0 ^= t << 32; a1 ^= t; }
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const u64 m = j == 16 ? 0x0000ffff0000ffffull : j == 8 ? 0x00ff00ff00ff00ffull : j == 4 ? 0x0f0f0f0f0f0f0f0full
+                    : j == 2 ? 0x3333333333333333ull : 0x5555555555555555ull;
+        const u64 p0 = __shfl_xor_sync(0xffffffffu, a0, j), p1 = __shfl_xor_sync(0xffffffffu, a1, j);
+        if ((lane & j) == 0) { a0 ^= (((a0 >> j) ^ p0) & m) << j; a1 ^= (((a1 >> j) ^ p1) & m) << j; }
+        else { a0 ^= ((p0 >> j) ^ a0) & m; a1 ^= ((p1 >> j) ^ a1) & m; }
     }
-    // inclusive scan over the chunks in sweep order: out[k] = g[k] | (p[k] & out[k-1])
-    const int pos = UP ? k : nt - 1 - k;   // position in sweep order
-    GP me{cf, pf, cb, pb};
-    s_gp[pos] = me;
-    __syncthreads();
-    for (int d = 1; d < nt; d <<= 1) {
-        GP lo;
-        const bool take = pos >= d;
-        if (take) lo = s_gp[pos - d];
-        __syncthreads();
-        if (take) {
-            me.gf |= me.pf & lo.gf; me.pf &= lo.pf;
-            me.gb |= me.pb & lo.gb; me.pb &= lo.pb;
-            s_gp[pos] = me;
-        }
-        __syncthreads();
-    }
-    cf = pos > 0 ? s_gp[pos - 1].gf : 0ull;
-    cb = pos > 0 ? s_gp[pos - 1].gb : 0ull;
-    __syncthreads();
-    // phase 2: apply with the carry-in
-    bool ch = false;
-    for (int j = 0; j < yhi - ylo; j++) {
-        const int y = UP ? ylo + j : yhi - 1 - j;
-        const size_t o = (size_t)y * wp + wx;
-        const u64 aF = arrF[o], aB = arrB[o];
-        const u64 f0 = __ldcg(bp.fw + o), b0 = __ldcg(bp.bw + o);
-        const u64 f = f0 | cf, b = b0 | (aB & cb);
-        if (f != f0) { bp.fw[o] = f; ch = true; }
-        if (b != b0) { bp.bw[o] = b; ch = true; }
-        cf = f & aF;
-        cb = b;
-    }
-    return ch;
 }
 
-// Persistent cooperative kernel: alternate row and column closures until an alternation changes nothing.
-__global__ void __launch_bounds__(256) reach_kernel(int H, Bits bp, int32_t *flags /* [0..2] change flags, [3] alternations */, int32_t *changed,
-                                                    int32_t *err) {
+// rows by*64 .. by*64+63 of word column bx of `src` ([src_rows][src_wp]) become words `by` of rows bx*64 .. bx*64+63
+// of `dst` ([dst_rows][dst_wp])
+__device__ __forceinline__ void transpose_block(const u64 *__restrict__ src, int src_rows, int src_wp, u64 *__restrict__ dst, int dst_rows, int dst_wp,
+                                                int bx, int by, int lane, bool coherent) {
+    const int r0 = by * 64 + lane, r1 = r0 + 32;
+    const u64 *p0 = src + (size_t)r0 * src_wp + bx, *p1 = src + (size_t)r1 * src_wp + bx;
+    u64 a0 = r0 < src_rows ? (coherent ? __ldcg(p0) : *p0) : 0ull, a1 = r1 < src_rows ? (coherent ? __ldcg(p1) : *p1) : 0ull;
+    t64(a0, a1, lane);
+    const int d0 = bx * 64 + lane, d1 = d0 + 32;
+    if (d0 < dst_rows) dst[(size_t)d0 * dst_wp + by] = a0;
+    if (d1 < dst_rows) dst[(size_t)d1 * dst_wp + by] = a1;
+}
+
+// Persistent cooperative kernel: alternate row closures of the row-major planes and row closures of the TRANSPOSED
+// planes (= column closures) until an alternation changes nothing.  Both sweeps are the same warp-per-line kernel
+// with fully coalesced word loads.  Work follows the frontier: a sweep marks the 64 x 64 blocks it changed, only
+// those are re-transposed, and only the lines that cross a re-transposed block are closed again (the first
+// alternation of a launch does everything once, whatever was seeded or merged into the planes from outside).
+struct ReachT {
+    u64 *aNt, *aSt, *fwT, *bwT;   // transposed planes: [W][wpT], bit y & 63 of word y >> 6
+    uint8_t *bdR, *bdT;           // [nby][nbx] block changed in the row-major / transposed planes since it was last transposed
+    uint8_t *rd, *cd;             // [nby] row block / [nbx] column block needs closing
+    int wpT;
+};
+
+__global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, ReachT rt, int32_t *flags /* [0..2] change flags, [3] alternations */,
+                                                    int32_t *changed, int32_t *err) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ GP s_gp[256];
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int warp = gtid >> 5, nwarps = nth >> 5;
+    const int nbx = bp.wp, nby = rt.wpT;           // blocks per row / per column of the row-major planes
+    const int px = (nbx + 3) >> 2, py = (nby + 1) >> 1;   // CTA patch = 4 (bx) x 2 (by) blocks: 8-byte words share 32-byte sectors
+    for (int patch = blockIdx.x; patch < px * py; patch += gridDim.x) {
+        const int bx = (patch % px) * 4 + (wid & 3), by = (patch / px) * 2 + (wid >> 2);
+        if (bx < nbx && by < nby) {
+            transpose_block(bp.aN, H, bp.wp, rt.aNt, W, rt.wpT, bx, by, lane, false);
+            transpose_block(bp.aS, H, bp.wp, rt.aSt, W, rt.wpT, bx, by, lane, false);
+        }
+    }
     for (int it = 0;; it++) {
         int32_t *flag = flags + it % 3;
+        const bool all = it == 0;
         bool ch = false;
-        for (int y = warp; y < H; y += nwarps) ch |= row_closure(bp, y, lane);
+        // ---- 1. close the rows whose block row received new bits
+        for (int y = warp; y < H; y += nwarps)
+            if (all || *((volatile uint8_t *)(rt.rd + (y >> 6)))) ch |= line_closure(bp.fw, bp.bw, bp.aE, bp.aW, (size_t)y * bp.wp, bp.wp, W, lane, rt.bdR + (size_t)(y >> 6) * nbx, 1);
         __threadfence();
         grid.sync();
-        for (int wx = blockIdx.x; wx < bp.wp; wx += gridDim.x) {
-            ch |= col_closure<true>(bp, H, wx, s_gp);
-            __syncthreads();
-            ch |= col_closure<false>(bp, H, wx, s_gp);
-            __syncthreads();
+        // ---- 2. changed blocks -> transposed planes
+        for (int i = gtid; i < nby; i += nth) rt.rd[i] = 0;
+        for (int patch = blockIdx.x; patch < px * py; patch += gridDim.x) {
+            const int bx = (patch % px) * 4 + (wid & 3), by = (patch / px) * 2 + (wid >> 2);
+            if (bx >= nbx || by >= nby) continue;
+            uint8_t *d = rt.bdR + (size_t)by * nbx + bx;
+            if (!all && !*((volatile uint8_t *)d)) continue;
+            transpose_block(bp.fw, H, bp.wp, rt.fwT, W, rt.wpT, bx, by, lane, true);
+            transpose_block(bp.bw, H, bp.wp, rt.bwT, W, rt.wpT, bx, by, lane, true);
+            if (lane == 0) { *d = 0; rt.cd[bx] = 1; }
         }
+        __threadfence();
+        grid.sync();
+        // ---- 3. close the columns (lines of the transposed planes) that cross a re-transposed block
+        for (int x = warp; x < W; x += nwarps)
+            if (all || *((volatile uint8_t *)(rt.cd + (x >> 6)))) ch |= line_closure(rt.fwT, rt.bwT, rt.aNt, rt.aSt, (size_t)x * rt.wpT, rt.wpT, H, lane, rt.bdT + (x >> 6), nbx);
         if (__syncthreads_or(ch) && threadIdx.x == 0) *flag = 1;
+        __threadfence();
+        grid.sync();
+        // ---- 4. changed blocks -> row-major planes
+        for (int i = gtid; i < nbx; i += nth) rt.cd[i] = 0;
+        for (int patch = blockIdx.x; patch < px * py; patch += gridDim.x) {
+            const int bx = (patch % px) * 4 + (wid & 3), by = (patch / px) * 2 + (wid >> 2);
+            if (bx >= nbx || by >= nby) continue;
+            uint8_t *d = rt.bdT + (size_t)by * nbx + bx;
+            if (!*((volatile uint8_t *)d)) continue;
+            transpose_block(rt.fwT, W, rt.wpT, bp.fw, H, bp.wp, by, bx, lane, true);   // block (bx, by) of the row-major planes = block (by, bx) of the transposed ones
+            transpose_block(rt.bwT, W, rt.wpT, bp.bw, H, bp.wp, by, bx, lane, true);
+            if (lane == 0) { *d = 0; rt.rd[by] = 1; }
+        }
         __threadfence();
         grid.sync();
         const int any = *((volatile int32_t *)flag);
@@ -618,6 +627,7 @@ using namespace tsim;
 struct LightsWs {   // fixed part of the workspace, shared by the three stages
     int32_t *scal;   // [0..1] pivot candidates, [4..5] link totals, [8..11] reach flags, [12] n_cr
     Bits bp;
+    ReachT rt;
     int32_t *cr_prefix, *tl_prefix, *scan_tmp, *cr_cell;
     u64 *rec;
     int W, H, wp, cap_cr;
@@ -638,6 +648,13 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
     u64 **planes[] = {&L.bp.aN, &L.bp.aE, &L.bp.aS, &L.bp.aW, &L.bp.I, &L.bp.R, &L.bp.fw, &L.bp.bw, &L.bp.cr, &L.bp.tl};
     for (u64 **pl : planes) *pl = (u64 *)take((size_t)L.nw * 8);
     L.bp.wp = L.wp;
+    L.rt.wpT = div_up(L.H, 64);
+    u64 **tplanes[] = {&L.rt.aNt, &L.rt.aSt, &L.rt.fwT, &L.rt.bwT};
+    for (u64 **pl : tplanes) *pl = (u64 *)take((size_t)L.rt.wpT * L.W * 8);
+    L.rt.bdR = (uint8_t *)take((size_t)L.rt.wpT * L.wp);
+    L.rt.bdT = (uint8_t *)take((size_t)L.rt.wpT * L.wp);
+    L.rt.rd = (uint8_t *)take((size_t)L.rt.wpT);
+    L.rt.cd = (uint8_t *)take((size_t)L.wp);
     L.cr_prefix = (int32_t *)take((size_t)L.nw * 4);
     L.tl_prefix = (int32_t *)take((size_t)L.nw * 4);
     L.scan_tmp = (int32_t *)take((size_t)(div_up(L.nw, SCAN_TILE) + 1) * 4);
@@ -708,11 +725,12 @@ extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t *changed, 
     TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reach_kernel, 256, 0));
     int grid = sms * (per_sm < 1 ? 1 : per_sm);
-    const int want = div_up(L.H, 8) > L.wp ? div_up(L.H, 8) : L.wp;   // 8 rows per CTA in the row sweep, one word column per CTA in the column sweep
+    const int want = div_up(L.H > L.W ? L.H : L.W, 8);   // one warp per row / per column
     if (grid > want) grid = want;
     int32_t *flags = L.scal + 8;
     TSIM_CUDA(cudaMemsetAsync(flags, 0, 16, cs));
-    void *args[] = {&L.H, &L.bp, &flags, &changed, &err_flag};
+    TSIM_CUDA(cudaMemsetAsync(L.rt.bdR, 0, (size_t)((char *)L.rt.cd - (char *)L.rt.bdR) + L.wp, cs));   // the four flag arrays are contiguous
+    void *args[] = {&L.W, &L.H, &L.bp, &L.rt, &flags, &changed, &err_flag};
     TSIM_COOP_LAUNCH(reach_kernel, dim3(grid), dim3(256), args, cs);
     return TSIM_OK;
 }
