@@ -110,6 +110,8 @@ SYNTH = [
     (102, dict(width=1024, height=768, ring_road_type="R1"), True),
     (103, dict(width=1000, height=1000), False),            # width not a multiple of 16: scalar paths
     (104, dict(width=2048, height=2048, optimized_intersections=False), True),
+    (105, dict(width=640, height=512, block_entrance_road_level=1), True),     # road-level filter of the entrance pass
+    (106, dict(width=512, height=640, block_entrance_road_level=2, ring_road_type="R3"), False),
 ]
 
 

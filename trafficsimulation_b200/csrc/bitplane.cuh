@@ -1,0 +1,68 @@
+// bitplane.cuh -- helpers for the 64-cells-per-word bit-planes shared by the labelling, entrance and light passes
+#pragma once
+#include "common.cuh"
+
+namespace tsim {
+
+typedef unsigned long long u64;
+
+// In-register transpose of a 64 x 64 bit block held by a warp as rows `lane` (a0) and `lane + 32` (a1): six
+// butterfly stages (Hacker's Delight), the five cross-lane ones with one 64-bit shuffle per word.
+__device__ __forceinline__ void t64(u64 &a0, u64 &a1, int lane) {
+    { const u64 t = ((a0 >> 32) ^ a1) & 0x00000000ffffffffull; a0 ^= t << 32; a1 ^= t; }
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const u64 m = j == 16 ? 0x0000ffff0000ffffull : j == 8 ? 0x00ff00ff00ff00ffull : j == 4 ? 0x0f0f0f0f0f0f0f0full
+                    : j == 2 ? 0x3333333333333333ull : 0x5555555555555555ull;
+        const u64 p0 = __shfl_xor_sync(0xffffffffu, a0, j), p1 = __shfl_xor_sync(0xffffffffu, a1, j);
+        if ((lane & j) == 0) { a0 ^= (((a0 >> j) ^ p0) & m) << j; a1 ^= (((a1 >> j) ^ p1) & m) << j; }
+        else { a0 ^= ((p0 >> j) ^ a0) & m; a1 ^= ((p1 >> j) ^ a1) & m; }
+    }
+}
+
+// rows by*64 .. by*64+63 of word column bx of `src` ([src_rows][src_wp]) become words `by` of rows bx*64 .. bx*64+63
+// of `dst` ([dst_rows][dst_wp])
+__device__ __forceinline__ void transpose_block(const u64 *__restrict__ src, int src_rows, int src_wp, u64 *__restrict__ dst, int dst_rows, int dst_wp,
+                                                int bx, int by, int lane, bool coherent) {
+    const int r0 = by * 64 + lane, r1 = r0 + 32;
+    const u64 *p0 = src + (size_t)r0 * src_wp + bx, *p1 = src + (size_t)r1 * src_wp + bx;
+    u64 a0 = r0 < src_rows ? (coherent ? __ldcg(p0) : *p0) : 0ull, a1 = r1 < src_rows ? (coherent ? __ldcg(p1) : *p1) : 0ull;
+    t64(a0, a1, lane);
+    const int d0 = bx * 64 + lane, d1 = d0 + 32;
+    if (d0 < dst_rows) dst[(size_t)d0 * dst_wp + by] = a0;
+    if (d1 < dst_rows) dst[(size_t)d1 * dst_wp + by] = a1;
+}
+
+
+// 16-bit membership mask of a 16-byte strip: bit k = type byte k is in `set` (bit t of `set` = type t)
+__device__ __forceinline__ uint32_t strip_set_mask(const uint4 &q, uint32_t set) {
+    uint32_t m = 0;
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) m |= ((set >> ((w[k] >> (8 * b)) & 31u)) & 1u) << (4 * k + b);
+    return m;
+}
+
+// four lanes of a quad hold the 16-bit masks of four consecutive strips -> the 64-bit word (valid in every lane of the quad)
+__device__ __forceinline__ u64 quad_pack(uint32_t m16, int q) {
+    u64 v = (u64)m16 << (16 * q);
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// bits [start, start + len) of a bit-row of `nwords` words (len <= 64); positions outside the row read as 0
+__device__ __forceinline__ u64 extract_bits(const u64 *__restrict__ row, int nwords, int start, int len) {
+    int shl = 0;
+    if (start < 0) { shl = -start; len += start; start = 0; }
+    if (len <= 0 || row == nullptr) return 0ull;
+    const int w = start >> 6, b = start & 63;
+    const u64 lo = w < nwords ? row[w] : 0ull, hi = w + 1 < nwords ? row[w + 1] : 0ull;
+    u64 v = b ? (lo >> b) | (hi << (64 - b)) : lo;
+    if (len < 64) v &= (1ull << len) - 1ull;
+    return v << shl;
+}
+
+}  // namespace tsim

@@ -7,7 +7,7 @@
 // cell becomes the BlockEntrance.  Blocks are independent: an entrance never changes another
 // block's ring or its road contacts (BlockEntrance is neither in the region test nor in
 // _touches_road's type list).
-#include "common.cuh"
+#include "bitplane.cuh"
 
 namespace tsim {
 
@@ -143,70 +143,102 @@ __global__ void __launch_bounds__(128) entrances_kernel(tsim_cfg c, uint8_t *T, 
 // Rectangular blocks (size == bounding-box area: almost every block of a city).  Their ring is the four
 // sides just outside the box, without the corners, and cells of different sides are never 4-adjacent,
 // so the runs are simply the maximal segments of road-touching cells on each side: no tile, no
-// union-find, no block_id reads.  One warp per block: lanes test the ring cells (three type loads
-// each), four ballots give the sides as bit-strings, lane 0 walks the handful of runs.
+// union-find, no block_id reads.  The road-touch test runs on BIT-PLANES: TR = cell has a type
+// _touches_road accepts (row-major) and its transpose TRt; a side's bit-string is the OR of three
+// <= 64-bit extractions (the ring row shifted left and right, and the row outside it).  ONE THREAD per
+// block: ~24 word loads from planes that live in L2, then a walk over the handful of runs.
 // Anything else (non-rectangular, or a side longer than 64) goes to `gen_list` for the tile kernel.
-__device__ __forceinline__ int run_len_at(unsigned long long m, int s) {   // length of the run of ones starting at bit s
-    const unsigned long long inv = ~(m >> s);
+__device__ __forceinline__ int run_len_at(u64 m, int s) {   // length of the run of ones starting at bit s
+    const u64 inv = ~(m >> s);
     const int l = inv ? __ffsll((long long)inv) - 1 : 64;
     return min(l, 64 - s);
 }
 
-__global__ void __launch_bounds__(256) entrances_rect_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B,
+struct EntPlanes { const u64 *tr, *trt, *pr, *prt; int wp, wpT; };   // pr / prt: preferred road level (NULL when the filter is off)
+
+// one 16-cell strip per thread -> TR (and PR) words
+__global__ void __launch_bounds__(256) ent_bits_kernel(int W, int LH, int wp, const uint8_t *__restrict__ T, int level, u64 *__restrict__ TR,
+                                                       u64 *__restrict__ PR) {
+    const int spr = wp * 4;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = threadIdx.x & 3;
+    const long long y = g / spr;
+    const int s = (int)(g % spr), x0 = s * 16;
+    const bool row_ok = y < LH;
+    const uint32_t pref_set = M(T_R1) | (level < 2 ? M(T_R2) : 0u);
+    uint32_t mt = 0, mp = 0;
+    if (row_ok && x0 < W) {
+        const size_t base = (size_t)y * W + x0;
+        if ((W & 15) == 0) {
+            const uint4 tq = *reinterpret_cast<const uint4 *>(T + base);
+            mt = strip_set_mask(tq, SET_TOUCH_ROAD);
+            if (PR) mp = strip_set_mask(tq, pref_set);
+        } else {
+            for (int k = 0; k < 16 && x0 + k < W; k++) {
+                const int t = T[base + k];
+                mt |= (uint32_t)in_set(SET_TOUCH_ROAD, t) << k;
+                mp |= (uint32_t)in_set(pref_set, t) << k;
+            }
+        }
+    }
+    const u64 wt = quad_pack(mt, q);
+    if (row_ok && q == 0) TR[(size_t)y * wp + (s >> 2)] = wt;
+    if (PR) {   // uniform branch
+        const u64 wq = quad_pack(mp, q);
+        if (row_ok && q == 0) PR[(size_t)y * wp + (s >> 2)] = wq;
+    }
+}
+
+// dst ([dst_rows][dst_wp]) = transpose of src ([src_rows][src_wp]); CTA = 4 (bx) x 2 (by) blocks of 64 x 64 bits
+__global__ void __launch_bounds__(256) bit_transpose_kernel(const u64 *__restrict__ src, int src_rows, int src_wp, u64 *__restrict__ dst, int dst_rows,
+                                                            int dst_wp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nbx = src_wp, nby = (src_rows + 63) >> 6;
+    const int px = (nbx + 3) >> 2;
+    const int bx = (blockIdx.x % px) * 4 + (wid & 3), by = (blockIdx.x / px) * 2 + (wid >> 2);
+    if (bx < nbx && by < nby) transpose_block(src, src_rows, src_wp, dst, dst_rows, dst_wp, bx, by, lane, false);
+}
+
+__global__ void __launch_bounds__(256) entrances_rect_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B, EntPlanes ep,
                                                              const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs, int cap_blobs,
                                                              const int32_t *__restrict__ id_base, const int32_t *__restrict__ run_by_block, int n_tape,
                                                              int32_t *entrances, int32_t *n_gen, int32_t *gen_list, int32_t *err) {
-    typedef unsigned long long u64;
-    const int lane = threadIdx.x & 31;
     const int nb = min(*n_blobs, cap_blobs);
     const int W = c.width, H = c.win_rows;   // window-local rows throughout
     const int base = id_base ? *id_base : 0;
     const int level = c.block_entrance_road_level;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int bk = gw; bk < nb; bk += nwarps) {
+    for (int bk = blockIdx.x * blockDim.x + threadIdx.x; bk < nb; bk += gridDim.x * blockDim.x) {
         const int b = bk + 1 + base;         // block id as stored in block_id
         const int32_t *bl = blobs + (size_t)bk * TSIM_BLOB_STRIDE;
         const int root = bl[5];
-        if (lane == 0) entrances[bk] = -1;
+        entrances[bk] = -1;
         if (b < 1) continue;                 // cut by the window's lower edge: not owned here
         if (T[root] > T_OTH) continue;       // Empty blocks get no entrance (:902)
         const int bx0 = bl[0], bx1 = bl[2], by0 = bl[1] - c.win_y0, by1 = bl[3] - c.win_y0;
         if ((by0 == 0 && c.win_y0 > 0) || (by1 == H - 1 && c.win_y0 + H < c.height)) continue;   // cut by a window edge: the owner sees it whole
-        if (b > n_tape) { if (lane == 0) *err = 1; continue; }
+        if (b > n_tape) { *err = 1; continue; }
         const int w = bx1 - bx0 + 1, h = by1 - by0 + 1;
-        if ((long long)w * h != bl[4] || w > 64 || h > 64) { if (lane == 0) gen_list[atomicAdd(n_gen, 1)] = bk; continue; }
-        // sides: 0 bottom (y = by0-1), 1 left (x = bx0-1), 2 right (x = bx1+1), 3 top (y = by1+1); bit j = j-th cell from the low end
-        u64 mk[4] = {0, 0, 0, 0}, pf[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-            const bool horiz = (s == 0 || s == 3);
-            const int len = horiz ? w : h;
-            const int fx = s == 1 ? bx0 - 1 : (s == 2 ? bx1 + 1 : bx0), fy = s == 0 ? by0 - 1 : (s == 3 ? by1 + 1 : by0);
-            if (fx < 0 || fx >= W || fy < 0 || fy >= H) continue;   // the side lies outside the window
-            for (int j0 = 0; j0 < len; j0 += 32) {
-                const int j = j0 + lane;
-                bool touch = false, pref = false;
-                if (j < len) {
-                    const int x = horiz ? fx + j : fx, y = horiz ? fy : fy + j;
-                    // the three neighbours that are not the block itself (a zone cell is never a road)
-                    const int ox[3] = {horiz ? -1 : 0, horiz ? 1 : 0, s == 1 ? -1 : (s == 2 ? 1 : 0)};
-                    const int oy[3] = {horiz ? 0 : -1, horiz ? 0 : 1, s == 0 ? -1 : (s == 3 ? 1 : 0)};
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const int nx = x + ox[k], ny = y + oy[k];
-                        if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
-                        const int t = T[(size_t)ny * W + nx];
-                        touch |= in_set(SET_TOUCH_ROAD, t);
-                        pref |= (t == T_R1) || (t == T_R2 && level < 2);
-                    }
-                }
-                const u64 bm = __ballot_sync(0xffffffffu, touch), bp = __ballot_sync(0xffffffffu, touch && pref);
-                mk[s] |= bm << j0; pf[s] |= bp << j0;
-            }
+        if ((long long)w * h != bl[4] || w > 64 || h > 64) { gen_list[atomicAdd(n_gen, 1)] = bk; continue; }
+        // sides: 0 bottom (y = by0-1), 1 left (x = bx0-1), 2 right (x = bx1+1), 3 top (y = by1+1); bit j = j-th cell from the low end.
+        // A ring cell is marked when one of its three neighbours that are not the block itself has a road type
+        // (a zone cell is never a road): its two neighbours along the side and the cell outside.
+        auto side = [&](const u64 *pl, const u64 *plt, u64 (&m)[4]) {
+            auto rowp = [&](int y) { return (y >= 0 && y < H) ? pl + (size_t)y * ep.wp : nullptr; };
+            auto colp = [&](int x) { return (x >= 0 && x < W) ? plt + (size_t)x * ep.wpT : nullptr; };
+            const int yb = by0 - 1, yt = by1 + 1, xl = bx0 - 1, xr = bx1 + 1;
+            m[0] = yb >= 0 ? extract_bits(rowp(yb), ep.wp, bx0 - 1, w) | extract_bits(rowp(yb), ep.wp, bx0 + 1, w) | extract_bits(rowp(yb - 1), ep.wp, bx0, w) : 0ull;
+            m[3] = yt < H ? extract_bits(rowp(yt), ep.wp, bx0 - 1, w) | extract_bits(rowp(yt), ep.wp, bx0 + 1, w) | extract_bits(rowp(yt + 1), ep.wp, bx0, w) : 0ull;
+            m[1] = xl >= 0 ? extract_bits(colp(xl), ep.wpT, by0 - 1, h) | extract_bits(colp(xl), ep.wpT, by0 + 1, h) | extract_bits(colp(xl - 1), ep.wpT, by0, h) : 0ull;
+            m[2] = xr < W ? extract_bits(colp(xr), ep.wpT, by0 - 1, h) | extract_bits(colp(xr), ep.wpT, by0 + 1, h) | extract_bits(colp(xr + 1), ep.wpT, by0, h) : 0ull;
+        };
+        u64 mk[4];
+        side(ep.tr, ep.trt, mk);
+        if (level > 0) {   // :911-923
+            u64 pf[4];
+            side(ep.pr, ep.prt, pf);
+            if ((pf[0] & mk[0]) | (pf[1] & mk[1]) | (pf[2] & mk[2]) | (pf[3] & mk[3])) { mk[0] &= pf[0]; mk[1] &= pf[1]; mk[2] &= pf[2]; mk[3] &= pf[3]; }
         }
-        if (level > 0 && (pf[0] | pf[1] | pf[2] | pf[3])) { mk[0] &= pf[0]; mk[1] &= pf[1]; mk[2] &= pf[2]; mk[3] &= pf[3]; }   // :911-923
         if (!(mk[0] | mk[1] | mk[2] | mk[3])) continue;   // land-locked block (:907-908)
-        if (lane != 0) continue;
         int maxlen = 0;
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -221,8 +253,8 @@ __global__ void __launch_bounds__(256) entrances_rect_kernel(tsim_cfg c, uint8_t
         // bottom side by x, then left / right runs by their first row (left before right), then the top side
         const int want = run_by_block[b - 1];
         int seen = 0, cs = -1, cst = 0;
-        auto visit = [&](int side, int st, int l) {
-            if (l == maxlen) { if (seen == want) { cs = side; cst = st; } seen++; }
+        auto visit = [&](int sd, int st, int l) {
+            if (l == maxlen) { if (seen == want) { cs = sd; cst = st; } seen++; }
         };
         {
             u64 m = mk[0];
@@ -420,15 +452,32 @@ extern "C" tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_pla
         set_error("tsim_layout_entrances: bad arguments");
         return TSIM_ERR_CONFIG;
     }
-    const size_t need = 256 + 2 * (((size_t)blobs->cap * 4 + 255) & ~(size_t)255);
+    const int W = cfg->width, LH = cfg->win_rows, wp = div_up(W, 64), wpT = div_up(LH, 64);
+    const bool pref = cfg->block_entrance_road_level > 0;
+    const size_t list_bytes = ((size_t)blobs->cap * 4 + 255) & ~(size_t)255;
+    const size_t plane_bytes = ((size_t)wp * LH * 8 + 255) & ~(size_t)255, planeT_bytes = ((size_t)wpT * W * 8 + 255) & ~(size_t)255;
+    const size_t need = 256 + 2 * list_bytes + (pref ? 2 : 1) * (plane_bytes + planeT_bytes);
     if (!workspace || ws_bytes < need) { set_error("tsim_layout_entrances needs %zu workspace bytes, got %zu", need, ws_bytes); return TSIM_ERR_WORKSPACE; }
     if (n_tape <= 0) return TSIM_OK;
     cudaStream_t cs = (cudaStream_t)stream;
-    int32_t *n_big = (int32_t *)workspace, *n_gen = n_big + 1, *big_list = (int32_t *)((char *)workspace + 256);
-    int32_t *gen_list = (int32_t *)((char *)big_list + (((size_t)blobs->cap * 4 + 255) & ~(size_t)255));
+    char *wsp = (char *)workspace;
+    int32_t *n_big = (int32_t *)wsp, *n_gen = n_big + 1, *big_list = (int32_t *)(wsp + 256);
+    int32_t *gen_list = (int32_t *)(wsp + 256 + list_bytes);
+    u64 *TR = (u64 *)(wsp + 256 + 2 * list_bytes), *TRt = (u64 *)((char *)TR + plane_bytes);
+    u64 *PR = pref ? (u64 *)((char *)TRt + planeT_bytes) : nullptr, *PRt = pref ? (u64 *)((char *)PR + plane_bytes) : nullptr;
     TSIM_CUDA(cudaMemsetAsync(n_big, 0, 8, cs));
-    const int rgrid = div_up(blobs->cap, 8) < 148 * 8 ? div_up(blobs->cap, 8) : 148 * 8;
-    entrances_rect_kernel<<<rgrid, 256, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, blobs->count, blobs->cap,
+    ent_bits_kernel<<<div_up((long long)wp * LH * 4, 256), 256, 0, cs>>>(W, LH, wp, p->cell_type, cfg->block_entrance_road_level, TR, PR);
+    TSIM_LAUNCH_CHECK();
+    const int tgrid = div_up(wp, 4) * div_up(wpT, 2);
+    bit_transpose_kernel<<<tgrid, 256, 0, cs>>>(TR, LH, wp, TRt, W, wpT);
+    TSIM_LAUNCH_CHECK();
+    if (pref) {
+        bit_transpose_kernel<<<tgrid, 256, 0, cs>>>(PR, LH, wp, PRt, W, wpT);
+        TSIM_LAUNCH_CHECK();
+    }
+    EntPlanes ep{TR, TRt, PR, PRt, wp, wpT};
+    const int rgrid = div_up(blobs->cap, 256) < 148 * 8 ? div_up(blobs->cap, 256) : 148 * 8;
+    entrances_rect_kernel<<<rgrid, 256, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, ep, blobs->table, blobs->count, blobs->cap,
                                                  blobs->id_base, run_by_block, n_tape, entrances, n_gen, gen_list, err_flag);
     TSIM_LAUNCH_CHECK();
     const int wgrid = div_up(blobs->cap, ENT_WARPS) < 148 * 6 ? div_up(blobs->cap, ENT_WARPS) : 148 * 6;   // 6 CTAs of 37 KB shared memory per SM

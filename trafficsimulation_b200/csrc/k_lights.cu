@@ -34,12 +34,12 @@
 //      light cells only (sparse), never as a full-plane sweep.
 #include <cooperative_groups.h>
 #include "scan.cuh"
+#include "bitplane.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace tsim {
 
-typedef unsigned long long u64;
 
 constexpr int BFS_CAP = 160;        // visited cells of an exact fallback search
 constexpr int MAX_TL_RANGE = 30;    // reverse-scan lengths are kept in 5 bits
@@ -251,33 +251,6 @@ __device__ bool line_closure(u64 *__restrict__ fpl, u64 *__restrict__ bpl, const
         if (!ch && pass >= 1) break;
     }
     return any;
-}
-
-// In-register transpose of a 64 x 64 bit block held by a warp as rows `lane` (a0) and `lane + 32` (a1): six
-// butterfly stages (Hacker's Delight), the five cross-lane ones with one 64-bit shuffle per word.
-__device__ __forceinline__ void t64(u64 &a0, u64 &a1, int lane) {
-    { const u64 t = ((a0 >> 32) ^ a1) & 0x00000000ffffffffull; a0 ^= t << 32; a1 ^= t; }
-#pragma unroll
-    for (int j = 16; j >= 1; j >>= 1) {
-        const u64 m = j == 16 ? 0x0000ffff0000ffffull : j == 8 ? 0x00ff00ff00ff00ffull : j == 4 ? 0x0f0f0f0f0f0f0f0full
-                    : j == 2 ? 0x3333333333333333ull : 0x5555555555555555ull;
-        const u64 p0 = __shfl_xor_sync(0xffffffffu, a0, j), p1 = __shfl_xor_sync(0xffffffffu, a1, j);
-        if ((lane & j) == 0) { a0 ^= (((a0 >> j) ^ p0) & m) << j; a1 ^= (((a1 >> j) ^ p1) & m) << j; }
-        else { a0 ^= ((p0 >> j) ^ a0) & m; a1 ^= ((p1 >> j) ^ a1) & m; }
-    }
-}
-
-// rows by*64 .. by*64+63 of word column bx of `src` ([src_rows][src_wp]) become words `by` of rows bx*64 .. bx*64+63
-// of `dst` ([dst_rows][dst_wp])
-__device__ __forceinline__ void transpose_block(const u64 *__restrict__ src, int src_rows, int src_wp, u64 *__restrict__ dst, int dst_rows, int dst_wp,
-                                                int bx, int by, int lane, bool coherent) {
-    const int r0 = by * 64 + lane, r1 = r0 + 32;
-    const u64 *p0 = src + (size_t)r0 * src_wp + bx, *p1 = src + (size_t)r1 * src_wp + bx;
-    u64 a0 = r0 < src_rows ? (coherent ? __ldcg(p0) : *p0) : 0ull, a1 = r1 < src_rows ? (coherent ? __ldcg(p1) : *p1) : 0ull;
-    t64(a0, a1, lane);
-    const int d0 = bx * 64 + lane, d1 = d0 + 32;
-    if (d0 < dst_rows) dst[(size_t)d0 * dst_wp + by] = a0;
-    if (d1 < dst_rows) dst[(size_t)d1 * dst_wp + by] = a1;
 }
 
 // Persistent cooperative kernel: alternate row closures of the row-major planes and row closures of the TRANSPOSED

@@ -66,6 +66,56 @@ __device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, u
     }
 }
 
+// The 4-neighbourhood of a 16-cell strip held in registers: the strip itself, the strips above and below it and the
+// two cells left and right of it.  The neighbour taps of a candidate cell then cost no memory instruction at all.
+struct StripView {
+    uint32_t r[3][4];   // rows yc-1, yc, yc+1 (16 type bytes each; 0xff.. when the row does not exist)
+    int left, right;    // cells (x0-1, yc) and (x0+16, yc), -1 outside the grid
+    int x0, yc;
+    const uint16_t *D; int W, y0;
+    __device__ __forceinline__ static int byte_of(const uint32_t (&w)[4], int k) {
+        const uint32_t v = k < 8 ? (k < 4 ? w[0] : w[1]) : (k < 12 ? w[2] : w[3]);
+        return (int)((v >> (8 * (k & 3))) & 0xffu);
+    }
+    __device__ __forceinline__ int t(int x, int y) const {   // (x, y) in the 4-neighbourhood of a strip cell
+        const int k = x - x0;
+        if (y == yc) return k < 0 ? left : (k > 15 ? right : byte_of(r[1], k));
+        const int v = byte_of(r[y < yc ? 0 : 2], k);
+        return v == 0xff ? -1 : v;
+    }
+    __device__ __forceinline__ uint32_t d(int x, int y) const { return D[(size_t)(y - y0) * W + x]; }
+    __device__ __forceinline__ size_t at(int x, int y) const { return (size_t)(y - y0) * W + x; }
+};
+
+// sparse sweep with the neighbourhood in registers: f(x, y, view) for every cell whose type is in `set` (W % 16 == 0)
+template <class F>
+__device__ __forceinline__ void sparse_sweep3(const Shard &s, const uint8_t *T, const uint16_t *D, uint32_t set, F f, long long tid, long long nthreads) {
+    const int sw = s.W >> 4;
+    const long long nstrips = (long long)sw * (s.yhi - s.ylo);
+    for (long long i = tid; i < nstrips; i += nthreads) {
+        const int y = s.ylo + (int)(i / sw), x0 = (int)(i % sw) << 4;
+        const uint8_t *row = T + (size_t)(y - s.y0) * s.W + x0;
+        const uint4 q = *reinterpret_cast<const uint4 *>(row);
+        uint32_t m = strip_mask(q, set);
+        if (!m) continue;
+        StripView v;
+        const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        const uint4 qd = y > s.y0 ? *reinterpret_cast<const uint4 *>(row - s.W) : none;
+        const uint4 qu = y + 1 < s.y0 + s.nrows ? *reinterpret_cast<const uint4 *>(row + s.W) : none;
+        v.r[0][0] = qd.x; v.r[0][1] = qd.y; v.r[0][2] = qd.z; v.r[0][3] = qd.w;
+        v.r[1][0] = q.x; v.r[1][1] = q.y; v.r[1][2] = q.z; v.r[1][3] = q.w;
+        v.r[2][0] = qu.x; v.r[2][1] = qu.y; v.r[2][2] = qu.z; v.r[2][3] = qu.w;
+        v.left = x0 > 0 ? (int)row[-1] : -1;
+        v.right = x0 + 16 < s.W ? (int)row[16] : -1;
+        v.x0 = x0; v.yc = y; v.D = D; v.W = s.W; v.y0 = s.y0;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            f(x0 + b, y, v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // dead ends: persistent cooperative kernel, sweeps until a whole sweep changes nothing.
 // Removal is monotone (a removed cell never comes back and only lowers its neighbours' counts), so
@@ -92,7 +142,7 @@ __global__ void __launch_bounds__(256) dead_ends_kernel(Shard s, uint8_t *T, uin
     for (;;) {
         sweeps++;
         bool changed = false;
-        sparse_sweep(s, T, SET_REMOVABLE, [&](int x, int y) {
+        auto remove_from = [&](int x, int y) {
             int cx = x, cy = y;
             for (int guard = 0; guard < (1 << 20); guard++) {
                 if (!dead_end_cell(v, cx, cy)) break;
@@ -110,7 +160,25 @@ __global__ void __launch_bounds__(256) dead_ends_kernel(Shard s, uint8_t *T, uin
                 if (nx < 0 || ny < s.ylo || ny >= s.yhi) break;
                 cx = nx; cy = ny;
             }
-        }, tid, nthreads);
+        };
+        if (sweeps == 1 && (s.W & 15) == 0) {
+            // First sweep: candidates are found from register strips (plain cached loads).  A stale type can only show
+            // MORE road neighbours than there are now, i.e. miss a dead end that another thread is creating right now --
+            // and that thread follows the stub it exposes with coherent loads.  If this sweep removes nothing, nothing
+            // was written at all and the result is exact; otherwise the coherent sweeps below run to the fixed point.
+            sparse_sweep3(s, T, D, SET_REMOVABLE, [&](int x, int y, const StripView &sv) {
+                // rows beyond a shard cut are unknown = road (see CoherentView)
+                auto rl = [&](int xx, int yy) {
+                    if (yy < 0 || yy >= s.H) return false;
+                    if (yy < s.y0 || yy >= s.y0 + s.nrows) return true;
+                    return is_road_like(sv.t(xx, yy));
+                };
+                const int n = (int)rl(x + 1, y) + (int)rl(x - 1, y) + (int)rl(x, y + 1) + (int)rl(x, y - 1);
+                if (n < 2) remove_from(x, y);
+            }, tid, nthreads);
+        } else {
+            sparse_sweep(s, T, SET_REMOVABLE, remove_from, tid, nthreads);
+        }
         if (changed) flags[0] = 1;
         grid.sync();
         const int any = *((volatile int32_t *)flags);
@@ -125,42 +193,57 @@ __global__ void __launch_bounds__(256) dead_ends_kernel(Shard s, uint8_t *T, uin
 __global__ void __launch_bounds__(256) upgrade_r2_kernel(tsim_cfg c, Shard s, uint8_t *T, uint16_t *D, uint8_t *A,
                                                          const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt, int32_t *err) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-    const PlaneView v = make_view(s, T, D, A);
-    sparse_sweep(s, T, M(T_R2), [&](int x, int y) {
+    const PlaneView pv = make_view(s, T, D, A);
+    auto cell = [&](int x, int y, const auto &v) {
         int t_new; uint32_t d_new;
         const int r = upgrade_r2_cell(c, v, __ldg(rowt + y), __ldg(colt + x), x, y, t_new, d_new);
         if (r == 0) return;
         if (r == 3) { *err = 1; return; }
-        const size_t i = v.at(x, y);
+        const size_t i = pv.at(x, y);
         // in place is safe: the pass reads Sidewalk-ness and sub-block-road-ness of neighbours, which it
         // never changes (an R2 neighbour matters only when subblock_road_type == R2, where the cell's own
         // type already decides).
         T[i] = (uint8_t)t_new; D[i] = (uint16_t)d_new;
         const uint8_t a = A[i] & (AUX_RING | AUX_EVER);
         A[i] = r == 1 ? (uint8_t)(a | AUX_EVER) : (uint8_t)(a & ~AUX_EVER);
-    }, tid, nthreads);
+    };
+    if ((s.W & 15) == 0) sparse_sweep3(s, T, D, M(T_R2), cell, tid, nthreads);
+    else sparse_sweep(s, T, M(T_R2), [&](int x, int y) { cell(x, y, pv); }, tid, nthreads);
 }
 
 __global__ void __launch_bounds__(256) validate_dirs_kernel(Shard s, const uint8_t *T, uint16_t *D) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-    const PlaneView v = make_view(s, T, D, nullptr);
+    const PlaneView pv = make_view(s, T, D, nullptr);
     // in place is safe: only Intersection lists are written, and an Intersection neighbour's list is never read
-    sparse_sweep(s, T, M(T_INTER), [&](int x, int y) {
-        const size_t i = v.at(x, y);
+    auto cell = [&](int x, int y, const auto &v) {
+        const size_t i = pv.at(x, y);
         const uint32_t od = D[i], nd = validate_dirs_cell(v, x, y, od);
         if (nd != od) D[i] = (uint16_t)nd;
-    }, tid, nthreads);
+    };
+    if ((s.W & 15) == 0) sparse_sweep3(s, T, D, M(T_INTER), cell, tid, nthreads);
+    else sparse_sweep(s, T, M(T_INTER), [&](int x, int y) { cell(x, y, pv); }, tid, nthreads);
 }
 
 __global__ void __launch_bounds__(256) entrance_dirs_kernel(Shard s, const uint8_t *T, uint16_t *D) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-    const PlaneView v = make_view(s, T, D, nullptr);
+    const PlaneView pv = make_view(s, T, D, nullptr);
     // in place is safe: a cell's new list depends on its own old list and on neighbour TYPES only
-    sparse_sweep(s, T, SET_ROAD_LIKE, [&](int x, int y) {
-        const size_t i = v.at(x, y);
-        const uint32_t od = D[i], nd = entrance_dirs_cell(v, x, y, (int)T[i], od);
-        if (nd != od) D[i] = (uint16_t)nd;
-    }, tid, nthreads);
+    if ((s.W & 15) == 0) {
+        // register strips; the dirs word is only touched when an entrance is involved (the cell is one, or has one next to it)
+        sparse_sweep3(s, T, D, SET_ROAD_LIKE, [&](int x, int y, const StripView &v) {
+            const int t = v.t(x, y);
+            if (t != T_BE && v.t(x + 1, y) != T_BE && v.t(x - 1, y) != T_BE && v.t(x, y + 1) != T_BE && v.t(x, y - 1) != T_BE) return;
+            const size_t i = pv.at(x, y);
+            const uint32_t od = D[i], nd = entrance_dirs_cell(v, x, y, t, od);
+            if (nd != od) D[i] = (uint16_t)nd;
+        }, tid, nthreads);
+    } else {
+        sparse_sweep(s, T, SET_ROAD_LIKE, [&](int x, int y) {
+            const size_t i = pv.at(x, y);
+            const uint32_t od = D[i], nd = entrance_dirs_cell(pv, x, y, (int)T[i], od);
+            if (nd != od) D[i] = (uint16_t)nd;
+        }, tid, nthreads);
+    }
 }
 
 template <int VEC>
