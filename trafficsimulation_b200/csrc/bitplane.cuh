@@ -45,6 +45,26 @@ __device__ __forceinline__ uint32_t strip_set_mask(const uint4 &q, uint32_t set)
     return m;
 }
 
+// SWAR range test (Bit Twiddling Hacks "hasbetween"): high bit of every byte b of x with lo < b < hi (bytes >= 128 never match)
+__device__ __forceinline__ uint32_t bytes_between(uint32_t x, uint32_t lo, uint32_t hi) {
+    const uint32_t a = x & 0x7f7f7f7fu;
+    return (0x01010101u * (127u + hi) - a) & ~x & (a + 0x01010101u * (127u - lo)) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t collapse4(uint32_t hibits) { return ((hibits >> 7) * 0x01020408u) >> 24; }   // byte k's flag -> bit k
+
+// a set of cell types as at most two exclusive byte ranges (lo < t < hi); lo2 == hi2 == 0: one range only
+struct TypeRanges { uint32_t lo1, hi1, lo2, hi2; };
+__device__ __forceinline__ uint32_t strip_range_mask(const uint32_t (&w)[4], const TypeRanges r) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t h = bytes_between(w[k], r.lo1, r.hi1);
+        if (r.hi2) h |= bytes_between(w[k], r.lo2, r.hi2);
+        m |= collapse4(h) << (4 * k);
+    }
+    return m;
+}
+
 // four lanes of a quad hold the 16-bit masks of four consecutive strips -> the 64-bit word (valid in every lane of the quad)
 __device__ __forceinline__ u64 quad_pack(uint32_t m16, int q) {
     u64 v = (u64)m16 << (16 * q);

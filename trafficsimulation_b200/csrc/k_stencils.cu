@@ -12,6 +12,7 @@
 // sectors -- the algorithmic bytes of SURVEY.md §8(d).
 #include <cooperative_groups.h>
 #include "cells_stencil.cuh"
+#include "bitplane.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -66,6 +67,17 @@ __device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, u
     }
 }
 
+// type sets as exclusive byte ranges (enum order in common.cuh: R1 9, R2 10, R3 11, Intersection 12, HighwayEntrance 13,
+// HighwayExit 14, BlockEntrance 19, Sidewalk 7)
+constexpr TypeRanges RNG_ROAD_LIKE{T_R1 - 1, T_HWY_OUT + 1, T_BE - 1, T_BE + 1};
+constexpr TypeRanges RNG_REMOVABLE{T_R2 - 1, T_INTER + 1, 0, 0};
+constexpr TypeRanges RNG_R2{T_R2 - 1, T_R2 + 1, 0, 0};
+constexpr TypeRanges RNG_SIDEWALK{T_SIDEWALK - 1, T_SIDEWALK + 1, 0, 0};
+constexpr TypeRanges RNG_BE{T_BE - 1, T_BE + 1, 0, 0};
+constexpr TypeRanges RNG_INTER{T_INTER - 1, T_INTER + 1, 0, 0};
+static_assert(SET_ROAD_LIKE == (M(T_R1) | M(T_R2) | M(T_R3) | M(T_INTER) | M(T_HWY_IN) | M(T_HWY_OUT) | M(T_BE)), "RNG_ROAD_LIKE");
+static_assert(SET_REMOVABLE == (M(T_R2) | M(T_R3) | M(T_INTER)), "RNG_REMOVABLE");
+
 // The 4-neighbourhood of a 16-cell strip held in registers: the strip itself, the strips above and below it and the
 // two cells left and right of it.  The neighbour taps of a candidate cell then cost no memory instruction at all.
 struct StripView {
@@ -85,18 +97,36 @@ struct StripView {
     }
     __device__ __forceinline__ uint32_t d(int x, int y) const { return D[(size_t)(y - y0) * W + x]; }
     __device__ __forceinline__ size_t at(int x, int y) const { return (size_t)(y - y0) * W + x; }
+    // 16-bit masks "the neighbour of strip cell k in that direction has a type of `rg`"
+    struct Nbr { uint32_t c, up, dn, lf, rt; };
+    __device__ __forceinline__ Nbr neighbours(const TypeRanges rg, bool in_left, bool in_right) const {
+        Nbr n;
+        n.c = strip_range_mask(r[1], rg); n.up = strip_range_mask(r[2], rg); n.dn = strip_range_mask(r[0], rg);
+        n.lf = ((n.c << 1) | (uint32_t)in_left) & 0xffffu;
+        n.rt = (n.c >> 1) | ((uint32_t)in_right << 15);
+        return n;
+    }
+    __device__ __forceinline__ bool edge_in(int t, const TypeRanges rg) const {
+        return t >= 0 && (((uint32_t)t > rg.lo1 && (uint32_t)t < rg.hi1) || ((uint32_t)t > rg.lo2 && (uint32_t)t < rg.hi2));
+    }
 };
+__device__ __forceinline__ uint32_t at_least_two(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return (a & b) | (c & d) | ((a | b) & (c | d));
+}
 
 // sparse sweep with the neighbourhood in registers: f(x, y, view) for every cell whose type is in `set` (W % 16 == 0)
-template <class F>
-__device__ __forceinline__ void sparse_sweep3(const Shard &s, const uint8_t *T, const uint16_t *D, uint32_t set, F f, long long tid, long long nthreads) {
+// `refine(view, mask)` narrows the candidate mask with word-level logic on the neighbour masks before the per-cell work
+template <class R, class F>
+__device__ __forceinline__ void sparse_sweep3(const Shard &s, const uint8_t *T, const uint16_t *D, const TypeRanges set, R refine, F f, long long tid,
+                                              long long nthreads) {
     const int sw = s.W >> 4;
     const long long nstrips = (long long)sw * (s.yhi - s.ylo);
     for (long long i = tid; i < nstrips; i += nthreads) {
         const int y = s.ylo + (int)(i / sw), x0 = (int)(i % sw) << 4;
         const uint8_t *row = T + (size_t)(y - s.y0) * s.W + x0;
         const uint4 q = *reinterpret_cast<const uint4 *>(row);
-        uint32_t m = strip_mask(q, set);
+        const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+        uint32_t m = strip_range_mask(qw, set);
         if (!m) continue;
         StripView v;
         const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -108,6 +138,7 @@ __device__ __forceinline__ void sparse_sweep3(const Shard &s, const uint8_t *T, 
         v.left = x0 > 0 ? (int)row[-1] : -1;
         v.right = x0 + 16 < s.W ? (int)row[16] : -1;
         v.x0 = x0; v.yc = y; v.D = D; v.W = s.W; v.y0 = s.y0;
+        m = refine(v, m);
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
@@ -166,16 +197,13 @@ __global__ void __launch_bounds__(256) dead_ends_kernel(Shard s, uint8_t *T, uin
             // MORE road neighbours than there are now, i.e. miss a dead end that another thread is creating right now --
             // and that thread follows the stub it exposes with coherent loads.  If this sweep removes nothing, nothing
             // was written at all and the result is exact; otherwise the coherent sweeps below run to the fixed point.
-            sparse_sweep3(s, T, D, SET_REMOVABLE, [&](int x, int y, const StripView &sv) {
+            sparse_sweep3(s, T, D, RNG_REMOVABLE, [&](const StripView &sv, uint32_t m) {
+                StripView::Nbr n = sv.neighbours(RNG_ROAD_LIKE, sv.edge_in(sv.left, RNG_ROAD_LIKE), sv.edge_in(sv.right, RNG_ROAD_LIKE));
                 // rows beyond a shard cut are unknown = road (see CoherentView)
-                auto rl = [&](int xx, int yy) {
-                    if (yy < 0 || yy >= s.H) return false;
-                    if (yy < s.y0 || yy >= s.y0 + s.nrows) return true;
-                    return is_road_like(sv.t(xx, yy));
-                };
-                const int n = (int)rl(x + 1, y) + (int)rl(x - 1, y) + (int)rl(x, y + 1) + (int)rl(x, y - 1);
-                if (n < 2) remove_from(x, y);
-            }, tid, nthreads);
+                if (sv.yc + 1 >= s.y0 + s.nrows && sv.yc + 1 < s.H) n.up = 0xffffu;
+                if (sv.yc - 1 < s.y0 && sv.yc - 1 >= 0) n.dn = 0xffffu;
+                return m & ~at_least_two(n.up, n.dn, n.lf, n.rt);
+            }, [&](int x, int y, const StripView &) { remove_from(x, y); }, tid, nthreads);
         } else {
             sparse_sweep(s, T, SET_REMOVABLE, remove_from, tid, nthreads);
         }
@@ -207,7 +235,11 @@ __global__ void __launch_bounds__(256) upgrade_r2_kernel(tsim_cfg c, Shard s, ui
         const uint8_t a = A[i] & (AUX_RING | AUX_EVER);
         A[i] = r == 1 ? (uint8_t)(a | AUX_EVER) : (uint8_t)(a & ~AUX_EVER);
     };
-    if ((s.W & 15) == 0) sparse_sweep3(s, T, D, M(T_R2), cell, tid, nthreads);
+    if ((s.W & 15) == 0)
+        sparse_sweep3(s, T, D, RNG_R2, [&](const StripView &sv, uint32_t m) {   // only R2 cells with >= 2 Sidewalk neighbours can change (:850-856)
+            const StripView::Nbr n = sv.neighbours(RNG_SIDEWALK, sv.left == T_SIDEWALK, sv.right == T_SIDEWALK);
+            return m & at_least_two(n.up, n.dn, n.lf, n.rt);
+        }, cell, tid, nthreads);
     else sparse_sweep(s, T, M(T_R2), [&](int x, int y) { cell(x, y, pv); }, tid, nthreads);
 }
 
@@ -220,7 +252,7 @@ __global__ void __launch_bounds__(256) validate_dirs_kernel(Shard s, const uint8
         const uint32_t od = D[i], nd = validate_dirs_cell(v, x, y, od);
         if (nd != od) D[i] = (uint16_t)nd;
     };
-    if ((s.W & 15) == 0) sparse_sweep3(s, T, D, M(T_INTER), cell, tid, nthreads);
+    if ((s.W & 15) == 0) sparse_sweep3(s, T, D, RNG_INTER, [](const StripView &, uint32_t m) { return m; }, cell, tid, nthreads);
     else sparse_sweep(s, T, M(T_INTER), [&](int x, int y) { cell(x, y, pv); }, tid, nthreads);
 }
 
@@ -230,9 +262,11 @@ __global__ void __launch_bounds__(256) entrance_dirs_kernel(Shard s, const uint8
     // in place is safe: a cell's new list depends on its own old list and on neighbour TYPES only
     if ((s.W & 15) == 0) {
         // register strips; the dirs word is only touched when an entrance is involved (the cell is one, or has one next to it)
-        sparse_sweep3(s, T, D, SET_ROAD_LIKE, [&](int x, int y, const StripView &v) {
+        sparse_sweep3(s, T, D, RNG_ROAD_LIKE, [&](const StripView &sv, uint32_t m) {
+            const StripView::Nbr n = sv.neighbours(RNG_BE, sv.left == T_BE, sv.right == T_BE);
+            return m & (n.c | n.up | n.dn | n.lf | n.rt);
+        }, [&](int x, int y, const StripView &v) {
             const int t = v.t(x, y);
-            if (t != T_BE && v.t(x + 1, y) != T_BE && v.t(x - 1, y) != T_BE && v.t(x, y + 1) != T_BE && v.t(x, y - 1) != T_BE) return;
             const size_t i = pv.at(x, y);
             const uint32_t od = D[i], nd = entrance_dirs_cell(v, x, y, t, od);
             if (nd != od) D[i] = (uint16_t)nd;
