@@ -468,62 +468,59 @@ __global__ void __launch_bounds__(128) lights_eval_kernel(LightsCtx L, const int
     }
 }
 
-// light index of a TrafficLight cell: lights are numbered in ascending cell order
-__device__ __forceinline__ int light_id(const LightsCtx &L, const int32_t *__restrict__ tl_prefix, int cell) {
-    const int x = cell % L.W, y = cell / L.W;
-    const size_t o = (size_t)y * L.b.wp + (x >> 6);
-    return tl_prefix[o] + __popcll(L.b.tl[o] & ((1ull << (x & 63)) - 1ull));
-}
-
-// 5a. count links per light
-__global__ void __launch_bounds__(128) lights_count_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
-                                                           const u64 *__restrict__ rec, const int32_t *__restrict__ tl_prefix,
-                                                           int32_t *ctrl_cnt, int32_t *inc_cnt) {
-    const int n = *n_cr;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const u64 r = rec[i];
-        const int na = rec_nacc(r);
-        if (!na) continue;
-        const int c = cr_cell[i], nsc = rec_nsc(r);
-        for (int u = 0; u < na; u++) {
-            const int l = light_id(L, tl_prefix, rec_acc(r, u, c, L.W));
-            if (l >= L.cap_lights) continue;
-            atomicAdd(ctrl_cnt + l, 1);
-            if (nsc) atomicAdd(inc_cnt + l, nsc);
+// 5. link tables, gather form: ONE thread per light scans the 5 x 5 cells around it (a ControlledRoad lists only
+// lights within two cells, see lights_eval) in ascending cell order and takes every candidate whose record names this
+// light.  No atomics, so the tables come out in a canonical order: controlled cells ascending, incoming lane cells
+// grouped by their controlled cell in scan order.  FILL == false: counts -> ctrl_off / inc_off (scanned afterwards).
+template <bool FILL>
+__global__ void __launch_bounds__(128) light_links_kernel(LightsCtx L, const int32_t *__restrict__ n_lights, const int32_t *__restrict__ light_cell,
+                                                          const int32_t *__restrict__ cr_prefix, const u64 *__restrict__ rec, int32_t *ctrl_off,
+                                                          int32_t *inc_off, int32_t *__restrict__ ctrl_cell, int32_t *__restrict__ inc_cell, int cap_ctrl,
+                                                          int cap_inc) {
+    const int n = min(*n_lights, L.cap_lights);
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
+        const int a = light_cell[l], ax = a % L.W, ay = a / L.W;
+        int nc = 0, ni = 0;
+        int pc = FILL ? ctrl_off[l] : 0, pi = FILL ? inc_off[l] : 0;
+        for (int y = max(ay - 2, 0); y <= min(ay + 2, L.H - 1); y++) {
+            const u64 *row = L.b.cr + (size_t)y * L.b.wp;
+            u64 m = extract_bits(row, L.b.wp, ax - 2, 5);
+            while (m) {
+                const int k = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int x = ax - 2 + k, c = y * L.W + x;
+                const size_t wi = (size_t)y * L.b.wp + (x >> 6);
+                const u64 r = rec[cr_prefix[wi] + __popcll(L.b.cr[wi] & ((1ull << (x & 63)) - 1ull))];
+                bool mine = false;
+                for (int u = 0; u < rec_nacc(r); u++) mine |= rec_acc(r, u, c, L.W) == a;
+                if (!mine) continue;
+                if (!FILL) { nc++; ni += rec_nsc(r); continue; }
+                if (pc < cap_ctrl) ctrl_cell[pc] = c; else *L.err = 20;
+                pc++;
+                const uint32_t rd = L.D[c];
+                for (int d = 0; d < dl_len(rd); d++) {
+                    const int kk = opp_of(dl_get(rd, d)), step = dy_of(kk) * L.W + dx_of(kk);
+                    for (int s = 1; s <= rec_cnt(r, d); s++, pi++) { if (pi < cap_inc) inc_cell[pi] = c + s * step; else *L.err = 21; }
+                }
+            }
         }
+        if (!FILL) { ctrl_off[l] = nc; inc_off[l] = ni; }
     }
 }
 
-// 5b. fill links, set has-light bits, convert the cell (place_cell(..., "ControlledRoad") keeps the
-// arrows and remembers the original type, :1455-1459)
-__global__ void __launch_bounds__(128) lights_fill_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
-                                                          const u64 *__restrict__ rec, const int32_t *__restrict__ tl_prefix, uint8_t *T, uint8_t *A,
-                                                          int32_t *B, int32_t *ctrl_cur, int32_t *inc_cur, const int32_t *__restrict__ ctrl_off,
-                                                          const int32_t *__restrict__ inc_off, int32_t *ctrl_cell, int32_t *inc_cell, int cap_ctrl,
-                                                          int cap_inc) {
+// per candidate: set the has-light bits and convert the cell (place_cell(..., "ControlledRoad") keeps the arrows and
+// remembers the original type, :1455-1459)
+__global__ void __launch_bounds__(128) cr_apply_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
+                                                       const u64 *__restrict__ rec, uint8_t *T, uint8_t *A, int32_t *B) {
     const int n = *n_cr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const u64 r = rec[i];
         const int c = cr_cell[i];
         const int na = rec_nacc(r);
         const int t = T[c];
-        const uint32_t rd = L.D[c];
         if (na) {
-            const int nsc = rec_nsc(r);
-            for (int u = 0; u < na; u++) {
-                const int l = light_id(L, tl_prefix, rec_acc(r, u, c, L.W));
-                if (l >= L.cap_lights) continue;
-                const int pc = ctrl_off[l] + atomicAdd(ctrl_cur + l, 1);
-                if (pc < cap_ctrl) ctrl_cell[pc] = c; else *L.err = 20;
-                if (nsc) {
-                    int pi = inc_off[l] + atomicAdd(inc_cur + l, nsc);
-                    for (int d = 0; d < dl_len(rd); d++) {
-                        const int k = opp_of(dl_get(rd, d)), step = dy_of(k) * L.W + dx_of(k);
-                        for (int s = 1; s <= rec_cnt(r, d); s++, pi++) { if (pi < cap_inc) inc_cell[pi] = c + s * step; else *L.err = 21; }
-                    }
-                }
-            }
             // nb.light = tl (:1542); lost again if nb itself is converted later (a fresh CellAgent)
+            const uint32_t rd = L.D[c];
             const int cx = c % L.W, cy = c / L.W;
             for (int d = 0; d < dl_len(rd); d++) {
                 const int k = opp_of(dl_get(rd, d));
@@ -546,40 +543,6 @@ __global__ void __launch_bounds__(256) tl_apply_kernel(const int32_t *__restrict
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = light_cell[i];
         T[c] = T_TL; D[c] = 0; A[c] &= (AUX_RING | AUX_EVER);
-    }
-}
-
-// canonical order inside every light's segments (the fill order above depends on atomics): each thread
-// pulls its light's segment into a local array, sorts it there and writes it back once
-__device__ __forceinline__ void sort_segment(int32_t *a, int n) {
-    constexpr int LOCAL = 48;
-    if (n < 2) return;
-    if (n <= LOCAL) {
-        int32_t v[LOCAL];
-        for (int i = 0; i < n; i++) v[i] = a[i];
-        for (int i = 1; i < n; i++) {
-            const int32_t x = v[i];
-            int j = i - 1;
-            while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; j--; }
-            v[j + 1] = x;
-        }
-        for (int i = 0; i < n; i++) a[i] = v[i];
-    } else {
-        for (int i = 1; i < n; i++) {
-            const int32_t x = a[i];
-            int j = i - 1;
-            while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; j--; }
-            a[j + 1] = x;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128) links_sort_kernel(const int32_t *__restrict__ n_lights, int cap, const int32_t *__restrict__ ctrl_off,
-                                                         int32_t *ctrl_cell, const int32_t *__restrict__ inc_off, int32_t *inc_cell) {
-    const int n = min(*n_lights, cap);
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
-        sort_segment(ctrl_cell + ctrl_off[l], ctrl_off[l + 1] - ctrl_off[l]);
-        sort_segment(inc_cell + inc_off[l], inc_off[l + 1] - inc_off[l]);
     }
 }
 
@@ -737,7 +700,6 @@ extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes
     size_t o = ws.end;
     auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
     int32_t *scan_tmp = (int32_t *)take((size_t)(div_up(ws.nw > lk->cap_lights ? ws.nw : lk->cap_lights, SCAN_TILE) + 1) * 4);
-    int32_t *cur_ctrl = (int32_t *)take((size_t)lk->cap_lights * 4), *cur_inc = (int32_t *)take((size_t)lk->cap_lights * 4);
     if (o > ws_bytes) { set_error("tsim_lights_finish needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
     cudaStream_t cs = (cudaStream_t)stream;
     const int W = ws.W, H = ws.H, wp = ws.wp, cap_cr = ws.cap_cr;
@@ -756,23 +718,20 @@ extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes
     if ((st = exclusive_scan_i32(tl_prefix, nw, scan_tmp, lk->n_lights, cs)) != TSIM_OK) return st;
     bit_list_kernel<<<div_up(nw, 256), 256, 0, cs>>>(W, H, wp, bp.tl, tl_prefix, lk->light_cell, lk->cap_lights, err_flag, 22);
     TSIM_LAUNCH_CHECK();
-    // count -> offsets -> fill
-    TSIM_CUDA(cudaMemsetAsync(lk->ctrl_off, 0, (size_t)(lk->cap_lights + 1) * 4, cs));
-    TSIM_CUDA(cudaMemsetAsync(lk->inc_off, 0, (size_t)(lk->cap_lights + 1) * 4, cs));
-    lights_count_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, tl_prefix, lk->ctrl_off, lk->inc_off);
+    // count -> offsets -> fill (gather form, one thread per light)
+    const int lgrid = div_up(lk->cap_lights, 128) < 148 * 16 ? div_up(lk->cap_lights, 128) : 148 * 16;
+    light_links_kernel<false><<<lgrid, 128, 0, cs>>>(L, lk->n_lights, lk->light_cell, ws.cr_prefix, rec, lk->ctrl_off, lk->inc_off, nullptr, nullptr, 0, 0);
     TSIM_LAUNCH_CHECK();
     if ((st = exclusive_scan_i32(lk->ctrl_off, lk->cap_lights, scan_tmp, scal + 4, cs, lk->n_lights)) != TSIM_OK) return st;
     if ((st = exclusive_scan_i32(lk->inc_off, lk->cap_lights, scan_tmp, scal + 5, cs, lk->n_lights)) != TSIM_OK) return st;
     close_offsets_kernel<<<1, 1, 0, cs>>>(lk->n_lights, lk->ctrl_off, lk->inc_off, scal + 4, lk->cap_lights, lk->cap_ctrl, lk->cap_inc, err_flag);
     TSIM_LAUNCH_CHECK();
-    TSIM_CUDA(cudaMemsetAsync(cur_ctrl, 0, (size_t)lk->cap_lights * 4, cs));
-    TSIM_CUDA(cudaMemsetAsync(cur_inc, 0, (size_t)lk->cap_lights * 4, cs));
-    lights_fill_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, tl_prefix, p->cell_type, p->aux, p->block_id, cur_ctrl, cur_inc,
-                                                            lk->ctrl_off, lk->inc_off, lk->ctrl_cell, lk->inc_cell, lk->cap_ctrl, lk->cap_inc);
+    light_links_kernel<true><<<lgrid, 128, 0, cs>>>(L, lk->n_lights, lk->light_cell, ws.cr_prefix, rec, lk->ctrl_off, lk->inc_off, lk->ctrl_cell,
+                                                    lk->inc_cell, lk->cap_ctrl, lk->cap_inc);
+    TSIM_LAUNCH_CHECK();
+    cr_apply_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->cell_type, p->aux, p->block_id);
     TSIM_LAUNCH_CHECK();
     tl_apply_kernel<<<(div_up(lk->cap_lights, 256) < 148 * 8 ? div_up(lk->cap_lights, 256) : 148 * 8), 256, 0, cs>>>(lk->n_lights, lk->light_cell, lk->cap_lights, p->cell_type, p->dirs, p->aux);
-    TSIM_LAUNCH_CHECK();
-    links_sort_kernel<<<(div_up(lk->cap_lights, 128) < 148 * 16 ? div_up(lk->cap_lights, 128) : 148 * 16), 128, 0, cs>>>(lk->n_lights, lk->cap_lights, lk->ctrl_off, lk->ctrl_cell, lk->inc_off, lk->inc_cell);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
