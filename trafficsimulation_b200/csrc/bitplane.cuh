@@ -34,6 +34,46 @@ __device__ __forceinline__ void transpose_block(const u64 *__restrict__ src, int
 }
 
 
+// Transpose of a 256-row x 4-word tile of TWO planes by a CTA of 256 threads through shared memory, so that both
+// global sides move whole 32-byte sectors (a lone 64 x 64 block moves 8 useful bytes per sector) and the loads of both
+// planes are in flight together.  Tile (tx, ty) = rows ty*256 .. +255, words tx*4 .. +3 of the sources; it lands in
+// rows tx*256 .. +255, words ty*4 .. +3 of the destinations.  s_in / s_out: [2][256][5] words.
+__device__ __forceinline__ void transpose_tile2(const u64 *__restrict__ srcA, const u64 *__restrict__ srcB, int src_rows, int src_wp,
+                                                u64 *__restrict__ dstA, u64 *__restrict__ dstB, int dst_rows, int dst_wp, int tx, int ty, bool coherent,
+                                                u64 (*s_in)[256][5], u64 (*s_out)[256][5]) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    {
+        const int r = ty * 256 + t;
+        const size_t o = (size_t)r * src_wp + tx * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool ok = r < src_rows && tx * 4 + k < src_wp;
+            s_in[0][t][k] = ok ? (coherent ? __ldcg(srcA + o + k) : srcA[o + k]) : 0ull;
+            s_in[1][t][k] = ok ? (coherent ? __ldcg(srcB + o + k) : srcB[o + k]) : 0ull;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = wid; b < 32; b += 8) {
+        const int pl = b >> 4, i = (b >> 2) & 3, j = b & 3;
+        u64 a0 = s_in[pl][64 * i + lane][j], a1 = s_in[pl][64 * i + 32 + lane][j];
+        t64(a0, a1, lane);
+        s_out[pl][64 * j + lane][i] = a0;
+        s_out[pl][64 * j + 32 + lane][i] = a1;
+    }
+    __syncthreads();
+    {
+        const int r = tx * 256 + t;
+        const size_t o = (size_t)r * dst_wp + ty * 4;
+        if (r < dst_rows) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (ty * 4 + k < dst_wp) { dstA[o + k] = s_out[0][t][k]; dstB[o + k] = s_out[1][t][k]; }
+        }
+    }
+    __syncthreads();
+}
+
 // 16-bit membership mask of a 16-byte strip: bit k = type byte k is in `set` (bit t of `set` = type t)
 __device__ __forceinline__ uint32_t strip_set_mask(const uint4 &q, uint32_t set) {
     uint32_t m = 0;

@@ -262,8 +262,11 @@ struct ReachT {
     u64 *aNt, *aSt, *fwT, *bwT;   // transposed planes: [W][wpT], bit y & 63 of word y >> 6
     uint8_t *bdR, *bdT;           // [nby][nbx] block changed in the row-major / transposed planes since it was last transposed
     uint8_t *rd, *cd;             // [nby] row block / [nbx] column block needs closing
+    unsigned long long *trace;    // [1 + 4 * 16] %globaltimer at kernel start and after each phase of the first 16 alternations
     int wpT;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, ReachT rt, int32_t *flags /* [0..2] change flags, [3] alternations */,
                                                     int32_t *changed, int32_t *err) {
@@ -271,56 +274,72 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int warp = gtid >> 5, nwarps = nth >> 5;
-    const int nbx = bp.wp, nby = rt.wpT;           // blocks per row / per column of the row-major planes
-    const int px = (nbx + 3) >> 2, py = (nby + 1) >> 1;   // CTA patch = 4 (bx) x 2 (by) blocks: 8-byte words share 32-byte sectors
-    for (int patch = blockIdx.x; patch < px * py; patch += gridDim.x) {
-        const int bx = (patch % px) * 4 + (wid & 3), by = (patch / px) * 2 + (wid >> 2);
-        if (bx < nbx && by < nby) {
-            transpose_block(bp.aN, H, bp.wp, rt.aNt, W, rt.wpT, bx, by, lane, false);
-            transpose_block(bp.aS, H, bp.wp, rt.aSt, W, rt.wpT, bx, by, lane, false);
-        }
+    const int nbx = bp.wp, nby = rt.wpT;           // 64 x 64 blocks per row / per column of the row-major planes
+    __shared__ u64 s_in[2][256][5], s_out[2][256][5];
+    const int ntx = (nbx + 3) >> 2, nty = (nby + 3) >> 2;   // 256 x 256 tiles of the row-major planes
+    const bool tracer = blockIdx.x == 0 && threadIdx.x == 0;
+    if (tracer) rt.trace[0] = global_ns();
+    for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
+        transpose_tile2(bp.aN, bp.aS, H, bp.wp, rt.aNt, rt.aSt, W, rt.wpT, tile % ntx, tile / ntx, false, s_in, s_out);
     }
+    // does tile (tx, ty) of the row-major block grid hold a dirty block?  (uniform over the CTA); clears the flags
+    auto tile_dirty = [&](uint8_t *bd, int tx, int ty) {
+        bool any = false;
+        for (int by = ty * 4; by < min(ty * 4 + 4, nby); by++)
+            for (int bx = tx * 4; bx < min(tx * 4 + 4, nbx); bx++) any |= *((volatile uint8_t *)(bd + (size_t)by * nbx + bx)) != 0;
+        return any;
+    };
+    auto tile_clear = [&](uint8_t *bd, int tx, int ty) {
+        if (threadIdx.x < 16) {
+            const int by = ty * 4 + (threadIdx.x >> 2), bx = tx * 4 + (threadIdx.x & 3);
+            if (by < nby && bx < nbx) bd[(size_t)by * nbx + bx] = 0;
+        }
+    };
     for (int it = 0;; it++) {
         int32_t *flag = flags + it % 3;
         const bool all = it == 0;
         bool ch = false;
         // ---- 1. close the rows whose block row received new bits
         for (int y = warp; y < H; y += nwarps)
-            if (all || *((volatile uint8_t *)(rt.rd + (y >> 6)))) ch |= line_closure(bp.fw, bp.bw, bp.aE, bp.aW, (size_t)y * bp.wp, bp.wp, W, lane, rt.bdR + (size_t)(y >> 6) * nbx, 1);
+            if (all || *((volatile uint8_t *)(rt.rd + (y >> 6))))
+                ch |= line_closure(bp.fw, bp.bw, bp.aE, bp.aW, (size_t)y * bp.wp, bp.wp, W, lane, rt.bdR + (size_t)(y >> 6) * nbx, 1);
         __threadfence();
         grid.sync();
-        // ---- 2. changed blocks -> transposed planes
+        if (tracer && it < 16) rt.trace[1 + 4 * it + 0] = global_ns();
+        // ---- 2. tiles with changed blocks -> transposed planes
         for (int i = gtid; i < nby; i += nth) rt.rd[i] = 0;
-        for (int patch = blockIdx.x; patch < px * py; patch += gridDim.x) {
-            const int bx = (patch % px) * 4 + (wid & 3), by = (patch / px) * 2 + (wid >> 2);
-            if (bx >= nbx || by >= nby) continue;
-            uint8_t *d = rt.bdR + (size_t)by * nbx + bx;
-            if (!all && !*((volatile uint8_t *)d)) continue;
-            transpose_block(bp.fw, H, bp.wp, rt.fwT, W, rt.wpT, bx, by, lane, true);
-            transpose_block(bp.bw, H, bp.wp, rt.bwT, W, rt.wpT, bx, by, lane, true);
-            if (lane == 0) { *d = 0; rt.cd[bx] = 1; }
+        for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
+            const int tx = tile % ntx, ty = tile / ntx;
+            if (!all && !tile_dirty(rt.bdR, tx, ty)) continue;
+            __syncthreads();   // every thread has read the flags
+            tile_clear(rt.bdR, tx, ty);
+            transpose_tile2(bp.fw, bp.bw, H, bp.wp, rt.fwT, rt.bwT, W, rt.wpT, tx, ty, true, s_in, s_out);
+            if (threadIdx.x < 4 && tx * 4 + (int)threadIdx.x < nbx) rt.cd[tx * 4 + threadIdx.x] = 1;
         }
         __threadfence();
         grid.sync();
-        // ---- 3. close the columns (lines of the transposed planes) that cross a re-transposed block
+        if (tracer && it < 16) rt.trace[1 + 4 * it + 1] = global_ns();
+        // ---- 3. close the columns (lines of the transposed planes) that cross a re-transposed tile
         for (int x = warp; x < W; x += nwarps)
-            if (all || *((volatile uint8_t *)(rt.cd + (x >> 6)))) ch |= line_closure(rt.fwT, rt.bwT, rt.aNt, rt.aSt, (size_t)x * rt.wpT, rt.wpT, H, lane, rt.bdT + (x >> 6), nbx);
+            if (all || *((volatile uint8_t *)(rt.cd + (x >> 6))))
+                ch |= line_closure(rt.fwT, rt.bwT, rt.aNt, rt.aSt, (size_t)x * rt.wpT, rt.wpT, H, lane, rt.bdT + (x >> 6), nbx);
         if (__syncthreads_or(ch) && threadIdx.x == 0) *flag = 1;
         __threadfence();
         grid.sync();
-        // ---- 4. changed blocks -> row-major planes
+        if (tracer && it < 16) rt.trace[1 + 4 * it + 2] = global_ns();
+        // ---- 4. tiles with changed blocks -> row-major planes (tile (tx, ty) of the row-major grid = tile (ty, tx) of the transposed one)
         for (int i = gtid; i < nbx; i += nth) rt.cd[i] = 0;
-        for (int patch = blockIdx.x; patch < px * py; patch += gridDim.x) {
-            const int bx = (patch % px) * 4 + (wid & 3), by = (patch / px) * 2 + (wid >> 2);
-            if (bx >= nbx || by >= nby) continue;
-            uint8_t *d = rt.bdT + (size_t)by * nbx + bx;
-            if (!*((volatile uint8_t *)d)) continue;
-            transpose_block(rt.fwT, W, rt.wpT, bp.fw, H, bp.wp, by, bx, lane, true);   // block (bx, by) of the row-major planes = block (by, bx) of the transposed ones
-            transpose_block(rt.bwT, W, rt.wpT, bp.bw, H, bp.wp, by, bx, lane, true);
-            if (lane == 0) { *d = 0; rt.rd[by] = 1; }
+        for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
+            const int tx = tile % ntx, ty = tile / ntx;
+            if (!tile_dirty(rt.bdT, tx, ty)) continue;
+            __syncthreads();
+            tile_clear(rt.bdT, tx, ty);
+            transpose_tile2(rt.fwT, rt.bwT, W, rt.wpT, bp.fw, bp.bw, H, bp.wp, ty, tx, true, s_in, s_out);
+            if (threadIdx.x < 4 && ty * 4 + (int)threadIdx.x < nby) rt.rd[ty * 4 + threadIdx.x] = 1;
         }
         __threadfence();
         grid.sync();
+        if (tracer && it < 16) rt.trace[1 + 4 * it + 3] = global_ns();
         const int any = *((volatile int32_t *)flag);
         if (blockIdx.x == 0 && threadIdx.x == 0) { flags[(it + 2) % 3] = 0; flags[3] = it + 1; if (any && changed) *changed = 1; }
         if (!any) break;
@@ -591,6 +610,7 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
     L.rt.bdT = (uint8_t *)take((size_t)L.rt.wpT * L.wp);
     L.rt.rd = (uint8_t *)take((size_t)L.rt.wpT);
     L.rt.cd = (uint8_t *)take((size_t)L.wp);
+    L.rt.trace = (unsigned long long *)take(65 * 8);
     L.cr_prefix = (int32_t *)take((size_t)L.nw * 4);
     L.tl_prefix = (int32_t *)take((size_t)L.nw * 4);
     L.scan_tmp = (int32_t *)take((size_t)(div_up(L.nw, SCAN_TILE) + 1) * 4);
@@ -681,6 +701,17 @@ extern "C" tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_b
     char dummy;
     if ((st = lights_ws(cfg, &dummy, ws_bytes, L)) != TSIM_OK) return st;
     *fw_off = (size_t)((char *)L.bp.fw - &dummy); *bw_off = (size_t)((char *)L.bp.bw - &dummy); *words_per_row = L.wp;
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_lights_reach_trace(const tsim_cfg *cfg, size_t ws_bytes, size_t *trace_off) {
+    tsim_status st = lights_check(cfg);
+    if (st != TSIM_OK) return st;
+    if (!trace_off) { set_error("tsim_lights_reach_trace: NULL output"); return TSIM_ERR_CONFIG; }
+    LightsWs L;
+    char dummy;
+    if ((st = lights_ws(cfg, &dummy, ws_bytes, L)) != TSIM_OK) return st;
+    *trace_off = (size_t)((char *)L.rt.trace - &dummy);
     return TSIM_OK;
 }
 
