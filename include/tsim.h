@@ -73,7 +73,7 @@ typedef struct tsim_cfg {
     int32_t subblock_road_type;                /* 1..3 */
     int32_t min_subblock_spacing;
     int32_t traffic_light_range;
-    int32_t forward_traffic_light_range;       /* must be 0 on the GPU path (TSIM_ERR_UNSUPPORTED) */
+    int32_t forward_traffic_light_range;
     int32_t forward_intersections_mode;
     int32_t block_entrance_road_level;         /* Defaults.BLOCK_ENTRANCE_ROAD_LEVEL, config.py:26 */
     /* row-band shard window: the planes passed with this cfg hold global rows
@@ -192,6 +192,11 @@ typedef struct tsim_light_links {
     int32_t *inc_off;         /* [cap_lights + 1]  assigned incoming lane cells (multiset) */
     int32_t *inc_cell;        /* [cap_inc]                                               */
     int32_t cap_lights, cap_ctrl, cap_inc;
+    /* assigned OUTGOING cells (forward_traffic_light_range, city_model.py:1550-1584); may be NULL / 0 when the
+       option is off */
+    int32_t *out_off;         /* [cap_lights + 1]                                        */
+    int32_t *out_cell;        /* [cap_out]                                               */
+    int32_t cap_out;
 } tsim_light_links;
 
 /* _add_traffic_lights (city_model.py:1422-1548, CellAgent.leads_to cell.py:201-227) */

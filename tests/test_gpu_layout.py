@@ -63,13 +63,12 @@ def lockstep(cfgd, hb, vb, tape_zone, tape_carve, tape_entrance):
     oc.validate_dirs(); oc.entrance_dirs()
     gc._remove_invalid_intersection_directions(); gc._add_entrance_directions()
     _cmp("fix_dirs", oc, gc)
-    if not fwd:
-        links = oc.lights()
-        gc._add_traffic_lights()
-        _cmp("lights", oc, gc)
-        gl = gc.light_links_host()
-        for k in ("lights", "ctrl", "incoming"):
-            assert np.array_equal(gl[k], links[k]), ("links", k, len(gl[k]), len(links[k]))
+    links = oc.lights()
+    gc._add_traffic_lights()
+    _cmp("lights", oc, gc)
+    gl = gc.light_links_host()
+    for k in ("lights", "ctrl", "incoming") + (("outgoing",) if fwd else ()):
+        assert np.array_equal(gl[k], links[k]), ("links", k, len(gl[k]), len(links[k]))
     gc._build_simple_maps()
     om, gm = oc.simple_maps(), gc.maps_host()
     for k in MAPS:
@@ -82,23 +81,23 @@ def test_gpu_matches_oracle_and_golden(path):
     g = load(path)
     cfgd = g["meta"]["cfg"]
     oc, gc = lockstep(cfgd, g["hbands"], g["vbands"], g["tape_zone"], g["tape_carve"], g["tape_entrance"])
-    if not cfgd["forward_traffic_light_range"]:
-        got = gc.planes_host()
-        for f in PLANES:
-            assert np.array_equal(got[f], g[f]), ("golden", f)
-        gm = gc.maps_host()
-        for k in MAPS:
-            assert np.array_equal(gm[k], g[k]), ("golden", k)
-        gl = gc.light_links_host()
-        for k in ("lights", "ctrl", "incoming"):
-            assert np.array_equal(gl[k], g["links_" + k]), ("golden links", k)
+    got = gc.planes_host()
+    for f in PLANES:
+        assert np.array_equal(got[f], g[f]), ("golden", f)
+    gm = gc.maps_host()
+    for k in MAPS:
+        assert np.array_equal(gm[k], g[k]), ("golden", k)
+    gl = gc.light_links_host()
+    for k in ("lights", "ctrl", "incoming") + (("outgoing",) if cfgd["forward_traffic_light_range"] else ()):
+        assert np.array_equal(gl[k], g["links_" + k]), ("golden links", k)
 
 
-def test_forward_range_is_refused_loudly():
+def test_unsupported_range_is_refused_loudly():
+    """traffic_light_range beyond what the 5-bit scan-length fields hold must raise, not truncate."""
     from trafficsimulation_b200 import _lib
     from trafficsimulation_b200.layout import GpuCityLayout
     g = load(layout_fixtures()[0])
-    gc = GpuCityLayout(forward_traffic_light_range=True)
+    gc = GpuCityLayout(traffic_light_range=31)
     gc.set_bands(g["hbands"], g["vbands"])
     gc._build_roads_and_sidewalks()
     with pytest.raises(_lib.TsimError, match="UNSUPPORTED"):
@@ -112,6 +111,10 @@ SYNTH = [
     (104, dict(width=2048, height=2048, optimized_intersections=False), True),
     (105, dict(width=640, height=512, block_entrance_road_level=1), True),     # road-level filter of the entrance pass
     (106, dict(width=512, height=640, block_entrance_road_level=2, ring_road_type="R3"), False),
+    (107, dict(width=768, height=512, forward_traffic_light_range=True, forward_traffic_light_range_intersections="Include in Range"), True),
+    (108, dict(width=512, height=512, forward_traffic_light_range=True, forward_traffic_light_range_intersections="Include as Extra",
+               traffic_light_range=4), False),
+    (109, dict(width=512, height=512, forward_traffic_light_range=True), True),
 ]
 
 

@@ -53,7 +53,8 @@ class Lines(C.Structure):
 class LightLinks(C.Structure):
     _fields_ = [("n_lights", C.c_void_p), ("light_cell", C.c_void_p), ("ctrl_off", C.c_void_p),
                 ("ctrl_cell", C.c_void_p), ("inc_off", C.c_void_p), ("inc_cell", C.c_void_p),
-                ("cap_lights", C.c_int32), ("cap_ctrl", C.c_int32), ("cap_inc", C.c_int32)]
+                ("cap_lights", C.c_int32), ("cap_ctrl", C.c_int32), ("cap_inc", C.c_int32),
+                ("out_off", C.c_void_p), ("out_cell", C.c_void_p), ("cap_out", C.c_int32)]
 
 
 class LightTables(C.Structure):

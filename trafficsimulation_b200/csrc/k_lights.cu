@@ -53,7 +53,7 @@ struct Bits {
 };
 
 struct LightsCtx {
-    int W, H, tl_range, cap_lights;
+    int W, H, tl_range, cap_lights, fwd, fwd_mode;
     const uint8_t *T; const uint16_t *D;
     Bits b;
     int32_t *err;
@@ -459,6 +459,45 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
     return rec;
 }
 
+// cell.py:229-239
+__device__ __forceinline__ bool directly_leads_to(const LightsCtx &L, int from, int to) {
+    const uint32_t d = L.D[from];
+    const int x = from % L.W, y = from / L.W;
+    for (int i = 0; i < dl_len(d); i++) {
+        const int k = dl_get(d, i), nx = x + dx_of(k), ny = y + dy_of(k);
+        if (L.has(nx, ny) && L.at(nx, ny) == to) return true;
+    }
+    return false;
+}
+
+// _scan_for_traffic_flow_forward (city_model.py:1550-1584) for the ControlledRoad (cx, cy), currently scanning from
+// "road" (rx, ry): emit(cell) for every assigned outgoing cell, in the reference's order.  Recursion depth is bounded
+// by traffic_light_range + 1.  The reference sees (cx, cy) itself and every earlier-converted candidate as
+// ControlledRoad (type_at_time), everything else with its original type.
+template <class F>
+__device__ void forward_scan(const LightsCtx &L, int cx, int cy, int rx, int ry, uint32_t sdirs, int orig, int scan_depth, F &emit) {
+    const int road = L.at(rx, ry);
+    for (int i = 0; i < dl_len(sdirs); i++) {
+        const int rd = dl_get(sdirs, i);
+        int bx = rx + dx_of(rd), by = ry + dy_of(rd), depth = scan_depth;
+        while (depth <= L.tl_range) {
+            if (!L.has(bx, by)) break;
+            const int c = L.at(bx, by);
+            const int t = (bx == cx && by == cy) ? T_CR : type_at_time(L, bx, by, cx, cy);
+            if (t == T_INTER) {
+                if (L.fwd_mode == 1) { emit(c); depth++; }
+                else if (L.fwd_mode == 2) emit(c);
+            } else if (t == orig) {
+                if (directly_leads_to(L, c, road)) forward_scan(L, cx, cy, bx, by, sdirs, orig, depth + 1, emit);
+                else if (dl_has(L.D[c], rd)) { emit(c); depth++; }
+            } else {
+                break;
+            }
+            bx += dx_of(rd); by += dy_of(rd);
+        }
+    }
+}
+
 __device__ __forceinline__ int rec_nacc(u64 r) { return (int)(r >> 60); }
 __device__ __forceinline__ int rec_acc(u64 r, int u, int c, int W) {
     const int code = (int)(r >> (5 * u)) & 31;
@@ -495,12 +534,12 @@ template <bool FILL>
 __global__ void __launch_bounds__(128) light_links_kernel(LightsCtx L, const int32_t *__restrict__ n_lights, const int32_t *__restrict__ light_cell,
                                                           const int32_t *__restrict__ cr_prefix, const u64 *__restrict__ rec, int32_t *ctrl_off,
                                                           int32_t *inc_off, int32_t *__restrict__ ctrl_cell, int32_t *__restrict__ inc_cell, int cap_ctrl,
-                                                          int cap_inc) {
+                                                          int cap_inc, int32_t *out_off, int32_t *__restrict__ out_cell, int cap_out) {
     const int n = min(*n_lights, L.cap_lights);
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
         const int a = light_cell[l], ax = a % L.W, ay = a / L.W;
-        int nc = 0, ni = 0;
-        int pc = FILL ? ctrl_off[l] : 0, pi = FILL ? inc_off[l] : 0;
+        int nc = 0, ni = 0, no = 0;
+        int pc = FILL ? ctrl_off[l] : 0, pi = FILL ? inc_off[l] : 0, po = (FILL && L.fwd) ? out_off[l] : 0;
         for (int y = max(ay - 2, 0); y <= min(ay + 2, L.H - 1); y++) {
             const u64 *row = L.b.cr + (size_t)y * L.b.wp;
             u64 m = extract_bits(row, L.b.wp, ax - 2, 5);
@@ -513,6 +552,10 @@ __global__ void __launch_bounds__(128) light_links_kernel(LightsCtx L, const int
                 bool mine = false;
                 for (int u = 0; u < rec_nacc(r); u++) mine |= rec_acc(r, u, c, L.W) == a;
                 if (!mine) continue;
+                if (L.fwd) {   // _scan_for_traffic_flow_forward, once per (light, controlled road) like the reference
+                    auto emit = [&](int cell) { if (FILL) { if (po < cap_out) out_cell[po] = cell; else *L.err = 27; po++; } else no++; };
+                    forward_scan(L, x, y, x, y, L.D[c], (int)L.T[c], 0, emit);
+                }
                 if (!FILL) { nc++; ni += rec_nsc(r); continue; }
                 if (pc < cap_ctrl) ctrl_cell[pc] = c; else *L.err = 20;
                 pc++;
@@ -523,7 +566,20 @@ __global__ void __launch_bounds__(128) light_links_kernel(LightsCtx L, const int
                 }
             }
         }
-        if (!FILL) { ctrl_off[l] = nc; inc_off[l] = ni; }
+        if (!FILL) { ctrl_off[l] = nc; inc_off[l] = ni; if (L.fwd) out_off[l] = no; }
+    }
+}
+
+// currently_scanned_road.light = traffic_light for the forward-scan cells (:1562,1566,1578); a candidate that is converted
+// later gets a fresh CellAgent, so only cells that are no candidates keep the bit.  Runs before cr_apply (types still original).
+__global__ void __launch_bounds__(128) fwd_mark_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
+                                                       const u64 *__restrict__ rec, uint8_t *A) {
+    const int n = *n_cr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!rec_nacc(rec[i])) continue;
+        const int c = cr_cell[i], cx = c % L.W, cy = c / L.W;
+        auto emit = [&](int cell) { if (!L.bit(L.b.cr, cell % L.W, cell / L.W)) or_byte(A + cell, AUX_LIGHT); };
+        forward_scan(L, cx, cy, cx, cy, L.D[c], (int)L.T[c], 0, emit);
     }
 }
 
@@ -565,14 +621,15 @@ __global__ void __launch_bounds__(256) tl_apply_kernel(const int32_t *__restrict
     }
 }
 
-__global__ void close_offsets_kernel(const int32_t *n_lights, int32_t *ctrl_off, int32_t *inc_off, const int32_t *totals, int cap_lights,
-                                     int cap_ctrl, int cap_inc, int32_t *err) {
+__global__ void close_offsets_kernel(const int32_t *n_lights, int32_t *ctrl_off, int32_t *inc_off, int32_t *out_off, const int32_t *totals,
+                                     int cap_lights, int cap_ctrl, int cap_inc, int cap_out, int32_t *err) {
     const int n = *n_lights;
     if (n > cap_lights) { *err = 22; return; }
     ctrl_off[n] = totals[0];
     inc_off[n] = totals[1];
     if (totals[0] > cap_ctrl) *err = 20;
     if (totals[1] > cap_inc) *err = 21;
+    if (out_off) { out_off[n] = totals[2]; if (totals[2] > cap_out) *err = 27; }
 }
 
 }  // namespace tsim
@@ -624,7 +681,6 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
 static tsim_status lights_check(const tsim_cfg *cfg) {
     tsim_status st = check_cfg(cfg);
     if (st != TSIM_OK) return st;
-    if (cfg->forward_traffic_light_range) { set_error("forward_traffic_light_range is not implemented on the GPU path"); return TSIM_ERR_UNSUPPORTED; }
     if (cfg->traffic_light_range < 0 || cfg->traffic_light_range > MAX_TL_RANGE) {
         set_error("traffic_light_range %d outside 0..%d", cfg->traffic_light_range, MAX_TL_RANGE);
         return TSIM_ERR_UNSUPPORTED;
@@ -740,7 +796,9 @@ extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes
     u64 *rec = ws.rec;
     // 4. evaluate every candidate once (launch covers the capacity; threads beyond *n_cr exit)
     const int list_grid = div_up(cap_cr, 128) < 148 * 16 ? div_up(cap_cr, 128) : 148 * 16;   // grid-stride over the compact list
-    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, p->cell_type, p->dirs, bp, err_flag};
+    const int fwd = cfg->forward_traffic_light_range ? 1 : 0;
+    if (fwd && (!lk->out_off || !lk->out_cell || lk->cap_out < 1)) { set_error("forward_traffic_light_range needs the outgoing link table"); return TSIM_ERR_CONFIG; }
+    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, fwd, cfg->forward_intersections_mode, p->cell_type, p->dirs, bp, err_flag};
     lights_eval_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec);
     TSIM_LAUNCH_CHECK();
     // 5. lights in ascending cell order
@@ -751,15 +809,22 @@ extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes
     TSIM_LAUNCH_CHECK();
     // count -> offsets -> fill (gather form, one thread per light)
     const int lgrid = div_up(lk->cap_lights, 128) < 148 * 16 ? div_up(lk->cap_lights, 128) : 148 * 16;
-    light_links_kernel<false><<<lgrid, 128, 0, cs>>>(L, lk->n_lights, lk->light_cell, ws.cr_prefix, rec, lk->ctrl_off, lk->inc_off, nullptr, nullptr, 0, 0);
+    light_links_kernel<false><<<lgrid, 128, 0, cs>>>(L, lk->n_lights, lk->light_cell, ws.cr_prefix, rec, lk->ctrl_off, lk->inc_off, nullptr, nullptr, 0, 0,
+                                                     lk->out_off, nullptr, 0);
     TSIM_LAUNCH_CHECK();
+    if (fwd && (st = exclusive_scan_i32(lk->out_off, lk->cap_lights, scan_tmp, scal + 6, cs, lk->n_lights)) != TSIM_OK) return st;
     if ((st = exclusive_scan_i32(lk->ctrl_off, lk->cap_lights, scan_tmp, scal + 4, cs, lk->n_lights)) != TSIM_OK) return st;
     if ((st = exclusive_scan_i32(lk->inc_off, lk->cap_lights, scan_tmp, scal + 5, cs, lk->n_lights)) != TSIM_OK) return st;
-    close_offsets_kernel<<<1, 1, 0, cs>>>(lk->n_lights, lk->ctrl_off, lk->inc_off, scal + 4, lk->cap_lights, lk->cap_ctrl, lk->cap_inc, err_flag);
+    close_offsets_kernel<<<1, 1, 0, cs>>>(lk->n_lights, lk->ctrl_off, lk->inc_off, fwd ? lk->out_off : nullptr, scal + 4, lk->cap_lights, lk->cap_ctrl,
+                                          lk->cap_inc, lk->cap_out, err_flag);
     TSIM_LAUNCH_CHECK();
     light_links_kernel<true><<<lgrid, 128, 0, cs>>>(L, lk->n_lights, lk->light_cell, ws.cr_prefix, rec, lk->ctrl_off, lk->inc_off, lk->ctrl_cell,
-                                                    lk->inc_cell, lk->cap_ctrl, lk->cap_inc);
+                                                    lk->inc_cell, lk->cap_ctrl, lk->cap_inc, lk->out_off, lk->out_cell, lk->cap_out);
     TSIM_LAUNCH_CHECK();
+    if (fwd) {
+        fwd_mark_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->aux);
+        TSIM_LAUNCH_CHECK();
+    }
     cr_apply_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->cell_type, p->aux, p->block_id);
     TSIM_LAUNCH_CHECK();
     tl_apply_kernel<<<(div_up(lk->cap_lights, 256) < 148 * 8 ? div_up(lk->cap_lights, 256) : 148 * 8), 256, 0, cs>>>(lk->n_lights, lk->light_cell, lk->cap_lights, p->cell_type, p->dirs, p->aux);

@@ -246,9 +246,14 @@ class GpuCityLayout:
             t = dict(n_lights=self.flags[3:4], light_cell=torch.empty(cap_l, dtype=torch.int32, device=dev),
                      ctrl_off=torch.empty(cap_l + 1, dtype=torch.int32, device=dev), ctrl_cell=torch.empty(cap_c, dtype=torch.int32, device=dev),
                      inc_off=torch.empty(cap_l + 1, dtype=torch.int32, device=dev), inc_cell=torch.empty(cap_i, dtype=torch.int32, device=dev))
+            if self.cfg.forward_traffic_light_range:
+                t["out_off"] = torch.empty(cap_l + 1, dtype=torch.int32, device=dev)
+                t["out_cell"] = torch.empty(cap_i, dtype=torch.int32, device=dev)
             self._link_tensors = t
+        fwd = "out_off" in t
         return _lib.LightLinks(self._flag_ptr(3), t["light_cell"].data_ptr(), t["ctrl_off"].data_ptr(), t["ctrl_cell"].data_ptr(),
-                               t["inc_off"].data_ptr(), t["inc_cell"].data_ptr(), cap_l, cap_c, cap_i)
+                               t["inc_off"].data_ptr(), t["inc_cell"].data_ptr(), cap_l, cap_c, cap_i,
+                               t["out_off"].data_ptr() if fwd else 0, t["out_cell"].data_ptr() if fwd else 0, cap_i if fwd else 0)
 
     def _add_traffic_lights(self, check=True):   # city_model.py:1422
         lk = self._links_struct()
@@ -302,7 +307,10 @@ class GpuCityLayout:
         n = int(self.flags[3].item())
         lights = t["light_cell"][:n].cpu().numpy()
         out = {"lights": lights}
-        for name, off, cell in (("ctrl", "ctrl_off", "ctrl_cell"), ("incoming", "inc_off", "inc_cell")):
+        tables = [("ctrl", "ctrl_off", "ctrl_cell"), ("incoming", "inc_off", "inc_cell")]
+        if "out_off" in t:
+            tables.append(("outgoing", "out_off", "out_cell"))
+        for name, off, cell in tables:
             o = t[off][: n + 1].cpu().numpy()
             c = t[cell][: int(o[-1])].cpu().numpy() if n else np.zeros(0, np.int32)
             owner = np.repeat(lights, np.diff(o)) if n else np.zeros(0, np.int32)
