@@ -211,14 +211,16 @@ tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const 
                [1] first intersection at all (0x7fffffff = none)
      seed    : pivot = device scalar with the window cell index of the agreed pivot (negative: outside this
                window); NULL = use this window's own candidate
-     reach   : closure inside the window; *changed (device, optional) is set to 1 when a bit was added
+     reach   : closure inside the window; *changed (device, optional) is set to 1 when a bit was added.
+               edge_rows < 0: first call after seed; edge_rows >= 0: resumed call, only that many rows at each end of
+               the window were changed from outside since the previous call (the halo exchange)
      reach_planes : byte offsets of the planes inside the workspace ([win_rows][words_per_row] uint64)
      finish  : evaluation, light numbering, link tables, cell conversion */
 tsim_status tsim_lights_prepare(const tsim_cfg *cfg, const tsim_planes *p, int32_t *pivot_out, int32_t *err_flag,
                                 void *workspace, size_t ws_bytes, void *stream);
 tsim_status tsim_lights_seed(const tsim_cfg *cfg, const int32_t *pivot, void *workspace, size_t ws_bytes, void *stream);
-tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes,
-                              void *stream);
+tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows, int32_t *changed, int32_t *err_flag, void *workspace,
+                              size_t ws_bytes, void *stream);
 tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_bytes, size_t *fw_off, size_t *bw_off,
                                      int32_t *words_per_row);
 /* profiling aid: byte offset of the reach kernel's phase trace inside the workspace (uint64[65]: %globaltimer at the

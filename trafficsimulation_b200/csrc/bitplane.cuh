@@ -38,9 +38,11 @@ __device__ __forceinline__ void transpose_block(const u64 *__restrict__ src, int
 // global sides move whole 32-byte sectors (a lone 64 x 64 block moves 8 useful bytes per sector) and the loads of both
 // planes are in flight together.  Tile (tx, ty) = rows ty*256 .. +255, words tx*4 .. +3 of the sources; it lands in
 // rows tx*256 .. +255, words ty*4 .. +3 of the destinations.  s_in / s_out: [2][256][5] words.
-__device__ __forceinline__ void transpose_tile2(const u64 *__restrict__ srcA, const u64 *__restrict__ srcB, int src_rows, int src_wp,
+// `compare`: read the destination first and return (uniformly over the CTA) whether a word changed; otherwise store
+// unconditionally and return true.
+__device__ __forceinline__ bool transpose_tile2(const u64 *__restrict__ srcA, const u64 *__restrict__ srcB, int src_rows, int src_wp,
                                                 u64 *__restrict__ dstA, u64 *__restrict__ dstB, int dst_rows, int dst_wp, int tx, int ty, bool coherent,
-                                                u64 (*s_in)[256][5], u64 (*s_out)[256][5]) {
+                                                bool compare, u64 (*s_in)[256][5], u64 (*s_out)[256][5]) {
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     {
         const int r = ty * 256 + t;
@@ -62,7 +64,7 @@ __device__ __forceinline__ void transpose_tile2(const u64 *__restrict__ srcA, co
         s_out[pl][64 * j + 32 + lane][i] = a1;
     }
     __syncthreads();
-    {
+    if (!compare) {
         const int r = tx * 256 + t;
         const size_t o = (size_t)r * dst_wp + ty * 4;
         if (r < dst_rows) {
@@ -70,8 +72,23 @@ __device__ __forceinline__ void transpose_tile2(const u64 *__restrict__ srcA, co
             for (int k = 0; k < 4; k++)
                 if (ty * 4 + k < dst_wp) { dstA[o + k] = s_out[0][t][k]; dstB[o + k] = s_out[1][t][k]; }
         }
+        __syncthreads();
+        return true;
     }
-    __syncthreads();
+    bool ch = false;
+    {
+        const int r = tx * 256 + t;
+        const size_t o = (size_t)r * dst_wp + ty * 4;
+        if (r < dst_rows) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (ty * 4 + k < dst_wp) {
+                    const u64 a = s_out[0][t][k], b = s_out[1][t][k];
+                    if (__ldcg(dstA + o + k) != a || __ldcg(dstB + o + k) != b) { dstA[o + k] = a; dstB[o + k] = b; ch = true; }
+                }
+        }
+    }
+    return __syncthreads_or(ch);
 }
 
 // 16-bit membership mask of a 16-byte strip: bit k = type byte k is in `set` (bit t of `set` = type t)

@@ -268,8 +268,9 @@ struct ReachT {
 
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-__global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, ReachT rt, int32_t *flags /* [0..2] change flags, [3] alternations */,
-                                                    int32_t *changed, int32_t *err) {
+__global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, ReachT rt, int edge_rows /* < 0: first call, everything is new; else only
+                                                    that many rows at each end of the window received bits since the last call */,
+                                                    int32_t *flags /* [0..2] change flags, [3] alternations */, int32_t *changed, int32_t *err) {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -279,8 +280,19 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
     const int ntx = (nbx + 3) >> 2, nty = (nby + 3) >> 2;   // 256 x 256 tiles of the row-major planes
     const bool tracer = blockIdx.x == 0 && threadIdx.x == 0;
     if (tracer) rt.trace[0] = global_ns();
-    for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
-        transpose_tile2(bp.aN, bp.aS, H, bp.wp, rt.aNt, rt.aSt, W, rt.wpT, tile % ntx, tile / ntx, false, s_in, s_out);
+    if (edge_rows < 0) {
+        for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x)
+            transpose_tile2(bp.aN, bp.aS, H, bp.wp, rt.aNt, rt.aSt, W, rt.wpT, tile % ntx, tile / ntx, false, false, s_in, s_out);
+    } else {
+        // resumed call: the transposed arrows and planes of the last call are still valid; only the edge rows must be
+        // re-closed and their blocks re-transposed
+        const int lo_blocks = (min(edge_rows, H) + 63) >> 6, hi_first = max(H - edge_rows, 0) >> 6;
+        for (int i = gtid; i < nby * nbx; i += nth) {
+            const int by = i / nbx;
+            if (by < lo_blocks || by >= hi_first) { rt.bdR[i] = 1; rt.rd[by] = 1; }
+        }
+        __threadfence();
+        grid.sync();
     }
     // does tile (tx, ty) of the row-major block grid hold a dirty block?  (uniform over the CTA); clears the flags
     auto tile_dirty = [&](uint8_t *bd, int tx, int ty) {
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
     };
     for (int it = 0;; it++) {
         int32_t *flag = flags + it % 3;
-        const bool all = it == 0;
+        const bool all = it == 0 && edge_rows < 0;
         bool ch = false;
         // ---- 1. close the rows whose block row received new bits
         for (int y = warp; y < H; y += nwarps)
@@ -313,8 +325,8 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
             if (!all && !tile_dirty(rt.bdR, tx, ty)) continue;
             __syncthreads();   // every thread has read the flags
             tile_clear(rt.bdR, tx, ty);
-            transpose_tile2(bp.fw, bp.bw, H, bp.wp, rt.fwT, rt.bwT, W, rt.wpT, tx, ty, true, s_in, s_out);
-            if (threadIdx.x < 4 && tx * 4 + (int)threadIdx.x < nbx) rt.cd[tx * 4 + threadIdx.x] = 1;
+            const bool tch = transpose_tile2(bp.fw, bp.bw, H, bp.wp, rt.fwT, rt.bwT, W, rt.wpT, tx, ty, true, it == 0 && edge_rows >= 0, s_in, s_out);
+            if (tch && threadIdx.x < 4 && tx * 4 + (int)threadIdx.x < nbx) rt.cd[tx * 4 + threadIdx.x] = 1;
         }
         __threadfence();
         grid.sync();
@@ -334,8 +346,8 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
             if (!tile_dirty(rt.bdT, tx, ty)) continue;
             __syncthreads();
             tile_clear(rt.bdT, tx, ty);
-            transpose_tile2(rt.fwT, rt.bwT, W, rt.wpT, bp.fw, bp.bw, H, bp.wp, ty, tx, true, s_in, s_out);
-            if (threadIdx.x < 4 && ty * 4 + (int)threadIdx.x < nby) rt.rd[ty * 4 + threadIdx.x] = 1;
+            const bool tch = transpose_tile2(rt.fwT, rt.bwT, W, rt.wpT, bp.fw, bp.bw, H, bp.wp, ty, tx, true, false, s_in, s_out);
+            if (tch && threadIdx.x < 4 && ty * 4 + (int)threadIdx.x < nby) rt.rd[ty * 4 + threadIdx.x] = 1;
         }
         __threadfence();
         grid.sync();
@@ -725,7 +737,8 @@ extern "C" tsim_status tsim_lights_seed(const tsim_cfg *cfg, const int32_t *pivo
 }
 
 // stage 2b: closure of the planes inside this window; *changed (device, optional) is set to 1 if a bit was added
-extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream) {
+extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes,
+                                         void *stream) {
     tsim_status st = lights_check(cfg);
     if (st != TSIM_OK) return st;
     if (!err_flag) { set_error("tsim_lights_reach: NULL err_flag"); return TSIM_ERR_CONFIG; }
@@ -742,7 +755,7 @@ extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t *changed, 
     int32_t *flags = L.scal + 8;
     TSIM_CUDA(cudaMemsetAsync(flags, 0, 16, cs));
     TSIM_CUDA(cudaMemsetAsync(L.rt.bdR, 0, (size_t)((char *)L.rt.cd - (char *)L.rt.bdR) + L.wp, cs));   // the four flag arrays are contiguous
-    void *args[] = {&L.W, &L.H, &L.bp, &L.rt, &flags, &changed, &err_flag};
+    void *args[] = {&L.W, &L.H, &L.bp, &L.rt, &edge_rows, &flags, &changed, &err_flag};
     TSIM_COOP_LAUNCH(reach_kernel, dim3(grid), dim3(256), args, cs);
     return TSIM_OK;
 }
@@ -837,6 +850,6 @@ extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes
     tsim_status st;
     if ((st = tsim_lights_prepare(cfg, p, nullptr, err_flag, workspace, ws_bytes, stream)) != TSIM_OK) return st;
     if ((st = tsim_lights_seed(cfg, nullptr, workspace, ws_bytes, stream)) != TSIM_OK) return st;
-    if ((st = tsim_lights_reach(cfg, nullptr, err_flag, workspace, ws_bytes, stream)) != TSIM_OK) return st;
+    if ((st = tsim_lights_reach(cfg, -1, nullptr, err_flag, workspace, ws_bytes, stream)) != TSIM_OK) return st;
     return tsim_lights_finish(cfg, p, lk, err_flag, workspace, ws_bytes, stream);
 }

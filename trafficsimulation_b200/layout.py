@@ -218,8 +218,8 @@ class GpuCityLayout:
     def _lights_seed(self):   # flags[10] = window cell of the agreed pivot (negative: outside)
         _lib.check(self.lib.tsim_lights_seed(C.byref(self.cfg), self._flag_ptr(10), _ptr(self.workspace), C.c_size_t(self.workspace.numel()), self._stream))
 
-    def _lights_reach(self):  # flags[11] is set when a bit was added
-        _lib.check(self.lib.tsim_lights_reach(C.byref(self.cfg), self._flag_ptr(11), self._flag_ptr(0), _ptr(self.workspace),
+    def _lights_reach(self, edge_rows=-1):  # flags[11] is set when a bit was added
+        _lib.check(self.lib.tsim_lights_reach(C.byref(self.cfg), C.c_int32(edge_rows), self._flag_ptr(11), self._flag_ptr(0), _ptr(self.workspace),
                                               C.c_size_t(self.workspace.numel()), self._stream))
 
     def reach_planes(self):

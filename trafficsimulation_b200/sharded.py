@@ -310,7 +310,7 @@ class ShardedCityLayout:
             changed = {}
             for s, L in S.items():
                 L.flags[11] = 0
-                L._lights_reach()
+                L._lights_reach(-1 if self.reach_rounds == 0 else p.halo)   # later rounds: only the halo rows received new bits
                 changed[s] = L.flags[11].clone()
             items = []
             for k in (0, 1):                                  # OR the owners' rows into the neighbours' halo rows
