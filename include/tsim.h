@@ -80,7 +80,8 @@ typedef struct tsim_cfg {
        [win_y0, win_y0 + win_rows) of the width x height grid, row-major, nothing else.  Every cell
        index a call takes or returns (component roots, light cells, link tables) is an index into THIS
        window; rows outside it do not exist for the call.  Single device: win_y0 = 0, win_rows = height. */
-    int32_t win_y0, win_rows, reserved0;
+    int32_t win_y0, win_rows;
+    int32_t win_halo;   /* rows at each CUT end of the window that belong to the neighbour shard (0 on a single device) */
 } tsim_cfg;
 
 typedef struct tsim_planes {

@@ -47,8 +47,10 @@ def test_sharded_equals_single_on_reference_fixture(n_shards):
         assert np.array_equal(got[f], g[f]), ("golden", f)
 
 
-@pytest.mark.parametrize("size,n_shards,carve", [((768, 1024), 4, True), ((1024, 1024), 8, True), ((1000, 600), 2, False)])
-def test_sharded_equals_single_synthetic(size, n_shards, carve):
+@pytest.mark.parametrize("size,n_shards,carve,global_reach", [((768, 1024), 4, True, False), ((1024, 1024), 8, True, False),
+                                                              ((1000, 600), 2, False, False), ((768, 1024), 4, True, True),
+                                                              ((512, 1536), 3, False, True)])
+def test_sharded_equals_single_synthetic(size, n_shards, carve, global_reach):
     from trafficsimulation_b200 import tapes
     from trafficsimulation_b200.layout import GpuCityLayout
     from trafficsimulation_b200.sharded import ShardedCityLayout
@@ -66,11 +68,11 @@ def test_sharded_equals_single_synthetic(size, n_shards, carve):
         tc = tapes.synth_carve_tape(seed, table.cpu().numpy())
         assert tc[:, 1].sum() > 0
     ref = _single(dict(width=W, height=H), carve, hb, vb, tz, tc, te)
-    sh = ShardedCityLayout(n_shards, halo=64, width=W, height=H, carve_subblock_roads=carve)
+    sh = ShardedCityLayout(n_shards, halo=64, width=W, height=H, carve_subblock_roads=carve, global_reach=global_reach)
     sh.set_bands(hb, vb)
     sh.generate(tz, tc, te)
     assert sh.n_blocks == ref.n_blocks
-    assert sh.reach_rounds >= 2 and sh.dead_end_rounds >= 1
+    assert sh.reach_rounds >= (2 if global_reach else 1) and sh.dead_end_rounds >= 1
     _compare(ref, sh)
 
 

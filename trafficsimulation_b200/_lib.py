@@ -34,7 +34,7 @@ class Cfg(C.Structure):
         "width", "height", "wall_thickness", "sidewalk_ring_width", "ring_road_type",
         "optimized_intersections", "subblock_roads_have_intersections", "subblock_road_type",
         "min_subblock_spacing", "traffic_light_range", "forward_traffic_light_range",
-        "forward_intersections_mode", "block_entrance_road_level", "win_y0", "win_rows", "reserved0")]
+        "forward_intersections_mode", "block_entrance_road_level", "win_y0", "win_rows", "win_halo")]
 
 
 class Planes(C.Structure):

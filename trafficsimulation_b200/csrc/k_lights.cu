@@ -54,6 +54,7 @@ struct Bits {
 
 struct LightsCtx {
     int W, H, tl_range, cap_lights, fwd, fwd_mode;
+    int cut_lo, cut_hi;   // rows at the window's low / high end that belong to a neighbour shard (0: that end is a grid edge)
     const uint8_t *T; const uint16_t *D;
     Bits b;
     int32_t *err;
@@ -360,15 +361,27 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
 }
 
 // ---------------------------------------------------------------- exact fallback searches
-__device__ bool bfs_forward(const LightsCtx &L, int from, int to) {
+// An exact search that comes up empty after touching a shard cut may have missed a path through rows this window does not
+// hold: that is reported (flag 13), never returned as "unreachable".
+__device__ __forceinline__ bool on_cut(const LightsCtx &L, int y) { return (L.cut_lo && y == 0) || (L.cut_hi && y == L.H - 1); }
+// does the result of the candidate in row y reach a row this shard owns?  (its lights lie within 2 rows, its scan cells
+// within traffic_light_range + 1); candidates deeper in the halo are recomputed by their owner and overwritten
+__device__ __forceinline__ bool matters(const LightsCtx &L, int y) {
+    const int m = L.tl_range + 3;
+    return y >= L.cut_lo - m && y < L.H - L.cut_hi + m;
+}
+
+__device__ bool bfs_forward(const LightsCtx &L, int from, int to, bool strict) {
     int q[BFS_CAP];
     int head = 0, tail = 0;
+    bool cut = false;
     q[tail++] = from;
     while (head < tail) {
         const int c = q[head++];
         if (c == to) return true;
         const uint32_t d = L.D[c];
         const int x = c % L.W, y = c / L.W;
+        cut |= on_cut(L, y);
         for (int i = 0; i < dl_len(d); i++) {
             const int k = dl_get(d, i), nx = x + dx_of(k), ny = y + dy_of(k);
             if (!L.has(nx, ny)) continue;
@@ -377,21 +390,24 @@ __device__ bool bfs_forward(const LightsCtx &L, int from, int to) {
             for (int u = 0; u < tail; u++) seen |= (q[u] == j);
             if (seen) continue;
             if (j != to && L.D[j] == 0) continue;   // arrow-less cells are dead ends of the BFS
-            if (tail == BFS_CAP) { *L.err = 10; return false; }
+            if (tail == BFS_CAP) { if (strict) *L.err = 10; return false; }
             q[tail++] = j;
         }
     }
+    if (cut && strict) *L.err = 13;
     return false;
 }
 
-__device__ bool bfs_backward(const LightsCtx &L, int from, int to) {   // does `from` reach `to`? search predecessors of `to`
+__device__ bool bfs_backward(const LightsCtx &L, int from, int to, bool strict) {   // does `from` reach `to`? search predecessors of `to`
     int q[BFS_CAP];
     int head = 0, tail = 0;
+    bool cut = false;
     q[tail++] = to;
     while (head < tail) {
         const int c = q[head++];
         if (c == from) return true;
         const int x = c % L.W, y = c / L.W;
+        cut |= on_cut(L, y);
         for (int k = 0; k < 4; k++) {   // predecessor p = c - dir(k) with arrow k
             const int nx = x - dx_of(k), ny = y - dy_of(k);
             if (!L.has(nx, ny)) continue;
@@ -400,21 +416,22 @@ __device__ bool bfs_backward(const LightsCtx &L, int from, int to) {   // does `
             bool seen = false;
             for (int u = 0; u < tail; u++) seen |= (q[u] == j);
             if (seen) continue;
-            if (tail == BFS_CAP) { *L.err = 11; return false; }
+            if (tail == BFS_CAP) { if (strict) *L.err = 11; return false; }
             q[tail++] = j;
         }
     }
+    if (cut && strict) *L.err = 13;
     return false;
 }
 
 // cell.py:201-227 `a.leads_to(b)`
-__device__ __forceinline__ bool leads_to(const LightsCtx &L, int a, int b) {
+__device__ __forceinline__ bool leads_to(const LightsCtx &L, int a, int b, bool strict) {
     if (a == b) return true;
     const int ax = a % L.W, ay = a / L.W, bx = b % L.W, by = b / L.W;
     const bool a_bw = L.bit(L.b.bw, ax, ay), b_fw = L.bit(L.b.fw, bx, by);
     if (a_bw && b_fw) return true;
-    if (!a_bw) return bfs_forward(L, a, b);
-    return bfs_backward(L, a, b);
+    if (!a_bw) return bfs_forward(L, a, b, strict);
+    return bfs_backward(L, a, b, strict);
 }
 
 // ---------------------------------------------------------------- 4. per ControlledRoad evaluation
@@ -462,7 +479,7 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
         while (depth <= L.tl_range) {
             if (!L.has(bx, by)) break;
             if (type_at_time(L, bx, by, cx, cy) != t) break;
-            if (!leads_to(L, L.at(bx, by), c)) break;
+            if (!leads_to(L, L.at(bx, by), c, matters(L, cy))) break;
             cnt++;
             bx += dx_of(k); by += dy_of(k); depth++;
         }
@@ -709,8 +726,9 @@ extern "C" tsim_status tsim_lights_prepare(const tsim_cfg *cfg, const tsim_plane
     LightsWs L;
     if ((st = lights_ws(cfg, workspace, ws_bytes, L)) != TSIM_OK) return st;
     cudaStream_t cs = (cudaStream_t)stream;
-    int mid_row = cfg->height / 2 - cfg->win_y0;   // the pivot is the first intersection at or after the grid's middle row
-    mid_row = mid_row < 0 ? 0 : (mid_row > L.H ? L.H : mid_row);
+    // the pivot is the first intersection at or after the middle row of the WINDOW: well inside it, so that (almost) every
+    // road of the window can reach it and be reached from it without leaving the window
+    const int mid_row = L.H / 2;
     TSIM_CUDA(cudaMemsetAsync(L.scal, 0, 64 * 4, cs));
     init_pivot_kernel<<<1, 1, 0, cs>>>(L.scal);
     TSIM_LAUNCH_CHECK();
@@ -811,7 +829,8 @@ extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes
     const int list_grid = div_up(cap_cr, 128) < 148 * 16 ? div_up(cap_cr, 128) : 148 * 16;   // grid-stride over the compact list
     const int fwd = cfg->forward_traffic_light_range ? 1 : 0;
     if (fwd && (!lk->out_off || !lk->out_cell || lk->cap_out < 1)) { set_error("forward_traffic_light_range needs the outgoing link table"); return TSIM_ERR_CONFIG; }
-    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, fwd, cfg->forward_intersections_mode, p->cell_type, p->dirs, bp, err_flag};
+    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, fwd, cfg->forward_intersections_mode, cfg->win_y0 > 0 ? cfg->win_halo : 0,
+                cfg->win_y0 + cfg->win_rows < cfg->height ? cfg->win_halo : 0, p->cell_type, p->dirs, bp, err_flag};
     lights_eval_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec);
     TSIM_LAUNCH_CHECK();
     // 5. lights in ascending cell order

@@ -41,7 +41,7 @@ class GpuCityLayout:
                  optimized_intersections=True, carve_subblock_roads=False, subblock_roads_have_intersections=True,
                  subblock_road_type="R3", min_subblock_spacing=5, traffic_light_range=10,
                  forward_traffic_light_range=False, forward_traffic_light_range_intersections="Skip",
-                 block_entrance_road_level=0, device="cuda:0", win_y0=0, win_rows=None, **_unused_reference_kwargs):
+                 block_entrance_road_level=0, device="cuda:0", win_y0=0, win_rows=None, win_halo=0, **_unused_reference_kwargs):
         """``win_y0`` / ``win_rows``: this object holds only the global rows [win_y0, win_y0 + win_rows) of the
         width x height city (a row-band shard window, see sharded.py); default = the whole grid."""
         if not torch.cuda.is_available():
@@ -56,7 +56,7 @@ class GpuCityLayout:
                             int(optimized_intersections), int(subblock_roads_have_intersections),
                             ROAD_CODE[subblock_road_type], min_subblock_spacing, traffic_light_range,
                             int(forward_traffic_light_range), FORWARD_MODES.index(forward_traffic_light_range_intersections),
-                            block_entrance_road_level, self.win_y0, self.win_rows, 0)
+                            block_entrance_road_level, self.win_y0, self.win_rows, int(win_halo))
         n = self.width * self.win_rows
         dev = self.device
         self.cell_type = torch.empty(n, dtype=torch.uint8, device=dev)

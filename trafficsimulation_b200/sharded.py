@@ -145,18 +145,20 @@ class ShardedCityLayout:
     """``GpuCityLayout`` over row-band shards.  Same constructor kwargs as the reference ``CityModel`` plus the
     shard geometry; ``generate`` runs the reference's pass sequence (city_model.py:125-139, 148)."""
 
-    def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, **city_kwargs):
+    def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, global_reach=False, **city_kwargs):
         from .layout import GpuCityLayout
         self.kw = dict(city_kwargs)
         self.width, self.height = int(city_kwargs.get("width", 200)), int(city_kwargs.get("height", 200))
         self.plan = ShardPlan(self.height, n_shards, halo if n_shards > 1 else 0)
         self.comm = Comm(n_shards, distributed, group)
         self.carve = bool(city_kwargs.get("carve_subblock_roads", False))
+        self.global_reach = bool(global_reach)
         self.shards = {}
         for i, s in enumerate(self.comm.local):
             dev = (devices[i] if devices else (city_kwargs.get("device", "cuda:0")))
             kw = {k: v for k, v in city_kwargs.items() if k != "device"}
-            self.shards[s] = GpuCityLayout(device=dev, win_y0=self.plan.win_lo[s], win_rows=self.plan.win_hi[s] - self.plan.win_lo[s], **kw)
+            self.shards[s] = GpuCityLayout(device=dev, win_y0=self.plan.win_lo[s], win_rows=self.plan.win_hi[s] - self.plan.win_lo[s],
+                                           win_halo=self.plan.halo, **kw)
         self.n_blocks = None
 
     # ------------------------------------------------------------------ plumbing
@@ -289,7 +291,20 @@ class ShardedCityLayout:
             self.n_blocks = int(self._total.item())
 
     def _lights(self):
+        """`leads_to` (cell.py:201-227) is reachability over the whole arrow graph, but every query of the lights pass
+        relates two cells at most ``traffic_light_range + 1`` apart on one lane.  Default: every shard answers from
+        reachability planes closed INSIDE its window around its own pivot (a -> pivot -> b inside the window is a
+        real path); a query the planes cannot answer is searched exactly, and a search that fails after touching a
+        shard cut raises (flag 13) instead of answering "unreachable" -- so no reachability data crosses shards and
+        the pass costs what it costs on one GPU.  ``global_reach=True`` runs the exchange protocol instead: one pivot
+        for the whole city, closure + OR-exchange of the halo rows of the planes until no shard changes."""
         p, W, S = self.plan, self.width, self.shards
+        if not self.global_reach:
+            for L in S.values():
+                L._add_traffic_lights(check=False)
+            self.reach_rounds = 1
+            self._exchange("cell_type", "aux", "block_id")
+            return
         cands = {}
         for s, L in S.items():
             L._lights_prepare()
