@@ -24,10 +24,9 @@
 // Carving needs steps 1-5 only (no per-cell label traffic at all); zoning adds step 6, which is the
 // compulsory 4 B/cell write of block_id + the 1 B/cell type update.
 #include "scan.cuh"
+#include "bitplane.cuh"
 
 namespace tsim {
-
-typedef unsigned long long u64;
 
 struct Runs {            // lives in the caller's workspace between the label call and the zoning call
     u64 *M;              // [wp * LH] target bit-plane
@@ -55,8 +54,7 @@ __global__ void __launch_bounds__(256) ccl_bits_kernel(int W, int LH, int wp, co
         if ((W & 15) == 0) {
             const uint4 tq = __ldg(reinterpret_cast<const uint4 *>(T + base));
             const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
-#pragma unroll
-            for (int k = 0; k < 16; k++) m |= (uint32_t)(((tw[k >> 2] >> (8 * (k & 3))) & 0xffu) == (uint32_t)target) << k;
+            m = strip_range_mask(tw, TypeRanges{(uint32_t)target - 1u, (uint32_t)target + 1u, 0u, 0u});   // target >= 1 (Nothing = 6, mask = 1)
         } else {
             for (int k = 0; k < 16 && x0 + k < W; k++) m |= (uint32_t)(T[base + k] == target) << k;
         }
@@ -164,14 +162,14 @@ __global__ void __launch_bounds__(256) ccl_flatten_kernel(Runs r) {
     }
 }
 
-__global__ void __launch_bounds__(256) ccl_roots_kernel(Runs r, int32_t *__restrict__ blobs, int cap_blobs, int32_t *err) {
+__global__ void __launch_bounds__(256) ccl_roots_kernel(int W, int y_global0, Runs r, int32_t *__restrict__ blobs, int cap_blobs, int32_t *err) {
     const int n = min(*r.n_runs, r.cap);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         if (r.parent[k] != k) continue;
         const int id = r.rank[k];   // 0-based
         if (id < cap_blobs) {
             int32_t *b = blobs + (size_t)id * TSIM_BLOB_STRIDE;
-            b[0] = 0x7fffffff; b[1] = 0x7fffffff; b[2] = -1; b[3] = -1; b[4] = 0; b[5] = r.start[k];
+            b[0] = 0x7fffffff; b[1] = r.start[k] / W + y_global0; b[2] = -1; b[3] = -1; b[4] = 0; b[5] = r.start[k];
         } else {
             *err = 25;
         }
@@ -187,8 +185,11 @@ __global__ void __launch_bounds__(256) ccl_bbox_kernel(int W, int y_global0, Run
         const int s = r.start[k], len = r.len[k];
         const int x = s % W, y = s / W + y_global0;
         int32_t *b = blobs + (size_t)id * TSIM_BLOB_STRIDE;
-        atomicMin(b + 0, x); atomicMax(b + 2, x + len - 1);
-        atomicMin(b + 1, y); atomicMax(b + 3, y);
+        // min / max only move one way, so a plain look first is safe: a stale value can only cause a redundant atomic.
+        // (the root run is the component's first row: miny is written there, no atomic at all)
+        if (__ldcg(b + 0) > x) atomicMin(b + 0, x);
+        if (__ldcg(b + 2) < x + len - 1) atomicMax(b + 2, x + len - 1);
+        if (__ldcg(b + 3) < y) atomicMax(b + 3, y);
         atomicAdd(b + 4, len);
     }
 }
@@ -222,34 +223,46 @@ __global__ void __launch_bounds__(256) zones_table_kernel(const int32_t *__restr
 template <bool FILL>
 __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Runs r, const int32_t *__restrict__ id_base, int cap_blobs,
                                                          int32_t *__restrict__ L, uint8_t *__restrict__ T, const uint8_t *__restrict__ fill) {
-    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i0 >= n) return;
     const int base = (id_base ? *id_base : 0) + 1;
     const int wp = r.wp;
-    if ((W & 3) == 0) {
+    if ((W & 7) == 0) {   // 8 cells of one row, inside one word
         const long long y = i0 / W;
         const int x = (int)(i0 % W), wx = x >> 6, sh = x & 63;
         const size_t wi = (size_t)y * wp + wx;
-        const uint32_t bits = (uint32_t)(r.M[wi] >> sh) & 0xfu;
-        int4 out = make_int4(0, 0, 0, 0);
+        const uint32_t bits = (uint32_t)(r.M[wi] >> sh) & 0xffu;
+        int4 lo = make_int4(0, 0, 0, 0), hi = lo;
         if (bits) {
             const u64 st = run_starts(r.M, wi, wx);
             const int sp = r.sprefix[wi];
-            int ids[4] = {0, 0, 0, 0};
-            int last_run = -1, last_id = 0;
+            const uint32_t inner = (uint32_t)(st >> sh) & 0xfeu;   // run starts strictly inside the group
+            if (bits == 0xffu && !inner) {   // the whole group lies in one run: one look-up, splat
+                const int run = sp + __popcll(st & ((2ull << sh) - 1ull)) - 1;
+                const int cid = run < r.cap ? r.len[run] : 0, id = cid + base;
+                lo = hi = make_int4(id, id, id, id);
+                if (FILL && cid < cap_blobs) {
+                    const uint32_t f = fill[cid];
+                    if (f != 0xffu) { const uint32_t f4 = f * 0x01010101u; *reinterpret_cast<uint2 *>(T + i0) = make_uint2(f4, f4); }
+                }
+            } else {
+                int ids[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int last_run = -1, last_id = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (!((bits >> k) & 1u)) continue;
-                const int run = sp + __popcll(st & ((2ull << (sh + k)) - 1ull)) - 1;
-                if (run != last_run) { last_run = run; last_id = run < r.cap ? r.len[run] : 0; }
-                ids[k] = last_id + base;
-                if (FILL && last_id < cap_blobs) { const uint8_t f = fill[last_id]; if (f != 0xff) T[i0 + k] = f; }
+                for (int k = 0; k < 8; k++) {
+                    if (!((bits >> k) & 1u)) continue;
+                    const int run = sp + __popcll(st & ((2ull << (sh + k)) - 1ull)) - 1;
+                    if (run != last_run) { last_run = run; last_id = run < r.cap ? r.len[run] : 0; }
+                    ids[k] = last_id + base;
+                    if (FILL && last_id < cap_blobs) { const uint8_t f = fill[last_id]; if (f != 0xff) T[i0 + k] = f; }
+                }
+                lo = make_int4(ids[0], ids[1], ids[2], ids[3]); hi = make_int4(ids[4], ids[5], ids[6], ids[7]);
             }
-            out = make_int4(ids[0], ids[1], ids[2], ids[3]);
         }
-        *reinterpret_cast<int4 *>(L + i0) = out;
+        *reinterpret_cast<int4 *>(L + i0) = lo;
+        *reinterpret_cast<int4 *>(L + i0 + 4) = hi;
     } else {
-        for (int k = 0; k < 4 && i0 + k < n; k++) {
+        for (int k = 0; k < 8 && i0 + k < n; k++) {
             const long long i = i0 + k, y = i / W;
             const int x = (int)(i % W), wx = x >> 6, p = x & 63;
             const size_t wi = (size_t)y * wp + wx;
@@ -321,7 +334,7 @@ tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int target, const 
     ccl_flatten_kernel<<<g, 256, 0, cs>>>(r);
     TSIM_LAUNCH_CHECK();
     if ((st = exclusive_scan_i32(r.rank, r.cap, scan_tmp, blobs->count, cs, r.n_runs)) != TSIM_OK) return st;
-    ccl_roots_kernel<<<g, 256, 0, cs>>>(r, blobs->table, blobs->cap, r.err);
+    ccl_roots_kernel<<<g, 256, 0, cs>>>(win.W, win.y0, r, blobs->table, blobs->cap, r.err);
     TSIM_LAUNCH_CHECK();
     ccl_bbox_kernel<<<g, 256, 0, cs>>>(win.W, win.y0, r, blobs->table, blobs->cap);
     TSIM_LAUNCH_CHECK();
@@ -349,7 +362,7 @@ extern "C" tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes 
     if (st != TSIM_OK) return st;
     if ((st = check_blobs(blobs, "tsim_layout_zones")) != TSIM_OK) return st;
     if (!p || !p->cell_type || !p->block_id || !zone_by_block || !err_flag || n_tape < 0) { set_error("tsim_layout_zones: bad arguments"); return TSIM_ERR_CONFIG; }
-    if (((uintptr_t)p->block_id & 15) != 0) { set_error("tsim_layout_zones: block_id must be 16-byte aligned"); return TSIM_ERR_CONFIG; }
+    if ((((uintptr_t)p->block_id) & 15) != 0 || (((uintptr_t)p->cell_type) & 7) != 0) { set_error("tsim_layout_zones: block_id must be 16-byte, cell_type 8-byte aligned"); return TSIM_ERR_CONFIG; }
     Runs r; int32_t *scan_tmp; uint8_t *fill;
     if ((st = runs_layout(cfg, workspace, ws_bytes, r, scan_tmp, fill, blobs->cap)) != TSIM_OK) return st;
     cudaStream_t cs = (cudaStream_t)stream;
@@ -358,7 +371,7 @@ extern "C" tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes 
     zones_table_kernel<<<list_grid(blobs->cap), 256, 0, cs>>>(blobs->table, blobs->count, blobs->cap, blobs->id_base, zone_by_block, n_tape, fill, err_flag);
     TSIM_LAUNCH_CHECK();
     // Nothing cells carry no arrows and no aux bits (frame pass / place_cell), so only the type changes
-    ccl_labels_kernel<true><<<div_up(div_up(n, 4), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, p->block_id, p->cell_type, fill);
+    ccl_labels_kernel<true><<<div_up(div_up(n, 8), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, p->block_id, p->cell_type, fill);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
@@ -375,7 +388,7 @@ extern "C" tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask,
     if ((st = runs_layout(cfg, workspace, ws_bytes, r, scan_tmp, fill, blobs->cap)) != TSIM_OK) return st;
     const Win win(*cfg);
     const long long n = win.cells();
-    ccl_labels_kernel<false><<<div_up(div_up(n, 4), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr);
+    ccl_labels_kernel<false><<<div_up(div_up(n, 8), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

@@ -94,18 +94,23 @@ __global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const ui
             }
             for (int k = W - x0; k < 16; k++) if (k >= 0) tw[k >> 2] |= (uint32_t)T_WALL << (8 * (k & 3));
         }
+        // SWAR: type sets as byte-range tests on 4 cells at once, arrow bits from 2 cells per dirs word
+        mI = strip_range_mask(tw, TypeRanges{T_INTER - 1, T_INTER + 1, 0, 0});
+        mR = strip_range_mask(tw, TypeRanges{T_R1 - 1, T_HWY_OUT + 1, T_BE - 1, T_BE + 1}) & ~mI;   // ROAD_LIKE_TYPES_WITHOUT_INTERSECTIONS (config.py:69)
+        uint32_t nz = 0;   // cells with at least one arrow
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const int t = (tw[k >> 2] >> (8 * (k & 3))) & 0xff;
-            const uint32_t d = (dw[k >> 1] >> (16 * (k & 1))) & 0xffff;
-            mN |= ((d >> DN) & 1u) << k; mE |= ((d >> DE) & 1u) << k; mS |= ((d >> DS) & 1u) << k; mW |= ((d >> DW) & 1u) << k;
-            mI |= (uint32_t)(t == T_INTER) << k;
-            mR |= ((SET_ROAD_NO_INT >> (t & 31)) & 1u) << k;
-            if (t == T_INTER && d != 0) {
-                const long long i = (long long)base + k;
-                if (i < p_all) p_all = (int)i;
-                if (i >= mid && i < p_mid) p_mid = (int)i;
-            }
+        for (int k = 0; k < 8; k++) {
+            const uint32_t w = dw[k];
+            auto two = [&](int d) { const uint32_t v = (w >> d) & 0x00010001u; return ((v | (v >> 15)) & 3u) << (2 * k); };
+            mN |= two(DN); mE |= two(DE); mS |= two(DS); mW |= two(DW);
+            nz |= ((uint32_t)((w & 0xffffu) != 0u) | ((uint32_t)((w >> 16) != 0u) << 1)) << (2 * k);
+        }
+        uint32_t cand = mI & nz;   // Intersection cells that still have an arrow: pivot candidates
+        if (cand) {
+            p_all = (int)base + __ffs(cand) - 1;
+            const long long rel = mid - (long long)base;
+            if (rel > 0) cand = rel < 16 ? cand & ~((1u << rel) - 1u) : 0u;
+            if (cand) p_mid = (int)base + __ffs(cand) - 1;
         }
     }
     // quad of lanes -> one 64-bit word per plane
