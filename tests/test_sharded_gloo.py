@@ -32,7 +32,10 @@ def _worker(rank, world, port, H, W, halo, out):
             truth = (torch.arange(H * W, dtype=torch.int64).view(H, W) % 251).to(dtype)
             win = torch.full((hi - lo, W), 99, dtype=dtype)
             win[plan.own_lo[rank] - lo: plan.own_hi[rank] - lo] = truth[plan.own_lo[rank]: plan.own_hi[rank]]
-            comm.exchange(plan, lambda s, a, b: win[a - lo: b - lo], lambda s, a, b, src: win[a - lo: b - lo].copy_(src))
+            if dtype in (torch.uint8, torch.int32):   # merge callback path
+                comm.exchange(plan, lambda s, a, b: win[a - lo: b - lo], lambda s, a, b, src: win[a - lo: b - lo].copy_(src))
+            else:                                      # plain refresh: received straight into the halo rows
+                comm.exchange(plan, [(lambda s, a, b: win[a - lo: b - lo], None)])
             assert torch.equal(win, truth[lo:hi]), f"halo exchange rank {rank} {dtype}"
         # root counts -> id bases: rank r owns 10 + r roots and sees 3 * r roots below its own rows
         own = torch.tensor([10 + rank], dtype=torch.int64)

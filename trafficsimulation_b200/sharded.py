@@ -76,7 +76,8 @@ class Comm:
     # halo exchange.  items: list of (get, put) with get(s, lo, hi) -> view of shard s's rows [lo, hi) (global row
     # numbers) and put(s, lo, hi, src).  All items travel in ONE batch of sends / receives per neighbour pair.
     def exchange(self, plan: ShardPlan, get, put=None):
-        items = [(get, put)] if put is not None else list(get)
+        """put(s, lo, hi, src) merges received rows; put = None means a plain refresh of the rows get(s, lo, hi) views."""
+        items = [(get, put)] if callable(get) else list(get)
         if self.n == 1:
             return
         if self.dist is None:
@@ -88,16 +89,23 @@ class Comm:
                     lo, hi = plan.down_rows(s + 1)
                     staged.append((s, lo, hi, g(s + 1, lo, hi).clone()))
                 for dst, lo, hi, src in staged:
-                    p(dst, lo, hi, src)
+                    if p is None:
+                        g(dst, lo, hi).copy_(src)
+                    else:
+                        p(dst, lo, hi, src)
             return
         dist, s = self.dist, self.rank
-        ops, recvs = [], []
+        ops, recvs, get_of = [], [], {}
 
         def add(g, p, peer, send_rows, recv_rows):   # rows travel as raw bytes (NCCL has no int16)
             src = g(s, *send_rows).contiguous()
             ops.append(dist.P2POp(dist.isend, src.view(torch.uint8).reshape(-1), peer, self.group))
             like = g(s, *recv_rows)
+            if p is None and like.is_contiguous():           # plain refresh: receive straight into the halo rows
+                ops.append(dist.P2POp(dist.irecv, like.view(torch.uint8).reshape(-1), peer, self.group))
+                return
             buf = torch.empty(like.numel() * like.element_size(), dtype=torch.uint8, device=like.device)
+            get_of[id(buf)] = g
             ops.append(dist.P2POp(dist.irecv, buf, peer, self.group))
             recvs.append((p, recv_rows, buf, like.dtype, like.shape))
 
@@ -109,7 +117,10 @@ class Comm:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         for p, (lo, hi), buf, dtype, shape in recvs:
-            p(s, lo, hi, buf.view(dtype).view(shape))
+            if p is None:
+                get_of[id(buf)](s, lo, hi).copy_(buf.view(dtype).view(shape))
+            else:
+                p(s, lo, hi, buf.view(dtype).view(shape))
 
     def all_gather(self, vals: dict):
         """vals: {local shard -> 1-D tensor[k]} -> {local shard -> tensor [n_shards, k]} (same device / dtype)."""
@@ -174,9 +185,7 @@ class ShardedCityLayout:
 
     def _exchange(self, *names):
         wl = self.plan.win_lo
-        self.comm.exchange(self.plan, [(lambda s, lo, hi, name=name: self._plane(s, name)[lo - wl[s]: hi - wl[s]],
-                                        lambda s, lo, hi, src, name=name: self._plane(s, name)[lo - wl[s]: hi - wl[s]].copy_(src))
-                                       for name in names])
+        self.comm.exchange(self.plan, [(lambda s, lo, hi, name=name: self._plane(s, name)[lo - wl[s]: hi - wl[s]], None) for name in names])
 
     def _label_and_number(self):
         """Label every window, then turn the window-local numbering into global raster ranks (id_base)."""
