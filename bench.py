@@ -154,7 +154,7 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()) if any(r[2].replace(".", "", 1).isdigit() for r in rows) else None}
 
 
-def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20):
+def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, route_len=400, e2e_ticks=50):
     """Second headline metric: agent-updates/s of the vehicle CA tick (BASELINE.json configs[3], in the
     simultaneous-occupancy form SURVEY.md §8d defines: 100k vehicles live at once on a 2048^2 city)."""
     import torch
@@ -169,7 +169,7 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20):
     city.generate(tz, None, te)
     tabs = light_tables_from_layout(city)
     planes = city.planes_host()
-    tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], n_vehicles, n_ticks, route_len=400, spawn_ticks=1)
+    tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], n_vehicles, n_ticks, route_len=route_len, spawn_ticks=1)
     nv = len(tp["origin"])
     sim = GpuTraffic(size, size, tabs, tp, n_ticks, device=dev)
     sim.step(5)           # warm-up ticks (also spawns everybody)
@@ -192,20 +192,24 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20):
     torch.cuda.synchronize()
     e0 = sim2.counters()["vehicle_updates"]
     t0 = time.perf_counter()
-    for _ in range(50):
+    for _ in range(e2e_ticks):
         sim2.step(1, check=True)
     t1 = time.perf_counter()
     e2e = (sim2.counters()["vehicle_updates"] - e0) / (t1 - t0)
     # CPU port on the same tapes
-    ora = O.OracleTicks(size, size, tabs, tp, n_ticks)
-    ora.run(5)
-    live0 = int(ora.a["alive"].sum())
-    t0 = time.perf_counter()
-    upd_cpu = 0
-    for _ in range(cpu_ticks):
-        upd_cpu += int(ora.a["alive"].sum())
-        ora.run(1)
-    cpu_s = time.perf_counter() - t0
+    cpu = None
+    if cpu_ticks > 0:
+        ora = O.OracleTicks(size, size, tabs, tp, n_ticks)
+        ora.run(5)
+        live0 = int(ora.a["alive"].sum())
+        t0 = time.perf_counter()
+        upd_cpu = 0
+        for _ in range(cpu_ticks):
+            upd_cpu += int(ora.a["alive"].sum())
+            ora.run(1)
+        cpu_s = time.perf_counter() - t0
+        cpu = {"value": upd_cpu / cpu_s, "unit": "agent-updates/s", "cores": 1, "kind": "port",
+               "sample": f"oracle/vehicle_oracle.c, same tapes, {cpu_ticks} ticks, {live0} live vehicles"}
     return {"metric": "agent-updates/sec (vehicle CA tick with traffic-light gating)", "value": ups, "unit": "agent-updates/s",
             "config": {"workload": f"{size}x{size} city, {nv} vehicles spawned at tick 0, {ticks} timed ticks in one persistent launch",
                        "groups": sim.n_groups, "lights": sim.n_lights},
@@ -214,9 +218,8 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20):
             "e2e": {"value": e2e, "unit": "agent-updates/s", "note": "one launch per tick + host read of the counters"},
             "roofline": {"bound": "hbm", "alg_bytes_per_update": 84, "achieved": round(ups * 84 / 1e9, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(ups * 84 / 1e9 / peak, 5), "peak_source": peak_src,
-                         "note": "latency-bound at this size: ~10 grid-wide barriers per tick dominate (DESIGN.md §6)"},
-            "cpu_baseline": {"value": upd_cpu / cpu_s, "unit": "agent-updates/s", "cores": 1, "kind": "port",
-                             "sample": f"oracle/vehicle_oracle.c, same tapes, {cpu_ticks} ticks, {live0} live vehicles"}}
+                         "note": "a tick costs its grid-wide barriers (3 + one per claim sweep + 2), not its bytes (DESIGN.md §4)"},
+            "cpu_baseline": cpu}
 
 
 def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
@@ -422,6 +425,7 @@ def ours(args):
         if world == 1:
             line["config1_4096"] = small_city_leg(dev) if size != 4096 else None
             line["vehicle_step"] = vehicle_bench(dev)
+            line["vehicle_step_1M"] = vehicle_bench(dev, n_ticks=60, size=8192, n_vehicles=1000000, cpu_ticks=0, route_len=100, e2e_ticks=20)
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                                     "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
         print(json.dumps(line))

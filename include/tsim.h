@@ -270,7 +270,8 @@ typedef struct tsim_tick_tapes {     /* all device pointers */
 
 typedef struct tsim_tick_state {     /* all device pointers, owned by the caller */
     uint8_t *occupancy, *stop_map, *stuck_map;   /* [H*W] CityModel.occupancy_map / stop_map / stuck_map      */
-    int32_t *claim, *stopw;                      /* [H*W] scratch planes, prepared by tsim_tick_init          */
+    uint64_t *claim;                             /* [2][H*W] generation-tagged claim words (scratch), zeroed by tsim_tick_init */
+    int32_t *stopw;                              /* [H*W] staged stop_map writes (scratch), zeroed by tsim_tick_init          */
     /* vehicle SoA [n_vehicles] */
     int32_t *pos, *path_len, *steps, *stranded;
     int64_t *path_off;

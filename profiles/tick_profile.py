@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""One persistent tick launch (100 k vehicles, 2048^2 city) for ncu."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from trafficsimulation_b200 import tapes
+from trafficsimulation_b200.layout import GpuCityLayout
+from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+dev = torch.device("cuda", 0)
+size, seed, nt = 2048, 2048, 100
+hb, vb, cap, tz, te = bench.synth_inputs(size, seed)
+city = GpuCityLayout(width=size, height=size, device=dev)
+city.set_bands(hb, vb)
+city.generate(tz, None, te)
+tabs = light_tables_from_layout(city)
+pl = city.planes_host()
+tp = tapes.synth_traffic(seed, size, size, pl["cell_type"], pl["dirs"], 100000, nt, route_len=400, spawn_ticks=1)
+sim = GpuTraffic(size, size, tabs, tp, nt, device=dev)
+sim.step(5)
+sim.step(90, check=False)
+torch.cuda.synchronize()
+print("ok", sim.counters())

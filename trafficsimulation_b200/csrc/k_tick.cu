@@ -17,11 +17,18 @@
 // the lowest-ranked undecided vehicle of every dependency chain, the fixed point is unique and equals
 // the sequential result.  Chains are as long as the platoons that move bumper to bumper (a few cars).
 //
-// Phases of one tick (grid.sync between them):
-//   0 scatter this tick's route events (replayed A* results) into the vehicle SoA
-//   1 phase A for every live vehicle (tick-start snapshot)  +  light groups decide and stage stop_map writes
-//   2 staged stop_map writes are committed (last writer in activation order wins)
-//   3 claim fixed point   4 clears   5 sets / arrivals / stuck counters   6-8 tape-driven spawner
+// A tick costs what its grid-wide barriers cost (the data of 100 k vehicles is a few MB), so the phases are arranged
+// for as few of them as possible:
+//   1 phase A for every live vehicle (tick-start snapshot) + light groups decide and STAGE their stop_map writes
+//     (`stopw`: atomicMax of a priority-coded word, last writer in activation order wins); vehicles read the staged
+//     value where there is one, so the commit needs no barrier of its own
+//   2 claim fixed point, ONE barrier per sweep: claims are generation-tagged 64-bit words (atomicMax: newer sweep,
+//     then lower rank, wins) in two planes used alternately, so a sweep reads the previous sweep's claims from one
+//     plane while writing its own into the other, and nothing ever has to be cleared
+//   3 moves are applied in one phase: a cell somebody enters this tick (it holds a claim of the final sweep) is not
+//     cleared by the vehicle that leaves it, so clears and sets cannot race
+//   4 spawner claims (lowest attempt index per free origin cell) + commit of the staged stop_map writes
+//   5 spawns + scatter of the NEXT tick's route events (replayed A* results)
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -32,7 +39,10 @@ namespace tsim {
 constexpr int MIN_GREEN = 5, MAX_GREEN = 30, GAP_TICKS = 3, GREEN_DURATION = 20;   // config.py:354-359
 constexpr int AWARENESS = 10, MALFUNCTION_TICKS = 400, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2;   // config.py:279,321,306,263
 constexpr int NO_CLAIM = 0x7fffffff;
-enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 };
+constexpr int MAX_SPEED = 5;          // random.randint(1, 5), vehicle_base.py:112: a vehicle plans at most 5 cells
+constexpr int GEN_PER_TICK = 1024;   // claim generations per tick: sweeps 1..1022, spawner 1023
+typedef unsigned long long u64;
+enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8 };
 
 struct TickArgs {
     int W, H, n_ticks, algo;
@@ -111,6 +121,21 @@ __device__ void group_apply(const TickArgs &a, int g) {
     }
 }
 
+// stop_map as the vehicles of this tick see it: the staged write of a light group that acted this tick, else the map
+__device__ __forceinline__ int stop_now(const tsim_tick_state &s, int c) {
+    const int w = __ldcg(s.stopw + c);
+    return w ? (w & 1) : (int)s.stop_map[c];
+}
+
+// claim of the sweep `gen` on cell c: rank of the lowest-ranked vehicle that ends there, NO_CLAIM if none
+__device__ __forceinline__ int claim_rank(const u64 *plane, int c, uint32_t gen) {
+    const u64 k = __ldcg(plane + c);
+    return (uint32_t)(k >> 32) == gen ? (int)(0xffffffffu - (uint32_t)k) : NO_CLAIM;
+}
+__device__ __forceinline__ void claim_cell(u64 *plane, int c, uint32_t gen, int rank) {
+    atomicMax(plane + c, ((u64)gen << 32) | (u64)(0xffffffffu - (uint32_t)rank));
+}
+
 // phase A of one vehicle: vehicle_base.py:616-663 on the tick-start snapshot
 __device__ void vehicle_decide(const TickArgs &a, int v, int t) {
     const tsim_tick_state &s = a.st;
@@ -138,10 +163,22 @@ __device__ void vehicle_decide(const TickArgs &a, int v, int t) {
     const int len = s.path_len[v];
     const int32_t *path = tp.ev_cells + s.path_off[v];
     int ms = min(sp, len);
-    const int look = min(len, AWARENESS);
-    for (int i = 0; i < look && i < ms; i++) {   // cells at or beyond `ms` cannot lower it any more
-        const int c = path[i];
-        if (s.stop_map[c] == 1 || s.occupancy[c] == 1) { ms = i; break; }
+    const int look = min(min(len, AWARENESS), ms);   // cells at or beyond `ms` cannot lower it any more
+    if (look <= MAX_SPEED) {
+        // all probes first (independent loads in flight together), then the decision
+        int cell[MAX_SPEED];
+        bool blocked[MAX_SPEED];
+#pragma unroll
+        for (int i = 0; i < MAX_SPEED; i++) cell[i] = i < look ? path[i] : -1;
+#pragma unroll
+        for (int i = 0; i < MAX_SPEED; i++) blocked[i] = cell[i] >= 0 && (s.stop_map[cell[i]] == 1 || s.occupancy[cell[i]] == 1);
+#pragma unroll
+        for (int i = MAX_SPEED - 1; i >= 0; i--) if (blocked[i]) ms = i;
+    } else {
+        for (int i = 0; i < look; i++) {
+            const int c = path[i];
+            if (s.stop_map[c] == 1 || s.occupancy[c] == 1) { ms = i; break; }
+        }
     }
     s.max_steps[v] = (int8_t)ms;
     if (ms <= 0) {
@@ -151,19 +188,48 @@ __device__ void vehicle_decide(const TickArgs &a, int v, int t) {
     }
 }
 
-// how far does v get, given the current claims?  (_execute_movement :733-753)
-__device__ __forceinline__ int vehicle_eval(const TickArgs &a, int v, int rank) {
+// how far does v get, given the claims of the previous sweep?  (_execute_movement :733-753)
+__device__ __forceinline__ int vehicle_eval(const TickArgs &a, int v, int rank, const u64 *prev, uint32_t gen_prev) {
     const tsim_tick_state &s = a.st;
     const int m = s.max_steps[v];
     const int32_t *path = a.tp.ev_cells + s.path_off[v];
     int k = 0;
+    if (m <= MAX_SPEED) {
+        // all probes first (independent loads in flight together), then the walk
+        int cell[MAX_SPEED], cr[MAX_SPEED], st[MAX_SPEED];
+#pragma unroll
+        for (int j = 0; j < MAX_SPEED; j++) cell[j] = j < m ? path[j] : -1;
+#pragma unroll
+        for (int j = 0; j < MAX_SPEED; j++) {
+            cr[j] = cell[j] >= 0 ? claim_rank(prev, cell[j], gen_prev) : NO_CLAIM;
+            st[j] = cell[j] >= 0 ? stop_now(s, cell[j]) : 0;
+        }
+        bool open = true;
+#pragma unroll
+        for (int j = 0; j < MAX_SPEED; j++) {
+            open = open && j < m && !(cr[j] < rank) && !(st[j] == 1 && j + 1 != m);
+            if (open) k = j + 1;
+        }
+        return k;
+    }
     for (int j = 1; j <= m; j++) {
         const int c = path[j - 1];
-        if (__ldcg(s.claim + c) < rank) break;                 // a lower-ranked vehicle ends here
-        if (s.stop_map[c] == 1 && j != m) break;               // a stop cell may only be entered on the last step
+        if (claim_rank(prev, c, gen_prev) < rank) break;       // a lower-ranked vehicle ends here
+        if (stop_now(s, c) == 1 && j != m) break;              // a stop cell may only be entered on the last step
         k = j;
     }
     return k;
+}
+
+__device__ __forceinline__ void scatter_events(const TickArgs &a, int t, int tid, int nth) {
+    const tsim_tick_tapes &tp = a.tp;
+    const tsim_tick_state &s = a.st;
+    if (t >= tp.n_ticks) return;
+    for (int e = tp.ev_first[t] + tid; e < tp.ev_first[t + 1]; e += nth) {
+        const int v = tp.ev_vehicle[e];
+        s.path_off[v] = tp.ev_off[e];
+        s.path_len[v] = (int32_t)(tp.ev_off[e + 1] - tp.ev_off[e]);
+    }
 }
 
 __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
@@ -172,17 +238,16 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
     const tsim_tick_tapes &tp = a.tp;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int nv = tp.n_vehicles, ng = a.lt.n_groups;
+    const size_t ncell = (size_t)a.W * a.H;
+    u64 *plane[2] = {(u64 *)s.claim, (u64 *)s.claim + ncell};
+    // route events of the first tick of this launch (later ticks: scattered at the end of the previous tick)
+    scatter_events(a, *((volatile int32_t *)(s.scalars + S_TICK)), tid, nth);
+    grid.sync();
     for (int it = 0; it < a.n_ticks; it++) {
         const int t = *((volatile int32_t *)(s.scalars + S_TICK));
         if (t >= tp.n_ticks) { if (tid == 0) s.scalars[S_ERR] = 31; break; }
-        // ---- 0: replay this tick's planned routes
-        for (int e = tp.ev_first[t] + tid; e < tp.ev_first[t + 1]; e += nth) {
-            const int v = tp.ev_vehicle[e];
-            s.path_off[v] = tp.ev_off[e];
-            s.path_len[v] = (int32_t)(tp.ev_off[e + 1] - tp.ev_off[e]);
-        }
-        grid.sync();
-        // ---- 1: phase A + light-group decisions
+        const uint32_t gen0 = (uint32_t)t * GEN_PER_TICK + 1u;   // generation nobody writes: "no claims yet"
+        // ---- 1: phase A + light-group decisions (staged)
         int live = 0;
         for (int v = tid; v < nv; v += nth)
             if (s.alive[v]) { vehicle_decide(a, v, t); live++; }
@@ -190,56 +255,37 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
         if ((threadIdx.x & 31) == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
         for (int g = tid; g < ng; g += nth) group_decide(a, g);
         grid.sync();
-        // ---- 2: commit the staged stop_map writes
-        for (int g = tid; g < ng; g += nth) group_apply(a, g);
-        grid.sync();
-        // ---- 3: claim fixed point
+        // ---- 2: claim fixed point, one barrier per sweep
         const int32_t *rank = tp.rank + (size_t)t * nv;
+        int last = 0;
         for (int iter = 0;; iter++) {
-            int32_t *flag = s.scalars + (iter & 1 ? S_FLAG1 : S_FLAG0);
+            const int fidx[3] = {S_FLAG0, S_FLAG1, S_FLAG2};   // three flags in rotation: the one zeroed after sweep i is written in sweep i + 2
+            int32_t *flag = s.scalars + fidx[iter % 3];
+            const u64 *prev = plane[(iter + 1) & 1];
+            u64 *cur = plane[iter & 1];
+            const uint32_t gen_prev = gen0 + iter, gen_cur = gen0 + iter + 1;
             bool ch = false;
             for (int v = tid; v < nv; v += nth) {
                 if (!s.alive[v] || s.early[v]) continue;
-                const int k = vehicle_eval(a, v, rank[v]);
+                const int r = rank[v];
+                const int k = vehicle_eval(a, v, r, prev, gen_prev);
                 if (k != s.moved[v]) { s.moved[v] = (int8_t)k; ch = true; }
+                if (k >= 1) {
+                    const int c = tp.ev_cells[s.path_off[v] + k - 1];
+                    if (c != tp.target[v]) claim_cell(cur, c, gen_cur, r);   // an arriving vehicle is removed at once
+                }
             }
             if (__any_sync(0xffffffffu, ch) && (threadIdx.x & 31) == 0) *flag = 1;
             grid.sync();
             const int any = *((volatile int32_t *)flag);
-            if (tid == 0) { s.scalars[iter & 1 ? S_FLAG0 : S_FLAG1] = 0; s.scalars[S_ITERS]++; }
+            if (tid == 0) { s.scalars[fidx[(iter + 2) % 3]] = 0; s.scalars[S_ITERS]++; }
+            last = iter;
             if (!any) break;
-            if (iter > 100000) { if (tid == 0) s.scalars[S_ERR] = 32; break; }
-            for (int v = tid; v < nv; v += nth) {      // drop every claim ...
-                if (!s.alive[v] || s.early[v]) continue;
-                const int32_t *path = tp.ev_cells + s.path_off[v];
-                for (int j = 0; j < s.max_steps[v]; j++) s.claim[path[j]] = NO_CLAIM;
-            }
-            grid.sync();
-            for (int v = tid; v < nv; v += nth) {      // ... and claim the current final cells again
-                if (!s.alive[v] || s.early[v]) continue;
-                const int k = s.moved[v];
-                if (k < 1) continue;
-                const int c = tp.ev_cells[s.path_off[v] + k - 1];
-                if (c != tp.target[v]) atomicMin(s.claim + c, rank[v]);   // an arriving vehicle is removed at once
-            }
-            grid.sync();
+            if (iter >= GEN_PER_TICK - 4) { if (tid == 0) s.scalars[S_ERR] = 32; break; }
         }
-        if (tid == 0) { s.scalars[S_FLAG0] = 0; s.scalars[S_FLAG1] = 0; }
-        // ---- 4: clears (cells left or passed through; claims)
-        for (int v = tid; v < nv; v += nth) {
-            if (!s.alive[v] || s.early[v]) continue;
-            const int32_t *path = tp.ev_cells + s.path_off[v];
-            const int k = s.moved[v], m = s.max_steps[v];
-            for (int j = 0; j < m; j++) s.claim[path[j]] = NO_CLAIM;
-            if (k >= 1) {
-                const int pos = s.pos[v];
-                s.occupancy[pos] = 0; s.stuck_map[pos] = 0;            // move_vehicle city_model.py:1952,1957
-                for (int j = 0; j + 1 < k; j++) s.stuck_map[path[j]] = 0;
-                if (path[k - 1] == tp.target[v]) s.stuck_map[path[k - 1]] = 0;   // arrives: remove_vehicle clears its cell again
-            }
-        }
-        grid.sync();
-        // ---- 5: sets, bookkeeping, arrivals
+        const u64 *fin_plane = plane[last & 1];
+        const uint32_t gen_fin = gen0 + last + 1;
+        // ---- 3: apply the moves
         for (int v = tid; v < nv; v += nth) {
             if (!s.alive[v]) continue;
             int pos = s.pos[v];
@@ -249,9 +295,15 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
                 if (k >= 1) {
                     const int32_t *path = tp.ev_cells + s.path_off[v];
                     const int fin = path[k - 1], prev = k >= 2 ? path[k - 2] : pos;
+                    // cells left or passed through: cleared unless somebody ends there this tick (their set wins)
+                    if (claim_rank(fin_plane, pos, gen_fin) == NO_CLAIM) { s.occupancy[pos] = 0; s.stuck_map[pos] = 0; }   // move_vehicle city_model.py:1952,1957
+                    for (int j = 0; j + 1 < k; j++)
+                        if (claim_rank(fin_plane, path[j], gen_fin) == NO_CLAIM) s.stuck_map[path[j]] = 0;
                     if (fin != target) {
                         s.occupancy[fin] = 1;
                         s.stuck_map[fin] = (k == 1 && s.is_stuck[v]) ? 1 : 0;   // move_vehicle :1956-1958, before _move_to resets is_stuck
+                    } else if (claim_rank(fin_plane, fin, gen_fin) == NO_CLAIM) {
+                        s.stuck_map[fin] = 0;                                    // arrives: remove_vehicle clears its cell again (unless a later-ranked vehicle ends there)
                     }
                     const int d = fin - prev;                                    // compute_direction numba_utilities.py:14-28
                     s.direction[v] = (int8_t)(d == a.W ? DN : d == 1 ? DE : d == -a.W ? DS : d == -1 ? DW : s.direction[v]);
@@ -263,7 +315,7 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
                 s.prev_valid[v] = 1;   // step() :677
             } else {
                 s.early[v] = 0;        // :679-680 tick_stuck :687-693
-                if (s.prev_valid[v] && s.stop_map[pos] != 1) {
+                if (s.prev_valid[v] && stop_now(s, pos) != 1) {
                     const int st = ++s.stuck_ticks[v];
                     if (st > STUCK_THRESHOLD && !s.is_stuck[v]) s.is_stuck[v] = 1;
                 }
@@ -272,21 +324,24 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
             if (pos == target) s.alive[v] = 0;   // on_target_reached :755-775 -> remove_vehicle city_model.py:1920-1929
         }
         grid.sync();
-        // ---- 6-8: spawner (attempts of this tick, lowest attempt index wins a free cell)
+        // ---- 4: spawner claims (attempts of this tick, lowest attempt index wins a free cell) + commit of the staged stop_map writes
         const int k0 = tp.spawn_first[t], k1 = tp.spawn_first[t + 1];
+        const uint32_t gen_spawn = (uint32_t)t * GEN_PER_TICK + GEN_PER_TICK - 1;
         for (int k = k0 + tid; k < k1; k += nth)
-            if (s.occupancy[tp.origin[k]] == 0) atomicMin(s.claim + tp.origin[k], k);
+            if (s.occupancy[tp.origin[k]] == 0) claim_cell(plane[0], tp.origin[k], gen_spawn, k);
+        for (int g = tid; g < ng; g += nth) group_apply(a, g);
+        if (tid == 0) { s.scalars[S_FLAG0] = 0; s.scalars[S_FLAG1] = 0; s.scalars[S_FLAG2] = 0; }   // nobody touches the sweep flags here
         grid.sync();
+        // ---- 5: spawns, the next tick's route events
         for (int k = k0 + tid; k < k1; k += nth) {
             const int o = tp.origin[k];
-            if (__ldcg(s.claim + o) != k) continue;
+            if (claim_rank(plane[0], o, gen_spawn) != k) continue;
             s.alive[k] = 1; s.pos[k] = o;
             s.base_speed[k] = 0; s.cur_speed[k] = 0; s.max_steps[k] = 0; s.early[k] = 0; s.is_stuck[k] = 0; s.prev_valid[k] = 0;
             s.malfunction[k] = 0; s.direction[k] = -1; s.stuck_ticks[k] = 0; s.stranded[k] = 0; s.steps[k] = 0; s.moved[k] = 0;
             s.occupancy[o] = 1; s.stuck_map[o] = 0;   // place_vehicle city_model.py:1904-1907
         }
-        grid.sync();
-        for (int k = k0 + tid; k < k1; k += nth) s.claim[tp.origin[k]] = NO_CLAIM;
+        scatter_events(a, t + 1, tid, nth);
         if (tid == 0) s.scalars[S_TICK] = t + 1;
         grid.sync();
     }
@@ -325,8 +380,7 @@ extern "C" tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tabl
     TSIM_CUDA(cudaMemsetAsync(st->stop_map, 0, n, cs));
     TSIM_CUDA(cudaMemsetAsync(st->stuck_map, 0, n, cs));
     TSIM_CUDA(cudaMemsetAsync(st->stopw, 0, n * 4, cs));
-    fill_i32_kernel<<<1184, 256, 0, cs>>>((long long)n, st->claim, NO_CLAIM);
-    TSIM_LAUNCH_CHECK();
+    TSIM_CUDA(cudaMemsetAsync(st->claim, 0, n * 16, cs));   // two planes of 64-bit generation-tagged claims; generation 0 is never read
     if (nv) {
         fill_i32_kernel<<<div_up((long long)nv, 256) < 1184 ? div_up((long long)nv, 256) : 1184, 256, 0, cs>>>((long long)nv, st->pos, -1);
         TSIM_LAUNCH_CHECK();
@@ -363,7 +417,7 @@ extern "C" tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_table
     // grid.sync cost grows with the CTA count: use just enough CTAs for the work, at most one full wave
     long long want = ((long long)tp->n_vehicles + 255) / 256;
     if (want < (lt->n_groups + 255) / 256) want = (lt->n_groups + 255) / 256;
-    long long cap = (long long)sms * (per_sm > 4 ? 4 : per_sm);
+    long long cap = (long long)sms * ((per_sm > 4 && tp->n_vehicles <= 262144) ? 4 : per_sm);   // small fleets: fewer CTAs, cheaper barriers
     int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     void *args[] = {&a};
     TSIM_COOP_LAUNCH(tick_kernel, dim3(grid), dim3(256), args, (cudaStream_t)stream);

@@ -99,7 +99,7 @@ class GpuTraffic:
         # ---- state
         z = lambda cnt, dt: torch.zeros(max(int(cnt), 1), dtype=dt, device=dev)
         s = {"occupancy": z(n, torch.uint8), "stop_map": z(n, torch.uint8), "stuck_map": z(n, torch.uint8),
-             "claim": z(n, torch.int32), "stopw": z(n, torch.int32)}
+             "claim": z(2 * n, torch.int64), "stopw": z(n, torch.int32)}
         for k in _I32:
             s[k] = z(nv, torch.int32)
         s["path_off"] = z(nv, torch.int64)
