@@ -33,8 +33,11 @@ sys.path.insert(0, ROOT)
 PASS_BYTES = {"frame_roads": 4, "carve": 6, "zones": 6, "dead_ends": 2, "upgrade_r2": 4, "entrances": 6,
               "fix_dirs": 10, "lights": 5, "maps": 8}
 CPU_SAMPLE = 2048   # the CPU arm runs a CPU_SAMPLE x CPU_SAMPLE city per step
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), by pass
-ROOFLINE_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per pass of ONE 16384 x 16384 city, summed over the pass's kernels, from the
+# committed ncu capture (profiles/r1_pass_traffic_16384.txt, profiles/r1_ncu_metrics_16384.csv); other sizes: null
+ROOFLINE_TRAFFIC_16384 = {"frame_roads": 1055145728, "carve": 1563896064, "zones": 2775480064, "dead_ends": 274719488,
+                          "upgrade_r2": 269025792, "entrances": 1040451072, "fix_dirs": 942758400, "lights": 7055882752,
+                          "maps": 2092813056}
 
 
 def measured_peaks():
@@ -397,7 +400,7 @@ def ours(args):
         if passes:
             top = max(passes, key=lambda n: passes[n]["ms"])
             roof = {"bound": "hbm", "kernel": top, "achieved": passes[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": passes[top]["frac_of_measured_peak"], "traffic": ROOFLINE_TRAFFIC.get(top), "peak_source": peak_src,
+                    "frac": passes[top]["frac_of_measured_peak"], "traffic": ROOFLINE_TRAFFIC_16384.get(top) if size == 16384 else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": cells * passes[top]["alg_bytes_per_cell"]}
         else:
             roof = {"bound": "hbm", "kernel": "whole pipeline (per GPU)", "achieved": round(pipeline_gbs, 1), "peak": peak, "unit": "GB/s",
