@@ -100,6 +100,10 @@ typedef struct tsim_lines {
     const uint8_t  *col_class;   /* [width]                                                     */
     const uint32_t *lut;         /* [n_row_classes][n_col_classes]: type | aux << 8 | dirs << 16 */
     int32_t n_row_classes, n_col_classes;
+    /* optional row patterns of tsim_build_row_patterns: the whole bulk part of a row of class k, ready to be copied */
+    const uint8_t  *pat_type;    /* [n_row_classes][width] */
+    const uint16_t *pat_dirs;    /* [n_row_classes][width] */
+    const uint8_t  *pat_aux;     /* [n_row_classes][width] */
 } tsim_lines;
 
 /* component table produced by the labelling passes, one row per component of the window in raster
@@ -135,6 +139,13 @@ tsim_status tsim_build_line_table(const int32_t *bands, int32_t n_bands, int32_t
 tsim_status tsim_build_class_tables(const tsim_cfg *cfg, const uint32_t *row_host, const uint32_t *col_host,
                                     uint8_t *row_class_host, uint8_t *col_class_host, uint32_t *lut_host,
                                     int32_t lut_cap, int32_t *n_row_classes, int32_t *n_col_classes);
+
+/* host-side helper: away from the frame, all rows of one class are IDENTICAL (the cell is a function of the row class and
+   of x).  Writes, for every row class, that row's cells for all x (valid where x lies in the bulk; the kernel evaluates
+   the frame columns itself), so the bulk of tsim_layout_frame_roads becomes a copy of ~n_row_classes cache-resident rows. */
+tsim_status tsim_build_row_patterns(const tsim_cfg *cfg, const uint32_t *row_host, const uint32_t *col_host,
+                                    const uint8_t *row_class_host, int32_t n_row_classes, uint8_t *pat_type_host,
+                                    uint16_t *pat_dirs_host, uint8_t *pat_aux_host);
 
 /* bytes of device workspace every tsim_layout_* / tsim_maps call may use */
 tsim_status tsim_workspace_bytes(const tsim_cfg *cfg, size_t *out_bytes);

@@ -104,6 +104,22 @@ def test_unsupported_range_is_refused_loudly():
         gc._add_traffic_lights()
 
 
+@pytest.mark.parametrize("mode", ["rows", "lut", "none"])
+def test_frame_pass_kernels_agree(mode):
+    """The three kernels of the frame + roads pass (pattern rows, class look-up, closed form per cell) write the same planes."""
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+    W, H = 1024, 640
+    hb, vb = tapes.synth_bands(77, width=W, height=H, ring_road_type="R2")
+    gc = GpuCityLayout(width=W, height=H, frame_tables=mode)
+    gc.set_bands(hb, vb)
+    gc._build_roads_and_sidewalks()
+    oc = O.OracleCity(O.make_cfg(width=W, height=H), hb, vb)
+    oc.frame(); oc.roads()
+    _cmp("roads/" + mode, oc, gc, ("cell_type", "dirs", "aux"))
+
+
 SYNTH = [
     (101, dict(width=512, height=512), True),
     (102, dict(width=1024, height=768, ring_road_type="R1"), True),

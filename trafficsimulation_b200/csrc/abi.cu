@@ -5,6 +5,7 @@
 #include <cstring>
 #include <atomic>
 #include <map>
+#include <vector>
 #include <tuple>
 #include "cells_frame.cuh"
 
@@ -132,6 +133,30 @@ extern "C" tsim_status tsim_build_class_tables(const tsim_cfg *cfg, const uint32
             lut[a * nc + b] = (uint32_t)t | (au << 8) | (d << 16);
         }
     *n_row = nr; *n_col = nc;
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_build_row_patterns(const tsim_cfg *cfg, const uint32_t *row, const uint32_t *col, const uint8_t *row_class, int32_t nr,
+                                               uint8_t *pt, uint16_t *pd, uint8_t *pa) {
+    tsim_status s = check_cfg(cfg);
+    if (s != TSIM_OK) return s;
+    if (!row || !col || !row_class || !pt || !pd || !pa || nr < 1 || nr > 256) { set_error("tsim_build_row_patterns: bad arguments"); return TSIM_ERR_CONFIG; }
+    const Geo g(*cfg);
+    const int W = cfg->width, H = cfg->height;
+    const int ybulk = g.iymin + 6;   // any bulk row stands for all of them (see Bulk in k_frame_roads.cu)
+    std::vector<int> rep(nr, -1);
+    for (int y = 0; y < H; y++) if (rep[row_class[y]] < 0) rep[row_class[y]] = y;
+    for (int k = 0; k < nr; k++) {
+        const int y = rep[k];
+        if (y < 0) { set_error("row class %d has no row", k); return TSIM_ERR_CONFIG; }
+        const uint32_t r0 = y > 0 ? row[y - 1] : 0u, r1 = row[y], r2 = y + 1 < H ? row[y + 1] : 0u;
+        for (int x = 0; x < W; x++) {
+            int t; uint32_t d, a;
+            frame_roads_cell(*cfg, g, r0, r1, r2, x > 0 ? col[x - 1] : 0u, col[x], x + 1 < W ? col[x + 1] : 0u, x, ybulk, t, d, a);
+            const size_t i = (size_t)k * W + x;
+            pt[i] = (uint8_t)t; pd[i] = (uint16_t)d; pa[i] = (uint8_t)a;
+        }
+    }
     return TSIM_OK;
 }
 

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) ccl_bbox_kernel(int W, int y_global0, Run
     const int n = min(*r.n_runs, r.cap);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int id = r.rank[r.parent[k]];
-        if (id >= cap_blobs) continue;
+        if (id >= cap_blobs) { r.len[k] = id; continue; }
         const int s = r.start[k], len = r.len[k];
         const int x = s % W, y = s / W + y_global0;
         int32_t *b = blobs + (size_t)id * TSIM_BLOB_STRIDE;
@@ -191,12 +191,8 @@ __global__ void __launch_bounds__(256) ccl_bbox_kernel(int W, int y_global0, Run
         if (__ldcg(b + 2) < x + len - 1) atomicMax(b + 2, x + len - 1);
         if (__ldcg(b + 3) < y) atomicMax(b + 3, y);
         atomicAdd(b + 4, len);
+        r.len[k] = id;   // from here on len[] holds the 0-based component id of the run (only this thread reads len[k])
     }
-}
-
-__global__ void __launch_bounds__(256) ccl_ids_kernel(Runs r) {   // separate pass: bbox reads parent[] of OTHER runs' roots
-    const int n = min(*r.n_runs, r.cap);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) r.len[k] = r.rank[r.parent[k]];   // len[] := component id
 }
 
 // ---------------------------------------------------------------- 6. label plane (+ zone fill)
@@ -337,8 +333,6 @@ tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int target, const 
     ccl_roots_kernel<<<g, 256, 0, cs>>>(win.W, win.y0, r, blobs->table, blobs->cap, r.err);
     TSIM_LAUNCH_CHECK();
     ccl_bbox_kernel<<<g, 256, 0, cs>>>(win.W, win.y0, r, blobs->table, blobs->cap);
-    TSIM_LAUNCH_CHECK();
-    ccl_ids_kernel<<<g, 256, 0, cs>>>(r);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

@@ -114,6 +114,48 @@ __global__ void __launch_bounds__(256) frame_roads_lut_kernel(tsim_cfg c, uint8_
     *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
 }
 
+// Bulk strips are a straight copy of the row class's pattern row (~60 rows, cache resident): four 128-bit loads, four
+// 128-bit stores per 16 cells.  Frame strips: closed form, as in the look-up kernel.
+__global__ void __launch_bounds__(256) frame_roads_rows_kernel(tsim_cfg c, uint8_t *__restrict__ T, uint16_t *__restrict__ D, uint8_t *__restrict__ A,
+                                                               const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt,
+                                                               const uint8_t *__restrict__ rowc, const uint8_t *__restrict__ pt,
+                                                               const uint16_t *__restrict__ pd, const uint8_t *__restrict__ pa) {
+    const Geo g(c);
+    const Bulk bk(g);
+    const int W = g.W, H = g.H;
+    const int xblocks = (W + 16 * 256 - 1) / (16 * 256);
+    const int ly = blockIdx.x / xblocks;
+    const int y = c.win_y0 + ly;
+    const int xv = ((blockIdx.x % xblocks) * blockDim.x + threadIdx.x) * 16;
+    if (xv >= W) return;
+    const size_t base = (size_t)ly * W + xv;
+    if (y >= bk.y0 && y <= bk.y1 && xv >= bk.x0 && xv + 15 <= bk.x1) {
+        const size_t src = (size_t)__ldg(rowc + y) * W + xv;
+        *reinterpret_cast<uint4 *>(T + base) = __ldg(reinterpret_cast<const uint4 *>(pt + src));
+        *reinterpret_cast<uint4 *>(A + base) = __ldg(reinterpret_cast<const uint4 *>(pa + src));
+        *reinterpret_cast<uint4 *>(D + base) = __ldg(reinterpret_cast<const uint4 *>(pd + src));
+        *reinterpret_cast<uint4 *>(D + base + 8) = __ldg(reinterpret_cast<const uint4 *>(pd + src + 8));
+        return;
+    }
+    uint32_t tw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0}, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t r0 = y > 0 ? __ldg(rowt + y - 1) : 0u, r1 = __ldg(rowt + y), r2 = y + 1 < H ? __ldg(rowt + y + 1) : 0u;
+    uint32_t cprev = xv > 0 ? __ldg(colt + xv - 1) : 0u, ccur = __ldg(colt + xv);
+    for (int k = 0; k < 16; k++) {   // W % 16 == 0: the strip is inside the row
+        const int x = xv + k;
+        const uint32_t cnext = x + 1 < W ? __ldg(colt + x + 1) : 0u;
+        int t; uint32_t d, a;
+        frame_roads_cell(c, g, r0, r1, r2, cprev, ccur, cnext, x, y, t, d, a);
+        tw[k >> 2] |= (uint32_t)t << (8 * (k & 3));
+        aw[k >> 2] |= a << (8 * (k & 3));
+        dw[k >> 1] |= d << (16 * (k & 1));
+        cprev = ccur; ccur = cnext;
+    }
+    *reinterpret_cast<uint4 *>(T + base) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+    *reinterpret_cast<uint4 *>(A + base) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+    *reinterpret_cast<uint4 *>(D + base) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+    *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+}
+
 }  // namespace tsim
 
 using namespace tsim;
@@ -128,7 +170,12 @@ extern "C" tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_p
     cudaStream_t st = (cudaStream_t)stream;
     const int W = cfg->width, rows = cfg->win_rows;
     const bool aligned = !(((uintptr_t)p->cell_type | (uintptr_t)p->dirs | (uintptr_t)p->aux) & 15);
-    if (W % 16 == 0 && aligned && lines->lut && lines->row_class && lines->col_class && lines->n_col_classes > 0 && lines->n_col_classes <= 256 &&
+    if (W % 16 == 0 && aligned && lines->row_class && lines->pat_type && lines->pat_dirs && lines->pat_aux &&
+        !(((uintptr_t)lines->pat_type | (uintptr_t)lines->pat_dirs | (uintptr_t)lines->pat_aux) & 15)) {
+        dim3 grid((unsigned)div_up(W, 16 * 256) * rows);
+        frame_roads_rows_kernel<<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, lines->row_class, lines->pat_type,
+                                                      lines->pat_dirs, lines->pat_aux);
+    } else if (W % 16 == 0 && aligned && lines->lut && lines->row_class && lines->col_class && lines->n_col_classes > 0 && lines->n_col_classes <= 256 &&
         !((uintptr_t)lines->col_class & 15)) {
         dim3 grid((unsigned)div_up(W, 16 * 256) * rows);
         frame_roads_lut_kernel<<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, lines->row_class, lines->col_class,

@@ -484,7 +484,10 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
         while (depth <= L.tl_range) {
             if (!L.has(bx, by)) break;
             if (type_at_time(L, bx, by, cx, cy) != t) break;
-            if (!leads_to(L, L.at(bx, by), c, matters(L, cy))) break;
+            // the cell one step closer to c leads to c (that is why the march got here), so a cell with an arrow onto it does too;
+            // only the others (lane-change arrows, opposite lanes) need the reachability planes
+            const int nbc = L.at(bx, by);
+            if (!dl_has(L.D[nbc], dl_get(rd, i)) && !leads_to(L, nbc, c, matters(L, cy))) break;
             cnt++;
             bx += dx_of(k); by += dy_of(k); depth++;
         }

@@ -41,7 +41,7 @@ class GpuCityLayout:
                  optimized_intersections=True, carve_subblock_roads=False, subblock_roads_have_intersections=True,
                  subblock_road_type="R3", min_subblock_spacing=5, traffic_light_range=10,
                  forward_traffic_light_range=False, forward_traffic_light_range_intersections="Skip",
-                 block_entrance_road_level=0, device="cuda:0", win_y0=0, win_rows=None, win_halo=0, **_unused_reference_kwargs):
+                 block_entrance_road_level=0, device="cuda:0", win_y0=0, win_rows=None, win_halo=0, frame_tables="rows", **_unused_reference_kwargs):
         """``win_y0`` / ``win_rows``: this object holds only the global rows [win_y0, win_y0 + win_rows) of the
         width x height city (a row-band shard window, see sharded.py); default = the whole grid."""
         if not torch.cuda.is_available():
@@ -52,6 +52,7 @@ class GpuCityLayout:
         self.win_y0 = int(win_y0)
         self.win_rows = int(self.height - self.win_y0 if win_rows is None else win_rows)
         self.carve_subblock_roads = bool(carve_subblock_roads)
+        self.frame_tables = frame_tables   # "rows" (pattern rows), "lut" (class look-up), "none" (closed form per cell): same result, three kernels
         self.cfg = _lib.Cfg(self.width, self.height, wall_thickness, sidewalk_ring_width, ROAD_CODE[ring_road_type],
                             int(optimized_intersections), int(subblock_roads_have_intersections),
                             ROAD_CODE[subblock_road_type], min_subblock_spacing, traffic_light_range,
@@ -109,14 +110,25 @@ class GpuCityLayout:
         st = self.lib.tsim_build_class_tables(C.byref(self.cfg), row.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p),
                                               rc.ctypes.data_as(C.c_void_p), cc.ctypes.data_as(C.c_void_p), lut.ctypes.data_as(C.c_void_p),
                                               len(lut), C.byref(nr), C.byref(nc))
+        if self.frame_tables == "none":
+            st = 6
         if st == 0:
             self.row_class = torch.from_numpy(rc).to(self.device)
             self.col_class = torch.from_numpy(cc).to(self.device)
             self.class_lut = torch.from_numpy(lut[: nr.value * nc.value].view(np.int32)).to(self.device)
+            # the bulk part of every row class as a ready-made row (a few MB, stays in L2)
+            pt = np.zeros((nr.value, self.width), np.uint8)
+            pd = np.zeros((nr.value, self.width), np.uint16)
+            pa = np.zeros((nr.value, self.width), np.uint8)
+            _lib.check(self.lib.tsim_build_row_patterns(C.byref(self.cfg), row.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p),
+                                                        rc.ctypes.data_as(C.c_void_p), nr.value, pt.ctypes.data_as(C.c_void_p),
+                                                        pd.ctypes.data_as(C.c_void_p), pa.ctypes.data_as(C.c_void_p)))
+            self._patterns = (torch.from_numpy(pt).to(self.device), torch.from_numpy(pd.view(np.int16)).to(self.device), torch.from_numpy(pa).to(self.device))
+            pats = [t.data_ptr() for t in self._patterns] if self.frame_tables == "rows" else [0, 0, 0]
             self._lines = _lib.Lines(self.row_table.data_ptr(), self.col_table.data_ptr(), self.row_class.data_ptr(), self.col_class.data_ptr(),
-                                     self.class_lut.data_ptr(), nr.value, nc.value)
+                                     self.class_lut.data_ptr(), nr.value, nc.value, *pats)
         elif st == 6:   # TSIM_ERR_CAPACITY: not an error, just no tables
-            self._lines = _lib.Lines(self.row_table.data_ptr(), self.col_table.data_ptr(), 0, 0, 0, 0, 0)
+            self._lines = _lib.Lines(self.row_table.data_ptr(), self.col_table.data_ptr(), 0, 0, 0, 0, 0, 0, 0, 0)
         else:
             _lib.check(st)
         # capacity of the component tables: every rectangle of the band grid can split in at most 3
