@@ -83,3 +83,30 @@ def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo):
         prev = got["pos"]
     assert moved > nveh   # traffic actually flows
     assert sim.counters()["fixed_point_iterations"] >= n_ticks
+
+
+def test_gpu_ticks_without_vehicles_cycle_the_lights():
+    """Edge case: an empty spawn tape.  The light groups still run their controllers; everything equals the oracle."""
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    size, nt = 256, 40
+    hb, vb = tapes.synth_bands(9, width=size, height=size)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    city = GpuCityLayout(width=size, height=size)
+    city.set_bands(hb, vb)
+    city.generate(tapes.synth_zone_tape(9, cap), None, None)
+    tabs = light_tables_from_layout(city)
+    pl = city.planes_host()
+    tp = tapes.synth_traffic(9, size, size, pl["cell_type"], pl["dirs"], 0, nt)
+    assert len(tp["origin"]) == 0
+    for algo in ("QUEUE_ACTUATED", "FIXED_TIME"):
+        sim = GpuTraffic(size, size, tabs, tp, nt, algo=algo)
+        ora = O.OracleTicks(size, size, tabs, tp, nt, algo=0 if algo == "QUEUE_ACTUATED" else 1)
+        sim.step(nt)
+        ora.run(nt)
+        got, want = sim.state_host(), ora.state()
+        for k in ("stop", "occ", "groups"):
+            assert np.array_equal(got[k], want[k]), (algo, k)
+        assert sim.counters()["vehicle_updates"] == 0

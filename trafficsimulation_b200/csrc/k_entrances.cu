@@ -156,6 +156,8 @@ __device__ __forceinline__ int run_len_at(u64 m, int s) {   // length of the run
 
 struct EntPlanes { const u64 *tr, *trt, *pr, *prt; int wp, wpT; };   // pr / prt: preferred road level (NULL when the filter is off)
 
+static_assert(SET_TOUCH_ROAD == (M(T_R1) | M(T_R2) | M(T_R3) | M(T_INTER) | M(T_HWY_IN) | M(T_CR)), "ent_bits_kernel range masks");
+
 // one 16-cell strip per thread -> TR (and PR) words
 __global__ void __launch_bounds__(256) ent_bits_kernel(int W, int LH, int wp, const uint8_t *__restrict__ T, int level, u64 *__restrict__ TR,
                                                        u64 *__restrict__ PR) {
@@ -171,8 +173,9 @@ __global__ void __launch_bounds__(256) ent_bits_kernel(int W, int LH, int wp, co
         const size_t base = (size_t)y * W + x0;
         if ((W & 15) == 0) {
             const uint4 tq = *reinterpret_cast<const uint4 *>(T + base);
-            mt = strip_set_mask(tq, SET_TOUCH_ROAD);
-            if (PR) mp = strip_set_mask(tq, pref_set);
+            const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
+            mt = strip_range_mask(tw, TypeRanges{T_R1 - 1, T_HWY_IN + 1, T_CR - 1, T_CR + 1});   // SET_TOUCH_ROAD: R1..HighwayEntrance, ControlledRoad
+            if (PR) mp = strip_range_mask(tw, TypeRanges{T_R1 - 1, (uint32_t)(level < 2 ? T_R2 + 1 : T_R1 + 1), 0, 0});
         } else {
             for (int k = 0; k < 16 && x0 + k < W; k++) {
                 const int t = T[base + k];

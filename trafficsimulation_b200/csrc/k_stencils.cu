@@ -30,17 +30,6 @@ __device__ __forceinline__ PlaneView make_view(const Shard &s, const uint8_t *T,
     return v;
 }
 
-// does any byte of the 16-byte strip belong to `set`?
-__device__ __forceinline__ uint32_t strip_mask(const uint4 &q, uint32_t set) {
-    uint32_t m = 0;
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) m |= ((set >> ((w[k] >> (8 * b)) & 31u)) & 1u) << (4 * k + b);
-    return m;
-}
-
 // Generic sparse sweep: calls f(x, y) for every owned cell whose type is in `set`.
 template <class F>
 __device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, uint32_t set, F f, long long tid, long long nthreads) {
@@ -50,7 +39,7 @@ __device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, u
         for (long long i = tid; i < nstrips; i += nthreads) {
             const int y = s.ylo + (int)(i / sw), x0 = (int)(i % sw) << 4;
             const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(T + (size_t)(y - s.y0) * s.W + x0));
-            uint32_t m = strip_mask(q, set);
+            uint32_t m = strip_set_mask(q, set);
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
