@@ -348,6 +348,13 @@ def ours(args):
             gbs = cells * bpc / (t * 1e-3) / 1e9
             passes[n] = {"ms": round(t, 4), "cells_per_s": cells / (t * 1e-3), "alg_bytes_per_cell": bpc,
                          "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4)}
+    shard_phases = None
+    if world > 1:   # where the step time goes on shards: device time between the marks of one more (untimed) step
+        barrier()
+        sh.trace = []
+        step()
+        shard_phases = {k: round(v, 3) for k, v in sh.phase_times()}
+        sh.trace = None
     t_clk1 = time.monotonic()
     clocks.__exit__(None, None, None)
 
@@ -424,6 +431,7 @@ def ours(args):
             "pipeline": {"algorithmic_bytes_per_cell": total_alg_per_cell, "achieved_gbs_per_gpu": round(pipeline_gbs, 1),
                          "frac_of_measured_peak": round(pipeline_gbs / peak, 4)},
             "passes": passes,
+            "shard_phases_ms": shard_phases,
         }
         if world == 1:
             line["config1_4096"] = small_city_leg(dev) if size != 4096 else None

@@ -164,6 +164,12 @@ tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_planes *p, c
 tsim_status tsim_layout_label_nothing(const tsim_cfg *cfg, const tsim_planes *p, const tsim_blobs *blobs,
                                       int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
 
+/* shard bookkeeping after a labelling call: with this device owning the global rows [own_lo, own_hi) of
+   its window, out (device int32[3]) receives the number of component roots below the own rows, the number inside them,
+   and 1 if a component meets the own rows AND a cut edge of the window (halo too small). */
+tsim_status tsim_shard_counts(const tsim_cfg *cfg, const tsim_blobs *blobs, int32_t own_lo, int32_t own_hi, int32_t *out,
+                              void *stream);
+
 /* _carve_subblock_roads (city_model.py:563-737) given the table of tsim_layout_label_nothing and
    the carve tape: one row of 8 int32 per blob id (drawn, carved, px, py (global), hor_dir, ver_dir,
    inbound_is_horizontal, tries).  err_flag (device int32) is set non-zero on an illegal row. */

@@ -274,6 +274,33 @@ __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Run
     }
 }
 
+// shard bookkeeping over the component table (one launch instead of a dozen tensor ops): out[0] = roots below the own
+// rows, out[1] = roots inside the own rows, out[2] = 1 if a component meets the own rows AND a cut edge of the window
+__global__ void __launch_bounds__(256) shard_counts_kernel(tsim_cfg c, const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs, int cap,
+                                                           int own_lo, int own_hi, int32_t *out) {
+    const int n = min(*n_blobs, cap);
+    const long long lo_cell = (long long)(own_lo - c.win_y0) * c.width, hi_cell = (long long)(own_hi - c.win_y0) * c.width;
+    const int win_lo = c.win_y0, win_hi = c.win_y0 + c.win_rows;
+    int below = 0, own = 0, bad = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int32_t *b = blobs + (size_t)k * TSIM_BLOB_STRIDE;
+        const long long root = b[5];
+        below += root < lo_cell;
+        own += root >= lo_cell && root < hi_cell;
+        const bool meets = b[3] >= own_lo && b[1] < own_hi;
+        const bool cut = (b[1] <= win_lo + 1 && win_lo > 0) || (b[3] >= win_hi - 2 && win_hi < c.height);   // ring cells need one more row
+        bad |= meets && cut;
+    }
+    below = __reduce_add_sync(0xffffffffu, below);
+    own = __reduce_add_sync(0xffffffffu, own);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (below) atomicAdd(out + 0, below);
+        if (own) atomicAdd(out + 1, own);
+        if (bad) atomicOr(out + 2, 1);
+    }
+}
+
 // workspace layout shared by the label call and the calls that materialise its result
 static tsim_status runs_layout(const tsim_cfg *cfg, void *workspace, size_t ws_bytes, Runs &r, int32_t *&scan_tmp, uint8_t *&fill, int cap_blobs) {
     const Win win(*cfg);
@@ -383,6 +410,18 @@ extern "C" tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask,
     const Win win(*cfg);
     const long long n = win.cells();
     ccl_labels_kernel<false><<<div_up(div_up(n, 8), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_shard_counts(const tsim_cfg *cfg, const tsim_blobs *blobs, int32_t own_lo, int32_t own_hi, int32_t *out, void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if ((st = check_blobs(blobs, "tsim_shard_counts")) != TSIM_OK) return st;
+    if (!out || own_lo < cfg->win_y0 || own_hi > cfg->win_y0 + cfg->win_rows || own_lo >= own_hi) { set_error("tsim_shard_counts: bad arguments"); return TSIM_ERR_CONFIG; }
+    cudaStream_t cs = (cudaStream_t)stream;
+    TSIM_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(int32_t), cs));
+    shard_counts_kernel<<<list_grid(blobs->cap), 256, 0, cs>>>(*cfg, blobs->table, blobs->count, blobs->cap, own_lo, own_hi, out);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

@@ -171,6 +171,7 @@ class ShardedCityLayout:
             self.shards[s] = GpuCityLayout(device=dev, win_y0=self.plan.win_lo[s], win_rows=self.plan.win_hi[s] - self.plan.win_lo[s],
                                            win_halo=self.plan.halo, **kw)
         self.n_blocks = None
+        self.trace = None   # set to [] to collect (label, cuda event) pairs of one generate() call (see phase_times)
 
     # ------------------------------------------------------------------ plumbing
     def set_bands(self, hbands, vbands):
@@ -195,21 +196,17 @@ class ShardedCityLayout:
             L._label_async()
             self._total = L.flags[2]
             return
+        import ctypes as C
+        from . import _lib
         counts, n_lo = {}, {}
         for s, L in self.shards.items():
             L._label_async()
-            tab = L.blobs.view(-1, 6)
-            valid = torch.arange(tab.shape[0], device=tab.device) < L.flags[2]
-            root = tab[:, 5].to(torch.int64)
-            lo_cell, hi_cell = (p.own_lo[s] - p.win_lo[s]) * W, (p.own_hi[s] - p.win_lo[s]) * W
-            n_lo[s] = (valid & (root < lo_cell)).sum()
-            counts[s] = (valid & (root >= lo_cell) & (root < hi_cell)).sum().reshape(1)
-            # a component that meets the own rows must not reach a cut edge of the window (ring cells need one more row)
-            miny, maxy = tab[:, 1], tab[:, 3]
-            meets = valid & (maxy >= p.own_lo[s]) & (miny < p.own_hi[s])
-            cut = ((miny <= p.win_lo[s] + 1) & (p.win_lo[s] > 0)) | ((maxy >= p.win_hi[s] - 2) & (p.win_hi[s] < self.height))
-            bad = (meets & cut).any()
-            L.flags[0] = torch.where(bad & (L.flags[0] == 0), torch.full_like(L.flags[0], ERR_HALO), L.flags[0])
+            out = L.flags[12:15]                              # n_lo, roots in the own rows, halo-too-small marker
+            _lib.check(L.lib.tsim_shard_counts(C.byref(L.cfg), C.byref(L._blobs), p.own_lo[s], p.own_hi[s], C.c_void_p(out.data_ptr()), L._stream))
+            n_lo[s] = out[0]
+            counts[s] = out[1:2].to(torch.int64)
+            # a component that meets the own rows must not reach a cut edge of the window
+            L.flags[0] = torch.where((out[2] != 0) & (L.flags[0] == 0), torch.full_like(L.flags[0], ERR_HALO), L.flags[0])
         gathered = self.comm.all_gather(counts)
         for s, L in self.shards.items():
             own = gathered[s].reshape(-1)
@@ -230,6 +227,18 @@ class ShardedCityLayout:
             t = torch.zeros((self.global_cap + 1, 8), dtype=torch.int32, device=L.device)
             out[s] = tapes.synth_carve_tape_device(u, L.blobs.view(-1, 6), L.flags[2], L.flags[4], t)
         return out
+
+    def _mark(self, label):
+        if self.trace is not None:
+            L = next(iter(self.shards.values()))
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(L.device))
+            self.trace.append((label, ev))
+
+    def phase_times(self):
+        """ms between the marks of the traced generate() call (device time line of the first local shard)."""
+        torch.cuda.synchronize()
+        return [(b[0], a[1].elapsed_time(b[1])) for a, b in zip(self.trace[:-1], self.trace[1:])]
 
     def _check(self, what):
         for L in self.shards.values():
@@ -261,17 +270,25 @@ class ShardedCityLayout:
             return
         if tape_entrance is None:                             # per-block tapes are indexed by GLOBAL block id
             tape_entrance = np.zeros(self.global_cap, np.int32)
+        self._mark("start")
         for L in S.values():
             L._build_roads_and_sidewalks()                    # closed form: exact on the whole window, no exchange
+        self._mark("frame_roads")
         if self.carve:
             self._label_and_number()
+            self._mark("carve: label + number")
             for s, L in S.items():
                 L._carve_subblock_roads(tape_carve[s] if isinstance(tape_carve, dict) else tape_carve, check=False, relabel=False)
+            self._mark("carve")
             self._exchange("cell_type", "dirs", "aux")
+            self._mark("carve: exchange")
         self._label_and_number()
+        self._mark("zones: label + number")
         for L in S.values():
             L._flood_fill_blocks_storing_data(tape_zone, check=False, relabel=False)
+        self._mark("zones")
         self._exchange("cell_type", "block_id")
+        self._mark("zones: exchange")
         self.dead_end_rounds = 0
         while True:                                           # monotone pruning: local fixed point, exchange, repeat
             for L in S.values():
@@ -280,21 +297,27 @@ class ShardedCityLayout:
             self.dead_end_rounds += 1
             if not self.comm.any({s: (L.flags[1] > 1).to(torch.int32) for s, L in S.items()}):
                 break
+        self._mark("dead_ends (+exchange, host round trip)")
         for L in S.values():
             L._upgrade_r2_to_intersections(check=False)
         self._exchange("cell_type", "dirs", "aux")
+        self._mark("upgrade_r2 + exchange")
         for L in S.values():
             L._final_place_block_entrances(tape_entrance, check=False)
         self._exchange("cell_type", "dirs", "aux", "block_id")
+        self._mark("entrances + exchange")
         for L in S.values():
             L._remove_invalid_intersection_directions()
             L._add_entrance_directions()
         self._exchange("dirs")
+        self._mark("fix_dirs + exchange")
         if lights:
             self._lights()
+            self._mark("lights + exchange")
         if maps:
             for L in S.values():
                 L._build_simple_maps()
+            self._mark("maps")
         if check:
             self._check("generate")
             self.n_blocks = int(self._total.item())
