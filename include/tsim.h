@@ -241,9 +241,7 @@ tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows, int32_t *c
                               size_t ws_bytes, void *stream);
 tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_bytes, size_t *fw_off, size_t *bw_off,
                                      int32_t *words_per_row);
-/* profiling aid: byte offset of the reach kernel's phase trace inside the workspace (uint64[65]: %globaltimer at the
-   start and after each of the four phases of its first 16 alternations) */
-tsim_status tsim_lights_reach_trace(const tsim_cfg *cfg, size_t ws_bytes, size_t *trace_off);
+
 tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *links,
                                int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
 

@@ -23,15 +23,6 @@ for rep in range(3):
     L._lights_seed(); L._lights_reach(); ev[2].record()
     L._lights_finish(check=False); ev[3].record()
     torch.cuda.synchronize()
-    alt = int(L.workspace[:256].view(torch.int32)[11].item())
-    import ctypes as C
-    off = C.c_size_t(0)
-    L.lib.tsim_lights_reach_trace(C.byref(L.cfg), C.c_size_t(L.workspace.numel()), C.byref(off))
-    tr = L.workspace[off.value: off.value + 65 * 8].view(torch.int64).cpu().numpy()
-    if rep == 2:
-        for i in range(min(alt, 16)):
-            t0 = tr[4 * i] if i else tr[0]
-            d = np.diff(np.concatenate([[t0], tr[1 + 4 * i: 5 + 4 * i]])) / 1e3
-            print(f"   alternation {i}: rows {d[0]:.0f} us, R->T {d[1]:.0f} us, columns {d[2]:.0f} us, T->R {d[3]:.0f} us")
+    alt = int(L.workspace[:256].view(torch.int32)[18].item())   # alternations of the per-phase launches
     print(f"size {a.size}: prepare {ev[0].elapsed_time(ev[1]):.3f} ms, reach {ev[1].elapsed_time(ev[2]):.3f} ms ({alt} alternations), finish {ev[2].elapsed_time(ev[3]):.3f} ms")
 L._check_flag("lights_stages")

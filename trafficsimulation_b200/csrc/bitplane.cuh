@@ -91,6 +91,64 @@ __device__ __forceinline__ bool transpose_tile2(const u64 *__restrict__ srcA, co
     return __syncthreads_or(ch);
 }
 
+// Transpose of a 512-row x 8-word tile of one plane by a CTA of 256 threads through shared memory.  Every row of the
+// tile is 64 contiguous bytes on BOTH global sides (the tile lands as 512 rows x 8 words), and four lanes cover a row
+// with 16-byte accesses, so a warp instruction moves 8 rows x 64 B: 8x fewer memory requests than word-wise access
+// (the 8-byte version was bound by the L2 request rate, profiles/).  Tile (tx, ty) = rows ty*512.., words tx*8.. of
+// `src`; it lands in rows tx*512.., words ty*8.. of `dst`.  s_in / s_out: [512][9] words each.
+// compare: read the destination first; returns (uniformly) whether a word changed, else stores blindly and returns true.
+__device__ __forceinline__ bool transpose_tile512(const u64 *__restrict__ src, int src_rows, int src_wp, u64 *__restrict__ dst, int dst_rows, int dst_wp,
+                                                  int tx, int ty, bool coherent, bool compare, u64 (*s_in)[9], u64 (*s_out)[9]) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const bool vec_in = (src_wp & 1) == 0, vec_out = (dst_wp & 1) == 0;
+#pragma unroll 4
+    for (int it = 0; it < 8; it++) {
+        const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;   // local row, 16-byte part of its 64 bytes
+        const int r = ty * 512 + lr, w = tx * 8 + part * 2;
+        u64 a = 0ull, b = 0ull;
+        if (r < src_rows) {
+            const u64 *p = src + (size_t)r * src_wp + w;
+            if (vec_in && w + 1 < src_wp) {
+                const ulonglong2 v = coherent ? __ldcg(reinterpret_cast<const ulonglong2 *>(p)) : *reinterpret_cast<const ulonglong2 *>(p);
+                a = v.x; b = v.y;
+            } else {
+                if (w < src_wp) a = coherent ? __ldcg(p) : p[0];
+                if (w + 1 < src_wp) b = coherent ? __ldcg(p + 1) : p[1];
+            }
+        }
+        s_in[lr][part * 2] = a; s_in[lr][part * 2 + 1] = b;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int blk = wid; blk < 64; blk += 8) {
+        const int i = blk >> 3, j = blk & 7;   // 64-row block i, word j of the tile
+        u64 a0 = s_in[64 * i + lane][j], a1 = s_in[64 * i + 32 + lane][j];
+        t64(a0, a1, lane);
+        s_out[64 * j + lane][i] = a0;
+        s_out[64 * j + 32 + lane][i] = a1;
+    }
+    __syncthreads();
+    bool ch = !compare;
+#pragma unroll 4
+    for (int it = 0; it < 8; it++) {
+        const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;
+        const int r = tx * 512 + lr, w = ty * 8 + part * 2;
+        if (r >= dst_rows || w >= dst_wp) continue;
+        const u64 a = s_out[lr][part * 2], b = s_out[lr][part * 2 + 1];
+        u64 *p = dst + (size_t)r * dst_wp + w;
+        const bool two = w + 1 < dst_wp;
+        if (compare) {
+            const bool diff = __ldcg(p) != a || (two && __ldcg(p + 1) != b);
+            if (!diff) continue;
+            ch = true;
+        }
+        if (vec_out && two) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b);
+        else { p[0] = a; if (two) p[1] = b; }
+    }
+    const bool any = __syncthreads_or(ch);
+    return any;
+}
+
 // 16-bit membership mask of a 16-byte strip: bit k = type byte k is in `set` (bit t of `set` = type t)
 __device__ __forceinline__ uint32_t strip_set_mask(const uint4 &q, uint32_t set) {
     uint32_t m = 0;

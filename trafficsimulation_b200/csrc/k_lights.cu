@@ -259,6 +259,136 @@ __device__ bool line_closure(u64 *__restrict__ fpl, u64 *__restrict__ bpl, const
     return any;
 }
 
+// The same closure with the whole line in REGISTERS (lines of up to 32 * NCH words): the words of the four planes are
+// fetched with independent loads (one memory latency per line instead of one per chunk and pass), the passes run on
+// registers, and only the words that changed are written back.
+template <int NCH>
+__device__ bool line_closure_reg(u64 *__restrict__ fpl, u64 *__restrict__ bpl, const u64 *__restrict__ up, const u64 *__restrict__ dn, size_t base, int wp,
+                                 int nbits, int lane, uint8_t *__restrict__ dirty, int dstride) {
+    u64 f[NCH], b[NCH], aU[NCH], aD[NCH];
+    bool live = false;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int w = c * 32 + lane;
+        const bool in = w < wp;
+        f[c] = in ? __ldcg(fpl + base + w) : 0ull; b[c] = in ? __ldcg(bpl + base + w) : 0ull;
+        aU[c] = in ? up[base + w] : 0ull; aD[c] = in ? dn[base + w] : 0ull;
+        live |= (f[c] | b[c]) != 0ull;
+    }
+    if (!__any_sync(0xffffffffu, live)) return false;   // nothing on this line yet: nothing can spread
+    const u64 tail = (nbits & 63) ? ((1ull << (nbits & 63)) - 1ull) : ~0ull;
+    uint32_t chm = 0;   // bit c: my word of chunk c changed
+    bool any = false;
+    for (int pass = 0; pass < 256; pass++) {
+        bool ch = false;
+        uint32_t cf = 0, cb = 0;
+        if ((pass & 1) == 0) {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int w = c * 32 + lane;
+                u64 f1 = fill_up(f[c], aU[c] << 1), b1 = fill_up(b[c], aD[c]);
+                const uint32_t gf = __ballot_sync(0xffffffffu, (f1 & aU[c]) >> 63), pf = __ballot_sync(0xffffffffu, aU[c] == ~0ull);
+                const uint32_t gb = __ballot_sync(0xffffffffu, b1 >> 63), pb = __ballot_sync(0xffffffffu, aD[c] == ~0ull);
+                uint32_t nf, nb;
+                const uint32_t inf = carry_chain(gf, pf, cf, nf), inb = carry_chain(gb, pb, cb, nb);
+                cf = nf; cb = nb;
+                if ((inf >> lane) & 1u) f1 = fill_up(f1 | 1ull, aU[c] << 1);
+                if ((inb >> lane) & 1u) b1 = fill_up(b1 | (aD[c] & 1ull), aD[c]);
+                if (w == wp - 1) { f1 &= tail; b1 &= tail; }
+                if (w < wp && (f1 != f[c] || b1 != b[c])) { f[c] = f1; b[c] = b1; chm |= 1u << c; ch = true; }
+            }
+        } else {
+#pragma unroll
+            for (int c = NCH - 1; c >= 0; c--) {
+                const int w = c * 32 + lane;
+                u64 f1 = fill_down(f[c], aD[c] >> 1), b1 = fill_down(b[c], aU[c]);
+                const uint32_t gf = __brev(__ballot_sync(0xffffffffu, f1 & aD[c] & 1ull)), pf = __brev(__ballot_sync(0xffffffffu, aD[c] == ~0ull));
+                const uint32_t gb = __brev(__ballot_sync(0xffffffffu, b1 & 1ull)), pb = __brev(__ballot_sync(0xffffffffu, aU[c] == ~0ull));
+                uint32_t nf, nb;
+                const uint32_t inf = __brev(carry_chain(gf, pf, cf, nf)), inb = __brev(carry_chain(gb, pb, cb, nb));
+                cf = nf; cb = nb;
+                if ((inf >> lane) & 1u) f1 = fill_down(f1 | (1ull << 63), aD[c] >> 1);
+                if ((inb >> lane) & 1u) b1 = fill_down(b1 | (aU[c] & (1ull << 63)), aU[c]);
+                if (w == wp - 1) { f1 &= tail; b1 &= tail; }
+                if (w < wp && (f1 != f[c] || b1 != b[c])) { f[c] = f1; b[c] = b1; chm |= 1u << c; ch = true; }
+            }
+        }
+        ch = __any_sync(0xffffffffu, ch);
+        any |= ch;
+        if (!ch && pass >= 1) break;
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+        if ((chm >> c) & 1u) { const int w = c * 32 + lane; fpl[base + w] = f[c]; bpl[base + w] = b[c]; dirty[(size_t)w * dstride] = 1; }
+    return any;
+}
+
+// ---- reachability as a sequence of ordinary launches (one per phase, each with its own grid and occupancy) ----------
+// ctl[0] = something changed in this alternation, ctl[1] = done, ctl[2] = alternations run.  Every phase kernel returns
+// at once when ctl[1] is set, so the host can enqueue a fixed number of alternations without reading anything back.
+struct ReachT;   // below
+
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) reach_lines_kernel(u64 *fpl, u64 *bpl, const u64 *__restrict__ up, const u64 *__restrict__ dn, int nlines, int wp,
+                                                          int nbits, const uint8_t *line_dirty, bool all, uint8_t *bd, int bd_line_stride,
+                                                          int bd_word_stride, int32_t *ctl) {
+    if (*((volatile int32_t *)(ctl + 1))) return;
+    const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (line >= nlines) return;
+    if (!all && !line_dirty[line >> 6]) return;
+    uint8_t *dirty = bd + (size_t)(line >> 6) * bd_line_stride;
+    const bool ch = NCH > 0 ? line_closure_reg<(NCH > 0 ? NCH : 1)>(fpl, bpl, up, dn, (size_t)line * wp, wp, nbits, lane, dirty, bd_word_stride)
+                            : line_closure(fpl, bpl, up, dn, (size_t)line * wp, wp, nbits, lane, dirty, bd_word_stride);
+    if (ch && lane == 0) ctl[0] = 1;
+}
+
+// 512 x 512-cell tiles of the SOURCE plane pair that hold a dirty 64 x 64 block (or all tiles) -> destination pair; marks the
+// destination's lines.  Dynamic shared memory: 2 x [512][9] words.
+__global__ void __launch_bounds__(256) reach_transpose_kernel(const u64 *srcA, const u64 *srcB, int src_rows, int src_wp, u64 *dstA, u64 *dstB, int dst_rows,
+                                                              int dst_wp, uint8_t *bd /* [nby][nbx], row-major block grid */, int nbx, int nby,
+                                                              bool src_is_rowmajor, bool all, bool compare, uint8_t *dst_line_dirty,
+                                                              uint8_t *clear_flags, int n_clear, const int32_t *ctl) {
+    extern __shared__ u64 s_tile[];
+    u64 (*s_in)[9] = reinterpret_cast<u64 (*)[9]>(s_tile);
+    u64 (*s_out)[9] = reinterpret_cast<u64 (*)[9]>(s_tile + 512 * 9);
+    if (*((volatile const int32_t *)(ctl + 1))) return;
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_clear; i += blockDim.x) clear_flags[i] = 0;   // the previous phase has read them
+    const int ntx = (nbx + 7) >> 3;
+    const int tx = blockIdx.x % ntx, ty = blockIdx.x / ntx;   // tile of the row-major block grid (8 x 8 blocks)
+    if (!all) {
+        bool any = false;
+        for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+            const int by = ty * 8 + (k >> 3), bx = tx * 8 + (k & 7);
+            if (by < nby && bx < nbx && bd[(size_t)by * nbx + bx]) { any = true; bd[(size_t)by * nbx + bx] = 0; }   // each flag has one reader
+        }
+        if (!__syncthreads_or(any)) return;
+    }
+    // a tile (tx, ty) of the row-major grid is tile (ty, tx) of the transposed planes
+    const int sx = src_is_rowmajor ? tx : ty, sy = src_is_rowmajor ? ty : tx;
+    bool tch = transpose_tile512(srcA, src_rows, src_wp, dstA, dst_rows, dst_wp, sx, sy, true, compare, s_in, s_out);
+    tch |= transpose_tile512(srcB, src_rows, src_wp, dstB, dst_rows, dst_wp, sx, sy, true, compare, s_in, s_out);
+    if (tch && threadIdx.x < 8) {
+        const int k = (src_is_rowmajor ? tx : ty) * 8 + threadIdx.x;   // destination lines = source bit columns
+        if (k < (src_is_rowmajor ? nbx : nby)) dst_line_dirty[k] = 1;
+    }
+}
+
+__global__ void reach_ctl_kernel(int32_t *ctl, int32_t *changed) {
+    if (ctl[1]) return;
+    ctl[2]++;
+    if (ctl[0]) { if (changed) *changed = 1; } else ctl[1] = 1;
+    ctl[0] = 0;
+}
+
+// resumed call: only `edge_rows` rows at each end of the window received bits from outside
+__global__ void __launch_bounds__(256) reach_mark_edges_kernel(int H, int edge_rows, int nbx, int nby, uint8_t *bdR, uint8_t *rd) {
+    const int lo_blocks = (min(edge_rows, H) + 63) >> 6, hi_first = max(H - edge_rows, 0) >> 6;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nby * nbx; i += gridDim.x * blockDim.x) {
+        const int by = i / nbx;
+        if (by < lo_blocks || by >= hi_first) { bdR[i] = 1; rd[by] = 1; }
+    }
+}
+
 // Persistent cooperative kernel: alternate row closures of the row-major planes and row closures of the TRANSPOSED
 // planes (= column closures) until an alternation changes nothing.  Both sweeps are the same warp-per-line kernel
 // with fully coalesced word loads.  Work follows the frontier: a sweep marks the 64 x 64 blocks it changed, only
@@ -268,15 +398,13 @@ struct ReachT {
     u64 *aNt, *aSt, *fwT, *bwT;   // transposed planes: [W][wpT], bit y & 63 of word y >> 6
     uint8_t *bdR, *bdT;           // [nby][nbx] block changed in the row-major / transposed planes since it was last transposed
     uint8_t *rd, *cd;             // [nby] row block / [nbx] column block needs closing
-    unsigned long long *trace;    // [1 + 4 * 16] %globaltimer at kernel start and after each phase of the first 16 alternations
     int wpT;
 };
 
-__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, ReachT rt, int edge_rows /* < 0: first call, everything is new; else only
                                                     that many rows at each end of the window received bits since the last call */,
-                                                    int32_t *flags /* [0..2] change flags, [3] alternations */, int32_t *changed, int32_t *err) {
+                                                    const int32_t *skip_if_done, int32_t *flags /* [0..2] change flags, [3] alternations */, int32_t *changed, int32_t *err) {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -284,8 +412,7 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
     const int nbx = bp.wp, nby = rt.wpT;           // 64 x 64 blocks per row / per column of the row-major planes
     __shared__ u64 s_in[2][256][5], s_out[2][256][5];
     const int ntx = (nbx + 3) >> 2, nty = (nby + 3) >> 2;   // 256 x 256 tiles of the row-major planes
-    const bool tracer = blockIdx.x == 0 && threadIdx.x == 0;
-    if (tracer) rt.trace[0] = global_ns();
+    if (skip_if_done && *((volatile const int32_t *)skip_if_done)) return;   // uniform over the grid, before any barrier
     if (edge_rows < 0) {
         for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x)
             transpose_tile2(bp.aN, bp.aS, H, bp.wp, rt.aNt, rt.aSt, W, rt.wpT, tile % ntx, tile / ntx, false, false, s_in, s_out);
@@ -323,7 +450,6 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
                 ch |= line_closure(bp.fw, bp.bw, bp.aE, bp.aW, (size_t)y * bp.wp, bp.wp, W, lane, rt.bdR + (size_t)(y >> 6) * nbx, 1);
         __threadfence();
         grid.sync();
-        if (tracer && it < 16) rt.trace[1 + 4 * it + 0] = global_ns();
         // ---- 2. tiles with changed blocks -> transposed planes
         for (int i = gtid; i < nby; i += nth) rt.rd[i] = 0;
         for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
@@ -336,7 +462,6 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
         }
         __threadfence();
         grid.sync();
-        if (tracer && it < 16) rt.trace[1 + 4 * it + 1] = global_ns();
         // ---- 3. close the columns (lines of the transposed planes) that cross a re-transposed tile
         for (int x = warp; x < W; x += nwarps)
             if (all || *((volatile uint8_t *)(rt.cd + (x >> 6))))
@@ -344,7 +469,6 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
         if (__syncthreads_or(ch) && threadIdx.x == 0) *flag = 1;
         __threadfence();
         grid.sync();
-        if (tracer && it < 16) rt.trace[1 + 4 * it + 2] = global_ns();
         // ---- 4. tiles with changed blocks -> row-major planes (tile (tx, ty) of the row-major grid = tile (ty, tx) of the transposed one)
         for (int i = gtid; i < nbx; i += nth) rt.cd[i] = 0;
         for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
@@ -357,7 +481,6 @@ __global__ void __launch_bounds__(256) reach_kernel(int W, int H, Bits bp, Reach
         }
         __threadfence();
         grid.sync();
-        if (tracer && it < 16) rt.trace[1 + 4 * it + 3] = global_ns();
         const int any = *((volatile int32_t *)flag);
         if (blockIdx.x == 0 && threadIdx.x == 0) { flags[(it + 2) % 3] = 0; flags[3] = it + 1; if (any && changed) *changed = 1; }
         if (!any) break;
@@ -704,7 +827,6 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
     L.rt.bdT = (uint8_t *)take((size_t)L.rt.wpT * L.wp);
     L.rt.rd = (uint8_t *)take((size_t)L.rt.wpT);
     L.rt.cd = (uint8_t *)take((size_t)L.wp);
-    L.rt.trace = (unsigned long long *)take(65 * 8);
     L.cr_prefix = (int32_t *)take((size_t)L.nw * 4);
     L.tl_prefix = (int32_t *)take((size_t)L.nw * 4);
     L.scan_tmp = (int32_t *)take((size_t)(div_up(L.nw, SCAN_TILE) + 1) * 4);
@@ -763,6 +885,31 @@ extern "C" tsim_status tsim_lights_seed(const tsim_cfg *cfg, const int32_t *pivo
 }
 
 // stage 2b: closure of the planes inside this window; *changed (device, optional) is set to 1 if a bit was added
+template <int NCH>
+static tsim_status launch_lines(u64 *f, u64 *b, const u64 *up, const u64 *dn, int nlines, int wp, int nbits, const uint8_t *line_dirty, bool all,
+                                uint8_t *bd, int bd_line_stride, int bd_word_stride, int32_t *ctl, cudaStream_t cs) {
+    reach_lines_kernel<NCH><<<div_up(nlines, 8), 256, 0, cs>>>(f, b, up, dn, nlines, wp, nbits, line_dirty, all, bd, bd_line_stride, bd_word_stride, ctl);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
+
+static tsim_status reach_lines(u64 *f, u64 *b, const u64 *up, const u64 *dn, int nlines, int wp, int nbits, const uint8_t *line_dirty, bool all,
+                               uint8_t *bd, int bd_line_stride, int bd_word_stride, int32_t *ctl, cudaStream_t cs) {
+    // lines of up to 256 words live in registers (1, 2, 4 or 8 words per lane); longer ones are closed from global memory
+    if (wp <= 32) return launch_lines<1>(f, b, up, dn, nlines, wp, nbits, line_dirty, all, bd, bd_line_stride, bd_word_stride, ctl, cs);
+    if (wp <= 64) return launch_lines<2>(f, b, up, dn, nlines, wp, nbits, line_dirty, all, bd, bd_line_stride, bd_word_stride, ctl, cs);
+    if (wp <= 128) return launch_lines<4>(f, b, up, dn, nlines, wp, nbits, line_dirty, all, bd, bd_line_stride, bd_word_stride, ctl, cs);
+    if (wp <= 256) return launch_lines<8>(f, b, up, dn, nlines, wp, nbits, line_dirty, all, bd, bd_line_stride, bd_word_stride, ctl, cs);
+    return launch_lines<0>(f, b, up, dn, nlines, wp, nbits, line_dirty, all, bd, bd_line_stride, bd_word_stride, ctl, cs);
+}
+
+constexpr int REACH_ALTERNATIONS = 10;   // enqueued as ordinary launches; anything beyond is finished by the cooperative kernel
+
+// stage 2b: closure of the planes inside this window; *changed (device, optional) is set to 1 if a bit was added.
+// Each phase (row closures, re-transposition of the changed tiles, column closures, transposition back) is its own
+// launch with its own grid; a phase kernel returns at once when the closure is already complete, so a fixed number of
+// alternations is enqueued without any host round trip.  A city that needs more turns than that is finished by the
+// persistent cooperative kernel (same result, one launch, grid-wide barriers), which otherwise exits immediately.
 extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes,
                                          void *stream) {
     tsim_status st = lights_check(cfg);
@@ -771,17 +918,53 @@ extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows,
     LightsWs L;
     if ((st = lights_ws(cfg, workspace, ws_bytes, L)) != TSIM_OK) return st;
     cudaStream_t cs = (cudaStream_t)stream;
+    const int W = L.W, H = L.H, wp = L.wp, wpT = L.rt.wpT, nbx = wp, nby = wpT;
+    const int ntiles = div_up(nbx, 8) * div_up(nby, 8);
+    const size_t tsmem = (size_t)2 * 512 * 9 * 8;   // 72 KB of dynamic shared memory per transposing CTA
+    TSIM_CUDA(cudaFuncSetAttribute(reach_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    const Bits &bp = L.bp;
+    const ReachT &rt = L.rt;
+    int32_t *ctl = L.scal + 16;      // [0] changed, [1] done, [2] alternations
+    int32_t *flags = L.scal + 8;     // cooperative kernel's own flags
+    TSIM_CUDA(cudaMemsetAsync(flags, 0, 16, cs));
+    TSIM_CUDA(cudaMemsetAsync(ctl, 0, 16, cs));
+    TSIM_CUDA(cudaMemsetAsync(rt.bdR, 0, (size_t)((char *)rt.cd - (char *)rt.bdR) + wp, cs));   // the four flag arrays are contiguous
+    const bool first = edge_rows < 0;
+    if (first) {   // transposed arrow planes (kept in the workspace for resumed calls)
+        reach_transpose_kernel<<<ntiles, 256, tsmem, cs>>>(bp.aN, bp.aS, H, wp, rt.aNt, rt.aSt, W, wpT, rt.bdR, nbx, nby, true, true, false, rt.cd, rt.cd, 0, ctl);
+        TSIM_LAUNCH_CHECK();
+        TSIM_CUDA(cudaMemsetAsync(rt.cd, 0, wp, cs));   // (the arrow transposition marked its lines; they are not reachability changes)
+    } else {
+        reach_mark_edges_kernel<<<div_up(nbx * nby, 256) < 1184 ? div_up(nbx * nby, 256) : 1184, 256, 0, cs>>>(H, edge_rows, nbx, nby, rt.bdR, rt.rd);
+        TSIM_LAUNCH_CHECK();
+    }
+    for (int a = 0; a < REACH_ALTERNATIONS; a++) {
+        const bool all = first && a == 0;
+        // rows: lines of the row-major planes; a changed word (y, w) marks block (y >> 6, w)
+        if ((st = reach_lines(bp.fw, bp.bw, bp.aE, bp.aW, H, wp, W, rt.rd, all, rt.bdR, nbx, 1, ctl, cs)) != TSIM_OK) return st;
+        reach_transpose_kernel<<<ntiles, 256, tsmem, cs>>>(bp.fw, bp.bw, H, wp, rt.fwT, rt.bwT, W, wpT, rt.bdR, nbx, nby, true, all, !first && a == 0, rt.cd,
+                                                       rt.rd, nby, ctl);
+        TSIM_LAUNCH_CHECK();
+        // columns: lines of the transposed planes; a changed word (x, wy) marks block (wy, x >> 6)
+        if ((st = reach_lines(rt.fwT, rt.bwT, rt.aNt, rt.aSt, W, wpT, H, rt.cd, all, rt.bdT, 1, nbx, ctl, cs)) != TSIM_OK) return st;
+        reach_transpose_kernel<<<ntiles, 256, tsmem, cs>>>(rt.fwT, rt.bwT, W, wpT, bp.fw, bp.bw, H, wp, rt.bdT, nbx, nby, false, false, false, rt.rd, rt.cd,
+                                                       nbx, ctl);
+        TSIM_LAUNCH_CHECK();
+        reach_ctl_kernel<<<1, 1, 0, cs>>>(ctl, changed);
+        TSIM_LAUNCH_CHECK();
+    }
+    // not converged after the enqueued alternations: the cooperative kernel finishes the closure (exits at once otherwise)
     int dev = 0, sms = 0, per_sm = 0;
     TSIM_CUDA(cudaGetDevice(&dev));
     TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reach_kernel, 256, 0));
     int grid = sms * (per_sm < 1 ? 1 : per_sm);
-    const int want = div_up(L.H > L.W ? L.H : L.W, 8);   // one warp per row / per column
+    const int want = div_up(H > W ? H : W, 8);   // one warp per row / per column
     if (grid > want) grid = want;
-    int32_t *flags = L.scal + 8;
-    TSIM_CUDA(cudaMemsetAsync(flags, 0, 16, cs));
-    TSIM_CUDA(cudaMemsetAsync(L.rt.bdR, 0, (size_t)((char *)L.rt.cd - (char *)L.rt.bdR) + L.wp, cs));   // the four flag arrays are contiguous
-    void *args[] = {&L.W, &L.H, &L.bp, &L.rt, &edge_rows, &flags, &changed, &err_flag};
+    int full = -1;
+    const int32_t *skip = ctl + 1;
+    LightsWs *Lp = &L;
+    void *args[] = {&Lp->W, &Lp->H, &Lp->bp, &Lp->rt, &full, &skip, &flags, &changed, &err_flag};
     TSIM_COOP_LAUNCH(reach_kernel, dim3(grid), dim3(256), args, cs);
     return TSIM_OK;
 }
@@ -796,17 +979,6 @@ extern "C" tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_b
     char dummy;
     if ((st = lights_ws(cfg, &dummy, ws_bytes, L)) != TSIM_OK) return st;
     *fw_off = (size_t)((char *)L.bp.fw - &dummy); *bw_off = (size_t)((char *)L.bp.bw - &dummy); *words_per_row = L.wp;
-    return TSIM_OK;
-}
-
-extern "C" tsim_status tsim_lights_reach_trace(const tsim_cfg *cfg, size_t ws_bytes, size_t *trace_off) {
-    tsim_status st = lights_check(cfg);
-    if (st != TSIM_OK) return st;
-    if (!trace_off) { set_error("tsim_lights_reach_trace: NULL output"); return TSIM_ERR_CONFIG; }
-    LightsWs L;
-    char dummy;
-    if ((st = lights_ws(cfg, &dummy, ws_bytes, L)) != TSIM_OK) return st;
-    *trace_off = (size_t)((char *)L.rt.trace - &dummy);
     return TSIM_OK;
 }
 
