@@ -120,6 +120,16 @@ def test_frame_pass_kernels_agree(mode):
     _cmp("roads/" + mode, oc, gc, ("cell_type", "dirs", "aux"))
 
 
+@pytest.mark.parametrize("n_alt", ["0", "1", "2"])
+def test_reach_fallback_kernel_gives_the_same_city(n_alt, monkeypatch):
+    """The reachability closure enqueues a fixed number of alternations and leaves the rest to the persistent cooperative
+    kernel; with 0 / 1 / 2 enqueued alternations that kernel does (almost) all the work and the result must not change."""
+    monkeypatch.setenv("TSIM_REACH_ALTERNATIONS", n_alt)
+    path = [p for p in layout_fixtures() if "s7_carve" in p][0]
+    g = load(path)
+    lockstep(g["meta"]["cfg"], g["hbands"], g["vbands"], g["tape_zone"], g["tape_carve"], g["tape_entrance"])
+
+
 SYNTH = [
     (101, dict(width=512, height=512), True),
     (102, dict(width=1024, height=768, ring_road_type="R1"), True),

@@ -33,6 +33,7 @@
 //      count -> scan -> fill from the records; type / aux updates are written for the candidate and
 //      light cells only (sparse), never as a full-plane sweep.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "scan.cuh"
 #include "bitplane.cuh"
 
@@ -905,6 +906,14 @@ static tsim_status reach_lines(u64 *f, u64 *b, const u64 *up, const u64 *dn, int
 
 constexpr int REACH_ALTERNATIONS = 10;   // enqueued as ordinary launches; anything beyond is finished by the cooperative kernel
 
+// TSIM_REACH_ALTERNATIONS=<n> overrides the number of enqueued alternations (tests use 0 / 1 to exercise the fallback kernel)
+static int reach_alternations() {
+    const char *e = getenv("TSIM_REACH_ALTERNATIONS");
+    if (!e || !*e) return REACH_ALTERNATIONS;
+    const int v = atoi(e);
+    return v < 0 ? 0 : (v > 64 ? 64 : v);
+}
+
 // stage 2b: closure of the planes inside this window; *changed (device, optional) is set to 1 if a bit was added.
 // Each phase (row closures, re-transposition of the changed tiles, column closures, transposition back) is its own
 // launch with its own grid; a phase kernel returns at once when the closure is already complete, so a fixed number of
@@ -938,7 +947,8 @@ extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows,
         reach_mark_edges_kernel<<<div_up(nbx * nby, 256) < 1184 ? div_up(nbx * nby, 256) : 1184, 256, 0, cs>>>(H, edge_rows, nbx, nby, rt.bdR, rt.rd);
         TSIM_LAUNCH_CHECK();
     }
-    for (int a = 0; a < REACH_ALTERNATIONS; a++) {
+    const int n_alt = reach_alternations();
+    for (int a = 0; a < n_alt; a++) {
         const bool all = first && a == 0;
         // rows: lines of the row-major planes; a changed word (y, w) marks block (y >> 6, w)
         if ((st = reach_lines(bp.fw, bp.bw, bp.aE, bp.aW, H, wp, W, rt.rd, all, rt.bdR, nbx, 1, ctl, cs)) != TSIM_OK) return st;
