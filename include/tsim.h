@@ -295,7 +295,9 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
     /* light-group state [n_groups] */
     int32_t *g_cur, *g_pend, *g_qt, *g_gap, *g_last, *g_ft_phase, *g_ft_timer, *g_plan;
     int32_t *scalars;                            /* [16]: [0] next tick, [1] error flag, [2] fixed-point iterations (sum),
-                                                    [3] vehicle updates (sum of live vehicles per tick), [4..] internal */
+                                                    [6..7] vehicle updates (int64: sum over ticks of the live vehicles on
+                                                    own rows), [9] shard-exchange error flag, rest internal           */
+    int32_t own_row_lo, own_row_hi;              /* LOCAL rows of the window this shard owns; 0, 0 = the whole window          */
 } tsim_tick_state;
 
 /* zero the maps / vehicle / group state and prepare the scratch planes */
@@ -305,6 +307,34 @@ tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, con
 /* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME */
 tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                           const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
+
+/* ---- row-band shards of the tick (SURVEY.md 8e "Vehicle step"; no reference counterpart: the reference is one process).
+   A shard runs tsim_tick_run on its WINDOW (tsim_cfg.win_y0 / win_rows / win_halo): every cell index in
+   tsim_light_tables, tsim_tick_state and the origin / target / ev_cells tapes is LOCAL to the window
+   ((y - win_y0) * width + x); a tape cell outside the window is TSIM_CELL_OUTSIDE.  The vehicle arrays keep
+   their global length (a vehicle is the same index on every shard).  After every tick the shards refresh the
+   halo: planes row-wise (caller), vehicles through the two calls below.                                        */
+#define TSIM_CELL_OUTSIDE (-2)
+#define TSIM_TICK_REC_WORDS 12      /* int32 words per vehicle record                                          */
+#define TSIM_TICK_REC_HEADER 16     /* int32 words before the first record; word 0 = number of records        */
+
+typedef struct tsim_tick_strips {    /* [0] = neighbour below (lower rows), [1] = neighbour above; LOCAL row ranges */
+    int32_t send_lo[2], send_hi[2];      /* own rows whose vehicles the neighbour needs (empty: no neighbour)      */
+    int32_t halo_lo[2], halo_hi[2];      /* halo rows owned by that neighbour                                      */
+    int32_t verify_lo[2], verify_hi[2];  /* halo rows where this shard's ghost must equal the owner's record      */
+    int32_t *records[2];                 /* [HEADER + cap * REC_WORDS] device buffers (NULL: no neighbour)         */
+    int32_t cap;
+} tsim_tick_strips;
+
+/* fills records[d] with the vehicles on send rows d; marks the vehicles on halo rows as awaiting their owner */
+tsim_status tsim_tick_pack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st,
+                           const tsim_tick_strips *strips, void *stream);
+
+/* records[d] = the buffers RECEIVED from the neighbours: installs the owners' vehicles on the halo rows, drops
+   the ghosts nobody sent; a ghost on the verify rows that differs from its owner sets scalars[9] (40..43):
+   the halo is too small for the dependency chains of this traffic                                             */
+tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st,
+                             const tsim_tick_strips *strips, void *stream);
 
 /* labels the 4-connected components of mask == 1 (u8 plane) in raster discovery order: component
    table as tsim_layout_label_nothing, plus the label plane (id, 0 elsewhere).  Used for the

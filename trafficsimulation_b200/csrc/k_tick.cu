@@ -42,10 +42,13 @@ constexpr int NO_CLAIM = 0x7fffffff;
 constexpr int MAX_SPEED = 5;          // random.randint(1, 5), vehicle_base.py:112: a vehicle plans at most 5 cells
 constexpr int GEN_PER_TICK = 1024;   // claim generations per tick: sweeps 1..1022, spawner 1023
 typedef unsigned long long u64;
-enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8 };
+enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8, S_XERR = 9 /* shard exchange */ };
+
+constexpr int OUTSIDE = -2;          // a tape cell that lies outside this shard's window (host-side translation, tsim.h)
 
 struct TickArgs {
-    int W, H, n_ticks, algo;
+    int W, H, n_ticks, algo;   // H = rows of the window; every cell index below is LOCAL to the window
+    int own_lo, own_hi;        // local cell range of the rows this shard owns (vehicle_updates counts only those)
     tsim_light_tables lt;
     tsim_tick_tapes tp;
     tsim_tick_state st;
@@ -171,13 +174,14 @@ __device__ void vehicle_decide(const TickArgs &a, int v, int t) {
 #pragma unroll
         for (int i = 0; i < MAX_SPEED; i++) cell[i] = i < look ? path[i] : -1;
 #pragma unroll
-        for (int i = 0; i < MAX_SPEED; i++) blocked[i] = cell[i] >= 0 && (s.stop_map[cell[i]] == 1 || s.occupancy[cell[i]] == 1);
+        for (int i = 0; i < MAX_SPEED; i++)   // a cell beyond the window edge blocks (only ghosts deep in the halo can see one)
+            blocked[i] = cell[i] == OUTSIDE || (cell[i] >= 0 && (s.stop_map[cell[i]] == 1 || s.occupancy[cell[i]] == 1));
 #pragma unroll
         for (int i = MAX_SPEED - 1; i >= 0; i--) if (blocked[i]) ms = i;
     } else {
         for (int i = 0; i < look; i++) {
             const int c = path[i];
-            if (s.stop_map[c] == 1 || s.occupancy[c] == 1) { ms = i; break; }
+            if (c < 0 || s.stop_map[c] == 1 || s.occupancy[c] == 1) { ms = i; break; }
         }
     }
     s.max_steps[v] = (int8_t)ms;
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
         // ---- 1: phase A + light-group decisions (staged)
         int live = 0;
         for (int v = tid; v < nv; v += nth)
-            if (s.alive[v]) { vehicle_decide(a, v, t); live++; }
+            if (s.alive[v]) { vehicle_decide(a, v, t); const int p = s.pos[v]; live += p >= a.own_lo && p < a.own_hi; }
         live = __reduce_add_sync(0xffffffffu, live);
         if ((threadIdx.x & 31) == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
         for (int g = tid; g < ng; g += nth) group_decide(a, g);
@@ -328,14 +332,14 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
         const int k0 = tp.spawn_first[t], k1 = tp.spawn_first[t + 1];
         const uint32_t gen_spawn = (uint32_t)t * GEN_PER_TICK + GEN_PER_TICK - 1;
         for (int k = k0 + tid; k < k1; k += nth)
-            if (s.occupancy[tp.origin[k]] == 0) claim_cell(plane[0], tp.origin[k], gen_spawn, k);
+            if (tp.origin[k] >= 0 && s.occupancy[tp.origin[k]] == 0) claim_cell(plane[0], tp.origin[k], gen_spawn, k);
         for (int g = tid; g < ng; g += nth) group_apply(a, g);
         if (tid == 0) { s.scalars[S_FLAG0] = 0; s.scalars[S_FLAG1] = 0; s.scalars[S_FLAG2] = 0; }   // nobody touches the sweep flags here
         grid.sync();
         // ---- 5: spawns, the next tick's route events
         for (int k = k0 + tid; k < k1; k += nth) {
             const int o = tp.origin[k];
-            if (claim_rank(plane[0], o, gen_spawn) != k) continue;
+            if (o < 0 || claim_rank(plane[0], o, gen_spawn) != k) continue;
             s.alive[k] = 1; s.pos[k] = o;
             s.base_speed[k] = 0; s.cur_speed[k] = 0; s.max_steps[k] = 0; s.early[k] = 0; s.is_stuck[k] = 0; s.prev_valid[k] = 0;
             s.malfunction[k] = 0; s.direction[k] = -1; s.stuck_ticks[k] = 0; s.stranded[k] = 0; s.steps[k] = 0; s.moved[k] = 0;
@@ -347,6 +351,91 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
     }
 }
 
+// ---- shards (SURVEY.md 8e "Vehicle step"): vehicle records travel between neighbour shards once per tick -------------------
+// record = TSIM_TICK_REC_WORDS int32: 0 vehicle, 1 global row, 2 column, 3 path_len, 4 steps, 5 stranded, 6..7 path_off,
+// 8 stuck_ticks | base_speed << 16 | cur_speed << 24, 9 is_stuck | prev_valid << 8 | malfunction << 16 | direction << 24
+constexpr int REC = TSIM_TICK_REC_WORDS, REC_HDR = TSIM_TICK_REC_HEADER;
+enum { ALIVE = 1, ZOMBIE = 2 };   // ZOMBIE: a ghost of the halo awaiting its owner's record
+
+struct StripArgs {
+    int W, y0, nv, cap;
+    tsim_tick_strips sp;
+    tsim_tick_state st;
+};
+
+__device__ __forceinline__ void make_record(const tsim_tick_state &s, int v, int W, int y0, int32_t *r) {
+    const int pos = s.pos[v];
+    const long long off = s.path_off[v];
+    r[0] = v; r[1] = pos / W + y0; r[2] = pos % W; r[3] = s.path_len[v]; r[4] = s.steps[v]; r[5] = s.stranded[v];
+    r[6] = (int32_t)(off & 0xffffffffLL); r[7] = (int32_t)(off >> 32);
+    r[8] = (int32_t)((uint32_t)(uint16_t)s.stuck_ticks[v] | ((uint32_t)(uint8_t)s.base_speed[v] << 16) | ((uint32_t)(uint8_t)s.cur_speed[v] << 24));
+    r[9] = (int32_t)((uint32_t)(uint8_t)s.is_stuck[v] | ((uint32_t)(uint8_t)s.prev_valid[v] << 8) | ((uint32_t)(uint8_t)s.malfunction[v] << 16) |
+                     ((uint32_t)(uint8_t)s.direction[v] << 24));
+    r[10] = 0; r[11] = 0;
+}
+
+// vehicles on the own rows next to a cut are packed for that neighbour; vehicles on halo rows become zombies
+__global__ void __launch_bounds__(256) tick_pack_kernel(StripArgs a) {
+    const tsim_tick_state &s = a.st;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.nv; v += gridDim.x * blockDim.x) {
+        if (s.alive[v] != ALIVE) continue;
+        const int row = s.pos[v] / a.W;
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            if (row >= a.sp.halo_lo[d] && row < a.sp.halo_hi[d]) s.alive[v] = ZOMBIE;
+            if (a.sp.records[d] && row >= a.sp.send_lo[d] && row < a.sp.send_hi[d]) {
+                const int k = atomicAdd(a.sp.records[d], 1);
+                if (k < a.cap) make_record(s, v, a.W, a.y0, a.sp.records[d] + REC_HDR + (size_t)k * REC);
+                else s.scalars[S_XERR] = 43;   // strip holds more vehicles than the record buffer
+            }
+        }
+    }
+}
+
+// the owner's records replace the ghosts of the halo; inside the verify rows the ghost this shard simulated must be identical
+__global__ void __launch_bounds__(256) tick_unpack_kernel(StripArgs a) {
+    const tsim_tick_state &s = a.st;
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        const int32_t *buf = a.sp.records[d];
+        if (!buf) continue;
+        const int n = min(buf[0], a.cap);
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+            const int32_t *r = buf + REC_HDR + (size_t)k * REC;
+            const int v = r[0], row = r[1] - a.y0;
+            if (v < 0 || v >= a.nv || row < a.sp.halo_lo[d] || row >= a.sp.halo_hi[d]) { s.scalars[S_XERR] = 40; continue; }
+            if (row >= a.sp.verify_lo[d] && row < a.sp.verify_hi[d]) {
+                int32_t mine[REC];
+                bool same = s.alive[v] == ZOMBIE;
+                if (same) {
+                    make_record(s, v, a.W, a.y0, mine);
+                    for (int i = 1; i < 10; i++) same = same && mine[i] == r[i];
+                }
+                if (!same) s.scalars[S_XERR] = 41;   // the ghost diverged from its owner: the halo is too small for this traffic
+            }
+            s.alive[v] = ALIVE;
+            s.pos[v] = row * a.W + r[2]; s.path_len[v] = r[3]; s.steps[v] = r[4]; s.stranded[v] = r[5];
+            s.path_off[v] = (long long)(uint32_t)r[6] | ((long long)r[7] << 32);
+            const uint32_t w8 = (uint32_t)r[8], w9 = (uint32_t)r[9];
+            s.stuck_ticks[v] = (int16_t)(w8 & 0xffff); s.base_speed[v] = (int8_t)(w8 >> 16); s.cur_speed[v] = (int8_t)(w8 >> 24);
+            s.is_stuck[v] = (int8_t)w9; s.prev_valid[v] = (int8_t)(w9 >> 8); s.malfunction[v] = (int8_t)(w9 >> 16); s.direction[v] = (int8_t)(w9 >> 24);
+            s.early[v] = 0; s.moved[v] = 0; s.max_steps[v] = 0;
+        }
+    }
+}
+
+// zombies nobody claimed are gone (they left the window or were never real); inside the verify rows that is a divergence
+__global__ void __launch_bounds__(256) tick_reap_kernel(StripArgs a) {
+    const tsim_tick_state &s = a.st;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.nv; v += gridDim.x * blockDim.x) {
+        if (s.alive[v] != ZOMBIE) continue;
+        const int row = s.pos[v] / a.W;
+        for (int d = 0; d < 2; d++)
+            if (row >= a.sp.verify_lo[d] && row < a.sp.verify_hi[d]) s.scalars[S_XERR] = 42;
+        s.alive[v] = 0;
+    }
+}
+
 __global__ void fill_i32_kernel(long long n, int32_t *p, int32_t v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -355,18 +444,71 @@ __global__ void fill_i32_kernel(long long n, int32_t *p, int32_t v) {
 
 using namespace tsim;
 
+// local cell range of the rows the window's shard owns
+static void own_cells(const tsim_cfg *cfg, const tsim_tick_state *st, int &lo, int &hi) {
+    const bool all = st->own_row_lo == 0 && st->own_row_hi == 0;
+    lo = all ? 0 : st->own_row_lo * cfg->width;
+    hi = all ? cfg->win_rows * cfg->width : st->own_row_hi * cfg->width;
+}
+
+static tsim_status strip_args(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, const tsim_tick_strips *sp, StripArgs &a) {
+    tsim_status r = check_cfg(cfg);
+    if (r != TSIM_OK) return r;
+    if (!tp || !st || !sp || sp->cap < 1 || !st->pos || !st->alive || !st->scalars) { set_error("tick strips: bad arguments"); return TSIM_ERR_CONFIG; }
+    for (int d = 0; d < 2; d++)
+        if (sp->send_lo[d] < 0 || sp->send_hi[d] > cfg->win_rows || sp->halo_lo[d] < 0 || sp->halo_hi[d] > cfg->win_rows ||
+            sp->verify_lo[d] < sp->halo_lo[d] || sp->verify_hi[d] > sp->halo_hi[d]) {
+            set_error("tick strips: row ranges outside the window");
+            return TSIM_ERR_CONFIG;
+        }
+    a = StripArgs{cfg->width, cfg->win_y0, tp->n_vehicles, sp->cap, *sp, *st};
+    return TSIM_OK;
+}
+
+static int strip_grid(int n) { const int g = div_up(n, 256); return g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g); }
+
+extern "C" tsim_status tsim_tick_pack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, const tsim_tick_strips *sp,
+                                      void *stream) {
+    StripArgs a;
+    tsim_status r = strip_args(cfg, tp, st, sp, a);
+    if (r != TSIM_OK) return r;
+    cudaStream_t cs = (cudaStream_t)stream;
+    for (int d = 0; d < 2; d++)
+        if (sp->records[d]) TSIM_CUDA(cudaMemsetAsync(sp->records[d], 0, REC_HDR * sizeof(int32_t), cs));
+    if (a.nv == 0) return TSIM_OK;
+    tick_pack_kernel<<<strip_grid(a.nv), 256, 0, cs>>>(a);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, const tsim_tick_strips *sp,
+                                        void *stream) {
+    StripArgs a;
+    tsim_status r = strip_args(cfg, tp, st, sp, a);
+    if (r != TSIM_OK) return r;
+    if (a.nv == 0) return TSIM_OK;
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (sp->records[0] || sp->records[1]) {
+        tick_unpack_kernel<<<strip_grid(a.cap), 256, 0, cs>>>(a);
+        TSIM_LAUNCH_CHECK();
+    }
+    tick_reap_kernel<<<strip_grid(a.nv), 256, 0, cs>>>(a);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
+
 static tsim_status check_tick_args(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st) {
     tsim_status s = check_cfg(cfg);
     if (s != TSIM_OK) return s;
     if (!lt || !tp || !st) { set_error("tick: NULL argument struct"); return TSIM_ERR_CONFIG; }
     if (tp->n_vehicles < 0 || tp->n_ticks < 1 || lt->n_groups < 0) { set_error("tick: bad sizes"); return TSIM_ERR_CONFIG; }
+    if (st->own_row_lo < 0 || st->own_row_hi < st->own_row_lo || st->own_row_hi > cfg->win_rows) { set_error("tick: bad own rows"); return TSIM_ERR_CONFIG; }
     if (!st->occupancy || !st->stop_map || !st->stuck_map || !st->claim || !st->stopw || !st->scalars) { set_error("tick: NULL map / scratch plane"); return TSIM_ERR_CONFIG; }
     if (tp->n_vehicles > 0 && (!st->pos || !st->path_off || !st->path_len || !st->alive || !st->moved || !tp->origin || !tp->target || !tp->speed ||
                                !tp->malfunction || !tp->rank || !tp->spawn_first || !tp->ev_first)) {
         set_error("tick: NULL vehicle array / tape");
         return TSIM_ERR_CONFIG;
     }
-    if (cfg->win_y0 != 0 || cfg->win_rows != cfg->height) { set_error("tick: sharded windows are handled by the host-side shard driver"); return TSIM_ERR_UNSUPPORTED; }
     return TSIM_OK;
 }
 
@@ -375,7 +517,7 @@ extern "C" tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tabl
     tsim_status r = check_tick_args(cfg, lt, tp, st);
     if (r != TSIM_OK) return r;
     cudaStream_t cs = (cudaStream_t)stream;
-    const size_t n = (size_t)cfg->width * cfg->height, nv = (size_t)tp->n_vehicles, ng = (size_t)lt->n_groups;
+    const size_t n = (size_t)cfg->width * cfg->win_rows, nv = (size_t)tp->n_vehicles, ng = (size_t)lt->n_groups;
     TSIM_CUDA(cudaMemsetAsync(st->occupancy, 0, n, cs));
     TSIM_CUDA(cudaMemsetAsync(st->stop_map, 0, n, cs));
     TSIM_CUDA(cudaMemsetAsync(st->stuck_map, 0, n, cs));
@@ -408,7 +550,8 @@ extern "C" tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_table
     tsim_status r = check_tick_args(cfg, lt, tp, st);
     if (r != TSIM_OK) return r;
     if (n_ticks < 1 || (algo != 0 && algo != 1)) { set_error("tick: n_ticks %d algo %d", n_ticks, algo); return TSIM_ERR_CONFIG; }
-    TickArgs a{cfg->width, cfg->height, n_ticks, algo, *lt, *tp, *st};
+    TickArgs a{cfg->width, cfg->win_rows, n_ticks, algo, 0, 0, *lt, *tp, *st};
+    own_cells(cfg, st, a.own_lo, a.own_hi);
     int dev = 0, sms = 0, per_sm = 0;
     TSIM_CUDA(cudaGetDevice(&dev));
     TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -60,16 +60,25 @@ class GpuTraffic:
     ev_tick (sorted), ev_vehicle, ev_off (int64, n_events+1), ev_cells, optional rain_map [H,W] u8.
     """
 
-    def __init__(self, width, height, light_tables, tapes, n_ticks, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0"):
+    def __init__(self, width, height, light_tables, tapes, n_ticks, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0",
+                 window=None, own_rows=None):
+        """window = (win_y0, win_rows, win_halo): this object is one row-band shard (``ShardedTraffic`` builds those);
+        every cell index in `light_tables` / `tapes` is then local to the window, cells outside it are -2;
+        own_rows = (lo, hi): local rows the shard owns (the update counter skips the ghosts on the other rows)."""
         if not torch.cuda.is_available():
             raise RuntimeError("trafficsimulation_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
         self.device = dev = torch.device(device)
         self.W, self.H, self.n_ticks = int(width), int(height), int(n_ticks)
         self.algo = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1}[algo]
-        self.cfg = _lib.Cfg(self.W, self.H, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, self.H, 0)   # win_y0 = 0, win_rows = H
-        n = self.W * self.H
-        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+        self.win_y0, self.win_rows, self.win_halo = (0, self.H, 0) if window is None else (int(v) for v in window)
+        self.cfg = _lib.Cfg(self.W, self.H, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, self.win_y0, self.win_rows, self.win_halo)
+        n = self.W * self.win_rows
+
+        def up(a, dt):   # host array -> device; a tensor already on the device is shared, not copied
+            if isinstance(a, torch.Tensor):
+                return a.to(device=dev, dtype=getattr(torch, np.dtype(dt).name)).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
         # ---- light tables
         self.lt_t = {k: up(light_tables[k], np.int32) for k in _LT}
         self.n_groups, self.n_lights = int(light_tables["n_groups"]), int(light_tables["n_lights"])
@@ -89,7 +98,8 @@ class GpuTraffic:
         tt["ev_first"] = up(np.searchsorted(ev_tick, np.arange(n_ticks + 1)), np.int32)
         tt["ev_vehicle"] = up(tapes["ev_vehicle"], np.int32)
         tt["ev_off"] = up(tapes["ev_off"], np.int64)
-        tt["ev_cells"] = up(np.append(np.asarray(tapes["ev_cells"], np.int32), 0), np.int32)
+        ev = tapes["ev_cells"]   # one spare entry at the end: the kernel may form the address of path[len]
+        tt["ev_cells"] = up(ev, np.int32) if isinstance(ev, torch.Tensor) else up(np.append(np.asarray(ev, np.int32), 0), np.int32)
         rain = tapes.get("rain_map") if rain_enabled else None
         tt["rain_map"] = up(np.asarray(rain).reshape(-1), np.uint8) if rain is not None else None
         self.tt = tt
@@ -106,12 +116,13 @@ class GpuTraffic:
         s["stuck_ticks"] = z(nv, torch.int16)
         for k in _I8:
             s[k] = z(nv, torch.int8)
-        for k in _G32:
-            s[k] = z(self.n_groups, torch.int32)
+        self.gstate = torch.zeros(len(_G32), max(self.n_groups, 1), dtype=torch.int32, device=dev)   # one row per field: shards exchange columns
+        for i, k in enumerate(_G32):
+            s[k] = self.gstate[i]
         s["scalars"] = z(16, torch.int32)
         self.s = s
-        order = [f[0] for f in _lib.TickState._fields_]
-        self.st = _lib.TickState(*[s[k].data_ptr() for k in order])
+        order = [f[0] for f in _lib.TickState._fields_ if f[1] is C.c_void_p]
+        self.st = _lib.TickState(*[s[k].data_ptr() for k in order], *(own_rows or (0, 0)))
         _lib.check(self.lib.tsim_tick_init(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), self._stream))
 
     @property
@@ -121,15 +132,15 @@ class GpuTraffic:
     # public maps of the reference model (city_model.py:109-115)
     @property
     def occupancy_map(self):
-        return self.s["occupancy"].view(self.H, self.W)
+        return self.s["occupancy"].view(self.win_rows, self.W)
 
     @property
     def stop_map(self):
-        return self.s["stop_map"].view(self.H, self.W)
+        return self.s["stop_map"].view(self.win_rows, self.W)
 
     @property
     def stuck_map(self):
-        return self.s["stuck_map"].view(self.H, self.W)
+        return self.s["stuck_map"].view(self.win_rows, self.W)
 
     def step(self, n=1, check=True):
         """Advance n ticks (CityModel.step, city_model.py:1831)."""
@@ -150,7 +161,7 @@ class GpuTraffic:
     def state_host(self):
         """Same dict as oracle.OracleTicks.state() / the reference fixtures."""
         s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw")}
-        alive = s["alive"][: self.nv].astype(bool)
+        alive = s["alive"][: self.nv] == 1
         cut = lambda a: a[: self.nv]
         flags = (cut(s["is_stuck"]).astype(np.uint8) & 1) | ((cut(s["malfunction"]).astype(np.uint8) & 1) << 1) | \
                 ((cut(s["direction"]) + 1).astype(np.uint8) << 2)
