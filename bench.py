@@ -225,6 +225,80 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
             "cpu_baseline": cpu}
 
 
+def sharded_vehicle_bench(dev, world, rank, size=4096, per_shard=150000, n_ticks=45, warm=5, route_len=100, halo=128):
+    """The tick over `world` row-band shards, one per rank (SURVEY.md 8e "Vehicle step"): ONE city of `size` columns x
+    `size * world` rows with `per_shard * world` vehicles live at once (weak scaling).  Every rank builds the same city,
+    light tables and tapes (seeded), simulates its own band + halo, and refreshes the halos over NCCL after every tick.
+    Rank 0 also runs the same tapes on one GPU (`GpuTraffic`) and the merged sharded state must be identical."""
+    import torch
+    import torch.distributed as dist
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    from trafficsimulation_b200.sharded_traffic import ShardedTraffic
+    W, H, seed = size, size * world, 4096
+    hb, vb = tapes.synth_bands(seed, width=W, height=H)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    city = GpuCityLayout(width=W, height=H, device=dev)
+    city.set_bands(hb, vb)
+    city.generate(tapes.synth_zone_tape(seed, cap), None, np.zeros(cap, np.int32))
+    tabs = light_tables_from_layout(city)
+    planes = city.planes_host()
+    del city
+    torch.cuda.empty_cache()
+    tp = tapes.synth_traffic(seed, W, H, planes["cell_type"], planes["dirs"], per_shard * world, n_ticks, route_len=route_len, spawn_ticks=1)
+    del planes
+    nv = len(tp["origin"])
+    sim = ShardedTraffic(W, H, tabs, tp, n_ticks, world, halo=halo, devices=[dev], distributed=True)
+    sim.step(warm)
+    u0 = sim.counters()["vehicle_updates"]
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    sim.step(n_ticks - warm, check=False)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    upd = torch.tensor([sim.counters()["vehicle_updates"] - u0], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(upd)
+    sim.check()
+    got = sim.state_host()          # collective: every rank contributes what it owns
+    same = None
+    if rank == 0:
+        one = GpuTraffic(W, H, tabs, tp, n_ticks, device=dev)
+        one.step(n_ticks)
+        want = one.state_host()
+        same = all(np.array_equal(got[k], want[k]) for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"))
+    ms = float(t.item())
+    ticks = n_ticks - warm
+    return {"metric": "agent-updates/sec (vehicle CA tick, row-band shards)", "value": float(upd.item()) / (ms * 1e-3), "unit": "agent-updates/s",
+            "n_gpus": world, "ms_per_tick": ms / ticks, "vehicle_updates": int(upd.item()), "scaling": "weak",
+            "config": {"workload": f"{W}x{H} city, {nv} vehicles spawned at tick 0, {ticks} timed ticks, one launch + one halo refresh per tick",
+                       "halo_rows": halo, "groups": int(tabs["n_groups"])},
+            "matches_single_gpu": same}
+
+
+def guarded(fn, rank, limit_s, on_timeout):
+    """Run a collective leg that must never take the headline line down with it: an exception becomes an {"error": ...}
+    entry; if the leg hangs (a rank died inside a collective) every rank leaves after `limit_s`, rank 0 printing first."""
+    def bail():
+        if rank == 0:
+            on_timeout()
+        sys.stdout.flush()
+        os._exit(0)
+    timer = threading.Timer(limit_s, bail)
+    timer.daemon = True
+    timer.start()
+    try:
+        return fn()
+    except Exception as e:   # noqa: BLE001 -- reported, not swallowed
+        return {"error": f"{type(e).__name__}: {e}"[:400]}
+    finally:
+        timer.cancel()
+
+
 def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
     """BASELINE.json configs[1] (4096 x 4096, all passes, 1 GPU) next to the headline size: device-resident cells/s."""
     import torch
@@ -441,6 +515,16 @@ def ours(args):
             line["vehicle_step_1M"] = vehicle_bench(dev, n_ticks=60, size=8192, n_vehicles=1000000, cpu_ticks=0, route_len=100, e2e_ticks=20)
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                                     "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
+    if world > 1:   # the second hot path on the same shards; a failure or hang here never costs the layout line
+        tick = None
+        if not args.no_sharded_tick:
+            def on_timeout():
+                line["vehicle_step_sharded"] = {"error": "timed out"}
+                print(json.dumps(line))
+            tick = guarded(lambda: sharded_vehicle_bench(dev, world, rank), rank, 420, on_timeout)
+        if rank == 0:
+            line["vehicle_step_sharded"] = tick
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -473,6 +557,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--no-sharded-tick", action="store_true", help="N > 1: skip the sharded vehicle-tick leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
