@@ -313,26 +313,38 @@ tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, cons
    tsim_light_tables, tsim_tick_state and the origin / target / ev_cells tapes is LOCAL to the window
    ((y - win_y0) * width + x); a tape cell outside the window is TSIM_CELL_OUTSIDE.  The vehicle arrays keep
    their global length (a vehicle is the same index on every shard).  After every tick the shards refresh the
-   halo: planes row-wise (caller), vehicles through the two calls below.                                        */
+   halo through the two calls below and one message per neighbour in between (the caller's transport: NCCL, a copy).                                        */
 #define TSIM_CELL_OUTSIDE (-2)
 #define TSIM_TICK_REC_WORDS 12      /* int32 words per vehicle record                                          */
 #define TSIM_TICK_REC_HEADER 16     /* int32 words before the first record; word 0 = number of records        */
+#define TSIM_TICK_GROUP_WORDS 7     /* g_cur, g_pend, g_qt, g_gap, g_last, g_ft_phase, g_ft_timer             */
+
+/* One MESSAGE per neighbour and tick (int32 words): header | cap vehicle records | state of the n_groups light groups
+   both shards simulate | `rows` rows of the occupancy, stop and stuck planes.  Sender and receiver agree on cap,
+   n_groups and rows; this is its length.                                                                        */
+long long tsim_tick_message_words(int32_t width, int32_t cap, int32_t n_groups, int32_t rows);
 
 typedef struct tsim_tick_strips {    /* [0] = neighbour below (lower rows), [1] = neighbour above; LOCAL row ranges */
-    int32_t send_lo[2], send_hi[2];      /* own rows whose vehicles the neighbour needs (empty: no neighbour)      */
+    int32_t send_lo[2], send_hi[2];      /* own rows the neighbour holds as halo (empty: no neighbour)             */
     int32_t halo_lo[2], halo_hi[2];      /* halo rows owned by that neighbour                                      */
-    int32_t verify_lo[2], verify_hi[2];  /* halo rows where this shard's ghost must equal the owner's record      */
-    int32_t *records[2];                 /* [HEADER + cap * REC_WORDS] device buffers (NULL: no neighbour)         */
-    int32_t cap;
+    int32_t verify_lo[2], verify_hi[2];  /* halo rows where this shard's ghosts must equal what the owner sends   */
+    int32_t *send_msg[2], *recv_msg[2];  /* device message buffers (NULL: no neighbour)                            */
+    int32_t cap;                         /* vehicle records per message                                            */
+    const int32_t *g_send[2];            /* local indices of the groups this shard owns and neighbour d simulates */
+    int32_t n_g_send[2];
+    const int32_t *g_recv[2];            /* local indices of the groups neighbour d owns and this shard simulates */
+    const uint8_t *g_verify[2];          /* per received group: 1 = this shard's copy must already be identical   */
+    int32_t n_g_recv[2];
 } tsim_tick_strips;
 
-/* fills records[d] with the vehicles on send rows d; marks the vehicles on halo rows as awaiting their owner */
+/* builds send_msg[d]: vehicles on send rows d, the state of g_send[d], the send rows of the three map planes;
+   marks the vehicles on halo rows as awaiting their owner                                                      */
 tsim_status tsim_tick_pack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st,
                            const tsim_tick_strips *strips, void *stream);
 
-/* records[d] = the buffers RECEIVED from the neighbours: installs the owners' vehicles on the halo rows, drops
-   the ghosts nobody sent; a ghost on the verify rows that differs from its owner sets scalars[9] (40..43):
-   the halo is too small for the dependency chains of this traffic                                             */
+/* installs recv_msg[d] (the neighbour's send_msg): halo rows, group state, the owners' vehicles; drops the ghosts
+   nobody sent.  Inside the verify rows everything this shard simulated must equal what arrives, else scalars[9]
+   is set (40..45): the halo is too small for the dependency chains of this traffic                             */
 tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st,
                              const tsim_tick_strips *strips, void *stream);
 

@@ -71,3 +71,20 @@ def test_sharded_ticks_reject_a_halo_smaller_than_a_light_group():
     tabs = light_tables_from_layout(city)
     with pytest.raises(ValueError, match="halo"):
         ShardedTraffic(r["W"], r["H"], tabs, r, r["n_ticks"], 2, halo=16)
+
+
+def test_sharded_ticks_flag_a_ghost_that_differs_from_its_owner():
+    """The halo refresh is a check, not only a copy: a ghost row that is not what the owner sends raises."""
+    from trafficsimulation_b200 import _lib
+    from trafficsimulation_b200.traffic import light_tables_from_layout
+    from trafficsimulation_b200.sharded_traffic import ShardedTraffic
+    r = load_ticks(tick_fixtures()[0])
+    city = build_city(r["meta"]["cfg"], r["hbands"], r["vbands"], r["tape_zone"], r["tape_carve"], r["tape_entrance"])
+    tabs = light_tables_from_layout(city)
+    sim = ShardedTraffic(r["W"], r["H"], tabs, r, r["n_ticks"], 2, halo=100)
+    sim.step(5)
+    s0 = sim.sims[0]
+    row = sim.plan.own_hi[0] + 3 - s0.win_y0          # a halo row of shard 0 inside its verify band
+    s0.occupancy_map[row, 0] = 1                       # a wall cell: nothing will ever clear it
+    with pytest.raises(_lib.TsimError, match="halo too small"):
+        sim.step(1)

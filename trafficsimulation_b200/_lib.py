@@ -19,7 +19,7 @@ SYMBOLS = [
     "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_shard_counts", "tsim_layout_carve", "tsim_layout_zones",
     "tsim_layout_dead_ends", "tsim_layout_upgrade_r2", "tsim_layout_entrances", "tsim_layout_fix_dirs",
     "tsim_layout_lights", "tsim_lights_prepare", "tsim_lights_seed", "tsim_lights_reach", "tsim_lights_reach_planes",
-    "tsim_lights_finish", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_tick_pack", "tsim_tick_unpack", "tsim_label_mask",
+    "tsim_lights_finish", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_tick_message_words", "tsim_tick_pack", "tsim_tick_unpack", "tsim_label_mask",
 ]
 
 
@@ -80,7 +80,9 @@ class TickState(C.Structure):
 
 class TickStrips(C.Structure):
     _fields_ = [(n, C.c_int32 * 2) for n in ("send_lo", "send_hi", "halo_lo", "halo_hi", "verify_lo", "verify_hi")] + \
-               [("records", C.c_void_p * 2), ("cap", C.c_int32)]
+               [("send_msg", C.c_void_p * 2), ("recv_msg", C.c_void_p * 2), ("cap", C.c_int32),
+                ("g_send", C.c_void_p * 2), ("n_g_send", C.c_int32 * 2),
+                ("g_recv", C.c_void_p * 2), ("g_verify", C.c_void_p * 2), ("n_g_recv", C.c_int32 * 2)]
 
 
 TICK_REC_WORDS, TICK_REC_HEADER, CELL_OUTSIDE = 12, 16, -2
@@ -100,6 +102,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.tsim_last_error.restype = C.c_char_p
     lib.tsim_launch_count.restype = C.c_longlong
+    lib.tsim_tick_message_words.restype = C.c_longlong
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError if the library does not export a declared symbol
     _lib = lib

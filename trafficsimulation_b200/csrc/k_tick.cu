@@ -351,11 +351,20 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
     }
 }
 
-// ---- shards (SURVEY.md 8e "Vehicle step"): vehicle records travel between neighbour shards once per tick -------------------
-// record = TSIM_TICK_REC_WORDS int32: 0 vehicle, 1 global row, 2 column, 3 path_len, 4 steps, 5 stranded, 6..7 path_off,
+// ---- shards (SURVEY.md 8e "Vehicle step"): after every tick a shard sends ONE message to each neighbour ------------------
+// message (int32 words): [0, HDR) header, word 0 = number of vehicle records | records, REC words each | state of the
+// light groups both shards simulate, GST words each | the three map planes' rows (occupancy, stop, stuck), bytes.
+// record: 0 vehicle, 1 global row, 2 column, 3 path_len, 4 steps, 5 stranded, 6..7 path_off,
 // 8 stuck_ticks | base_speed << 16 | cur_speed << 24, 9 is_stuck | prev_valid << 8 | malfunction << 16 | direction << 24
-constexpr int REC = TSIM_TICK_REC_WORDS, REC_HDR = TSIM_TICK_REC_HEADER;
+constexpr int REC = TSIM_TICK_REC_WORDS, REC_HDR = TSIM_TICK_REC_HEADER, GST = TSIM_TICK_GROUP_WORDS;
 enum { ALIVE = 1, ZOMBIE = 2 };   // ZOMBIE: a ghost of the halo awaiting its owner's record
+
+__host__ __device__ inline long long msg_groups_at(int cap) { return REC_HDR + (long long)cap * REC; }
+__host__ __device__ inline long long msg_planes_at(int cap, int n_groups) { return msg_groups_at(cap) + (((long long)n_groups * GST + 3) & ~3LL); }
+__host__ __device__ inline long long msg_plane_bytes(int rows, int W) { return ((long long)rows * W + 15) & ~15LL; }
+__host__ __device__ inline long long msg_words(int cap, int n_groups, int rows, int W) {
+    return msg_planes_at(cap, n_groups) + 3 * msg_plane_bytes(rows, W) / 4;
+}
 
 struct StripArgs {
     int W, y0, nv, cap;
@@ -374,33 +383,90 @@ __device__ __forceinline__ void make_record(const tsim_tick_state &s, int v, int
     r[10] = 0; r[11] = 0;
 }
 
-// vehicles on the own rows next to a cut are packed for that neighbour; vehicles on halo rows become zombies
+__device__ __forceinline__ int32_t *group_field(const tsim_tick_state &s, int f) {
+    return f == 0 ? s.g_cur : f == 1 ? s.g_pend : f == 2 ? s.g_qt : f == 3 ? s.g_gap : f == 4 ? s.g_last : f == 5 ? s.g_ft_phase : s.g_ft_timer;
+}
+
+__device__ __forceinline__ bool differ(uint4 a, uint4 b) { return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0; }
+__device__ __forceinline__ bool differ(uint32_t a, uint32_t b) { return a != b; }
+__device__ __forceinline__ bool differ(uint8_t a, uint8_t b) { return a != b; }
+
+// rows [lo, hi) of the three map planes <-> the plane part of a message, V bytes at a time.  INSTALL: message -> planes,
+// and inside the verify rows the ghost rows this shard simulated must already hold what the owner sends.
+template <class V, bool INSTALL>
+__device__ void plane_rows(const StripArgs &a, int d, int32_t *msg, int n_groups, int lo, int hi, int tid, int nth) {
+    const tsim_tick_state &s = a.st;
+    const long long nbytes = (long long)(hi - lo) * a.W, first = (long long)lo * a.W;
+    const long long v0 = (long long)a.sp.verify_lo[d] * a.W, v1 = (long long)a.sp.verify_hi[d] * a.W;
+    uint8_t *body = (uint8_t *)(msg + msg_planes_at(a.cap, n_groups));
+    uint8_t *planes[3] = {s.occupancy, s.stop_map, s.stuck_map};
+    const long long nvec = nbytes / (long long)sizeof(V);
+    bool bad = false;
+    for (int p = 0; p < 3; p++) {
+        V *m = (V *)(body + p * msg_plane_bytes(hi - lo, a.W));
+        V *g = (V *)(planes[p] + first);
+        for (long long i = tid; i < nvec; i += nth) {
+            if (INSTALL) {
+                const V got = m[i];
+                const long long at = first + i * (long long)sizeof(V);
+                if (at >= v0 && at < v1) {
+                    const V mine = g[i];
+                    bad |= differ(mine, got);
+                }
+                g[i] = got;
+            } else {
+                m[i] = g[i];
+            }
+        }
+    }
+    if (bad) s.scalars[S_XERR] = 44;   // a halo row differs from its owner's: the halo is too small for this traffic
+}
+
+template <bool INSTALL>
+__device__ void plane_rows_any(const StripArgs &a, int d, int32_t *msg, int n_groups, int lo, int hi, int tid, int nth) {
+    if (a.W % 16 == 0) plane_rows<uint4, INSTALL>(a, d, msg, n_groups, lo, hi, tid, nth);
+    else if (a.W % 4 == 0) plane_rows<uint32_t, INSTALL>(a, d, msg, n_groups, lo, hi, tid, nth);
+    else plane_rows<uint8_t, INSTALL>(a, d, msg, n_groups, lo, hi, tid, nth);
+}
+
+// vehicles on the own rows next to a cut, the shared groups' state and the own rows themselves go into the message for
+// that neighbour; vehicles on halo rows become zombies
 __global__ void __launch_bounds__(256) tick_pack_kernel(StripArgs a) {
     const tsim_tick_state &s = a.st;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.nv; v += gridDim.x * blockDim.x) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int v = tid; v < a.nv; v += nth) {
         if (s.alive[v] != ALIVE) continue;
         const int row = s.pos[v] / a.W;
 #pragma unroll
         for (int d = 0; d < 2; d++) {
             if (row >= a.sp.halo_lo[d] && row < a.sp.halo_hi[d]) s.alive[v] = ZOMBIE;
-            if (a.sp.records[d] && row >= a.sp.send_lo[d] && row < a.sp.send_hi[d]) {
-                const int k = atomicAdd(a.sp.records[d], 1);
-                if (k < a.cap) make_record(s, v, a.W, a.y0, a.sp.records[d] + REC_HDR + (size_t)k * REC);
+            if (a.sp.send_msg[d] && row >= a.sp.send_lo[d] && row < a.sp.send_hi[d]) {
+                const int k = atomicAdd(a.sp.send_msg[d], 1);
+                if (k < a.cap) make_record(s, v, a.W, a.y0, a.sp.send_msg[d] + REC_HDR + (size_t)k * REC);
                 else s.scalars[S_XERR] = 43;   // strip holds more vehicles than the record buffer
             }
         }
     }
+    for (int d = 0; d < 2; d++) {
+        int32_t *msg = a.sp.send_msg[d];
+        if (!msg) continue;
+        int32_t *gw = msg + msg_groups_at(a.cap);
+        for (int i = tid; i < a.sp.n_g_send[d] * GST; i += nth) gw[i] = group_field(s, i % GST)[a.sp.g_send[d][i / GST]];
+        plane_rows_any<false>(a, d, msg, a.sp.n_g_send[d], a.sp.send_lo[d], a.sp.send_hi[d], tid, nth);
+    }
 }
 
-// the owner's records replace the ghosts of the halo; inside the verify rows the ghost this shard simulated must be identical
+// the owner's message replaces the halo: rows, group state, vehicles; inside the verify rows what this shard simulated
+// must be identical to what arrives
 __global__ void __launch_bounds__(256) tick_unpack_kernel(StripArgs a) {
     const tsim_tick_state &s = a.st;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
 #pragma unroll
     for (int d = 0; d < 2; d++) {
-        const int32_t *buf = a.sp.records[d];
+        int32_t *buf = a.sp.recv_msg[d];
         if (!buf) continue;
         const int n = min(buf[0], a.cap);
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        for (int k = tid; k < n; k += nth) {
             const int32_t *r = buf + REC_HDR + (size_t)k * REC;
             const int v = r[0], row = r[1] - a.y0;
             if (v < 0 || v >= a.nv || row < a.sp.halo_lo[d] || row >= a.sp.halo_hi[d]) { s.scalars[S_XERR] = 40; continue; }
@@ -421,6 +487,13 @@ __global__ void __launch_bounds__(256) tick_unpack_kernel(StripArgs a) {
             s.is_stuck[v] = (int8_t)w9; s.prev_valid[v] = (int8_t)(w9 >> 8); s.malfunction[v] = (int8_t)(w9 >> 16); s.direction[v] = (int8_t)(w9 >> 24);
             s.early[v] = 0; s.moved[v] = 0; s.max_steps[v] = 0;
         }
+        const int32_t *gw = buf + msg_groups_at(a.cap);
+        for (int i = tid; i < a.sp.n_g_recv[d] * GST; i += nth) {
+            int32_t *mine = group_field(s, i % GST) + a.sp.g_recv[d][i / GST];
+            if (a.sp.g_verify[d][i / GST] && *mine != gw[i]) s.scalars[S_XERR] = 45;   // a ghost light group diverged from its owner
+            *mine = gw[i];
+        }
+        plane_rows_any<true>(a, d, buf, a.sp.n_g_recv[d], a.sp.halo_lo[d], a.sp.halo_hi[d], tid, nth);
     }
 }
 
@@ -454,18 +527,32 @@ static void own_cells(const tsim_cfg *cfg, const tsim_tick_state *st, int &lo, i
 static tsim_status strip_args(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, const tsim_tick_strips *sp, StripArgs &a) {
     tsim_status r = check_cfg(cfg);
     if (r != TSIM_OK) return r;
-    if (!tp || !st || !sp || sp->cap < 1 || !st->pos || !st->alive || !st->scalars) { set_error("tick strips: bad arguments"); return TSIM_ERR_CONFIG; }
-    for (int d = 0; d < 2; d++)
+    if (!tp || !st || !sp || sp->cap < 1 || !st->pos || !st->alive || !st->scalars || !st->occupancy || !st->stop_map || !st->stuck_map) {
+        set_error("tick strips: bad arguments");
+        return TSIM_ERR_CONFIG;
+    }
+    for (int d = 0; d < 2; d++) {
         if (sp->send_lo[d] < 0 || sp->send_hi[d] > cfg->win_rows || sp->halo_lo[d] < 0 || sp->halo_hi[d] > cfg->win_rows ||
-            sp->verify_lo[d] < sp->halo_lo[d] || sp->verify_hi[d] > sp->halo_hi[d]) {
+            sp->send_hi[d] < sp->send_lo[d] || sp->halo_hi[d] < sp->halo_lo[d] ||
+            (sp->verify_hi[d] > sp->verify_lo[d] && (sp->verify_lo[d] < sp->halo_lo[d] || sp->verify_hi[d] > sp->halo_hi[d]))) {
             set_error("tick strips: row ranges outside the window");
             return TSIM_ERR_CONFIG;
         }
+        if (sp->n_g_send[d] < 0 || sp->n_g_recv[d] < 0 || (sp->n_g_send[d] > 0 && !sp->g_send[d]) ||
+            (sp->n_g_recv[d] > 0 && (!sp->g_recv[d] || !sp->g_verify[d]))) {
+            set_error("tick strips: bad light-group lists");
+            return TSIM_ERR_CONFIG;
+        }
+    }
     a = StripArgs{cfg->width, cfg->win_y0, tp->n_vehicles, sp->cap, *sp, *st};
     return TSIM_OK;
 }
 
-static int strip_grid(int n) { const int g = div_up(n, 256); return g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g); }
+static int strip_grid(long long n) { const long long g = (n + 255) / 256; return g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : (int)g); }
+
+extern "C" long long tsim_tick_message_words(int32_t width, int32_t cap, int32_t n_groups, int32_t rows) {
+    return msg_words(cap, n_groups, rows, width);
+}
 
 extern "C" tsim_status tsim_tick_pack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, const tsim_tick_strips *sp,
                                       void *stream) {
@@ -473,10 +560,14 @@ extern "C" tsim_status tsim_tick_pack(const tsim_cfg *cfg, const tsim_tick_tapes
     tsim_status r = strip_args(cfg, tp, st, sp, a);
     if (r != TSIM_OK) return r;
     cudaStream_t cs = (cudaStream_t)stream;
+    long long work = a.nv;
     for (int d = 0; d < 2; d++)
-        if (sp->records[d]) TSIM_CUDA(cudaMemsetAsync(sp->records[d], 0, REC_HDR * sizeof(int32_t), cs));
-    if (a.nv == 0) return TSIM_OK;
-    tick_pack_kernel<<<strip_grid(a.nv), 256, 0, cs>>>(a);
+        if (sp->send_msg[d]) {
+            TSIM_CUDA(cudaMemsetAsync(sp->send_msg[d], 0, REC_HDR * sizeof(int32_t), cs));
+            const long long cells = (long long)(sp->send_hi[d] - sp->send_lo[d]) * a.W / 16;
+            if (cells > work) work = cells;
+        }
+    tick_pack_kernel<<<strip_grid(work), 256, 0, cs>>>(a);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
@@ -486,14 +577,20 @@ extern "C" tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tap
     StripArgs a;
     tsim_status r = strip_args(cfg, tp, st, sp, a);
     if (r != TSIM_OK) return r;
-    if (a.nv == 0) return TSIM_OK;
     cudaStream_t cs = (cudaStream_t)stream;
-    if (sp->records[0] || sp->records[1]) {
-        tick_unpack_kernel<<<strip_grid(a.cap), 256, 0, cs>>>(a);
+    if (sp->recv_msg[0] || sp->recv_msg[1]) {
+        long long work = a.cap;
+        for (int d = 0; d < 2; d++) {
+            const long long cells = (long long)(sp->halo_hi[d] - sp->halo_lo[d]) * a.W / 16;
+            if (sp->recv_msg[d] && cells > work) work = cells;
+        }
+        tick_unpack_kernel<<<strip_grid(work), 256, 0, cs>>>(a);
         TSIM_LAUNCH_CHECK();
     }
-    tick_reap_kernel<<<strip_grid(a.nv), 256, 0, cs>>>(a);
-    TSIM_LAUNCH_CHECK();
+    if (a.nv > 0) {
+        tick_reap_kernel<<<strip_grid(a.nv), 256, 0, cs>>>(a);
+        TSIM_LAUNCH_CHECK();
+    }
     return TSIM_OK;
 }
 

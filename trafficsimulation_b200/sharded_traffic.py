@@ -9,8 +9,10 @@ depends on state a few rows away -- except through chains of vehicles that block
 but not bounded a priori.  After EVERY tick the owners refresh the neighbours' halos:
 
 * the three map planes (occupancy, stop, stuck) row-wise,
-* the vehicles on the ``halo`` own rows next to a cut as fixed-size records (``tsim_tick_pack`` / ``tsim_tick_unpack``),
-* the state of the light groups both shards simulate.
+* the vehicles on the ``halo`` own rows next to a cut as fixed-size records,
+* the state of the light groups both shards simulate,
+
+all in ONE message per neighbour, built by one kernel (``tsim_tick_pack``) and installed by another (``tsim_tick_unpack``).
 
 Exactness is checked, not assumed: on the half of a halo next to the cut the receiving shard compares its own
 ghost simulation with what the owner sent (rows, vehicle records, group state).  An error that starts at the
@@ -127,8 +129,7 @@ class ShardedTraffic:
         if n_shards > 1:   # a strip of `halo` rows cannot hold more vehicles than road cells; 1/2 of its cells is generous
             cap = int(min(nv, self.halo * W // 2)) + 16
         self.cap = cap
-        self.sims, self.strips, self.send, self.recv, self.vflag = {}, {}, {}, {}, {}
-        self.g_send, self.g_recv, self.g_verify = {}, {}, {}
+        self.sims, self.strips, self.send, self.recv = {}, {}, {}, {}
         if devices is None:
             devices = ["cuda:0"] * n_shards
         shared = {}
@@ -152,16 +153,12 @@ class ShardedTraffic:
             sim = GpuTraffic(W, self.H, lt, tl, n_ticks, algo=algo, rain_enabled=rain_enabled, device=dev,
                              window=(y0, rows, self.halo), own_rows=(plan.own_lo[s] - y0, plan.own_hi[s] - y0))
             self.sims[s] = sim
-            self.vflag[s] = torch.zeros(1, dtype=torch.int32, device=dev)
             if n_shards == 1:
                 continue
-            words = _lib.TICK_REC_HEADER + cap * _lib.TICK_REC_WORDS
-            self.send[s] = [torch.zeros(words, dtype=torch.int32, device=dev) if ok else None for ok in (s > 0, s + 1 < n_shards)]
-            self.recv[s] = [None, None]
             st = _lib.TickStrips()
             h2 = self.halo // 2
             own0, own1 = plan.own_lo[s] - y0, plan.own_hi[s] - y0
-            # [0] neighbour below: send my lowest `halo` own rows, my lower halo is refreshed, its upper half is verified
+            # [0] neighbour below: my lowest `halo` own rows travel, my lower halo is refreshed, its upper half is verified
             st.send_lo[0], st.send_hi[0] = (own0, own0 + self.halo) if s > 0 else (0, 0)
             st.halo_lo[0], st.halo_hi[0] = (0, own0) if s > 0 else (0, 0)
             st.verify_lo[0], st.verify_hi[0] = (own0 - h2, own0) if s > 0 else (0, 0)
@@ -169,20 +166,28 @@ class ShardedTraffic:
             st.halo_lo[1], st.halo_hi[1] = (own1, rows) if s + 1 < n_shards else (0, 0)
             st.verify_lo[1], st.verify_hi[1] = (own1, own1 + h2) if s + 1 < n_shards else (0, 0)
             st.cap = cap
-            self.strips[s] = st
             # light groups both neighbours simulate: the owner sends, the other installs (and verifies away from its window edge)
-            self.g_send[s], self.g_recv[s], self.g_verify[s] = [None, None], [None, None], [None, None]
             v_lo = plan.win_lo[s] + (h2 if plan.win_lo[s] > 0 else 0)
             v_hi = plan.win_hi[s] - (h2 if plan.win_hi[s] < self.H else 0)
+            self.send[s], self.recv[s], keep = [None, None], [None, None], []
             for d, r in ((0, s - 1), (1, s + 1)):
                 if r < 0 or r >= n_shards:
                     continue
                 both = self.g_sel[s] & self.g_sel[r]
                 mine = np.flatnonzero(both & (self.g_owner == s))
                 theirs = np.flatnonzero(both & (self.g_owner == r))
-                self.g_send[s][d] = torch.from_numpy(self.g_local[s][mine]).to(dev)
-                self.g_recv[s][d] = torch.from_numpy(self.g_local[s][theirs]).to(dev)
-                self.g_verify[s][d] = torch.from_numpy((g_lo[theirs] >= v_lo) & (g_hi[theirs] < v_hi)).to(dev)
+                g_send = torch.from_numpy(self.g_local[s][mine].astype(np.int32)).to(dev)
+                g_recv = torch.from_numpy(self.g_local[s][theirs].astype(np.int32)).to(dev)
+                g_ver = torch.from_numpy(((g_lo[theirs] >= v_lo) & (g_hi[theirs] < v_hi)).astype(np.uint8)).to(dev)
+                keep += [g_send, g_recv, g_ver]
+                st.g_send[d], st.n_g_send[d] = g_send.data_ptr(), len(mine)
+                st.g_recv[d], st.g_verify[d], st.n_g_recv[d] = g_recv.data_ptr(), g_ver.data_ptr(), len(theirs)
+                words = lambda ng_, rows_: int(sim.lib.tsim_tick_message_words(W, cap, ng_, rows_))
+                self.send[s][d] = torch.zeros(words(len(mine), st.send_hi[d] - st.send_lo[d]), dtype=torch.int32, device=dev)
+                self.recv[s][d] = torch.zeros(words(len(theirs), st.halo_hi[d] - st.halo_lo[d]), dtype=torch.int32, device=dev)
+                st.send_msg[d], st.recv_msg[d] = self.send[s][d].data_ptr(), self.recv[s][d].data_ptr()
+            self._keep = getattr(self, "_keep", []) + keep
+            self.strips[s] = st
 
     # ---- exchange plumbing (Comm.exchange talks in global row ranges; the ranges identify the direction)
     def _role(self, s, lo, hi):
@@ -197,76 +202,29 @@ class ShardedTraffic:
             return "recv", 0
         raise AssertionError((s, lo, hi))
 
-    def _verify_rows(self, s, d):
-        """global rows of shard s's halo towards neighbour d where its ghosts must equal the owner's data"""
-        p, h2 = self.plan, self.halo // 2
-        return (p.own_lo[s] - h2, p.own_lo[s]) if d == 0 else (p.own_hi[s], p.own_hi[s] + h2)
+    def _message(self, s, lo, hi):
+        """Comm.exchange item: shard s's message buffer for the neighbour the row range belongs to (sent / received in place)."""
+        role, d = self._role(s, lo, hi)
+        return (self.send if role == "send" else self.recv)[s][d]
 
-    def _items(self):
-        items = []
-        for name in ("occupancy", "stop_map", "stuck_map"):
-            def get(s, lo, hi, name=name):
-                sim = self.sims[s]
-                return sim.s[name].view(sim.win_rows, self.W)[lo - sim.win_y0:hi - sim.win_y0]
-
-            def put(s, lo, hi, src, name=name, get=get):
-                _, d = self._role(s, lo, hi)
-                a, b = self._verify_rows(s, d)
-                mine = get(s, lo, hi)
-                self.vflag[s] += (mine[a - lo:b - lo] != src[a - lo:b - lo]).any().to(torch.int32)
-                mine.copy_(src)
-            items.append((get, put))
-
-        def get_rec(s, lo, hi):
-            role, d = self._role(s, lo, hi)
-            return self.send[s][d]   # as a receive template only the shape matters
-
-        def put_rec(s, lo, hi, src):
-            self.recv[s][self._role(s, lo, hi)[1]] = src
-        items.append((get_rec, put_rec))
-
-        def get_grp(s, lo, hi):
-            role, d = self._role(s, lo, hi)
-            sim = self.sims[s]
-            idx = self.g_send[s][d] if role == "send" else self.g_recv[s][d]
-            out = torch.zeros(_N_GSTATE, len(idx) + 1, dtype=torch.int32, device=sim.device)   # + 1: never an empty message
-            if role == "send" and len(idx):
-                out[:, :-1] = sim.gstate[:_N_GSTATE, idx]
-            return out
-
-        def put_grp(s, lo, hi, src):
-            _, d = self._role(s, lo, hi)
-            sim, idx = self.sims[s], self.g_recv[s][d]
-            if len(idx) == 0:
-                return
-            got = src[:, :-1]
-            mine = sim.gstate[:_N_GSTATE, idx]
-            self.vflag[s] += ((mine != got) & self.g_verify[s][d]).any().to(torch.int32)
-            sim.gstate[:_N_GSTATE, idx] = got
-        items.append((get_grp, put_grp))
-        return items
-
-    def _strip_call(self, fn, s, bufs):
-        sim, st = self.sims[s], self.strips[s]
-        for d in (0, 1):
-            st.records[d] = bufs[d].data_ptr() if bufs[d] is not None else None
-        _lib.check(fn(C.byref(sim.cfg), C.byref(sim.tp), C.byref(sim.st), C.byref(st), sim._stream))
+    def _strip_call(self, fn, s):
+        sim = self.sims[s]
+        _lib.check(fn(C.byref(sim.cfg), C.byref(sim.tp), C.byref(sim.st), C.byref(self.strips[s]), sim._stream))
 
     def step(self, n=1, check=True):
         """Advance n ticks: one persistent launch per tick and shard, then the halo refresh."""
-        items = self._items() if self.n > 1 else None
         for _ in range(n):
             for s, sim in self.sims.items():
                 with torch.cuda.device(sim.device):
                     sim.step(1, check=False)
                     if self.n > 1:
-                        self._strip_call(sim.lib.tsim_tick_pack, s, self.send[s])
+                        self._strip_call(sim.lib.tsim_tick_pack, s)
             if self.n == 1:
                 continue
-            self.comm.exchange(self.plan, items)
+            self.comm.exchange(self.plan, self._message)
             for s, sim in self.sims.items():
                 with torch.cuda.device(sim.device):
-                    self._strip_call(sim.lib.tsim_tick_unpack, s, self.recv[s])
+                    self._strip_call(sim.lib.tsim_tick_unpack, s)
         if check:
             self.check()
 
@@ -275,12 +233,12 @@ class ShardedTraffic:
         codes = {}
         for s, sim in self.sims.items():
             sc = sim.s["scalars"][:10].cpu().numpy()
-            codes[s] = torch.tensor([max(int(sc[1]), int(sc[9]), 44 if int(self.vflag[s].item()) else 0)], dtype=torch.int32, device=sim.device)
+            codes[s] = torch.tensor([max(int(sc[1]), int(sc[9]))], dtype=torch.int32, device=sim.device)
         if self.comm.any(codes):
             mine = {s: int(c.item()) for s, c in codes.items()}
-            halo = any(40 <= c <= 44 for c in mine.values()) or not any(mine.values())
+            halo = any(40 <= c <= 45 for c in mine.values()) or not any(mine.values())
             raise _lib.TsimError(6 if halo else 4, f"sharded tick: error flags per local shard {mine}"
-                                 + (" (40..44: a ghost diverged from its owner -- halo too small for this traffic)" if halo else ""))
+                                 + (" (40..45: a ghost diverged from its owner -- halo too small for this traffic)" if halo else ""))
 
     def counters(self):
         """Totals over the LOCAL shards (sum over ranks for the global figure)."""
