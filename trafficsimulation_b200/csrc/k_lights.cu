@@ -260,12 +260,22 @@ __device__ bool line_closure(u64 *__restrict__ fpl, u64 *__restrict__ bpl, const
     return any;
 }
 
+// What a carry INTO a word adds, without running the fill again: the carry enters at the lowest (highest) cell and runs
+// through the consecutive arrows from there.  (Checked against fill_up / fill_down on the host.)
+__device__ __forceinline__ u64 low_run_incl(u64 a) { return a ^ (a + 1ull); }                 // cells 0 .. first cell without an arrow, inclusive
+__device__ __forceinline__ u64 low_run(u64 a) { return a & ~(a + 1ull); }                     // the arrows below the first missing one
+__device__ __forceinline__ u64 high_run_incl(u64 a) { const u64 m = ~a; return m ? (~0ull << (63 - __clzll((long long)m))) : ~0ull; }
+__device__ __forceinline__ u64 high_run(u64 a) { const u64 m = ~a; return m ? ~(~0ull >> __clzll((long long)m)) : ~0ull; }
+
 // The same closure with the whole line in REGISTERS (lines of up to 32 * NCH words): the words of the four planes are
 // fetched with independent loads (one memory latency per line instead of one per chunk and pass), the passes run on
-// registers, and only the words that changed are written back.
+// registers, and only the words that changed are written back.  A pass only runs when its FRONTIER is not empty (some
+// set cell has an arrow of that direction into an unset cell -- a few bit operations and ballots per chunk instead of a
+// whole pass), so a line that is already closed costs two tests and no pass, and no pass is spent on noticing the end.
 template <int NCH>
 __device__ bool line_closure_reg(u64 *__restrict__ fpl, u64 *__restrict__ bpl, const u64 *__restrict__ up, const u64 *__restrict__ dn, size_t base, int wp,
                                  int nbits, int lane, uint8_t *__restrict__ dirty, int dstride) {
+    constexpr uint32_t FULL = 0xffffffffu;
     u64 f[NCH], b[NCH], aU[NCH], aD[NCH];
     bool live = false;
 #pragma unroll
@@ -276,52 +286,96 @@ __device__ bool line_closure_reg(u64 *__restrict__ fpl, u64 *__restrict__ bpl, c
         aU[c] = in ? up[base + w] : 0ull; aD[c] = in ? dn[base + w] : 0ull;
         live |= (f[c] | b[c]) != 0ull;
     }
-    if (!__any_sync(0xffffffffu, live)) return false;   // nothing on this line yet: nothing can spread
+    // all four planes' loads are in flight before the first use: one memory round trip per line, not two (the profile showed
+    // the arrow loads sunk below the early exit and a second full latency exposed on every live line)
+#pragma unroll
+    for (int c = 0; c < NCH; c++) asm volatile("" ::"l"(aU[c]), "l"(aD[c]));
+    if (!__any_sync(FULL, live)) return false;   // nothing on this line yet: nothing can spread
     const u64 tail = (nbits & 63) ? ((1ull << (nbits & 63)) - 1ull) : ~0ull;
-    uint32_t chm = 0;   // bit c: my word of chunk c changed
-    bool any = false;
-    for (int pass = 0; pass < 256; pass++) {
-        bool ch = false;
-        uint32_t cf = 0, cb = 0;
-        if ((pass & 1) == 0) {
+    uint32_t allU[NCH], allD[NCH];   // lanes whose word has the arrow on every cell: a carry runs straight through
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const int w = c * 32 + lane;
-                u64 f1 = fill_up(f[c], aU[c] << 1), b1 = fill_up(b[c], aD[c]);
-                const uint32_t gf = __ballot_sync(0xffffffffu, (f1 & aU[c]) >> 63), pf = __ballot_sync(0xffffffffu, aU[c] == ~0ull);
-                const uint32_t gb = __ballot_sync(0xffffffffu, b1 >> 63), pb = __ballot_sync(0xffffffffu, aD[c] == ~0ull);
-                uint32_t nf, nb;
-                const uint32_t inf = carry_chain(gf, pf, cf, nf), inb = carry_chain(gb, pb, cb, nb);
-                cf = nf; cb = nb;
-                if ((inf >> lane) & 1u) f1 = fill_up(f1 | 1ull, aU[c] << 1);
-                if ((inb >> lane) & 1u) b1 = fill_up(b1 | (aD[c] & 1ull), aD[c]);
-                if (w == wp - 1) { f1 &= tail; b1 &= tail; }
-                if (w < wp && (f1 != f[c] || b1 != b[c])) { f[c] = f1; b[c] = b1; chm |= 1u << c; ch = true; }
-            }
-        } else {
+    for (int c = 0; c < NCH; c++) { allU[c] = __ballot_sync(FULL, aU[c] == ~0ull); allD[c] = __ballot_sync(FULL, aD[c] == ~0ull); }
+
+    auto frontier_up = [&]() {     // f moves with aU, b against aD, towards the higher cells
+        uint32_t hit = 0, cf = 0, cb = 0;
 #pragma unroll
-            for (int c = NCH - 1; c >= 0; c--) {
-                const int w = c * 32 + lane;
-                u64 f1 = fill_down(f[c], aD[c] >> 1), b1 = fill_down(b[c], aU[c]);
-                const uint32_t gf = __brev(__ballot_sync(0xffffffffu, f1 & aD[c] & 1ull)), pf = __brev(__ballot_sync(0xffffffffu, aD[c] == ~0ull));
-                const uint32_t gb = __brev(__ballot_sync(0xffffffffu, b1 & 1ull)), pb = __brev(__ballot_sync(0xffffffffu, aU[c] == ~0ull));
-                uint32_t nf, nb;
-                const uint32_t inf = __brev(carry_chain(gf, pf, cf, nf)), inb = __brev(carry_chain(gb, pb, cb, nb));
-                cf = nf; cb = nb;
-                if ((inf >> lane) & 1u) f1 = fill_down(f1 | (1ull << 63), aD[c] >> 1);
-                if ((inb >> lane) & 1u) b1 = fill_down(b1 | (aU[c] & (1ull << 63)), aU[c]);
-                if (w == wp - 1) { f1 &= tail; b1 &= tail; }
-                if (w < wp && (f1 != f[c] || b1 != b[c])) { f[c] = f1; b[c] = b1; chm |= 1u << c; ch = true; }
-            }
+        for (int c = 0; c < NCH; c++) {
+            const int w = c * 32 + lane;
+            const bool in = w < wp;
+            const u64 fa = f[c] & aU[c];
+            u64 inner = ((fa << 1) & ~f[c]) | ((b[c] << 1) & aD[c] & ~b[c]);
+            if (w == wp - 1) inner &= tail;
+            const uint32_t sf = __ballot_sync(FULL, fa >> 63), df = __ballot_sync(FULL, in && !(f[c] & 1ull));
+            const uint32_t sb = __ballot_sync(FULL, b[c] >> 63), db = __ballot_sync(FULL, in && ((aD[c] & ~b[c]) & 1ull));
+            hit |= __ballot_sync(FULL, inner != 0ull) | (((sf << 1) | cf) & df) | (((sb << 1) | cb) & db);
+            cf = sf >> 31; cb = sb >> 31;
         }
-        ch = __any_sync(0xffffffffu, ch);
-        any |= ch;
-        if (!ch && pass >= 1) break;
+        return hit != 0;
+    };
+    auto frontier_down = [&]() {   // f moves with aD, b against aU, towards the lower cells
+        uint32_t hit = 0, cf = 0, cb = 0;
+#pragma unroll
+        for (int c = NCH - 1; c >= 0; c--) {
+            const int w = c * 32 + lane;
+            const bool in = w < wp;
+            const u64 fa = f[c] & aD[c];
+            const u64 inner = ((fa >> 1) & ~f[c]) | ((b[c] >> 1) & aU[c] & ~b[c]);
+            const uint32_t sf = __ballot_sync(FULL, fa & 1ull), df = __ballot_sync(FULL, in && !(f[c] >> 63));
+            const uint32_t sb = __ballot_sync(FULL, b[c] & 1ull), db = __ballot_sync(FULL, in && ((aU[c] & ~b[c]) >> 63));
+            hit |= __ballot_sync(FULL, inner != 0ull) | (((sf >> 1) | (cf << 31)) & df) | (((sb >> 1) | (cb << 31)) & db);
+            cf = sf & 1u; cb = sb & 1u;
+        }
+        return hit != 0;
+    };
+
+    uint32_t chm = 0;   // bit c: my word of chunk c changed
+    bool up_closed = false, dn_closed = false;
+    for (int guard = 0; guard < 128 && !(up_closed && dn_closed); guard++) {
+        if (!up_closed) {
+            if (frontier_up()) {
+                uint32_t cf = 0, cb = 0;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    const int w = c * 32 + lane;
+                    u64 f1 = fill_up(f[c], aU[c] << 1), b1 = fill_up(b[c], aD[c]);
+                    const uint32_t gf = __ballot_sync(FULL, (f1 & aU[c]) >> 63), gb = __ballot_sync(FULL, b1 >> 63);
+                    uint32_t nf, nb;
+                    const uint32_t inf = carry_chain(gf, allU[c], cf, nf), inb = carry_chain(gb, allD[c], cb, nb);
+                    cf = nf; cb = nb;
+                    if ((inf >> lane) & 1u) f1 |= low_run_incl(aU[c]);
+                    if ((inb >> lane) & 1u) b1 |= low_run(aD[c]);
+                    if (w == wp - 1) { f1 &= tail; b1 &= tail; }
+                    if (w < wp && (f1 != f[c] || b1 != b[c])) { f[c] = f1; b[c] = b1; chm |= 1u << c; }
+                }
+                dn_closed = false;
+            }
+            up_closed = true;
+        }
+        if (!dn_closed) {
+            if (frontier_down()) {
+                uint32_t cf = 0, cb = 0;
+#pragma unroll
+                for (int c = NCH - 1; c >= 0; c--) {
+                    const int w = c * 32 + lane;
+                    u64 f1 = fill_down(f[c], aD[c] >> 1), b1 = fill_down(b[c], aU[c]);
+                    const uint32_t gf = __brev(__ballot_sync(FULL, f1 & aD[c] & 1ull)), gb = __brev(__ballot_sync(FULL, b1 & 1ull));
+                    uint32_t nf, nb;
+                    const uint32_t inf = __brev(carry_chain(gf, __brev(allD[c]), cf, nf)), inb = __brev(carry_chain(gb, __brev(allU[c]), cb, nb));
+                    cf = nf; cb = nb;
+                    if ((inf >> lane) & 1u) f1 |= high_run_incl(aD[c]);
+                    if ((inb >> lane) & 1u) b1 |= high_run(aU[c]);
+                    if (w == wp - 1) { f1 &= tail; b1 &= tail; }
+                    if (w < wp && (f1 != f[c] || b1 != b[c])) { f[c] = f1; b[c] = b1; chm |= 1u << c; }
+                }
+                up_closed = false;
+            }
+            dn_closed = true;
+        }
     }
 #pragma unroll
     for (int c = 0; c < NCH; c++)
         if ((chm >> c) & 1u) { const int w = c * 32 + lane; fpl[base + w] = f[c]; bpl[base + w] = b[c]; dirty[(size_t)w * dstride] = 1; }
-    return any;
+    return __any_sync(FULL, chm != 0);
 }
 
 // ---- reachability as a sequence of ordinary launches (one per phase, each with its own grid and occupancy) ----------
@@ -333,7 +387,9 @@ template <int NCH>
 __global__ void __launch_bounds__(256, 2) reach_lines_kernel(u64 *fpl, u64 *bpl, const u64 *__restrict__ up, const u64 *__restrict__ dn, int nlines, int wp,
                                                           int nbits, const uint8_t *line_dirty, bool all, uint8_t *bd, int bd_line_stride,
                                                           int bd_word_stride, int32_t *ctl) {
-    if (*((volatile int32_t *)(ctl + 1))) return;
+    // ctl[1] was written by the previous launch and is constant during this one: a cached read-only load.  (As a volatile
+    // load it was served by L2 for each of the 16 k warps and was the top stall of this kernel: 46 % of the samples.)
+    if (__ldg(ctl + 1)) return;
     const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (line >= nlines) return;
     if (!all && !line_dirty[line >> 6]) return;
@@ -352,7 +408,7 @@ __global__ void __launch_bounds__(256) reach_transpose_kernel(const u64 *srcA, c
     extern __shared__ u64 s_tile[];
     u64 (*s_in)[9] = reinterpret_cast<u64 (*)[9]>(s_tile);
     u64 (*s_out)[9] = reinterpret_cast<u64 (*)[9]>(s_tile + 512 * 9);
-    if (*((volatile const int32_t *)(ctl + 1))) return;
+    if (__ldg(ctl + 1)) return;
     if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_clear; i += blockDim.x) clear_flags[i] = 0;   // the previous phase has read them
     const int ntx = (nbx + 7) >> 3;
     const int tx = blockIdx.x % ntx, ty = blockIdx.x / ntx;   // tile of the row-major block grid (8 x 8 blocks)
