@@ -324,17 +324,23 @@ __global__ void __launch_bounds__(32 * ENT_WARPS) entrances_warp_kernel(tsim_cfg
         const int tw = x1 - x0 + 1, th = y1 - y0 + 1, n = tw * th;
         if (n > ENT_WCAP) { if (lane == 0) big_list[atomicAdd(n_big, 1)] = bk; continue; }
         // 0. stage the tile: bit0 member of the block, bit1 _touches_road type, bit2 preferred road level
-        {
-            int ly = lane / tw, lx = lane - ly * tw;
-            for (int i = lane; i < n; i += 32) {
-                const size_t g = (size_t)(y0 + ly) * W + x0 + lx;
-                const int t = T[g];
-                uint8_t code = 0;
-                if (in_set(SET_ZONE, t)) code = (B[g] == b) ? 1 : 0;
-                else code = (in_set(SET_TOUCH_ROAD, t) ? 2 : 0) | (((t == T_R1) || (t == T_R2 && level < 2)) ? 4 : 0);
-                s_code[i] = code;
-                lx += 32;
-                while (lx >= tw) { lx -= tw; ly++; }
+        for (int i0 = lane; i0 < n; i0 += 128) {   // four cells per lane with both planes' loads in flight together
+            size_t g[4];
+            int t[4], bid[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = min(i0 + 32 * u, n - 1), ly = i / tw;
+                g[u] = (size_t)(y0 + ly) * W + x0 + (i - ly * tw);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { t[u] = T[g[u]]; bid[u] = B[g[u]]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i0 + 32 * u >= n) continue;
+                uint8_t code;
+                if (in_set(SET_ZONE, t[u])) code = (bid[u] == b) ? 1 : 0;
+                else code = (in_set(SET_TOUCH_ROAD, t[u]) ? 2 : 0) | (((t[u] == T_R1) || (t[u] == T_R2 && level < 2)) ? 4 : 0);
+                s_code[i0 + 32 * u] = code;
             }
         }
         __syncwarp();

@@ -647,13 +647,19 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
     }
     for (int u = 0; u < nv; u++) {
         if (!L.has(vx[u], vy[u])) continue;
-        const int st = type_at_time(L, vx[u], vy[u], cx, cy);
+        // everything this neighbour can be asked is fetched together (independent loads: one memory round trip, not four)
+        const int vc = L.at(vx[u], vy[u]);
+        const int fx = 2 * vx[u] - cx, fy = 2 * vy[u] - cy;
+        const bool f_in = L.has(fx, fy);
+        const bool conv = before_cm(vx[u], vy[u], cx, cy) && L.bit(L.b.cr, vx[u], vy[u]);
+        const int vt = L.T[vc], ft = f_in ? (int)L.T[L.at(fx, fy)] : -1;
+        const uint32_t vd = L.D[vc];
+        const int st = conv ? (int)T_CR : vt;   // type_at_time
         if (st == T_CR || st == t) {
-            if (!(L.D[L.at(vx[u], vy[u])] & rd & 0xf)) continue;   // shares no arrow (:1483)
-            const int fx = 2 * vx[u] - cx, fy = 2 * vy[u] - cy;
-            if (L.has(fx, fy) && L.T[L.at(fx, fy)] == T_SIDEWALK) push(fx, fy);
+            if (!(vd & rd & 0xf)) continue;   // shares no arrow (:1483)
+            if (ft == T_SIDEWALK) push(fx, fy);
         }
-        if (L.T[L.at(vx[u], vy[u])] == T_SIDEWALK) push(vx[u], vy[u]);
+        if (vt == T_SIDEWALK) push(vx[u], vy[u]);
     }
     if (nacc == 0) return 0;
     rec |= (u64)nacc << 60;
@@ -663,11 +669,15 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
         int bx = cx + dx_of(k), by = cy + dy_of(k), cnt = 0;
         while (depth <= L.tl_range) {
             if (!L.has(bx, by)) break;
-            if (type_at_time(L, bx, by, cx, cy) != t) break;
+            const int nbc = L.at(bx, by);
+            // type, arrows and candidate bit of the cell travel together (one round trip per step instead of three)
+            const bool conv = before_cm(bx, by, cx, cy) && L.bit(L.b.cr, bx, by);
+            const int bt = L.T[nbc];
+            const uint32_t bd = L.D[nbc];
+            if ((conv ? (int)T_CR : bt) != t) break;   // type_at_time
             // the cell one step closer to c leads to c (that is why the march got here), so a cell with an arrow onto it does too;
             // only the others (lane-change arrows, opposite lanes) need the reachability planes
-            const int nbc = L.at(bx, by);
-            if (!dl_has(L.D[nbc], dl_get(rd, i)) && !leads_to(L, nbc, c, matters(L, cy))) break;
+            if (!dl_has(bd, dl_get(rd, i)) && !leads_to(L, nbc, c, matters(L, cy))) break;
             cnt++;
             bx += dx_of(k); by += dy_of(k); depth++;
         }
