@@ -97,11 +97,15 @@ __device__ __forceinline__ bool transpose_tile2(const u64 *__restrict__ srcA, co
 // (the 8-byte version was bound by the L2 request rate, profiles/).  Tile (tx, ty) = rows ty*512.., words tx*8.. of
 // `src`; it lands in rows tx*512.., words ty*8.. of `dst`.  s_in / s_out: [512][9] words each.
 // compare: read the destination first; returns (uniformly) whether a word changed, else stores blindly and returns true.
-__device__ __forceinline__ bool transpose_tile512(const u64 *__restrict__ src, int src_rows, int src_wp, u64 *__restrict__ dst, int dst_rows, int dst_wp,
-                                                  int tx, int ty, bool coherent, bool compare, u64 (*s_in)[9], u64 (*s_out)[9]) {
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const bool vec_in = (src_wp & 1) == 0, vec_out = (dst_wp & 1) == 0;
-#pragma unroll 4
+// The three steps are separate so that a kernel that transposes two planes can have the second plane's loads in flight while
+// it works on the first (the profile of the one-plane-after-the-other version had its warps waiting on the loads: each thread's
+// 8 loads of 16 bytes went out four at a time, and nothing overlapped them).
+struct Tile512Regs { u64 v[16]; };
+
+__device__ __forceinline__ void tile512_load(const u64 *__restrict__ src, int src_rows, int src_wp, int tx, int ty, bool coherent, Tile512Regs &q) {
+    const int t = threadIdx.x;
+    const bool vec_in = (src_wp & 1) == 0;
+#pragma unroll
     for (int it = 0; it < 8; it++) {
         const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;   // local row, 16-byte part of its 64 bytes
         const int r = ty * 512 + lr, w = tx * 8 + part * 2;
@@ -116,9 +120,25 @@ __device__ __forceinline__ bool transpose_tile512(const u64 *__restrict__ src, i
                 if (w + 1 < src_wp) b = coherent ? __ldcg(p + 1) : p[1];
             }
         }
-        s_in[lr][part * 2] = a; s_in[lr][part * 2 + 1] = b;
+        q.v[2 * it] = a; q.v[2 * it + 1] = b;
     }
-    __syncthreads();
+}
+
+__device__ __forceinline__ void tile512_stage(const Tile512Regs &q, u64 (*s_in)[9]) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;
+        s_in[lr][part * 2] = q.v[2 * it]; s_in[lr][part * 2 + 1] = q.v[2 * it + 1];
+    }
+}
+
+// s_in (staged, after a __syncthreads) -> transposed -> dst.  compare: read the destination first; returns (uniformly)
+// whether a word changed, else stores blindly and returns true.
+__device__ __forceinline__ bool tile512_finish(u64 *__restrict__ dst, int dst_rows, int dst_wp, int tx, int ty, bool compare, u64 (*s_in)[9],
+                                               u64 (*s_out)[9]) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const bool vec_out = (dst_wp & 1) == 0;
 #pragma unroll 2
     for (int blk = wid; blk < 64; blk += 8) {
         const int i = blk >> 3, j = blk & 7;   // 64-row block i, word j of the tile
@@ -129,24 +149,43 @@ __device__ __forceinline__ bool transpose_tile512(const u64 *__restrict__ src, i
     }
     __syncthreads();
     bool ch = !compare;
-#pragma unroll 4
-    for (int it = 0; it < 8; it++) {
-        const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;
-        const int r = tx * 512 + lr, w = ty * 8 + part * 2;
-        if (r >= dst_rows || w >= dst_wp) continue;
-        const u64 a = s_out[lr][part * 2], b = s_out[lr][part * 2 + 1];
-        u64 *p = dst + (size_t)r * dst_wp + w;
-        const bool two = w + 1 < dst_wp;
-        if (compare) {
-            const bool diff = __ldcg(p) != a || (two && __ldcg(p + 1) != b);
-            if (!diff) continue;
-            ch = true;
+    if (compare) {   // all destination words of this thread in flight together, then the differing ones are rewritten
+        u64 old[16];
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;
+            const int r = tx * 512 + lr, w = ty * 8 + part * 2;
+            const u64 *p = dst + (size_t)r * dst_wp + w;
+            old[2 * it] = (r < dst_rows && w < dst_wp) ? __ldcg(p) : 0ull;
+            old[2 * it + 1] = (r < dst_rows && w + 1 < dst_wp) ? __ldcg(p + 1) : 0ull;
         }
-        if (vec_out && two) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b);
-        else { p[0] = a; if (two) p[1] = b; }
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;
+            const int r = tx * 512 + lr, w = ty * 8 + part * 2;
+            if (r >= dst_rows || w >= dst_wp) continue;
+            const u64 a = s_out[lr][part * 2], b = s_out[lr][part * 2 + 1];
+            const bool two = w + 1 < dst_wp;
+            if (old[2 * it] == a && (!two || old[2 * it + 1] == b)) continue;
+            ch = true;
+            u64 *p = dst + (size_t)r * dst_wp + w;
+            if (vec_out && two) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b);
+            else { p[0] = a; if (two) p[1] = b; }
+        }
+    } else {
+#pragma unroll 4
+        for (int it = 0; it < 8; it++) {
+            const int idx = it * 256 + t, lr = idx >> 2, part = idx & 3;
+            const int r = tx * 512 + lr, w = ty * 8 + part * 2;
+            if (r >= dst_rows || w >= dst_wp) continue;
+            const u64 a = s_out[lr][part * 2], b = s_out[lr][part * 2 + 1];
+            u64 *p = dst + (size_t)r * dst_wp + w;
+            const bool two = w + 1 < dst_wp;
+            if (vec_out && two) *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b);
+            else { p[0] = a; if (two) p[1] = b; }
+        }
     }
-    const bool any = __syncthreads_or(ch);
-    return any;
+    return __syncthreads_or(ch);   // also: s_in / s_out may be reused
 }
 
 // 16-bit membership mask of a 16-byte strip: bit k = type byte k is in `set` (bit t of `set` = type t)

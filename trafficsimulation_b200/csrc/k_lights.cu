@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256, 2) reach_lines_kernel(u64 *fpl, u64 *bpl,
 
 // 512 x 512-cell tiles of the SOURCE plane pair that hold a dirty 64 x 64 block (or all tiles) -> destination pair; marks the
 // destination's lines.  Dynamic shared memory: 2 x [512][9] words.
-__global__ void __launch_bounds__(256) reach_transpose_kernel(const u64 *srcA, const u64 *srcB, int src_rows, int src_wp, u64 *dstA, u64 *dstB, int dst_rows,
+__global__ void __launch_bounds__(256, 3) reach_transpose_kernel(const u64 *srcA, const u64 *srcB, int src_rows, int src_wp, u64 *dstA, u64 *dstB, int dst_rows,
                                                               int dst_wp, uint8_t *bd /* [nby][nbx], row-major block grid */, int nbx, int nby,
                                                               bool src_is_rowmajor, bool all, bool compare, uint8_t *dst_line_dirty,
                                                               uint8_t *clear_flags, int n_clear, const int32_t *ctl) {
@@ -422,8 +422,15 @@ __global__ void __launch_bounds__(256) reach_transpose_kernel(const u64 *srcA, c
     }
     // a tile (tx, ty) of the row-major grid is tile (ty, tx) of the transposed planes
     const int sx = src_is_rowmajor ? tx : ty, sy = src_is_rowmajor ? ty : tx;
-    bool tch = transpose_tile512(srcA, src_rows, src_wp, dstA, dst_rows, dst_wp, sx, sy, true, compare, s_in, s_out);
-    tch |= transpose_tile512(srcB, src_rows, src_wp, dstB, dst_rows, dst_wp, sx, sy, true, compare, s_in, s_out);
+    Tile512Regs qa, qb;
+    tile512_load(srcA, src_rows, src_wp, sx, sy, true, qa);
+    tile512_stage(qa, s_in);
+    tile512_load(srcB, src_rows, src_wp, sx, sy, true, qb);   // in flight while plane A is transposed and written
+    __syncthreads();
+    bool tch = tile512_finish(dstA, dst_rows, dst_wp, sx, sy, compare, s_in, s_out);
+    tile512_stage(qb, s_in);
+    __syncthreads();
+    tch |= tile512_finish(dstB, dst_rows, dst_wp, sx, sy, compare, s_in, s_out);
     if (tch && threadIdx.x < 8) {
         const int k = (src_is_rowmajor ? tx : ty) * 8 + threadIdx.x;   // destination lines = source bit columns
         if (k < (src_is_rowmajor ? nbx : nby)) dst_line_dirty[k] = 1;

@@ -34,10 +34,9 @@ import torch
 
 from . import _lib
 from .sharded import Comm, ShardPlan
-from .traffic import GpuTraffic, _LT
+from .traffic import GpuTraffic
 
 _GROUP_LISTS = ("g_all", "g_ns", "g_ew", "g_nsin", "g_ewin", "g_cl")
-_N_GSTATE = 7   # g_cur, g_pend, g_qt, g_gap, g_last, g_ft_phase, g_ft_timer travel; g_plan lives inside one tick
 MAX_LINK_ROWS = 10   # a vehicle reaches 5 rows; the vehicle that blocks it started at most 5 rows from the contested cell
 
 
@@ -130,6 +129,7 @@ class ShardedTraffic:
             cap = int(min(nv, self.halo * W // 2)) + 16
         self.cap = cap
         self.sims, self.strips, self.send, self.recv = {}, {}, {}, {}
+        self._keep = []   # device index lists the strips point into
         if devices is None:
             devices = ["cuda:0"] * n_shards
         shared = {}
@@ -186,7 +186,7 @@ class ShardedTraffic:
                 self.send[s][d] = torch.zeros(words(len(mine), st.send_hi[d] - st.send_lo[d]), dtype=torch.int32, device=dev)
                 self.recv[s][d] = torch.zeros(words(len(theirs), st.halo_hi[d] - st.halo_lo[d]), dtype=torch.int32, device=dev)
                 st.send_msg[d], st.recv_msg[d] = self.send[s][d].data_ptr(), self.recv[s][d].data_ptr()
-            self._keep = getattr(self, "_keep", []) + keep
+            self._keep += keep
             self.strips[s] = st
 
     # ---- exchange plumbing (Comm.exchange talks in global row ranges; the ranges identify the direction)
