@@ -497,7 +497,7 @@ def ours(args):
             roof = {"bound": "hbm", "kernel": top, "achieved": passes[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": passes[top]["frac_of_measured_peak"], "traffic": ROOFLINE_TRAFFIC_16384.get(top) if size == 16384 else None, "peak_source": peak_src,
                     "note": "the dominant PASS (all kernels of one tsim_layout_* call, timed with CUDA events on the launch stream); its top kernel and "
-                            "every kernel's share are in profiles/r1_launches_16384.summary.txt",
+                            "every kernel's share are in profiles/r1b_launches_bench_16384.summary.txt",
                     "algorithmic_bytes_per_launch": cells * passes[top]["alg_bytes_per_cell"]}
         else:
             roof = {"bound": "hbm", "kernel": "whole pipeline (per GPU)", "achieved": round(pipeline_gbs, 1), "peak": peak, "unit": "GB/s",
