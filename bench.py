@@ -237,6 +237,16 @@ def sharded_vehicle_bench(dev, world, rank, size=4096, per_shard=150000, n_ticks
     from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
     from trafficsimulation_b200.sharded_traffic import ShardedTraffic
     W, H, seed = size, size * world, 4096
+    # every rank holds the whole city's planes, cluster labels and routes on the host while it builds the tables (~6 GB per
+    # rank at 8 shards): leave the leg out rather than push a small host into swap
+    try:
+        import psutil
+        free_gb = torch.tensor([psutil.virtual_memory().available / 2**30], dtype=torch.float64, device=dev)
+        dist.all_reduce(free_gb, op=dist.ReduceOp.MIN)
+        if float(free_gb.item()) < 8.0 * world:
+            return {"skipped": f"host memory: {float(free_gb.item()):.0f} GiB available, {8 * world} GiB wanted for {world} ranks"}
+    except ImportError:
+        pass
     hb, vb = tapes.synth_bands(seed, width=W, height=H)
     cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
     city = GpuCityLayout(width=W, height=H, device=dev)
