@@ -94,3 +94,53 @@ def test_local_comm_matches_distributed_semantics():
     assert all(g[s].reshape(-1).tolist() == [1, 2, 3] for s in range(n))
     assert comm.any({s: torch.tensor(0) for s in range(n)}) is False
     assert comm.any({0: torch.tensor(0), 1: torch.tensor(1), 2: torch.tensor(0)}) is True
+
+
+def _tick_message_worker(rank, world, port, H, halo, out):
+    """The sharded tick's exchange (ShardedTraffic._message through Comm.exchange): one message per neighbour, different
+    lengths per direction, received in place -- with CPU tensors standing in for the device message buffers."""
+    import torch.distributed as dist
+    from trafficsimulation_b200.sharded_traffic import ShardedTraffic
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Stub:
+            pass
+        st = Stub()
+        st.plan, st.n = ShardPlan(H, world, halo), world
+        comm = Comm(world, True)
+        # message from shard a to shard b has 100 + 10 a + b words, every word = 1000 a + b
+        length = lambda a, b: 100 + 10 * a + b
+        mk = lambda a, b: torch.full((length(a, b),), 1000 * a + b, dtype=torch.int32)
+        st.send = {rank: [mk(rank, rank - 1) if rank > 0 else None, mk(rank, rank + 1) if rank + 1 < world else None]}
+        st.recv = {rank: [torch.zeros(length(rank - 1, rank), dtype=torch.int32) if rank > 0 else None,
+                          torch.zeros(length(rank + 1, rank), dtype=torch.int32) if rank + 1 < world else None]}
+        st._role = lambda s, lo, hi: ShardedTraffic._role(st, s, lo, hi)
+        for _ in range(3):   # every tick reuses the buffers
+            comm.exchange(st.plan, lambda s, lo, hi: ShardedTraffic._message(st, s, lo, hi))
+            if rank > 0:
+                assert torch.equal(st.recv[rank][0], mk(rank - 1, rank)), "message from the shard below"
+            if rank + 1 < world:
+                assert torch.equal(st.recv[rank][1], mk(rank + 1, rank)), "message from the shard above"
+            for b in st.recv[rank]:
+                if b is not None:
+                    b.zero_()
+        out.put((rank, "ok"))
+    except Exception as e:   # noqa: BLE001
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tick_messages_under_gloo(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tick_message_worker, args=(r, world, port, 600, 128, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
