@@ -1,4 +1,4 @@
-"""ctypes front-end of the CPU oracle (oracle/city_oracle.c, oracle/vehicle_oracle.c).
+"""ctypes front-end of the CPU oracle (oracle/city_oracle.c, oracle/vehicle_oracle.c, oracle/astar_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports it.
@@ -22,7 +22,7 @@ class OCfg(C.Structure):
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("city_oracle.c", "vehicle_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("city_oracle.c", "vehicle_oracle.c", "astar_oracle.c")]
     if force or not os.path.exists(_LIB) or any(
             os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -273,3 +273,34 @@ class OracleTicks:
                     occ=np.flatnonzero(a["occ"]).astype(np.int32), stop=np.flatnonzero(a["stop"]).astype(np.int32),
                     stuckmap=np.flatnonzero(a["stuckmap"]).astype(np.int32),
                     groups=np.stack([a["g_cur"], a["g_pend"], a["g_qt"], a["g_gap"], a["g_last"]], 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# route planner oracle (oracle/astar_oracle.c)
+# ------------------------------------------------------------------------------------------------
+class AstarMaps(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32)] + [(n, C.c_void_p) for n in
+                                                          ("occupancy", "stop_map", "is_road", "road_type", "allowed_dirs", "density")]
+
+
+class OracleAstar:
+    """`astar_numba(width, height, sx, sy, gx, gy, maps..., flags)` of the reference (astar_numba.py:240-281) on fixed maps.
+    Maps are [H][W]; `query` returns the path as (x, y) tuples, first step first, like the reference."""
+
+    def __init__(self, occupancy, stop_map, is_road_map, road_type_map, allowed_dirs_map, density_map=None):
+        self.H, self.W = np.asarray(is_road_map).shape
+        u8 = lambda a: np.ascontiguousarray(np.asarray(a).astype(np.uint8))
+        self._keep = [u8(occupancy), u8(stop_map), u8(is_road_map), u8(road_type_map), u8(allowed_dirs_map),
+                      None if density_map is None else np.ascontiguousarray(density_map, np.float64)]
+        self.maps = AstarMaps(self.W, self.H, *[(a.ctypes.data if a is not None else None) for a in self._keep])
+        self._out = np.zeros(self.W * self.H, np.int32)
+        lib().oracle_astar.restype = C.c_int
+
+    def query(self, sx, sy, gx, gy, respect_awareness=False, awareness_range=10, soft_obstacles=False, ignore_flow=False,
+              maximum_steps=0x7FFFFFFF):
+        n = lib().oracle_astar(C.byref(self.maps), int(sx), int(sy), int(gx), int(gy), int(respect_awareness), int(awareness_range),
+                               int(soft_obstacles), int(ignore_flow), int(maximum_steps), _p(self._out, C.c_int32), len(self._out))
+        if n < 0:
+            raise ValueError(f"astar oracle error {n}")
+        cells = self._out[:n]
+        return [(int(c % self.W), int(c // self.W)) for c in cells]

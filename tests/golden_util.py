@@ -77,3 +77,23 @@ def compare_tick(t, got, r):
         want = r[k + "_cells"][r[k + "_off"][t]:r[k + "_off"][t + 1]]
         assert np.array_equal(got[k], want), (t, k, len(got[k]), len(want))
     assert np.array_equal(got["groups"], r["group_state"][t]), (t, "groups")
+
+
+def load_astar(path):
+    """tests/golden/astar_*.npz -> maps ([H][W] uint8 / float64), queries [n, 8], paths (list of int64 cell arrays)."""
+    d = np.load(path, allow_pickle=True)
+    lay = np.load(os.path.join(os.path.dirname(path), str(d["fixture"])), allow_pickle=True)
+    H, W = lay["is_road_map"].shape
+    step = np.array([W, 1, -W, -1], np.int64)
+    first, off, codes = d["path_first"], d["path_off"], d["path_steps"]
+    paths = []
+    for i in range(len(first)):
+        n = int(off[i + 1] - off[i])
+        if n == 0:
+            paths.append(np.zeros(0, np.int64))
+            continue
+        c = codes[off[i]:off[i + 1]]
+        paths.append(first[i] + np.concatenate([[0], np.cumsum(step[c[:-1]])]))
+    return dict(W=W, H=H, is_road_map=lay["is_road_map"].astype(np.uint8), road_type_map=lay["road_type_map"].astype(np.uint8),
+                allowed_dirs_map=lay["allowed_dirs_map"].astype(np.uint8), occupancy=d["occupancy"], stop_map=d["stop_map"],
+                density=d["density"], queries=d["queries"], paths=paths)
