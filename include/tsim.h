@@ -348,6 +348,39 @@ tsim_status tsim_tick_pack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const
 tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st,
                              const tsim_tick_strips *strips, void *stream);
 
+/* ---- batched route planning.  Replaces astar_numba(width, height, start_x, start_y, goal_x, goal_y,
+   occupancy_map, stop_map, is_road_map, road_type_map, allowed_dirs_map, respect_awareness, awareness_range, density_map,
+   soft_obstacles, ignore_flow, maximum_steps) -> [(x, y)] (utilities/pathfinding/astar_numba.py:240-281; same signature as
+   the reference's pybind11 module, utilities/pathfinding/astar_cpp.cpp:35-50) for MANY queries on one set of maps.
+   The result is the reference's path cell for cell (same heap, same tie-breaking, same penalties), not just a path of
+   equal cost.                                                                                                       */
+typedef struct tsim_astar_maps {      /* device pointers, [height][width], values as in city_model.py:109-115 */
+    const uint8_t *occupancy, *stop_map, *is_road_map, *road_type_map, *allowed_dirs_map;
+    const double *density_map;        /* NULL = 0 everywhere (it only scales the soft vehicle penalty) */
+} tsim_astar_maps;
+
+#define TSIM_ASTAR_RESPECT_AWARENESS 1
+#define TSIM_ASTAR_SOFT_OBSTACLES 2
+#define TSIM_ASTAR_IGNORE_FLOW 4
+
+typedef struct tsim_astar_query {
+    int32_t sx, sy, gx, gy;
+    int32_t flags;                    /* TSIM_ASTAR_* */
+    int32_t awareness_range;          /* Defaults.VEHICLE_AWARENESS_RANGE = 10 */
+    int32_t maximum_steps;            /* 0x7FFFFFFF = unbounded */
+    int32_t reserved;
+} tsim_astar_query;
+
+/* every query works on its own dist / came_from / heap arrays (26 bytes per cell), like the reference's wrapper (:264-272) */
+tsim_status tsim_astar_scratch_bytes(const tsim_cfg *cfg, int32_t n_queries, size_t *out);
+
+/* path_len[q] = cells of query q's path (0: none, or start == goal), path_cells[q * max_path ...] = cell indices
+   y * width + x, first step first, goal last.  err_flag: 50 a path is longer than max_path (path_len[q] = -(needed)),
+   51 open list overflow, 52 query outside the grid.                                                              */
+tsim_status tsim_astar_batch(const tsim_cfg *cfg, const tsim_astar_maps *maps, const tsim_astar_query *queries,
+                             int32_t n_queries, int32_t *path_len, int32_t *path_cells, int32_t max_path,
+                             int32_t *err_flag, void *scratch, size_t scratch_bytes, void *stream);
+
 /* labels the 4-connected components of mask == 1 (u8 plane) in raster discovery order: component
    table as tsim_layout_label_nothing, plus the label plane (id, 0 elsewhere).  Used for the
    intersection clusters of _create_intersection_light_groups (city_model.py:1587-1650). */

@@ -19,7 +19,7 @@ SYMBOLS = [
     "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_shard_counts", "tsim_layout_carve", "tsim_layout_zones",
     "tsim_layout_dead_ends", "tsim_layout_upgrade_r2", "tsim_layout_entrances", "tsim_layout_fix_dirs",
     "tsim_layout_lights", "tsim_lights_prepare", "tsim_lights_seed", "tsim_lights_reach", "tsim_lights_reach_planes",
-    "tsim_lights_finish", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_tick_message_words", "tsim_tick_pack", "tsim_tick_unpack", "tsim_label_mask",
+    "tsim_lights_finish", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_tick_message_words", "tsim_tick_pack", "tsim_tick_unpack", "tsim_astar_scratch_bytes", "tsim_astar_batch", "tsim_label_mask",
 ]
 
 
@@ -84,6 +84,12 @@ class TickStrips(C.Structure):
                 ("g_send", C.c_void_p * 2), ("n_g_send", C.c_int32 * 2),
                 ("g_recv", C.c_void_p * 2), ("g_verify", C.c_void_p * 2), ("n_g_recv", C.c_int32 * 2)]
 
+
+class AstarMaps(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("occupancy", "stop_map", "is_road_map", "road_type_map", "allowed_dirs_map", "density_map")]
+
+
+ASTAR_QUERY_WORDS = 8   # tsim_astar_query: sx, sy, gx, gy, flags, awareness_range, maximum_steps, reserved (int32 each)
 
 TICK_REC_WORDS, TICK_REC_HEADER, CELL_OUTSIDE = 12, 16, -2
 
