@@ -4,16 +4,25 @@
 #include <cstring>
 #include "../../trafficsimulation_b200/csrc/astar_core.cuh"
 
+// cap <= 0: the capacity tsim_astar_batch uses (half the grid)
 extern "C" int host_astar(int W, int H, const uint8_t *occ, const uint8_t *stop, const uint8_t *road, const uint8_t *rtype, const uint8_t *adirs,
-                          const double *dens, int sx, int sy, int gx, int gy, int flags, int awareness, int max_steps, int32_t *out, int out_cap) {
+                          const double *dens, int sx, int sy, int gx, int gy, int flags, int awareness, int max_steps, int32_t *out, int out_cap,
+                          int cap) {
     const size_t n = (size_t)W * H;
-    tsim::AstarMaps m{W, H, occ, stop, road, rtype, adirs, dens};
+    if (cap <= 0) cap = (int)(((n / 2 + 64) + 15) & ~(size_t)15);
+    uint16_t *cell = (uint16_t *)malloc(n * sizeof(uint16_t));
+    for (size_t i = 0; i < n; i++) cell[i] = tsim::as_pack(occ[i], stop[i], road[i], rtype[i], adirs[i]);   // astar_pack_kernel
+    tsim::AstarMaps m{W, H, cell, dens};
     tsim::AstarWork w;
-    int32_t *ints = (int32_t *)malloc(6 * n * sizeof(int32_t));
-    w.dist = ints; w.came = ints + n; w.f = ints + 2 * n; w.g = ints + 3 * n; w.s = ints + 4 * n; w.ix = ints + 5 * n;
-    w.dir = (int8_t *)malloc(n); w.fov = (uint8_t *)calloc(n, 1);
-    memset(w.dist, 0x3F, n * 4); memset(w.came, 0xFF, n * 4); memset(w.dir, 0xFF, n);   // what tsim_astar_batch does with cudaMemsetAsync
+    w.dist = (uint32_t *)malloc(n * 4);
+    w.heap = (tsim::AsEntry *)aligned_alloc(16, sizeof(tsim::AsEntry) * (size_t)cap);
+    w.dir = (int8_t *)malloc(cap);
+    w.fov = (uint8_t *)calloc(n, 1);
+    w.cap = cap;
+    memset(w.dist, 0x3F, n * 4);          // what tsim_astar_batch does with cudaMemsetAsync
+    memset(w.heap, 0xA5, sizeof(tsim::AsEntry) * (size_t)cap);   // heap and dir start as garbage on the device
+    memset(w.dir, 0x5A, cap);
     const int r = tsim::astar_search(m, sx, sy, gx, gy, flags, awareness, max_steps, w, out, out_cap);
-    free(ints); free(w.dir); free(w.fov);
+    free(cell); free(w.dist); free(w.heap); free(w.dir); free(w.fov);
     return r;
 }

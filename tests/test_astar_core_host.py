@@ -34,7 +34,7 @@ def test_product_core_reproduces_golden(core, path):
     for q, want in zip(r["queries"], r["paths"]):
         sx, sy, gx, gy, ra, so, ig, ms = (int(v) for v in q)
         n = core.host_astar(W, H, *[u8(a) for a in keep], dens.ctypes.data_as(C.POINTER(C.c_double)), sx, sy, gx, gy,
-                            ra | (so << 1) | (ig << 2), 10, ms, out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
+                            ra | (so << 1) | (ig << 2), 10, ms, out.ctypes.data_as(C.POINTER(C.c_int32)), len(out), 0)
         assert n >= 0 and out[:n].tolist() == list(want), tuple(q)
 
 
@@ -47,5 +47,20 @@ def test_product_core_reports_a_short_output_buffer(core):
     out = np.zeros(4, np.int32)
     u8 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8))
     n = core.host_astar(W, H, *[u8(a) for a in keep], None, sx, sy, gx, gy, ra | (so << 1) | (ig << 2), 10, ms,
-                        out.ctypes.data_as(C.POINTER(C.c_int32)), 4)
+                        out.ctypes.data_as(C.POINTER(C.c_int32)), 4, 0)
     assert n < 0    # -(cells needed); with density = NULL the path may differ in length, never fit in 4 cells
+
+
+def test_product_core_reports_open_list_overflow(core):
+    """The open list is bounded (half the grid in tsim_astar_batch); outgrowing it is an error code, never a silent wrong path."""
+    r = load_astar(FIXTURES[0])
+    W, H = r["W"], r["H"]
+    keep = [np.ascontiguousarray(r[k], np.uint8) for k in ("occupancy", "stop_map", "is_road_map", "road_type_map", "allowed_dirs_map")]
+    i = int(np.argmax([len(p) for p in r["paths"]]))
+    sx, sy, gx, gy, ra, so, ig, ms = (int(v) for v in r["queries"][i])
+    out = np.zeros(W * H, np.int32)
+    u8 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8))
+    args = [W, H, *[u8(a) for a in keep], r["density"].ctypes.data_as(C.POINTER(C.c_double)), sx, sy, gx, gy, ra | (so << 1) | (ig << 2), 10, ms,
+            out.ctypes.data_as(C.POINTER(C.c_int32)), len(out)]
+    assert core.host_astar(*args, 8) == -0x40000000
+    assert core.host_astar(*args, 0) == len(r["paths"][i])

@@ -31,27 +31,37 @@ constexpr double AS_DYN_SCALE = 4.0;
 enum { AS_RESPECT_AWARENESS = 1, AS_SOFT_OBSTACLES = 2, AS_IGNORE_FLOW = 4 };
 constexpr int AS_ERR_HEAP = -0x40000000;                 // the open list outgrew the reference's own arrays (W * H entries)
 
-struct AstarMaps {      // [H][W] planes of the model (city_model.py:109-115)
+// Memory layout (a query is a chain of dependent loads, so every access counts):
+//  * the five byte maps are packed once per batch into ONE 16-bit word per cell (as_pack): a neighbour costs one load;
+//  * a heap entry (f, g, steps, cell) is one 16-byte struct: a sift moves whole entries with single 128-bit accesses, and
+//    moves a hole instead of swapping (same final arrangement as the reference's swaps, fewer stores);
+//  * dist and came_from share a word: cost in the low 30 bits (AS_INF = 0x3F3F3F3F fits), the direction the cell was
+//    entered by in the top 2, which is all came_from is ever used for (the parent is the neighbour that direction came from).
+constexpr uint32_t AS_COST_MASK = 0x3FFFFFFFu;
+enum { ASC_DIRS = 0xF, ASC_ROAD = 0x10, ASC_RT_SHIFT = 5, ASC_OCC = 0x80, ASC_STOP = 0x100 };
+
+TSIM_HD uint16_t as_pack(uint8_t occupancy, uint8_t stop, uint8_t is_road, uint8_t road_type, uint8_t allowed_dirs) {
+    return (uint16_t)((allowed_dirs & ASC_DIRS) | (is_road == 1 ? ASC_ROAD : 0) | ((road_type <= 3 ? road_type : 0) << ASC_RT_SHIFT) |
+                      (occupancy == 1 ? ASC_OCC : 0) | (stop == 1 ? ASC_STOP : 0));
+}
+
+struct AstarMaps {      // [H][W]
     int W, H;
-    const uint8_t *occupancy, *stop_map, *is_road, *road_type, *allowed_dirs;
+    const uint16_t *cell;    // as_pack of the model's planes (city_model.py:109-115)
     const double *density;   // may be null (= 0 everywhere)
 };
 
-struct AstarWork {      // per query, W * H entries each.  Expected on entry: dist = AS_INF, came = -1, dir = -1, fov = 0
-    int32_t *dist, *came, *f, *g, *s, *ix;
-    int8_t *dir;
-    uint8_t *fov;
+struct alignas(16) AsEntry { int32_t f, g, s, ix; };
+
+struct AstarWork {      // per query.  Expected on entry: dist = AS_INF (0x3F bytes), fov = 0; heap / dir need no initialisation
+    uint32_t *dist;     // [W * H]
+    AsEntry *heap;      // [cap]
+    int8_t *dir;        // [cap] the reference's dir_arr in its per-heap-slot role
+    uint8_t *fov;       // [W * H]
+    int cap;            // the reference's arrays hold W * H entries; a city's open list stays below a third of its road cells
 };
 
 TSIM_HD int as_abs(int v) { return v < 0 ? -v : v; }
-
-TSIM_HD void as_swap(const AstarWork &w, int a, int b) {
-    int32_t t;
-    t = w.f[a]; w.f[a] = w.f[b]; w.f[b] = t;
-    t = w.g[a]; w.g[a] = w.g[b]; w.g[b] = t;
-    t = w.s[a]; w.s[a] = w.s[b]; w.s[b] = t;
-    t = w.ix[a]; w.ix[a] = w.ix[b]; w.ix[b] = t;
-}
 
 TSIM_HD long long as_dynamic_penalty(double density) {   // int(p * (1.0 + SCALE * local_density)), :193-196
 #ifdef __CUDA_ARCH__
@@ -68,19 +78,20 @@ TSIM_HD long long as_dynamic_penalty(double density) {   // int(p * (1.0 + SCALE
 TSIM_HD int astar_search(const AstarMaps &m, int sx, int sy, int gx, int gy, int flags, int awareness_range, int maximum_steps,
                          const AstarWork &w, int32_t *out, int out_cap) {
     static const int8_t DXY[8] = {0, 1, 1, 0, 0, -1, -1, 0};   // NEIGHBOR_DELTAS N, E, S, W (:9)
-    const int W = m.W, H = m.H, n = W * H;
+    const int W = m.W, H = m.H;
     const int start = sy * W + sx, goal = gy * W + gx;
     const bool respect = flags & AS_RESPECT_AWARENESS, soft = flags & AS_SOFT_OBSTACLES, ignore_flow = flags & AS_IGNORE_FLOW;
     w.dist[start] = 0;
     int heap = 1;
-    w.f[0] = as_abs(sx - gx) + as_abs(sy - gy); w.g[0] = 0; w.s[0] = 0; w.ix[0] = start; w.dir[0] = -1;
+    w.heap[0] = AsEntry{as_abs(sx - gx) + as_abs(sy - gy), 0, 0, start};
+    w.dir[0] = -1;                                          // dir_arr[i] = -1 for every node, slot 0 included (:121-125,130)
     if (respect) {   // compute_fov_inplace :30-50 (fov arrives zeroed)
         for (int d = 0; d < 4; d++) {
             const int dx = DXY[2 * d], dy = DXY[2 * d + 1], px = -dy, py = dx;
             for (int off = -awareness_range + 1; off < awareness_range; off++) {
                 const int x0 = sx + off * px, y0 = sy + off * py;
                 int x = x0, y = y0, step = 0;
-                while (x >= 0 && x < W && y >= 0 && y < H && m.is_road[y * W + x] == 1) {
+                while (x >= 0 && x < W && y >= 0 && y < H && (m.cell[y * W + x] & ASC_ROAD)) {
                     w.fov[y * W + x] = 1;
                     step++;
                     x = x0 + dx * step; y = y0 + dy * step;
@@ -88,72 +99,83 @@ TSIM_HD int astar_search(const AstarMaps &m, int sx, int sy, int gx, int gy, int
             }
         }
     }
+    // w.dir needs no initialisation: slot i is written by the push that first grows the heap to i + 1, before any pop reads it
     while (heap > 0) {
-        const int32_t cg = w.g[0], steps = w.s[0], cur = w.ix[0];
+        const AsEntry top = w.heap[0];
         const int prev_dir = w.dir[0];
         heap--;
         if (heap > 0) {
-            w.f[0] = w.f[heap]; w.g[0] = w.g[heap]; w.s[0] = w.s[heap]; w.ix[0] = w.ix[heap]; w.dir[0] = w.dir[heap];
-            int idx = 0;                                    // heap_sift_down :66-85
+            const AsEntry last = w.heap[heap];
+            w.dir[0] = w.dir[heap];
+            int idx = 0;                                    // heap_sift_down :66-85, moving a hole
             for (;;) {
                 const int left = 2 * idx + 1, right = left + 1;
+                if (left >= heap) break;
+                const AsEntry l = w.heap[left];
                 int smallest = idx;
-                if (left < heap && w.f[left] < w.f[smallest]) smallest = left;
-                if (right < heap && w.f[right] < w.f[smallest]) smallest = right;
+                AsEntry pick = last;
+                if (l.f < pick.f) { smallest = left; pick = l; }
+                if (right < heap) {
+                    const AsEntry r = w.heap[right];
+                    if (r.f < pick.f) { smallest = right; pick = r; }
+                }
                 if (smallest == idx) break;
-                as_swap(w, idx, smallest);
+                w.heap[idx] = pick;
                 idx = smallest;
             }
+            w.heap[idx] = last;
         }
+        const int cur = top.ix;
         if (cur == goal) {
             int len = 0;
-            for (int i = cur; i != start; i = w.came[i]) len++;
+            for (int i = cur; i != start;) { const int d = (int)(w.dist[i] >> 30); i -= DXY[2 * d + 1] * W + DXY[2 * d]; len++; }
             if (len > out_cap) return -len;
             int k = len;
-            for (int i = cur; i != start; i = w.came[i]) out[--k] = i;
+            for (int i = cur; i != start;) { out[--k] = i; const int d = (int)(w.dist[i] >> 30); i -= DXY[2 * d + 1] * W + DXY[2 * d]; }
             return len;
         }
-        if (cg > w.dist[cur]) continue;
+        if ((uint32_t)top.g > (w.dist[cur] & AS_COST_MASK)) continue;
         const int cx = cur % W, cy = cur / W;
-        const int bits = m.allowed_dirs[cur];
+        const int bits = m.cell[cur] & ASC_DIRS;
         for (int d = 0; d < 4; d++) {
             const int nx = cx + DXY[2 * d], ny = cy + DXY[2 * d + 1];
             if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
-            const int ns = steps + 1;
+            const int ns = top.s + 1;
             if (ns > maximum_steps) continue;
             const int nidx = ny * W + nx;
-            long long ng = (long long)cg + 1;
+            const uint32_t c = m.cell[nidx];
+            long long ng = (long long)top.g + 1;
             if (prev_dir != -1 && d != prev_dir) ng += AS_TURN;
-            const bool road = m.is_road[nidx] == 1;
             if ((bits & (1 << d)) == 0) {
-                if (ignore_flow && road) ng += AS_CONTRA;
+                if (ignore_flow && (c & ASC_ROAD)) ng += AS_CONTRA;
                 else continue;
             }
             const bool seen = !respect || w.fov[nidx] == 1;
-            if (m.occupancy[nidx] == 1 && seen) {
+            if ((c & ASC_OCC) && seen) {
                 if (soft) ng += as_dynamic_penalty(m.density ? m.density[nidx] : 0.0);
                 else continue;
             }
-            if (m.stop_map[nidx] == 1 && seen) {
+            if ((c & ASC_STOP) && seen) {
                 if (soft) ng += AS_STOP;
                 else continue;
             }
-            if (road) {
-                const int rt = m.road_type[nidx];
+            if (c & ASC_ROAD) {
+                const int rt = (c >> ASC_RT_SHIFT) & 3;
                 ng += rt == 2 ? AS_R2 : rt == 3 ? AS_R3 : 0;   // R1's 0.5 never survives a comparison or a store (see the header)
             }
-            if (ng < (long long)w.dist[nidx]) {
-                if (heap >= n) return AS_ERR_HEAP;
-                w.dist[nidx] = (int32_t)ng;
-                w.came[nidx] = cur;
+            if (ng < (long long)(w.dist[nidx] & AS_COST_MASK)) {
+                if (heap >= w.cap) return AS_ERR_HEAP;
+                w.dist[nidx] = (uint32_t)ng | ((uint32_t)d << 30);
+                const AsEntry e{(int32_t)(ng + as_abs(nx - gx) + as_abs(ny - gy)), (int32_t)ng, ns, nidx};
                 int i = heap;
-                w.f[i] = (int32_t)(ng + as_abs(nx - gx) + as_abs(ny - gy)); w.g[i] = (int32_t)ng; w.s[i] = ns; w.ix[i] = nidx;
-                w.dir[i] = (int8_t)d;
-                while (i > 0) {                             // heap_sift_up :52-64
+                w.dir[i] = (int8_t)d;                       // stays with the SLOT (:229), whatever the sift does to the entry
+                while (i > 0) {                             // heap_sift_up :52-64, moving a hole
                     const int parent = (i - 1) / 2;
-                    if (w.f[i] < w.f[parent]) { as_swap(w, i, parent); i = parent; }
+                    const AsEntry pe = w.heap[parent];
+                    if (e.f < pe.f) { w.heap[i] = pe; i = parent; }
                     else break;
                 }
+                w.heap[i] = e;
                 heap++;
             }
         }

@@ -16,27 +16,31 @@ namespace tsim {
 struct AstarBatch {
     AstarMaps m;
     const tsim_astar_query *q;
-    int n_queries, max_path;
+    int n_queries, max_path, cap;
     int32_t *path_len, *path_cells;
-    int32_t *ints;      // [6][n_queries][W*H]: dist, came, f, g, s, ix
-    int8_t *dir;        // [n_queries][W*H]
+    AsEntry *heap;      // [n_queries][cap]
+    uint32_t *dist;     // [n_queries][W*H]
+    int8_t *dir;        // [n_queries][cap]
     uint8_t *fov;       // [n_queries][W*H]
     int32_t *err;
 };
 
+__global__ void __launch_bounds__(256) astar_pack_kernel(long long n, tsim_astar_maps maps, uint16_t *cell) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        cell[i] = as_pack(maps.occupancy[i], maps.stop_map[i], maps.is_road_map[i], maps.road_type_map[i], maps.allowed_dirs_map[i]);
+}
+
 __global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n_queries) return;
-    const size_t n = (size_t)b.m.W * b.m.H, plane = n * b.n_queries;
+    const size_t n = (size_t)b.m.W * b.m.H;
     const tsim_astar_query q = b.q[i];
     if (q.sx < 0 || q.sx >= b.m.W || q.gx < 0 || q.gx >= b.m.W || q.sy < 0 || q.sy >= b.m.H || q.gy < 0 || q.gy >= b.m.H || q.awareness_range < 0) {
         *b.err = 52;   // a query outside the grid
         b.path_len[i] = 0;
         return;
     }
-    AstarWork w;
-    w.dist = b.ints + n * i; w.came = w.dist + plane; w.f = w.came + plane; w.g = w.f + plane; w.s = w.g + plane; w.ix = w.s + plane;
-    w.dir = b.dir + n * i; w.fov = b.fov + n * i;
+    const AstarWork w{b.dist + n * i, b.heap + (size_t)b.cap * i, b.dir + (size_t)b.cap * i, b.fov + n * i, b.cap};
     const int r = astar_search(b.m, q.sx, q.sy, q.gx, q.gy, q.flags, q.awareness_range, q.maximum_steps, w, b.path_cells + (size_t)i * b.max_path,
                                b.max_path);
     if (r == AS_ERR_HEAP) { *b.err = 51; b.path_len[i] = 0; }
@@ -44,7 +48,13 @@ __global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
     else b.path_len[i] = r;
 }
 
-static size_t astar_bytes(long long n, int nq) { return (size_t)n * nq * (6 * sizeof(int32_t) + 2) + 256; }
+// open-list capacity per query: the reference's arrays hold W * H entries; on city maps the list peaks below a third of the
+// ROAD cells (~ W * H / 14 on the reference's default city), so half the grid is generous -- and overflow is an error, not UB
+static int astar_cap(long long n) { return (int)(((n / 2 + 64) + 15) & ~15LL); }
+static size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+static size_t astar_bytes(long long n, int nq) {
+    return round16((size_t)n * 2) + (size_t)nq * (sizeof(AsEntry) * astar_cap(n) + round16((size_t)n * 4) + astar_cap(n) + round16((size_t)n)) + 256;
+}
 
 }  // namespace tsim
 
@@ -75,20 +85,22 @@ extern "C" tsim_status tsim_astar_batch(const tsim_cfg *cfg, const tsim_astar_ma
         set_error("tsim_astar_batch needs %zu scratch bytes for %d queries, got %zu", astar_bytes(n, n_queries), n_queries, scratch_bytes);
         return TSIM_ERR_WORKSPACE;
     }
-    if (((uintptr_t)scratch & 3) != 0) { set_error("tsim_astar_batch: scratch must be 4-byte aligned"); return TSIM_ERR_CONFIG; }
+    if (((uintptr_t)scratch & 15) != 0) { set_error("tsim_astar_batch: scratch must be 16-byte aligned"); return TSIM_ERR_CONFIG; }
     cudaStream_t cs = (cudaStream_t)stream;
-    const size_t plane = (size_t)n * n_queries;
+    const int cap = astar_cap(n);
+    char *p = (char *)scratch;
+    uint16_t *cell = (uint16_t *)p;                       p += round16((size_t)n * 2);
     AstarBatch b;
-    b.m = AstarMaps{cfg->width, cfg->height, maps->occupancy, maps->stop_map, maps->is_road_map, maps->road_type_map, maps->allowed_dirs_map,
-                    maps->density_map};
-    b.q = queries; b.n_queries = n_queries; b.max_path = max_path; b.path_len = path_len; b.path_cells = path_cells; b.err = err_flag;
-    b.ints = (int32_t *)scratch;
-    b.dir = (int8_t *)(b.ints + 6 * plane);
-    b.fov = (uint8_t *)(b.dir + plane);
-    TSIM_CUDA(cudaMemsetAsync(b.ints, 0x3F, plane * 4, cs));            // dist = INF = 0x3F3F3F3F (:118)
-    TSIM_CUDA(cudaMemsetAsync(b.ints + plane, 0xFF, plane * 4, cs));    // came_from = -1
-    TSIM_CUDA(cudaMemsetAsync(b.dir, 0xFF, plane, cs));                 // dir_arr = -1
-    TSIM_CUDA(cudaMemsetAsync(b.fov, 0, plane, cs));                    // fov_map = 0
+    b.heap = (AsEntry *)p;                                p += sizeof(AsEntry) * (size_t)cap * n_queries;
+    b.dist = (uint32_t *)p;                               p += round16((size_t)n * 4) * n_queries;
+    b.dir = (int8_t *)p;                                  p += (size_t)cap * n_queries;
+    b.fov = (uint8_t *)p;
+    b.m = AstarMaps{cfg->width, cfg->height, cell, maps->density_map};
+    b.q = queries; b.n_queries = n_queries; b.max_path = max_path; b.cap = cap; b.path_len = path_len; b.path_cells = path_cells; b.err = err_flag;
+    astar_pack_kernel<<<(int)(div_up(n, 256) < 1184 ? div_up(n, 256) : 1184), 256, 0, cs>>>(n, *maps, cell);
+    TSIM_LAUNCH_CHECK();
+    TSIM_CUDA(cudaMemsetAsync(b.dist, 0x3F, (size_t)n * 4 * n_queries, cs));   // dist = INF = 0x3F3F3F3F (:118), no parent direction
+    TSIM_CUDA(cudaMemsetAsync(b.fov, 0, (size_t)n * n_queries, cs));           // fov_map = 0
     astar_kernel<<<div_up(n_queries, 64), 64, 0, cs>>>(b);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
