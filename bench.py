@@ -309,6 +309,42 @@ def guarded(fn, rank, limit_s, on_timeout):
         timer.cancel()
 
 
+def route_planning_leg(dev, n_queries=16384):
+    """reference-exact routes/s of the batched planner on the reference's default city (the maps of the committed
+    fixture tests/golden/astar_default12345.npz), the C oracle on a sample of the same queries beside it (same code as
+    profiles/astar_bench.py)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import load_astar
+    from oracle import oracle as O
+    from trafficsimulation_b200.pathfinding import GpuAstar
+    r = load_astar(os.path.join(ROOT, "tests", "golden", "astar_default12345.npz"))
+    W, H = r["W"], r["H"]
+    rng = np.random.default_rng(1)
+    road = np.flatnonzero(r["is_road_map"].reshape(-1) == 1)
+    a, b = rng.choice(road, n_queries), rng.choice(road, n_queries)
+    q = np.stack([a % W, a // W, b % W, b // W, np.zeros(n_queries, np.int64), np.full(n_queries, 10), np.full(n_queries, 0x7FFFFFFF)], 1)
+    free = np.zeros((H, W), np.uint8)
+    planner = GpuAstar(W, H, free, r["stop_map"], r["is_road_map"], r["road_type_map"], r["allowed_dirs_map"], r["density"], device=dev)
+    planner.plan_cells(q[:256])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    paths = planner.plan_cells(q)
+    wall = time.perf_counter() - t0
+    ora = O.OracleAstar(free, r["stop_map"], r["is_road_map"], r["road_type_map"], r["allowed_dirs_map"], r["density"])
+    ns = 200
+    t0 = time.perf_counter()
+    ref = [ora.query(*[int(v) for v in q[i, :4]]) for i in range(ns)]
+    cpu = time.perf_counter() - t0
+    same = all([y * W + x for x, y in ref[i]] == paths[i].tolist() for i in range(ns))
+    return {"metric": "routes/s (batched A*, the reference's path cell for cell)", "value": n_queries / wall, "unit": "routes/s",
+            "config": {"workload": f"{n_queries} plain routes between random road cells of the default {W}x{H} city, one CUDA thread per query",
+                       "with_route": int(sum(len(p) > 0 for p in paths)), "mean_path_cells": float(np.mean([len(p) for p in paths]))},
+            "note": "host wall time: queries up, paths back on the host",
+            "cpu_baseline": {"value": ns / cpu, "unit": "routes/s", "cores": 1, "kind": "port", "sample": f"{ns} of the same queries, oracle/astar_oracle.c"},
+            "sample_matches_oracle": bool(same)}
+
+
 def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
     """BASELINE.json configs[1] (4096 x 4096, all passes, 1 GPU) next to the headline size: device-resident cells/s."""
     import torch
@@ -538,6 +574,10 @@ def ours(args):
             line["config1_4096"] = small_city_leg(dev) if size != 4096 else None
             line["vehicle_step"] = vehicle_bench(dev)
             line["vehicle_step_1M"] = vehicle_bench(dev, n_ticks=60, size=8192, n_vehicles=1000000, cpu_ticks=0, route_len=100, e2e_ticks=20)
+            try:
+                line["route_planning"] = route_planning_leg(dev)
+            except Exception as e:   # noqa: BLE001 -- an extra leg never costs the headline line
+                line["route_planning"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                                     "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
     if world > 1:   # the second hot path on the same shards; a failure or hang here never costs the layout line
