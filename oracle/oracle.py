@@ -1,4 +1,4 @@
-"""ctypes front-end of the CPU oracle (oracle/city_oracle.c, oracle/vehicle_oracle.c, oracle/astar_oracle.c).
+"""ctypes front-end of the CPU oracle (oracle/city_oracle.c, oracle/vehicle_oracle.c, oracle/astar_oracle.c, oracle/density_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports it.
@@ -22,7 +22,7 @@ class OCfg(C.Structure):
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("city_oracle.c", "vehicle_oracle.c", "astar_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("city_oracle.c", "vehicle_oracle.c", "astar_oracle.c", "density_oracle.c")]
     if force or not os.path.exists(_LIB) or any(
             os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -304,3 +304,13 @@ class OracleAstar:
             raise ValueError(f"astar oracle error {n}")
         cells = self._out[:n]
         return [(int(c % self.W), int(c // self.W)) for c in cells]
+
+
+def density_map(occupancy_map, is_road_map):
+    """CityModel._update_density_map (city_model.py:1764-1778): float32 [H][W]."""
+    occ = np.ascontiguousarray(np.asarray(occupancy_map) != 0, np.uint8)
+    road = np.ascontiguousarray(np.asarray(is_road_map) != 0, np.uint8)
+    H, W = occ.shape
+    out = np.zeros((H, W), np.float32)
+    lib().oracle_density_map(W, H, _p(occ, C.c_uint8), _p(road, C.c_uint8), _p(out, C.c_float))
+    return out
