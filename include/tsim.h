@@ -381,6 +381,12 @@ tsim_status tsim_astar_batch(const tsim_cfg *cfg, const tsim_astar_maps *maps, c
                              int32_t n_queries, int32_t *path_len, int32_t *path_cells, int32_t max_path,
                              int32_t *err_flag, void *scratch, size_t scratch_bytes, void *stream);
 
+/* CityModel._update_density_map (city_model.py:1764-1778): density[y][x] = occupied cells / road cells of the 21 x 21 window
+   around (x, y), bit for bit what the reference gets from scipy.ndimage.uniform_filter in float32.  Either output may be
+   NULL; density64 is the same values widened, the form tsim_astar_maps.density_map takes.  scratch: 2 bytes per cell.   */
+tsim_status tsim_density_map(const tsim_cfg *cfg, const uint8_t *occupancy, const uint8_t *is_road_map, float *density32,
+                             double *density64, void *scratch, size_t scratch_bytes, void *stream);
+
 /* labels the 4-connected components of mask == 1 (u8 plane) in raster discovery order: component
    table as tsim_layout_label_nothing, plus the label plane (id, 0 elsewhere).  Used for the
    intersection clusters of _create_intersection_light_groups (city_model.py:1587-1650). */

@@ -72,3 +72,19 @@ def test_gpu_astar_matches_oracle_on_a_synthetic_city():
         assert g == want, (sx, sy, gx, gy, flags, ms)
         found += bool(want)
     assert found > 100
+
+
+@pytest.mark.parametrize("seed,shape,p_road,p_occ", [(1, (200, 200), 0.3, 0.1), (2, (64, 150), 0.6, 0.5), (4, (5, 90), 0.2, 1.0), (6, (300, 257), 0.32, 0.02)])
+def test_gpu_density_map_is_bit_exact(seed, shape, p_road, p_occ):
+    """tsim_density_map == the oracle == SciPy's float32 uniform_filter (CityModel._update_density_map), bit for bit."""
+    from oracle import oracle as O
+    from trafficsimulation_b200.pathfinding import GpuAstar
+    rng = np.random.default_rng(seed)
+    H, W = shape
+    road = (rng.random(shape) < p_road).astype(np.uint8)
+    occ = ((rng.random(shape) < p_occ) & (road == 1)).astype(np.uint8)
+    planner = GpuAstar(W, H, occ, np.zeros(shape, np.uint8), road, road, np.full(shape, 15, np.uint8))
+    got = planner.update_density().cpu().numpy()
+    want = O.density_map(occ, road)
+    assert got.dtype == np.float64 and np.array_equal(got, want.astype(np.float64))
+    assert planner.maps["density_map"].data_ptr() == planner._maps_struct().density_map   # the planner reads this plane

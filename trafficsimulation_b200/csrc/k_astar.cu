@@ -10,6 +10,7 @@
 // flight at once.
 #include "common.cuh"
 #include "astar_core.cuh"
+#include "density_core.cuh"
 
 namespace tsim {
 
@@ -46,6 +47,39 @@ __global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
     if (r == AS_ERR_HEAP) { *b.err = 51; b.path_len[i] = 0; }
     else if (r < 0) { *b.err = 50; b.path_len[i] = r; }   // -(cells needed): the caller's max_path is too small
     else b.path_len[i] = r;
+}
+
+// ---- CityModel._update_density_map (city_model.py:1764-1778): what the planner's soft vehicle penalty reads ----------------
+// two passes like SciPy's separable filter: ones per 21-cell COLUMN window (exact integers, one byte per cell and plane), then
+// per cell the sum over a 21-cell ROW window of the float32 values the first pass would have stored (density_core.cuh)
+__global__ void __launch_bounds__(256) density_columns_kernel(int W, int H, const uint8_t *__restrict__ occ, const uint8_t *__restrict__ road,
+                                                              uint8_t *__restrict__ k_occ, uint8_t *__restrict__ k_road) {
+    const long long n = (long long)W * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W);
+        int a = 0, b = 0;
+        for (int yy = max(y - DENS_RADIUS, 0); yy <= min(y + DENS_RADIUS, H - 1); yy++) {
+            const long long j = i + (long long)(yy - y) * W;
+            a += occ[j] != 0; b += road[j] != 0;
+        }
+        k_occ[i] = (uint8_t)a; k_road[i] = (uint8_t)b;
+    }
+}
+
+__global__ void __launch_bounds__(256) density_rows_kernel(int W, int H, const uint8_t *__restrict__ k_occ, const uint8_t *__restrict__ k_road,
+                                                           float *density32, double *density64) {
+    const long long n = (long long)W * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        double so = 0.0, sr = 0.0;
+        for (int xx = max(x - DENS_RADIUS, 0); xx <= min(x + DENS_RADIUS, W - 1); xx++) {
+            so += (double)dens_after_pass1(k_occ[i + (xx - x)]);
+            sr += (double)dens_after_pass1(k_road[i + (xx - x)]);
+        }
+        const float d = dens_ratio(dens_after_pass2(so), dens_after_pass2(sr));
+        if (density32) density32[i] = d;
+        if (density64) density64[i] = (double)d;
+    }
 }
 
 // open-list capacity per query: the reference's arrays hold W * H entries; on city maps the list peaks below a third of the
@@ -102,6 +136,24 @@ extern "C" tsim_status tsim_astar_batch(const tsim_cfg *cfg, const tsim_astar_ma
     TSIM_CUDA(cudaMemsetAsync(b.dist, 0x3F, (size_t)n * 4 * n_queries, cs));   // dist = INF = 0x3F3F3F3F (:118), no parent direction
     TSIM_CUDA(cudaMemsetAsync(b.fov, 0, (size_t)n * n_queries, cs));           // fov_map = 0
     astar_kernel<<<div_up(n_queries, 64), 64, 0, cs>>>(b);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_density_map(const tsim_cfg *cfg, const uint8_t *occupancy, const uint8_t *is_road_map, float *density32,
+                                        double *density64, void *scratch, size_t scratch_bytes, void *stream) {
+    tsim_status st = check_cfg(cfg);
+    if (st != TSIM_OK) return st;
+    if (cfg->win_y0 != 0 || cfg->win_rows != cfg->height) { set_error("tsim_density_map works on the whole grid (no shard windows)"); return TSIM_ERR_UNSUPPORTED; }
+    if (!occupancy || !is_road_map || (!density32 && !density64)) { set_error("tsim_density_map: bad arguments"); return TSIM_ERR_CONFIG; }
+    const long long n = (long long)cfg->width * cfg->height;
+    if (!scratch || scratch_bytes < (size_t)2 * n) { set_error("tsim_density_map needs %lld scratch bytes, got %zu", 2 * n, scratch_bytes); return TSIM_ERR_WORKSPACE; }
+    cudaStream_t cs = (cudaStream_t)stream;
+    uint8_t *k_occ = (uint8_t *)scratch, *k_road = k_occ + n;
+    const int grid = (int)(div_up(n, 256) < 148 * 8 ? div_up(n, 256) : 148 * 8);
+    density_columns_kernel<<<grid, 256, 0, cs>>>(cfg->width, cfg->height, occupancy, is_road_map, k_occ, k_road);
+    TSIM_LAUNCH_CHECK();
+    density_rows_kernel<<<grid, 256, 0, cs>>>(cfg->width, cfg->height, k_occ, k_road, density32, density64);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

@@ -51,6 +51,20 @@ class GpuAstar:
                 raise ValueError(f"{k}: expected {self.H} x {self.W} cells")
             self.maps[k] = t
 
+    def update_density(self):
+        """``CityModel._update_density_map`` (city_model.py:1764-1778) on the device, from the current occupancy and road maps;
+        the result (float64 plane, the reference's float32 values widened) becomes the planner's ``density_map``."""
+        n = self.W * self.H
+        if self.maps.get("density_map") is None:
+            self.maps["density_map"] = torch.empty(n, dtype=torch.float64, device=self.device)
+        if self._scratch is None or self._scratch.numel() < 2 * n:
+            self._scratch = torch.empty(max(2 * n, 1 << 20), dtype=torch.uint8, device=self.device)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.tsim_density_map(C.byref(self.cfg), C.c_void_p(self.maps["occupancy_map"].data_ptr()),
+                                             C.c_void_p(self.maps["is_road_map"].data_ptr()), None, C.c_void_p(self.maps["density_map"].data_ptr()),
+                                             C.c_void_p(self._scratch.data_ptr()), C.c_size_t(self._scratch.numel()), stream))
+        return self.maps["density_map"].view(self.H, self.W)
+
     def _maps_struct(self):
         m = self.maps
         ptr = lambda k: m[k].data_ptr() if m.get(k) is not None else None
