@@ -183,4 +183,127 @@ TSIM_HD int astar_search(const AstarMaps &m, int sx, int sy, int gx, int gy, int
     return 0;
 }
 
+// ---- the same search on a WINDOW of the grid (groundwork for r2; not wired into the kernel yet) --------------------------------
+// A query's work arrays cost 13.5 bytes per cell, which on a 2048 x 2048 city is 56 MB per query although a route between two
+// cells a block apart touches a few hundred cells.  The search restricted to a window [wx0, wx1] x [wy0, wy1] is IDENTICAL to the
+// unrestricted one as long as it never tries to relax a cell outside the window (such a cell would have been pushed, since its
+// dist is still INF): every heap operation before that point is the same.  So: run in the window, and the first time a cell
+// outside it reaches the relaxation test return AS_ERR_WINDOW -- the caller retries with a larger window or the whole grid.
+// w.dist / w.fov hold (wx1 - wx0 + 1) * (wy1 - wy0 + 1) entries; heap entries and the output keep GLOBAL cell indices.
+constexpr int AS_ERR_WINDOW = -0x40000001;
+
+TSIM_HD int astar_search_window(const AstarMaps &m, int sx, int sy, int gx, int gy, int flags, int awareness_range, int maximum_steps,
+                                int wx0, int wy0, int wx1, int wy1, const AstarWork &w, int32_t *out, int out_cap) {
+    static const int8_t DXY[8] = {0, 1, 1, 0, 0, -1, -1, 0};
+    const int W = m.W, H = m.H, ww = wx1 - wx0 + 1;
+    const int start = sy * W + sx, goal = gy * W + gx;
+    const bool respect = flags & AS_RESPECT_AWARENESS, soft = flags & AS_SOFT_OBSTACLES, ignore_flow = flags & AS_IGNORE_FLOW;
+    auto local = [&](int x, int y) { return (y - wy0) * ww + (x - wx0); };
+    auto inside = [&](int x, int y) { return x >= wx0 && x <= wx1 && y >= wy0 && y <= wy1; };
+    if (!inside(sx, sy) || !inside(gx, gy)) return AS_ERR_WINDOW;
+    w.dist[local(sx, sy)] = 0;
+    int heap = 1;
+    w.heap[0] = AsEntry{as_abs(sx - gx) + as_abs(sy - gy), 0, 0, start};
+    w.dir[0] = -1;
+    if (respect) {   // rays are clipped to the window: a cell outside it is never looked up before the search gives up
+        for (int d = 0; d < 4; d++) {
+            const int dx = DXY[2 * d], dy = DXY[2 * d + 1], px = -dy, py = dx;
+            for (int off = -awareness_range + 1; off < awareness_range; off++) {
+                const int x0 = sx + off * px, y0 = sy + off * py;
+                int x = x0, y = y0, step = 0;
+                while (x >= 0 && x < W && y >= 0 && y < H && (m.cell[y * W + x] & ASC_ROAD)) {
+                    if (inside(x, y)) w.fov[local(x, y)] = 1;
+                    step++;
+                    x = x0 + dx * step; y = y0 + dy * step;
+                }
+            }
+        }
+    }
+    while (heap > 0) {
+        const AsEntry top = w.heap[0];
+        const int prev_dir = w.dir[0];
+        heap--;
+        if (heap > 0) {
+            const AsEntry last = w.heap[heap];
+            w.dir[0] = w.dir[heap];
+            int idx = 0;
+            for (;;) {
+                const int left = 2 * idx + 1, right = left + 1;
+                if (left >= heap) break;
+                const AsEntry l = w.heap[left];
+                int smallest = idx;
+                AsEntry pick = last;
+                if (l.f < pick.f) { smallest = left; pick = l; }
+                if (right < heap) {
+                    const AsEntry r = w.heap[right];
+                    if (r.f < pick.f) { smallest = right; pick = r; }
+                }
+                if (smallest == idx) break;
+                w.heap[idx] = pick;
+                idx = smallest;
+            }
+            w.heap[idx] = last;
+        }
+        const int cur = top.ix;
+        const int cx = cur % W, cy = cur / W;
+        if (cur == goal) {
+            int len = 0;
+            for (int x = cx, y = cy; y * W + x != start;) { const int d = (int)(w.dist[local(x, y)] >> 30); x -= DXY[2 * d]; y -= DXY[2 * d + 1]; len++; }
+            if (len > out_cap) return -len;
+            int k = len;
+            for (int x = cx, y = cy; y * W + x != start;) { out[--k] = y * W + x; const int d = (int)(w.dist[local(x, y)] >> 30); x -= DXY[2 * d]; y -= DXY[2 * d + 1]; }
+            return len;
+        }
+        if ((uint32_t)top.g > (w.dist[local(cx, cy)] & AS_COST_MASK)) continue;
+        const int bits = m.cell[cur] & ASC_DIRS;
+        for (int d = 0; d < 4; d++) {
+            const int nx = cx + DXY[2 * d], ny = cy + DXY[2 * d + 1];
+            if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
+            const int ns = top.s + 1;
+            if (ns > maximum_steps) continue;
+            const int nidx = ny * W + nx;
+            const uint32_t c = m.cell[nidx];
+            long long ng = (long long)top.g + 1;
+            if (prev_dir != -1 && d != prev_dir) ng += AS_TURN;
+            if ((bits & (1 << d)) == 0) {
+                if (ignore_flow && (c & ASC_ROAD)) ng += AS_CONTRA;
+                else continue;
+            }
+            const bool in = inside(nx, ny);
+            if (!in && respect) return AS_ERR_WINDOW;        // its field-of-view bit is not held
+            const bool seen = !respect || w.fov[local(nx, ny)] == 1;
+            if ((c & ASC_OCC) && seen) {
+                if (soft) ng += as_dynamic_penalty(m.density ? m.density[nidx] : 0.0);
+                else continue;
+            }
+            if ((c & ASC_STOP) && seen) {
+                if (soft) ng += AS_STOP;
+                else continue;
+            }
+            if (!in) return AS_ERR_WINDOW;                   // the unrestricted search would push this cell
+            if (c & ASC_ROAD) {
+                const int rt = (c >> ASC_RT_SHIFT) & 3;
+                ng += rt == 2 ? AS_R2 : rt == 3 ? AS_R3 : 0;
+            }
+            const int li = local(nx, ny);
+            if (ng < (long long)(w.dist[li] & AS_COST_MASK)) {
+                if (heap >= w.cap) return AS_ERR_HEAP;
+                w.dist[li] = (uint32_t)ng | ((uint32_t)d << 30);
+                const AsEntry e{(int32_t)(ng + as_abs(nx - gx) + as_abs(ny - gy)), (int32_t)ng, ns, nidx};
+                int i = heap;
+                w.dir[i] = (int8_t)d;
+                while (i > 0) {
+                    const int parent = (i - 1) / 2;
+                    const AsEntry pe = w.heap[parent];
+                    if (e.f < pe.f) { w.heap[i] = pe; i = parent; }
+                    else break;
+                }
+                w.heap[i] = e;
+                heap++;
+            }
+        }
+    }
+    return 0;   // no route, and the search never left the window: the unrestricted search finds none either
+}
+
 }  // namespace tsim
