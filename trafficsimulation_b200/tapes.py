@@ -150,3 +150,56 @@ def synth_traffic(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.nda
         rank=np.argsort(rng.random((n_ticks, nv)), axis=1).astype(np.int32),
         ev_tick=spawn_tick.copy(), ev_vehicle=np.arange(nv, dtype=np.int32), ev_off=ev_off, ev_cells=ev_cells,
         rain_map=np.zeros((H, W), np.uint8))
+
+
+def synth_trips(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarray, trips_per_tick: int, n_ticks: int, route_len: int = 80):
+    """Tick tapes for SURVEY.md §8d config 4 in its literal form: `trips_per_tick` vehicle trips INJECTED EVERY TICK (100 k trips
+    over 1000 ticks on the default city), rather than one fleet spawned at tick 0 (`synth_traffic`).
+
+    Every trip is a spawn attempt of its tick on a random road cell (with replacement: an attempt on an occupied cell fails,
+    as in the reference, city_model.py:1897-1918) with a pre-planned route like `synth_traffic`'s.  The activation order of a
+    tick is an affine permutation `(a_t * v + b_t) mod P` of the vehicle indices (any order is a valid tape; this one costs no
+    sort of a 1000 x 100 000 matrix).  Returns the tape dict consumed by `GpuTraffic` and the tick oracle."""
+    rng = np.random.default_rng(seed)
+    D = dirs.reshape(-1).astype(np.int64)
+    road = np.flatnonzero((D & 0xF) != 0)
+    nv0 = trips_per_tick * n_ticks
+    base = synth_traffic(seed, W, H, cell_type, dirs, 0, 1, route_len=route_len)   # empty tapes with the right keys
+    origin = rng.choice(road, size=nv0, replace=True).astype(np.int64)
+    step_x, step_y = np.array([0, 1, 0, -1]), np.array([1, 0, -1, 0])
+    pos, last_dir, alive = origin.copy(), np.full(nv0, -1, np.int64), np.ones(nv0, bool)
+    cols = []
+    for _ in range(route_len):
+        d = D[pos]
+        n = (d >> 12) & 7
+        pick = (rng.random(nv0) * np.maximum(n, 1)).astype(np.int64)
+        choice = (d >> (4 + 2 * pick)) & 3
+        uturn = (choice == (last_dir + 2) % 4) & (last_dir >= 0) & (n > 1)
+        choice = np.where(uturn, (d >> (4 + 2 * ((pick + 1) % np.maximum(n, 1)))) & 3, choice)
+        nx, ny = pos % W + step_x[choice], pos // W + step_y[choice]
+        ok = alive & (n > 0) & (nx >= 0) & (nx < W) & (ny >= 0) & (ny < H)
+        nxt = np.where(ok, ny * W + nx, pos)
+        ok &= (D[nxt] & 0xF) != 0
+        nxt = np.where(ok, nxt, pos)
+        alive = ok
+        cols.append(np.where(ok, nxt, -1).astype(np.int32))
+        pos = nxt
+        last_dir = np.where(ok, choice, last_dir)
+    route = np.stack(cols, 1)
+    length = (route >= 0).sum(1)
+    tick_of = np.repeat(np.arange(n_ticks, dtype=np.int32), trips_per_tick)
+    target = route[np.arange(nv0), np.maximum(length - 1, 0)]
+    keep = (length >= 1) & (target != origin)
+    origin, route, length, target, tick_of = origin[keep], route[keep], length[keep], target[keep], tick_of[keep]
+    nv = len(origin)
+    ev_off = np.zeros(nv + 1, np.int64)
+    ev_off[1:] = np.cumsum(length)
+    P = 2147483647                                        # prime > any vehicle count: v -> (a v + b) mod P is injective
+    a = rng.integers(1, P, size=(n_ticks, 1), dtype=np.int64)
+    b = rng.integers(0, P, size=(n_ticks, 1), dtype=np.int64)
+    rank = ((a * np.arange(nv, dtype=np.int64)[None, :] + b) % P).astype(np.int32)
+    base.update(spawn_tick=tick_of, origin=origin.astype(np.int32), target=target.astype(np.int32),
+                speed=rng.integers(1, 6, size=(n_ticks, nv), dtype=np.uint8), malfunction=np.zeros((n_ticks, nv), np.uint8), rank=rank,
+                ev_tick=tick_of.copy(), ev_vehicle=np.arange(nv, dtype=np.int32), ev_off=ev_off, ev_cells=route[route >= 0].astype(np.int32),
+                rain_map=np.zeros((H, W), np.uint8))
+    return base
