@@ -1,5 +1,6 @@
-"""Full-size cities (BASELINE.json configs[1] 4096^2 and configs[2] 16384^2), where the CPU oracle is too slow to be
-the checker: size-independent properties of the finished city, computed on the device with plain torch ops."""
+"""Full-size cities (BASELINE.json configs[1] 4096^2 and configs[2] 16384^2), the sizes bench.py times: the finished city is
+compared with the C oracle byte for byte (planes, maps, link tables: a few seconds of CPU at 4096^2, about a minute at
+16384^2), and checked for size-independent properties computed on the device with plain torch ops."""
 import numpy as np
 import pytest
 import torch
@@ -135,3 +136,41 @@ def test_sharded_equals_single_at_4096():
     ma, mb = sh1.maps_host(), sh4.maps_host()
     for k in ma:
         assert np.array_equal(ma[k], mb[k]), k
+
+
+def _oracle_city(size, seed, tz, tc, te):
+    """The C oracle on the inputs the GPU run consumed (band lists from the same generator, the same three tapes)."""
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    hb, vb = tapes.synth_bands(seed, width=size, height=size)
+    oc = O.OracleCity(O.make_cfg(width=size, height=size, fast_reach=1), hb, vb)
+    oc.run_all(tz, tc, te, carve=True)
+    return oc
+
+
+@pytest.mark.parametrize("size", [4096, 16384])
+def test_full_size_city_equals_oracle(size):
+    """The benchmarked workload itself (seed 4096, carve + lights + maps) against the oracle: every plane, every derived map and
+    the three link tables, bit for bit.  The carve tape is the one bench.py uses (drawn on the device from the blob table, one
+    row per blob id); the oracle discovers the blobs itself, so a wrong table or id order cannot cancel out."""
+    seed = 4096
+    sh, tz, tc, te = _city(size, seed)
+    L = sh.shards[0]
+    sh.generate(tz, tc, te)
+    torch.cuda.synchronize()
+    oc = _oracle_city(size, seed, tz.cpu().numpy(), tc[0][:-1].cpu().numpy(), te.cpu().numpy())
+    assert oc.n_blocks == sh.n_blocks
+    got, want = L.planes_host(), oc.planes()
+    for f in ("cell_type", "dirs", "aux", "block_id"):
+        same = np.array_equal(got[f], want[f])
+        if not same:
+            bad = np.argwhere(got[f] != want[f])
+            raise AssertionError((f, len(bad), [(int(y), int(x), int(want[f][y, x]), int(got[f][y, x])) for y, x in bad[:8]]))
+    del got
+    gm, om = L.maps_host(), oc.simple_maps()
+    for k in om:
+        assert np.array_equal(gm[k], om[k]), k
+    del gm, om
+    gl, ol = L.light_links_host(), oc.links
+    for k in ("lights", "ctrl", "incoming"):
+        assert np.array_equal(gl[k], ol[k]), ("links", k, len(gl[k]), len(ol[k]))

@@ -52,125 +52,200 @@ def bands_from_array(arr):
     return [(int(s), int(e), f"R{int(t)}", DIR_NAMES[int(d)] if int(d) >= 0 else "") for s, e, t, d in np.asarray(arr).reshape(-1, 4)]
 
 
-def fill_model_from_planes(model, planes, links, hbands=None, vbands=None):
+def _defaults(defaults=None):
+    """The reference's own vocabulary: ``Simulation.config.Defaults`` of the process this runs in, unless the caller hands one in."""
+    if defaults is not None:
+        return defaults
+    from Simulation.config import Defaults
+    return Defaults
+
+
+def fill_model_from_planes(model, planes, links, hbands=None, vbands=None, window=None, defaults=None):
     """planes: numpy [H,W] ``cell_type`` u8, ``dirs`` u16, ``aux`` u8, ``block_id`` i32; links: ``lights`` [n] cell
     indices, ``ctrl`` / ``incoming`` [m,2] (light cell, cell) pairs (``GpuCityLayout.light_links_host()``);
     hbands / vbands: the band lists (int32 [n,4]) the city was built from -- the light groups read them
-    (intersection_light_group.py:190)."""
+    (intersection_light_group.py:190).
+
+    ``window = (x0, y0, x1, y1)``: materialise ``CellAgent`` objects only for that rectangle (a front-end's viewport on a
+    city too large to hold one Python object per cell); the trackers and ``_blocks_data`` always cover the whole city.
+
+    Everything that can be decided per plane is decided with numpy on the planes (type names and direction lists through
+    look-up tables, the sparse sets -- controlled roads, lights, highway ends, tracker sets, block regions and rings -- by
+    ``flatnonzero`` / sorting); the only per-cell Python work left is the reference's own ``place_cell`` call
+    (city_model.py:1864-1870), which is what creates the Mesa agent."""
     if hbands is not None:
         model.horizontal_bands = bands_from_array(hbands)
     if vbands is not None:
         model.vertical_bands = bands_from_array(vbands)
-    from Simulation.config import Defaults   # the reference's own vocabulary (this runs inside its process)
+    Defaults = _defaults(defaults)
     zones = list(Defaults.ZONES)
-    road_like = set(Defaults.ROAD_LIKE_TYPES)
-    T, D, A, B = planes["cell_type"], planes["dirs"], planes["aux"], planes["block_id"]
+    T, D, A, B = (np.asarray(planes[k]) for k in ("cell_type", "dirs", "aux", "block_id"))
     H, W = T.shape
-    zone_names = set(Defaults.AVAILABLE_CITY_BLOCKS) | {"Empty"}
+    x0, y0, x1, y1 = (0, 0, W, H) if window is None else window
+    code_of = {z: i for i, z in enumerate(zones)}
+    road_like = np.zeros(len(zones), bool)
+    for z in list(Defaults.ROAD_LIKE_TYPES) + ["ControlledRoad"]:
+        road_like[code_of[z]] = True
+    is_zone = np.zeros(len(zones), bool)
+    for z in list(Defaults.AVAILABLE_CITY_BLOCKS) + ["Empty"]:
+        is_zone[code_of[z]] = True
+    # ---- cells of the window: one place_cell each, attributes from look-up tables
+    dir_lut = {}
     cells = {}
-    blocks = {}
-    model._intersection_cells = set()
-    model._ring_road_cells = set()
-    model._road_cells = set()
-    for y in range(H):
-        for x in range(W):
-            name = zones[int(T[y, x])]
-            model.place_cell(x, y, name, f"{name}_{x}_{y}")
-            c = model.get_cell_contents(x, y)[0]
+    place, get = model.place_cell, model.get_cell_contents
+    for y in range(y0, y1):
+        trow, drow = T[y].tolist(), D[y].tolist()
+        for x in range(x0, x1):
+            name = zones[trow[x]]
+            place(x, y, name, f"{name}_{x}_{y}")
+            c = get(x, y)[0]
             cells[(x, y)] = c
-            code = int(D[y, x])
+            code = drow[x]
             if code:
-                c.directions = _decode_dirs(code)
-            a = int(A[y, x])
-            if name == "ControlledRoad":
-                c.road_type = zones[a & AUX_ORIG]
-                c.base_color = Defaults.ZONE_COLORS.get(c.road_type)
-                model.controlled_roads.append(c)
-            elif name == "TrafficLight":
-                model.traffic_lights.append(c)
-            elif name in ("HighwayEntrance", "HighwayExit"):
+                d = dir_lut.get(code)
+                if d is None:
+                    d = dir_lut[code] = _decode_dirs(code)
+                c.directions = list(d)
+    cell_at = cells.get
+
+    def each(mask):
+        ys, xs = np.nonzero(mask)
+        return zip(xs.tolist(), ys.tolist())
+    # ---- sparse per-type attributes and tracker lists (raster order)
+    for x, y in each(T == code_of["ControlledRoad"]):
+        c = cell_at((x, y))
+        if c is not None:
+            c.road_type = zones[int(A[y, x]) & AUX_ORIG]
+            c.base_color = Defaults.ZONE_COLORS.get(c.road_type)
+            model.controlled_roads.append(c)
+    for x, y in each(T == code_of["TrafficLight"]):
+        c = cell_at((x, y))
+        if c is not None:
+            model.traffic_lights.append(c)
+    for name, tracker in (("HighwayEntrance", model.highway_entrances), ("HighwayExit", model.highway_exits)):
+        for x, y in each(T == code_of[name]):
+            c = cell_at((x, y))
+            if c is not None:
                 c.highway_orientation = "horizontal" if y in (0, H - 1) else "vertical"
                 c.highway_id = f"highway_{c.highway_orientation}"
-                (model.highway_entrances if name == "HighwayEntrance" else model.highway_exits).append(c)
-            if a & AUX_EVER:
-                model._intersection_cells.add((x, y))
-            if a & AUX_RING:
-                model._ring_road_cells.add((x, y))
-            if name in road_like or name == "ControlledRoad":
-                model._road_cells.add((x, y))
-            b = int(B[y, x])
-            if b > 0 and name in zone_names:
-                info = blocks.setdefault(b, {"block_id": b, "block_type": name, "region": [], "ring": set()})
-                info["region"].append((x, y))
-    # blocks in id order; ring = 4-neighbours of the region outside it (:795-800)
+                tracker.append(c)
+    model._intersection_cells = set(each((A & AUX_EVER) != 0))
+    model._ring_road_cells = set(each((A & AUX_RING) != 0))
+    model._road_cells = set(each(road_like[T]))
+    # ---- blocks in id order: region = the zone cells carrying the id (raster order), ring = their 4-neighbours outside (:795-800)
+    zone_cell = is_zone[T] & (B > 0)
+    flat_b = np.where(zone_cell, B, 0).reshape(-1)
+    order = np.argsort(flat_b, kind="stable")
+    order = order[np.searchsorted(flat_b[order], 1):]
+    ids, first = np.unique(flat_b[order], return_index=True)
+    bounds = list(first) + [len(order)]
+    ring_pairs = []
+    Bz = np.where(zone_cell, B, 0)
+    for dy, dx in ((0, 1), (0, -1), (1, 0), (-1, 0)):
+        src = Bz[max(0, -dy): H - max(0, dy), max(0, -dx): W - max(0, dx)]
+        dst = Bz[max(0, dy): H - max(0, -dy), max(0, dx): W - max(0, -dx)]
+        ys, xs = np.nonzero((src > 0) & (dst != src))
+        ring_pairs.append(np.stack([src[ys, xs].astype(np.int64), ys + max(0, dy), xs + max(0, dx)], 1))
+    ring_all = np.unique(np.concatenate(ring_pairs, 0), axis=0) if ring_pairs else np.zeros((0, 3), np.int64)
+    ring_first = np.searchsorted(ring_all[:, 0], ids) if len(ring_all) else np.zeros(len(ids), np.int64)
+    ring_last = np.searchsorted(ring_all[:, 0], ids, side="right") if len(ring_all) else np.zeros(len(ids), np.int64)
     model._blocks_data = []
-    for b in sorted(blocks):
-        info = blocks[b]
-        reg = set(info["region"])
-        for (x, y) in info["region"]:
-            for nx, ny in ((x + 1, y), (x - 1, y), (x, y + 1), (x, y - 1)):
-                if 0 <= nx < W and 0 <= ny < H and (nx, ny) not in reg:
-                    info["ring"].add((nx, ny))
-        info["ring"] = sorted(info["ring"])
-        model._blocks_data.append(info)
-    btype = {b: blocks[b]["block_type"] for b in blocks}
-    for (x, y), c in cells.items():
-        if c.cell_type == "BlockEntrance":
+    btype = {}
+    for k, b in enumerate(ids.tolist()):
+        cell_idx = order[bounds[k]: bounds[k + 1]]
+        ys, xs = np.divmod(cell_idx, W)
+        name = zones[int(T[ys[0], xs[0]])]
+        btype[b] = name
+        ring = ring_all[ring_first[k]: ring_last[k]]
+        model._blocks_data.append({"block_id": b, "block_type": name, "region": list(zip(xs.tolist(), ys.tolist())),
+                                   "ring": sorted(zip(ring[:, 2].tolist(), ring[:, 1].tolist()))})
+    for x, y in each(T == code_of["BlockEntrance"]):
+        c = cell_at((x, y))
+        if c is not None:
             b = int(B[y, x])
             c.block_id = b
             c.block_type = btype.get(b)
             model.block_entrances.append(c)
-    # lights: controlled blocks, assigned lane cells, cell.light
+    # ---- lights: controlled blocks, assigned lane cells, cell.light
     lights = np.asarray(links["lights"]).reshape(-1)
-    for li in lights:
-        model.stop_map[int(li) // W, int(li) % W] = 0
-    for li, ci in np.asarray(links["ctrl"]).reshape(-1, 2):
-        tl, road = cells[(int(li) % W, int(li) // W)], cells[(int(ci) % W, int(ci) // W)]
-        tl.controlled_blocks.append(road)
-        road.light = tl
-    for li, ci in np.asarray(links["incoming"]).reshape(-1, 2):
-        tl, lane = cells[(int(li) % W, int(li) // W)], cells[(int(ci) % W, int(ci) // W)]
-        tl.assigned_incoming_road_blocks.append(lane)
-        if int(A[int(ci) // W, int(ci) % W]) & AUX_LIGHT:
-            lane.light = tl
+    if len(lights):
+        model.stop_map[lights // W, lights % W] = 0
+    for li, ci in np.asarray(links["ctrl"]).reshape(-1, 2).tolist():
+        tl, road = cell_at((li % W, li // W)), cell_at((ci % W, ci // W))
+        if tl is not None and road is not None:
+            tl.controlled_blocks.append(road)
+            road.light = tl
+    inc = np.asarray(links["incoming"]).reshape(-1, 2)
+    has_light = (A.reshape(-1)[inc[:, 1]] & AUX_LIGHT) != 0 if len(inc) else np.zeros(0, bool)
+    for (li, ci), keep in zip(inc.tolist(), has_light.tolist()):
+        tl, lane = cell_at((li % W, li // W)), cell_at((ci % W, ci // W))
+        if tl is not None and lane is not None:
+            tl.assigned_incoming_road_blocks.append(lane)
+            if keep:
+                lane.light = tl
     return cells
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _draw_carve_tape(model, table):
+def _draw_carve_tape(model, table, defaults=None):
     """The draws of _carve_subblock_roads (city_model.py:649-682) for the blobs of `table` (minx, miny, maxx, maxy, size, root),
-    in discovery order, with the global `random` module exactly as the reference calls it."""
-    from Simulation.config import Defaults
+    in discovery order, with the global `random` module exactly as the reference calls it (same calls, same arguments,
+    same order, including the up-to-20 pivot attempts and their side tests)."""
     ms = model.min_subblock_spacing
-    chance = getattr(model, "subblock_chance", Defaults.SUBBLOCK_CHANGE)
+    chance = getattr(model, "subblock_chance", None)
+    if chance is None:
+        chance = _defaults(defaults).SUBBLOCK_CHANGE
     rows = np.zeros((len(table), 8), np.int32)
     code = {"N": 0, "E": 1, "S": 2, "W": 3}
-    for i, (minx, miny, maxx, maxy, size, _root) in enumerate(table.tolist()):
+    for i, (minx, miny, maxx, maxy, _size, _root) in enumerate(np.asarray(table).tolist()):
         if random.random() > chance:                      # :649
             continue
         rows[i, 0] = 1
         w, h = maxx - minx + 1, maxy - miny + 1
         if w < 2 * ms + 1 or h < 2 * ms + 1:              # :655
             continue
+        accepted = False
         for attempt in range(20):                         # :659-675
             px, py = random.randint(minx + ms, maxx - ms), random.randint(miny + ms, maxy - ms)
             hd, vd = random.choice(["W", "E"]), random.choice(["N", "S"])
             rows[i, 7] = attempt + 1
-            rows[i, 2:6] = (px, py, code[hd], code[vd])
-            break                                         # a pivot inside [min+ms, max-ms] always passes the side tests
+            small_w = (px - minx) if hd == "W" else (maxx - px)
+            small_h = (py - miny) if vd == "S" else (maxy - py)
+            if small_w >= ms and small_h >= ms:
+                rows[i, 2:6] = (px, py, code[hd], code[vd])
+                accepted = True
+                break
+        if not accepted:
+            continue
         leg = random.choice([("horizontal", "vertical"), ("vertical", "horizontal")])   # :682
         rows[i, 1] = 1
         rows[i, 6] = 1 if leg[0] == "horizontal" else 0
     return rows
 
 
-def build_layout_on_gpu(model, tapes=None, device="cuda:0"):
+def _draw_zone_tape(table, defaults=None):
+    """One ``random.choices`` per block with a bounding box of at least 3 x 3, in block-id order (city_model.py:775-781);
+    `table` = the component table of the labelling right before the zoning pass."""
+    Defaults = _defaults(defaults)
+    types = Defaults.AVAILABLE_CITY_BLOCKS
+    weights = [Defaults.CITY_BLOCK_CHANCE[bt] for bt in types]
+    tab = np.asarray(table)
+    tz = np.zeros(max(len(tab), 1), np.uint8)
+    for i in range(len(tab)):
+        if tab[i, 2] - tab[i, 0] + 1 >= 3 and tab[i, 3] - tab[i, 1] + 1 >= 3:
+            tz[i] = types.index(random.choices(types, weights=weights, k=1)[0])
+    return tz
+
+
+def build_layout_on_gpu(model, tapes=None, device="cuda:0", window=None, defaults=None):
     """Run every layout pass of ``CityModel.__init__`` (:125-139) on the GPU and fill ``model``'s grid.
 
     ``tapes``: optional dict with ``hbands``, ``vbands``, ``tape_zone``, ``tape_carve``, ``tape_entrance`` (a recorded
     reference run, oracle/refharness) -- replayed verbatim.  Without it the decisions are drawn here.
+    ``window``: see ``fill_model_from_planes``.  ``defaults``: the reference's ``Defaults`` (imported from
+    ``Simulation.config`` when omitted).
     """
-    from Simulation.config import Defaults
+    Defaults = _defaults(defaults)
     from .bands import BandParams, bands_to_array, make_city_bands
     from .layout import GpuCityLayout
     kw = dict(width=model.width, height=model.height, wall_thickness=model.wall_thickness,
@@ -201,20 +276,13 @@ def build_layout_on_gpu(model, tapes=None, device="cuda:0"):
             tc = tapes["tape_carve"]
         else:
             _, table = city.label_nothing()
-            tc = _draw_carve_tape(model, table.cpu().numpy())
+            tc = _draw_carve_tape(model, table.cpu().numpy(), Defaults)
         city._carve_subblock_roads(tc)
     if tapes is not None:
         tz, te = tapes["tape_zone"], tapes["tape_entrance"]
     else:
-        # one random.choices per block with a bounding box of at least 3 x 3, in block-id order (:781)
-        n, table = city.label_nothing()
-        tab = table.cpu().numpy()
-        types = Defaults.AVAILABLE_CITY_BLOCKS
-        weights = [Defaults.CITY_BLOCK_CHANCE[bt] for bt in types]
-        tz = np.zeros(max(n, 1), np.uint8)
-        for i in range(n):
-            if tab[i, 2] - tab[i, 0] + 1 >= 3 and tab[i, 3] - tab[i, 1] + 1 >= 3:
-                tz[i] = types.index(random.choices(types, weights=weights, k=1)[0])
+        _, table = city.label_nothing()
+        tz = _draw_zone_tape(table.cpu().numpy(), Defaults)
         te = None                                          # first of the longest runs (see the module docstring)
     city._flood_fill_blocks_storing_data(tz)
     city._eliminate_dead_ends()
@@ -222,5 +290,92 @@ def build_layout_on_gpu(model, tapes=None, device="cuda:0"):
     city._final_place_block_entrances(te)
     city._remove_invalid_intersection_directions(); city._add_entrance_directions()
     city._add_traffic_lights()
-    fill_model_from_planes(model, city.planes_host(), city.light_links_host(), hb, vb)
+    fill_model_from_planes(model, city.planes_host(), city.light_links_host(), hb, vb, window=window, defaults=Defaults)
     return city
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class GpuTickMirror:
+    """The tick side of the seam: ``CityModel.step()`` (city_model.py:1831-1860) with the vehicle CA and the light groups on
+    the device.
+
+        mirror = GpuTickMirror(model, sim, vehicles)      # sim: GpuTraffic / ShardedTraffic built from the model's tapes
+        mirror.gpu_step(n)                                # instead of model.schedule.step() n times
+        mirror.sync_to_model()                            # only when a front-end / statistic reads the Python objects
+
+    ``gpu_step`` advances the device state and ``model.step_count`` and nothing else: no Python object is touched per tick.
+    ``sync_to_model`` writes the device state back into the reference's own containers, the way its own movement code leaves
+    them (city_model.py:1897-1963, vehicle_base.py:521-532): ``occupancy_map`` / ``stop_map`` / ``stuck_map`` (numpy [H, W]),
+    and per vehicle ``pos`` (through ``model.move_vehicle`` bookkeeping: ``grid.move_agent``), ``current_speed``, ``base_speed``,
+    ``is_stuck``, ``stuck_ticks``, ``direction``, ``is_in_malfunction``; vehicles that arrived are removed through
+    ``model.remove_vehicle``, vehicles the device spawned are placed through ``model.place_vehicle`` (the caller supplies them
+    through ``vehicles``: spawn-attempt index -> VehicleAgent, or a factory called with the attempt index).
+    """
+
+    DIRS = ("N", "E", "S", "W")
+
+    def __init__(self, model, sim, vehicles=None, vehicle_factory=None):
+        self.model, self.sim = model, sim
+        self.vehicles = dict(vehicles or {})       # attempt index -> VehicleAgent currently on the model's grid
+        self.factory = vehicle_factory
+        self._placed = set(self.vehicles)
+
+    def gpu_step(self, n=1, check=True):
+        self.sim.step(n, check=check)
+        self.model.step_count = getattr(self.model, "step_count", 0) + n
+
+    def sync_to_model(self):
+        m, st = self.model, self.sim.state_host()
+        W = self.sim.W
+        H = len(m.occupancy_map)
+        for name, key in (("occupancy_map", "occ"), ("stop_map", "stop"), ("stuck_map", "stuckmap")):
+            plane = getattr(m, name)
+            plane[...] = 0
+            cells = st[key]
+            plane[cells // W, cells % W] = 1
+        pos = st["pos"]
+        live = np.flatnonzero(pos >= 0)
+        for v in sorted(self._placed - set(live.tolist())):          # arrived (on_target_reached vehicle_base.py:755-775)
+            ag = self.vehicles.pop(v)
+            self._placed.discard(v)
+            self._untrack(ag)
+        flags = st["vflags"]
+        for v in live.tolist():
+            xy = (int(pos[v] % W), int(pos[v] // W))
+            ag = self.vehicles.get(v)
+            if ag is None:
+                if self.factory is None:
+                    continue
+                ag = self.vehicles[v] = self.factory(v)
+            if v not in self._placed:                                # place_vehicle city_model.py:1897-1908, maps already mirrored
+                m.active_vehicle_agents.append(ag)
+                m.grid.place_agent(ag, xy)
+                if hasattr(m, "schedule"):
+                    m.schedule.add(ag)
+                self._placed.add(v)
+            elif tuple(ag.pos) != xy:                                # move_vehicle :1945-1963
+                m.grid.move_agent(ag, xy)
+            ag.pos = xy
+            f = int(flags[v])
+            ag.base_speed = int(st["base_speed"][v])
+            ag.is_stuck = bool(f & 1)
+            ag.is_in_malfunction = bool(f & 2)
+            ag.stuck_ticks = int(st["stuck_ticks"][v])
+            d = (f >> 2) - 1
+            ag.direction = self.DIRS[d] if d >= 0 else None
+        assert H * W == m.occupancy_map.size
+        return st
+
+    def _untrack(self, ag):
+        m = self.model
+        if ag in m.active_vehicle_agents:
+            m.active_vehicle_agents.remove(ag)
+        m.grid.remove_agent(ag)
+        if hasattr(m, "schedule") and ag in getattr(m.schedule, "agents", ()):
+            m.schedule.remove(ag)
+
+
+def gpu_step(model, n=1):
+    """``CityModel.step`` with the backend switch on: ``model._tsim_mirror`` is the ``GpuTickMirror`` the
+    constructor hook installed."""
+    model._tsim_mirror.gpu_step(n)
