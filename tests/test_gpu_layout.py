@@ -125,9 +125,42 @@ def test_reach_fallback_kernel_gives_the_same_city(n_alt, monkeypatch):
     """The reachability closure enqueues a fixed number of alternations and leaves the rest to the persistent cooperative
     kernel; with 0 / 1 / 2 enqueued alternations that kernel does (almost) all the work and the result must not change."""
     monkeypatch.setenv("TSIM_REACH_ALTERNATIONS", n_alt)
+    monkeypatch.setenv("TSIM_LIGHTS_STAGES", "3")   # no local searches: every undecided `leads_to` is read from the planes
     path = [p for p in layout_fixtures() if "s7_carve" in p][0]
     g = load(path)
     lockstep(g["meta"]["cfg"], g["hbands"], g["vbands"], g["tape_zone"], g["tape_carve"], g["tape_entrance"])
+
+
+LEADS_TO_FIXTURES = ("default12345", "s11_ringR1", "s15_96x128", "s16_64_carve", "s24_400x300_carve", "s13_noopt")
+
+
+@pytest.mark.parametrize("stages", ["1", "2", "3"])
+@pytest.mark.parametrize("name", LEADS_TO_FIXTURES)
+def test_leads_to_search_stages_agree(name, stages, monkeypatch):
+    """`leads_to` beyond the lane itself is settled by Z witnesses, then window closures, then the reachability planes of the
+    whole window (k_lights.cu).  With the first, the second or both local stages switched off the later ones must build the
+    same city: the fixtures hold ring corners (window closures), opposite carriageways (Z witnesses) and unreachable lanes
+    (only the planes can say "False")."""
+    monkeypatch.setenv("TSIM_LIGHTS_STAGES", stages)
+    g = load([p for p in layout_fixtures() if name in p][0])
+    oc, gc = lockstep(g["meta"]["cfg"], g["hbands"], g["vbands"], g["tape_zone"], g["tape_carve"], g["tape_entrance"])
+    got = gc.planes_host()
+    for f in PLANES:
+        assert np.array_equal(got[f], g[f]), ("golden", f)
+
+
+def test_leads_to_stage_counters():
+    """What the stages leave over on a synthetic city: a handful of candidates reach the window closures, none the planes."""
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+    size, seed = 1024, 7
+    hb, vb = tapes.synth_bands(seed, width=size, height=size)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    gc = GpuCityLayout(width=size, height=size)
+    gc.set_bands(hb, vb)
+    gc.generate(tapes.synth_zone_tape(seed, cap), None, np.zeros(cap, np.int32))
+    left = gc.lights_undecided()
+    assert 0 < left["after_z_witness"] < 64 and left["after_window"] == 0, left
 
 
 SYNTH = [

@@ -55,6 +55,7 @@ struct Bits {
 
 struct LightsCtx {
     int W, H, tl_range, cap_lights, fwd, fwd_mode;
+    int stages;           // bit 0: Z witnesses off, bit 1: window closures off (TSIM_LIGHTS_STAGES, tests only)
     int cut_lo, cut_hi;   // rows at the window's low / high end that belong to a neighbour shard (0: that end is a grid edge)
     const uint8_t *T; const uint16_t *D;
     Bits b;
@@ -437,6 +438,9 @@ __global__ void __launch_bounds__(256, 3) reach_transpose_kernel(const u64 *srcA
     }
 }
 
+// ctl[1] = "done": set from the start when nobody needs the planes (*gate == 0), so that every phase kernel returns at once
+__global__ void reach_gate_kernel(int32_t *ctl, const int32_t *gate) { ctl[0] = 0; ctl[1] = (gate && *gate == 0) ? 1 : 0; ctl[2] = 0; ctl[3] = 0; }
+
 __global__ void reach_ctl_kernel(int32_t *ctl, int32_t *changed) {
     if (ctl[1]) return;
     ctl[2]++;
@@ -635,10 +639,45 @@ __device__ __forceinline__ int type_at_time(const LightsCtx &L, int sx, int sy, 
     return L.T[L.at(sx, sy)];
 }
 
+// ---- `leads_to` without reachability planes ---------------------------------------------------------------------------
+// Almost every query of the reverse march is answered by the lane itself (the cell has an arrow onto the cell one step
+// closer, which leads to the road).  What is left (0.6 % of the queries of a synthetic city: lane-change arrows make the
+// march cross to the opposite carriageway, ring corners) asks for a real path a ~> c between two cells at most
+// traffic_light_range + 1 apart on one line, c = a + k * p.  A path that is FOUND is an exact "True" whatever the rest of
+// the city looks like, so the search runs in stages of growing cost and only what no stage can settle (and every
+// "False") falls through to the reachability planes of the whole window:
+//   1. Z witness (one thread): a runs straight along a lateral direction s, crosses to the line of c through k arrows p,
+//      and runs back against s into c:  a -s-> a_j -p-> c_j -(-s)-> c.  On a two-way road this is the U-turn at the next
+//      crossing; it settles all but a handful of queries per city.
+//   2. window closure (one warp): the set of cells that reach c inside a 128 x 128-cell window around c, as the fixed
+//      point of word fills on the arrow bit-planes (rows in registers, neighbours by shuffle).
+constexpr int Z_REACH = 96;      // cells a Z witness may run along the lateral direction
+constexpr int WIN_CELLS = 128;   // side of the closure window (2 words x 128 rows, 4 rows per lane)
+
+__device__ bool z_witness(const LightsCtx &L, int ax, int ay, int cx, int cy, int p, int k) {
+    for (int side = 0; side < 2; side++) {
+        const int s = side ? ((p + 3) & 3) : right_of(p), o = opp_of(s);
+        int x1 = ax, y1 = ay, x2 = cx, y2 = cy;   // a_{j-1}, c_{j-1}
+        for (int j = 1; j <= Z_REACH; j++) {
+            if (!dl_has(L.D[L.at(x1, y1)], s)) break;                 // a's run ends here
+            x1 += dx_of(s); y1 += dy_of(s); x2 += dx_of(s); y2 += dy_of(s);
+            if (!L.has(x1, y1) || !L.has(x2, y2)) break;
+            if (!dl_has(L.D[L.at(x2, y2)], o)) break;                 // c_j must step towards c
+            bool link = true;                                          // k arrows p from a_j land on c_j
+            for (int m = 0, lx = x1, ly = y1; m < k && link; m++, lx += dx_of(p), ly += dy_of(p)) link = dl_has(L.D[L.at(lx, ly)], p);
+            if (link) return true;
+        }
+    }
+    return false;
+}
+
 // Result record of one ControlledRoad: bits 0..39 up to 8 light cells as 5-bit offsets (dy+2)*5+(dx+2),
 // bits 40..59 reverse-scan length per entry of the ordered direction list (5 bits each), bits 60..63 the
 // number of light cells.
-__device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
+// `lt(nb, c, dir, k)` answers nb.leads_to(c) for the cell k steps behind c against arrow `dir` when the lane itself does
+// not: true / false; a functor that cannot decide remembers that and says false (the caller re-evaluates the candidate).
+template <class LT>
+__device__ u64 lights_eval(const LightsCtx &L, int cx, int cy, LT &lt) {
     const int c = L.at(cx, cy);
     const int t = L.T[c];
     const uint32_t rd = L.D[c];
@@ -672,7 +711,7 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
     rec |= (u64)nacc << 60;
     int depth = 0;   // budget shared by all directions (:1528-1548)
     for (int i = 0; i < dl_len(rd); i++) {
-        const int k = opp_of(dl_get(rd, i));
+        const int fd = dl_get(rd, i), k = opp_of(fd);
         int bx = cx + dx_of(k), by = cy + dy_of(k), cnt = 0;
         while (depth <= L.tl_range) {
             if (!L.has(bx, by)) break;
@@ -683,8 +722,8 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
             const uint32_t bd = L.D[nbc];
             if ((conv ? (int)T_CR : bt) != t) break;   // type_at_time
             // the cell one step closer to c leads to c (that is why the march got here), so a cell with an arrow onto it does too;
-            // only the others (lane-change arrows, opposite lanes) need the reachability planes
-            if (!dl_has(bd, dl_get(rd, i)) && !leads_to(L, nbc, c, matters(L, cy))) break;
+            // only the others (lane-change arrows, opposite lanes) need a search
+            if (!dl_has(bd, fd) && !lt(nbc, c, fd, cnt + 1)) break;
             cnt++;
             bx += dx_of(k); by += dy_of(k); depth++;
         }
@@ -692,6 +731,30 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy) {
     }
     return rec;
 }
+
+struct LtPlanes {   // the reachability planes of the window + exact bounded searches (leads_to above)
+    const LightsCtx &L; bool strict;
+    __device__ bool operator()(int nb, int c, int, int) const { return leads_to(L, nb, c, strict); }
+};
+
+struct LtWitness {   // stage 1
+    const LightsCtx &L; bool undecided;
+    __device__ bool operator()(int nb, int c, int fd, int k) {
+        if (!(L.stages & 1) && z_witness(L, nb % L.W, nb / L.W, c % L.W, c / L.W, fd, k)) return true;
+        undecided = true;
+        return false;
+    }
+};
+
+struct LtWindow {   // stage 2: bit (x, y) of `win` (rows y0.., words wx0, wx0 + 1) = that cell reaches c inside the window
+    const LightsCtx &L; const u64 (*win)[2]; int wx0, y0; bool undecided;
+    __device__ bool operator()(int nb, int, int, int) {
+        const int x = nb % L.W - wx0 * 64, y = nb / L.W - y0;
+        if (x >= 0 && x < WIN_CELLS && y >= 0 && y < WIN_CELLS && ((win[y][x >> 6] >> (x & 63)) & 1ull)) return true;
+        undecided = true;   // not reached inside the window: the planes decide (a path may leave the window)
+        return false;
+    }
+};
 
 // cell.py:229-239
 __device__ __forceinline__ bool directly_leads_to(const LightsCtx &L, int from, int to) {
@@ -745,17 +808,143 @@ __device__ __forceinline__ void or_byte(uint8_t *p, uint32_t bits) {
     atomicOr(w, bits << (8 * ((uintptr_t)p & 3)));
 }
 
+// controlled_road.light = tl (:1517) and nb.light = tl for the cells of the reverse march (:1542; lost again if nb itself is
+// converted later -- a fresh CellAgent -- so candidates are skipped): the aux updates a finished record implies.  The cell
+// TYPE of the candidate changes later (cr_type_kernel): other candidates still read the original types.
+__device__ __forceinline__ void apply_aux(const LightsCtx &L, int c, u64 r, uint8_t *A) {
+    const int na = rec_nacc(r);
+    if (na) {
+        const uint32_t rd = L.D[c];
+        const int cx = c % L.W, cy = c / L.W;
+        for (int d = 0; d < dl_len(rd); d++) {
+            const int k = opp_of(dl_get(rd, d));
+            for (int s = 1; s <= rec_cnt(r, d); s++) {
+                const int sx = cx + s * dx_of(k), sy = cy + s * dy_of(k);
+                if (!L.bit(L.b.cr, sx, sy)) or_byte(A + L.at(sx, sy), AUX_LIGHT);
+            }
+        }
+    }
+    A[c] = (uint8_t)((A[c] & (AUX_RING | AUX_EVER)) | (na ? AUX_LIGHT : 0) | L.T[c]);
+}
+
+__device__ __forceinline__ void mark_lights(const LightsCtx &L, int c, u64 r) {
+    for (int u = 0; u < rec_nacc(r); u++) {
+        const int a = rec_acc(r, u, c, L.W);
+        const int ax = a % L.W, ay = a / L.W;
+        atomicOr(L.b.tl + (size_t)ay * L.b.wp + (ax >> 6), 1ull << (ax & 63));
+    }
+}
+
+// MODE 0: every candidate, `leads_to` from Z witnesses; candidates with an undecided query go to the `pend` list.
+// MODE 1: every candidate, from the reachability planes (the staged entry points: the caller has closed them).
+// MODE 2: the candidates of the list `sel` (what stages 1 and 2 left over), from the reachability planes.
+template <int MODE>
 __global__ void __launch_bounds__(128) lights_eval_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
-                                                          u64 *__restrict__ rec) {
-    const int n = *n_cr;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+                                                          u64 *__restrict__ rec, uint8_t *A, const int32_t *__restrict__ sel,
+                                                          int32_t *n_pend, int32_t *pend, int cap_pend) {
+    const int n = MODE == 2 ? min(*n_cr, cap_pend) : *n_cr;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int i = MODE == 2 ? sel[j] : j;
         const int c = cr_cell[i];
-        const u64 r = lights_eval(L, c % L.W, c / L.W);
-        rec[i] = r;
-        for (int u = 0; u < rec_nacc(r); u++) {
-            const int a = rec_acc(r, u, c, L.W);
-            const int ax = a % L.W, ay = a / L.W;
-            atomicOr(L.b.tl + (size_t)ay * L.b.wp + (ax >> 6), 1ull << (ax & 63));
+        if (MODE == 0) {
+            LtWitness lt{L, false};
+            const u64 r = lights_eval(L, c % L.W, c / L.W, lt);
+            rec[i] = r;
+            mark_lights(L, c, r);   // the light cells never depend on `leads_to`
+            if (!lt.undecided) { apply_aux(L, c, r, A); continue; }
+            const int k = atomicAdd(n_pend, 1);
+            if (k < cap_pend) pend[k] = i; else *L.err = 28;
+        } else {
+            LtPlanes lt{L, matters(L, c / L.W)};
+            const u64 r = lights_eval(L, c % L.W, c / L.W, lt);
+            rec[i] = r;
+            if (MODE == 1) mark_lights(L, c, r);
+            apply_aux(L, c, r, A);
+        }
+    }
+}
+
+// Stage 2: one warp per candidate stage 1 left undecided.  B = cells that reach c inside the window = least fixed point of
+//   B |= aE & (B >> 1)  |  aW & (B << 1)  (row fills, one subtraction per word)   |  aN & B[y + 1]  |  aS & B[y - 1].
+// Lane l keeps rows 4l .. 4l + 3 (two words each) of B and of the four arrow planes in registers; the rows of the
+// neighbouring lanes arrive by shuffle.  A converged window goes to shared memory and lane 0 evaluates the candidate.
+__global__ void __launch_bounds__(128) lights_window_kernel(LightsCtx L, const int32_t *__restrict__ n_pend, const int32_t *__restrict__ pend,
+                                                            const int32_t *__restrict__ cr_cell, u64 *__restrict__ rec, uint8_t *A,
+                                                            int32_t *n_pend2, int32_t *pend2, int cap_pend) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    __shared__ u64 s_win[4][WIN_CELLS][2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = min(*n_pend, cap_pend);
+    for (int e = warp; e < n; e += nwarps) {
+        const int i = pend[e];
+        const int c = cr_cell[i], cx = c % L.W, cy = c / L.W;
+        bool undecided = true;
+        u64 r = 0;
+        if (!(L.stages & 2)) {
+            const int wp = L.b.wp;
+            int wx0 = (cx >> 6) - ((cx & 63) < 32 ? 1 : 0);
+            wx0 = max(0, min(wx0, wp - 2));
+            const int y0 = max(0, min(cy - WIN_CELLS / 2, L.H - WIN_CELLS));
+            u64 aN[4][2], aE[4][2], aS[4][2], aW[4][2], b[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    const int y = y0 + lane * 4 + q, wx = wx0 + w;
+                    const bool in = y < L.H && wx < wp;
+                    const size_t o = (size_t)y * wp + wx;
+                    aN[q][w] = in ? L.b.aN[o] : 0ull; aE[q][w] = in ? L.b.aE[o] : 0ull;
+                    aS[q][w] = in ? L.b.aS[o] : 0ull; aW[q][w] = in ? L.b.aW[o] : 0ull;
+                    b[q][w] = (y == cy && wx == (cx >> 6)) ? 1ull << (cx & 63) : 0ull;
+                }
+            // an arrow out of the window must not pull anything in: the top row's N arrows and the bottom row's S arrows see
+            // zeros through the shuffles below, the E / W arrows at the word ends see no carry
+            for (int iter = 0; iter < 1024; iter++) {
+                bool ch = false;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {   // rows: towards higher x through W arrows, towards lower x through E arrows
+                    u64 w0 = fill_up(b[q][0], aW[q][0]);
+                    u64 w1 = fill_up(b[q][1] | ((w0 >> 63) & aW[q][1] & 1ull), aW[q][1]);
+                    w1 = fill_down(w1, aE[q][1]);
+                    w0 = fill_down(w0 | (((w1 & 1ull) << 63) & aE[q][0]), aE[q][0]);
+                    ch |= (w0 != b[q][0]) | (w1 != b[q][1]);
+                    b[q][0] = w0; b[q][1] = w1;
+                }
+#pragma unroll
+                for (int w = 0; w < 2; w++) {   // columns: the row above through N arrows (downwards), the row below through S arrows
+                    u64 up = __shfl_down_sync(FULL, b[0][w], 1);
+                    if (lane == 31) up = 0ull;
+#pragma unroll
+                    for (int q = 3; q >= 0; q--) {
+                        const u64 v = b[q][w] | (aN[q][w] & (q == 3 ? up : b[q + 1][w]));
+                        ch |= v != b[q][w];
+                        b[q][w] = v;
+                    }
+                    u64 dn = __shfl_up_sync(FULL, b[3][w], 1);
+                    if (lane == 0) dn = 0ull;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const u64 v = b[q][w] | (aS[q][w] & (q == 0 ? dn : b[q - 1][w]));
+                        ch |= v != b[q][w];
+                        b[q][w] = v;
+                    }
+                }
+                if (!__any_sync(FULL, ch)) break;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) { s_win[wid][lane * 4 + q][0] = b[q][0]; s_win[wid][lane * 4 + q][1] = b[q][1]; }
+            __syncwarp();
+            if (lane == 0) {
+                LtWindow lt{L, s_win[wid], wx0, y0, false};
+                r = lights_eval(L, cx, cy, lt);
+                undecided = lt.undecided;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (!undecided) { rec[i] = r; apply_aux(L, c, r, A); }
+            else { const int k = atomicAdd(n_pend2, 1); if (k < cap_pend) pend2[k] = i; else *L.err = 28; }
         }
     }
 }
@@ -817,31 +1006,14 @@ __global__ void __launch_bounds__(128) fwd_mark_kernel(LightsCtx L, const int32_
     }
 }
 
-// per candidate: set the has-light bits and convert the cell (place_cell(..., "ControlledRoad") keeps the arrows and
-// remembers the original type, :1455-1459)
-__global__ void __launch_bounds__(128) cr_apply_kernel(LightsCtx L, const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell,
-                                                       const u64 *__restrict__ rec, uint8_t *T, uint8_t *A, int32_t *B) {
+// per candidate: convert the cell (place_cell(..., "ControlledRoad") keeps the arrows and remembers the original type,
+// :1455-1459; the aux side of it was written with the record, apply_aux)
+__global__ void __launch_bounds__(256) cr_type_kernel(const int32_t *__restrict__ n_cr, const int32_t *__restrict__ cr_cell, uint8_t *T, int32_t *B) {
     const int n = *n_cr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const u64 r = rec[i];
         const int c = cr_cell[i];
-        const int na = rec_nacc(r);
-        const int t = T[c];
-        if (na) {
-            // nb.light = tl (:1542); lost again if nb itself is converted later (a fresh CellAgent)
-            const uint32_t rd = L.D[c];
-            const int cx = c % L.W, cy = c / L.W;
-            for (int d = 0; d < dl_len(rd); d++) {
-                const int k = opp_of(dl_get(rd, d));
-                for (int s = 1; s <= rec_cnt(r, d); s++) {
-                    const int sx = cx + s * dx_of(k), sy = cy + s * dy_of(k);
-                    if (!L.bit(L.b.cr, sx, sy)) or_byte(A + L.at(sx, sy), AUX_LIGHT);
-                }
-            }
-        }
+        if (T[c] == T_BE) B[c] = 0;
         T[c] = T_CR;
-        A[c] = (uint8_t)((A[c] & (AUX_RING | AUX_EVER)) | (na ? AUX_LIGHT : 0) | t);   // controlled_road.light = tl (:1517)
-        if (t == T_BE) B[c] = 0;
     }
 }
 
@@ -871,12 +1043,13 @@ __global__ void close_offsets_kernel(const int32_t *n_lights, int32_t *ctrl_off,
 using namespace tsim;
 
 struct LightsWs {   // fixed part of the workspace, shared by the three stages
-    int32_t *scal;   // [0..1] pivot candidates, [4..5] link totals, [8..11] reach flags, [12] n_cr
+    int32_t *scal;   // [0..1] pivot candidates, [4..6] link totals, [8..11] reach flags, [12] n_cr, [13] / [14] candidates left undecided by stage 1 / 2, [16..19] reach control
     Bits bp;
     ReachT rt;
     int32_t *cr_prefix, *tl_prefix, *scan_tmp, *cr_cell;
     u64 *rec;
-    int W, H, wp, cap_cr;
+    int32_t *pend, *pend2;   // candidates whose `leads_to` queries stage 1 (Z witnesses) / stage 2 (window closures) left undecided
+    int W, H, wp, cap_cr, cap_pend;
     long long n, nw;
     size_t end;      // first free byte after the fixed part
 };
@@ -887,6 +1060,7 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
     L.wp = div_up(L.W, 64);
     L.nw = (long long)L.wp * L.H;
     L.cap_cr = (int)(L.n / 4 + 1024);
+    L.cap_pend = (int)(L.n / 64 + 4096);
     char *w = (char *)workspace;
     size_t o = 0;
     auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
@@ -906,6 +1080,8 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
     L.scan_tmp = (int32_t *)take((size_t)(div_up(L.nw, SCAN_TILE) + 1) * 4);
     L.cr_cell = (int32_t *)take((size_t)L.cap_cr * 4);
     L.rec = (u64 *)take((size_t)L.cap_cr * 8);
+    L.pend = (int32_t *)take((size_t)L.cap_pend * 4);
+    L.pend2 = (int32_t *)take((size_t)L.cap_pend * 4);
     L.end = o;
     if (!workspace || o > ws_bytes) { set_error("the lights pass needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
     return TSIM_OK;
@@ -992,8 +1168,9 @@ static int reach_alternations() {
 // launch with its own grid; a phase kernel returns at once when the closure is already complete, so a fixed number of
 // alternations is enqueued without any host round trip.  A city that needs more turns than that is finished by the
 // persistent cooperative kernel (same result, one launch, grid-wide barriers), which otherwise exits immediately.
-extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes,
-                                         void *stream) {
+// `gate` (device scalar, optional): the closure is skipped -- every phase kernel returns at its first instruction -- when *gate == 0
+static tsim_status lights_reach_impl(const tsim_cfg *cfg, int32_t edge_rows, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes,
+                                     void *stream, const int32_t *gate) {
     tsim_status st = lights_check(cfg);
     if (st != TSIM_OK) return st;
     if (!err_flag) { set_error("tsim_lights_reach: NULL err_flag"); return TSIM_ERR_CONFIG; }
@@ -1009,7 +1186,8 @@ extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows,
     int32_t *ctl = L.scal + 16;      // [0] changed, [1] done, [2] alternations
     int32_t *flags = L.scal + 8;     // cooperative kernel's own flags
     TSIM_CUDA(cudaMemsetAsync(flags, 0, 16, cs));
-    TSIM_CUDA(cudaMemsetAsync(ctl, 0, 16, cs));
+    reach_gate_kernel<<<1, 1, 0, cs>>>(ctl, gate);
+    TSIM_LAUNCH_CHECK();
     TSIM_CUDA(cudaMemsetAsync(rt.bdR, 0, (size_t)((char *)rt.cd - (char *)rt.bdR) + wp, cs));   // the four flag arrays are contiguous
     const bool first = edge_rows < 0;
     if (first) {   // transposed arrow planes (kept in the workspace for resumed calls)
@@ -1052,6 +1230,11 @@ extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows,
     return TSIM_OK;
 }
 
+extern "C" tsim_status tsim_lights_reach(const tsim_cfg *cfg, int32_t edge_rows, int32_t *changed, int32_t *err_flag, void *workspace, size_t ws_bytes,
+                                         void *stream) {
+    return lights_reach_impl(cfg, edge_rows, changed, err_flag, workspace, ws_bytes, stream, nullptr);
+}
+
 // byte offsets of the two reachability planes inside the workspace ([win_rows][words_per_row] uint64, bit x & 63 of
 // word x >> 6 = cell x), so that shards can exchange (OR) their halo rows between tsim_lights_reach calls
 extern "C" tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_bytes, size_t *fw_off, size_t *bw_off, int32_t *words_per_row) {
@@ -1066,8 +1249,17 @@ extern "C" tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_b
 }
 
 // stage 3: evaluate the candidates, number the lights, build the link tables, convert the cells
-extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
-                                          size_t ws_bytes, void *stream) {
+// TSIM_LIGHTS_STAGES=<mask> switches search stages off (tests: every stage must give the same city): 1 no Z witnesses, 2 no window closures
+static int lights_stages_off() {
+    const char *e = getenv("TSIM_LIGHTS_STAGES");
+    return (e && *e) ? (atoi(e) & 3) : 0;
+}
+
+// lazy == false: the caller has closed the reachability planes (tsim_lights_seed / tsim_lights_reach) and every `leads_to` is read
+// from them.  lazy == true (tsim_layout_lights): the queries are settled by the staged searches first and the planes are only
+// closed -- inside this call, around this window's own pivot -- when a query is left over.
+static tsim_status lights_finish_impl(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
+                                      size_t ws_bytes, void *stream, bool lazy) {
     tsim_status st = lights_check(cfg);
     if (st != TSIM_OK) return st;
     if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id || !lk || !err_flag || !lk->n_lights || !lk->light_cell || !lk->ctrl_off ||
@@ -1092,10 +1284,24 @@ extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes
     const int list_grid = div_up(cap_cr, 128) < 148 * 16 ? div_up(cap_cr, 128) : 148 * 16;   // grid-stride over the compact list
     const int fwd = cfg->forward_traffic_light_range ? 1 : 0;
     if (fwd && (!lk->out_off || !lk->out_cell || lk->cap_out < 1)) { set_error("forward_traffic_light_range needs the outgoing link table"); return TSIM_ERR_CONFIG; }
-    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, fwd, cfg->forward_intersections_mode, cfg->win_y0 > 0 ? cfg->win_halo : 0,
+    LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, fwd, cfg->forward_intersections_mode, lights_stages_off(), cfg->win_y0 > 0 ? cfg->win_halo : 0,
                 cfg->win_y0 + cfg->win_rows < cfg->height ? cfg->win_halo : 0, p->cell_type, p->dirs, bp, err_flag};
-    lights_eval_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec);
-    TSIM_LAUNCH_CHECK();
+    if (!lazy) {
+        lights_eval_kernel<1><<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->aux, nullptr, nullptr, nullptr, 0);
+        TSIM_LAUNCH_CHECK();
+    } else {
+        int32_t *n_pend = scal + 13, *n_pend2 = scal + 14;
+        lights_eval_kernel<0><<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->aux, nullptr, n_pend, ws.pend, ws.cap_pend);
+        TSIM_LAUNCH_CHECK();
+        lights_window_kernel<<<148 * 4, 128, 0, cs>>>(L, n_pend, ws.pend, cr_cell, rec, p->aux, n_pend2, ws.pend2, ws.cap_pend);
+        TSIM_LAUNCH_CHECK();
+        // whatever is still undecided (and every "False") needs the planes: closed now, or skipped when the list is empty
+        if ((st = tsim_lights_seed(cfg, nullptr, workspace, ws_bytes, stream)) != TSIM_OK) return st;
+        if ((st = lights_reach_impl(cfg, -1, nullptr, err_flag, workspace, ws_bytes, stream, n_pend2)) != TSIM_OK) return st;
+        const int pgrid = div_up(ws.cap_pend, 128) < 148 * 4 ? div_up(ws.cap_pend, 128) : 148 * 4;
+        lights_eval_kernel<2><<<pgrid, 128, 0, cs>>>(L, n_pend2, cr_cell, rec, p->aux, ws.pend2, nullptr, nullptr, ws.cap_pend);
+        TSIM_LAUNCH_CHECK();
+    }
     // 5. lights in ascending cell order
     bit_count_kernel<<<div_up(nw, 256), 256, 0, cs>>>(nw, bp.tl, tl_prefix);
     TSIM_LAUNCH_CHECK();
@@ -1120,18 +1326,21 @@ extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes
         fwd_mark_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->aux);
         TSIM_LAUNCH_CHECK();
     }
-    cr_apply_kernel<<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->cell_type, p->aux, p->block_id);
+    cr_type_kernel<<<(div_up(cap_cr, 256) < 148 * 8 ? div_up(cap_cr, 256) : 148 * 8), 256, 0, cs>>>(n_cr, cr_cell, p->cell_type, p->block_id);
     TSIM_LAUNCH_CHECK();
     tl_apply_kernel<<<(div_up(lk->cap_lights, 256) < 148 * 8 ? div_up(lk->cap_lights, 256) : 148 * 8), 256, 0, cs>>>(lk->n_lights, lk->light_cell, lk->cap_lights, p->cell_type, p->dirs, p->aux);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
 
+extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
+                                          size_t ws_bytes, void *stream) {
+    return lights_finish_impl(cfg, p, lk, err_flag, workspace, ws_bytes, stream, false);
+}
+
 extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag,
                                           void *workspace, size_t ws_bytes, void *stream) {
     tsim_status st;
     if ((st = tsim_lights_prepare(cfg, p, nullptr, err_flag, workspace, ws_bytes, stream)) != TSIM_OK) return st;
-    if ((st = tsim_lights_seed(cfg, nullptr, workspace, ws_bytes, stream)) != TSIM_OK) return st;
-    if ((st = tsim_lights_reach(cfg, -1, nullptr, err_flag, workspace, ws_bytes, stream)) != TSIM_OK) return st;
-    return tsim_lights_finish(cfg, p, lk, err_flag, workspace, ws_bytes, stream);
+    return lights_finish_impl(cfg, p, lk, err_flag, workspace, ws_bytes, stream, true);
 }

@@ -274,6 +274,12 @@ class GpuCityLayout:
         if check:
             self._check_flag("_add_traffic_lights")
 
+    def lights_undecided(self):
+        """Candidates whose `leads_to` queries the search stages of the last `_add_traffic_lights` left undecided: after the Z
+        witnesses (they went to the window closures) and after those (they made the pass close the reachability planes)."""
+        sc = self.workspace[: 64 * 4].view(torch.int32)[13:15].cpu().numpy()   # scalars at the head of the lights workspace
+        return {"after_z_witness": int(sc[0]), "after_window": int(sc[1])}
+
     def _build_simple_maps(self):   # city_model.py:2151
         n = self.width * self.win_rows
         if self.maps is None:
