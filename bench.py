@@ -157,7 +157,7 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()) if any(r[2].replace(".", "", 1).isdigit() for r in rows) else None}
 
 
-def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, route_len=400, e2e_ticks=50):
+def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, route_len=400, e2e_ticks=50, parity_check=True):
     """Second headline metric: agent-updates/s of the vehicle CA tick (BASELINE.json configs[3], in the
     simultaneous-occupancy form SURVEY.md §8d defines: 100k vehicles live at once on a 2048^2 city)."""
     import torch
@@ -199,20 +199,27 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
         sim2.step(1, check=True)
     t1 = time.perf_counter()
     e2e = (sim2.counters()["vehicle_updates"] - e0) / (t1 - t0)
-    # CPU port on the same tapes
-    cpu = None
-    if cpu_ticks > 0:
+    # CPU port on the same tapes: timed on `cpu_ticks` ticks, then run on to the tick the device is at, where the WHOLE state --
+    # every vehicle's position / speed / stuck counter / flags, the three maps, the light groups -- must be identical
+    cpu, parity = None, None
+    if cpu_ticks > 0 or parity_check:
         ora = O.OracleTicks(size, size, tabs, tp, n_ticks)
         ora.run(5)
         live0 = int(ora.a["alive"].sum())
-        t0 = time.perf_counter()
-        upd_cpu = 0
-        for _ in range(cpu_ticks):
-            upd_cpu += int(ora.a["alive"].sum())
-            ora.run(1)
-        cpu_s = time.perf_counter() - t0
-        cpu = {"value": upd_cpu / cpu_s, "unit": "agent-updates/s", "cores": 1, "kind": "port",
-               "sample": f"oracle/vehicle_oracle.c, same tapes, {cpu_ticks} ticks, {live0} live vehicles"}
+        if cpu_ticks > 0:
+            t0 = time.perf_counter()
+            upd_cpu = 0
+            for _ in range(cpu_ticks):
+                upd_cpu += int(ora.a["alive"].sum())
+                ora.run(1)
+            cpu_s = time.perf_counter() - t0
+            cpu = {"value": upd_cpu / cpu_s, "unit": "agent-updates/s", "cores": 1, "kind": "port",
+                   "sample": f"oracle/vehicle_oracle.c, same tapes, {cpu_ticks} ticks, {live0} live vehicles"}
+        if parity_check:
+            ora.run(n_ticks - ora.sim.tick)
+            got, want = sim.state_host(), ora.state()
+            parity = {"parity_checked": bool(all(np.array_equal(got[k], want[k]) for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"))),
+                      "against": f"oracle/vehicle_oracle.c after {n_ticks} ticks: positions, speeds, stuck counters, flags of all {nv} vehicles, occupancy / stop / stuck maps, light-group state"}
     return {"metric": "agent-updates/sec (vehicle CA tick with traffic-light gating)", "value": ups, "unit": "agent-updates/s",
             "config": {"workload": f"{size}x{size} city, {nv} vehicles spawned at tick 0, {ticks} timed ticks in one persistent launch",
                        "groups": sim.n_groups, "lights": sim.n_lights},
@@ -222,7 +229,7 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
             "roofline": {"bound": "hbm", "alg_bytes_per_update": 84, "achieved": round(ups * 84 / 1e9, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(ups * 84 / 1e9 / peak, 5), "peak_source": peak_src,
                          "note": "a tick costs its grid-wide barriers (3 + one per claim sweep + 2), not its bytes (DESIGN.md §4)"},
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "parity": parity}
 
 
 def sharded_vehicle_bench(dev, world, rank, size=4096, per_shard=150000, n_ticks=45, warm=5, route_len=100, halo=128):

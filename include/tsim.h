@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TSIM_ABI_VERSION 2
+#define TSIM_ABI_VERSION 3
 
 /* cell_type codes = index into Defaults.ZONES (Simulation/config.py:74-95) */
 enum tsim_cell_type {
@@ -298,7 +298,19 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
                                                     [6..7] vehicle updates (int64: sum over ticks of the live vehicles on
                                                     own rows), [9] shard-exchange error flag, rest internal           */
     int32_t own_row_lo, own_row_hi;              /* LOCAL rows of the window this shard owns; 0, 0 = the whole window          */
+    /* Working set of the LIVE-LIST kernel (all NULL: the vehicle-indexed kernel, which row-band shards use).  With these
+       the tick iterates a compacted list of the live vehicles instead of the attempt array: a vehicle is a 48-byte record
+       in `recs` that moves to a new slot every tick (warp-aggregated append into the other half), its plan for the tick
+       a 32-byte record in `plans`, and every cell probe reads ONE word of `probe` (occupancy, stop, staged stop and
+       "somebody claimed this cell this tick" tags).  The vehicle SoA above is then only written by tsim_tick_export.  */
+    uint32_t *probe;                             /* [H*W]                                                                      */
+    void *recs;                                  /* [2][n_vehicles] x TSIM_TICK_VREC_BYTES                                     */
+    void *plans;                                 /* [n_vehicles] x TSIM_TICK_PLAN_BYTES                                        */
+    int32_t *ev_stamp, *ev_plen;                 /* [n_vehicles] tick of the vehicle's pending route event, its length         */
+    int64_t *ev_poff;                            /* [n_vehicles] ... and its offset in ev_cells                                */
 } tsim_tick_state;
+#define TSIM_TICK_VREC_BYTES 48
+#define TSIM_TICK_PLAN_BYTES 32
 
 /* zero the maps / vehicle / group state and prepare the scratch planes */
 tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
@@ -307,6 +319,10 @@ tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, con
 /* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME */
 tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                           const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
+
+/* live-list kernel only: scatter the live records into the vehicle SoA of `st` (alive = 0 for everybody else), so that the
+   host reads the same arrays whichever kernel ran */
+tsim_status tsim_tick_export(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, void *stream);
 
 /* ---- row-band shards of the tick (SURVEY.md 8e "Vehicle step"; no reference counterpart: the reference is one process).
    A shard runs tsim_tick_run on its WINDOW (tsim_cfg.win_y0 / win_rows / win_halo): every cell index in

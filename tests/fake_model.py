@@ -107,4 +107,5 @@ def extract_links(model):
     lights = np.array(sorted(idx(t) for t in model.traffic_lights), np.int32)
     ctrl = np.array(sorted((idx(t), idx(c)) for t in model.traffic_lights for c in t.controlled_blocks), np.int32).reshape(-1, 2)
     inc = np.array(sorted((idx(t), idx(c)) for t in model.traffic_lights for c in t.assigned_incoming_road_blocks), np.int32).reshape(-1, 2)
-    return {"lights": lights, "ctrl": ctrl, "incoming": inc}
+    out = np.array(sorted((idx(t), idx(c)) for t in model.traffic_lights for c in t.assigned_outgoing_road_blocks), np.int32).reshape(-1, 2)
+    return {"lights": lights, "ctrl": ctrl, "incoming": inc, "outgoing": out}

@@ -10,7 +10,8 @@ import pytest
 from fake_model import FakeModel, extract_links, extract_planes, fake_defaults
 from golden_util import layout_fixtures, load, PLANES
 
-FIX = [p for p in layout_fixtures() if any(k in p for k in ("default12345", "s14_150x110_carve", "s16_64_carve", "s26_hw4"))]
+FIX = [p for p in layout_fixtures() if any(k in p for k in ("default12345", "s14_150x110_carve", "s16_64_carve", "s26_hw4", "s22_fwd_inrange",
+                                                            "s23_fwd_extra_carve"))]
 
 
 @pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[7:-4])
@@ -19,7 +20,7 @@ def test_fill_round_trips_fixture(path):
     g = load(path)
     m = FakeModel(**g["meta"]["cfg"])
     planes = {k: g[k] for k in PLANES}
-    links = {"lights": g["links_lights"], "ctrl": g["links_ctrl"], "incoming": g["links_incoming"]}
+    links = {"lights": g["links_lights"], "ctrl": g["links_ctrl"], "incoming": g["links_incoming"], "outgoing": g["links_outgoing"]}
     fill_model_from_planes(m, planes, links, g["hbands"], g["vbands"], defaults=fake_defaults())
     H, W = planes["cell_type"].shape
     assert m.place_calls == W * H
@@ -27,7 +28,7 @@ def test_fill_round_trips_fixture(path):
     for f in PLANES:
         assert np.array_equal(got[f], planes[f]), f
     gl = extract_links(m)
-    for k in ("lights", "ctrl", "incoming"):
+    for k in ("lights", "ctrl", "incoming", "outgoing"):
         assert np.array_equal(gl[k], links[k]), k
     # trackers (city_model.py:96-107)
     T = planes["cell_type"]

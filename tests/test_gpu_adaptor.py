@@ -27,7 +27,7 @@ def test_build_layout_on_gpu_fills_the_model_like_the_reference(path):
     for f in PLANES:
         assert np.array_equal(got[f], g[f]), f
     gl = extract_links(m)
-    for k in ("lights", "ctrl", "incoming"):
+    for k in ("lights", "ctrl", "incoming", "outgoing"):
         assert np.array_equal(gl[k], g["links_" + k]), k
     assert len(m._blocks_data) == g["meta"]["n_blocks"]
     assert m.horizontal_bands and m.vertical_bands and m.horizontal_bands[0][2] in ("R1", "R2", "R3")

@@ -19,8 +19,9 @@ def build_city(cfgd, hb, vb, tz, tc, te):
     return city
 
 
+@pytest.mark.parametrize("live_list", [True, False], ids=["live_list", "vehicle_indexed"])
 @pytest.mark.parametrize("path", tick_fixtures(), ids=lambda p: os.path.basename(p)[6:-4])
-def test_gpu_ticks_match_reference_fixture(path):
+def test_gpu_ticks_match_reference_fixture(path, live_list):
     from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
     from trafficsimulation_b200.light_groups import groups_as_cell_lists
     r = load_ticks(path)
@@ -32,7 +33,7 @@ def test_gpu_ticks_match_reference_fixture(path):
     for i, (a, b) in enumerate(zip(mine, r["groups"])):
         for k in a:
             assert np.array_equal(a[k], b[k]), ("group table", i, k)
-    sim = GpuTraffic(r["W"], r["H"], tabs, r, r["n_ticks"], rain_enabled=r["meta"]["rain_enabled"])
+    sim = GpuTraffic(r["W"], r["H"], tabs, r, r["n_ticks"], rain_enabled=r["meta"]["rain_enabled"], live_list=live_list)
     for t in range(r["n_ticks"]):
         sim.step(1)
         compare_tick(t, sim.state_host(), r)
@@ -53,8 +54,9 @@ def test_gpu_ticks_multi_tick_launch_equals_single_ticks():
     compare_tick(r["n_ticks"] - 1, sim.state_host(), r)
 
 
-@pytest.mark.parametrize("size,nveh,algo", [(512, 20000, "QUEUE_ACTUATED"), (768, 60000, "FIXED_TIME")])
-def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo):
+@pytest.mark.parametrize("size,nveh,algo,live_list", [(512, 20000, "QUEUE_ACTUATED", True), (768, 60000, "FIXED_TIME", True),
+                                                       (512, 20000, "FIXED_TIME", False)])
+def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo, live_list):
     """Dense synthetic traffic on a city the reference cannot plan routes for: CUDA vs the pinned C oracle."""
     from oracle import oracle as O
     from trafficsimulation_b200 import tapes
@@ -68,7 +70,7 @@ def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo):
     n_ticks = 50
     tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], nveh, n_ticks, route_len=120, spawn_ticks=5,
                              malfunction_p=0.001)
-    sim = GpuTraffic(size, size, tabs, tp, n_ticks, algo=algo)
+    sim = GpuTraffic(size, size, tabs, tp, n_ticks, algo=algo, live_list=live_list)
     ora = O.OracleTicks(size, size, tabs, tp, n_ticks, algo=0 if algo == "QUEUE_ACTUATED" else 1)
     moved = 0
     prev = None
@@ -110,3 +112,29 @@ def test_gpu_ticks_without_vehicles_cycle_the_lights():
         for k in ("stop", "occ", "groups"):
             assert np.array_equal(got[k], want[k]), (algo, k)
         assert sim.counters()["vehicle_updates"] == 0
+
+
+def test_gpu_ticks_trips_injected_every_tick():
+    """Trips injected every tick over a long run (BASELINE.json configs[3] in miniature): the live list grows and shrinks all the
+    time, attempts pile up on occupied origins and are dropped; the whole state equals the oracle's every few ticks."""
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    size, seed, n_ticks = 256, 21, 160
+    hb, vb = tapes.synth_bands(seed, width=size, height=size)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    city = build_city(dict(width=size, height=size), hb, vb, tapes.synth_zone_tape(seed, cap), None, np.zeros(cap, np.int32))
+    tabs = light_tables_from_layout(city)
+    planes = city.planes_host()
+    tp = tapes.synth_trips(seed, size, size, planes["cell_type"], planes["dirs"], trips_per_tick=40, n_ticks=n_ticks, route_len=60)
+    sim = GpuTraffic(size, size, tabs, tp, n_ticks)
+    ora = O.OracleTicks(size, size, tabs, tp, n_ticks)
+    done = 0
+    for step in (1, 1, 1, 7, 10, 20, 40, 80):
+        sim.step(step)
+        ora.run(step)
+        done += step
+        got, want = sim.state_host(), ora.state()
+        for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"):
+            assert np.array_equal(got[k], want[k]), (done, k)
+    assert done == n_ticks and int((want["pos"] >= 0).sum()) > 0

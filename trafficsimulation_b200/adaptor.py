@@ -62,9 +62,9 @@ def _defaults(defaults=None):
 
 def fill_model_from_planes(model, planes, links, hbands=None, vbands=None, window=None, defaults=None):
     """planes: numpy [H,W] ``cell_type`` u8, ``dirs`` u16, ``aux`` u8, ``block_id`` i32; links: ``lights`` [n] cell
-    indices, ``ctrl`` / ``incoming`` [m,2] (light cell, cell) pairs (``GpuCityLayout.light_links_host()``);
-    hbands / vbands: the band lists (int32 [n,4]) the city was built from -- the light groups read them
-    (intersection_light_group.py:190).
+    indices, ``ctrl`` / ``incoming`` (/ ``outgoing`` with forward_traffic_light_range) [m,2] (light cell, cell) pairs
+    (``GpuCityLayout.light_links_host()``); hbands / vbands: the band lists (int32 [n,4]) the city was built from -- the
+    light groups read them (intersection_light_group.py:190).
 
     ``window = (x0, y0, x1, y1)``: materialise ``CellAgent`` objects only for that rectangle (a front-end's viewport on a
     city too large to hold one Python object per cell); the trackers and ``_blocks_data`` always cover the whole city.
@@ -182,6 +182,15 @@ def fill_model_from_planes(model, planes, links, hbands=None, vbands=None, windo
         if tl is not None and lane is not None:
             tl.assigned_incoming_road_blocks.append(lane)
             if keep:
+                lane.light = tl
+    # forward_traffic_light_range (city_model.py:1550-1584): assigned outgoing cells; `.light` wherever the plane says so
+    out = np.asarray(links["outgoing"]).reshape(-1, 2) if links.get("outgoing") is not None else np.zeros((0, 2), np.int64)
+    out_light = (A.reshape(-1)[out[:, 1]] & AUX_LIGHT) != 0 if len(out) else np.zeros(0, bool)
+    for (li, ci), keep in zip(out.tolist(), out_light.tolist()):
+        tl, lane = cell_at((li % W, li // W)), cell_at((ci % W, ci // W))
+        if tl is not None and lane is not None:
+            tl.assigned_outgoing_road_blocks.append(lane)
+            if keep and lane.light is None:
                 lane.light = tl
     return cells
 

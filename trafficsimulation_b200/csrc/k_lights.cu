@@ -1190,7 +1190,12 @@ static tsim_status lights_reach_impl(const tsim_cfg *cfg, int32_t edge_rows, int
     TSIM_LAUNCH_CHECK();
     TSIM_CUDA(cudaMemsetAsync(rt.bdR, 0, (size_t)((char *)rt.cd - (char *)rt.bdR) + wp, cs));   // the four flag arrays are contiguous
     const bool first = edge_rows < 0;
-    if (first) {   // transposed arrow planes (kept in the workspace for resumed calls)
+    // A gated closure (tsim_layout_lights: only cities with a query the local searches cannot settle need it) is left to the one
+    // persistent kernel below: a city that does not need it pays two launches, not fifty that return at once.
+    const int n_alt = gate ? 0 : reach_alternations();
+    if (n_alt == 0) {
+        // nothing enqueued: the cooperative kernel transposes the arrows itself
+    } else if (first) {   // transposed arrow planes (kept in the workspace for resumed calls)
         reach_transpose_kernel<<<ntiles, 256, tsmem, cs>>>(bp.aN, bp.aS, H, wp, rt.aNt, rt.aSt, W, wpT, rt.bdR, nbx, nby, true, true, false, rt.cd, rt.cd, 0, ctl);
         TSIM_LAUNCH_CHECK();
         TSIM_CUDA(cudaMemsetAsync(rt.cd, 0, wp, cs));   // (the arrow transposition marked its lines; they are not reachability changes)
@@ -1198,7 +1203,6 @@ static tsim_status lights_reach_impl(const tsim_cfg *cfg, int32_t edge_rows, int
         reach_mark_edges_kernel<<<div_up(nbx * nby, 256) < 1184 ? div_up(nbx * nby, 256) : 1184, 256, 0, cs>>>(H, edge_rows, nbx, nby, rt.bdR, rt.rd);
         TSIM_LAUNCH_CHECK();
     }
-    const int n_alt = reach_alternations();
     for (int a = 0; a < n_alt; a++) {
         const bool all = first && a == 0;
         // rows: lines of the row-major planes; a changed word (y, w) marks block (y >> 6, w)

@@ -30,114 +30,11 @@
 //   4 spawner claims (lowest attempt index per free origin cell) + commit of the staged stop_map writes
 //   5 spawns + scatter of the NEXT tick's route events (replayed A* results)
 #include <cooperative_groups.h>
-#include "common.cuh"
+#include "tick_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace tsim {
-
-constexpr int MIN_GREEN = 5, MAX_GREEN = 30, GAP_TICKS = 3, GREEN_DURATION = 20;   // config.py:354-359
-constexpr int AWARENESS = 10, MALFUNCTION_TICKS = 400, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2;   // config.py:279,321,306,263
-constexpr int NO_CLAIM = 0x7fffffff;
-constexpr int MAX_SPEED = 5;          // random.randint(1, 5), vehicle_base.py:112: a vehicle plans at most 5 cells
-constexpr int GEN_PER_TICK = 1024;   // claim generations per tick: sweeps 1..1022, spawner 1023
-typedef unsigned long long u64;
-enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8, S_XERR = 9 /* shard exchange */ };
-
-constexpr int OUTSIDE = -2;          // a tape cell that lies outside this shard's window (host-side translation, tsim.h)
-
-struct TickArgs {
-    int W, H, n_ticks, algo;   // H = rows of the window; every cell index below is LOCAL to the window
-    int own_lo, own_hi;        // local cell range of the rows this shard owns (vehicle_updates counts only those)
-    tsim_light_tables lt;
-    tsim_tick_tapes tp;
-    tsim_tick_state st;
-};
-
-template <class F>
-__device__ __forceinline__ void for_light_cells(const tsim_light_tables &lt, const int32_t *off, const int32_t *lights, int g, F f) {
-    for (int k = off[g]; k < off[g + 1]; k++) {
-        const int l = lights[k];
-        for (int q = lt.tl_off[l]; q < lt.tl_off[l + 1]; q++) f(lt.tl_cells[q]);
-    }
-}
-
-// light group: controller + decision; stop_map writes are staged in `stopw` (atomicMax, priority =
-// group index, then order inside the group) so that concurrent groups reproduce the sequential result
-__device__ void group_decide(const TickArgs &a, int g) {
-    const tsim_light_tables &lt = a.lt;
-    const tsim_tick_state &s = a.st;
-    int cur = s.g_cur[g], pend = s.g_pend[g];
-    if (pend < 0) {
-        if (a.algo == 0) {   // run_queue_actuated :463-494
-            const int qt = ++s.g_qt[g];
-            int ns_q = 0, ew_q = 0;
-            for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += s.occupancy[lt.g_nsin[k]];
-            for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += s.occupancy[lt.g_ewin[k]];
-            const int cur_q = cur == 0 ? ns_q : ew_q, opp_q = cur == 0 ? ew_q : ns_q;
-            if (qt == 1) { s.g_last[g] = cur_q; s.g_gap[g] = 0; }
-            if (cur_q > s.g_last[g]) { s.g_last[g] = cur_q; s.g_gap[g] = 0; } else s.g_gap[g]++;
-            if (qt >= MIN_GREEN && (s.g_gap[g] >= GAP_TICKS || qt >= MAX_GREEN || (opp_q > cur_q && cur_q == 0))) {
-                const int next = 1 - cur;
-                if (next != cur && next != pend) pend = next;   // apply_phase :386-393
-                s.g_qt[g] = 0;
-            }
-        } else {             // run_fixed_time :427-441
-            const int ft = ++s.g_ft_timer[g];
-            if (ft == 1) { const int ph = s.g_ft_phase[g]; if (ph != cur && ph != pend) pend = ph; }
-            if (ft >= GREEN_DURATION) { s.g_ft_phase[g] = 1 - s.g_ft_phase[g]; s.g_ft_timer[g] = 0; }
-        }
-    }
-    int plan = 0;
-    if (pend >= 0) {         // _execute_phase_change :348-384
-        bool occupied = false;
-        for (int k = lt.g_cl_off[g]; k < lt.g_cl_off[g + 1]; k++) occupied |= s.occupancy[lt.g_cl[k]] != 0;
-        const int base = (g + 1) * 4;
-        if (occupied) {
-            plan = 1;
-            for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); });
-        } else {
-            plan = 2 + pend;
-            const bool ns_go = pend == 0;
-            for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); });
-            for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); });
-            cur = pend; pend = -1;
-        }
-    }
-    s.g_cur[g] = cur; s.g_pend[g] = pend; s.g_plan[g] = plan;
-}
-
-__device__ void group_apply(const TickArgs &a, int g) {
-    const tsim_light_tables &lt = a.lt;
-    const tsim_tick_state &s = a.st;
-    const int plan = s.g_plan[g];
-    if (plan == 0) return;
-    auto commit = [&](int c) {
-        const int w = *((volatile int32_t *)(s.stopw + c));
-        if ((w >> 2) == g + 1) { s.stop_map[c] = (uint8_t)(w & 1); s.stopw[c] = 0; }
-    };
-    if (plan == 1) {
-        for_light_cells(lt, lt.g_all_off, lt.g_all, g, commit);
-    } else {
-        for_light_cells(lt, lt.g_ns_off, lt.g_ns, g, commit);
-        for_light_cells(lt, lt.g_ew_off, lt.g_ew, g, commit);
-    }
-}
-
-// stop_map as the vehicles of this tick see it: the staged write of a light group that acted this tick, else the map
-__device__ __forceinline__ int stop_now(const tsim_tick_state &s, int c) {
-    const int w = __ldcg(s.stopw + c);
-    return w ? (w & 1) : (int)s.stop_map[c];
-}
-
-// claim of the sweep `gen` on cell c: rank of the lowest-ranked vehicle that ends there, NO_CLAIM if none
-__device__ __forceinline__ int claim_rank(const u64 *plane, int c, uint32_t gen) {
-    const u64 k = __ldcg(plane + c);
-    return (uint32_t)(k >> 32) == gen ? (int)(0xffffffffu - (uint32_t)k) : NO_CLAIM;
-}
-__device__ __forceinline__ void claim_cell(u64 *plane, int c, uint32_t gen, int rank) {
-    atomicMax(plane + c, ((u64)gen << 32) | (u64)(0xffffffffu - (uint32_t)rank));
-}
 
 // phase A of one vehicle: vehicle_base.py:616-663 on the tick-start snapshot
 __device__ void vehicle_decide(const TickArgs &a, int v, int t) {
@@ -257,7 +154,7 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
             if (s.alive[v]) { vehicle_decide(a, v, t); const int p = s.pos[v]; live += p >= a.own_lo && p < a.own_hi; }
         live = __reduce_add_sync(0xffffffffu, live);
         if ((threadIdx.x & 31) == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
-        for (int g = tid; g < ng; g += nth) group_decide(a, g);
+        for (int g = tid; g < ng; g += nth) group_decide<false>(a, g);
         grid.sync();
         // ---- 2: claim fixed point, one barrier per sweep
         const int32_t *rank = tp.rank + (size_t)t * nv;
@@ -333,7 +230,7 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
         const uint32_t gen_spawn = (uint32_t)t * GEN_PER_TICK + GEN_PER_TICK - 1;
         for (int k = k0 + tid; k < k1; k += nth)
             if (tp.origin[k] >= 0 && s.occupancy[tp.origin[k]] == 0) claim_cell(plane[0], tp.origin[k], gen_spawn, k);
-        for (int g = tid; g < ng; g += nth) group_apply(a, g);
+        for (int g = tid; g < ng; g += nth) group_apply<false>(a, g);
         if (tid == 0) { s.scalars[S_FLAG0] = 0; s.scalars[S_FLAG1] = 0; s.scalars[S_FLAG2] = 0; }   // nobody touches the sweep flags here
         grid.sync();
         // ---- 5: spawns, the next tick's route events
@@ -594,6 +491,13 @@ extern "C" tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tap
     return TSIM_OK;
 }
 
+// the live-list kernel (k_tick2.cu)
+bool tick2_enabled(const tsim_tick_state *st);
+tsim_status tick2_check(const tsim_tick_state *st, const tsim_tick_tapes *tp);
+tsim_status tick2_init(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, cudaStream_t cs);
+tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st, int32_t n_ticks,
+                      int32_t algo, cudaStream_t cs);
+
 static tsim_status check_tick_args(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st) {
     tsim_status s = check_cfg(cfg);
     if (s != TSIM_OK) return s;
@@ -601,11 +505,21 @@ static tsim_status check_tick_args(const tsim_cfg *cfg, const tsim_light_tables 
     if (tp->n_vehicles < 0 || tp->n_ticks < 1 || lt->n_groups < 0) { set_error("tick: bad sizes"); return TSIM_ERR_CONFIG; }
     if (st->own_row_lo < 0 || st->own_row_hi < st->own_row_lo || st->own_row_hi > cfg->win_rows) { set_error("tick: bad own rows"); return TSIM_ERR_CONFIG; }
     if (!st->occupancy || !st->stop_map || !st->stuck_map || !st->claim || !st->stopw || !st->scalars) { set_error("tick: NULL map / scratch plane"); return TSIM_ERR_CONFIG; }
+    // the kernels read spawn_first / ev_first every tick whatever the fleet size, and the group arrays whenever there are groups
+    if (!tp->spawn_first || !tp->ev_first) { set_error("tick: NULL spawn_first / ev_first"); return TSIM_ERR_CONFIG; }
     if (tp->n_vehicles > 0 && (!st->pos || !st->path_off || !st->path_len || !st->alive || !st->moved || !tp->origin || !tp->target || !tp->speed ||
-                               !tp->malfunction || !tp->rank || !tp->spawn_first || !tp->ev_first)) {
+                               !tp->malfunction || !tp->rank || !st->steps || !st->stranded || !st->stuck_ticks || !st->base_speed || !st->cur_speed ||
+                               !st->max_steps || !st->early || !st->is_stuck || !st->prev_valid || !st->malfunction || !st->direction)) {
         set_error("tick: NULL vehicle array / tape");
         return TSIM_ERR_CONFIG;
     }
+    if (lt->n_groups > 0 && (!st->g_cur || !st->g_pend || !st->g_qt || !st->g_gap || !st->g_last || !st->g_ft_phase || !st->g_ft_timer || !st->g_plan ||
+                             !lt->tl_off || !lt->tl_cells || !lt->g_all_off || !lt->g_all || !lt->g_ns_off || !lt->g_ns || !lt->g_ew_off || !lt->g_ew ||
+                             !lt->g_nsin_off || !lt->g_nsin || !lt->g_ewin_off || !lt->g_ewin || !lt->g_cl_off || !lt->g_cl)) {
+        set_error("tick: NULL light-group array / table");
+        return TSIM_ERR_CONFIG;
+    }
+    if (tick2_enabled(st)) return tick2_check(st, tp);
     return TSIM_OK;
 }
 
@@ -639,6 +553,7 @@ extern "C" tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tabl
         for (int32_t *z : zero) TSIM_CUDA(cudaMemsetAsync(z, 0, ng * 4, cs));
     }
     TSIM_CUDA(cudaMemsetAsync(st->scalars, 0, 16 * 4, cs));
+    if (tick2_enabled(st)) return tick2_init(cfg, tp, st, cs);
     return TSIM_OK;
 }
 
@@ -647,6 +562,7 @@ extern "C" tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_table
     tsim_status r = check_tick_args(cfg, lt, tp, st);
     if (r != TSIM_OK) return r;
     if (n_ticks < 1 || (algo != 0 && algo != 1)) { set_error("tick: n_ticks %d algo %d", n_ticks, algo); return TSIM_ERR_CONFIG; }
+    if (tick2_enabled(st)) return tick2_run(cfg, lt, tp, st, n_ticks, algo, (cudaStream_t)stream);
     TickArgs a{cfg->width, cfg->win_rows, n_ticks, algo, 0, 0, *lt, *tp, *st};
     own_cells(cfg, st, a.own_lo, a.own_hi);
     int dev = 0, sms = 0, per_sm = 0;

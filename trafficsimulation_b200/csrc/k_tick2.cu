@@ -1,0 +1,393 @@
+// k_tick2.cu -- the vehicle tick around the LIVE vehicles (tsim_tick_state.probe / recs / plans set).
+//
+// Same tick as k_tick.cu (same reference lines, same claim fixed point: see its header); what changes is what a tick touches:
+//   * a compacted LIVE LIST instead of the attempt array.  A vehicle is a 48-byte record that moves to a new slot every
+//     tick: survivors of the move phase and the spawns of the tick are appended (one atomic per warp) to the other half of
+//     `recs`, so that every phase reads its vehicles as consecutive 48-byte records and a fleet that has mostly arrived (or
+//     has mostly not spawned yet) costs what its live vehicles cost;
+//   * ONE probe word per cell (`probe`: occupancy | stop | staged-stop bits and two 12-bit tick tags "a vehicle claimed this
+//     cell in claim plane 0 / 1 during this tick").  Phase A reads one word per look-ahead cell instead of two maps; a claim
+//     sweep reads one word per planned cell and only follows it into the 64-bit claim plane (or the staged stop word) when
+//     the tag (the staged bit) says there is something to find -- a stale tag only costs that extra load;
+//   * a per-tick PLAN record (32 bytes: the <= 5 planned cells, activation rank, max_steps, stop bits): the sweeps of the
+//     fixed point read it instead of the vehicle state, the tapes and the route arena;
+//   * the spawner's claims (lowest attempt index per origin cell) are made during the move phase in the claim plane the
+//     final sweep did not use, so a tick has one grid-wide barrier less: decide | sweep x n | move | spawn.
+// The public maps (occupancy / stop_map / stuck_map) are kept up to date as before; the vehicle SoA of tsim_tick_state is
+// written on demand by tsim_tick_export.
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include "tick_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tsim {
+
+enum { S_NLIVE0 = 10, S_NLIVE1 = 11 };   // scalars: entries of the two halves of the live list
+
+struct __align__(16) VRec {   // TSIM_TICK_VREC_BYTES
+    long long path_off;   // next cell of the route in ev_cells
+    int32_t v;            // spawn-attempt index (row of the tapes)
+    int32_t pos;          // cell
+    int32_t path_len, steps, stranded, target;
+    int16_t stuck_ticks;
+    int8_t base_speed, cur_speed;
+    int8_t is_stuck, prev_valid, malfunction, direction;
+    int32_t pad[2];
+};
+static_assert(sizeof(VRec) == TSIM_TICK_VREC_BYTES, "VRec size");
+
+struct __align__(16) VPlan {   // TSIM_TICK_PLAN_BYTES
+    int32_t cell[MAX_SPEED];   // the cells the vehicle may enter this tick (first max_steps entries)
+    int32_t rank;
+    uint8_t m, k, stop, early;   // max_steps; steps granted by the last sweep (0xff: none yet); stop_now bits of the cells; early exit
+    int32_t target;              // an arriving vehicle claims nothing
+};
+static_assert(sizeof(VPlan) == TSIM_TICK_PLAN_BYTES, "VPlan size");
+
+__device__ __forceinline__ uint32_t tick_tag(int t) { return (uint32_t)(t % 4095) + 1u; }
+
+// stop_map as the vehicles of this tick see it, from the probe word (the staged write of a light group that acted this tick wins)
+__device__ __forceinline__ int stop_seen(const tsim_tick_state &s, int c, uint32_t p) {
+    return (p & P_STAGED) ? (__ldcg(s.stopw + c) & 1) : (int)((p >> 1) & 1u);
+}
+
+// rank of the lowest-ranked vehicle that claimed cell c in `plane` during sweep `gen` (NO_CLAIM: nobody); p = probe word of c
+__device__ __forceinline__ int claim_seen(const u64 *plane, int shift, uint32_t tag, int c, uint32_t p, uint32_t gen) {
+    return ((p >> shift) & P_TAG_MASK) == tag ? claim_rank(plane, c, gen) : NO_CLAIM;
+}
+
+__device__ __forceinline__ void claim_tagged(u64 *plane, uint32_t *probe, int shift, uint32_t tag, int c, uint32_t gen, int rank) {
+    claim_cell(plane, c, gen, rank);
+    const uint32_t p = __ldcg(probe + c);
+    if (((p >> shift) & P_TAG_MASK) != tag) {   // every claimer of the tick writes the same tag: clear, then set
+        atomicAnd(probe + c, ~(P_TAG_MASK << shift));
+        atomicOr(probe + c, tag << shift);
+    }
+}
+
+// phase A of one vehicle (vehicle_base.py:616-663 on the tick-start snapshot): updates the record, fills the plan
+__device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, int t) {
+    const tsim_tick_state &s = a.st;
+    const tsim_tick_tapes &tp = a.tp;
+    const int v = r.v;
+    const size_t tv = (size_t)t * tp.n_vehicles + v;
+    // everything this vehicle may need from the tapes travels together (independent loads)
+    const int stamp = s.ev_stamp[v];
+    const uint8_t malf = tp.malfunction[tv];
+    pl.rank = tp.rank[tv];
+    pl.m = 0; pl.k = 0xff; pl.stop = 0; pl.early = 0; pl.target = r.target;
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++) pl.cell[i] = -1;
+    if (stamp == t) { r.path_off = s.ev_poff[v]; r.path_len = s.ev_plen[v]; }   // the re-plan the reference made this tick (replayed)
+    if (r.malfunction) {   // _tick_stranded :552-565
+        if (--r.stranded <= 0) { r.malfunction = 0; r.stranded = 0; }
+        if (r.malfunction) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }
+    }
+    if (malf) {   // _check_malfunction :608-610
+        r.malfunction = 1; r.stranded = MALFUNCTION_TICKS; r.base_speed = 0; r.cur_speed = 0; pl.early = 1;
+        return;
+    }
+    const int pos = r.pos;
+    if (__ldcg(s.probe + pos) & P_STOP) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }   // :639-643
+    int base = r.base_speed;
+    if (base == 0) { base = tp.speed[tv]; r.base_speed = (int8_t)base; }   // :94-112
+    int sp = base;
+    if (tp.rain_map && tp.rain_map[pos] == 1) sp = max(1, sp - RAIN_REDUCTION);
+    r.cur_speed = (int8_t)sp;
+    if (sp > MAX_SPEED) s.scalars[S_ERR] = 33;   // tape contract: speeds are random.randint(1, 5) (vehicle_base.py:112)
+    // _scan_ahead_for_obstacles :422-452 and _determine_max_steps :719-731: cells at or beyond min(speed, len) cannot lower max_steps
+    const int len = r.path_len;
+    const int32_t *path = tp.ev_cells + r.path_off;
+    int ms = min(min(sp, len), MAX_SPEED);
+    int cell[MAX_SPEED];
+    uint32_t pw[MAX_SPEED];
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++) cell[i] = i < ms ? path[i] : -1;
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++) pw[i] = cell[i] >= 0 ? __ldcg(s.probe + cell[i]) : 0u;
+#pragma unroll
+    for (int i = MAX_SPEED - 1; i >= 0; i--)
+        if (i < ms && (cell[i] < 0 || (pw[i] & (P_OCC | P_STOP)))) ms = i;   // a cell outside the window blocks, like a vehicle
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++) pl.cell[i] = i < ms ? cell[i] : -1;
+    pl.m = (uint8_t)ms;
+    if (ms <= 0) {
+        r.base_speed = 0;
+        if (pos == r.target) s.scalars[S_ERR] = 30;   // tape contract: a live vehicle is never at its target in phase A
+        pl.early = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    constexpr uint32_t FULL = 0xffffffffu;
+    const tsim_tick_state &s = a.st;
+    const tsim_tick_tapes &tp = a.tp;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    const int nv = tp.n_vehicles, ng = a.lt.n_groups;
+    const size_t ncell = (size_t)a.W * a.H;
+    u64 *plane[2] = {(u64 *)s.claim, (u64 *)s.claim + ncell};
+    VRec *recs[2] = {(VRec *)s.recs, (VRec *)s.recs + nv};
+    VPlan *plans = (VPlan *)s.plans;
+    const int shift[2] = {P_TAG_SHIFT0, P_TAG_SHIFT1};
+
+    auto scatter_events = [&](int t) {   // route events of tick t: the vehicle picks its own up in phase A (or when it spawns)
+        if (t >= tp.n_ticks) return;
+        for (int e = tp.ev_first[t] + tid; e < tp.ev_first[t + 1]; e += nth) {
+            const int v = tp.ev_vehicle[e];
+            s.ev_poff[v] = tp.ev_off[e];
+            s.ev_plen[v] = (int32_t)(tp.ev_off[e + 1] - tp.ev_off[e]);
+            s.ev_stamp[v] = t;
+        }
+    };
+    scatter_events(*((volatile int32_t *)(s.scalars + S_TICK)));
+    grid.sync();
+    for (int it = 0; it < a.n_ticks; it++) {
+        const int t = *((volatile int32_t *)(s.scalars + S_TICK));
+        if (t >= tp.n_ticks) { if (tid == 0) s.scalars[S_ERR] = 31; break; }
+        const int cur = t & 1, nxt = cur ^ 1;
+        VRec *rc = recs[cur], *rn = recs[nxt];
+        const int n_live = *((volatile int32_t *)(s.scalars + S_NLIVE0 + cur));
+        const uint32_t gen0 = (uint32_t)t * GEN_PER_TICK + 1u;   // generation nobody writes: "no claims yet"
+        const uint32_t tag = tick_tag(t);
+        // ---- 1: phase A of every live vehicle + light-group decisions (staged)
+        int live = 0;
+        for (int i = tid; i < n_live; i += nth) {
+            VRec r = rc[i];
+            VPlan pl;
+            decide2(a, r, pl, t);
+            rc[i] = r;
+            plans[i] = pl;
+            live += r.pos >= a.own_lo && r.pos < a.own_hi;
+        }
+        live = __reduce_add_sync(FULL, live);
+        if (lane == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
+        for (int g = tid; g < ng; g += nth) group_decide<true>(a, g);
+        if (tid == 0) s.scalars[S_NLIVE0 + nxt] = 0;   // the other half was last read as `cur` one tick ago
+        grid.sync();
+        // ---- 2: claim fixed point, one barrier per sweep
+        int last = 0;
+        for (int iter = 0;; iter++) {
+            const int fidx[3] = {S_FLAG0, S_FLAG1, S_FLAG2};   // three flags in rotation: the one zeroed after sweep i is written in sweep i + 2
+            int32_t *flag = s.scalars + fidx[iter % 3];
+            const int pp = (iter + 1) & 1, pc = iter & 1;
+            const uint32_t gen_prev = gen0 + iter, gen_cur = gen0 + iter + 1;
+            bool ch = false;
+            for (int i = tid; i < n_live; i += nth) {
+                VPlan pl = plans[i];
+                if (pl.early || pl.m == 0) continue;
+                const int m = pl.m;
+                uint32_t pw[MAX_SPEED];
+#pragma unroll
+                for (int j = 0; j < MAX_SPEED; j++) pw[j] = j < m ? __ldcg(s.probe + pl.cell[j]) : 0u;
+                if (iter == 0) {   // the staged stop_map writes of this tick's light groups are complete now: fold them into the plan
+                    uint32_t sm = 0;
+#pragma unroll
+                    for (int j = 0; j < MAX_SPEED; j++) if (j < m && stop_seen(s, pl.cell[j], pw[j]) == 1) sm |= 1u << j;
+                    pl.stop = (uint8_t)sm;
+                }
+                int k = 0;
+                bool open = true;
+#pragma unroll
+                for (int j = 0; j < MAX_SPEED; j++) {   // _execute_movement :733-753
+                    // a lower-ranked vehicle ends here; a stop cell may only be entered on the last step
+                    const int cr = (iter > 0 && j < m) ? claim_seen(plane[pp], shift[pp], tag, pl.cell[j], pw[j], gen_prev) : NO_CLAIM;
+                    open = open && j < m && !(cr < pl.rank) && !(((pl.stop >> j) & 1u) && j + 1 != m);
+                    if (open) k = j + 1;
+                }
+                if (k != pl.k || iter == 0) {
+                    ch |= k != pl.k;
+                    pl.k = (uint8_t)k;
+                    *reinterpret_cast<uint32_t *>(&plans[i].m) = *reinterpret_cast<const uint32_t *>(&pl.m);   // m, k, stop, early
+                }
+                if (k >= 1) {
+                    const int c = pl.cell[k - 1];
+                    if (c != pl.target) claim_tagged(plane[pc], s.probe, shift[pc], tag, c, gen_cur, pl.rank);   // an arriving vehicle is removed at once
+                }
+            }
+            if (__any_sync(FULL, ch) && lane == 0) *flag = 1;
+            grid.sync();
+            const int any = *((volatile int32_t *)flag);
+            if (tid == 0) { s.scalars[fidx[(iter + 2) % 3]] = 0; s.scalars[S_ITERS]++; }
+            last = iter;
+            if (!any) break;
+            if (iter >= GEN_PER_TICK - 4) { if (tid == 0) s.scalars[S_ERR] = 32; break; }
+        }
+        const int pf = last & 1, po = pf ^ 1;   // plane of the final sweep; the other one takes the spawner's claims
+        const uint32_t gen_fin = gen0 + last + 1;
+        const uint32_t gen_spawn = (uint32_t)t * GEN_PER_TICK + GEN_PER_TICK - 1;
+        // ---- 3: apply the moves, append the survivors to the other half of the list; spawner claims
+        const int k0 = tp.spawn_first[t], k1 = tp.spawn_first[t + 1];
+        for (int i0 = tid - lane; i0 < n_live; i0 += nth) {   // whole warps: the append is one atomic per warp
+            const int i = i0 + lane;
+            bool keep = false;
+            VRec r;
+            if (i < n_live) {
+                r = rc[i];
+                const VPlan pl = plans[i];
+                int pos = r.pos;
+                const int target = r.target;
+                if (!pl.early) {
+                    const int k = pl.k == 0xff ? 0 : pl.k;
+                    if (k >= 1) {
+                        const int fin = pl.cell[k - 1], prev = k >= 2 ? pl.cell[k - 2] : pos;
+                        // cells left or passed through: cleared unless somebody ends there this tick (their set wins)
+                        if (claim_seen(plane[pf], shift[pf], tag, pos, __ldcg(s.probe + pos), gen_fin) == NO_CLAIM) {   // move_vehicle city_model.py:1952,1957
+                            s.occupancy[pos] = 0; s.stuck_map[pos] = 0; atomicAnd(s.probe + pos, ~P_OCC);
+                        }
+                        for (int j = 0; j + 1 < k; j++)
+                            if (claim_seen(plane[pf], shift[pf], tag, pl.cell[j], __ldcg(s.probe + pl.cell[j]), gen_fin) == NO_CLAIM) s.stuck_map[pl.cell[j]] = 0;
+                        if (fin != target) {
+                            s.occupancy[fin] = 1; atomicOr(s.probe + fin, P_OCC);
+                            s.stuck_map[fin] = (k == 1 && r.is_stuck) ? 1 : 0;   // move_vehicle :1956-1958, before _move_to resets is_stuck
+                        } else if (claim_seen(plane[pf], shift[pf], tag, fin, __ldcg(s.probe + fin), gen_fin) == NO_CLAIM) {
+                            s.stuck_map[fin] = 0;                                // arrives: remove_vehicle clears its cell again (unless a later-ranked vehicle ends there)
+                        }
+                        const int d = fin - prev;                                // compute_direction numba_utilities.py:14-28
+                        r.direction = (int8_t)(d == a.W ? DN : d == 1 ? DE : d == -a.W ? DS : d == -1 ? DW : r.direction);
+                        if (r.stuck_ticks > 0) { r.is_stuck = 0; r.stuck_ticks = 0; }   // _move_to :528-532
+                        r.steps += k;
+                        r.path_off += k; r.path_len -= k;
+                        r.pos = pos = fin;
+                    }
+                    r.prev_valid = 1;   // step() :677
+                } else {                // :679-680 tick_stuck :687-693
+                    const uint32_t pw = __ldcg(s.probe + pos);
+                    if (r.prev_valid && stop_seen(s, pos, pw) != 1) {
+                        const int st = ++r.stuck_ticks;
+                        if (st > STUCK_THRESHOLD && !r.is_stuck) r.is_stuck = 1;
+                    }
+                    if (pos == target) { s.occupancy[pos] = 0; s.stuck_map[pos] = 0; atomicAnd(s.probe + pos, ~P_OCC); }
+                }
+                keep = pos != target;   // on_target_reached :755-775 -> remove_vehicle city_model.py:1920-1929
+            }
+            const uint32_t mask = __ballot_sync(FULL, keep);
+            if (mask) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(s.scalars + S_NLIVE0 + nxt, __popc(mask));
+                base = __shfl_sync(FULL, base, 0);
+                if (keep) rn[base + __popc(mask & ((1u << lane) - 1u))] = r;
+            }
+        }
+        for (int k = k0 + tid; k < k1; k += nth)   // lowest attempt index per origin cell; whether the cell is free is known after the barrier
+            if (tp.origin[k] >= 0) claim_tagged(plane[po], s.probe, shift[po], tag, tp.origin[k], gen_spawn, k);
+        if (tid == 0) { s.scalars[S_FLAG0] = 0; s.scalars[S_FLAG1] = 0; s.scalars[S_FLAG2] = 0; }   // nobody touches the sweep flags here
+        grid.sync();
+        // ---- 4: spawns (appended like the survivors), commit of the staged stop_map writes, the next tick's route events
+        for (int k0w = k0 + tid - lane; k0w < k1; k0w += nth) {
+            const int k = k0w + lane;
+            bool born = false;
+            int o = -1;
+            if (k < k1) {
+                o = tp.origin[k];
+                born = o >= 0 && !(__ldcg(s.probe + o) & P_OCC) && claim_rank(plane[po], o, gen_spawn) == k;
+            }
+            const uint32_t mask = __ballot_sync(FULL, born);
+            if (mask) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(s.scalars + S_NLIVE0 + nxt, __popc(mask));
+                base = __shfl_sync(FULL, base, 0);
+                if (born) {
+                    VRec r;
+                    r.v = k; r.pos = o; r.target = tp.target[k];
+                    const bool ev = s.ev_stamp[k] == t;   // the route planned at spawn time
+                    r.path_off = ev ? s.ev_poff[k] : 0; r.path_len = ev ? s.ev_plen[k] : 0;
+                    r.steps = 0; r.stranded = 0; r.stuck_ticks = 0; r.base_speed = 0; r.cur_speed = 0;
+                    r.is_stuck = 0; r.prev_valid = 0; r.malfunction = 0; r.direction = -1; r.pad[0] = 0; r.pad[1] = 0;
+                    rn[base + __popc(mask & ((1u << lane) - 1u))] = r;
+                    s.occupancy[o] = 1; s.stuck_map[o] = 0; atomicOr(s.probe + o, P_OCC);   // place_vehicle city_model.py:1904-1907
+                }
+            }
+        }
+        for (int g = tid; g < ng; g += nth) group_apply<true>(a, g);
+        scatter_events(t + 1);
+        if (tid == 0) s.scalars[S_TICK] = t + 1;
+        grid.sync();
+    }
+}
+
+// live records -> the vehicle SoA of tsim_tick_state (the caller zeroed `alive`)
+__global__ void __launch_bounds__(256) tick2_export_kernel(tsim_tick_state s, int nv) {
+    const int cur = s.scalars[S_TICK] & 1;
+    const int n = s.scalars[S_NLIVE0 + cur];
+    const VRec *rc = (const VRec *)s.recs + (size_t)cur * nv;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const VRec r = rc[i];
+        const int v = r.v;
+        s.alive[v] = 1; s.pos[v] = r.pos; s.path_off[v] = r.path_off; s.path_len[v] = r.path_len; s.steps[v] = r.steps; s.stranded[v] = r.stranded;
+        s.stuck_ticks[v] = r.stuck_ticks; s.base_speed[v] = r.base_speed; s.cur_speed[v] = r.cur_speed; s.is_stuck[v] = r.is_stuck;
+        s.prev_valid[v] = r.prev_valid; s.malfunction[v] = r.malfunction; s.direction[v] = r.direction;
+    }
+}
+
+__global__ void fill_i32_kernel2(long long n, int32_t *p, int32_t v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace tsim
+
+using namespace tsim;
+
+bool tick2_enabled(const tsim_tick_state *st) { return st->probe != nullptr; }
+
+tsim_status tick2_check(const tsim_tick_state *st, const tsim_tick_tapes *tp) {
+    if (!st->probe || !st->recs || !st->plans || !st->ev_stamp || !st->ev_plen || !st->ev_poff) {
+        set_error("tick (live list): probe / recs / plans / ev_stamp / ev_plen / ev_poff must all be set");
+        return TSIM_ERR_CONFIG;
+    }
+    if (st->own_row_lo != 0 || st->own_row_hi != 0) { set_error("tick (live list): row-band shards use the vehicle-indexed kernel"); return TSIM_ERR_UNSUPPORTED; }
+    (void)tp;
+    return TSIM_OK;
+}
+
+tsim_status tick2_init(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, cudaStream_t cs) {
+    const size_t n = (size_t)cfg->width * cfg->win_rows, nv = (size_t)tp->n_vehicles;
+    TSIM_CUDA(cudaMemsetAsync(st->probe, 0, n * 4, cs));
+    if (nv) {
+        fill_i32_kernel2<<<div_up((long long)nv, 256) < 1184 ? div_up((long long)nv, 256) : 1184, 256, 0, cs>>>((long long)nv, st->ev_stamp, -1);
+        TSIM_LAUNCH_CHECK();
+    }
+    return TSIM_OK;   // the live-list counters are part of `scalars`, zeroed by the caller
+}
+
+tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st, int32_t n_ticks,
+                      int32_t algo, cudaStream_t cs) {
+    TickArgs a{cfg->width, cfg->win_rows, n_ticks, algo, 0, cfg->win_rows * cfg->width, *lt, *tp, *st};
+    int dev = 0, sms = 0, per_sm = 0;
+    TSIM_CUDA(cudaGetDevice(&dev));
+    TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick2_kernel, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    // a barrier costs more the more CTAs arrive: just enough CTAs for the fleet, at most `k` per SM (TSIM_TICK_CTAS_PER_SM, default 4)
+    int k = 4;
+    if (const char *e = getenv("TSIM_TICK_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1) k = v; }
+    if (k > per_sm) k = per_sm;
+    long long want = ((long long)tp->n_vehicles + 255) / 256;
+    if (want < (lt->n_groups + 255) / 256) want = (lt->n_groups + 255) / 256;
+    const long long cap = (long long)sms * k;
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    void *args[] = {&a};
+    TSIM_COOP_LAUNCH(tick2_kernel, dim3(grid), dim3(256), args, cs);
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_tick_export(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, void *stream) {
+    tsim_status r = check_cfg(cfg);
+    if (r != TSIM_OK) return r;
+    if (!tp || !st || !st->scalars) { set_error("tsim_tick_export: NULL argument"); return TSIM_ERR_CONFIG; }
+    if (!tick2_enabled(st)) return TSIM_OK;   // the vehicle-indexed kernel keeps the SoA itself
+    if ((r = tick2_check(st, tp)) != TSIM_OK) return r;
+    const int nv = tp->n_vehicles;
+    if (nv == 0) return TSIM_OK;
+    if (!st->alive || !st->pos || !st->path_off || !st->path_len || !st->steps || !st->stranded || !st->stuck_ticks || !st->base_speed ||
+        !st->cur_speed || !st->is_stuck || !st->prev_valid || !st->malfunction || !st->direction) {
+        set_error("tsim_tick_export: NULL vehicle array");
+        return TSIM_ERR_CONFIG;
+    }
+    cudaStream_t cs = (cudaStream_t)stream;
+    TSIM_CUDA(cudaMemsetAsync(st->alive, 0, (size_t)nv, cs));
+    tick2_export_kernel<<<div_up(nv, 256) < 1184 ? div_up(nv, 256) : 1184, 256, 0, cs>>>(*st, nv);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}

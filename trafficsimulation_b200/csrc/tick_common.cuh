@@ -1,0 +1,121 @@
+// tick_common.cuh -- what the two tick kernels share: constants of the reference (config.py), the light-group controller
+// (intersection_light_group.py:396-494) with its staged stop_map writes, and the generation-tagged claim words.
+#pragma once
+#include "common.cuh"
+
+namespace tsim {
+
+constexpr int MIN_GREEN = 5, MAX_GREEN = 30, GAP_TICKS = 3, GREEN_DURATION = 20;   // config.py:354-359
+constexpr int AWARENESS = 10, MALFUNCTION_TICKS = 400, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2;   // config.py:279,321,306,263
+constexpr int NO_CLAIM = 0x7fffffff;
+constexpr int MAX_SPEED = 5;          // random.randint(1, 5), vehicle_base.py:112: a vehicle plans at most 5 cells
+constexpr int GEN_PER_TICK = 1024;   // claim generations per tick: sweeps 1..1022, spawner 1023
+typedef unsigned long long u64;
+enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8, S_XERR = 9 /* shard exchange */ };
+
+// probe word of a cell (live-list kernel): what a vehicle needs to know about a cell, in one load
+constexpr uint32_t P_OCC = 1u, P_STOP = 2u, P_STAGED = 4u;   // occupancy_map, stop_map, "a light group staged a stop_map write this tick"
+constexpr int P_TAG_SHIFT0 = 8, P_TAG_SHIFT1 = 20;            // 12-bit tick tags: some vehicle claimed the cell in claim plane 0 / 1 this tick
+constexpr uint32_t P_TAG_MASK = 0xfffu;
+
+constexpr int OUTSIDE = -2;          // a tape cell that lies outside this shard's window (host-side translation, tsim.h)
+
+struct TickArgs {
+    int W, H, n_ticks, algo;   // H = rows of the window; every cell index below is LOCAL to the window
+    int own_lo, own_hi;        // local cell range of the rows this shard owns (vehicle_updates counts only those)
+    tsim_light_tables lt;
+    tsim_tick_tapes tp;
+    tsim_tick_state st;
+};
+
+template <class F>
+__device__ __forceinline__ void for_light_cells(const tsim_light_tables &lt, const int32_t *off, const int32_t *lights, int g, F f) {
+    for (int k = off[g]; k < off[g + 1]; k++) {
+        const int l = lights[k];
+        for (int q = lt.tl_off[l]; q < lt.tl_off[l + 1]; q++) f(lt.tl_cells[q]);
+    }
+}
+
+// light group: controller + decision; stop_map writes are staged in `stopw` (atomicMax, priority =
+// group index, then order inside the group) so that concurrent groups reproduce the sequential result
+template <bool PROBE>
+__device__ void group_decide(const TickArgs &a, int g) {
+    const tsim_light_tables &lt = a.lt;
+    const tsim_tick_state &s = a.st;
+    int cur = s.g_cur[g], pend = s.g_pend[g];
+    if (pend < 0) {
+        if (a.algo == 0) {   // run_queue_actuated :463-494
+            const int qt = ++s.g_qt[g];
+            int ns_q = 0, ew_q = 0;
+            for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += s.occupancy[lt.g_nsin[k]];
+            for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += s.occupancy[lt.g_ewin[k]];
+            const int cur_q = cur == 0 ? ns_q : ew_q, opp_q = cur == 0 ? ew_q : ns_q;
+            if (qt == 1) { s.g_last[g] = cur_q; s.g_gap[g] = 0; }
+            if (cur_q > s.g_last[g]) { s.g_last[g] = cur_q; s.g_gap[g] = 0; } else s.g_gap[g]++;
+            if (qt >= MIN_GREEN && (s.g_gap[g] >= GAP_TICKS || qt >= MAX_GREEN || (opp_q > cur_q && cur_q == 0))) {
+                const int next = 1 - cur;
+                if (next != cur && next != pend) pend = next;   // apply_phase :386-393
+                s.g_qt[g] = 0;
+            }
+        } else {             // run_fixed_time :427-441
+            const int ft = ++s.g_ft_timer[g];
+            if (ft == 1) { const int ph = s.g_ft_phase[g]; if (ph != cur && ph != pend) pend = ph; }
+            if (ft >= GREEN_DURATION) { s.g_ft_phase[g] = 1 - s.g_ft_phase[g]; s.g_ft_timer[g] = 0; }
+        }
+    }
+    int plan = 0;
+    if (pend >= 0) {         // _execute_phase_change :348-384
+        bool occupied = false;
+        for (int k = lt.g_cl_off[g]; k < lt.g_cl_off[g + 1]; k++) occupied |= s.occupancy[lt.g_cl[k]] != 0;
+        const int base = (g + 1) * 4;
+        if (occupied) {
+            plan = 1;
+            for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); if (PROBE) atomicOr(s.probe + c, P_STAGED); });
+        } else {
+            plan = 2 + pend;
+            const bool ns_go = pend == 0;
+            for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); if (PROBE) atomicOr(s.probe + c, P_STAGED); });
+            for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); if (PROBE) atomicOr(s.probe + c, P_STAGED); });
+            cur = pend; pend = -1;
+        }
+    }
+    s.g_cur[g] = cur; s.g_pend[g] = pend; s.g_plan[g] = plan;
+}
+
+template <bool PROBE>
+__device__ void group_apply(const TickArgs &a, int g) {
+    const tsim_light_tables &lt = a.lt;
+    const tsim_tick_state &s = a.st;
+    const int plan = s.g_plan[g];
+    if (plan == 0) return;
+    auto commit = [&](int c) {
+        const int w = *((volatile int32_t *)(s.stopw + c));
+        if ((w >> 2) == g + 1) {
+            s.stop_map[c] = (uint8_t)(w & 1); s.stopw[c] = 0;
+            if (PROBE) { atomicAnd(s.probe + c, ~(P_STOP | P_STAGED)); if (w & 1) atomicOr(s.probe + c, P_STOP); }
+        }
+    };
+    if (plan == 1) {
+        for_light_cells(lt, lt.g_all_off, lt.g_all, g, commit);
+    } else {
+        for_light_cells(lt, lt.g_ns_off, lt.g_ns, g, commit);
+        for_light_cells(lt, lt.g_ew_off, lt.g_ew, g, commit);
+    }
+}
+
+// stop_map as the vehicles of this tick see it: the staged write of a light group that acted this tick, else the map
+__device__ __forceinline__ int stop_now(const tsim_tick_state &s, int c) {
+    const int w = __ldcg(s.stopw + c);
+    return w ? (w & 1) : (int)s.stop_map[c];
+}
+
+// claim of the sweep `gen` on cell c: rank of the lowest-ranked vehicle that ends there, NO_CLAIM if none
+__device__ __forceinline__ int claim_rank(const u64 *plane, int c, uint32_t gen) {
+    const u64 k = __ldcg(plane + c);
+    return (uint32_t)(k >> 32) == gen ? (int)(0xffffffffu - (uint32_t)k) : NO_CLAIM;
+}
+__device__ __forceinline__ void claim_cell(u64 *plane, int c, uint32_t gen, int rank) {
+    atomicMax(plane + c, ((u64)gen << 32) | (u64)(0xffffffffu - (uint32_t)rank));
+}
+
+}  // namespace tsim

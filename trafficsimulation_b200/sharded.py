@@ -35,12 +35,18 @@ ERR_HALO = 26   # a component meets both a shard's own rows and a cut edge of it
 class ShardPlan:
     """Row ranges of every shard: own rows (even split) and window (own rows + halo, clipped to the grid)."""
 
-    def __init__(self, height: int, n_shards: int, halo: int):
+    def __init__(self, height: int, n_shards: int, halo: int, cuts=None):
+        """``cuts``: the n_shards - 1 rows where the bands meet (default: an even split)."""
         if n_shards < 1 or height < n_shards:
             raise ValueError(f"cannot cut {height} rows into {n_shards} shards")
         self.height, self.n, self.halo = int(height), int(n_shards), int(halo)
-        self.own_lo = [s * height // n_shards for s in range(n_shards)]
-        self.own_hi = [(s + 1) * height // n_shards for s in range(n_shards)]
+        if cuts is None:
+            cuts = [s * height // n_shards for s in range(1, n_shards)]
+        cuts = [int(c) for c in cuts]
+        if len(cuts) != n_shards - 1 or any(b <= a for a, b in zip([0] + cuts, cuts + [height])):
+            raise ValueError(f"cuts {cuts} do not split {height} rows into {n_shards} bands")
+        self.own_lo = [0] + cuts
+        self.own_hi = cuts + [int(height)]
         if n_shards > 1 and min(h - l for l, h in zip(self.own_lo, self.own_hi)) < halo:
             raise ValueError(f"halo {halo} exceeds the rows of a shard ({height} rows / {n_shards} shards)")
         self.win_lo = [max(0, l - halo) for l in self.own_lo]
@@ -156,11 +162,11 @@ class ShardedCityLayout:
     """``GpuCityLayout`` over row-band shards.  Same constructor kwargs as the reference ``CityModel`` plus the
     shard geometry; ``generate`` runs the reference's pass sequence (city_model.py:125-139, 148)."""
 
-    def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, global_reach=False, **city_kwargs):
+    def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, global_reach=False, cuts=None, **city_kwargs):
         from .layout import GpuCityLayout
         self.kw = dict(city_kwargs)
         self.width, self.height = int(city_kwargs.get("width", 200)), int(city_kwargs.get("height", 200))
-        self.plan = ShardPlan(self.height, n_shards, halo if n_shards > 1 else 0)
+        self.plan = ShardPlan(self.height, n_shards, halo if n_shards > 1 else 0, cuts)
         self.comm = Comm(n_shards, distributed, group)
         self.carve = bool(city_kwargs.get("carve_subblock_roads", False))
         self.global_reach = bool(global_reach)

@@ -197,7 +197,10 @@ def synth_trips(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarr
     P = 2147483647                                        # prime > any vehicle count: v -> (a v + b) mod P is injective
     a = rng.integers(1, P, size=(n_ticks, 1), dtype=np.int64)
     b = rng.integers(0, P, size=(n_ticks, 1), dtype=np.int64)
-    rank = ((a * np.arange(nv, dtype=np.int64)[None, :] + b) % P).astype(np.int32)
+    rank = np.empty((n_ticks, nv), np.int32)              # row by row: no [T, V] int64 temporaries
+    idx = np.arange(nv, dtype=np.int64)
+    for t in range(n_ticks):
+        rank[t] = (a[t, 0] * idx + b[t, 0]) % P
     base.update(spawn_tick=tick_of, origin=origin.astype(np.int32), target=target.astype(np.int32),
                 speed=rng.integers(1, 6, size=(n_ticks, nv), dtype=np.uint8), malfunction=np.zeros((n_ticks, nv), np.uint8), rank=rank,
                 ev_tick=tick_of.copy(), ev_vehicle=np.arange(nv, dtype=np.int32), ev_off=ev_off, ev_cells=route[route >= 0].astype(np.int32),

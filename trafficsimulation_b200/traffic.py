@@ -61,10 +61,12 @@ class GpuTraffic:
     """
 
     def __init__(self, width, height, light_tables, tapes, n_ticks, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0",
-                 window=None, own_rows=None):
+                 window=None, own_rows=None, live_list=None):
         """window = (win_y0, win_rows, win_halo): this object is one row-band shard (``ShardedTraffic`` builds those);
         every cell index in `light_tables` / `tapes` is then local to the window, cells outside it are -2;
-        own_rows = (lo, hi): local rows the shard owns (the update counter skips the ghosts on the other rows)."""
+        own_rows = (lo, hi): local rows the shard owns (the update counter skips the ghosts on the other rows).
+        live_list: run the live-list kernel (k_tick2.cu: compacted vehicle records, one probe word per cell); default: yes
+        on a whole city, no on a shard window (the halo exchange works on the vehicle-indexed arrays)."""
         if not torch.cuda.is_available():
             raise RuntimeError("trafficsimulation_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
@@ -85,16 +87,16 @@ class GpuTraffic:
         self.lt = _lib.LightTables(self.n_groups, self.n_lights, *[self.lt_t[k].data_ptr() for k in _LT])
         # ---- tapes
         spawn_tick = np.asarray(tapes["spawn_tick"], np.int32)
-        assert np.all(np.diff(spawn_tick) >= 0), "spawn attempts must be sorted by tick"
         ev_tick = np.asarray(tapes["ev_tick"], np.int32)
-        assert np.all(np.diff(ev_tick) >= 0), "route events must be sorted by tick"
+        if np.any(np.diff(spawn_tick) < 0) or np.any(np.diff(ev_tick) < 0):
+            raise ValueError("spawn attempts and route events must be sorted by tick")
         self.nv = nv = len(spawn_tick)
+        self._validate_tapes(tapes, n_ticks, nv, len(ev_tick), n)
         tt = {}
         tt["spawn_first"] = up(np.searchsorted(spawn_tick, np.arange(n_ticks + 1)), np.int32)
         tt["origin"], tt["target"] = up(tapes["origin"], np.int32), up(tapes["target"], np.int32)
         tt["speed"], tt["malfunction"] = up(tapes["speed"], np.uint8), up(tapes["malfunction"], np.uint8)
         tt["rank"] = up(tapes["rank"], np.int32)
-        assert tt["speed"].numel() >= n_ticks * nv and tt["rank"].numel() >= n_ticks * nv
         tt["ev_first"] = up(np.searchsorted(ev_tick, np.arange(n_ticks + 1)), np.int32)
         tt["ev_vehicle"] = up(tapes["ev_vehicle"], np.int32)
         tt["ev_off"] = up(tapes["ev_off"], np.int64)
@@ -120,10 +122,44 @@ class GpuTraffic:
         for i, k in enumerate(_G32):
             s[k] = self.gstate[i]
         s["scalars"] = z(16, torch.int32)
+        self.live_list = (window is None and own_rows is None) if live_list is None else bool(live_list)
+        if self.live_list:
+            s["probe"] = z(n, torch.int32)
+            s["recs"] = torch.empty(max(2 * nv * 48, 16), dtype=torch.uint8, device=dev)
+            s["plans"] = torch.empty(max(nv * 32, 16), dtype=torch.uint8, device=dev)
+            s["ev_stamp"], s["ev_plen"], s["ev_poff"] = z(nv, torch.int32), z(nv, torch.int32), z(nv, torch.int64)
         self.s = s
-        order = [f[0] for f in _lib.TickState._fields_ if f[1] is C.c_void_p]
-        self.st = _lib.TickState(*[s[k].data_ptr() for k in order], *(own_rows or (0, 0)))
+        v1 = [f[0] for f in _lib.TickState._fields_ if f[1] is C.c_void_p][:30]
+        v2 = ("probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff")
+        self.st = _lib.TickState(*[s[k].data_ptr() for k in v1], *(own_rows or (0, 0)), *[(s[k].data_ptr() if self.live_list else 0) for k in v2])
         _lib.check(self.lib.tsim_tick_init(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), self._stream))
+
+    @staticmethod
+    def _validate_tapes(tapes, n_ticks, nv, n_events, n_cells):
+        """The kernels index the tapes without bounds checks: everything they can reach is checked here, once."""
+        size = lambda a: a.numel() if isinstance(a, torch.Tensor) else np.asarray(a).size
+        for k in ("speed", "malfunction", "rank"):
+            if size(tapes[k]) < n_ticks * nv:
+                raise ValueError(f"tape '{k}' holds {size(tapes[k])} entries, {n_ticks} ticks x {nv} vehicles need {n_ticks * nv}")
+        for k in ("origin", "target"):
+            if size(tapes[k]) != nv:
+                raise ValueError(f"tape '{k}' must have one entry per spawn attempt ({nv})")
+        if size(tapes["ev_vehicle"]) != n_events or size(tapes["ev_off"]) != n_events + 1:
+            raise ValueError("ev_vehicle needs one entry per route event and ev_off one more")
+        ev_off, ev_cells = tapes["ev_off"], tapes["ev_cells"]
+        if n_events:
+            last = int(ev_off[-1]) if not isinstance(ev_off, torch.Tensor) else int(ev_off[-1].item())
+            if last > size(ev_cells):
+                raise ValueError(f"ev_off ends at {last}, ev_cells holds {size(ev_cells)} cells")
+        for k in ("origin", "target", "ev_cells", "ev_vehicle"):
+            a = tapes[k]
+            if size(a) == 0:
+                continue
+            lo, hi = (int(a.min().item()), int(a.max().item())) if isinstance(a, torch.Tensor) else (int(np.min(a)), int(np.max(a)))
+            top = nv if k == "ev_vehicle" else n_cells
+            floor = 0 if k == "ev_vehicle" else _lib.CELL_OUTSIDE
+            if lo < floor or hi >= top or (k != "ev_vehicle" and lo == -1):
+                raise ValueError(f"tape '{k}' holds values outside [{floor}, {top})")
 
     @property
     def _stream(self):
@@ -160,7 +196,9 @@ class GpuTraffic:
 
     def state_host(self):
         """Same dict as oracle.OracleTicks.state() / the reference fixtures."""
-        s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw")}
+        if self.live_list:   # the vehicle SoA is only written on demand
+            _lib.check(self.lib.tsim_tick_export(C.byref(self.cfg), C.byref(self.tp), C.byref(self.st), self._stream))
+        s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw", "probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff")}
         alive = s["alive"][: self.nv] == 1
         cut = lambda a: a[: self.nv]
         flags = (cut(s["is_stuck"]).astype(np.uint8) & 1) | ((cut(s["malfunction"]).astype(np.uint8) & 1) << 1) | \
