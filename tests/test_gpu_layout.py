@@ -131,6 +131,30 @@ def test_reach_fallback_kernel_gives_the_same_city(n_alt, monkeypatch):
     lockstep(g["meta"]["cfg"], g["hbands"], g["vbands"], g["tape_zone"], g["tape_carve"], g["tape_entrance"])
 
 
+@pytest.mark.parametrize("name", ["default12345", "s14_150x110_carve", "s24_400x300_carve"])
+def test_general_labelling_equals_product_short_cut(name, monkeypatch):
+    """The Nothing cells of a fresh layout are (rows without a band) x (columns without one); k_ccl.cu then reads the components
+    off the row / column runs instead of running the union-find.  With the short cut switched off the general path must give
+    the same tables, ids and city (the lock-step run compares them with the oracle's)."""
+    monkeypatch.setenv("TSIM_CCL_PRODUCT", "0")
+    g = load([p for p in layout_fixtures() if name in p][0])
+    lockstep(g["meta"]["cfg"], g["hbands"], g["vbands"], g["tape_zone"], g["tape_carve"], g["tape_entrance"])
+
+
+def test_product_short_cut_is_taken_and_refused():
+    """Which path labelled: a fresh layout is a product (short cut), a carved one is not (union-find)."""
+    import torch
+    g = load([p for p in layout_fixtures() if "s14_150x110_carve" in p][0])
+    oc, gc, carve = _mk(g["meta"]["cfg"], g["hbands"], g["vbands"])
+    gc._build_roads_and_sidewalks()
+    gc.label_nothing()
+    head = lambda: gc.workspace[: 64 * 4].view(torch.int32).cpu().numpy()
+    assert head()[1] == 1 and head()[2] * head()[3] == int(gc.flags[2].item())
+    gc._carve_subblock_roads(g["tape_carve"])
+    gc.label_nothing()
+    assert head()[1] == 0 and head()[0] > 0   # not a product any more: the runs were built
+
+
 LEADS_TO_FIXTURES = ("default12345", "s11_ringR1", "s15_96x128", "s16_64_carve", "s24_400x300_carve", "s13_noopt")
 
 

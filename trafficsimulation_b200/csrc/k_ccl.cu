@@ -21,12 +21,31 @@
 //   6. labels  : only when a label plane is wanted (zoning, clusters): one coalesced 4 B/cell write of
 //                the ids, fused with the zone fill of the type plane.
 //
+// PRODUCT SHORT CUT.  The Nothing cells of a freshly laid-out city are the cells of (rows without a road band) x (columns
+// without one): the target set is a PRODUCT R x C of a row set and a column set.  Then its components are exactly the
+// rectangles (maximal run of consecutive rows of R) x (maximal run of consecutive columns of C), in raster order row run
+// by row run -- no union-find at all.  Whether the plane IS such a product is checked exactly on the device (the plane
+// is a subset of rows-hit x columns-hit by construction; it equals it iff the cell counts agree), and every kernel of the
+// general path returns at once when it is (and the other way round), so the host enqueues both without reading anything
+// back.  Carved cities, intersection clusters and anything irregular take the general path.
+//
 // Carving needs steps 1-5 only (no per-cell label traffic at all); zoning adds step 6, which is the
 // compulsory 4 B/cell write of block_id + the 1 B/cell type update.
+#include <cstdlib>
 #include "scan.cuh"
 #include "bitplane.cuh"
 
 namespace tsim {
+
+struct Prod {            // product short cut (see the header comment)
+    u64 *col_any;        // [wp] OR of all rows
+    uint32_t *row_any;   // [LH] row holds a target cell
+    int32_t *rg_lo, *rg_hi, *cg_lo, *cg_hi;   // row / column runs ("gaps" between the road bands), inclusive bounds
+    int32_t *row_gap, *col_gap;               // [LH] / [W] run index of the row / column, -1 outside
+    int32_t *scal;       // [1] is product, [2] row runs, [3] column runs, [4..5] target cells (64-bit), [6] 0 if product else INT_MAX
+};
+enum { PS_FLAG = 1, PS_NRG = 2, PS_NCG = 3, PS_POPC = 4, PS_GATE = 6 };
+constexpr int PROD_MAX_RUN = 4096;   // a longer run of rows / columns is left to the general path
 
 struct Runs {            // lives in the caller's workspace between the label call and the zoning call
     u64 *M;              // [wp * LH] target bit-plane
@@ -38,6 +57,7 @@ struct Runs {            // lives in the caller's workspace between the label ca
     int32_t *n_runs;     // device scalar
     int32_t *err;        // the caller's error flag: 24 = run capacity, 25 = component capacity
     int wp, cap;
+    Prod pr;
 };
 
 // ---------------------------------------------------------------- 1. bit-plane of the target type
@@ -78,12 +98,14 @@ __device__ __forceinline__ int run_of(const u64 *__restrict__ M, const int32_t *
 }
 
 // ---------------------------------------------------------------- 2. runs
-__global__ void __launch_bounds__(256) ccl_count_kernel(long long nw, int wp, const u64 *__restrict__ M, int32_t *__restrict__ cnt) {
+__global__ void __launch_bounds__(256) ccl_count_kernel(long long nw, int wp, const u64 *__restrict__ M, int32_t *__restrict__ cnt, const int32_t *__restrict__ skip) {
+    if (__ldg(skip)) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nw) cnt[i] = __popcll(run_starts(M, (size_t)i, (int)(i % wp)));
 }
 
 __global__ void __launch_bounds__(256) ccl_runs_kernel(int W, long long nw, Runs r) {
+    if (__ldg(r.pr.scal + PS_FLAG)) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nw) return;
     const int wp = r.wp, wx = (int)(i % wp);
@@ -137,6 +159,7 @@ __device__ __forceinline__ void uf_union(int32_t *L, int a, int b) {
 }
 
 __global__ void __launch_bounds__(256) ccl_merge_kernel(long long nw, Runs r) {
+    if (__ldg(r.pr.scal + PS_FLAG)) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + r.wp;   // rows 1..
     if (i >= nw) return;
     const int wp = r.wp, wx = (int)(i % wp);
@@ -195,6 +218,110 @@ __global__ void __launch_bounds__(256) ccl_bbox_kernel(int W, int y_global0, Run
     }
 }
 
+// ---------------------------------------------------------------- product short cut
+// rows / columns hit by the plane and its cell count.  A CTA takes 32 word columns x 64 rows: lanes = words of a row, warps =
+// rows; the column ORs are combined through shared memory: 32 atomics per CTA.
+__global__ void __launch_bounds__(256) prod_reduce_kernel(int LH, int wp, const u64 *__restrict__ M, Prod p) {
+    __shared__ u64 s_col[8][32];
+    __shared__ int s_cnt;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ncx = (wp + 31) >> 5;
+    const int wx = (blockIdx.x % ncx) * 32 + lane, y0 = (blockIdx.x / ncx) * 64;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    u64 col = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int y = y0 + k * 8 + w;
+        const u64 m = (y < LH && wx < wp) ? M[(size_t)y * wp + wx] : 0ull;
+        col |= m;
+        cnt += __popcll(m);
+        if (__any_sync(0xffffffffu, m != 0ull) && lane == 0) p.row_any[y] = 1u;   // idempotent plain store
+    }
+    s_col[w][lane] = col;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (w == 0) {
+        u64 v = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) v |= s_col[q][lane];
+        if (v && wx < wp) atomicOr(p.col_any + wx, v);
+        if (lane == 0 && s_cnt) atomicAdd((unsigned long long *)(p.scal + PS_POPC), (unsigned long long)s_cnt);
+    }
+}
+
+// one CTA: runs of consecutive hit rows / hit columns, numbered in order, and the verdict "the plane is rows x columns"
+__global__ void __launch_bounds__(1024) prod_gaps_kernel(int W, int LH, Prod p) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry, s_bad;
+    __shared__ int s_set[2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_bad = 0; s_set[0] = 0; s_set[1] = 0; }
+    for (int axis = 0; axis < 2; axis++) {
+        const int n = axis ? W : LH;
+        int32_t *lo = axis ? p.cg_lo : p.rg_lo, *hi = axis ? p.cg_hi : p.rg_hi, *idx = axis ? p.col_gap : p.row_gap;
+        auto on = [&](int i) -> bool {
+            if (i < 0 || i >= n) return false;
+            return axis ? ((p.col_any[i >> 6] >> (i & 63)) & 1ull) != 0ull : p.row_any[i] != 0u;
+        };
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        int set_local = 0;
+        for (int base = 0; base < n; base += 1024) {
+            const int i = base + threadIdx.x;
+            const bool me = on(i);
+            set_local += me;
+            const bool start = me && !on(i - 1);
+            const unsigned bal = __ballot_sync(0xffffffffu, start);
+            if (lane == 0) s_warp[w] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int q = 0; q < 32; q++) { const int c = s_warp[q]; if (q < w) before += c; total += c; }
+            const int k = s_carry + before + __popc(bal & ((1u << lane) - 1u));
+            if (start) {
+                int e = i;
+                while (on(e + 1) && e - i < PROD_MAX_RUN) e++;
+                if (on(e + 1)) s_bad = 1;
+                lo[k] = i; hi[k] = e;
+                for (int j = i; j <= e; j++) idx[j] = k;
+            }
+            if (i < n && !me) idx[i] = -1;
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry += total;
+            __syncthreads();
+        }
+        set_local = __reduce_add_sync(0xffffffffu, set_local);
+        if (lane == 0 && set_local) atomicAdd(&s_set[axis], set_local);
+        __syncthreads();
+        if (threadIdx.x == 0) p.scal[PS_NRG + axis] = s_carry;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long cells = *(const unsigned long long *)(p.scal + PS_POPC);
+        const bool product = !s_bad && cells == (unsigned long long)s_set[0] * (unsigned long long)s_set[1];
+        p.scal[PS_FLAG] = product ? 1 : 0;
+        p.scal[PS_GATE] = product ? 0 : 0x7fffffff;
+    }
+}
+
+// component table of a product plane: component k = (row run k / n_cg) x (column run k % n_cg)
+__global__ void __launch_bounds__(256) prod_table_kernel(int W, int y_global0, Prod p, int32_t *__restrict__ blobs, int cap_blobs, int32_t *count, int32_t *err) {
+    if (!p.scal[PS_FLAG]) return;
+    const int n_rg = p.scal[PS_NRG], n_cg = p.scal[PS_NCG];
+    const long long n = (long long)n_rg * n_cg;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *count = (int)(n < 0x7fffffffLL ? n : 0x7fffffffLL); if (n > cap_blobs) *err = 25; }
+    const long long lim = n < cap_blobs ? n : cap_blobs;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < lim; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / n_cg), j = (int)(k % n_cg);
+        const int x0 = p.cg_lo[j], x1 = p.cg_hi[j], y0 = p.rg_lo[i], y1 = p.rg_hi[i];
+        int32_t *b = blobs + (size_t)k * TSIM_BLOB_STRIDE;
+        b[0] = x0; b[1] = y0 + y_global0; b[2] = x1; b[3] = y1 + y_global0; b[4] = (x1 - x0 + 1) * (y1 - y0 + 1); b[5] = y0 * W + x0;
+    }
+}
+
 // ---------------------------------------------------------------- 6. label plane (+ zone fill)
 // fill[id] (u8): new type of the component's cells, or 0xff = leave the type plane alone
 __global__ void __launch_bounds__(256) zones_table_kernel(const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_blobs, int cap_blobs,
@@ -223,13 +350,37 @@ __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Run
     if (i0 >= n) return;
     const int base = (id_base ? *id_base : 0) + 1;
     const int wp = r.wp;
+    const bool prod = r.pr.scal[PS_FLAG] != 0;
+    const int n_cg = r.pr.scal[PS_NCG];
     if ((W & 7) == 0) {   // 8 cells of one row, inside one word
         const long long y = i0 / W;
         const int x = (int)(i0 % W), wx = x >> 6, sh = x & 63;
         const size_t wi = (size_t)y * wp + wx;
         const uint32_t bits = (uint32_t)(r.M[wi] >> sh) & 0xffu;
         int4 lo = make_int4(0, 0, 0, 0), hi = lo;
-        if (bits) {
+        if (bits && prod) {   // product plane: id = row run * column runs + column run (rows / columns of a set cell always have one)
+            const int row0 = r.pr.row_gap[y] * n_cg;
+            const int4 c0 = *reinterpret_cast<const int4 *>(r.pr.col_gap + x), c1 = *reinterpret_cast<const int4 *>(r.pr.col_gap + x + 4);
+            const int cg[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            int ids[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (bits == 0xffu && cg[0] == cg[7]) {
+                const int cid = row0 + cg[0], id = cid + base;
+                lo = hi = make_int4(id, id, id, id);
+                if (FILL && cid < cap_blobs) {
+                    const uint32_t f = fill[cid];
+                    if (f != 0xffu) { const uint32_t f4 = f * 0x01010101u; *reinterpret_cast<uint2 *>(T + i0) = make_uint2(f4, f4); }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (!((bits >> k) & 1u)) continue;
+                    const int cid = row0 + cg[k];
+                    ids[k] = cid + base;
+                    if (FILL && cid < cap_blobs) { const uint8_t f = fill[cid]; if (f != 0xff) T[i0 + k] = f; }
+                }
+                lo = make_int4(ids[0], ids[1], ids[2], ids[3]); hi = make_int4(ids[4], ids[5], ids[6], ids[7]);
+            }
+        } else if (bits) {
             const u64 st = run_starts(r.M, wi, wx);
             const int sp = r.sprefix[wi];
             const uint32_t inner = (uint32_t)(st >> sh) & 0xfeu;   // run starts strictly inside the group
@@ -264,8 +415,8 @@ __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Run
             const size_t wi = (size_t)y * wp + wx;
             int id = 0;
             if ((r.M[wi] >> p) & 1ull) {
-                const int run = run_of(r.M, r.sprefix, wi, wx, p);
-                const int cid = run < r.cap ? r.len[run] : 0;
+                const int run = prod ? 0 : run_of(r.M, r.sprefix, wi, wx, p);
+                const int cid = prod ? r.pr.row_gap[y] * n_cg + r.pr.col_gap[x] : (run < r.cap ? r.len[run] : 0);
                 id = cid + base;
                 if (FILL && cid < cap_blobs) { const uint8_t f = fill[cid]; if (f != 0xff) T[i] = f; }
             }
@@ -322,8 +473,22 @@ static tsim_status runs_layout(const tsim_cfg *cfg, void *workspace, size_t ws_b
     scan_tmp = (int32_t *)take((size_t)(div_up(nw > cap ? nw : cap, SCAN_TILE) + 1) * 4);
     fill = (uint8_t *)take((size_t)(cap_blobs > 0 ? cap_blobs : 1));
     r.wp = wp; r.cap = cap;
+    r.pr.scal = scal;
+    r.pr.col_any = (u64 *)take((size_t)wp * 8 + (size_t)win.LH * 4);   // col_any and row_any in one piece (one memset)
+    r.pr.row_any = (uint32_t *)(r.pr.col_any + wp);
+    r.pr.rg_lo = (int32_t *)take((size_t)(win.LH / 2 + 2) * 4); r.pr.rg_hi = (int32_t *)take((size_t)(win.LH / 2 + 2) * 4);
+    r.pr.cg_lo = (int32_t *)take((size_t)(win.W / 2 + 2) * 4); r.pr.cg_hi = (int32_t *)take((size_t)(win.W / 2 + 2) * 4);
+    r.pr.row_gap = (int32_t *)take((size_t)win.LH * 4); r.pr.col_gap = (int32_t *)take((size_t)(win.W + 8) * 4);
     if (!workspace || o > ws_bytes) { set_error("labelling needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
     return TSIM_OK;
+}
+
+__global__ void set_i32_kernel(int32_t *p, int32_t v) { *p = v; }
+
+// TSIM_CCL_PRODUCT=0 switches the product short cut off (tests: both paths must label alike)
+static bool product_shortcut_enabled() {
+    const char *e = getenv("TSIM_CCL_PRODUCT");
+    return !(e && *e == '0');
 }
 
 static int list_grid(long long n) {
@@ -344,9 +509,21 @@ tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int target, const 
     TSIM_CUDA(cudaMemsetAsync(r.n_runs, 0, 64 * 4, cs));
     ccl_bits_kernel<<<div_up(nw * 4, 256), 256, 0, cs>>>(win.W, win.LH, r.wp, T, target, r.M);
     TSIM_LAUNCH_CHECK();
-    ccl_count_kernel<<<div_up(nw, 256), 256, 0, cs>>>(nw, r.wp, r.M, r.sprefix);
+    // product short cut: is the plane (rows hit) x (columns hit)?  Then the general path below is skipped on the device.
+    const bool try_product = product_shortcut_enabled();
+    if (try_product) {
+        TSIM_CUDA(cudaMemsetAsync(r.pr.col_any, 0, (size_t)r.wp * 8 + (size_t)win.LH * 4, cs));
+        prod_reduce_kernel<<<div_up(r.wp, 32) * div_up(win.LH, 64), 256, 0, cs>>>(win.LH, r.wp, r.M, r.pr);
+        TSIM_LAUNCH_CHECK();
+        prod_gaps_kernel<<<1, 1024, 0, cs>>>(win.W, win.LH, r.pr);
+        TSIM_LAUNCH_CHECK();
+    } else {
+        set_i32_kernel<<<1, 1, 0, cs>>>(r.pr.scal + PS_GATE, 0x7fffffff);   // (PS_FLAG is 0 from the memset)
+        TSIM_LAUNCH_CHECK();
+    }
+    ccl_count_kernel<<<div_up(nw, 256), 256, 0, cs>>>(nw, r.wp, r.M, r.sprefix, r.pr.scal + PS_FLAG);
     TSIM_LAUNCH_CHECK();
-    if ((st = exclusive_scan_i32(r.sprefix, nw, scan_tmp, r.n_runs, cs)) != TSIM_OK) return st;
+    if ((st = exclusive_scan_i32(r.sprefix, nw, scan_tmp, r.n_runs, cs, r.pr.scal + PS_GATE)) != TSIM_OK) return st;
     ccl_runs_kernel<<<div_up(nw, 256), 256, 0, cs>>>(win.W, nw, r);
     TSIM_LAUNCH_CHECK();
     if (win.LH > 1) {
@@ -361,6 +538,10 @@ tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int target, const 
     TSIM_LAUNCH_CHECK();
     ccl_bbox_kernel<<<g, 256, 0, cs>>>(win.W, win.y0, r, blobs->table, blobs->cap);
     TSIM_LAUNCH_CHECK();
+    if (try_product) {   // last: the general path's scan has just written a count of 0
+        prod_table_kernel<<<list_grid(blobs->cap), 256, 0, cs>>>(win.W, win.y0, r.pr, blobs->table, blobs->cap, blobs->count, r.err);
+        TSIM_LAUNCH_CHECK();
+    }
     return TSIM_OK;
 }
 
