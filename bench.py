@@ -297,6 +297,74 @@ def sharded_vehicle_bench(dev, world, rank, size=4096, per_shard=150000, n_ticks
             "matches_single_gpu": same}
 
 
+def sharded_layout_parity(dev, world, rank, sh, W, H, seed, d_tz, d_te):
+    """Is the city the N ranks just generated the right one?  Two independent recomputations of the SAME city from the same
+    tapes, compared through position-weighted digests (tsim_rows_digest, planes + maps) of the 2N half-bands of rows:
+      * different cuts: the N ranks generate the city again with every cut moved by half a band, so that every row next to a
+        cut of the timed run lies deep inside a shard (and the other way round);
+      * one device: where the whole city fits the int32 cell index of one window (N = 2 at 65536 columns), rank 0 generates it
+        alone, uncut.
+    Returns {"parity_checked": ..., ...}; all ranks take part (collectives)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from trafficsimulation_b200 import _lib
+    from trafficsimulation_b200.sharded import ShardedCityLayout
+    n_half, hh = 2 * world, H // (2 * world)
+
+    def digests(layout):   # [n_half, 8] int64: cell_type, dirs, aux, block_id, 4 maps of the half-bands this process owns
+        out = torch.zeros(n_half, 8, dtype=torch.int64, device=dev)
+        for s, L in layout.shards.items():
+            lo, hi, w0 = layout.plan.own_lo[s], layout.plan.own_hi[s], layout.plan.win_lo[s]
+            for j in range(n_half):
+                a, b = j * hh, (j + 1) * hh
+                if a < lo or b > hi:
+                    continue
+                for k, what in enumerate((1, 2, 4, 8)):
+                    _lib.check(L.lib.tsim_rows_digest(C.byref(L.cfg), C.byref(L._planes), a - w0, b - w0, what,
+                                                      C.c_void_p(out.data_ptr() + 8 * (8 * j + k)), L._stream))
+                for k, name in enumerate(("is_road_map", "road_type_map", "intersection_map", "allowed_dirs_map")):
+                    as_plane = _lib.Planes(L.maps[name].data_ptr(), 0, 0, 0)
+                    _lib.check(L.lib.tsim_rows_digest(C.byref(L.cfg), C.byref(as_plane), a - w0, b - w0, 1,
+                                                      C.c_void_p(out.data_ptr() + 8 * (8 * j + 4 + k)), L._stream))
+        return out
+
+    mine = digests(sh)
+    dist.all_reduce(mine)                      # every half-band has one owner: the sum is its digest
+    n_blocks = int(sh._total.item())
+    result = {"half_bands": n_half, "digest_fields": 8}
+    # ---- the same city, cut elsewhere
+    h = H // world
+    cuts = [k * h + h // 2 for k in range(1, world)]
+    shb = ShardedCityLayout(world, halo=192, lean=True, distributed=True, cuts=cuts, width=W, height=H, carve_subblock_roads=True, device=dev)
+    shb.set_bands(sh.shards[rank].hbands, sh.shards[rank].vbands)
+    tcb = shb.synth_carve_tapes(seed)[rank]
+    shb.generate(d_tz, {rank: tcb}, d_te, check=True)
+    other = digests(shb)
+    dist.all_reduce(other)
+    result["vs_shifted_cuts"] = bool(torch.equal(mine, other)) and int(shb._total.item()) == n_blocks
+    result["shifted_cuts_rows"] = cuts
+    del shb, tcb
+    torch.cuda.empty_cache()
+    # ---- the same city on one device
+    result["vs_single_gpu"] = None
+    if W * (H + 1) < 2 ** 31:
+        flag = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            one = ShardedCityLayout(1, width=W, height=H, carve_subblock_roads=True, device=dev)
+            one.set_bands(sh.shards[rank].hbands, sh.shards[rank].vbands)
+            tc1 = one.synth_carve_tapes(seed)
+            one.generate(d_tz, tc1, d_te, check=True)
+            flag[0] = int(torch.equal(digests(one), mine) and one.n_blocks == n_blocks)
+            del one, tc1
+            torch.cuda.empty_cache()
+        dist.broadcast(flag, 0)
+        result["vs_single_gpu"] = bool(flag.item())
+    result["parity_checked"] = result["vs_shifted_cuts"] and result["vs_single_gpu"] is not False
+    return result
+
+
+
 def guarded(fn, rank, limit_s, on_timeout):
     """Run a collective leg that must never take the headline line down with it: an exception becomes an {"error": ...}
     entry; if the leg hangs (a rank died inside a collective) every rank leaves after `limit_s`, rank 0 printing first."""
@@ -393,12 +461,15 @@ def ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    # weak scaling: ONE city of `size` columns x `size * world` rows, cut into `world` row-band shards (one per GPU,
-    # 64 halo rows, NCCL neighbour exchange after every pass); at world == 1 this is the plain size x size city
+    # N = 1: the size x size city (BASELINE.json configs[2]).  N > 1: BASELINE.json configs[4], ONE city of 65536 columns x 8192 * N
+    # rows (65536 x 65536 at N = 8) in N row-band shards, one per GPU: weak scaling with 8192 rows per GPU.  The shards run LEAN
+    # (sharded.py): 192 halo rows computed redundantly, no halo exchange; the rows around every cut are digested after every pass
+    # and compared at the end of the step (one all-gather), the labellings all-gather their root counts.
     size, seed = args.size, 4096
-    W, H = size, size * world
+    W, H = (size, size) if world == 1 else (args.shard_width, args.shard_rows * world)
+    halo = 192 if world > 1 else 0
     hb, vb = tapes.synth_bands(seed, width=W, height=H)
-    sh = ShardedCityLayout(world, halo=64, distributed=world > 1, width=W, height=H, carve_subblock_roads=True, device=dev)
+    sh = ShardedCityLayout(world, halo=halo, lean=world > 1, distributed=world > 1, width=W, height=H, carve_subblock_roads=True, device=dev)
     sh.set_bands(hb, vb)
     city = sh.shards[rank]
     cap = sh.global_cap
@@ -563,7 +634,8 @@ def ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{W}x{H} synthetic city layout, all generation passes (carve + lights + maps)",
                        "cells_per_gpu": cells,
-                       "parallelism": f"{world} row-band shards of {own_rows} rows (+64 halo rows), NCCL halo exchange after each pass" if world > 1 else "single GPU",
+                       "parallelism": (f"{world} row-band shards of {own_rows} rows (+{halo} halo rows computed redundantly, no halo exchange; the rows around "
+                                       "every cut are digested after every pass and compared at the end of the step; NCCL all-gather of root counts and digests") if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write)", "seed": seed,
                        "blocks": n_blocks, "lights": int(n_lights.item()), "dead_end_sweeps": city.sweeps(),
                        "shard_rounds": {"dead_ends": getattr(sh, "dead_end_rounds", 1), "reach": getattr(sh, "reach_rounds", 1)}},
@@ -587,6 +659,13 @@ def ours(args):
                 line["route_planning"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                                     "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
+    if world > 1 and not args.no_parity:   # is it the right city?  (after all timing; collective)
+        def parity_timeout():
+            line["parity"] = {"error": "timed out"}
+            print(json.dumps(line))
+        par = guarded(lambda: sharded_layout_parity(dev, world, rank, sh, W, H, seed, d_tz, d_te), rank, 600, parity_timeout)
+        if rank == 0:
+            line["parity"] = par
     if world > 1:   # the second hot path on the same shards; a failure or hang here never costs the layout line
         tick = None
         if not args.no_sharded_tick:
@@ -630,6 +709,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--no-sharded-tick", action="store_true", help="N > 1: skip the sharded vehicle-tick leg")
+    ap.add_argument("--shard-width", type=int, default=65536, help="N > 1: columns of the sharded city")
+    ap.add_argument("--shard-rows", type=int, default=8192, help="N > 1: rows per GPU of the sharded city")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the shifted-cut / single-GPU digest comparison")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

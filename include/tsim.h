@@ -170,6 +170,13 @@ tsim_status tsim_layout_label_nothing(const tsim_cfg *cfg, const tsim_planes *p,
 tsim_status tsim_shard_counts(const tsim_cfg *cfg, const tsim_blobs *blobs, int32_t own_lo, int32_t own_hi, int32_t *out,
                               void *stream);
 
+/* position-weighted 64-bit digest of the LOCAL rows [row_lo, row_hi) of the planes selected by `what` (1 cell_type, 2 dirs, 4 aux,
+   8 block_id), ADDED to *out (device).  The digest of a row depends on its global position (win_y0 + row), so two shards
+   that hold the same global rows get the same value exactly when the bytes agree: what row-band shards compare instead of
+   exchanging their halos after every pass. */
+tsim_status tsim_rows_digest(const tsim_cfg *cfg, const tsim_planes *p, int32_t row_lo, int32_t row_hi, int32_t what, uint64_t *out,
+                             void *stream);
+
 /* _carve_subblock_roads (city_model.py:563-737) given the table of tsim_layout_label_nothing and
    the carve tape: one row of 8 int32 per blob id (drawn, carved, px, py (global), hor_dir, ver_dir,
    inbound_is_horizontal, tries).  err_flag (device int32) is set non-zero on an illegal row. */

@@ -144,7 +144,8 @@ def test_general_labelling_equals_product_short_cut(name, monkeypatch):
 def test_product_short_cut_is_taken_and_refused():
     """Which path labelled: a fresh layout is a product (short cut), a carved one is not (union-find)."""
     import torch
-    g = load([p for p in layout_fixtures() if "s14_150x110_carve" in p][0])
+    g = load([p for p in layout_fixtures() if "s24_400x300_carve" in p][0])
+    assert g["tape_carve"][:, 1].sum() > 0   # something does get carved
     oc, gc, carve = _mk(g["meta"]["cfg"], g["hbands"], g["vbands"])
     gc._build_roads_and_sidewalks()
     gc.label_nothing()

@@ -86,3 +86,48 @@ def test_halo_too_small_is_refused_loudly():
     sh.set_bands(hb, vb)
     with pytest.raises(_lib.TsimError):
         sh.generate(tapes.synth_zone_tape(5, cap), None, None)
+
+
+@pytest.mark.parametrize("size,n_shards,carve", [((768, 1024), 4, True), ((1024, 2048), 8, True), ((1000, 1200), 2, False), ((640, 1800), 3, True)])
+def test_lean_shards_equal_single(size, n_shards, carve):
+    """No halo exchange at all (sharded.py, lean mode): every shard computes its halo itself, the digests of the rows around
+    every cut are compared after every pass; the own rows must be the single-device city byte for byte."""
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+    from trafficsimulation_b200.sharded import ShardedCityLayout
+    W, H = size
+    seed = 900 + n_shards
+    hb, vb = tapes.synth_bands(seed, width=W, height=H)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    tz, te = tapes.synth_zone_tape(seed, cap), np.zeros(cap, np.int32)
+    tc = None
+    if carve:
+        g0 = GpuCityLayout(width=W, height=H, carve_subblock_roads=True)
+        g0.set_bands(hb, vb)
+        g0._build_roads_and_sidewalks()
+        n, table = g0.label_nothing()
+        tc = tapes.synth_carve_tape(seed, table.cpu().numpy())
+    ref = _single(dict(width=W, height=H), carve, hb, vb, tz, tc, te)
+    sh = ShardedCityLayout(n_shards, halo=192, lean=True, width=W, height=H, carve_subblock_roads=carve)
+    sh.set_bands(hb, vb)
+    sh.generate(tz, tc, te)
+    assert sh.n_blocks == ref.n_blocks
+    _compare(ref, sh)
+    # the digests are those of real bytes: every pass left a non-zero digest on both sides of a cut
+    d = sh._dig[1].cpu().numpy()
+    assert (d[[0, 2, 3, 4, 5, 6, 7]][:, :2] != 0).all()
+
+
+def test_lean_shards_refuse_a_halo_that_is_too_small():
+    """With a halo of 10 rows, all of them verified, the zone that a shard cannot compute correctly (blocks cut by the window
+    edge, their entrances, the lights next to them) lies in the compared rows: the digests differ (or a block straddles the
+    whole halo) and the call raises instead of returning a different city."""
+    from trafficsimulation_b200 import _lib, tapes
+    from trafficsimulation_b200.sharded import ShardedCityLayout
+    W, H = 768, 1024
+    hb, vb = tapes.synth_bands(31, width=W, height=H)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    sh = ShardedCityLayout(4, halo=10, lean=True, verify=10, width=W, height=H)
+    sh.set_bands(hb, vb)
+    with pytest.raises(_lib.TsimError):
+        sh.generate(tapes.synth_zone_tape(31, cap), None, None)

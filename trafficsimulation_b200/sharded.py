@@ -19,6 +19,18 @@ out-of-window rows do not exist), then the shards refresh their halo rows from t
   the "changed" flags, repeat until no shard changed.  Dead-end removal treats rows beyond a shard cut as
   unknown (= road), so missing information can only delay a removal (the pass is monotone).
 
+LEAN mode (``lean=True``; what ``bench.py --gpus N`` runs): no halo refresh at all.  A shard computes its halo rows itself
+on every pass; what it cannot see beyond its window edge spoils at most the dependency radius of the pass, pass after pass,
+from the edge inwards, so with a halo deeper than the sum of the radii (block height for carving / zoning / entrances,
+``traffic_light_range`` + the reach of the local `leads_to` searches for the lights, 1 for the stencils: about 150 rows
+with the defaults, hence ``halo=192``) the own rows come out exact without a single exchange.  "Deeper than the sum" is
+not taken on trust (dead-end chains have no a-priori length): after EVERY pass both shards of a cut digest the
+``verify`` rows on either side of it (``tsim_rows_digest``, position-weighted, a few hundred KB read per band), and the
+digests are compared once at the end -- one all-gather of a few hundred bytes.  Spoilt data can only reach an own row by
+first spoiling the verify band of the previous pass, where the owner's copy is still exact, so equal digests on both sides
+of every cut prove the own rows exact; a mismatch raises ``TSIM_ERR_CAPACITY`` (flag 26: halo too small).  What is left of
+the communication is the all-gather of the root counts per labelling (global block ids) and that comparison.
+
 Two deployments share this code: one process per GPU under ``torch.distributed`` (NCCL; gloo on CPU for
 the host-logic tests) with one local shard each, or ONE process holding all shards on one device (how the
 ``-m gpu`` tests check N-shard == 1-shard on a single GPU).  The data path has no other collective.
@@ -162,7 +174,10 @@ class ShardedCityLayout:
     """``GpuCityLayout`` over row-band shards.  Same constructor kwargs as the reference ``CityModel`` plus the
     shard geometry; ``generate`` runs the reference's pass sequence (city_model.py:125-139, 148)."""
 
-    def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, global_reach=False, cuts=None, **city_kwargs):
+    PASSES = ("frame", "carve", "zones", "dead_ends", "upgrade_r2", "entrances", "fix_dirs", "lights")
+
+    def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, global_reach=False, cuts=None, lean=False,
+                 verify=None, **city_kwargs):
         from .layout import GpuCityLayout
         self.kw = dict(city_kwargs)
         self.width, self.height = int(city_kwargs.get("width", 200)), int(city_kwargs.get("height", 200))
@@ -170,6 +185,10 @@ class ShardedCityLayout:
         self.comm = Comm(n_shards, distributed, group)
         self.carve = bool(city_kwargs.get("carve_subblock_roads", False))
         self.global_reach = bool(global_reach)
+        self.lean = bool(lean) and n_shards > 1
+        self.verify = int(min(80, halo // 2) if verify is None else verify)   # rows on either side of a cut whose digests are compared
+        if self.lean and (self.global_reach or not 0 < self.verify <= halo):
+            raise ValueError("lean shards: verify rows must fit the halo, and the reachability exchange is not available")
         self.shards = {}
         for i, s in enumerate(self.comm.local):
             dev = (devices[i] if devices else (city_kwargs.get("device", "cuda:0")))
@@ -178,6 +197,9 @@ class ShardedCityLayout:
                                            win_halo=self.plan.halo, **kw)
         self.n_blocks = None
         self.trace = None   # set to [] to collect (label, cuda event) pairs of one generate() call (see phase_times)
+        # lean mode: digests[pass][band] per local shard; bands: 0 own rows above the lower cut, 1 halo rows below it,
+        # 2 own rows below the upper cut, 3 halo rows above it (int64 bit patterns of the unsigned digests)
+        self._dig = {s: torch.zeros(len(self.PASSES), 4, dtype=torch.int64, device=L.device) for s, L in self.shards.items()} if self.lean else None
 
     # ------------------------------------------------------------------ plumbing
     def set_bands(self, hbands, vbands):
@@ -193,6 +215,36 @@ class ShardedCityLayout:
     def _exchange(self, *names):
         wl = self.plan.win_lo
         self.comm.exchange(self.plan, [(lambda s, lo, hi, name=name: self._plane(s, name)[lo - wl[s]: hi - wl[s]], None) for name in names])
+
+    def _digest(self, pass_name, what):
+        """Lean mode: add the digests of the verify bands around this shard's cuts after pass `pass_name` (`what`: plane mask)."""
+        if not self.lean:
+            return
+        import ctypes as C
+        from . import _lib
+        p, v, k = self.plan, self.verify, self.PASSES.index(pass_name)
+        for s, L in self.shards.items():
+            w0 = p.win_lo[s]
+            bands = []
+            if s > 0:
+                bands += [(0, p.own_lo[s], p.own_lo[s] + v), (1, p.own_lo[s] - v, p.own_lo[s])]
+            if s + 1 < p.n:
+                bands += [(2, p.own_hi[s] - v, p.own_hi[s]), (3, p.own_hi[s], p.own_hi[s] + v)]
+            for b, lo, hi in bands:
+                out = C.c_void_p(self._dig[s].data_ptr() + 8 * (4 * k + b))
+                _lib.check(L.lib.tsim_rows_digest(C.byref(L.cfg), C.byref(L._planes), lo - w0, hi - w0, what, out, L._stream))
+
+    def _verify_digests(self):
+        """Lean mode, end of the pipeline: every cut's two shards must have digested the same bytes after every pass."""
+        gathered = self.comm.all_gather({s: d.reshape(-1) for s, d in self._dig.items()})
+        for s, L in self.shards.items():
+            g = gathered[s].view(self.plan.n, len(self.PASSES), 4)
+            bad = torch.zeros((), dtype=torch.bool, device=L.device)
+            if s > 0:
+                bad = bad | (g[s, :, 1] != g[s - 1, :, 2]).any() | (g[s, :, 0] != g[s - 1, :, 3]).any()
+            if s + 1 < self.plan.n:
+                bad = bad | (g[s, :, 2] != g[s + 1, :, 1]).any() | (g[s, :, 3] != g[s + 1, :, 0]).any()
+            L.flags[0] = torch.where(bad & (L.flags[0] == 0), torch.full_like(L.flags[0], ERR_HALO), L.flags[0])
 
     def _label_and_number(self):
         """Label every window, then turn the window-local numbering into global raster ranks (id_base)."""
@@ -276,6 +328,8 @@ class ShardedCityLayout:
             return
         if tape_entrance is None:                             # per-block tapes are indexed by GLOBAL block id
             tape_entrance = np.zeros(self.global_cap, np.int32)
+        if self.lean:
+            return self._generate_lean(tape_zone, tape_carve, tape_entrance, check, lights, maps)
         self._mark("start")
         for L in S.values():
             L._build_roads_and_sidewalks()                    # closed form: exact on the whole window, no exchange
@@ -324,6 +378,65 @@ class ShardedCityLayout:
             for L in S.values():
                 L._build_simple_maps()
             self._mark("maps")
+        if check:
+            self._check("generate")
+            self.n_blocks = int(self._total.item())
+
+    def _generate_lean(self, tape_zone, tape_carve, tape_entrance, check, lights, maps):
+        """The pipeline without halo exchanges (module docstring): every pass on the whole window, a digest of the verify bands
+        after it, one comparison at the end.  Communication: the root counts of the labellings and the digests."""
+        S = self.shards
+        T, D, A, B = 1, 2, 4, 8
+        for d in self._dig.values():
+            d.zero_()
+        self._mark("start")
+        for L in S.values():
+            L._build_roads_and_sidewalks()
+        self._digest("frame", T | D | A)
+        self._mark("frame_roads")
+        if self.carve:
+            self._label_and_number()
+            self._mark("carve: label + number")
+            for s, L in S.items():
+                L._carve_subblock_roads(tape_carve[s] if isinstance(tape_carve, dict) else tape_carve, check=False, relabel=False)
+            self._digest("carve", T | D | A)
+            self._mark("carve")
+        self._label_and_number()
+        self._mark("zones: label + number")
+        for L in S.values():
+            L._flood_fill_blocks_storing_data(tape_zone, check=False, relabel=False)
+        self._digest("zones", T | B)
+        self._mark("zones")
+        for L in S.values():
+            L._eliminate_dead_ends()                          # local fixed point; a chain that comes in over the window edge shows in the digests
+        self.dead_end_rounds = 1
+        self._digest("dead_ends", T | D | A)
+        self._mark("dead_ends")
+        for L in S.values():
+            L._upgrade_r2_to_intersections(check=False)
+        self._digest("upgrade_r2", T | D | A)
+        self._mark("upgrade_r2")
+        for L in S.values():
+            L._final_place_block_entrances(tape_entrance, check=False)
+        self._digest("entrances", T | D | A | B)
+        self._mark("entrances")
+        for L in S.values():
+            L._remove_invalid_intersection_directions()
+            L._add_entrance_directions()
+        self._digest("fix_dirs", D)
+        self._mark("fix_dirs")
+        if lights:
+            for L in S.values():
+                L._add_traffic_lights(check=False)
+            self.reach_rounds = 1
+            self._digest("lights", T | A | B)
+            self._mark("lights")
+        if maps:
+            for L in S.values():
+                L._build_simple_maps()
+            self._mark("maps")
+        self._verify_digests()
+        self._mark("verify")
         if check:
             self._check("generate")
             self.n_blocks = int(self._total.item())
