@@ -29,15 +29,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# algorithmic bytes per cell per pass
-PASS_BYTES = {"frame_roads": 4, "carve": 6, "zones": 6, "dead_ends": 2, "upgrade_r2": 4, "entrances": 6,
-              "fix_dirs": 10, "lights": 5, "maps": 8}
+# algorithmic bytes per cell per pass.  SURVEY.md §8d counts dense reads + writes (frame 4, carve 6, zones 6, dead ends 2 per sweep,
+# R2 4, entrances 6, direction fixes 5 + 5, lights 5, maps 8 = 52 with one sweep); where a pass only CHANGES a sparse set of cells
+# the compulsory traffic is the read alone, and that smaller figure is the one the fractions below use (so that no fraction can
+# exceed 1): R2 upgrade reads T (1 B), the direction fixes read T + D (3 B).
+SURVEY_BYTES = {"frame_roads": 4, "carve": 6, "zones": 6, "dead_ends": 2, "upgrade_r2": 4, "entrances": 6, "fix_dirs": 10, "lights": 5, "maps": 8}
+PASS_BYTES = dict(SURVEY_BYTES, upgrade_r2=1, fix_dirs=3)
 CPU_SAMPLE = 2048   # the CPU arm runs a CPU_SAMPLE x CPU_SAMPLE city per step
-# dram__bytes_read.sum + dram__bytes_write.sum per pass of ONE 16384 x 16384 city, summed over the pass's kernels, from the
-# committed ncu capture (profiles/r1_pass_traffic_16384.txt, profiles/r1_ncu_metrics_16384.csv); other sizes: null
-ROOFLINE_TRAFFIC_16384 = {"frame_roads": 1055145728, "carve": 1563896064, "zones": 2775480064, "dead_ends": 274719488,
-                          "upgrade_r2": 269025792, "entrances": 1040451072, "fix_dirs": 942758400, "lights": 7055882752,
-                          "maps": 2092813056}
+PASS_TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r2_pass_traffic_16384.json")   # written by profiles/pass_traffic.py from an ncu launch list
+
+
+def pass_traffic(size):
+    """DRAM bytes and kernel shares per pass of one 16384 x 16384 city, from the committed ncu capture (None for other sizes)."""
+    if size != 16384 or not os.path.exists(PASS_TRAFFIC_JSON):
+        return None
+    return json.load(open(PASS_TRAFFIC_JSON))["passes"]
 
 
 def measured_peaks():
@@ -420,6 +426,17 @@ def route_planning_leg(dev, n_queries=16384):
             "sample_matches_oracle": bool(same)}
 
 
+def capture_or_none(city, fn):
+    """CUDA graph of one step (GpuCityLayout.capture), or (None, None) with the reason on stderr: the numbers then are eager ones."""
+    import torch
+    try:
+        return city.capture(fn)
+    except Exception as e:   # noqa: BLE001 -- reported; the eager path is the same kernels
+        print(f"bench: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+        torch.cuda.synchronize()
+        return None, None
+
+
 def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
     """BASELINE.json configs[1] (4096 x 4096, all passes, 1 GPU) next to the headline size: device-resident cells/s."""
     import torch
@@ -434,17 +451,23 @@ def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(warmup):
         sh.generate(tz, tc, te, check=False)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for a, b in ev:
-        flush.fill_(1)
-        a.record()
-        sh.generate(tz, tc, te, check=False)
-        b.record()
-    torch.cuda.synchronize()
-    sh.shards[0]._check_flag("small_city_leg")
-    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+
+    def timed(step_fn):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            step_fn()
+            b.record()
+        torch.cuda.synchronize()
+        sh.shards[0]._check_flag("small_city_leg")
+        return sum(a.elapsed_time(b) for a, b in ev) / steps
+    ms_eager = timed(lambda: sh.generate(tz, tc, te, check=False))
+    graph, launches = capture_or_none(sh.shards[0], lambda: sh.generate(tz, tc, te, check=False))
+    ms = timed(graph.replay) if graph is not None else ms_eager
     return {"workload": f"{size}x{size} synthetic city layout, all generation passes, 1 GPU (BASELINE.json configs[1])",
             "value": size * size / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms, "steps": steps,
+            "cuda_graph": graph is not None, "launches_per_step": launches, "ms_per_step_without_graph": ms_eager,
             "frac_of_measured_peak": round(size * size * sum(PASS_BYTES.values()) / (ms * 1e-3) / 1e9 / measured_peaks()[0], 4)}
 
 
@@ -493,6 +516,12 @@ def ours(args):
         step()
     torch.cuda.synchronize()
     city._check_flag("warmup")
+    # one city = one CUDA graph launch on a single device (every launch is static); shards interleave NCCL collectives and stay eager
+    eager_step, graph, graph_launches = step, None, None
+    if world == 1 and not args.no_graph:
+        graph, graph_launches = capture_or_none(city, eager_step)
+        if graph is not None:
+            step = graph.replay
 
     # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events on the launch stream
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -509,6 +538,8 @@ def ours(args):
         b.record()
     barrier()
     launches = city.lib.tsim_launch_count() - launches0   # counted inside libtsim at every kernel launch
+    if graph is not None:
+        launches = graph_launches * args.steps              # replayed: the launches the graph holds (counted while it was captured)
     ms = sum(a.elapsed_time(b) for a, b in ev)
     city._check_flag("timed steps")
     t_dev = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -540,12 +571,33 @@ def ours(args):
                 acc[n] += marks[i].elapsed_time(marks[i + 1])
         peak, peak_src = measured_peaks()
         sweeps = city.sweeps()
+        traffic = pass_traffic(size)
         for n in names:
             t = acc[n] / reps
             bpc = PASS_BYTES[n] * (sweeps if n == "dead_ends" else 1)
             gbs = cells * bpc / (t * 1e-3) / 1e9
-            passes[n] = {"ms": round(t, 4), "cells_per_s": cells / (t * 1e-3), "alg_bytes_per_cell": bpc,
-                         "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4)}
+            passes[n] = {"ms": round(t, 4), "cells_per_s": cells / (t * 1e-3), "alg_bytes_per_cell": bpc, "survey_bytes_per_cell": SURVEY_BYTES[n],
+                         "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 4), "frac_of_nominal_8tbs": round(gbs / 8000.0, 4)}
+            if traffic and n in traffic:   # what the pass really moved (ncu, committed capture) over the time measured here
+                tr = traffic[n]
+                passes[n].update(dram_bytes=int(tr["dram_bytes"]), dram_gbs=round(tr["dram_bytes"] / (t * 1e-3) / 1e9, 1), launches=tr["launches"],
+                                 top_kernel=tr["top_kernel"], top_kernel_share=tr["top_kernel_share"])
+        # the lights pass stage by stage (tsim_lights_prepare / _eval / _links): its top kernel, lights_eval_kernel<0>, IS the eval stage
+        # but for four launches that return at once, so that stage's time is the kernel's own duration, measured live
+        stage = {"prepare": 0.0, "eval": 0.0, "links": 0.0}
+        for _ in range(reps):
+            for f in calls[:7]:
+                f()
+            flush.fill_(1)
+            ev4 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev4[0].record(); city._lights_prepare(); ev4[1].record(); city._lights_eval(); ev4[2].record(); city._lights_links(check=False); ev4[3].record()
+            torch.cuda.synchronize()
+            for i, k in enumerate(stage):
+                stage[k] += ev4[i].elapsed_time(ev4[i + 1]) / reps
+        n_cr = int(city.workspace[: 64 * 4].view(torch.int32)[12].item())
+        passes["lights"]["stages_ms"] = {k: round(v, 4) for k, v in stage.items()}
+        passes["lights"]["candidates"] = n_cr
+        passes["lights"]["undecided"] = city.lights_undecided()
     shard_phases = None
     if world > 1:   # where the step time goes on shards: device time between the marks of one more (untimed) step
         barrier()
@@ -618,11 +670,25 @@ def ours(args):
         pipeline_gbs = cells * total_alg_per_cell * args.steps / (ms * 1e-3) / 1e9   # per GPU
         if passes:
             top = max(passes, key=lambda n: passes[n]["ms"])
-            roof = {"bound": "hbm", "kernel": top, "achieved": passes[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": passes[top]["frac_of_measured_peak"], "traffic": ROOFLINE_TRAFFIC_16384.get(top) if size == 16384 else None, "peak_source": peak_src,
-                    "note": "the dominant PASS (all kernels of one tsim_layout_* call, timed with CUDA events on the launch stream); its top kernel and "
-                            "every kernel's share are in profiles/r1b_launches_bench_16384.summary.txt",
-                    "algorithmic_bytes_per_launch": cells * passes[top]["alg_bytes_per_cell"]}
+            tp = passes[top]
+            if top == "lights":   # kernel-level: the eval stage is lights_eval_kernel<0>
+                k_ms = tp["stages_ms"]["eval"]
+                # what that kernel must move: T + D of every cell once (3 B/cell: the candidates and the lanes behind them are spread over
+                # the whole city), its list entry and its record per candidate (4 + 8 B)
+                k_bytes = cells * 3 + tp["candidates"] * 12
+                k_dram = (pass_traffic(size) or {}).get("lights", {}).get("kernels", {}).get("lights_eval_kernel<0>", {}).get("dram_bytes")
+                roof = {"bound": "hbm", "kernel": "tsim::lights_eval_kernel<0> (top kernel of the top pass, lights)", "kernel_ms": round(k_ms, 4), "kernel_launches_per_step": 1,
+                        "achieved": round(k_bytes / (k_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s", "frac": round(k_bytes / (k_ms * 1e-3) / 1e9 / peak, 4),
+                        "traffic": int(k_dram) if k_dram else None, "dram_gbs": round(k_dram / (k_ms * 1e-3) / 1e9, 1) if k_dram else None,
+                        "algorithmic_bytes_per_launch": int(k_bytes), "peak_source": peak_src,
+                        "note": "duration = CUDA events around tsim_lights_eval on the launch stream (that stage is this kernel plus four launches that return at "
+                                "once); traffic = dram__bytes_read + write of the kernel in the committed ncu capture (profiles/r2_pass_traffic_16384.json)",
+                        "pass": {"name": top, "ms": tp["ms"], "frac": tp["frac_of_measured_peak"], "dram_gbs": tp.get("dram_gbs"), "dram_bytes": tp.get("dram_bytes")}}
+            else:
+                roof = {"bound": "hbm", "kernel": f"tsim::{tp.get('top_kernel', top)} (top kernel of the top pass, {top}; share {tp.get('top_kernel_share')})",
+                        "achieved": tp["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": tp["frac_of_measured_peak"], "traffic": tp.get("dram_bytes"),
+                        "dram_gbs": tp.get("dram_gbs"), "peak_source": peak_src, "algorithmic_bytes_per_launch": cells * tp["alg_bytes_per_cell"],
+                        "note": "pass-level: all kernels of the tsim_layout_* call, CUDA events on the launch stream"}
         else:
             roof = {"bound": "hbm", "kernel": "whole pipeline (per GPU)", "achieved": round(pipeline_gbs, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(pipeline_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
@@ -636,7 +702,7 @@ def ours(args):
                        "cells_per_gpu": cells,
                        "parallelism": (f"{world} row-band shards of {own_rows} rows (+{halo} halo rows computed redundantly, no halo exchange; the rows around "
                                        "every cut are digested after every pass and compared at the end of the step; NCCL all-gather of root counts and digests") if world > 1 else "single GPU",
-                       "l2": "flushed between timed steps (256 MiB write)", "seed": seed,
+                       "l2": "flushed between timed steps (256 MiB write)", "seed": seed, "cuda_graph": graph is not None,
                        "blocks": n_blocks, "lights": int(n_lights.item()), "dead_end_sweeps": city.sweeps(),
                        "shard_rounds": {"dead_ends": getattr(sh, "dead_end_rounds", 1), "reach": getattr(sh, "reach_rounds", 1)}},
             "clocks": clocks.summary(t_clk0, t_clk1),
@@ -644,8 +710,8 @@ def ours(args):
                     "note": "host buffers in and out every step; the copy-out of step i (from a device staging copy, second stream) overlaps the kernels of step i+1"},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "pipeline": {"algorithmic_bytes_per_cell": total_alg_per_cell, "achieved_gbs_per_gpu": round(pipeline_gbs, 1),
-                         "frac_of_measured_peak": round(pipeline_gbs / peak, 4)},
+            "pipeline": {"algorithmic_bytes_per_cell": total_alg_per_cell, "survey_bytes_per_cell": sum(SURVEY_BYTES.values()), "achieved_gbs_per_gpu": round(pipeline_gbs, 1),
+                         "frac_of_measured_peak": round(pipeline_gbs / peak, 4), "frac_of_nominal_8tbs": round(pipeline_gbs / 8000.0, 4)},
             "passes": passes,
             "shard_phases_ms": shard_phases,
         }
@@ -711,6 +777,7 @@ def main():
     ap.add_argument("--no-sharded-tick", action="store_true", help="N > 1: skip the sharded vehicle-tick leg")
     ap.add_argument("--shard-width", type=int, default=65536, help="N > 1: columns of the sharded city")
     ap.add_argument("--shard-rows", type=int, default=8192, help="N > 1: rows per GPU of the sharded city")
+    ap.add_argument("--no-graph", action="store_true", help="N = 1: time eager launches instead of one CUDA graph per city")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the shifted-cut / single-GPU digest comparison")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -252,6 +252,16 @@ tsim_status tsim_lights_reach_planes(const tsim_cfg *cfg, size_t ws_bytes, size_
 tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *links,
                                int32_t *err_flag, void *workspace, size_t ws_bytes, void *stream);
 
+/* tsim_layout_lights = tsim_lights_prepare + tsim_lights_eval + tsim_lights_links, for callers (bench.py) that time the stages:
+     eval  : every candidate's record.  `leads_to` beyond the lane itself is settled by local searches (Z-shaped witnesses, then
+             closures of a 128 x 128 window); the reachability planes of the window are only closed, inside this call, when a
+             query is left over
+     links : light numbering, link tables, cell conversion (the second half of tsim_lights_finish) */
+tsim_status tsim_lights_eval(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *links, int32_t *err_flag,
+                             void *workspace, size_t ws_bytes, void *stream);
+tsim_status tsim_lights_links(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *links, int32_t *err_flag,
+                              void *workspace, size_t ws_bytes, void *stream);
+
 /* _build_simple_maps (city_model.py:2151-2199) */
 tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint8_t *is_road, uint8_t *road_type,
                       uint8_t *intersection, uint8_t *allowed_dirs, void *stream);

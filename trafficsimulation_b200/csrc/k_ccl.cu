@@ -45,7 +45,6 @@ struct Prod {            // product short cut (see the header comment)
     int32_t *scal;       // [1] is product, [2] row runs, [3] column runs, [4..5] target cells (64-bit), [6] 0 if product else INT_MAX
 };
 enum { PS_FLAG = 1, PS_NRG = 2, PS_NCG = 3, PS_POPC = 4, PS_GATE = 6 };
-constexpr int PROD_MAX_RUN = 4096;   // a longer run of rows / columns is left to the general path
 
 struct Runs {            // lives in the caller's workspace between the label call and the zoning call
     u64 *M;              // [wp * LH] target bit-plane
@@ -252,56 +251,77 @@ __global__ void __launch_bounds__(256) prod_reduce_kernel(int LH, int wp, const 
     }
 }
 
-// one CTA: runs of consecutive hit rows / hit columns, numbered in order, and the verdict "the plane is rows x columns"
+// one CTA: runs of consecutive hit rows / hit columns, numbered in order, and the verdict "the plane is rows x columns".
+// Both axes are handled as BIT strings in shared memory (a row / column per bit): run starts and run ends are one shift
+// and one AND per word, their numbering a popcount scan by one warp per axis, and the run index of every row / column a
+// prefix popcount -- no serial walk anywhere (the first version walked and took 125 us per labelling).
+constexpr int PROD_MAX_AXIS = 1 << 16;   // rows / columns per axis this kernel handles (longer: the general path)
 __global__ void __launch_bounds__(1024) prod_gaps_kernel(int W, int LH, Prod p) {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry, s_bad;
-    __shared__ int s_set[2];
+    __shared__ uint32_t s_bits[2][PROD_MAX_AXIS / 32 + 1];
+    __shared__ int s_pref[2][PROD_MAX_AXIS / 32 + 1];   // run starts before the word
+    __shared__ int s_runs[2], s_set[2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { s_bad = 0; s_set[0] = 0; s_set[1] = 0; }
+    if (W > PROD_MAX_AXIS || LH > PROD_MAX_AXIS) {
+        if (threadIdx.x == 0) { p.scal[PS_FLAG] = 0; p.scal[PS_GATE] = 0x7fffffff; }
+        return;
+    }
+    const int nwords[2] = {(LH + 31) >> 5, (W + 31) >> 5};
+    // ---- bit strings (zero padded, plus one zero word at the end)
+    for (int base = 0; base < nwords[0] * 32; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned bal = __ballot_sync(0xffffffffu, i < LH && p.row_any[i] != 0u);
+        if (lane == 0) s_bits[0][i >> 5] = bal;
+    }
+    for (int i = threadIdx.x; i < nwords[1]; i += 1024) {
+        const u64 v = p.col_any[i >> 1];
+        uint32_t b = (uint32_t)(i & 1 ? v >> 32 : v);
+        if (i == nwords[1] - 1 && (W & 31)) b &= (1u << (W & 31)) - 1u;
+        s_bits[1][i] = b;
+    }
+    if (threadIdx.x < 2) s_bits[threadIdx.x][nwords[threadIdx.x]] = 0u;
+    __syncthreads();
+    // ---- one warp per axis: number the run starts / ends, write the run bounds
+    if (w < 2) {
+        const int axis = w, nw = nwords[axis];
+        const uint32_t *bits = s_bits[axis];
+        int32_t *lo = axis ? p.cg_lo : p.rg_lo, *hi = axis ? p.cg_hi : p.rg_hi;
+        const int chunk = (nw + 31) >> 5, w0 = lane * chunk, w1 = min(w0 + chunk, nw);
+        auto starts = [&](int i) { const uint32_t b = bits[i], prev = i > 0 ? bits[i - 1] >> 31 : 0u; return b & ~((b << 1) | prev); };
+        auto ends = [&](int i) { const uint32_t b = bits[i], next = bits[i + 1] & 1u; return b & ~((b >> 1) | (next << 31)); };
+        int ns = 0, ne = 0, nb = 0;
+        for (int i = w0; i < w1; i++) { ns += __popc(starts(i)); ne += __popc(ends(i)); nb += __popc(bits[i]); }
+        int is = ns, ie = ne;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, is, o), b = __shfl_up_sync(0xffffffffu, ie, o);
+            if (lane >= o) { is += a; ie += b; }
+        }
+        const int total = __shfl_sync(0xffffffffu, is, 31);
+        nb = __reduce_add_sync(0xffffffffu, nb);
+        int ks = is - ns, ke = ie - ne;
+        for (int i = w0; i < w1; i++) {
+            s_pref[axis][i] = ks;
+            for (uint32_t m = starts(i); m; m &= m - 1) lo[ks++] = i * 32 + __ffs(m) - 1;
+            for (uint32_t m = ends(i); m; m &= m - 1) hi[ke++] = i * 32 + __ffs(m) - 1;
+        }
+        if (lane == 0) { s_runs[axis] = total; s_set[axis] = nb; p.scal[PS_NRG + axis] = total; }
+    }
+    __syncthreads();
+    // ---- run index of every row / column (-1 outside the runs)
     for (int axis = 0; axis < 2; axis++) {
         const int n = axis ? W : LH;
-        int32_t *lo = axis ? p.cg_lo : p.rg_lo, *hi = axis ? p.cg_hi : p.rg_hi, *idx = axis ? p.col_gap : p.row_gap;
-        auto on = [&](int i) -> bool {
-            if (i < 0 || i >= n) return false;
-            return axis ? ((p.col_any[i >> 6] >> (i & 63)) & 1ull) != 0ull : p.row_any[i] != 0u;
-        };
-        if (threadIdx.x == 0) s_carry = 0;
-        __syncthreads();
-        int set_local = 0;
-        for (int base = 0; base < n; base += 1024) {
-            const int i = base + threadIdx.x;
-            const bool me = on(i);
-            set_local += me;
-            const bool start = me && !on(i - 1);
-            const unsigned bal = __ballot_sync(0xffffffffu, start);
-            if (lane == 0) s_warp[w] = __popc(bal);
-            __syncthreads();
-            int before = 0, total = 0;
-#pragma unroll
-            for (int q = 0; q < 32; q++) { const int c = s_warp[q]; if (q < w) before += c; total += c; }
-            const int k = s_carry + before + __popc(bal & ((1u << lane) - 1u));
-            if (start) {
-                int e = i;
-                while (on(e + 1) && e - i < PROD_MAX_RUN) e++;
-                if (on(e + 1)) s_bad = 1;
-                lo[k] = i; hi[k] = e;
-                for (int j = i; j <= e; j++) idx[j] = k;
-            }
-            if (i < n && !me) idx[i] = -1;
-            __syncthreads();
-            if (threadIdx.x == 0) s_carry += total;
-            __syncthreads();
+        int32_t *idx = axis ? p.col_gap : p.row_gap;
+        const uint32_t *bits = s_bits[axis];
+        for (int i = threadIdx.x; i < n; i += 1024) {
+            const int wi = i >> 5, b = i & 31;
+            const uint32_t v = bits[wi], prev = wi > 0 ? bits[wi - 1] >> 31 : 0u;
+            const uint32_t st = v & ~((v << 1) | prev);
+            idx[i] = ((v >> b) & 1u) ? s_pref[axis][wi] + __popc(st & ((2u << b) - 1u)) - 1 : -1;
         }
-        set_local = __reduce_add_sync(0xffffffffu, set_local);
-        if (lane == 0 && set_local) atomicAdd(&s_set[axis], set_local);
-        __syncthreads();
-        if (threadIdx.x == 0) p.scal[PS_NRG + axis] = s_carry;
-        __syncthreads();
     }
     if (threadIdx.x == 0) {
         const unsigned long long cells = *(const unsigned long long *)(p.scal + PS_POPC);
-        const bool product = !s_bad && cells == (unsigned long long)s_set[0] * (unsigned long long)s_set[1];
+        const bool product = cells == (unsigned long long)s_set[0] * (unsigned long long)s_set[1];
         p.scal[PS_FLAG] = product ? 1 : 0;
         p.scal[PS_GATE] = product ? 0 : 0x7fffffff;
     }
@@ -470,7 +490,7 @@ static tsim_status runs_layout(const tsim_cfg *cfg, void *workspace, size_t ws_b
     r.start = (int32_t *)take((size_t)cap * 4);
     r.len = (int32_t *)take((size_t)cap * 4);
     r.rank = (int32_t *)take((size_t)cap * 4);
-    scan_tmp = (int32_t *)take((size_t)(div_up(nw > cap ? nw : cap, SCAN_TILE) + 1) * 4);
+    scan_tmp = (int32_t *)take(scan_tmp_bytes(nw > cap ? nw : cap));
     fill = (uint8_t *)take((size_t)(cap_blobs > 0 ? cap_blobs : 1));
     r.wp = wp; r.cap = cap;
     r.pr.scal = scal;

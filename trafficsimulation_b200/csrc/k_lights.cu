@@ -1077,7 +1077,7 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
     L.rt.cd = (uint8_t *)take((size_t)L.wp);
     L.cr_prefix = (int32_t *)take((size_t)L.nw * 4);
     L.tl_prefix = (int32_t *)take((size_t)L.nw * 4);
-    L.scan_tmp = (int32_t *)take((size_t)(div_up(L.nw, SCAN_TILE) + 1) * 4);
+    L.scan_tmp = (int32_t *)take(scan_tmp_bytes(L.nw));
     L.cr_cell = (int32_t *)take((size_t)L.cap_cr * 4);
     L.rec = (u64 *)take((size_t)L.cap_cr * 8);
     L.pend = (int32_t *)take((size_t)L.cap_pend * 4);
@@ -1262,8 +1262,10 @@ static int lights_stages_off() {
 // lazy == false: the caller has closed the reachability planes (tsim_lights_seed / tsim_lights_reach) and every `leads_to` is read
 // from them.  lazy == true (tsim_layout_lights): the queries are settled by the staged searches first and the planes are only
 // closed -- inside this call, around this window's own pivot -- when a query is left over.
+// what: 1 = evaluate the candidates (records, light bit-plane, aux updates), 2 = number the lights, build the link tables, convert
+// the cells; 3 = both.
 static tsim_status lights_finish_impl(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
-                                      size_t ws_bytes, void *stream, bool lazy) {
+                                      size_t ws_bytes, void *stream, bool lazy, int what = 3) {
     tsim_status st = lights_check(cfg);
     if (st != TSIM_OK) return st;
     if (!p || !p->cell_type || !p->dirs || !p->aux || !p->block_id || !lk || !err_flag || !lk->n_lights || !lk->light_cell || !lk->ctrl_off ||
@@ -1276,7 +1278,7 @@ static tsim_status lights_finish_impl(const tsim_cfg *cfg, const tsim_planes *p,
     char *w = (char *)workspace;
     size_t o = ws.end;
     auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
-    int32_t *scan_tmp = (int32_t *)take((size_t)(div_up(ws.nw > lk->cap_lights ? ws.nw : lk->cap_lights, SCAN_TILE) + 1) * 4);
+    int32_t *scan_tmp = (int32_t *)take(scan_tmp_bytes(ws.nw > lk->cap_lights ? ws.nw : lk->cap_lights));
     if (o > ws_bytes) { set_error("tsim_lights_finish needs %zu workspace bytes, got %zu", o, ws_bytes); return TSIM_ERR_WORKSPACE; }
     cudaStream_t cs = (cudaStream_t)stream;
     const int W = ws.W, H = ws.H, wp = ws.wp, cap_cr = ws.cap_cr;
@@ -1290,7 +1292,9 @@ static tsim_status lights_finish_impl(const tsim_cfg *cfg, const tsim_planes *p,
     if (fwd && (!lk->out_off || !lk->out_cell || lk->cap_out < 1)) { set_error("forward_traffic_light_range needs the outgoing link table"); return TSIM_ERR_CONFIG; }
     LightsCtx L{W, H, cfg->traffic_light_range, lk->cap_lights, fwd, cfg->forward_intersections_mode, lights_stages_off(), cfg->win_y0 > 0 ? cfg->win_halo : 0,
                 cfg->win_y0 + cfg->win_rows < cfg->height ? cfg->win_halo : 0, p->cell_type, p->dirs, bp, err_flag};
-    if (!lazy) {
+    if (!(what & 1)) {
+        // records are there already (tsim_lights_eval)
+    } else if (!lazy) {
         lights_eval_kernel<1><<<list_grid, 128, 0, cs>>>(L, n_cr, cr_cell, rec, p->aux, nullptr, nullptr, nullptr, 0);
         TSIM_LAUNCH_CHECK();
     } else {
@@ -1306,6 +1310,7 @@ static tsim_status lights_finish_impl(const tsim_cfg *cfg, const tsim_planes *p,
         lights_eval_kernel<2><<<pgrid, 128, 0, cs>>>(L, n_pend2, cr_cell, rec, p->aux, ws.pend2, nullptr, nullptr, ws.cap_pend);
         TSIM_LAUNCH_CHECK();
     }
+    if (!(what & 2)) return TSIM_OK;
     // 5. lights in ascending cell order
     bit_count_kernel<<<div_up(nw, 256), 256, 0, cs>>>(nw, bp.tl, tl_prefix);
     TSIM_LAUNCH_CHECK();
@@ -1340,6 +1345,16 @@ static tsim_status lights_finish_impl(const tsim_cfg *cfg, const tsim_planes *p,
 extern "C" tsim_status tsim_lights_finish(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
                                           size_t ws_bytes, void *stream) {
     return lights_finish_impl(cfg, p, lk, err_flag, workspace, ws_bytes, stream, false);
+}
+
+extern "C" tsim_status tsim_lights_eval(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
+                                        size_t ws_bytes, void *stream) {
+    return lights_finish_impl(cfg, p, lk, err_flag, workspace, ws_bytes, stream, true, 1);
+}
+
+extern "C" tsim_status tsim_lights_links(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag, void *workspace,
+                                         size_t ws_bytes, void *stream) {
+    return lights_finish_impl(cfg, p, lk, err_flag, workspace, ws_bytes, stream, true, 2);
 }
 
 extern "C" tsim_status tsim_layout_lights(const tsim_cfg *cfg, const tsim_planes *p, const tsim_light_links *lk, int32_t *err_flag,

@@ -1,91 +1,93 @@
-// k_scan.cu -- exclusive scan building blocks (tile sums -> single-CTA scan of sums -> tile scans)
+// k_scan.cu -- exclusive scan in one pass over the data: chained scan with decoupled look-back.
+//
+// Every CTA takes a ticket (so that a CTA only ever waits for CTAs that started before it), scans its tile of 4096 elements
+// in registers, publishes the tile's sum as a 64-bit status word (flag | value: one store, no fence needed), then walks back
+// over the predecessors' status words -- sums until it meets a word that already is an inclusive prefix -- publishes its own
+// inclusive prefix and writes its elements.  One read and one write of the data, one launch (the three-kernel form it
+// replaces -- tile sums, single-CTA scan of the sums, tile scans -- read the data twice and cost three launches, nine times
+// per city).
 #include "scan.cuh"
 
 namespace tsim {
 
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(int ntiles, int32_t *tile_count, int32_t *n_out) {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < ntiles; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < ntiles ? tile_count[i] : 0;
-        int incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int w = s_warp[threadIdx.x];
-            int wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += t; }
-            s_warp[threadIdx.x] = wi - w;   // exclusive warp offsets
-        }
-        __syncthreads();
-        const int excl = s_carry + s_warp[threadIdx.x >> 5] + incl - v;
-        if (i < ntiles) tile_count[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *n_out = s_carry;
-}
+typedef unsigned long long u64;
+constexpr int SCAN_ITEMS = SCAN_TILE / 256;
+constexpr u64 ST_SUM = 1ull << 32, ST_PREFIX = 2ull << 32;
 
-__global__ void __launch_bounds__(256) tile_sum_kernel(long long n, const int32_t *__restrict__ n_dev, const int32_t *__restrict__ data,
-                                                       int32_t *__restrict__ tile_sum) {
-    __shared__ int s_sum;
-    if (n_dev && *n_dev < n) n = *n_dev;   // the live prefix of a capacity-sized array
-    const long long base = (long long)blockIdx.x * SCAN_TILE;
-    if (base >= n) { if (threadIdx.x == 0) tile_sum[blockIdx.x] = 0; return; }
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_TILE / 256; k++) {
-        const long long i = base + k * 256 + threadIdx.x;
-        if (i < n) c += data[i];
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_sum, c);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = s_sum;
-}
-
-__global__ void __launch_bounds__(256) tile_scan_kernel(long long n, const int32_t *__restrict__ n_dev, int32_t *data,
-                                                        const int32_t *__restrict__ tile_off) {
+__global__ void __launch_bounds__(256) scan_lookback_kernel(long long n, const int32_t *__restrict__ n_dev, int32_t *data, u64 *status, int32_t *ticket,
+                                                            int32_t *total_out, int ntiles) {
+    __shared__ int s_tile, s_prefix;
     __shared__ int s_warp[8];
-    if (n_dev && *n_dev < n) n = *n_dev;
-    const long long base = (long long)blockIdx.x * SCAN_TILE;
-    if (base >= n) return;
-    int running = tile_off[blockIdx.x];
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    if (n_dev) { const long long live = *n_dev; if (live < n) n = live < 0 ? 0 : live; }
+    const long long base = (long long)tile * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n && (((uintptr_t)data) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            const int4 q = *reinterpret_cast<const int4 *>(data + base + 4 * k);
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) v[k] = base + k < n ? data[base + k] : 0;
+    }
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) sum += v[k];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int k = 0; k < SCAN_TILE / 256; k++) {
-        const long long i = base + k * 256 + threadIdx.x;
-        const int v = i < n ? data[i] : 0;
-        int incl = v;
+    int incl = sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) s_warp[w] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
 #pragma unroll
-        for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < w) before += c; total += c; }
-        if (i < n) data[i] = running + before + incl - v;
-        running += total;
-        __syncthreads();
+    for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < w) before += c; total += c; }
+    if (threadIdx.x == 0) {
+        int prefix = 0;
+        if (tile > 0) {
+            *((volatile u64 *)(status + tile)) = ST_SUM | (u64)(uint32_t)total;
+            for (int j = tile - 1;; ) {
+                const u64 s = *((volatile u64 *)(status + j));
+                if ((s >> 32) == 0) continue;          // not published yet: that CTA holds an earlier ticket, it is running
+                prefix += (int)(uint32_t)s;
+                if ((s >> 32) == 2) break;
+                j--;
+            }
+        }
+        *((volatile u64 *)(status + tile)) = ST_PREFIX | (u64)(uint32_t)(prefix + total);
+        s_prefix = prefix;
+        if (tile == ntiles - 1) *total_out = prefix + total;
+    }
+    __syncthreads();
+    int running = s_prefix + before + incl - sum;
+    if (base + SCAN_ITEMS <= n && (((uintptr_t)data) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; k++) {
+            int4 q;
+            q.x = running; running += v[4 * k];
+            q.y = running; running += v[4 * k + 1];
+            q.z = running; running += v[4 * k + 2];
+            q.w = running; running += v[4 * k + 3];
+            *reinterpret_cast<int4 *>(data + base + 4 * k) = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) data[base + k] = running; running += v[k]; }
     }
 }
 
 tsim_status exclusive_scan_i32(int32_t *data, long long n, int32_t *tmp, int32_t *total_out, cudaStream_t cs, const int32_t *n_dev) {
     if (n <= 0) { TSIM_CUDA(cudaMemsetAsync(total_out, 0, 4, cs)); return TSIM_OK; }
+    if (((uintptr_t)tmp) & 7) { set_error("exclusive_scan_i32: scratch must be 8-byte aligned"); return TSIM_ERR_CONFIG; }
     const int ntiles = div_up(n, SCAN_TILE);
-    tile_sum_kernel<<<ntiles, 256, 0, cs>>>(n, n_dev, data, tmp);
-    TSIM_LAUNCH_CHECK();
-    scan_tiles_kernel<<<1, 1024, 0, cs>>>(ntiles, tmp, total_out);
-    TSIM_LAUNCH_CHECK();
-    tile_scan_kernel<<<ntiles, 256, 0, cs>>>(n, n_dev, data, tmp);
+    u64 *status = reinterpret_cast<u64 *>(tmp);
+    int32_t *ticket = reinterpret_cast<int32_t *>(status + ntiles);
+    TSIM_CUDA(cudaMemsetAsync(tmp, 0, (size_t)ntiles * 8 + 8, cs));
+    scan_lookback_kernel<<<ntiles, 256, 0, cs>>>(n, n_dev, data, status, ticket, total_out, ntiles);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

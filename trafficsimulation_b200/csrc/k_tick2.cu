@@ -359,8 +359,11 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
     TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick2_kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;
-    // a barrier costs more the more CTAs arrive: just enough CTAs for the fleet, at most `k` per SM (TSIM_TICK_CTAS_PER_SM, default 4)
-    int k = 4;
+    // A barrier costs more the more CTAs arrive, a thread with many vehicles serialises their load chains: one CTA per SM up to
+    // ~4 vehicles per thread, then more (measured: 100 k vehicles 0.081 / 0.094 / 0.088 ms per tick at 1 / 2 / 4 CTAs per SM,
+    // 1 M vehicles 1.22 / 0.85 / 0.71).  TSIM_TICK_CTAS_PER_SM overrides.
+    int k = (int)(((long long)tp->n_vehicles + (long long)sms * 256 * 4 - 1) / ((long long)sms * 256 * 4));
+    k = k < 1 ? 1 : (k > 4 ? 4 : k);
     if (const char *e = getenv("TSIM_TICK_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1) k = v; }
     if (k > per_sm) k = per_sm;
     long long want = ((long long)tp->n_vehicles + 255) / 256;

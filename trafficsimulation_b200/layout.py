@@ -249,6 +249,18 @@ class GpuCityLayout:
         if check:
             self._check_flag("_add_traffic_lights")
 
+    def _lights_eval(self):    # staged form of _add_traffic_lights: _lights_prepare, _lights_eval, _lights_links
+        lk = self._links_struct()
+        _lib.check(self.lib.tsim_lights_eval(C.byref(self.cfg), C.byref(self._planes), C.byref(lk), self._flag_ptr(0), _ptr(self.workspace),
+                                             C.c_size_t(self.workspace.numel()), self._stream))
+
+    def _lights_links(self, check=True):
+        lk = self._links_struct()
+        _lib.check(self.lib.tsim_lights_links(C.byref(self.cfg), C.byref(self._planes), C.byref(lk), self._flag_ptr(0), _ptr(self.workspace),
+                                              C.c_size_t(self.workspace.numel()), self._stream))
+        if check:
+            self._check_flag("_add_traffic_lights")
+
     def _links_struct(self):
         n = self.width * self.win_rows
         cap_l, cap_c, cap_i = max(1024, n // 16), max(1024, n // 8), max(4096, n // 2)
@@ -306,6 +318,19 @@ class GpuCityLayout:
             self._add_traffic_lights(check=check)
         if maps:
             self._build_simple_maps()
+
+    def capture(self, fn):
+        """CUDA graph of one call of ``fn()`` (any sequence of this object's passes with device-resident tapes and ``check=False``):
+        every launch of the pipeline is static -- grids, pointers, the cooperative kernels included -- so a city is ONE graph launch
+        instead of ~90 kernel launches.  Returns (graph, launches): ``graph.replay()`` regenerates the city from whatever the tape
+        tensors hold at that moment.  ``fn`` is run once eagerly first (allocations, lazy initialisation happen outside the capture)."""
+        fn()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        n0 = self.lib.tsim_launch_count()
+        with torch.cuda.graph(g):
+            fn()
+        return g, int(self.lib.tsim_launch_count() - n0)
 
     # ------------------------------------------------------------------ read-back
     def planes_host(self):
