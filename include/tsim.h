@@ -325,6 +325,10 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
     void *plans;                                 /* [n_vehicles] x TSIM_TICK_PLAN_BYTES                                        */
     int32_t *ev_stamp, *ev_plen;                 /* [n_vehicles] tick of the vehicle's pending route event, its length         */
     int64_t *ev_poff;                            /* [n_vehicles] ... and its offset in ev_cells                                */
+    /* vehicle-indexed kernel on a shard (optional, NULL = scan the whole attempt array): [n_vehicles] indices of the vehicles
+       alive in THIS window, rebuilt by tsim_tick_unpack after every halo refresh (scalars[12] = entries, [13] = valid for the
+       next tick), so that a shard's tick costs what its own vehicles and ghosts cost, not the fleet of the whole city          */
+    int32_t *live_idx;
 } tsim_tick_state;
 #define TSIM_TICK_VREC_BYTES 48
 #define TSIM_TICK_PLAN_BYTES 32
@@ -419,6 +423,12 @@ tsim_status tsim_astar_batch(const tsim_cfg *cfg, const tsim_astar_maps *maps, c
    NULL; density64 is the same values widened, the form tsim_astar_maps.density_map takes.  scratch: 2 bytes per cell.   */
 tsim_status tsim_density_map(const tsim_cfg *cfg, const uint8_t *occupancy, const uint8_t *is_road_map, float *density32,
                              double *density64, void *scratch, size_t scratch_bytes, void *stream);
+
+/* CityModel.rain_map (city_model.py:113) from the clouds of a tick: writes `value` (0 or 1) into every cell of the discs
+   {(cx + dx, cy + dy) : dx^2 + dy^2 <= r^2}, discs = device int32 [n][3] = (cx, cy, r) with (cx, cy) = (int(x), int(y)) of the
+   cloud in GLOBAL coordinates (RainAgent.step, agents/rain.py:61-72; cells outside the grid / the window are skipped).
+   RainManager.step (:154-185) = one call with value 0 on the previous tick's discs, one with value 1 on this tick's. */
+tsim_status tsim_rain_discs(const tsim_cfg *cfg, const int32_t *discs, int32_t n_discs, int32_t value, uint8_t *rain_map, void *stream);
 
 /* labels the 4-connected components of mask == 1 (u8 plane) in raster discovery order: component
    table as tsim_layout_label_nothing, plus the label plane (id, 0 elsewhere).  Used for the

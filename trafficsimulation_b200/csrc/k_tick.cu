@@ -148,10 +148,15 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
         const int t = *((volatile int32_t *)(s.scalars + S_TICK));
         if (t >= tp.n_ticks) { if (tid == 0) s.scalars[S_ERR] = 31; break; }
         const uint32_t gen0 = (uint32_t)t * GEN_PER_TICK + 1u;   // generation nobody writes: "no claims yet"
+        // a shard iterates the list of the vehicles alive in its window (built after the last halo refresh: valid for one tick)
+        const bool use_list = it == 0 && s.live_idx && *((volatile int32_t *)(s.scalars + S_LIST_OK)) != 0;
+        const int n_it = use_list ? min(*((volatile int32_t *)(s.scalars + S_NLIST)), nv) : nv;
         // ---- 1: phase A + light-group decisions (staged)
         int live = 0;
-        for (int v = tid; v < nv; v += nth)
+        for (int i = tid; i < n_it; i += nth) {
+            const int v = use_list ? s.live_idx[i] : i;
             if (s.alive[v]) { vehicle_decide(a, v, t); const int p = s.pos[v]; live += p >= a.own_lo && p < a.own_hi; }
+        }
         live = __reduce_add_sync(0xffffffffu, live);
         if ((threadIdx.x & 31) == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
         for (int g = tid; g < ng; g += nth) group_decide<false>(a, g);
@@ -166,7 +171,8 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
             u64 *cur = plane[iter & 1];
             const uint32_t gen_prev = gen0 + iter, gen_cur = gen0 + iter + 1;
             bool ch = false;
-            for (int v = tid; v < nv; v += nth) {
+            for (int i = tid; i < n_it; i += nth) {
+                const int v = use_list ? s.live_idx[i] : i;
                 if (!s.alive[v] || s.early[v]) continue;
                 const int r = rank[v];
                 const int k = vehicle_eval(a, v, r, prev, gen_prev);
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
         const u64 *fin_plane = plane[last & 1];
         const uint32_t gen_fin = gen0 + last + 1;
         // ---- 3: apply the moves
-        for (int v = tid; v < nv; v += nth) {
+        for (int i = tid; i < n_it; i += nth) {
+            const int v = use_list ? s.live_idx[i] : i;
             if (!s.alive[v]) continue;
             int pos = s.pos[v];
             const int target = tp.target[v];
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
             s.occupancy[o] = 1; s.stuck_map[o] = 0;   // place_vehicle city_model.py:1904-1907
         }
         scatter_events(a, t + 1, tid, nth);
-        if (tid == 0) s.scalars[S_TICK] = t + 1;
+        if (tid == 0) { s.scalars[S_TICK] = t + 1; s.scalars[S_LIST_OK] = 0; }   // this tick's spawns are not on the list
         grid.sync();
     }
 }
@@ -397,13 +404,30 @@ __global__ void __launch_bounds__(256) tick_unpack_kernel(StripArgs a) {
 // zombies nobody claimed are gone (they left the window or were never real); inside the verify rows that is a divergence
 __global__ void __launch_bounds__(256) tick_reap_kernel(StripArgs a) {
     const tsim_tick_state &s = a.st;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.nv; v += gridDim.x * blockDim.x) {
-        if (s.alive[v] != ZOMBIE) continue;
-        const int row = s.pos[v] / a.W;
-        for (int d = 0; d < 2; d++)
-            if (row >= a.sp.verify_lo[d] && row < a.sp.verify_hi[d]) s.scalars[S_XERR] = 42;
-        s.alive[v] = 0;
+    const int lane = threadIdx.x & 31;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int v0 = tid - lane; v0 < a.nv; v0 += nth) {   // whole warps: the list append is one atomic per warp
+        const int v = v0 + lane;
+        bool keep = false;
+        if (v < a.nv) {
+            const int al = s.alive[v];
+            if (al == ZOMBIE) {
+                const int row = s.pos[v] / a.W;
+                for (int d = 0; d < 2; d++)
+                    if (row >= a.sp.verify_lo[d] && row < a.sp.verify_hi[d]) s.scalars[S_XERR] = 42;
+                s.alive[v] = 0;
+            }
+            keep = al == ALIVE;
+        }
+        if (!s.live_idx) continue;
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (!mask) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(s.scalars + S_NLIST, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) s.live_idx[base + __popc(mask & ((1u << lane) - 1u))] = v;
     }
+    if (tid == 0 && s.live_idx) s.scalars[S_LIST_OK] = 1;   // the next tick_run (a later launch) may use the list
 }
 
 __global__ void fill_i32_kernel(long long n, int32_t *p, int32_t v) {
@@ -485,6 +509,7 @@ extern "C" tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tap
         TSIM_LAUNCH_CHECK();
     }
     if (a.nv > 0) {
+        if (st->live_idx) TSIM_CUDA(cudaMemsetAsync(st->scalars + S_NLIST, 0, 2 * sizeof(int32_t), cs));
         tick_reap_kernel<<<strip_grid(a.nv), 256, 0, cs>>>(a);
         TSIM_LAUNCH_CHECK();
     }

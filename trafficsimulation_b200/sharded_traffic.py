@@ -257,7 +257,7 @@ class ShardedTraffic:
         W = self.W
         for s, sim in self.sims.items():
             p, y0 = self.plan, sim.win_y0
-            st = {k: v.cpu().numpy() for k, v in sim.s.items() if k not in ("claim", "stopw", "scalars")}
+            st = {k: v.cpu().numpy() for k, v in sim.s.items() if k not in ("claim", "stopw", "scalars", "live_idx")}
             row = st["pos"][: self.nv] // W + y0
             own = (st["alive"][: self.nv] == 1) & (row >= p.own_lo[s]) & (row < p.own_hi[s])
             ids = np.flatnonzero(own)
