@@ -61,12 +61,11 @@ struct Runs {            // lives in the caller's workspace between the label ca
 
 // ---------------------------------------------------------------- 1. bit-plane of the target type
 __global__ void __launch_bounds__(256) ccl_bits_kernel(int W, int LH, int wp, const uint8_t *__restrict__ T, int target, u64 *__restrict__ M) {
-    const int spr = wp * 4;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // blockIdx.y (+ 65535 * blockIdx.z) = row, blockIdx.x * 256 + thread = 16-cell strip of the row: no division per thread
     const int q = threadIdx.x & 3;
-    const long long y_ll = g / spr;
-    const int s = (int)(g % spr), x0 = s * 16;
-    const bool row_ok = y_ll < LH;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, x0 = s * 16;
+    const long long y_ll = (long long)blockIdx.y + (long long)blockIdx.z * 65535;
+    const bool row_ok = y_ll < LH && s < wp * 4;
     uint32_t m = 0;
     if (row_ok && x0 < W) {
         const size_t base = (size_t)y_ll * W + x0;
@@ -527,7 +526,7 @@ tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int target, const 
     const Win win(*cfg);
     const long long nw = (long long)r.wp * win.LH;
     TSIM_CUDA(cudaMemsetAsync(r.n_runs, 0, 64 * 4, cs));
-    ccl_bits_kernel<<<div_up(nw * 4, 256), 256, 0, cs>>>(win.W, win.LH, r.wp, T, target, r.M);
+    ccl_bits_kernel<<<dim3(div_up(r.wp * 4, 256), win.LH < 65535 ? win.LH : 65535, div_up(win.LH, 65535)), 256, 0, cs>>>(win.W, win.LH, r.wp, T, target, r.M);
     TSIM_LAUNCH_CHECK();
     // product short cut: is the plane (rows hit) x (columns hit)?  Then the general path below is skipped on the device.
     const bool try_product = product_shortcut_enabled();

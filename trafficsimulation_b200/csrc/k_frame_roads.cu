@@ -10,6 +10,7 @@
 // the descriptors of its 4 neighbours, so the 13 in-place sweeps of the reference collapse into a
 // single pass that only WRITES the planes: 1 (type) + 2 (dirs) + 1 (aux) B/cell, no reads except
 // the O(W+H) line tables (L1/L2 resident).  block_id is written as a whole by the zoning pass.
+#include <cstdlib>
 #include "cells_frame.cuh"
 
 namespace tsim {
@@ -156,6 +157,107 @@ __global__ void __launch_bounds__(256) frame_roads_rows_kernel(tsim_cfg c, uint8
     *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
 }
 
+// ---- the bulk of the pass as TMA bulk copies ------------------------------------------------------------------------------
+// Away from the frame every row of one class IS that class's pattern row, so the bulk of the pass is a broadcast of ~60
+// cache-resident rows into 16 384 rows of the planes: pure data movement.  A CTA takes one (row class, x tile, row chunk):
+// one thread fetches the tile of the three pattern rows into shared memory with cp.async.bulk (completion on an mbarrier),
+// then every thread walks its share of the chunk's rows and, for the rows of that class, issues the three bulk stores shared ->
+// global (cp.async.bulk.global.shared::cta, SASS UBLKCP).  No register ever holds a cell: the SM issues a few hundred copy
+// descriptors instead of 8 load / store instructions per 16 cells, and the stores leave as whole 2 - 4 KB bursts.
+constexpr int TMA_ROWS = 1024;   // rows per CTA; TX = cells per tile (TX bytes of types, TX of aux, 2 TX of dirs in shared memory)
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int TMA_TX>
+__global__ void __launch_bounds__(128) frame_roads_tma_kernel(tsim_cfg c, uint8_t *__restrict__ T, uint16_t *__restrict__ D, uint8_t *__restrict__ A,
+                                                              const uint8_t *__restrict__ rowc, const uint8_t *__restrict__ pt,
+                                                              const uint16_t *__restrict__ pd, const uint8_t *__restrict__ pa, int xs, int xe) {
+    __shared__ __align__(128) uint8_t s_t[TMA_TX];
+    __shared__ __align__(128) uint8_t s_a[TMA_TX];
+    __shared__ __align__(128) uint16_t s_d[TMA_TX];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const Geo g(c);
+    const Bulk bk(g);
+    const int W = g.W;
+    const int x0 = xs + (int)blockIdx.x * TMA_TX, len = min(TMA_TX, xe - x0);
+    const int k = blockIdx.y;
+    const int ly0 = (int)blockIdx.z * TMA_ROWS, ly1 = min(ly0 + TMA_ROWS, c.win_rows);
+    if (len <= 0) return;
+    // does this chunk hold a row of class k at all?  (most (class, chunk) pairs do not: leave before fetching anything)
+    bool mine = false;
+    for (int ly = ly0 + threadIdx.x; ly < ly1; ly += blockDim.x) {
+        const int y = c.win_y0 + ly;
+        mine |= y >= bk.y0 && y <= bk.y1 && rowc[y] == k;
+    }
+    if (!__syncthreads_or(mine)) return;
+    const uint32_t bar = smem_addr(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const size_t src = (size_t)k * W + x0;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * (uint32_t)len) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(s_t)), "l"(pt + src),
+                     "r"((uint32_t)len), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(s_a)), "l"(pa + src),
+                     "r"((uint32_t)len), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(s_d)), "l"(pd + src),
+                     "r"(2u * (uint32_t)len), "r"(bar) : "memory");
+    }
+    __syncthreads();   // the barrier is initialised before anybody polls it
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    bool issued = false;
+    for (int ly = ly0 + threadIdx.x; ly < ly1; ly += blockDim.x) {
+        const int y = c.win_y0 + ly;
+        if (!(y >= bk.y0 && y <= bk.y1 && rowc[y] == k)) continue;
+        const size_t dst = (size_t)ly * W + x0;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(T + dst), "r"(smem_addr(s_t)), "r"((uint32_t)len) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(A + dst), "r"(smem_addr(s_a)), "r"((uint32_t)len) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(D + dst), "r"(smem_addr(s_d)), "r"(2u * (uint32_t)len) : "memory");
+        issued = true;
+    }
+    if (issued) {   // the tile must stay in shared memory until the copy engine has read it
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// what the bulk copies leave out: the rows outside the bulk rows (whole width) and, in the bulk rows, the strips left of xs and
+// right of xe -- closed form, 16 cells per thread.  item = (row, strip) pairs, enumerated without a division per cell.
+__global__ void __launch_bounds__(128) frame_edges_kernel(tsim_cfg c, uint8_t *__restrict__ T, uint16_t *__restrict__ D, uint8_t *__restrict__ A,
+                                                          const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt, int xs, int xe) {
+    const Geo g(c);
+    const Bulk bk(g);
+    const int W = g.W, H = g.H;
+    const int ly = blockIdx.x, y = c.win_y0 + ly;
+    const bool row_bulk = y >= bk.y0 && y <= bk.y1;
+    const int n_left = xs / 16, n_all = W / 16, first_right = xe / 16;
+    const int n_items = row_bulk ? n_left + (n_all - first_right) : n_all;
+    const uint32_t r0 = y > 0 ? __ldg(rowt + y - 1) : 0u, r1 = __ldg(rowt + y), r2 = y + 1 < H ? __ldg(rowt + y + 1) : 0u;
+    for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+        const int strip = row_bulk ? (it < n_left ? it : first_right + (it - n_left)) : it;
+        const int xv = strip * 16;
+        uint32_t tw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0}, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t cprev = xv > 0 ? __ldg(colt + xv - 1) : 0u, ccur = __ldg(colt + xv);
+        for (int k = 0; k < 16; k++) {
+            const int x = xv + k;
+            const uint32_t cnext = x + 1 < W ? __ldg(colt + x + 1) : 0u;
+            int t; uint32_t d, a;
+            frame_roads_cell(c, g, r0, r1, r2, cprev, ccur, cnext, x, y, t, d, a);
+            tw[k >> 2] |= (uint32_t)t << (8 * (k & 3));
+            aw[k >> 2] |= a << (8 * (k & 3));
+            dw[k >> 1] |= d << (16 * (k & 1));
+            cprev = ccur; ccur = cnext;
+        }
+        const size_t base = (size_t)ly * W + xv;
+        *reinterpret_cast<uint4 *>(T + base) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+        *reinterpret_cast<uint4 *>(A + base) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+        *reinterpret_cast<uint4 *>(D + base) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+    }
+}
+
 }  // namespace tsim
 
 using namespace tsim;
@@ -170,8 +272,24 @@ extern "C" tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_p
     cudaStream_t st = (cudaStream_t)stream;
     const int W = cfg->width, rows = cfg->win_rows;
     const bool aligned = !(((uintptr_t)p->cell_type | (uintptr_t)p->dirs | (uintptr_t)p->aux) & 15);
-    if (W % 16 == 0 && aligned && lines->row_class && lines->pat_type && lines->pat_dirs && lines->pat_aux &&
-        !(((uintptr_t)lines->pat_type | (uintptr_t)lines->pat_dirs | (uintptr_t)lines->pat_aux) & 15)) {
+    const bool patterns = W % 16 == 0 && aligned && lines->row_class && lines->pat_type && lines->pat_dirs && lines->pat_aux &&
+                          !(((uintptr_t)lines->pat_type | (uintptr_t)lines->pat_dirs | (uintptr_t)lines->pat_aux) & 15);
+    const Geo g(*cfg);
+    const Bulk bk(g);
+    const int xs = (bk.x0 + 15) & ~15, xe = (bk.x1 + 1) & ~15;   // the 16-cell strips that lie inside the bulk columns
+    const char *tma_env = getenv("TSIM_FRAME_TMA");
+    const int tma_tx = tma_env ? atoi(tma_env) : 0;               // TSIM_FRAME_TMA=<tile cells>: 2048 or 8192 switch the bulk-copy kernel on
+    if (patterns && xe - xs >= 64 && lines->n_row_classes > 0 && lines->n_row_classes <= 65535 && (tma_tx == 2048 || tma_tx == 8192)) {
+        dim3 grid((unsigned)div_up(xe - xs, tma_tx), (unsigned)lines->n_row_classes, (unsigned)div_up(rows, TMA_ROWS));
+        if (tma_tx == 2048)
+            frame_roads_tma_kernel<2048><<<grid, 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row_class, lines->pat_type, lines->pat_dirs,
+                                                               lines->pat_aux, xs, xe);
+        else
+            frame_roads_tma_kernel<8192><<<grid, 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row_class, lines->pat_type, lines->pat_dirs,
+                                                               lines->pat_aux, xs, xe);
+        TSIM_LAUNCH_CHECK();
+        frame_edges_kernel<<<rows, 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, xs, xe);
+    } else if (patterns) {
         dim3 grid((unsigned)div_up(W, 16 * 256) * rows);
         frame_roads_rows_kernel<<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, lines->row_class, lines->pat_type,
                                                       lines->pat_dirs, lines->pat_aux);

@@ -68,13 +68,12 @@ struct LightsCtx {
 // ---------------------------------------------------------------- 1. bit-planes from T and D
 __global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const uint8_t *__restrict__ T, const uint16_t *__restrict__ D, Bits bp,
                                                           long long mid, int32_t *piv /* [0] first >= mid, [1] first */) {
-    const int spr = bp.wp * 4;   // 16-cell strips per row (a quad of lanes = one word)
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // blockIdx.y = row, blockIdx.x * 256 + thread = 16-cell strip of the row (a quad of lanes = one word).  (As one flat index
+    // this took a 64-bit division per thread: 26 % of the kernel's stall samples.)
     const int lane = threadIdx.x & 31, q = lane & 3;
-    const long long y_ll = g / spr;
-    const int s = (int)(g % spr), x0 = s * 16;
-    const bool row_ok = y_ll < H;
-    const int y = (int)y_ll;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, x0 = s * 16;
+    const int y = blockIdx.y + blockIdx.z * 65535;
+    const bool row_ok = y < H && s < bp.wp * 4;
     uint32_t mN = 0, mE = 0, mS = 0, mW = 0, mI = 0, mR = 0;
     int p_all = 0x7fffffff, p_mid = 0x7fffffff;
     if (row_ok && x0 < W) {
@@ -713,19 +712,26 @@ __device__ u64 lights_eval(const LightsCtx &L, int cx, int cy, LT &lt) {
     for (int i = 0; i < dl_len(rd); i++) {
         const int fd = dl_get(rd, i), k = opp_of(fd);
         int bx = cx + dx_of(k), by = cy + dy_of(k), cnt = 0;
+        // type, arrows and candidate bit of a cell travel together, and the NEXT cell's are requested before this cell's are
+        // looked at: two steps of the march are in flight at any time (the march is a chain of dependent round trips otherwise;
+        // fetching all twelve cells up front was tried and lost to its own traffic)
+        struct Cell { bool in, conv; int t; uint32_t d; };
+        auto fetch = [&](int x, int y) {
+            Cell q{L.has(x, y), false, -1, 0u};
+            if (q.in) { const int i = L.at(x, y); q.conv = before_cm(x, y, cx, cy) && L.bit(L.b.cr, x, y); q.t = L.T[i]; q.d = L.D[i]; }
+            return q;
+        };
+        Cell cur = fetch(bx, by);
         while (depth <= L.tl_range) {
-            if (!L.has(bx, by)) break;
-            const int nbc = L.at(bx, by);
-            // type, arrows and candidate bit of the cell travel together (one round trip per step instead of three)
-            const bool conv = before_cm(bx, by, cx, cy) && L.bit(L.b.cr, bx, by);
-            const int bt = L.T[nbc];
-            const uint32_t bd = L.D[nbc];
-            if ((conv ? (int)T_CR : bt) != t) break;   // type_at_time
+            if (!cur.in) break;
+            const Cell nxt = depth < L.tl_range ? fetch(bx + dx_of(k), by + dy_of(k)) : Cell{false, false, -1, 0u};
+            if ((cur.conv ? (int)T_CR : cur.t) != t) break;   // type_at_time
             // the cell one step closer to c leads to c (that is why the march got here), so a cell with an arrow onto it does too;
             // only the others (lane-change arrows, opposite lanes) need a search
-            if (!dl_has(bd, fd) && !lt(nbc, c, fd, cnt + 1)) break;
+            if (!dl_has(cur.d, fd) && !lt(L.at(bx, by), c, fd, cnt + 1)) break;
             cnt++;
             bx += dx_of(k); by += dy_of(k); depth++;
+            cur = nxt;
         }
         rec |= (u64)cnt << (40 + 5 * i);
     }
@@ -852,6 +858,7 @@ __global__ void __launch_bounds__(128) lights_eval_kernel(LightsCtx L, const int
             rec[i] = r;
             mark_lights(L, c, r);   // the light cells never depend on `leads_to`
             if (!lt.undecided) { apply_aux(L, c, r, A); continue; }
+            if (!matters(L, c / L.W)) { apply_aux(L, c, r, A); continue; }   // deep in a neighbour's rows: its owner computes it, nothing here reads it
             const int k = atomicAdd(n_pend, 1);
             if (k < cap_pend) pend[k] = i; else *L.err = 28;
         } else {
@@ -958,36 +965,63 @@ __global__ void __launch_bounds__(128) light_links_kernel(LightsCtx L, const int
                                                           const int32_t *__restrict__ cr_prefix, const u64 *__restrict__ rec, int32_t *ctrl_off,
                                                           int32_t *inc_off, int32_t *__restrict__ ctrl_cell, int32_t *__restrict__ inc_cell, int cap_ctrl,
                                                           int cap_inc, int32_t *out_off, int32_t *__restrict__ out_cell, int cap_out) {
+    constexpr int CH = 4;   // candidates looked up together: their prefix words, then their records, travel as independent loads
     const int n = min(*n_lights, L.cap_lights);
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
         const int a = light_cell[l], ax = a % L.W, ay = a / L.W;
         int nc = 0, ni = 0, no = 0;
         int pc = FILL ? ctrl_off[l] : 0, pi = FILL ? inc_off[l] : 0, po = (FILL && L.fwd) ? out_off[l] : 0;
-        for (int y = max(ay - 2, 0); y <= min(ay + 2, L.H - 1); y++) {
-            const u64 *row = L.b.cr + (size_t)y * L.b.wp;
-            u64 m = extract_bits(row, L.b.wp, ax - 2, 5);
-            while (m) {
-                const int k = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const int x = ax - 2 + k, c = y * L.W + x;
-                const size_t wi = (size_t)y * L.b.wp + (x >> 6);
-                const u64 r = rec[cr_prefix[wi] + __popcll(L.b.cr[wi] & ((1ull << (x & 63)) - 1ull))];
-                bool mine = false;
-                for (int u = 0; u < rec_nacc(r); u++) mine |= rec_acc(r, u, c, L.W) == a;
-                if (!mine) continue;
-                if (L.fwd) {   // _scan_for_traffic_flow_forward, once per (light, controlled road) like the reference
-                    auto emit = [&](int cell) { if (FILL) { if (po < cap_out) out_cell[po] = cell; else *L.err = 27; po++; } else no++; };
-                    forward_scan(L, x, y, x, y, L.D[c], (int)L.T[c], 0, emit);
-                }
-                if (!FILL) { nc++; ni += rec_nsc(r); continue; }
-                if (pc < cap_ctrl) ctrl_cell[pc] = c; else *L.err = 20;
-                pc++;
-                const uint32_t rd = L.D[c];
-                for (int d = 0; d < dl_len(rd); d++) {
-                    const int kk = opp_of(dl_get(rd, d)), step = dy_of(kk) * L.W + dx_of(kk);
-                    for (int s = 1; s <= rec_cnt(r, d); s++, pi++) { if (pi < cap_inc) inc_cell[pi] = c + s * step; else *L.err = 21; }
-                }
+        auto rec_of = [&](int c) {
+            const int x = c % L.W, y = c / L.W;
+            const size_t wi = (size_t)y * L.b.wp + (x >> 6);
+            return cr_prefix[wi] + __popcll(L.b.cr[wi] & ((1ull << (x & 63)) - 1ull));
+        };
+        auto process = [&](int c, u64 q) {
+            bool mine = false;
+            for (int u = 0; u < rec_nacc(q); u++) mine |= rec_acc(q, u, c, L.W) == a;
+            if (!mine) return;
+            if (L.fwd) {   // _scan_for_traffic_flow_forward, once per (light, controlled road) like the reference
+                auto emit = [&](int cell) { if (FILL) { if (po < cap_out) out_cell[po] = cell; else *L.err = 27; po++; } else no++; };
+                forward_scan(L, c % L.W, c / L.W, c % L.W, c / L.W, L.D[c], (int)L.T[c], 0, emit);
             }
+            if (!FILL) { nc++; ni += rec_nsc(q); return; }
+            if (pc < cap_ctrl) ctrl_cell[pc] = c; else *L.err = 20;
+            pc++;
+            const uint32_t rd = L.D[c];
+            for (int d = 0; d < dl_len(rd); d++) {
+                const int kk = opp_of(dl_get(rd, d)), step = dy_of(kk) * L.W + dx_of(kk);
+                for (int s2 = 1; s2 <= rec_cnt(q, d); s2++, pi++) { if (pi < cap_inc) inc_cell[pi] = c + s2 * step; else *L.err = 21; }
+            }
+        };
+        // the candidate bits of the 5 x 5 cells around the light, row by row (= ascending cell order), five independent loads
+        uint32_t all = 0;   // bit 5 * r + k = candidate at (ax - 2 + k, ay - 2 + r)
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const int y = ay - 2 + r;
+            const uint32_t row = (y >= 0 && y < L.H) ? (uint32_t)extract_bits(L.b.cr + (size_t)y * L.b.wp, L.b.wp, ax - 2, 5) : 0u;
+            all |= row << (5 * r);
+        }
+        // the first CH candidates are looked up TOGETHER (their prefix words, then their records, as independent loads: the chain
+        // bit -> prefix -> record used to be walked candidate by candidate); static indices only, so everything stays in registers
+        auto cell_of = [&](int bit) { return (ay - 2 + bit / 5) * L.W + ax - 2 + bit % 5; };
+        int cc[CH], m = 0;
+        uint32_t rest = all;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            if (rest) { cc[j] = cell_of(__ffs(rest) - 1); rest &= rest - 1; m = j + 1; }
+        }
+        int idx[CH];
+        u64 rr[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) if (j < m) idx[j] = rec_of(cc[j]);
+#pragma unroll
+        for (int j = 0; j < CH; j++) if (j < m) rr[j] = rec[idx[j]];
+#pragma unroll
+        for (int j = 0; j < CH; j++) if (j < m) process(cc[j], rr[j]);
+        while (rest) {   // (a light with more than CH candidates around it: the rest one by one, in order)
+            const int c = cell_of(__ffs(rest) - 1);
+            rest &= rest - 1;
+            process(c, rec[rec_of(c)]);
         }
         if (!FILL) { ctrl_off[l] = nc; inc_off[l] = ni; if (L.fwd) out_off[l] = no; }
     }
@@ -1112,7 +1146,8 @@ extern "C" tsim_status tsim_lights_prepare(const tsim_cfg *cfg, const tsim_plane
     TSIM_CUDA(cudaMemsetAsync(L.scal, 0, 64 * 4, cs));
     init_pivot_kernel<<<1, 1, 0, cs>>>(L.scal);
     TSIM_LAUNCH_CHECK();
-    lights_bits_kernel<<<div_up(L.nw * 4, 256), 256, 0, cs>>>(L.W, L.H, p->cell_type, p->dirs, L.bp, (long long)mid_row * L.W, L.scal);
+    lights_bits_kernel<<<dim3(div_up(L.wp * 4, 256), L.H < 65535 ? L.H : 65535, div_up(L.H, 65535)), 256, 0, cs>>>(L.W, L.H, p->cell_type, p->dirs, L.bp,
+                                                                                                                   (long long)mid_row * L.W, L.scal);
     TSIM_LAUNCH_CHECK();
     cr_bits_kernel<<<div_up(L.nw, 256), 256, 0, cs>>>(L.H, L.bp, L.cr_prefix);
     TSIM_LAUNCH_CHECK();

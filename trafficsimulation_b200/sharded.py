@@ -174,7 +174,7 @@ class ShardedCityLayout:
     """``GpuCityLayout`` over row-band shards.  Same constructor kwargs as the reference ``CityModel`` plus the
     shard geometry; ``generate`` runs the reference's pass sequence (city_model.py:125-139, 148)."""
 
-    PASSES = ("frame", "carve", "zones", "dead_ends", "upgrade_r2", "entrances", "fix_dirs", "lights")
+    PASSES = ("frame", "carve", "zones", "dead_ends", "upgrade_r2", "entrances", "fix_dirs")
 
     def __init__(self, n_shards, halo=64, devices=None, distributed=False, group=None, global_reach=False, cuts=None, lean=False,
                  verify=None, **city_kwargs):
@@ -236,7 +236,9 @@ class ShardedCityLayout:
 
     def _verify_digests(self):
         """Lean mode, end of the pipeline: every cut's two shards must have digested the same bytes after every pass."""
+        self._mark("verify: last digests")
         gathered = self.comm.all_gather({s: d.reshape(-1) for s, d in self._dig.items()})
+        self._mark("verify: all-gather")
         for s, L in self.shards.items():
             g = gathered[s].view(self.plan.n, len(self.PASSES), 4)
             bad = torch.zeros((), dtype=torch.bool, device=L.device)
@@ -429,8 +431,7 @@ class ShardedCityLayout:
             for L in S.values():
                 L._add_traffic_lights(check=False)
             self.reach_rounds = 1
-            self._digest("lights", T | A | B)
-            self._mark("lights")
+            self._mark("lights")                              # the last pass that changes the planes: nothing downstream reads its halo rows
         if maps:
             for L in S.values():
                 L._build_simple_maps()
