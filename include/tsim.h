@@ -329,6 +329,12 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
        alive in THIS window, rebuilt by tsim_tick_unpack after every halo refresh (scalars[12] = entries, [13] = valid for the
        next tick), so that a shard's tick costs what its own vehicles and ghosts cost, not the fleet of the whole city          */
     int32_t *live_idx;
+    /* live-list kernel, optional (both NULL = plain append): with these the survivors of a tick are appended TILE BY TILE
+       (counting sort by the tile of the new position, tsim_tick_tiles), so that the vehicles a warp handles next tick are
+       neighbours on the grid and their cell probes share cache lines -- the cell-sorted vehicle SoA of large fleets.
+       `recs` then holds THREE halves of n_vehicles records.                                                                 */
+    int32_t *sort_keys;                          /* [2 * n_vehicles] (tile, rank inside the tile) of the record in slot i      */
+    int32_t *tile_ws;                            /* [2 * n_tiles] vehicles per tile, first slot of the tile                    */
 } tsim_tick_state;
 #define TSIM_TICK_VREC_BYTES 48
 #define TSIM_TICK_PLAN_BYTES 32
@@ -340,6 +346,9 @@ tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, con
 /* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME */
 tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                           const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
+
+/* number of tiles the live-list kernel sorts by for this grid (tiles are 64 x 64 cells, doubled until there are at most 32768) */
+tsim_status tsim_tick_tiles(const tsim_cfg *cfg, int32_t *n_tiles);
 
 /* live-list kernel only: scatter the live records into the vehicle SoA of `st` (alive = 0 for everybody else), so that the
    host reads the same arrays whichever kernel ran */

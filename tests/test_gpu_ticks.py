@@ -55,9 +55,12 @@ def test_gpu_ticks_multi_tick_launch_equals_single_ticks():
 
 
 @pytest.mark.parametrize("size,nveh,algo,live_list", [(512, 20000, "QUEUE_ACTUATED", True), (768, 60000, "FIXED_TIME", True),
-                                                       (512, 20000, "FIXED_TIME", False)])
-def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo, live_list):
+                                                       (512, 20000, "FIXED_TIME", False), (768, 60000, "QUEUE_ACTUATED", "sorted")])
+def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo, live_list, monkeypatch):
     """Dense synthetic traffic on a city the reference cannot plan routes for: CUDA vs the pinned C oracle."""
+    if live_list == "sorted":
+        monkeypatch.setenv("TSIM_TICK_SORT", "1")
+        live_list = True
     from oracle import oracle as O
     from trafficsimulation_b200 import tapes
     from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
@@ -114,9 +117,12 @@ def test_gpu_ticks_without_vehicles_cycle_the_lights():
         assert sim.counters()["vehicle_updates"] == 0
 
 
-def test_gpu_ticks_trips_injected_every_tick():
+@pytest.mark.parametrize("tile_sorted", ["0", "1"], ids=["plain_append", "tile_sorted_append"])
+def test_gpu_ticks_trips_injected_every_tick(tile_sorted, monkeypatch):
     """Trips injected every tick over a long run (BASELINE.json configs[3] in miniature): the live list grows and shrinks all the
-    time, attempts pile up on occupied origins and are dropped; the whole state equals the oracle's every few ticks."""
+    time, attempts pile up on occupied origins and are dropped; the whole state equals the oracle's every few ticks.  Both
+    forms of the live list: survivors appended as they come, and appended tile by tile (what fleets of >= 200 k vehicles get)."""
+    monkeypatch.setenv("TSIM_TICK_SORT", tile_sorted)
     from oracle import oracle as O
     from trafficsimulation_b200 import tapes
     from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout

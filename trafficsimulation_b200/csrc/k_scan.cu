@@ -12,7 +12,8 @@ namespace tsim {
 
 typedef unsigned long long u64;
 constexpr int SCAN_ITEMS = SCAN_TILE / 256;
-constexpr u64 ST_SUM = 1ull << 32, ST_PREFIX = 2ull << 32;
+#define ST_SUM (1ull << 32)      // status word = flag << 32 | value: the tile's own sum ...
+#define ST_PREFIX (2ull << 32)   // ... or the inclusive prefix up to and including the tile
 
 __global__ void __launch_bounds__(256) scan_lookback_kernel(long long n, const int32_t *__restrict__ n_dev, int32_t *data, u64 *status, int32_t *ticket,
                                                             int32_t *total_out, int ntiles) {
@@ -46,21 +47,27 @@ __global__ void __launch_bounds__(256) scan_lookback_kernel(long long n, const i
     int before = 0, total = 0;
 #pragma unroll
     for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < w) before += c; total += c; }
-    if (threadIdx.x == 0) {
+    if (w == 0) {   // the first warp looks back 32 predecessors at a time (one lane each), not one by one
         int prefix = 0;
         if (tile > 0) {
-            *((volatile u64 *)(status + tile)) = ST_SUM | (u64)(uint32_t)total;
-            for (int j = tile - 1;; ) {
-                const u64 s = *((volatile u64 *)(status + j));
-                if ((s >> 32) == 0) continue;          // not published yet: that CTA holds an earlier ticket, it is running
-                prefix += (int)(uint32_t)s;
-                if ((s >> 32) == 2) break;
-                j--;
+            if (lane == 0) *((volatile u64 *)(status + tile)) = ST_SUM | (u64)(uint32_t)total;
+            for (int hi = tile - 1;; hi -= 32) {   // lane l reads tile hi - l; tiles below 0 count as an inclusive prefix of 0
+                const int j = hi - lane;
+                u64 sw;
+                do {   // a predecessor that has not published yet holds an earlier ticket: it is running
+                    sw = j >= 0 ? *((volatile u64 *)(status + j)) : ST_PREFIX;
+                } while (__any_sync(0xffffffffu, (sw >> 32) == 0));
+                const uint32_t pref = __ballot_sync(0xffffffffu, (sw >> 32) == 2);
+                const int first = pref ? __ffs(pref) - 1 : 32;   // nearest predecessor that already is an inclusive prefix
+                prefix += __reduce_add_sync(0xffffffffu, lane <= first ? (int)(uint32_t)sw : 0);
+                if (pref) break;
             }
         }
-        *((volatile u64 *)(status + tile)) = ST_PREFIX | (u64)(uint32_t)(prefix + total);
-        s_prefix = prefix;
-        if (tile == ntiles - 1) *total_out = prefix + total;
+        if (lane == 0) {
+            *((volatile u64 *)(status + tile)) = ST_PREFIX | (u64)(uint32_t)(prefix + total);
+            s_prefix = prefix;
+            if (tile == ntiles - 1) *total_out = prefix + total;
+        }
     }
     __syncthreads();
     int running = s_prefix + before + incl - sum;

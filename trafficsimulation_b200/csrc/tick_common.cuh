@@ -27,6 +27,7 @@ struct TickArgs {
     tsim_light_tables lt;
     tsim_tick_tapes tp;
     tsim_tick_state st;
+    int tile_sx, tile_sy, tiles_x, n_tiles;   // live-list kernel, sorted append: tile = (y >> tile_sy) * tiles_x + (x >> tile_sx); n_tiles == 0: plain append
 };
 
 template <class F>

@@ -149,6 +149,14 @@ class Comm:
         self.dist.all_gather_into_tensor(out, v, group=self.group)
         return {self.rank: out.view(self.n, v.numel())}
 
+    def max(self, vals: dict) -> int:
+        """vals: {local shard -> 0-d / 1-element integer tensor}; the maximum over ALL shards (host sync)."""
+        if self.dist is None:
+            return max(int(v.reshape(-1)[0].item()) for v in vals.values())
+        f = vals[self.rank].reshape(-1)[:1].to(torch.int32).clone()
+        self.dist.all_reduce(f, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(f.item())
+
     def any(self, flags: dict) -> bool:
         """flags: {local shard -> 0-d / 1-element integer tensor}; True if any shard's flag is non-zero (host sync)."""
         if self.dist is None:

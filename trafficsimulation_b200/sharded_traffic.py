@@ -229,16 +229,19 @@ class ShardedTraffic:
             self.check()
 
     def check(self):
-        """Raise if any shard's kernel flagged an error or a ghost diverged from its owner (host sync)."""
-        codes = {}
+        """Raise if any shard's kernel flagged an error or a ghost diverged from its owner (host sync).  The diagnosis is made
+        from the code reduced over ALL shards, so every rank raises the same error for the same reason."""
+        codes, mine = {}, {}
         for s, sim in self.sims.items():
             sc = sim.s["scalars"][:10].cpu().numpy()
-            codes[s] = torch.tensor([max(int(sc[1]), int(sc[9]))], dtype=torch.int32, device=sim.device)
-        if self.comm.any(codes):
-            mine = {s: int(c.item()) for s, c in codes.items()}
-            halo = any(40 <= c <= 45 for c in mine.values()) or not any(mine.values())
-            raise _lib.TsimError(6 if halo else 4, f"sharded tick: error flags per local shard {mine}"
-                                 + (" (40..45: a ghost diverged from its owner -- halo too small for this traffic)" if halo else ""))
+            mine[s] = (int(sc[1]), int(sc[9]))
+            codes[s] = torch.tensor([max(mine[s])], dtype=torch.int32, device=sim.device)
+        worst = self.comm.max(codes)
+        if worst:
+            halo = 40 <= worst <= 45
+            raise _lib.TsimError(6 if halo or worst == 32 else 4,
+                                 f"sharded tick: device error flag {worst} (kernel flag, exchange flag per local shard: {mine})"
+                                 + (" -- a ghost diverged from its owner: the halo is too small for this traffic" if halo else ""))
 
     def counters(self):
         """Totals over the LOCAL shards (sum over ranks for the global figure)."""
@@ -257,7 +260,7 @@ class ShardedTraffic:
         W = self.W
         for s, sim in self.sims.items():
             p, y0 = self.plan, sim.win_y0
-            st = {k: v.cpu().numpy() for k, v in sim.s.items() if k not in ("claim", "stopw", "scalars", "live_idx")}
+            st = {k: v.cpu().numpy() for k, v in sim.s.items() if k not in ("claim", "stopw", "scalars", "live_idx", "sort_keys", "tile_ws", "probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff")}
             row = st["pos"][: self.nv] // W + y0
             own = (st["alive"][: self.nv] == 1) & (row >= p.own_lo[s]) & (row < p.own_hi[s])
             ids = np.flatnonzero(own)

@@ -125,7 +125,10 @@ class GpuTraffic:
         self.live_list = (window is None and own_rows is None) if live_list is None else bool(live_list)
         if self.live_list:
             s["probe"] = z(n, torch.int32)
-            s["recs"] = torch.empty(max(2 * nv * 48, 16), dtype=torch.uint8, device=dev)
+            nt = C.c_int32(0)
+            _lib.check(self.lib.tsim_tick_tiles(C.byref(self.cfg), C.byref(nt)))
+            s["recs"] = torch.empty(max(3 * nv * 48, 16), dtype=torch.uint8, device=dev)   # two halves of the live list + the sort's staging copy
+            s["sort_keys"], s["tile_ws"] = z(2 * nv, torch.int32), z(2 * nt.value, torch.int32)
             s["plans"] = torch.empty(max(nv * 32, 16), dtype=torch.uint8, device=dev)
             s["ev_stamp"], s["ev_plen"], s["ev_poff"] = z(nv, torch.int32), z(nv, torch.int32), z(nv, torch.int64)
         if window is not None and not self.live_list:
@@ -134,7 +137,8 @@ class GpuTraffic:
         v1 = [f[0] for f in _lib.TickState._fields_ if f[1] is C.c_void_p][:30]
         v2 = ("probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff")
         self.st = _lib.TickState(*[s[k].data_ptr() for k in v1], *(own_rows or (0, 0)), *[(s[k].data_ptr() if self.live_list else 0) for k in v2],
-                                 s["live_idx"].data_ptr() if "live_idx" in s else 0)
+                                 s["live_idx"].data_ptr() if "live_idx" in s else 0,
+                                 s["sort_keys"].data_ptr() if self.live_list else 0, s["tile_ws"].data_ptr() if self.live_list else 0)
         _lib.check(self.lib.tsim_tick_init(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), self._stream))
 
     @staticmethod
@@ -201,7 +205,7 @@ class GpuTraffic:
         """Same dict as oracle.OracleTicks.state() / the reference fixtures."""
         if self.live_list:   # the vehicle SoA is only written on demand
             _lib.check(self.lib.tsim_tick_export(C.byref(self.cfg), C.byref(self.tp), C.byref(self.st), self._stream))
-        s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw", "probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff", "live_idx")}
+        s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw", "probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff", "live_idx", "sort_keys", "tile_ws")}
         alive = s["alive"][: self.nv] == 1
         cut = lambda a: a[: self.nv]
         flags = (cut(s["is_stuck"]).astype(np.uint8) & 1) | ((cut(s["malfunction"]).astype(np.uint8) & 1) << 1) | \
