@@ -23,6 +23,10 @@ __global__ void __launch_bounds__(256) scan_lookback_kernel(long long n, const i
     __syncthreads();
     const int tile = s_tile;
     if (n_dev) { const long long live = *n_dev; if (live < n) n = live < 0 ? 0 : live; }
+    // tiles beyond the live prefix have nothing to scan and nobody behind them needs their sum: only the live tiles form the chain
+    const int live_tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    if (tile >= live_tiles) { if (tile == 0 && threadIdx.x == 0) *total_out = 0; return; }
+    ntiles = live_tiles;
     const long long base = (long long)tile * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     if (base + SCAN_ITEMS <= n && (((uintptr_t)data) & 15) == 0) {

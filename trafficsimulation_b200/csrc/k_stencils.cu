@@ -34,10 +34,11 @@ __device__ __forceinline__ PlaneView make_view(const Shard &s, const uint8_t *T,
 template <class F>
 __device__ __forceinline__ void sparse_sweep(const Shard &s, const uint8_t *T, uint32_t set, F f, long long tid, long long nthreads) {
     if ((s.W & 15) == 0) {
-        const int sw = s.W >> 4;
-        const long long nstrips = (long long)sw * (s.yhi - s.ylo);
-        for (long long i = tid; i < nstrips; i += nthreads) {
-            const int y = s.ylo + (int)(i / sw), x0 = (int)(i % sw) << 4;
+        const uint32_t sw = (uint32_t)s.W >> 4;
+        const uint32_t nstrips = sw * (uint32_t)(s.yhi - s.ylo);
+        for (uint32_t i = (uint32_t)tid; i < nstrips; i += (uint32_t)nthreads) {
+            const uint32_t ry = i / sw;
+            const int y = s.ylo + (int)ry, x0 = (int)(i - ry * sw) << 4;
             const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(T + (size_t)(y - s.y0) * s.W + x0));
             uint32_t m = strip_set_mask(q, set);
             while (m) {
@@ -108,10 +109,13 @@ __device__ __forceinline__ uint32_t at_least_two(uint32_t a, uint32_t b, uint32_
 template <class R, class F>
 __device__ __forceinline__ void sparse_sweep3(const Shard &s, const uint8_t *T, const uint16_t *D, const TypeRanges set, R refine, F f, long long tid,
                                               long long nthreads) {
-    const int sw = s.W >> 4;
-    const long long nstrips = (long long)sw * (s.yhi - s.ylo);
-    for (long long i = tid; i < nstrips; i += nthreads) {
-        const int y = s.ylo + (int)(i / sw), x0 = (int)(i % sw) << 4;
+    // strip index arithmetic in 32 bits (a window holds < 2^31 cells, so < 2^27 strips): the 64-bit division this loop used to do
+    // per strip is a ~100-instruction software routine
+    const uint32_t sw = (uint32_t)s.W >> 4;
+    const uint32_t nstrips = sw * (uint32_t)(s.yhi - s.ylo);
+    for (uint32_t i = (uint32_t)tid; i < nstrips; i += (uint32_t)nthreads) {
+        const uint32_t ry = i / sw;
+        const int y = s.ylo + (int)ry, x0 = (int)(i - ry * sw) << 4;
         const uint8_t *row = T + (size_t)(y - s.y0) * s.W + x0;
         const uint4 q = *reinterpret_cast<const uint4 *>(row);
         const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
