@@ -177,6 +177,10 @@ tsim_status tsim_shard_counts(const tsim_cfg *cfg, const tsim_blobs *blobs, int3
 tsim_status tsim_rows_digest(const tsim_cfg *cfg, const tsim_planes *p, int32_t row_lo, int32_t row_hi, int32_t what, uint64_t *out,
                              void *stream);
 
+/* measurement aid, not part of the path (profiles/write_peak.py): a write-only kernel storing hashed (incompressible) words to
+   `streams` planes of n_bytes each starting at `base`, `blocks` CTAs of 256 threads, grid-stride */
+tsim_status tsim_debug_write_probe(void *base, long long n_bytes, int32_t streams, int32_t blocks, void *stream);
+
 /* _carve_subblock_roads (city_model.py:563-737) given the table of tsim_layout_label_nothing and
    the carve tape: one row of 8 int32 per blob id (drawn, carved, px, py (global), hor_dir, ver_dir,
    inbound_is_horizontal, tries).  err_flag (device int32) is set non-zero on an illegal row. */

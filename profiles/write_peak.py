@@ -31,4 +31,16 @@ out["copy_gbs_read_plus_write"] = best(lambda: b.copy_(r), 2 * n * 4)
 q = a.view(4, n // 4)
 out["iota_4_planes_gbs"] = best(lambda: torch.add(r[: n // 4].view(1, -1), torch.arange(4, device=dev, dtype=torch.int32).view(4, 1), out=q), n * 4 + n)
 out["xor_inplace_gbs_read_plus_write"] = best(lambda: r.bitwise_xor_(12345), 2 * n * 4)
+# hand-written write-only kernel with hashed data (libtsim's measurement aid): 1, 3 and 4 output planes
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from trafficsimulation_b200 import _lib
+lib = _lib.load()
+big = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for streams in (1, 3, 4):
+    per = (1 << 30) // streams // 16 * 16
+    for blocks in (148 * 8, 148 * 32):
+        out[f"hashed_write_{streams}_planes_{blocks}_ctas_gbs"] = best(
+            lambda: _lib.check(lib.tsim_debug_write_probe(C.c_void_p(big.data_ptr()), C.c_longlong(per), streams, blocks, st)), per * streams)
 print(json.dumps(out))

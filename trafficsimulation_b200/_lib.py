@@ -16,7 +16,7 @@ STATUS_NAMES = {0: "TSIM_OK", 1: "TSIM_ERR_CONFIG", 2: "TSIM_ERR_WORKSPACE", 3: 
 # every symbol include/tsim.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "tsim_version", "tsim_last_error", "tsim_launch_count", "tsim_build_line_table", "tsim_build_class_tables", "tsim_build_row_patterns", "tsim_workspace_bytes",
-    "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_shard_counts", "tsim_rows_digest", "tsim_layout_carve", "tsim_layout_zones",
+    "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_shard_counts", "tsim_rows_digest", "tsim_debug_write_probe", "tsim_layout_carve", "tsim_layout_zones",
     "tsim_layout_dead_ends", "tsim_layout_upgrade_r2", "tsim_layout_entrances", "tsim_layout_fix_dirs",
     "tsim_layout_lights", "tsim_lights_prepare", "tsim_lights_seed", "tsim_lights_reach", "tsim_lights_reach_planes",
     "tsim_lights_finish", "tsim_lights_eval", "tsim_lights_links", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_tick_export", "tsim_tick_tiles", "tsim_tick_message_words", "tsim_tick_pack", "tsim_tick_unpack", "tsim_astar_scratch_bytes", "tsim_astar_batch", "tsim_density_map", "tsim_rain_discs", "tsim_label_mask",

@@ -65,3 +65,26 @@ extern "C" tsim_status tsim_rows_digest(const tsim_cfg *cfg, const tsim_planes *
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
+
+// ---- measurement aid (profiles/write_peak.py): what a WRITE-ONLY kernel reaches on this device with data that is not a constant
+// (a constant fill runs above the copy peak: the memory system compresses it).  Every thread stores `streams` x 16 bytes of a
+// hash of its index per step, to `streams` planes of n bytes each laid out back to back, like the layout passes that write T, A, D.
+namespace tsim {
+__global__ void __launch_bounds__(256) write_probe_kernel(uint8_t *base, long long n_bytes, int streams) {
+    const long long nvec = n_bytes / 16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const u64 h = mix64((u64)i);
+        for (int s = 0; s < streams; s++) {
+            const u64 g = h + (u64)s * 0x9e3779b97f4a7c15ull;
+            reinterpret_cast<uint4 *>(base + (size_t)s * n_bytes)[i] = make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(g >> 13), (uint32_t)(g >> 45));
+        }
+    }
+}
+}  // namespace tsim
+
+extern "C" tsim_status tsim_debug_write_probe(void *base, long long n_bytes, int32_t streams, int32_t blocks, void *stream) {
+    if (!base || n_bytes < 16 || streams < 1 || streams > 8 || blocks < 1) { set_error("tsim_debug_write_probe: bad arguments"); return TSIM_ERR_CONFIG; }
+    write_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((uint8_t *)base, n_bytes, streams);
+    TSIM_LAUNCH_CHECK();
+    return TSIM_OK;
+}
