@@ -104,12 +104,15 @@ def test_unsupported_range_is_refused_loudly():
         gc._add_traffic_lights()
 
 
-@pytest.mark.parametrize("mode", ["rows", "rows_tma2048", "rows_tma8192", "lut", "none"])
+@pytest.mark.parametrize("mode", ["rows", "rows_legacy", "rows_tma2048", "rows_tma8192", "lut", "none"])
 def test_frame_pass_kernels_agree(mode, monkeypatch):
-    """The kernels of the frame + roads pass (pattern rows copied through registers, pattern rows as TMA bulk copies with two
-    tile sizes, class look-up, closed form per cell) write the same planes."""
+    """The kernels of the frame + roads pass (pattern rows copied through registers, eight rows or one row per thread; pattern rows
+    as TMA bulk copies with two tile sizes; class look-up; closed form per cell) write the same planes."""
     if mode.startswith("rows_tma"):
         monkeypatch.setenv("TSIM_FRAME_TMA", mode[8:])
+        mode = "rows"
+    if mode == "rows_legacy":
+        monkeypatch.setenv("TSIM_FRAME_COPY", "legacy")
         mode = "rows"
     from oracle import oracle as O
     from trafficsimulation_b200 import tapes

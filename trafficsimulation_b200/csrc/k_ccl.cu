@@ -99,15 +99,16 @@ __device__ __forceinline__ int run_of(const u64 *__restrict__ M, const int32_t *
 __global__ void __launch_bounds__(256) ccl_count_kernel(long long nw, int wp, const u64 *__restrict__ M, int32_t *__restrict__ cnt, const int32_t *__restrict__ skip) {
     if (__ldg(skip)) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nw) cnt[i] = __popcll(run_starts(M, (size_t)i, (int)(i % wp)));
+    if (i < nw) cnt[i] = __popcll(run_starts(M, (size_t)i, (int)((uint32_t)i % (uint32_t)wp)));   // word indices fit 32 bits
 }
 
 __global__ void __launch_bounds__(256) ccl_runs_kernel(int W, long long nw, Runs r) {
     if (__ldg(r.pr.scal + PS_FLAG)) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nw) return;
-    const int wp = r.wp, wx = (int)(i % wp);
-    const long long y = i / wp;
+    const int wp = r.wp;
+    const long long y = (uint32_t)i / (uint32_t)wp;   // word indices fit 32 bits
+    const int wx = (int)((uint32_t)i - (uint32_t)y * (uint32_t)wp);
     u64 st = run_starts(r.M, (size_t)i, wx);
     if (!st) return;
     const u64 m = r.M[i];
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(long long nw, Runs r) {
     if (__ldg(r.pr.scal + PS_FLAG)) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + r.wp;   // rows 1..
     if (i >= nw) return;
-    const int wp = r.wp, wx = (int)(i % wp);
+    const int wp = r.wp, wx = (int)((uint32_t)i % (uint32_t)wp);
     const u64 ov = r.M[i] & r.M[i - wp];
     if (!ov) return;
     const u64 ovprev = wx > 0 ? (r.M[i - 1] & r.M[i - wp - 1]) >> 63 : 0ull;
@@ -365,15 +366,17 @@ __global__ void __launch_bounds__(256) zones_table_kernel(const int32_t *__restr
 template <bool FILL>
 __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Runs r, const int32_t *__restrict__ id_base, int cap_blobs,
                                                          int32_t *__restrict__ L, uint8_t *__restrict__ T, const uint8_t *__restrict__ fill) {
-    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (i0 >= n) return;
+    // blockIdx.y (+ 65535 * blockIdx.z) = row, blockIdx.x * 256 + thread = group of 8 cells of the row: no 64-bit division per thread
+    const long long y = (long long)blockIdx.y + (long long)blockIdx.z * 65535;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (x >= W || y * W >= n) return;
+    const long long i0 = y * W + x;
     const int base = (id_base ? *id_base : 0) + 1;
     const int wp = r.wp;
     const bool prod = r.pr.scal[PS_FLAG] != 0;
     const int n_cg = r.pr.scal[PS_NCG];
     if ((W & 7) == 0) {   // 8 cells of one row, inside one word
-        const long long y = i0 / W;
-        const int x = (int)(i0 % W), wx = x >> 6, sh = x & 63;
+        const int wx = x >> 6, sh = x & 63;
         const size_t wi = (size_t)y * wp + wx;
         const uint32_t bits = (uint32_t)(r.M[wi] >> sh) & 0xffu;
         int4 lo = make_int4(0, 0, 0, 0), hi = lo;
@@ -428,14 +431,14 @@ __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Run
         *reinterpret_cast<int4 *>(L + i0) = lo;
         *reinterpret_cast<int4 *>(L + i0 + 4) = hi;
     } else {
-        for (int k = 0; k < 8 && i0 + k < n; k++) {
-            const long long i = i0 + k, y = i / W;
-            const int x = (int)(i % W), wx = x >> 6, p = x & 63;
+        for (int k = 0; k < 8 && x + k < W; k++) {
+            const long long i = i0 + k;
+            const int xk = x + k, wx = xk >> 6, p = xk & 63;
             const size_t wi = (size_t)y * wp + wx;
             int id = 0;
             if ((r.M[wi] >> p) & 1ull) {
                 const int run = prod ? 0 : run_of(r.M, r.sprefix, wi, wx, p);
-                const int cid = prod ? r.pr.row_gap[y] * n_cg + r.pr.col_gap[x] : (run < r.cap ? r.len[run] : 0);
+                const int cid = prod ? r.pr.row_gap[y] * n_cg + r.pr.col_gap[xk] : (run < r.cap ? r.len[run] : 0);
                 id = cid + base;
                 if (FILL && cid < cap_blobs) { const uint8_t f = fill[cid]; if (f != 0xff) T[i] = f; }
             }
@@ -592,7 +595,8 @@ extern "C" tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes 
     zones_table_kernel<<<list_grid(blobs->cap), 256, 0, cs>>>(blobs->table, blobs->count, blobs->cap, blobs->id_base, zone_by_block, n_tape, fill, err_flag);
     TSIM_LAUNCH_CHECK();
     // Nothing cells carry no arrows and no aux bits (frame pass / place_cell), so only the type changes
-    ccl_labels_kernel<true><<<div_up(div_up(n, 8), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, p->block_id, p->cell_type, fill);
+    ccl_labels_kernel<true><<<dim3(div_up(div_up(win.W, 8), 256), win.LH < 65535 ? win.LH : 65535, div_up(win.LH, 65535)), 256, 0, cs>>>(
+        win.W, n, r, blobs->id_base, blobs->cap, p->block_id, p->cell_type, fill);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
@@ -609,7 +613,8 @@ extern "C" tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask,
     if ((st = runs_layout(cfg, workspace, ws_bytes, r, scan_tmp, fill, blobs->cap)) != TSIM_OK) return st;
     const Win win(*cfg);
     const long long n = win.cells();
-    ccl_labels_kernel<false><<<div_up(div_up(n, 8), 256), 256, 0, cs>>>(win.W, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr);
+    ccl_labels_kernel<false><<<dim3(div_up(div_up(win.W, 8), 256), win.LH < 65535 ? win.LH : 65535, div_up(win.LH, 65535)), 256, 0, cs>>>(
+        win.W, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

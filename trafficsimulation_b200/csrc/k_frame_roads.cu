@@ -10,6 +10,7 @@
 // the descriptors of its 4 neighbours, so the 13 in-place sweeps of the reference collapse into a
 // single pass that only WRITES the planes: 1 (type) + 2 (dirs) + 1 (aux) B/cell, no reads except
 // the O(W+H) line tables (L1/L2 resident).  block_id is written as a whole by the zoning pass.
+#include <algorithm>
 #include <cstdlib>
 #include "cells_frame.cuh"
 
@@ -223,39 +224,87 @@ __global__ void __launch_bounds__(128) frame_roads_tma_kernel(tsim_cfg c, uint8_
     }
 }
 
-// what the bulk copies leave out: the rows outside the bulk rows (whole width) and, in the bulk rows, the strips left of xs and
-// right of xe -- closed form, 16 cells per thread.  item = (row, strip) pairs, enumerated without a division per cell.
+// The bulk as a register copy with little else in the kernel: a thread owns one 16-cell strip column and copies it for R
+// consecutive rows -- the row classes first, then 4 loads and 4 stores per row, all independent -- so that a warp has
+// R x 4 x 512 bytes in flight and the kernel needs 30-odd registers (the one-strip-per-thread kernel that also evaluated the
+// frame's closed form needed 55 and ran at 34 % occupancy, 2.9 TB/s; a write-only probe with hashed data reaches 6 - 6.9 TB/s
+// on this device, profiles/r2_write_peak.json).
+template <int R>
+__global__ void __launch_bounds__(256) frame_copy_kernel(tsim_cfg c, uint8_t *__restrict__ T, uint16_t *__restrict__ D, uint8_t *__restrict__ A,
+                                                         const uint8_t *__restrict__ rowc, const uint8_t *__restrict__ pt,
+                                                         const uint16_t *__restrict__ pd, const uint8_t *__restrict__ pa, int xs, int xe) {
+    const Geo g(c);
+    const Bulk bk(g);
+    const int W = g.W;
+    const int xv = xs + (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (xv >= xe) return;
+    const int ly0 = blockIdx.y * R;
+    int cls[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int ly = ly0 + r, y = c.win_y0 + ly;
+        cls[r] = (ly < c.win_rows && y >= bk.y0 && y <= bk.y1) ? (int)__ldg(rowc + y) : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (cls[r] < 0) continue;
+        const size_t src = (size_t)cls[r] * W + xv, dst = (size_t)(ly0 + r) * W + xv;
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(pt + src)), a = __ldg(reinterpret_cast<const uint4 *>(pa + src));
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4 *>(pd + src)), d1 = __ldg(reinterpret_cast<const uint4 *>(pd + src + 8));
+        *reinterpret_cast<uint4 *>(T + dst) = t;
+        *reinterpret_cast<uint4 *>(A + dst) = a;
+        *reinterpret_cast<uint4 *>(D + dst) = d0;
+        *reinterpret_cast<uint4 *>(D + dst + 8) = d1;
+    }
+}
+
+// what the bulk copies leave out, closed form, one thread per 16-cell strip:
+//   mode 0: in every row of the window, the strips left of xs and right of xe;
+//   mode 1: in the rows outside the bulk rows, the strips between xs and xe.
 __global__ void __launch_bounds__(128) frame_edges_kernel(tsim_cfg c, uint8_t *__restrict__ T, uint16_t *__restrict__ D, uint8_t *__restrict__ A,
-                                                          const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt, int xs, int xe) {
+                                                          const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt, int xs, int xe, int mode) {
     const Geo g(c);
     const Bulk bk(g);
     const int W = g.W, H = g.H;
-    const int ly = blockIdx.x, y = c.win_y0 + ly;
-    const bool row_bulk = y >= bk.y0 && y <= bk.y1;
     const int n_left = xs / 16, n_all = W / 16, first_right = xe / 16;
-    const int n_items = row_bulk ? n_left + (n_all - first_right) : n_all;
-    const uint32_t r0 = y > 0 ? __ldg(rowt + y - 1) : 0u, r1 = __ldg(rowt + y), r2 = y + 1 < H ? __ldg(rowt + y + 1) : 0u;
-    for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
-        const int strip = row_bulk ? (it < n_left ? it : first_right + (it - n_left)) : it;
-        const int xv = strip * 16;
-        uint32_t tw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0}, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint32_t cprev = xv > 0 ? __ldg(colt + xv - 1) : 0u, ccur = __ldg(colt + xv);
-        for (int k = 0; k < 16; k++) {
-            const int x = xv + k;
-            const uint32_t cnext = x + 1 < W ? __ldg(colt + x + 1) : 0u;
-            int t; uint32_t d, a;
-            frame_roads_cell(c, g, r0, r1, r2, cprev, ccur, cnext, x, y, t, d, a);
-            tw[k >> 2] |= (uint32_t)t << (8 * (k & 3));
-            aw[k >> 2] |= a << (8 * (k & 3));
-            dw[k >> 1] |= d << (16 * (k & 1));
-            cprev = ccur; ccur = cnext;
-        }
-        const size_t base = (size_t)ly * W + xv;
-        *reinterpret_cast<uint4 *>(T + base) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
-        *reinterpret_cast<uint4 *>(A + base) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
-        *reinterpret_cast<uint4 *>(D + base) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
-        *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+    int ly, strip;
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 0) {
+        const int per = n_left + (n_all - first_right);
+        if (per == 0 || it >= (long long)per * c.win_rows) return;
+        ly = (int)(it / per);
+        const int e = (int)(it % per);
+        strip = e < n_left ? e : first_right + (e - n_left);
+    } else {
+        // rows of the window below bk.y0 and above bk.y1, in order
+        const int per = first_right - n_left;
+        const int lo_rows = max(0, min(c.win_rows, bk.y0 - c.win_y0));                  // local rows [0, lo_rows) lie below the bulk rows
+        const int hi_first = max(0, min(c.win_rows, bk.y1 + 1 - c.win_y0));             // local rows [hi_first, win_rows) lie above them
+        const int n_rows = lo_rows + (c.win_rows - hi_first);
+        if (per <= 0 || it >= (long long)per * n_rows) return;
+        const int k = (int)(it / per);
+        ly = k < lo_rows ? k : hi_first + (k - lo_rows);
+        strip = n_left + (int)(it % per);
     }
+    const int y = c.win_y0 + ly, xv = strip * 16;
+    const uint32_t r0 = y > 0 ? __ldg(rowt + y - 1) : 0u, r1 = __ldg(rowt + y), r2 = y + 1 < H ? __ldg(rowt + y + 1) : 0u;
+    uint32_t tw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0}, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t cprev = xv > 0 ? __ldg(colt + xv - 1) : 0u, ccur = __ldg(colt + xv);
+    for (int k = 0; k < 16; k++) {
+        const int x = xv + k;
+        const uint32_t cnext = x + 1 < W ? __ldg(colt + x + 1) : 0u;
+        int t; uint32_t d, a;
+        frame_roads_cell(c, g, r0, r1, r2, cprev, ccur, cnext, x, y, t, d, a);
+        tw[k >> 2] |= (uint32_t)t << (8 * (k & 3));
+        aw[k >> 2] |= a << (8 * (k & 3));
+        dw[k >> 1] |= d << (16 * (k & 1));
+        cprev = ccur; ccur = cnext;
+    }
+    const size_t base = (size_t)ly * W + xv;
+    *reinterpret_cast<uint4 *>(T + base) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+    *reinterpret_cast<uint4 *>(A + base) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+    *reinterpret_cast<uint4 *>(D + base) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+    *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
 }
 
 }  // namespace tsim
@@ -279,6 +328,22 @@ extern "C" tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_p
     const int xs = (bk.x0 + 15) & ~15, xe = (bk.x1 + 1) & ~15;   // the 16-cell strips that lie inside the bulk columns
     const char *tma_env = getenv("TSIM_FRAME_TMA");
     const int tma_tx = tma_env ? atoi(tma_env) : 0;               // TSIM_FRAME_TMA=<tile cells>: 2048 or 8192 switch the bulk-copy kernel on
+    const char *copy_env = getenv("TSIM_FRAME_COPY");             // "legacy": the one-strip-per-thread kernel (copy + frame in one launch)
+    const bool legacy = copy_env && *copy_env == 'l';
+    auto edges = [&]() -> tsim_status {   // frame strips of every row, then the rows outside the bulk rows
+        const long long n0 = (long long)(xs / 16 + (W / 16 - xe / 16)) * rows;
+        const int lo_rows = std::max(0, std::min(rows, bk.y0 - cfg->win_y0)), hi_first = std::max(0, std::min(rows, bk.y1 + 1 - cfg->win_y0));
+        const long long n1 = (long long)(xe / 16 - xs / 16) * (lo_rows + (rows - hi_first));
+        if (n0 > 0) {
+            frame_edges_kernel<<<div_up(n0, 128), 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, xs, xe, 0);
+            TSIM_LAUNCH_CHECK();
+        }
+        if (n1 > 0) {
+            frame_edges_kernel<<<div_up(n1, 128), 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, xs, xe, 1);
+            TSIM_LAUNCH_CHECK();
+        }
+        return TSIM_OK;
+    };
     if (patterns && xe - xs >= 64 && lines->n_row_classes > 0 && lines->n_row_classes <= 65535 && (tma_tx == 2048 || tma_tx == 8192)) {
         dim3 grid((unsigned)div_up(xe - xs, tma_tx), (unsigned)lines->n_row_classes, (unsigned)div_up(rows, TMA_ROWS));
         if (tma_tx == 2048)
@@ -288,7 +353,15 @@ extern "C" tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_p
             frame_roads_tma_kernel<8192><<<grid, 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row_class, lines->pat_type, lines->pat_dirs,
                                                                lines->pat_aux, xs, xe);
         TSIM_LAUNCH_CHECK();
-        frame_edges_kernel<<<rows, 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, xs, xe);
+        return edges();
+    } else if (patterns && xe - xs >= 64 && !legacy) {
+        constexpr int R = 8;
+        dim3 grid((unsigned)div_up(xe - xs, 16 * 256), (unsigned)div_up(rows, R));
+        if (grid.y > 65535) { set_error("tsim_layout_frame_roads: window of %d rows too tall for the copy kernel", rows); return TSIM_ERR_CONFIG; }
+        frame_copy_kernel<R><<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row_class, lines->pat_type, lines->pat_dirs, lines->pat_aux,
+                                                   xs, xe);
+        TSIM_LAUNCH_CHECK();
+        return edges();
     } else if (patterns) {
         dim3 grid((unsigned)div_up(W, 16 * 256) * rows);
         frame_roads_rows_kernel<<<grid, 256, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, lines->row_class, lines->pat_type,

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) cr_bits_kernel(int H, Bits bp, int32_t *_
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nw = (long long)bp.wp * H;
     if (i >= nw) return;
-    const int y = (int)(i / bp.wp), wx = (int)(i % bp.wp);
+    const int y = (int)((uint32_t)i / (uint32_t)bp.wp), wx = (int)((uint32_t)i - (uint32_t)y * (uint32_t)bp.wp);   // word indices fit 32 bits
     const u64 I0 = bp.I[i];
     const u64 Iup = y + 1 < H ? bp.I[i + bp.wp] : 0ull, Idn = y > 0 ? bp.I[i - bp.wp] : 0ull;
     const u64 Inx = wx + 1 < bp.wp ? bp.I[i + 1] : 0ull, Ipv = wx > 0 ? bp.I[i - 1] : 0ull;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) bit_list_kernel(int W, int H, int wp, con
     if (i >= (long long)wp * H) return;
     u64 m = plane[i];
     if (!m) return;
-    const int y = (int)(i / wp), wx = (int)(i % wp);
+    const int y = (int)((uint32_t)i / (uint32_t)wp), wx = (int)((uint32_t)i - (uint32_t)y * (uint32_t)wp);   // word indices fit 32 bits
     int k = prefix[i];
     const int base = y * W + wx * 64;
     while (m) {

@@ -110,51 +110,32 @@ template <class R, class F>
 __device__ __forceinline__ void sparse_sweep3(const Shard &s, const uint8_t *T, const uint16_t *D, const TypeRanges set, R refine, F f, long long tid,
                                               long long nthreads) {
     // strip index arithmetic in 32 bits (a window holds < 2^31 cells, so < 2^27 strips): the 64-bit division this loop used to do
-    // per strip is a ~100-instruction software routine.  Four strips per trip: their loads are issued together, so a thread
-    // keeps 64 bytes in flight instead of 16 (these sweeps read 1 B/cell and reject most strips at once: they are latency-bound,
-    // 1.2 - 2 TB/s with one load per trip).
-    constexpr int U = 4;
+    // per strip is a ~100-instruction software routine
     const uint32_t sw = (uint32_t)s.W >> 4;
-    const uint32_t nstrips = sw * (uint32_t)(s.yhi - s.ylo), stride = (uint32_t)nthreads;
-    for (uint32_t i0 = (uint32_t)tid; i0 < nstrips; i0 += U * stride) {
-        const uint8_t *rows[U];
-        int ys[U], xs[U];
-        uint4 qs[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i = i0 + (uint32_t)u * stride;
-            const bool ok = i < nstrips && i >= i0;   // (i >= i0: no wrap-around)
-            const uint32_t ry = ok ? i / sw : 0u;
-            ys[u] = ok ? s.ylo + (int)ry : -1;
-            xs[u] = ok ? (int)(i - ry * sw) << 4 : 0;
-            rows[u] = T + (size_t)(ok ? ys[u] - s.y0 : 0) * s.W + xs[u];
-            qs[u] = ok ? *reinterpret_cast<const uint4 *>(rows[u]) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (ys[u] < 0) continue;
-            const int y = ys[u], x0 = xs[u];
-            const uint8_t *row = rows[u];
-            const uint4 q = qs[u];
-            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
-            uint32_t m = strip_range_mask(qw, set);
-            if (!m) continue;
-            StripView v;
-            const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            const uint4 qd = y > s.y0 ? *reinterpret_cast<const uint4 *>(row - s.W) : none;
-            const uint4 qu = y + 1 < s.y0 + s.nrows ? *reinterpret_cast<const uint4 *>(row + s.W) : none;
-            v.r[0][0] = qd.x; v.r[0][1] = qd.y; v.r[0][2] = qd.z; v.r[0][3] = qd.w;
-            v.r[1][0] = q.x; v.r[1][1] = q.y; v.r[1][2] = q.z; v.r[1][3] = q.w;
-            v.r[2][0] = qu.x; v.r[2][1] = qu.y; v.r[2][2] = qu.z; v.r[2][3] = qu.w;
-            v.left = x0 > 0 ? (int)row[-1] : -1;
-            v.right = x0 + 16 < s.W ? (int)row[16] : -1;
-            v.x0 = x0; v.yc = y; v.D = D; v.W = s.W; v.y0 = s.y0;
-            m = refine(v, m);
-            while (m) {
-                const int b2 = __ffs(m) - 1;
-                m &= m - 1;
-                f(x0 + b2, y, v);
-            }
+    const uint32_t nstrips = sw * (uint32_t)(s.yhi - s.ylo);
+    for (uint32_t i = (uint32_t)tid; i < nstrips; i += (uint32_t)nthreads) {
+        const uint32_t ry = i / sw;
+        const int y = s.ylo + (int)ry, x0 = (int)(i - ry * sw) << 4;
+        const uint8_t *row = T + (size_t)(y - s.y0) * s.W + x0;
+        const uint4 q = *reinterpret_cast<const uint4 *>(row);
+        const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+        uint32_t m = strip_range_mask(qw, set);
+        if (!m) continue;
+        StripView v;
+        const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        const uint4 qd = y > s.y0 ? *reinterpret_cast<const uint4 *>(row - s.W) : none;
+        const uint4 qu = y + 1 < s.y0 + s.nrows ? *reinterpret_cast<const uint4 *>(row + s.W) : none;
+        v.r[0][0] = qd.x; v.r[0][1] = qd.y; v.r[0][2] = qd.z; v.r[0][3] = qd.w;
+        v.r[1][0] = q.x; v.r[1][1] = q.y; v.r[1][2] = q.z; v.r[1][3] = q.w;
+        v.r[2][0] = qu.x; v.r[2][1] = qu.y; v.r[2][2] = qu.z; v.r[2][3] = qu.w;
+        v.left = x0 > 0 ? (int)row[-1] : -1;
+        v.right = x0 + 16 < s.W ? (int)row[16] : -1;
+        v.x0 = x0; v.yc = y; v.D = D; v.W = s.W; v.y0 = s.y0;
+        m = refine(v, m);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            f(x0 + b, y, v);
         }
     }
 }
