@@ -295,7 +295,10 @@ typedef struct tsim_tick_tapes {     /* all device pointers */
     const int32_t *spawn_first;      /* [n_ticks+1] vehicles (= spawn attempts) are sorted by spawn tick      */
     const int32_t *origin, *target;  /* [n_vehicles] cell indices                                             */
     const uint8_t *speed;            /* [n_ticks][n_vehicles] value of random.randint(1,5) if drawn           */
-    const uint8_t *malfunction;      /* [n_ticks][n_vehicles] 1 = the malfunction draw fires                  */
+    const uint8_t *malfunction;      /* [n_ticks][n_vehicles] bit 0 = the malfunction draw fires (vehicle_base.py:608-610);
+                                        bit 1 = the sideswipe draw fires IF the vehicle gets to make it (:567-605; live-list
+                                        kernel only, the vehicle-indexed one raises error flag 34).  After a run
+                                        state.malfunction[v] bit 1 (tsim_tick_export) = is_in_collision               */
     const int32_t *rank;             /* [n_ticks][n_vehicles] activation rank (lower steps first)             */
     const int32_t *ev_first;         /* [n_ticks+1] route events sorted by tick                               */
     const int32_t *ev_vehicle;       /* [n_events]                                                            */

@@ -186,7 +186,7 @@ class VSim(C.Structure):
                     "stuck_ticks", "stranded",
                     "tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
                     "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl",
-                    "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer")])
+                    "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "collision", "veh_at")])
 
 
 def csr(lists, dtype=np.int32):
@@ -245,6 +245,8 @@ class OracleTicks:
             a[k] = np.zeros(nv, np.int8)
         a["direction"] = np.full(nv, -1, np.int8)
         a["stuck_ticks"] = np.zeros(nv, np.int16)
+        a["collision"] = np.zeros(nv, np.int8)
+        a["veh_at"] = np.full(W * H, -1, np.int32)
         for k in ("tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
                   "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl"):
             a[k] = np.ascontiguousarray(tables[k], np.int32)
@@ -267,7 +269,8 @@ class OracleTicks:
         a = self.a
         alive = a["alive"].astype(bool)
         pos = np.where(alive, a["pos"], -1)
-        flags = (a["is_stuck"].astype(np.uint8) & 1) | ((a["malfunction"].astype(np.uint8) & 1) << 1) | ((a["direction"] + 1).astype(np.uint8) << 2)
+        flags = (a["is_stuck"].astype(np.uint8) & 1) | ((a["malfunction"].astype(np.uint8) & 1) << 1) | ((a["direction"] + 1).astype(np.uint8) << 2) | \
+                ((a["collision"].astype(np.uint8) & 1) << 5)
         return dict(pos=pos, base_speed=np.where(alive, a["base_speed"], 0), stuck_ticks=np.where(alive, a["stuck_ticks"], 0),
                     vflags=np.where(alive, flags, 0).astype(np.uint8),
                     occ=np.flatnonzero(a["occ"]).astype(np.int32), stop=np.flatnonzero(a["stop"]).astype(np.int32),

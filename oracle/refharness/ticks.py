@@ -7,9 +7,10 @@ Tape conventions:
     light groups first (canonical order: by the minimum (y,x) cell of their intersection cluster),
     then city blocks, then vehicles by ascending `rank[tick, vehicle]`, the traffic generator last;
   * `run_parallel_decide` runs with ONE worker (F4) so phase A visits vehicles in spawn order;
-  * `random.randint` inside `step_decide` (vehicle_base.py:112) returns `speed[tick, vehicle]`,
-    `random.random` (vehicle_base.py:609, :600) returns 0.0 where `malfunction[tick, vehicle]` is set,
-    else 0.5 (sideswipes never fire);
+  * `random.randint` inside `step_decide` (vehicle_base.py:112) returns `speed[tick, vehicle]`; the FIRST
+    `random.random` of a `step_decide` (the malfunction draw, vehicle_base.py:609) returns 0.0 where bit 0 of
+    `malfunction[tick, vehicle]` is set, else 0.5; the SECOND one (the sideswipe draw, :600 -- it only happens when a
+    moving vehicle heading the opposite way stands next to the vehicle) returns 0.0 where bit 1 is set, else 0.5;
   * the traffic generator's step is replaced by a tape-driven spawner: attempt `k` creates vehicle `k` at
     `origin[k]` heading for `target[k]` at tick `spawn_tick[k]` unless the origin cell is occupied, in
     which case the attempt is DROPPED (the reference's own generator would stack vehicles; the generator
@@ -66,7 +67,7 @@ def light_group_tables(model):
     return [t[2] for t in groups], [t[1] for t in groups]
 
 
-def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=None, layout_kwargs=None, tape_seed=None):
+def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=None, layout_kwargs=None, tape_seed=None, sideswipe_p=0.0):
     """Build the reference city with `random.seed(seed)` and run `n_ticks` ticks under tapes.
 
     Returns a dict with the layout (as harness.run_layout), the tapes and the per-tick states.
@@ -103,10 +104,11 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
     speed = rng.integers(1, 6, size=(n_ticks, n_attempts), dtype=np.uint8)
     malf = (rng.random((n_ticks, n_attempts)) < malfunction_p)
     rank = np.stack([rng.permutation(n_attempts) for _ in range(n_ticks)]).astype(np.int32)
+    swipe = (rng.random((n_ticks, n_attempts)) < sideswipe_p) if sideswipe_p > 0 else np.zeros((n_ticks, n_attempts), bool)   # drawn last: older fixtures keep their tapes
 
     groups, group_order = light_group_tables(model)
     gindex = {id(g): i for i, g in enumerate(group_order)}
-    state = {"tick": 0, "veh": None, "planned": False}
+    state = {"tick": 0, "veh": None, "planned": False, "swipes": 0}
     spawned = np.zeros(n_attempts, np.uint8)
     route_events = []   # (tick, vidx, [cells])
     vehicles = {}
@@ -151,6 +153,9 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
         state["rcalls"] = calls + 1
         if calls == 0 and malf[state["tick"], state["veh"]]:
             return 0.0
+        if calls == 1 and swipe[state["tick"], state["veh"]]:
+            state["swipes"] += 1
+            return 0.0
         return 0.5
 
     def decide(self):
@@ -178,7 +183,7 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
     pos = np.full((n_ticks, n_attempts), -1, np.int32)
     base = np.zeros((n_ticks, n_attempts), np.int8)
     stuck = np.zeros((n_ticks, n_attempts), np.int16)
-    flags = np.zeros((n_ticks, n_attempts), np.uint8)   # bit0 is_stuck, bit1 malfunction, bits 2-4 direction+1
+    flags = np.zeros((n_ticks, n_attempts), np.uint8)   # bit0 is_stuck, bit1 malfunction, bits 2-4 direction+1, bit5 collision
     occ_cells, stop_cells, stuckmap_cells, group_phase = [], [], [], []
     try:
         with H._in_tmpdir():
@@ -191,7 +196,8 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
                     pos[t, k] = v.pos[1] * W + v.pos[0]
                     base[t, k] = v.base_speed
                     stuck[t, k] = v.stuck_ticks
-                    flags[t, k] = (1 if v.is_stuck else 0) | (2 if v.is_in_malfunction else 0) | ((DIRS[v.direction] + 1) << 2)
+                    flags[t, k] = (1 if v.is_stuck else 0) | (2 if v.is_in_malfunction else 0) | ((DIRS[v.direction] + 1) << 2) | \
+                                  (32 if v.is_in_collision else 0)
                 occ_cells.append(np.flatnonzero(model.occupancy_map.reshape(-1)).astype(np.int32))
                 stop_cells.append(np.flatnonzero(model.stop_map.reshape(-1)).astype(np.int32))
                 stuckmap_cells.append(np.flatnonzero(model.stuck_map.reshape(-1)).astype(np.int32))
@@ -216,7 +222,7 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
         spawn_tick=np.array([p[0] for p in plan], np.int32),
         origin=np.array([p[1].position[1] * W + p[1].position[0] for p in plan], np.int32),
         target=np.array([p[2].position[1] * W + p[2].position[0] for p in plan], np.int32),
-        spawned=spawned, speed=speed, malfunction=malf.astype(np.uint8), rank=rank,
+        spawned=spawned, speed=speed, malfunction=(malf.astype(np.uint8) | (swipe.astype(np.uint8) << 1)), rank=rank, sideswipes_fired=state["swipes"],
         rain_map=model.rain_map.astype(np.uint8).copy(),
         ev_tick=np.array([e[0] for e in route_events], np.int32), ev_vehicle=np.array([e[1] for e in route_events], np.int32),
         ev_off=ev_off, ev_cells=ev_cells,

@@ -4,7 +4,8 @@
  * Follows, in the reference (kurisu-n/TrafficSimulation):
  *   CityModel.step                       Simulation/city_model.py:1831-1860
  *   VehicleAgent.step_decide / step      Simulation/agents/vehicles/vehicle_base.py:616-685
- *     _tick_stranded :552-565, _check_malfunction :608-610, _is_at_stopped_cell :121-127,
+ *     _tick_stranded :552-565, _check_malfunction :608-610, _check_sideswipe_collision :567-605 (+ _set_collision :534-541),
+ *     _is_at_stopped_cell :121-127,
  *     _compute_speed :94-112, _scan_ahead_for_obstacles :422-452, _determine_max_steps :719-731,
  *     _execute_movement :733-753, _move_to :521-532, tick_stuck :687-693, on_target_reached :755-775
  *   CityModel.move_vehicle / remove_vehicle / place_vehicle   city_model.py:1897-1963
@@ -14,7 +15,8 @@
  *   CellAgent.set_light_stop / set_light_go   agents/city_structure_entities/cell.py:241-251
  *
  * under the tape conventions of oracle/refharness/ticks.py (activation order, speed / malfunction /
- * rank tapes, tape-driven spawner that drops attempts onto occupied cells, replayed route events).
+ * rank tapes, tape-driven spawner that drops attempts onto occupied cells, replayed route events; bit 0 of a
+ * malfunction tape entry = the malfunction draw fires, bit 1 = the sideswipe draw fires IF it is made).
  * Pinned against the live reference by tests/test_ticks_vs_reference.py and tests/golden/ticks_*.npz.
  */
 #include <stdint.h>
@@ -45,10 +47,12 @@ typedef struct {
     const int32_t *g_nsin_off, *g_nsin, *g_ewin_off, *g_ewin, *g_cl_off, *g_cl;
     /* group state [n_groups] */
     int32_t *g_cur, *g_pend, *g_qt, *g_gap, *g_last, *g_ft_phase, *g_ft_timer;
+    /* sideswipes: is_in_collision per vehicle, vehicle standing on a cell (-1: none) */
+    int8_t *collision; int32_t *veh_at;
 } vsim;
 
 enum { MIN_GREEN = 5, MAX_GREEN = 30, GAP = 3, GREEN_DURATION = 20, AWARENESS = 10,
-       MALFUNCTION_TICKS = 400, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2 };
+       MALFUNCTION_TICKS = 400, COLLISION_TICKS = 600, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2 };
 
 size_t oracle_vsim_sizeof(void) { return sizeof(vsim); }
 
@@ -99,23 +103,52 @@ static void group_step(vsim *s, int g) {
 static void remove_vehicle(vsim *s, int v) { /* city_model.py:1920-1941 */
     s->occ[s->pos[v]] = 0;
     s->stuckmap[s->pos[v]] = 0;
+    if (s->veh_at[s->pos[v]] == v) s->veh_at[s->pos[v]] = -1;
     s->alive[v] = 0;
+}
+
+static void set_collision(vsim *s, int v) { /* _set_collision vehicle_base.py:534-541 */
+    s->collision[v] = 1; s->malfunction[v] = 0; s->stranded[v] = COLLISION_TICKS; s->base_speed[v] = 0; s->cur_speed[v] = 0;
+}
+
+/* _check_sideswipe_collision vehicle_base.py:567-605: the vehicle to my left, then the one to my right; the first one that is
+   moving (as far as its last step_decide knows) in the OPPOSITE direction decides: one draw, collision for both or nothing */
+static void check_sideswipe(vsim *s, int v, int fires) {
+    static const int LEFT[4] = {3, 0, 1, 2}, RIGHT[4] = {1, 2, 3, 0}, DXv[4] = {0, 1, 0, -1}, DYv[4] = {1, 0, -1, 0};
+    const int d = s->direction[v];
+    if (d < 0) return;
+    const int x = s->pos[v] % s->W, y = s->pos[v] / s->W;
+    for (int side = 0; side < 2; side++) {
+        const int l = side ? RIGHT[d] : LEFT[d], nx = x + DXv[l], ny = y + DYv[l];
+        if (nx < 0 || nx >= s->W || ny < 0 || ny >= s->H) continue;
+        const int u = s->veh_at[ny * s->W + nx];
+        if (u < 0) continue;
+        if (s->cur_speed[u] <= 0 || s->is_stuck[u] || s->collision[u] || s->malfunction[u]) continue;
+        if (s->direction[u] != ((d + 2) & 3)) continue;
+        if (!fires) return;
+        set_collision(s, v);
+        set_collision(s, u);
+        return;
+    }
 }
 
 /* returns -1 when a tape contract is violated (vehicle already at its target in phase A) */
 static int decide(vsim *s, int v, int t) {
     const int nv = s->n_vehicles;
     s->early[v] = 0;
-    if (s->malfunction[v]) { /* _tick_stranded :552-565 */
+    if (s->malfunction[v] || s->collision[v]) { /* _tick_stranded :552-565 */
         s->stranded[v]--;
-        if (s->stranded[v] <= 0) { s->malfunction[v] = 0; s->stranded[v] = 0; }
-        if (s->malfunction[v]) { s->base_speed[v] = 0; s->cur_speed[v] = 0; s->early[v] = 1; return 0; }
+        if (s->stranded[v] <= 0) { s->malfunction[v] = 0; s->collision[v] = 0; s->stranded[v] = 0; }
+        if (s->malfunction[v] || s->collision[v]) { s->base_speed[v] = 0; s->cur_speed[v] = 0; s->early[v] = 1; return 0; }
     }
-    if (s->malf[(size_t)t * nv + v]) { /* _check_malfunction :608-610 */
-        s->malfunction[v] = 1; s->stranded[v] = MALFUNCTION_TICKS; s->base_speed[v] = 0; s->cur_speed[v] = 0;
+    const int draws = s->malf[(size_t)t * nv + v];
+    if (draws & 1) { /* _check_malfunction :608-610 */
+        s->malfunction[v] = 1; s->collision[v] = 0; s->stranded[v] = MALFUNCTION_TICKS; s->base_speed[v] = 0; s->cur_speed[v] = 0;
         s->early[v] = 1;
         return 0;
     }
+    check_sideswipe(s, v, draws & 2);
+    if (s->collision[v]) { s->base_speed[v] = 0; s->cur_speed[v] = 0; s->early[v] = 1; return 0; } /* :633-638 */
     if (s->stop[s->pos[v]] == 1) { s->base_speed[v] = 0; s->cur_speed[v] = 0; s->early[v] = 1; return 0; } /* :639-643 */
     if (s->base_speed[v] == 0) s->base_speed[v] = (int8_t)s->speed[(size_t)t * nv + v]; /* :94-112 */
     int sp = s->base_speed[v];
@@ -154,6 +187,8 @@ static void vehicle_step(vsim *s, int v) { /* :666-685 */
             /* _move_to :521-532 -> move_vehicle city_model.py:1945-1963 */
             s->occ[old] = 0; s->occ[c] = 1;
             s->stuckmap[old] = 0; s->stuckmap[c] = s->is_stuck[v] ? 1 : 0;
+            if (s->veh_at[old] == v) s->veh_at[old] = -1;
+            s->veh_at[c] = v;
             s->pos[v] = c;
             int d = c - old;
             if (d == s->W) s->direction[v] = 0; else if (d == 1) s->direction[v] = 1;
@@ -197,6 +232,7 @@ int oracle_ticks_run(vsim *s, int n) {
             if (s->occ[s->origin[v]] == 1) continue; /* dropped attempt */
             s->alive[v] = 1; s->pos[v] = s->origin[v];
             s->occ[s->origin[v]] = 1; s->stuckmap[s->origin[v]] = 0; /* place_vehicle :1897-1908 */
+            s->veh_at[s->origin[v]] = v;
             s->path_off[v] = 0; s->path_len[v] = 0;
             for (int e = s->ev_first[t]; e < s->ev_first[t + 1]; e++)
                 if (s->ev_vehicle[e] == v) { s->path_off[v] = (int32_t)s->ev_off[e]; s->path_len[v] = (int32_t)(s->ev_off[e + 1] - s->ev_off[e]); }

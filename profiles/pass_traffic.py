@@ -15,7 +15,7 @@ import sys
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
 from summarize_metrics import load   # noqa: E402
 
-OPENERS = [("frame_roads", "frame_roads"), ("dead_ends_kernel", "dead_ends"), ("upgrade_r2_kernel", "upgrade_r2"), ("ent_bits_kernel", "entrances"),
+OPENERS = [("frame_roads", "frame_roads"), ("frame_copy", "frame_roads"), ("dead_ends_kernel", "dead_ends"), ("upgrade_r2_kernel", "upgrade_r2"), ("ent_bits_kernel", "entrances"),
            ("validate_dirs_kernel", "fix_dirs"), ("init_pivot_kernel", "lights"), ("lights_bits_kernel", "lights"), ("maps_kernel", "maps")]
 
 
@@ -25,7 +25,7 @@ def main(src, dst):
         e = per.setdefault(int(_id), [name, 0.0, 0.0, 0.0])
         e[1 if metric.startswith("gpu__time") else (2 if "read" in metric else 3)] += val
     launches = [per[k] for k in sorted(per)]
-    start = max(i for i, l in enumerate(launches) if "frame_roads" in l[0])
+    start = max(i for i, l in enumerate(launches) if "frame_roads" in l[0] or "frame_copy" in l[0])
     passes = collections.OrderedDict()
     cur, labellings = None, 0
     for name, us, rd, wr in launches[start:]:

@@ -1,6 +1,6 @@
 """Generates tests/golden/ticks_*.npz from the LIVE reference tick loop (build container only).
 
-    python tests/golden/make_golden_ticks.py
+    python tests/golden/make_golden_ticks.py [case ...]
 
 Each fixture holds the layout inputs (cfg, bands, layout tapes), the reference's light tables, the tick
 tapes (spawn attempts, speed / malfunction / rank tapes, route events) and the per-tick vehicle and map
@@ -25,6 +25,8 @@ CASES = {
     "s7_rain": dict(seed=7, n_ticks=100, spawns_per_tick=10, malfunction_p=0.0, rain_rect=(40, 40, 160, 120)),
     "s14_carve": dict(seed=14, n_ticks=100, spawns_per_tick=4, malfunction_p=0.01,
                       layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
+    # sideswipe draws that fire (vehicle_base.py:567-605; stored as a second bit plane beside the malfunction tape)
+    "s21_sideswipe": dict(seed=21, n_ticks=140, spawns_per_tick=12, malfunction_p=0.002, sideswipe_p=0.35),
 }
 
 
@@ -51,6 +53,8 @@ def csr(lists):
 
 def main():
     for name, case in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         r = ticks.run_ticks(**case)
         lay = r["layout"]
         model = lay["model"]
@@ -63,13 +67,15 @@ def main():
             hbands=lay["hbands"], vbands=lay["vbands"], tape_zone=zone, tape_carve=lay["tape_carve"], tape_entrance=run,
             links_lights=lay["links"]["lights"], links_ctrl=lay["links"]["ctrl"],
             spawn_tick=r["spawn_tick"], origin=r["origin"], target=r["target"], spawned=r["spawned"],
-            speed=r["speed"], malfunction=np.packbits(r["malfunction"], axis=1), rank=r["rank"],
+            speed=r["speed"], malfunction=np.packbits(r["malfunction"] & 1, axis=1), rank=r["rank"],
             rain_map=np.packbits(r["rain_map"], axis=1),
             ev_tick=r["ev_tick"], ev_vehicle=r["ev_vehicle"], ev_len=np.diff(r["ev_off"]).astype(np.int32),
             ev_first=first, ev_steps=steps,
             pos=r["pos"], base_speed=r["base_speed"], stuck_ticks=r["stuck_ticks"], vflags=r["vflags"],
             group_state=r["group_state"].astype(np.int16),
         )
+        if case.get("sideswipe_p"):
+            arrays["sideswipe"] = np.packbits((r["malfunction"] >> 1) & 1, axis=1)
         for k in ("occ", "stop", "stuckmap"):
             arrays[k + "_off"], arrays[k + "_cells"] = r[k + "_off"], r[k + "_cells"]
         for f in ("cluster", "lights", "ns_lights", "ew_lights", "ns_in", "ew_in"):

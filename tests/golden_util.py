@@ -37,6 +37,8 @@ def load_ticks(path):
     W, H, nv = d["meta"]["W"], d["meta"]["H"], d["meta"]["n_attempts"]
     d["W"], d["H"], d["n_ticks"] = W, H, d["meta"]["n_ticks"]
     d["malfunction"] = np.unpackbits(d["malfunction"], axis=1)[:, :nv]
+    if "sideswipe" in d:   # bit 1 of a tape entry: the sideswipe draw of that (tick, vehicle) fires
+        d["malfunction"] = d["malfunction"] | (np.unpackbits(d.pop("sideswipe"), axis=1)[:, :nv] << 1)
     d["rain_map"] = np.unpackbits(d["rain_map"], axis=1)[:, :W]
     ev_len = d["ev_len"]
     off = np.zeros(len(ev_len) + 1, np.int64)

@@ -34,6 +34,14 @@ def test_gpu_ticks_match_reference_fixture(path, live_list):
         for k in a:
             assert np.array_equal(a[k], b[k]), ("group table", i, k)
     sim = GpuTraffic(r["W"], r["H"], tabs, r, r["n_ticks"], rain_enabled=r["meta"]["rain_enabled"], live_list=live_list)
+    if not live_list and (r["malfunction"] & 2).any():
+        # sideswipe draws that fire are settled by the live-list kernel only; the vehicle-indexed one (shards) refuses such a tape
+        from trafficsimulation_b200._lib import TsimError
+        with pytest.raises(TsimError, match="flag 34"):
+            sim.step(r["n_ticks"])
+        return
+    if (r["malfunction"] & 2).any():
+        assert (r["vflags"] & 32).any()   # the fixture does hold collisions
     for t in range(r["n_ticks"]):
         sim.step(1)
         compare_tick(t, sim.state_host(), r)
@@ -144,3 +152,29 @@ def test_gpu_ticks_trips_injected_every_tick(tile_sorted, monkeypatch):
         for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"):
             assert np.array_equal(got[k], want[k]), (done, k)
     assert done == n_ticks and int((want["pos"] >= 0).sum()) > 0
+
+
+def test_gpu_ticks_sideswipes_match_oracle():
+    """Sideswipe draws that fire, in dense synthetic traffic: hundreds of candidates per tick, partners earlier and later in the
+    list, chains (a vehicle hit as a partner is no candidate any more); CUDA vs the C oracle, which is pinned against the live
+    reference on this rule (tests/test_ticks_vs_reference.py, sideswipe case)."""
+    from oracle import oracle as O
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.traffic import GpuTraffic, light_tables_from_layout
+    size, nveh, n_ticks, seed = 512, 20000, 60, 77
+    hb, vb = tapes.synth_bands(seed, width=size, height=size)
+    cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
+    city = build_city(dict(width=size, height=size), hb, vb, tapes.synth_zone_tape(seed, cap), None, np.zeros(cap, np.int32))
+    tabs = light_tables_from_layout(city)
+    planes = city.planes_host()
+    tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], nveh, n_ticks, route_len=120, spawn_ticks=5,
+                             malfunction_p=0.001, sideswipe_p=0.05)
+    sim = GpuTraffic(size, size, tabs, tp, n_ticks)
+    ora = O.OracleTicks(size, size, tabs, tp, n_ticks)
+    for t in range(n_ticks):
+        sim.step(1)
+        ora.run(1)
+        got, want = sim.state_host(), ora.state()
+        for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"):
+            assert np.array_equal(got[k], want[k]), (t, k)
+    assert int(((want["vflags"] & 32) != 0).sum()) >= 20   # collisions did happen

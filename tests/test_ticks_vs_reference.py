@@ -12,10 +12,12 @@ CASES = [
     dict(seed=7, n_ticks=80, spawns_per_tick=10, malfunction_p=0.0, rain_rect=(40, 40, 160, 120)),
     dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01,
          layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
+    # sideswipe draws that fire (vehicle_base.py:567-605): collisions strand both vehicles for 600 ticks
+    dict(seed=21, n_ticks=140, spawns_per_tick=12, malfunction_p=0.002, sideswipe_p=0.35),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: f"s{c['seed']}")
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"s{c['seed']}" + ("_sideswipe" if c.get("sideswipe_p") else ""))
 def test_tick_oracle_matches_reference(case):
     from oracle.refharness import ticks
     r = ticks.run_ticks(**case)
@@ -23,6 +25,8 @@ def test_tick_oracle_matches_reference(case):
     tables = O.light_tables_from_reference(lay["links"]["lights"], lay["links"]["ctrl"], r["groups"])
     sim = O.OracleTicks(r["W"], r["H"], tables, r, r["n_ticks"], rain_enabled=case.get("rain_rect") is not None)
     assert (r["pos"] >= 0).any()
+    if case.get("sideswipe_p"):
+        assert r["sideswipes_fired"] >= 5 and (r["vflags"] & 32).any(), r["sideswipes_fired"]
     for t in range(r["n_ticks"]):
         sim.run(1)
         compare_tick(t, sim.state(), r)

@@ -258,53 +258,55 @@ __global__ void __launch_bounds__(256) frame_copy_kernel(tsim_cfg c, uint8_t *__
     }
 }
 
-// what the bulk copies leave out, closed form, one thread per 16-cell strip:
-//   mode 0: in every row of the window, the strips left of xs and right of xe;
-//   mode 1: in the rows outside the bulk rows, the strips between xs and xe.
+// what the bulk copies leave out, closed form, ONE launch, four cells per thread (a quad of lanes = one 16-cell strip; the closed
+// form is a few hundred instructions per cell, so a thread that walks a whole strip is a 30 us dependent chain):
+//   items [0, n0): in every row of the window, the strips left of xs and right of xe;
+//   items [n0, n0 + n1): in the rows outside the bulk rows, the strips between xs and xe.
 __global__ void __launch_bounds__(128) frame_edges_kernel(tsim_cfg c, uint8_t *__restrict__ T, uint16_t *__restrict__ D, uint8_t *__restrict__ A,
-                                                          const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt, int xs, int xe, int mode) {
+                                                          const uint32_t *__restrict__ rowt, const uint32_t *__restrict__ colt, int xs, int xe,
+                                                          long long n0, long long n1) {
     const Geo g(c);
     const Bulk bk(g);
     const int W = g.W, H = g.H;
     const int n_left = xs / 16, n_all = W / 16, first_right = xe / 16;
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long it = gt >> 2;
+    const int q = (int)(gt & 3);
+    if (it >= n0 + n1) return;
     int ly, strip;
-    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (mode == 0) {
+    if (it < n0) {
         const int per = n_left + (n_all - first_right);
-        if (per == 0 || it >= (long long)per * c.win_rows) return;
         ly = (int)(it / per);
         const int e = (int)(it % per);
         strip = e < n_left ? e : first_right + (e - n_left);
     } else {
-        // rows of the window below bk.y0 and above bk.y1, in order
+        it -= n0;
         const int per = first_right - n_left;
-        const int lo_rows = max(0, min(c.win_rows, bk.y0 - c.win_y0));                  // local rows [0, lo_rows) lie below the bulk rows
-        const int hi_first = max(0, min(c.win_rows, bk.y1 + 1 - c.win_y0));             // local rows [hi_first, win_rows) lie above them
-        const int n_rows = lo_rows + (c.win_rows - hi_first);
-        if (per <= 0 || it >= (long long)per * n_rows) return;
+        const int lo_rows = max(0, min(c.win_rows, bk.y0 - c.win_y0));        // local rows [0, lo_rows) lie below the bulk rows
+        const int hi_first = max(0, min(c.win_rows, bk.y1 + 1 - c.win_y0));   // local rows [hi_first, win_rows) lie above them
         const int k = (int)(it / per);
         ly = k < lo_rows ? k : hi_first + (k - lo_rows);
         strip = n_left + (int)(it % per);
     }
-    const int y = c.win_y0 + ly, xv = strip * 16;
+    const int y = c.win_y0 + ly, xv = strip * 16 + 4 * q;
     const uint32_t r0 = y > 0 ? __ldg(rowt + y - 1) : 0u, r1 = __ldg(rowt + y), r2 = y + 1 < H ? __ldg(rowt + y + 1) : 0u;
-    uint32_t tw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0}, dw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t tw = 0, aw = 0, dw[2] = {0, 0};
     uint32_t cprev = xv > 0 ? __ldg(colt + xv - 1) : 0u, ccur = __ldg(colt + xv);
-    for (int k = 0; k < 16; k++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
         const int x = xv + k;
         const uint32_t cnext = x + 1 < W ? __ldg(colt + x + 1) : 0u;
         int t; uint32_t d, a;
         frame_roads_cell(c, g, r0, r1, r2, cprev, ccur, cnext, x, y, t, d, a);
-        tw[k >> 2] |= (uint32_t)t << (8 * (k & 3));
-        aw[k >> 2] |= a << (8 * (k & 3));
+        tw |= (uint32_t)t << (8 * k);
+        aw |= a << (8 * k);
         dw[k >> 1] |= d << (16 * (k & 1));
         cprev = ccur; ccur = cnext;
     }
     const size_t base = (size_t)ly * W + xv;
-    *reinterpret_cast<uint4 *>(T + base) = make_uint4(tw[0], tw[1], tw[2], tw[3]);
-    *reinterpret_cast<uint4 *>(A + base) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
-    *reinterpret_cast<uint4 *>(D + base) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
-    *reinterpret_cast<uint4 *>(D + base + 8) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+    *reinterpret_cast<uint32_t *>(T + base) = tw;
+    *reinterpret_cast<uint32_t *>(A + base) = aw;
+    *reinterpret_cast<uint2 *>(D + base) = make_uint2(dw[0], dw[1]);
 }
 
 }  // namespace tsim
@@ -334,12 +336,8 @@ extern "C" tsim_status tsim_layout_frame_roads(const tsim_cfg *cfg, const tsim_p
         const long long n0 = (long long)(xs / 16 + (W / 16 - xe / 16)) * rows;
         const int lo_rows = std::max(0, std::min(rows, bk.y0 - cfg->win_y0)), hi_first = std::max(0, std::min(rows, bk.y1 + 1 - cfg->win_y0));
         const long long n1 = (long long)(xe / 16 - xs / 16) * (lo_rows + (rows - hi_first));
-        if (n0 > 0) {
-            frame_edges_kernel<<<div_up(n0, 128), 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, xs, xe, 0);
-            TSIM_LAUNCH_CHECK();
-        }
-        if (n1 > 0) {
-            frame_edges_kernel<<<div_up(n1, 128), 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, xs, xe, 1);
+        if (n0 + n1 > 0) {
+            frame_edges_kernel<<<div_up(4 * (n0 + n1), 128), 128, 0, st>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, xs, xe, n0, n1);
             TSIM_LAUNCH_CHECK();
         }
         return TSIM_OK;

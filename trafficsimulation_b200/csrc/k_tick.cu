@@ -48,7 +48,8 @@ __device__ void vehicle_decide(const TickArgs &a, int v, int t) {
         if (--s.stranded[v] <= 0) { s.malfunction[v] = 0; s.stranded[v] = 0; }
         if (s.malfunction[v]) { s.base_speed[v] = 0; s.cur_speed[v] = 0; s.early[v] = 1; return; }
     }
-    if (tp.malfunction[tv]) {   // _check_malfunction :608-610
+    if (tp.malfunction[tv] & 2) s.scalars[S_ERR] = 34;   // sideswipe draws that fire are only handled by the live-list kernel
+    if (tp.malfunction[tv] & 1) {   // _check_malfunction :608-610
         s.malfunction[v] = 1; s.stranded[v] = MALFUNCTION_TICKS; s.base_speed[v] = 0; s.cur_speed[v] = 0; s.early[v] = 1;
         return;
     }

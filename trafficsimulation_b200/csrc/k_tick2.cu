@@ -38,7 +38,11 @@ struct __align__(16) VRec {   // TSIM_TICK_VREC_BYTES
     int16_t stuck_ticks;
     int8_t base_speed, cur_speed;
     int8_t is_stuck, prev_valid, malfunction, direction;
-    int32_t pad[2];
+    int8_t collision;     // is_in_collision (sideswipe, vehicle_base.py:534-541); shares `stranded` with the malfunction
+    int8_t prev_cur;      // current_speed / stranded flags as they were BEFORE this tick's phase A: what a vehicle earlier in the
+    int8_t prev_flags;    //   list sees of one later in the list (bit 0 malfunction, bit 1 collision)
+    int8_t pad8;
+    int32_t pad;
 };
 static_assert(sizeof(VRec) == TSIM_TICK_VREC_BYTES, "VRec size");
 
@@ -72,7 +76,7 @@ __device__ __forceinline__ void claim_tagged(u64 *plane, uint32_t *probe, int sh
 }
 
 // phase A of one vehicle (vehicle_base.py:616-663 on the tick-start snapshot): updates the record, fills the plan
-__device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, int t) {
+__device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, int t, int slot) {
     const tsim_tick_state &s = a.st;
     const tsim_tick_tapes &tp = a.tp;
     const int v = r.v;
@@ -85,15 +89,33 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
 #pragma unroll
     for (int i = 0; i < MAX_SPEED; i++) pl.cell[i] = -1;
     if (stamp == t) { r.path_off = s.ev_poff[v]; r.path_len = s.ev_plen[v]; }   // the re-plan the reference made this tick (replayed)
-    if (r.malfunction) {   // _tick_stranded :552-565
-        if (--r.stranded <= 0) { r.malfunction = 0; r.stranded = 0; }
-        if (r.malfunction) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }
+    r.prev_cur = r.cur_speed;
+    r.prev_flags = (int8_t)((r.malfunction ? 1 : 0) | (r.collision ? 2 : 0));
+    if (r.malfunction || r.collision) {   // _tick_stranded :552-565
+        if (--r.stranded <= 0) { r.malfunction = 0; r.collision = 0; r.stranded = 0; }
+        if (r.malfunction || r.collision) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }
     }
-    if (malf) {   // _check_malfunction :608-610
-        r.malfunction = 1; r.stranded = MALFUNCTION_TICKS; r.base_speed = 0; r.cur_speed = 0; pl.early = 1;
+    if (malf & 1) {   // _check_malfunction :608-610
+        r.malfunction = 1; r.collision = 0; r.stranded = MALFUNCTION_TICKS; r.base_speed = 0; r.cur_speed = 0; pl.early = 1;
         return;
     }
     const int pos = r.pos;
+    // _check_sideswipe_collision :567-605.  The draw only matters where the tape says it fires (bit 1); whether it is made at all
+    // depends on the vehicle next to this one AS IT IS WHEN THIS VEHICLE'S TURN COMES in list order, so a vehicle with a firing
+    // draw, a direction and an occupied cell to its left or right is only REGISTERED here (and asks who stands there); the
+    // candidates of a tick are settled one after the other once every vehicle has decided (sideswipe_fixup)
+    if ((malf & 2) && r.direction >= 0) {
+        const int d = r.direction, x = pos % a.W, y = pos / a.W;
+        bool any = false;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
+            if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
+            const int c = ny * a.W + nx;
+            if (__ldcg(s.probe + c) & P_OCC) { atomicOr(s.probe + c, P_WANT); any = true; }
+        }
+        if (any) s.sort_keys[atomicAdd(s.scalars + S_NCAND, 1)] = slot;
+    }
     if (__ldcg(s.probe + pos) & P_STOP) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }   // :639-643
     int base = r.base_speed;
     if (base == 0) { base = tp.speed[tv]; r.base_speed = (int8_t)base; }   // :94-112
@@ -122,6 +144,60 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
         if (pos == r.target) s.scalars[S_ERR] = 30;   // tape contract: a live vehicle is never at its target in phase A
         pl.early = 1;
     }
+}
+
+// The candidates of a tick, ONE thread, in list order (= ascending spawn-attempt index, the order run_parallel_decide visits
+// the vehicles with one worker): the vehicle to the left, then the one to the right; the first that is moving -- as far as its
+// last step_decide says: this tick's if it comes earlier in the list, last tick's if later -- the opposite way takes the draw,
+// which fires (that is why the vehicle is a candidate): _set_collision for both (vehicle_base.py:534-541, 600 ticks).  The
+// partner, if it comes LATER in the list, meets its own step_decide already stranded (599 left, early exit); if it came earlier
+// its plan for this tick stands.  Rare by construction (the reference's chance is 1e-9 per draw); a few loads per candidate.
+__device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const u64 *who, uint32_t gen0, int n_cand) {
+    const tsim_tick_state &s = a.st;
+    int32_t *cand = s.sort_keys;
+    for (int i = 1; i < n_cand; i++) {   // insertion sort by vehicle index
+        const int c = cand[i], cv = rc[c].v;
+        int j = i - 1;
+        while (j >= 0 && rc[cand[j]].v > cv) { cand[j + 1] = cand[j]; j--; }
+        cand[j + 1] = c;
+    }
+    for (int q = 0; q < n_cand; q++) {
+        const int i = cand[q];
+        VRec &R = rc[i];
+        const int d = R.direction, x = R.pos % a.W, y = R.pos / a.W;
+        bool settled = R.collision || R.malfunction;   // hit by an earlier candidate of this tick: its own turn finds it stranded
+        for (int side = 0; side < 2; side++) {
+            const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
+            if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
+            const int c = ny * a.W + nx;
+            if (settled || !(s.probe[c] & P_OCC)) continue;
+            const u64 w = who[c];
+            if ((uint32_t)(w >> 32) != gen0) { s.scalars[S_ERR] = 35; continue; }   // an occupied cell without a live vehicle on it
+            const int j = (int)(uint32_t)w;
+            VRec &U = rc[j];
+            const bool earlier = U.v < R.v;
+            const int u_cur = earlier ? U.cur_speed : U.prev_cur;
+            const bool u_stranded = earlier ? (U.malfunction || U.collision) : (U.prev_flags != 0);
+            if (u_cur <= 0 || U.is_stuck || u_stranded) continue;
+            if (U.direction != opp_of(d)) continue;
+            R.collision = 1; R.malfunction = 0; R.stranded = COLLISION_TICKS; R.base_speed = 0; R.cur_speed = 0;
+            plans[i].m = 0; plans[i].k = 0xff; plans[i].early = 1;
+            U.collision = 1; U.malfunction = 0; U.base_speed = 0; U.cur_speed = 0; U.prev_cur = 0; U.prev_flags = 2;
+            if (earlier) U.stranded = COLLISION_TICKS;                                   // decided before the hit: it still makes this tick's move
+            else { U.stranded = COLLISION_TICKS - 1; plans[j].m = 0; plans[j].k = 0xff; plans[j].early = 1; }   // _tick_stranded at its own turn
+            settled = true;
+        }
+    }
+    for (int q = 0; q < n_cand; q++) {   // the questions are answered: take the marks off again (a cell may have been asked about twice)
+        const VRec &R = rc[cand[q]];
+        const int d = R.direction, x = R.pos % a.W, y = R.pos / a.W;
+        for (int side = 0; side < 2; side++) {
+            const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
+            if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
+            if (s.probe[ny * a.W + nx] & P_WANT) atomicAnd(s.probe + ny * a.W + nx, ~P_WANT);
+        }
+    }
+    s.scalars[S_NCAND] = 0;
 }
 
 __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
@@ -164,7 +240,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
         for (int i = tid; i < n_live; i += nth) {
             VRec r = rc[i];
             VPlan pl;
-            decide2(a, r, pl, t);
+            decide2(a, r, pl, t, i);
             rc[i] = r;
             plans[i] = pl;
             live += r.pos >= a.own_lo && r.pos < a.own_hi;
@@ -174,6 +250,18 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
         for (int g = tid; g < ng; g += nth) group_decide<true>(a, g);
         if (tid == 0) s.scalars[S_NLIVE0 + nxt] = 0;   // the other half was last read as `cur` one tick ago
         grid.sync();
+        // ---- 1b: sideswipes (only on a tick with a registered candidate: two more barriers)
+        const int n_cand = *((volatile int32_t *)(s.scalars + S_NCAND));
+        if (n_cand > 0) {
+            // who stands on the cells the candidates asked about: slot of that vehicle, tagged with a generation nobody reads as a claim
+            for (int i = tid; i < n_live; i += nth) {
+                const int p = rc[i].pos;
+                if (__ldcg(s.probe + p) & P_WANT) plane[1][p] = ((u64)gen0 << 32) | (u64)(uint32_t)i;
+            }
+            grid.sync();
+            if (tid == 0) sideswipe_fixup(a, rc, plans, plane[1], gen0, n_cand);
+            grid.sync();
+        }
         // ---- 2: claim fixed point, one barrier per sweep
         int last = 0;
         for (int iter = 0;; iter++) {
@@ -346,7 +434,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                     const bool ev = s.ev_stamp[k] == t;   // the route planned at spawn time
                     r.path_off = ev ? s.ev_poff[k] : 0; r.path_len = ev ? s.ev_plen[k] : 0;
                     r.steps = 0; r.stranded = 0; r.stuck_ticks = 0; r.base_speed = 0; r.cur_speed = 0;
-                    r.is_stuck = 0; r.prev_valid = 0; r.malfunction = 0; r.direction = -1; r.pad[0] = 0; r.pad[1] = 0;
+                    r.is_stuck = 0; r.prev_valid = 0; r.malfunction = 0; r.direction = -1; r.collision = 0; r.prev_cur = 0; r.prev_flags = 0; r.pad8 = 0; r.pad = 0;
                     rn[base + __popc(mask & ((1u << lane) - 1u))] = r;
                     s.occupancy[o] = 1; s.stuck_map[o] = 0; atomicOr(s.probe + o, P_OCC);   // place_vehicle city_model.py:1904-1907
                 }
@@ -369,7 +457,7 @@ __global__ void __launch_bounds__(256) tick2_export_kernel(tsim_tick_state s, in
         const int v = r.v;
         s.alive[v] = 1; s.pos[v] = r.pos; s.path_off[v] = r.path_off; s.path_len[v] = r.path_len; s.steps[v] = r.steps; s.stranded[v] = r.stranded;
         s.stuck_ticks[v] = r.stuck_ticks; s.base_speed[v] = r.base_speed; s.cur_speed[v] = r.cur_speed; s.is_stuck[v] = r.is_stuck;
-        s.prev_valid[v] = r.prev_valid; s.malfunction[v] = r.malfunction; s.direction[v] = r.direction;
+        s.prev_valid[v] = r.prev_valid; s.malfunction[v] = (int8_t)((r.malfunction ? 1 : 0) | (r.collision ? 2 : 0)); s.direction[v] = r.direction;
     }
 }
 

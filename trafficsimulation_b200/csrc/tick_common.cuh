@@ -6,16 +6,17 @@
 namespace tsim {
 
 constexpr int MIN_GREEN = 5, MAX_GREEN = 30, GAP_TICKS = 3, GREEN_DURATION = 20;   // config.py:354-359
-constexpr int AWARENESS = 10, MALFUNCTION_TICKS = 400, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2;   // config.py:279,321,306,263
+constexpr int AWARENESS = 10, MALFUNCTION_TICKS = 400, COLLISION_TICKS = 600, STUCK_THRESHOLD = 30, RAIN_REDUCTION = 2;   // config.py:279,321,326,306,263
 constexpr int NO_CLAIM = 0x7fffffff;
 constexpr int MAX_SPEED = 5;          // random.randint(1, 5), vehicle_base.py:112: a vehicle plans at most 5 cells
 constexpr int GEN_PER_TICK = 1024;   // claim generations per tick: sweeps 1..1022, spawner 1023
 typedef unsigned long long u64;
 enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8, S_XERR = 9 /* shard exchange */,
-       S_NLIST = 12, S_LIST_OK = 13 /* live_idx: entries, valid for the next tick */ };
+       S_NLIST = 12, S_LIST_OK = 13 /* live_idx: entries, valid for the next tick */, S_NCAND = 14 /* sideswipe candidates of the tick */ };
 
 // probe word of a cell (live-list kernel): what a vehicle needs to know about a cell, in one load
 constexpr uint32_t P_OCC = 1u, P_STOP = 2u, P_STAGED = 4u;   // occupancy_map, stop_map, "a light group staged a stop_map write this tick"
+constexpr uint32_t P_WANT = 8u;                               // a sideswipe candidate asks which vehicle stands here (this tick's phase A only)
 constexpr int P_TAG_SHIFT0 = 8, P_TAG_SHIFT1 = 20;            // 12-bit tick tags: some vehicle claimed the cell in claim plane 0 / 1 this tick
 constexpr uint32_t P_TAG_MASK = 0xfffu;
 

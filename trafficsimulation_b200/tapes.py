@@ -92,7 +92,7 @@ def synth_carve_tape_device(uniforms, table, count, id_base, out, min_subblock_s
 
 
 def synth_traffic(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarray, n_vehicles: int, n_ticks: int,
-                  route_len: int = 200, spawn_ticks: int = 1, malfunction_p: float = 0.0):
+                  route_len: int = 200, spawn_ticks: int = 1, malfunction_p: float = 0.0, sideswipe_p: float = 0.0):
     """Synthetic tick tapes for cities too large for the reference's A* (SURVEY.md §8d configs 4/5).
 
     Vehicles are spawn attempts on distinct random road cells during the first `spawn_ticks` ticks; each
@@ -143,13 +143,16 @@ def synth_traffic(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.nda
     ev_off = np.zeros(nv + 1, np.int64)
     ev_off[1:] = np.cumsum(length)
     ev_cells = route[route >= 0].astype(np.int32)
-    return dict(
+    tp = dict(
         spawn_tick=spawn_tick, origin=origin.astype(np.int32), target=target.astype(np.int32),
         speed=rng.integers(1, 6, size=(n_ticks, nv), dtype=np.uint8),
         malfunction=(rng.random((n_ticks, nv)) < malfunction_p).astype(np.uint8) if malfunction_p > 0 else np.zeros((n_ticks, nv), np.uint8),
         rank=np.argsort(rng.random((n_ticks, nv)), axis=1).astype(np.int32),
         ev_tick=spawn_tick.copy(), ev_vehicle=np.arange(nv, dtype=np.int32), ev_off=ev_off, ev_cells=ev_cells,
         rain_map=np.zeros((H, W), np.uint8))
+    if sideswipe_p > 0:   # bit 1: the sideswipe draw of that (tick, vehicle) fires if it is made; its own stream, the other tapes stay as they are
+        tp["malfunction"] |= (np.random.default_rng(seed ^ 0x51DE).random((n_ticks, nv)) < sideswipe_p).astype(np.uint8) << 1
+    return tp
 
 
 def synth_trips(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarray, trips_per_tick: int, n_ticks: int, route_len: int = 80):

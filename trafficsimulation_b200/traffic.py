@@ -191,7 +191,11 @@ class GpuTraffic:
         if check:
             err = int(self.s["scalars"][1].item())
             if err:
-                raise _lib.TsimError(4 if err == 30 else 6, f"tick kernel error flag {err}")
+                why = {30: "a live vehicle stands on its target in phase A (tape contract)", 31: "ran past the end of the tapes",
+                       32: "the claim fixed point did not settle", 33: "a tape speed above 5",
+                       34: "a firing sideswipe draw (tape bit 1) needs the live-list kernel (live_list=True)",
+                       35: "an occupied cell without a live vehicle on it"}.get(err, "")
+                raise _lib.TsimError(4 if err in (30, 33, 34) else 6, f"tick kernel error flag {err}: {why}")
 
     @property
     def tick(self):
@@ -208,8 +212,10 @@ class GpuTraffic:
         s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw", "probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff", "live_idx", "sort_keys", "tile_ws")}
         alive = s["alive"][: self.nv] == 1
         cut = lambda a: a[: self.nv]
-        flags = (cut(s["is_stuck"]).astype(np.uint8) & 1) | ((cut(s["malfunction"]).astype(np.uint8) & 1) << 1) | \
-                ((cut(s["direction"]) + 1).astype(np.uint8) << 2)
+        # bit 0 is_stuck, bit 1 is_in_malfunction, bits 2-4 direction + 1, bit 5 is_in_collision (the live-list kernel exports the
+        # collision flag as bit 1 of the malfunction byte)
+        malf = cut(s["malfunction"]).astype(np.uint8)
+        flags = (cut(s["is_stuck"]).astype(np.uint8) & 1) | ((malf & 1) << 1) | ((cut(s["direction"]) + 1).astype(np.uint8) << 2) | (((malf >> 1) & 1) << 5)
         ng = self.n_groups
         return dict(pos=np.where(alive, cut(s["pos"]), -1), base_speed=np.where(alive, cut(s["base_speed"]), 0),
                     stuck_ticks=np.where(alive, cut(s["stuck_ticks"]), 0), vflags=np.where(alive, flags, 0).astype(np.uint8),
