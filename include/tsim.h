@@ -325,9 +325,11 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
     /* Working set of the LIVE-LIST kernel (all NULL: the vehicle-indexed kernel, which row-band shards use).  With these
        the tick iterates a compacted list of the live vehicles instead of the attempt array: a vehicle is a 48-byte record
        in `recs` that moves to a new slot every tick (warp-aggregated append into the other half), its plan for the tick
-       a 32-byte record in `plans`, and every cell probe reads ONE word of `probe` (occupancy, stop, staged stop and
-       "somebody claimed this cell this tick" tags).  The vehicle SoA above is then only written by tsim_tick_export.  */
-    uint32_t *probe;                             /* [H*W]                                                                      */
+       a 32-byte record in `plans`, and every cell probe reads ONE BYTE of `probe` (occupancy, stop, staged stop, "somebody
+       claimed this cell this tick" and "lies on the planned cells of one / several vehicles" bits).  A tick then touches
+       neither the vehicle SoA nor the occupancy / stop_map / stuck_map byte maps above: tsim_tick_export writes all of them
+       (the maps must start out all zero: tsim_tick_init builds the probe plane for an empty city with every light at go).   */
+    uint32_t *probe;                             /* [ceil(H*W / 4)] words = one byte per cell                                  */
     void *recs;                                  /* [2][n_vehicles] x TSIM_TICK_VREC_BYTES                                     */
     void *plans;                                 /* [n_vehicles] x TSIM_TICK_PLAN_BYTES                                        */
     int32_t *ev_stamp, *ev_plen;                 /* [n_vehicles] tick of the vehicle's pending route event, its length         */
@@ -336,12 +338,17 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
        alive in THIS window, rebuilt by tsim_tick_unpack after every halo refresh (scalars[12] = entries, [13] = valid for the
        next tick), so that a shard's tick costs what its own vehicles and ghosts cost, not the fleet of the whole city          */
     int32_t *live_idx;
-    /* live-list kernel, optional (both NULL = plain append): with these the survivors of a tick are appended TILE BY TILE
+    /* live-list kernel: scratch lists of a tick (sideswipe candidates, the vehicles in the claim fixed point, sort keys)     */
+    int32_t *sort_keys;                          /* [2 * n_vehicles]                                                           */
+    /* live-list kernel, optional (NULL = plain append): with it the survivors of a tick are appended TILE BY TILE
        (counting sort by the tile of the new position, tsim_tick_tiles), so that the vehicles a warp handles next tick are
        neighbours on the grid and their cell probes share cache lines -- the cell-sorted vehicle SoA of large fleets.
        `recs` then holds THREE halves of n_vehicles records.                                                                 */
-    int32_t *sort_keys;                          /* [2 * n_vehicles] (tile, rank inside the tile) of the record in slot i      */
     int32_t *tile_ws;                            /* [2 * n_tiles] vehicles per tile, first slot of the tile                    */
+    /* live-list kernel: what the light groups read, tsim_tick_group_ws_bytes() bytes, 8-byte aligned, filled by tsim_tick_init:
+       occupancy as one bit per cell in 8 x 8-cell tiles, and every group's incoming lanes and cluster as (tile, mask) pairs,
+       so that a queue count (intersection_light_group.py:463-494) is a handful of popcounts instead of one load per lane cell */
+    void *group_ws;
 } tsim_tick_state;
 #define TSIM_TICK_VREC_BYTES 48
 #define TSIM_TICK_PLAN_BYTES 32
@@ -350,15 +357,26 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
 tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                            const tsim_tick_state *st, void *stream);
 
+/* bytes of tsim_tick_state.group_ws for these light tables (reads three table entries back: synchronises) */
+tsim_status tsim_tick_group_ws_bytes(const tsim_cfg *cfg, const tsim_light_tables *lt, long long *bytes);
+
 /* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME */
 tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                           const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
 
+/* debug / profiling: where the live-list kernel's time went since the last reset, in nanoseconds summed over ticks (device
+   globaltimer between the grid-wide barriers): ns16[0] decide, [1] sideswipes, [2] sweep 0, [3] later sweeps, [4] move + append
+   (sorted append: + ranks), [5] tile scan, [6] (sorted append: record moves +) spawns + light commits; [7] is not a time: vehicles that took part in the claim fixed point;
+   [8..13] thread 0's own work inside those phases: decide vehicles, decide light groups, -, spawns, light commits, route events.
+   Synchronises the device. */
+tsim_status tsim_debug_tick_phases(unsigned long long *ns16, int32_t reset);
+
 /* number of tiles the live-list kernel sorts by for this grid (tiles are 64 x 64 cells, doubled until there are at most 32768) */
 tsim_status tsim_tick_tiles(const tsim_cfg *cfg, int32_t *n_tiles);
 
-/* live-list kernel only: scatter the live records into the vehicle SoA of `st` (alive = 0 for everybody else), so that the
-   host reads the same arrays whichever kernel ran */
+/* live-list kernel only: scatter the live records into the vehicle SoA of `st` (alive = 0 for everybody else) and write the
+   occupancy / stop_map / stuck_map byte maps (from the records and the probe bytes), so that the host reads the same arrays
+   whichever kernel ran.  stop_map must be 4-byte aligned. */
 tsim_status tsim_tick_export(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, void *stream);
 
 /* ---- row-band shards of the tick (SURVEY.md 8e "Vehicle step"; no reference counterpart: the reference is one process).

@@ -520,7 +520,7 @@ extern "C" tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tap
 // the live-list kernel (k_tick2.cu)
 bool tick2_enabled(const tsim_tick_state *st);
 tsim_status tick2_check(const tsim_tick_state *st, const tsim_tick_tapes *tp);
-tsim_status tick2_init(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, cudaStream_t cs);
+tsim_status tick2_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st, cudaStream_t cs);
 tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st, int32_t n_ticks,
                       int32_t algo, cudaStream_t cs);
 
@@ -579,7 +579,7 @@ extern "C" tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tabl
         for (int32_t *z : zero) TSIM_CUDA(cudaMemsetAsync(z, 0, ng * 4, cs));
     }
     TSIM_CUDA(cudaMemsetAsync(st->scalars, 0, 16 * 4, cs));
-    if (tick2_enabled(st)) return tick2_init(cfg, tp, st, cs);
+    if (tick2_enabled(st)) return tick2_init(cfg, lt, tp, st, cs);
     return TSIM_OK;
 }
 

@@ -5,10 +5,11 @@
 //     tick: survivors of the move phase and the spawns of the tick are appended (one atomic per warp) to the other half of
 //     `recs`, so that every phase reads its vehicles as consecutive 48-byte records and a fleet that has mostly arrived (or
 //     has mostly not spawned yet) costs what its live vehicles cost;
-//   * ONE probe word per cell (`probe`: occupancy | stop | staged-stop bits and two 12-bit tick tags "a vehicle claimed this
-//     cell in claim plane 0 / 1 during this tick").  Phase A reads one word per look-ahead cell instead of two maps; a claim
-//     sweep reads one word per planned cell and only follows it into the 64-bit claim plane (or the staged stop word) when
-//     the tag (the staged bit) says there is something to find -- a stale tag only costs that extra load;
+//   * ONE probe byte per cell (`probe`: occupancy | stop | staged-stop bits and two bits "a vehicle claimed this cell in claim
+//     plane 0 / 1 during this tick").  Phase A reads one byte per look-ahead cell instead of two maps; a claim sweep reads one
+//     byte per planned cell and only follows it into the 64-bit claim plane (or the staged stop word) when the bit says there is
+//     something to find.  A byte per cell, because the plane of an 8192 x 8192 city (64 MB) then stays in the 126 MB L2 and the
+//     scattered look-ahead gathers of a large fleet stop going to DRAM one 32-byte sector per cell;
 //   * a per-tick PLAN record (32 bytes: the <= 5 planned cells, activation rank, max_steps, stop bits): the sweeps of the
 //     fixed point read it instead of the vehicle state, the tapes and the route arena;
 //   * the spawner's claims (lowest attempt index per origin cell) are made during the move phase in the claim plane the
@@ -18,9 +19,12 @@
 //     counts by one CTA, one more pass that moves the 48-byte records), so that the vehicles a warp handles are neighbours on the
 //     grid and their probes hit the same cache lines: the fleet is memory-bound on these 32-byte sector gathers (ncu: 2.4 KB of
 //     DRAM traffic per vehicle and tick without the sort), which a cell-sorted order turns into cache hits.  One barrier more.
-// The public maps (occupancy / stop_map / stuck_map) are kept up to date as before; the vehicle SoA of tsim_tick_state is
-// written on demand by tsim_tick_export.
+// The public maps (occupancy / stop_map / stuck_map) and the vehicle SoA of tsim_tick_state are written on demand by
+// tsim_tick_export: a tick does not touch them (a scattered byte write costs a 32-byte sector read and written back).  What
+// stuck_map says about a cell is a property of the vehicle standing on it (move_vehicle city_model.py:1956-1958 sets the cell a
+// vehicle ends on, every cell it leaves or crosses is cleared): one bit of its record.
 #include <cooperative_groups.h>
+#include <cstdio>
 #include <cstdlib>
 #include "tick_common.cuh"
 
@@ -41,7 +45,7 @@ struct __align__(16) VRec {   // TSIM_TICK_VREC_BYTES
     int8_t collision;     // is_in_collision (sideswipe, vehicle_base.py:534-541); shares `stranded` with the malfunction
     int8_t prev_cur;      // current_speed / stranded flags as they were BEFORE this tick's phase A: what a vehicle earlier in the
     int8_t prev_flags;    //   list sees of one later in the list (bit 0 malfunction, bit 1 collision)
-    int8_t pad8;
+    int8_t mark;          // stuck_map of the cell the vehicle stands on (set by the move that brought it there)
     int32_t pad;
 };
 static_assert(sizeof(VRec) == TSIM_TICK_VREC_BYTES, "VRec size");
@@ -54,25 +58,19 @@ struct __align__(16) VPlan {   // TSIM_TICK_PLAN_BYTES
 };
 static_assert(sizeof(VPlan) == TSIM_TICK_PLAN_BYTES, "VPlan size");
 
-__device__ __forceinline__ uint32_t tick_tag(int t) { return (uint32_t)(t % 4095) + 1u; }
-
-// stop_map as the vehicles of this tick see it, from the probe word (the staged write of a light group that acted this tick wins)
+// stop_map as the vehicles of this tick see it, from the probe byte (the staged write of a light group that acted this tick wins)
 __device__ __forceinline__ int stop_seen(const tsim_tick_state &s, int c, uint32_t p) {
     return (p & P_STAGED) ? (__ldcg(s.stopw + c) & 1) : (int)((p >> 1) & 1u);
 }
 
-// rank of the lowest-ranked vehicle that claimed cell c in `plane` during sweep `gen` (NO_CLAIM: nobody); p = probe word of c
-__device__ __forceinline__ int claim_seen(const u64 *plane, int shift, uint32_t tag, int c, uint32_t p, uint32_t gen) {
-    return ((p >> shift) & P_TAG_MASK) == tag ? claim_rank(plane, c, gen) : NO_CLAIM;
+// rank of the lowest-ranked vehicle that claimed cell c in claim plane `pi` during sweep `gen` (NO_CLAIM: nobody); p = probe byte of c
+__device__ __forceinline__ int claim_seen(const u64 *plane, int pi, int c, uint32_t p, uint32_t gen) {
+    return (p & (P_CLAIM0 << pi)) ? claim_rank(plane, c, gen) : NO_CLAIM;
 }
 
-__device__ __forceinline__ void claim_tagged(u64 *plane, uint32_t *probe, int shift, uint32_t tag, int c, uint32_t gen, int rank) {
+__device__ __forceinline__ void claim_marked(u64 *plane, uint32_t *probe, int pi, int c, uint32_t gen, int rank) {
     claim_cell(plane, c, gen, rank);
-    const uint32_t p = __ldcg(probe + c);
-    if (((p >> shift) & P_TAG_MASK) != tag) {   // every claimer of the tick writes the same tag: clear, then set
-        atomicAnd(probe + c, ~(P_TAG_MASK << shift));
-        atomicOr(probe + c, tag << shift);
-    }
+    if (!(pb_load(probe, c) & (P_CLAIM0 << pi))) pb_or(probe, c, P_CLAIM0 << pi);
 }
 
 // phase A of one vehicle (vehicle_base.py:616-663 on the tick-start snapshot): updates the record, fills the plan
@@ -112,11 +110,11 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
             const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
             if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
             const int c = ny * a.W + nx;
-            if (__ldcg(s.probe + c) & P_OCC) { atomicOr(s.probe + c, P_WANT); any = true; }
+            if (pb_load(s.probe, c) & P_OCC) { pb_or(s.probe, c, P_WANT); any = true; }
         }
         if (any) s.sort_keys[atomicAdd(s.scalars + S_NCAND, 1)] = slot;
     }
-    if (__ldcg(s.probe + pos) & P_STOP) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }   // :639-643
+    if (pb_load(s.probe, pos) & P_STOP) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }   // :639-643
     int base = r.base_speed;
     if (base == 0) { base = tp.speed[tv]; r.base_speed = (int8_t)base; }   // :94-112
     int sp = base;
@@ -132,13 +130,22 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
 #pragma unroll
     for (int i = 0; i < MAX_SPEED; i++) cell[i] = i < ms ? path[i] : -1;
 #pragma unroll
-    for (int i = 0; i < MAX_SPEED; i++) pw[i] = cell[i] >= 0 ? __ldcg(s.probe + cell[i]) : 0u;
+    for (int i = 0; i < MAX_SPEED; i++) pw[i] = cell[i] >= 0 ? pb_load(s.probe, cell[i]) : 0u;
 #pragma unroll
     for (int i = MAX_SPEED - 1; i >= 0; i--)
         if (i < ms && (cell[i] < 0 || (pw[i] & (P_OCC | P_STOP)))) ms = i;   // a cell outside the window blocks, like a vehicle
 #pragma unroll
     for (int i = 0; i < MAX_SPEED; i++) pl.cell[i] = i < ms ? cell[i] : -1;
     pl.m = (uint8_t)ms;
+    // Every cell this vehicle could end on is marked: once = nobody else plans to come here, twice = somebody does.  Only vehicles
+    // with a twice-marked cell take part in the claim fixed point (the marks come off again in the move phase).
+    uint32_t was[MAX_SPEED];
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++)   // all marks first (independent round trips), then the second marks
+        was[i] = i < ms ? pb_or(s.probe, cell[i], (pw[i] & P_TOUCH1) ? (P_TOUCH1 | P_TOUCH2) : P_TOUCH1) : 0u;
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++)
+        if (i < ms && (was[i] & P_TOUCH1) && !(pw[i] & P_TOUCH1)) pb_or(s.probe, cell[i], P_TOUCH2);
     if (ms <= 0) {
         r.base_speed = 0;
         if (pos == r.target) s.scalars[S_ERR] = 30;   // tape contract: a live vehicle is never at its target in phase A
@@ -170,7 +177,7 @@ __device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const
             const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
             if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
             const int c = ny * a.W + nx;
-            if (settled || !(s.probe[c] & P_OCC)) continue;
+            if (settled || !(pb_load(s.probe, c) & P_OCC)) continue;
             const u64 w = who[c];
             if ((uint32_t)(w >> 32) != gen0) { s.scalars[S_ERR] = 35; continue; }   // an occupied cell without a live vehicle on it
             const int j = (int)(uint32_t)w;
@@ -181,10 +188,10 @@ __device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const
             if (u_cur <= 0 || U.is_stuck || u_stranded) continue;
             if (U.direction != opp_of(d)) continue;
             R.collision = 1; R.malfunction = 0; R.stranded = COLLISION_TICKS; R.base_speed = 0; R.cur_speed = 0;
-            plans[i].m = 0; plans[i].k = 0xff; plans[i].early = 1;
+            plans[i].k = 0xff; plans[i].early = 1;   // m stays: the marks on its planned cells still come off in the move phase
             U.collision = 1; U.malfunction = 0; U.base_speed = 0; U.cur_speed = 0; U.prev_cur = 0; U.prev_flags = 2;
             if (earlier) U.stranded = COLLISION_TICKS;                                   // decided before the hit: it still makes this tick's move
-            else { U.stranded = COLLISION_TICKS - 1; plans[j].m = 0; plans[j].k = 0xff; plans[j].early = 1; }   // _tick_stranded at its own turn
+            else { U.stranded = COLLISION_TICKS - 1; plans[j].k = 0xff; plans[j].early = 1; }   // _tick_stranded at its own turn
             settled = true;
         }
     }
@@ -194,11 +201,18 @@ __device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const
         for (int side = 0; side < 2; side++) {
             const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
             if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
-            if (s.probe[ny * a.W + nx] & P_WANT) atomicAnd(s.probe + ny * a.W + nx, ~P_WANT);
+            if (pb_load(s.probe, ny * a.W + nx) & P_WANT) pb_clear(s.probe, ny * a.W + nx, P_WANT);
         }
     }
     s.scalars[S_NCAND] = 0;
 }
+
+// where a tick's time goes: nanoseconds (globaltimer) between the grid-wide barriers, summed over the ticks since the last reset
+// by one thread: [0] decide, [1] sideswipes, [2] sweep 0, [3] later sweeps, [4] move + append, [5] sorted append, [6] spawns + lights
+__device__ unsigned long long g_tick_phase_ns[16];   // [8..]: thread 0's own share: decide vehicles, decide groups, phase-4 record moves, spawns, group commits, events
+__device__ __forceinline__ unsigned long long timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define OWN_DONE(slot) do { if (tid == 0) { const unsigned long long now_ = timer_ns(); g_tick_phase_ns[slot] += now_ - t_own; t_own = now_; } } while (0)
+#define PHASE_DONE(slot) do { if (tid == 0) { const unsigned long long now_ = timer_ns(); g_tick_phase_ns[slot] += now_ - t_phase; t_phase = now_; } } while (0)
 
 __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
     cg::grid_group grid = cg::this_grid();
@@ -214,7 +228,6 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
     const bool sorted = a.n_tiles > 0;
     int32_t *tile_cnt = s.tile_ws, *tile_base = s.tile_ws ? s.tile_ws + a.n_tiles : nullptr;
     VPlan *plans = (VPlan *)s.plans;
-    const int shift[2] = {P_TAG_SHIFT0, P_TAG_SHIFT1};
 
     auto scatter_events = [&](int t) {   // route events of tick t: the vehicle picks its own up in phase A (or when it spawns)
         if (t >= tp.n_ticks) return;
@@ -227,6 +240,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
     };
     scatter_events(*((volatile int32_t *)(s.scalars + S_TICK)));
     grid.sync();
+    unsigned long long t_phase = timer_ns(), t_own = t_phase;
     for (int it = 0; it < a.n_ticks; it++) {
         const int t = *((volatile int32_t *)(s.scalars + S_TICK));
         if (t >= tp.n_ticks) { if (tid == 0) s.scalars[S_ERR] = 31; break; }
@@ -234,7 +248,6 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
         VRec *rc = recs[cur], *rn = recs[nxt];
         const int n_live = *((volatile int32_t *)(s.scalars + S_NLIVE0 + cur));
         const uint32_t gen0 = (uint32_t)t * GEN_PER_TICK + 1u;   // generation nobody writes: "no claims yet"
-        const uint32_t tag = tick_tag(t);
         // ---- 1: phase A of every live vehicle + light-group decisions (staged)
         int live = 0;
         for (int i = tid; i < n_live; i += nth) {
@@ -245,65 +258,115 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
             plans[i] = pl;
             live += r.pos >= a.own_lo && r.pos < a.own_hi;
         }
+        if (tid == 0) t_own = t_phase;
+        OWN_DONE(8);
         live = __reduce_add_sync(FULL, live);
         if (lane == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
         for (int g = tid; g < ng; g += nth) group_decide<true>(a, g);
+        OWN_DONE(9);
         if (tid == 0) s.scalars[S_NLIVE0 + nxt] = 0;   // the other half was last read as `cur` one tick ago
         grid.sync();
+        PHASE_DONE(0);
         // ---- 1b: sideswipes (only on a tick with a registered candidate: two more barriers)
         const int n_cand = *((volatile int32_t *)(s.scalars + S_NCAND));
         if (n_cand > 0) {
             // who stands on the cells the candidates asked about: slot of that vehicle, tagged with a generation nobody reads as a claim
             for (int i = tid; i < n_live; i += nth) {
                 const int p = rc[i].pos;
-                if (__ldcg(s.probe + p) & P_WANT) plane[1][p] = ((u64)gen0 << 32) | (u64)(uint32_t)i;
+                if (pb_load(s.probe, p) & P_WANT) plane[1][p] = ((u64)gen0 << 32) | (u64)(uint32_t)i;
             }
             grid.sync();
             if (tid == 0) sideswipe_fixup(a, rc, plans, plane[1], gen0, n_cand);
             grid.sync();
+            PHASE_DONE(1);
         }
-        // ---- 2: claim fixed point, one barrier per sweep
+        // ---- 2: claim fixed point, one barrier per sweep.  Sweep 0 visits every vehicle: the staged stop_map writes of this tick's
+        // light groups are complete now and are folded into the plan; a vehicle none of whose planned cells is marked twice is
+        // DONE (nobody can claim a cell it may enter, nobody cares where it ends); the others make their first claim and go on the
+        // contested list, which is all the later sweeps read.
         int last = 0;
+        int32_t *cont = s.sort_keys;   // free between the sideswipe candidates of phase 1 and the sort keys of phase 3
         for (int iter = 0;; iter++) {
             const int fidx[3] = {S_FLAG0, S_FLAG1, S_FLAG2};   // three flags in rotation: the one zeroed after sweep i is written in sweep i + 2
             int32_t *flag = s.scalars + fidx[iter % 3];
             const int pp = (iter + 1) & 1, pc = iter & 1;
             const uint32_t gen_prev = gen0 + iter, gen_cur = gen0 + iter + 1;
             bool ch = false;
-            for (int i = tid; i < n_live; i += nth) {
-                VPlan pl = plans[i];
-                if (pl.early || pl.m == 0) continue;
-                const int m = pl.m;
-                uint32_t pw[MAX_SPEED];
+            if (iter == 0) {
+                for (int i0 = tid - lane; i0 < n_live; i0 += nth) {   // whole warps: one atomic per warp for the list
+                    const int i = i0 + lane;
+                    bool contested = false;
+                    if (i < n_live) {
+                        VPlan pl = plans[i];
+                        if (!pl.early && pl.m) {
+                            const int m = pl.m;
+                            uint32_t pw[MAX_SPEED], sm = 0, any2 = 0;
 #pragma unroll
-                for (int j = 0; j < MAX_SPEED; j++) pw[j] = j < m ? __ldcg(s.probe + pl.cell[j]) : 0u;
-                if (iter == 0) {   // the staged stop_map writes of this tick's light groups are complete now: fold them into the plan
-                    uint32_t sm = 0;
+                            for (int j = 0; j < MAX_SPEED; j++) pw[j] = j < m ? pb_load(s.probe, pl.cell[j]) : 0u;
 #pragma unroll
-                    for (int j = 0; j < MAX_SPEED; j++) if (j < m && stop_seen(s, pl.cell[j], pw[j]) == 1) sm |= 1u << j;
-                    pl.stop = (uint8_t)sm;
-                }
-                int k = 0;
-                bool open = true;
+                            for (int j = 0; j < MAX_SPEED; j++) {
+                                if (j < m && stop_seen(s, pl.cell[j], pw[j]) == 1) sm |= 1u << j;
+                                any2 |= pw[j] & P_TOUCH2;
+                            }
+                            int k = 0;
+                            bool open = true;
 #pragma unroll
-                for (int j = 0; j < MAX_SPEED; j++) {   // _execute_movement :733-753
-                    // a lower-ranked vehicle ends here; a stop cell may only be entered on the last step
-                    const int cr = (iter > 0 && j < m) ? claim_seen(plane[pp], shift[pp], tag, pl.cell[j], pw[j], gen_prev) : NO_CLAIM;
-                    open = open && j < m && !(cr < pl.rank) && !(((pl.stop >> j) & 1u) && j + 1 != m);
-                    if (open) k = j + 1;
+                            for (int j = 0; j < MAX_SPEED; j++) {   // _execute_movement :733-753: a stop cell may only be entered on the last step
+                                open = open && j < m && !(((sm >> j) & 1u) && j + 1 != m);
+                                if (open) k = j + 1;
+                            }
+                            contested = any2 != 0;
+                            pl.stop = (uint8_t)(sm | (contested ? 0x80u : 0u));
+                            pl.k = (uint8_t)k;
+                            *reinterpret_cast<uint32_t *>(&plans[i].m) = *reinterpret_cast<const uint32_t *>(&pl.m);   // m, k, stop, early
+                            if (contested && k >= 1) {
+                                const int c = pl.cell[k - 1];
+                                if (c != pl.target) claim_marked(plane[pc], s.probe, pc, c, gen_cur, pl.rank);   // an arriving vehicle is removed at once
+                            }
+                        }
+                    }
+                    const uint32_t mask = __ballot_sync(FULL, contested);
+                    if (mask) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(s.scalars + S_NCONT, __popc(mask));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (contested) cont[base + __popc(mask & ((1u << lane) - 1u))] = i;
+                        ch = true;
+                    }
                 }
-                if (k != pl.k || iter == 0) {
-                    ch |= k != pl.k;
-                    pl.k = (uint8_t)k;
-                    *reinterpret_cast<uint32_t *>(&plans[i].m) = *reinterpret_cast<const uint32_t *>(&pl.m);   // m, k, stop, early
-                }
-                if (k >= 1) {
-                    const int c = pl.cell[k - 1];
-                    if (c != pl.target) claim_tagged(plane[pc], s.probe, shift[pc], tag, c, gen_cur, pl.rank);   // an arriving vehicle is removed at once
+            } else {
+                const int n_cont = *((volatile int32_t *)(s.scalars + S_NCONT));
+                for (int q = tid; q < n_cont; q += nth) {
+                    const int i = cont[q];
+                    VPlan pl = plans[i];
+                    if (pl.early) continue;   // (a sideswipe cannot hit after sweep 0; kept for symmetry)
+                    const int m = pl.m;
+                    uint32_t pw[MAX_SPEED];
+#pragma unroll
+                    for (int j = 0; j < MAX_SPEED; j++) pw[j] = j < m ? pb_load(s.probe, pl.cell[j]) : 0u;
+                    int k = 0;
+                    bool open = true;
+#pragma unroll
+                    for (int j = 0; j < MAX_SPEED; j++) {   // _execute_movement :733-753
+                        // a lower-ranked vehicle ends here; a stop cell may only be entered on the last step
+                        const int cr = j < m ? claim_seen(plane[pp], pp, pl.cell[j], pw[j], gen_prev) : NO_CLAIM;
+                        open = open && j < m && !(cr < pl.rank) && !(((pl.stop >> j) & 1u) && j + 1 != m);
+                        if (open) k = j + 1;
+                    }
+                    if (k != pl.k) {
+                        ch = true;
+                        plans[i].k = (uint8_t)k;
+                    }
+                    if (k >= 1) {
+                        const int c = pl.cell[k - 1];
+                        if (c != pl.target) claim_marked(plane[pc], s.probe, pc, c, gen_cur, pl.rank);
+                    }
                 }
             }
             if (__any_sync(FULL, ch) && lane == 0) *flag = 1;
             grid.sync();
+            PHASE_DONE(iter == 0 ? 2 : 3);
+            if (iter == 0 && tid == 0) g_tick_phase_ns[7] += (unsigned long long)*((volatile int32_t *)(s.scalars + S_NCONT));
             const int any = *((volatile int32_t *)flag);
             if (tid == 0) { s.scalars[fidx[(iter + 2) % 3]] = 0; s.scalars[S_ITERS]++; }
             last = iter;
@@ -311,7 +374,6 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
             if (iter >= GEN_PER_TICK - 4) { if (tid == 0) s.scalars[S_ERR] = 32; break; }
         }
         const int pf = last & 1, po = pf ^ 1;   // plane of the final sweep; the other one takes the spawner's claims
-        const uint32_t gen_fin = gen0 + last + 1;
         const uint32_t gen_spawn = (uint32_t)t * GEN_PER_TICK + GEN_PER_TICK - 1;
         // ---- 3: apply the moves, append the survivors to the other half of the list; spawner claims
         const int k0 = tp.spawn_first[t], k1 = tp.spawn_first[t + 1];
@@ -324,22 +386,19 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                 const VPlan pl = plans[i];
                 int pos = r.pos;
                 const int target = r.target;
+#pragma unroll
+                for (int j = 0; j < MAX_SPEED; j++)   // nobody reads the marks and claim bits of this tick any more
+                    if (j < pl.m) pb_clear(s.probe, pl.cell[j], P_TOUCH1 | P_TOUCH2 | P_CLAIM0 | P_CLAIM1);
                 if (!pl.early) {
                     const int k = pl.k == 0xff ? 0 : pl.k;
                     if (k >= 1) {
                         const int fin = pl.cell[k - 1], prev = k >= 2 ? pl.cell[k - 2] : pos;
-                        // cells left or passed through: cleared unless somebody ends there this tick (their set wins)
-                        if (claim_seen(plane[pf], shift[pf], tag, pos, __ldcg(s.probe + pos), gen_fin) == NO_CLAIM) {   // move_vehicle city_model.py:1952,1957
-                            s.occupancy[pos] = 0; s.stuck_map[pos] = 0; atomicAnd(s.probe + pos, ~P_OCC);
-                        }
-                        for (int j = 0; j + 1 < k; j++)
-                            if (claim_seen(plane[pf], shift[pf], tag, pl.cell[j], __ldcg(s.probe + pl.cell[j]), gen_fin) == NO_CLAIM) s.stuck_map[pl.cell[j]] = 0;
-                        if (fin != target) {
-                            s.occupancy[fin] = 1; atomicOr(s.probe + fin, P_OCC);
-                            s.stuck_map[fin] = (k == 1 && r.is_stuck) ? 1 : 0;   // move_vehicle :1956-1958, before _move_to resets is_stuck
-                        } else if (claim_seen(plane[pf], shift[pf], tag, fin, __ldcg(s.probe + fin), gen_fin) == NO_CLAIM) {
-                            s.stuck_map[fin] = 0;                                // arrives: remove_vehicle clears its cell again (unless a later-ranked vehicle ends there)
-                        }
+                        // move_vehicle city_model.py:1945-1963.  Nobody ends on the cell this vehicle leaves (it was occupied when
+                        // everybody looked ahead), so its occupancy bit simply goes; what stuck_map says about the new cell
+                        // travels in the record (:1956-1958, before _move_to resets is_stuck)
+                        pb_clear(s.probe, pos, P_OCC); occ_clear(a, pos);
+                        if (fin != target) { pb_or(s.probe, fin, P_OCC); occ_set(a, fin); }
+                        r.mark = (k == 1 && r.is_stuck) ? 1 : 0;
                         const int d = fin - prev;                                // compute_direction numba_utilities.py:14-28
                         r.direction = (int8_t)(d == a.W ? DN : d == 1 ? DE : d == -a.W ? DS : d == -1 ? DW : r.direction);
                         if (r.stuck_ticks > 0) { r.is_stuck = 0; r.stuck_ticks = 0; }   // _move_to :528-532
@@ -349,12 +408,12 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                     }
                     r.prev_valid = 1;   // step() :677
                 } else {                // :679-680 tick_stuck :687-693
-                    const uint32_t pw = __ldcg(s.probe + pos);
+                    const uint32_t pw = pb_load(s.probe, pos);
                     if (r.prev_valid && stop_seen(s, pos, pw) != 1) {
                         const int st = ++r.stuck_ticks;
                         if (st > STUCK_THRESHOLD && !r.is_stuck) r.is_stuck = 1;
                     }
-                    if (pos == target) { s.occupancy[pos] = 0; s.stuck_map[pos] = 0; atomicAnd(s.probe + pos, ~P_OCC); }
+                    if (pos == target) { pb_clear(s.probe, pos, P_OCC); occ_clear(a, pos); }
                 }
                 keep = pos != target;   // on_target_reached :755-775 -> remove_vehicle city_model.py:1920-1929
             }
@@ -379,9 +438,10 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
             }
         }
         for (int k = k0 + tid; k < k1; k += nth)   // lowest attempt index per origin cell; whether the cell is free is known after the barrier
-            if (tp.origin[k] >= 0) claim_tagged(plane[po], s.probe, shift[po], tag, tp.origin[k], gen_spawn, k);
+            if (tp.origin[k] >= 0) claim_cell(plane[po], tp.origin[k], gen_spawn, k);   // read back without asking the probe byte
         if (tid == 0) { s.scalars[S_FLAG0] = 0; s.scalars[S_FLAG1] = 0; s.scalars[S_FLAG2] = 0; }   // nobody touches the sweep flags here
         grid.sync();
+        PHASE_DONE(4);
         if (sorted) {
             // ---- 3b: first slot of every tile = exclusive scan of the tile counts (one CTA; the counts are zeroed for the next tick)
             if (blockIdx.x == 0) {
@@ -408,12 +468,14 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                 for (int q = t0; q < t1; q++) { const int c = tile_cnt[q]; tile_base[q] = run; run += c; tile_cnt[q] = 0; }
             }
             grid.sync();
+            PHASE_DONE(5);
             // ---- 3c: the survivors move to their tile's slots
             for (int i = tid; i < n_live; i += nth) {
                 const int tile = s.sort_keys[2 * i];
                 if (tile >= 0) rn[tile_base[tile] + s.sort_keys[2 * i + 1]] = tmp[i];
             }
         }
+        if (tid == 0) t_own = timer_ns();
         // ---- 4: spawns (appended like the survivors), commit of the staged stop_map writes, the next tick's route events
         for (int k0w = k0 + tid - lane; k0w < k1; k0w += nth) {
             const int k = k0w + lane;
@@ -421,7 +483,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
             int o = -1;
             if (k < k1) {
                 o = tp.origin[k];
-                born = o >= 0 && !(__ldcg(s.probe + o) & P_OCC) && claim_rank(plane[po], o, gen_spawn) == k;
+                born = o >= 0 && !(pb_load(s.probe, o) & P_OCC) && claim_rank(plane[po], o, gen_spawn) == k;
             }
             const uint32_t mask = __ballot_sync(FULL, born);
             if (mask) {
@@ -434,16 +496,20 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                     const bool ev = s.ev_stamp[k] == t;   // the route planned at spawn time
                     r.path_off = ev ? s.ev_poff[k] : 0; r.path_len = ev ? s.ev_plen[k] : 0;
                     r.steps = 0; r.stranded = 0; r.stuck_ticks = 0; r.base_speed = 0; r.cur_speed = 0;
-                    r.is_stuck = 0; r.prev_valid = 0; r.malfunction = 0; r.direction = -1; r.collision = 0; r.prev_cur = 0; r.prev_flags = 0; r.pad8 = 0; r.pad = 0;
+                    r.is_stuck = 0; r.prev_valid = 0; r.malfunction = 0; r.direction = -1; r.collision = 0; r.prev_cur = 0; r.prev_flags = 0; r.mark = 0; r.pad = 0;
                     rn[base + __popc(mask & ((1u << lane) - 1u))] = r;
-                    s.occupancy[o] = 1; s.stuck_map[o] = 0; atomicOr(s.probe + o, P_OCC);   // place_vehicle city_model.py:1904-1907
+                    pb_or(s.probe, o, P_OCC); occ_set(a, o);   // place_vehicle city_model.py:1904-1907
                 }
             }
         }
+        OWN_DONE(11);
         for (int g = tid; g < ng; g += nth) group_apply<true>(a, g);
+        OWN_DONE(12);
         scatter_events(t + 1);
-        if (tid == 0) s.scalars[S_TICK] = t + 1;
+        OWN_DONE(13);
+        if (tid == 0) { s.scalars[S_TICK] = t + 1; s.scalars[S_NCONT] = 0; }
         grid.sync();
+        PHASE_DONE(6);
     }
 }
 
@@ -458,7 +524,58 @@ __global__ void __launch_bounds__(256) tick2_export_kernel(tsim_tick_state s, in
         s.alive[v] = 1; s.pos[v] = r.pos; s.path_off[v] = r.path_off; s.path_len[v] = r.path_len; s.steps[v] = r.steps; s.stranded[v] = r.stranded;
         s.stuck_ticks[v] = r.stuck_ticks; s.base_speed[v] = r.base_speed; s.cur_speed[v] = r.cur_speed; s.is_stuck[v] = r.is_stuck;
         s.prev_valid[v] = r.prev_valid; s.malfunction[v] = (int8_t)((r.malfunction ? 1 : 0) | (r.collision ? 2 : 0)); s.direction[v] = r.direction;
+        s.occupancy[r.pos] = 1; s.stuck_map[r.pos] = (uint8_t)r.mark;   // the caller zeroed both maps
     }
+}
+
+// stop_map = the committed stop bit of every probe byte (four cells per thread; the plane is padded to whole words)
+__global__ void __launch_bounds__(256) tick2_export_stop_kernel(long long n, const uint32_t *probe, uint8_t *stop_map) {
+    const long long n_words = n / 4, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = t0; i < n_words; i += (long long)gridDim.x * blockDim.x)
+        reinterpret_cast<uint32_t *>(stop_map)[i] = (probe[i] >> 1) & 0x01010101u;
+    if (t0 < n - n_words * 4) stop_map[n_words * 4 + t0] = (uint8_t)((reinterpret_cast<const uint8_t *>(probe)[n_words * 4 + t0] >> 1) & 1);
+}
+
+// tsim_tick_state.group_ws: | header int64[4] = entries of the N-S lane, W-E lane and cluster lists, occupancy words | occupancy
+// words u64 | masks u64[entries] | tiles int32[entries] | counts int32[3][n_groups] |.  The (tile, mask) pairs of a group's list
+// start where its cells start in the CSR table of tsim_light_tables (W-E lanes and clusters shifted by the lists before them).
+struct GroupWs {
+    long long n_ns, n_ew, n_cl, n_occ;
+    unsigned long long *occ, *mask;
+    int32_t *tile, *cnt;
+    size_t bytes;
+};
+static GroupWs group_ws_layout(void *base, long long n_ns, long long n_ew, long long n_cl, long long n_occ, int ng) {
+    GroupWs w{n_ns, n_ew, n_cl, n_occ, nullptr, nullptr, nullptr, nullptr, 0};
+    const long long e = n_ns + n_ew + n_cl;
+    char *p = (char *)base + 32;
+    w.occ = (unsigned long long *)p; p += n_occ * 8;
+    w.mask = (unsigned long long *)p; p += e * 8;
+    w.tile = (int32_t *)p; p += e * 4;
+    w.cnt = (int32_t *)p; p += (long long)3 * ng * 4;
+    w.bytes = (size_t)(p - (char *)base);
+    return w;
+}
+
+__global__ void __launch_bounds__(256) group_masks_kernel(int ng, int W, int tiles_x, const int32_t *off0, const int32_t *cells0, const int32_t *off1,
+                                                          const int32_t *cells1, const int32_t *off2, const int32_t *cells2, int base1, int base2,
+                                                          unsigned long long *mask, int32_t *tile, int32_t *cnt) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 3 * ng) return;
+    const int kind = id / ng, g = id - kind * ng;
+    const int32_t *off = kind == 0 ? off0 : kind == 1 ? off1 : off2, *cells = kind == 0 ? cells0 : kind == 1 ? cells1 : cells2;
+    const int base = (kind == 0 ? 0 : kind == 1 ? base1 : base2) + off[g];
+    int n = 0;
+    for (int k = off[g]; k < off[g + 1]; k++) {
+        const int c = cells[k];
+        if (c < 0) continue;
+        const int y = c / W, x = c - y * W, w = (y >> 3) * tiles_x + (x >> 3);
+        const unsigned long long bit = 1ull << ((y & 7) * 8 + (x & 7));
+        int i = 0;
+        for (; i < n; i++) if (tile[base + i] == w && !(mask[base + i] & bit)) break;   // a cell listed twice opens an entry of its own
+        if (i == n) { tile[base + n] = w; mask[base + n] = bit; n++; } else mask[base + i] |= bit;
+    }
+    cnt[kind * ng + g] = n;
 }
 
 __global__ void fill_i32_kernel2(long long n, int32_t *p, int32_t v) {
@@ -482,9 +599,35 @@ static void tick_tiles(const tsim_cfg *cfg, int &sx, int &sy, int &tiles_x, int 
 
 bool tick2_enabled(const tsim_tick_state *st) { return st->probe != nullptr; }
 
+static tsim_status group_list_sizes(const tsim_light_tables *lt, long long *n_ns, long long *n_ew, long long *n_cl) {
+    int32_t v[3] = {0, 0, 0};
+    if (lt->n_groups > 0) {
+        if (!lt->g_nsin_off || !lt->g_ewin_off || !lt->g_cl_off) { set_error("tick: NULL light-group table"); return TSIM_ERR_CONFIG; }
+        TSIM_CUDA(cudaMemcpy(&v[0], lt->g_nsin_off + lt->n_groups, 4, cudaMemcpyDeviceToHost));
+        TSIM_CUDA(cudaMemcpy(&v[1], lt->g_ewin_off + lt->n_groups, 4, cudaMemcpyDeviceToHost));
+        TSIM_CUDA(cudaMemcpy(&v[2], lt->g_cl_off + lt->n_groups, 4, cudaMemcpyDeviceToHost));
+    }
+    *n_ns = v[0]; *n_ew = v[1]; *n_cl = v[2];
+    return TSIM_OK;
+}
+
+extern "C" tsim_status tsim_tick_group_ws_bytes(const tsim_cfg *cfg, const tsim_light_tables *lt, long long *bytes) {
+    tsim_status r = check_cfg(cfg);
+    if (r != TSIM_OK) return r;
+    if (!lt || !bytes) { set_error("tsim_tick_group_ws_bytes: NULL argument"); return TSIM_ERR_CONFIG; }
+    long long a = 0, b = 0, c = 0;
+    if ((r = group_list_sizes(lt, &a, &b, &c)) != TSIM_OK) return r;
+    const long long n_occ = (long long)((cfg->width + 7) / 8) * ((cfg->win_rows + 7) / 8);
+    *bytes = (long long)group_ws_layout(nullptr, a, b, c, n_occ, lt->n_groups).bytes;
+    return TSIM_OK;
+}
+
+// what tick2_init found in a workspace (tick2_run must not synchronise to read the header back)
+static struct { const void *ws; long long n_ns, n_ew, n_cl, n_occ; int ng; } g_ws_seen = {nullptr, 0, 0, 0, 0, 0};
+
 tsim_status tick2_check(const tsim_tick_state *st, const tsim_tick_tapes *tp) {
-    if (!st->probe || !st->recs || !st->plans || !st->ev_stamp || !st->ev_plen || !st->ev_poff) {
-        set_error("tick (live list): probe / recs / plans / ev_stamp / ev_plen / ev_poff must all be set");
+    if (!st->probe || !st->recs || !st->plans || !st->ev_stamp || !st->ev_plen || !st->ev_poff || !st->sort_keys || !st->group_ws) {
+        set_error("tick (live list): probe / recs / plans / ev_stamp / ev_plen / ev_poff / sort_keys / group_ws must all be set");
         return TSIM_ERR_CONFIG;
     }
     if (st->own_row_lo != 0 || st->own_row_hi != 0) { set_error("tick (live list): row-band shards use the vehicle-indexed kernel"); return TSIM_ERR_UNSUPPORTED; }
@@ -492,9 +635,27 @@ tsim_status tick2_check(const tsim_tick_state *st, const tsim_tick_tapes *tp) {
     return TSIM_OK;
 }
 
-tsim_status tick2_init(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsim_tick_state *st, cudaStream_t cs) {
+tsim_status tick2_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st, cudaStream_t cs) {
     const size_t n = (size_t)cfg->width * cfg->win_rows, nv = (size_t)tp->n_vehicles;
-    TSIM_CUDA(cudaMemsetAsync(st->probe, 0, n * 4, cs));
+    {   // light groups: empty occupancy tiles, lanes and clusters as (tile, mask) pairs
+        long long a = 0, b = 0, c = 0;
+        tsim_status r = group_list_sizes(lt, &a, &b, &c);
+        if (r != TSIM_OK) return r;
+        const int tiles_x = (cfg->width + 7) / 8;
+        const long long n_occ = (long long)tiles_x * ((cfg->win_rows + 7) / 8);
+        const GroupWs w = group_ws_layout(st->group_ws, a, b, c, n_occ, lt->n_groups);
+        const long long hdr[4] = {a, b, c, n_occ};
+        TSIM_CUDA(cudaMemcpyAsync(st->group_ws, hdr, sizeof(hdr), cudaMemcpyHostToDevice, cs));
+        TSIM_CUDA(cudaStreamSynchronize(cs));   // hdr lives on this stack frame
+        TSIM_CUDA(cudaMemsetAsync(w.occ, 0, (size_t)n_occ * 8, cs));
+        if (lt->n_groups > 0) {
+            group_masks_kernel<<<div_up(3ll * lt->n_groups, 256), 256, 0, cs>>>(lt->n_groups, cfg->width, tiles_x, lt->g_nsin_off, lt->g_nsin, lt->g_ewin_off,
+                                                                                 lt->g_ewin, lt->g_cl_off, lt->g_cl, (int)a, (int)(a + b), w.mask, w.tile, w.cnt);
+            TSIM_LAUNCH_CHECK();
+        }
+        g_ws_seen = {st->group_ws, a, b, c, n_occ, lt->n_groups};
+    }
+    TSIM_CUDA(cudaMemsetAsync(st->probe, 0, (n + 3) / 4 * 4, cs));   // one byte per cell, whole words
     if (nv) {
         fill_i32_kernel2<<<div_up((long long)nv, 256) < 1184 ? div_up((long long)nv, 256) : 1184, 256, 0, cs>>>((long long)nv, st->ev_stamp, -1);
         TSIM_LAUNCH_CHECK();
@@ -505,6 +666,12 @@ tsim_status tick2_init(const tsim_cfg *cfg, const tsim_tick_tapes *tp, const tsi
         TSIM_CUDA(cudaMemsetAsync(st->tile_ws, 0, (size_t)nt * 2 * sizeof(int32_t), cs));
     }
     return TSIM_OK;   // the live-list counters are part of `scalars`, zeroed by the caller
+}
+
+extern "C" tsim_status tsim_debug_tick_phases(unsigned long long *ns16, int32_t reset) {
+    if (ns16) TSIM_CUDA(cudaMemcpyFromSymbol(ns16, g_tick_phase_ns, sizeof(unsigned long long) * 16));
+    if (reset) { unsigned long long z[16] = {0}; TSIM_CUDA(cudaMemcpyToSymbol(g_tick_phase_ns, z, sizeof(z))); }
+    return TSIM_OK;
 }
 
 extern "C" tsim_status tsim_tick_tiles(const tsim_cfg *cfg, int32_t *n_tiles) {
@@ -525,6 +692,16 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
         if (const char *e = getenv("TSIM_TICK_SORT")) on = *e != '0';
         if (on) tick_tiles(cfg, a.tile_sx, a.tile_sy, a.tiles_x, a.n_tiles);
     }
+    if (g_ws_seen.ws != st->group_ws || g_ws_seen.ng != lt->n_groups) {   // another state than the last tsim_tick_init prepared: read its header
+        long long hdr[4];
+        TSIM_CUDA(cudaMemcpy(hdr, st->group_ws, sizeof(hdr), cudaMemcpyDeviceToHost));
+        g_ws_seen = {st->group_ws, hdr[0], hdr[1], hdr[2], hdr[3], lt->n_groups};
+    }
+    {
+        const GroupWs w = group_ws_layout(st->group_ws, g_ws_seen.n_ns, g_ws_seen.n_ew, g_ws_seen.n_cl, g_ws_seen.n_occ, lt->n_groups);
+        a.occ = w.occ; a.gq_mask = w.mask; a.gq_tile = w.tile; a.gq_cnt = w.cnt;
+        a.occ_tiles_x = (cfg->width + 7) / 8; a.gq_base_ew = (int)g_ws_seen.n_ns; a.gq_base_cl = (int)(g_ws_seen.n_ns + g_ws_seen.n_ew);
+    }
     int dev = 0, sms = 0, per_sm = 0;
     TSIM_CUDA(cudaGetDevice(&dev));
     TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -542,7 +719,37 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
     const long long cap = (long long)sms * k;
     const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     void *args[] = {&a};
-    TSIM_COOP_LAUNCH(tick2_kernel, dim3(grid), dim3(256), args, cs);
+    // The probe plane is what every look-ahead gathers from: ask for it to stay in L2 (persisting lines; everything else a tick
+    // reads is streamed once per phase).  TSIM_TICK_L2_PERSIST=0 launches without the window.
+    static int max_persist = -1, max_window = 0;
+    if (max_persist < 0) {
+        TSIM_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+        TSIM_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+        if (const char *e = getenv("TSIM_TICK_L2_PERSIST")) if (*e == '0') max_persist = 0;
+        if (getenv("TSIM_DEBUG")) fprintf(stderr, "[tsim] tick: persisting L2 up to %d bytes, access window up to %d bytes\n", max_persist, max_window);
+    }
+    const size_t plane_bytes = ((size_t)cfg->width * cfg->win_rows + 3) / 4 * 4;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    attr[n_attr].id = cudaLaunchAttributeCooperative;
+    attr[n_attr++].val.cooperative = 1;
+    if (max_persist > 0 && max_window > 0) {
+        const size_t win = plane_bytes < (size_t)max_window ? plane_bytes : (size_t)max_window;
+        const size_t keep = win < (size_t)max_persist ? win : (size_t)max_persist;
+        static size_t limit_set = 0;
+        if (limit_set != keep) { TSIM_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, keep)); limit_set = keep; }
+        attr[n_attr].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[n_attr].val.accessPolicyWindow.base_ptr = (void *)st->probe;
+        attr[n_attr].val.accessPolicyWindow.num_bytes = win;
+        attr[n_attr].val.accessPolicyWindow.hitRatio = (float)((double)keep / (double)win);
+        attr[n_attr].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[n_attr].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        n_attr++;
+    }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0; lc.stream = cs; lc.attrs = attr; lc.numAttrs = n_attr;
+    count_launch();
+    TSIM_CUDA(cudaLaunchKernelExC(&lc, (const void *)tick2_kernel, args));
     return TSIM_OK;
 }
 
@@ -553,13 +760,20 @@ extern "C" tsim_status tsim_tick_export(const tsim_cfg *cfg, const tsim_tick_tap
     if (!tick2_enabled(st)) return TSIM_OK;   // the vehicle-indexed kernel keeps the SoA itself
     if ((r = tick2_check(st, tp)) != TSIM_OK) return r;
     const int nv = tp->n_vehicles;
+    cudaStream_t cs = (cudaStream_t)stream;
+    const long long n = (long long)cfg->width * cfg->win_rows;
+    if (!st->occupancy || !st->stop_map || !st->stuck_map) { set_error("tsim_tick_export: NULL map"); return TSIM_ERR_CONFIG; }
+    if (((uintptr_t)st->stop_map & 3) != 0) { set_error("tsim_tick_export: stop_map must be 4-byte aligned"); return TSIM_ERR_CONFIG; }
+    TSIM_CUDA(cudaMemsetAsync(st->occupancy, 0, (size_t)n, cs));
+    TSIM_CUDA(cudaMemsetAsync(st->stuck_map, 0, (size_t)n, cs));
+    tick2_export_stop_kernel<<<div_up(n / 4 + 1, 256) < 2368 ? div_up(n / 4 + 1, 256) : 2368, 256, 0, cs>>>(n, st->probe, st->stop_map);
+    TSIM_LAUNCH_CHECK();
     if (nv == 0) return TSIM_OK;
     if (!st->alive || !st->pos || !st->path_off || !st->path_len || !st->steps || !st->stranded || !st->stuck_ticks || !st->base_speed ||
         !st->cur_speed || !st->is_stuck || !st->prev_valid || !st->malfunction || !st->direction) {
         set_error("tsim_tick_export: NULL vehicle array");
         return TSIM_ERR_CONFIG;
     }
-    cudaStream_t cs = (cudaStream_t)stream;
     TSIM_CUDA(cudaMemsetAsync(st->alive, 0, (size_t)nv, cs));
     tick2_export_kernel<<<div_up(nv, 256) < 1184 ? div_up(nv, 256) : 1184, 256, 0, cs>>>(*st, nv);
     TSIM_LAUNCH_CHECK();

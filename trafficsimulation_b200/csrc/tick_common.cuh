@@ -12,13 +12,22 @@ constexpr int MAX_SPEED = 5;          // random.randint(1, 5), vehicle_base.py:1
 constexpr int GEN_PER_TICK = 1024;   // claim generations per tick: sweeps 1..1022, spawner 1023
 typedef unsigned long long u64;
 enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8, S_XERR = 9 /* shard exchange */,
-       S_NLIST = 12, S_LIST_OK = 13 /* live_idx: entries, valid for the next tick */, S_NCAND = 14 /* sideswipe candidates of the tick */ };
+       S_NLIST = 12, S_LIST_OK = 13 /* live_idx: entries, valid for the next tick */, S_NCAND = 14 /* sideswipe candidates of the tick */, S_NCONT = 15 /* vehicles in the claim fixed point of the tick */ };
 
-// probe word of a cell (live-list kernel): what a vehicle needs to know about a cell, in one load
+// probe BYTE of a cell (live-list kernel): what a vehicle needs to know about a cell, in one load.  One byte per cell keeps the
+// whole plane (64 MB for 8192 x 8192) in the 126 MB L2, where the look-ahead gathers of a large fleet hit instead of going to DRAM
 constexpr uint32_t P_OCC = 1u, P_STOP = 2u, P_STAGED = 4u;   // occupancy_map, stop_map, "a light group staged a stop_map write this tick"
 constexpr uint32_t P_WANT = 8u;                               // a sideswipe candidate asks which vehicle stands here (this tick's phase A only)
-constexpr int P_TAG_SHIFT0 = 8, P_TAG_SHIFT1 = 20;            // 12-bit tick tags: some vehicle claimed the cell in claim plane 0 / 1 this tick
-constexpr uint32_t P_TAG_MASK = 0xfffu;
+constexpr uint32_t P_CLAIM0 = 16u, P_CLAIM1 = 32u;            // some vehicle claimed the cell in claim plane 0 / 1 this tick (taken off again in phase 4;
+                                                              //   a stale bit only costs the load of a claim word of another generation)
+constexpr uint32_t P_TOUCH1 = 64u, P_TOUCH2 = 128u;           // the cell lies on the planned cells of one / of more than one vehicle this tick
+
+__device__ __forceinline__ uint32_t pb_load(const uint32_t *probe, int c) { return __ldcg(reinterpret_cast<const uint8_t *>(probe) + c); }
+__device__ __forceinline__ uint32_t pb_or(uint32_t *probe, int c, uint32_t bits) {   // returns the byte as it was
+    const int sh = (c & 3) * 8;
+    return (atomicOr(probe + (c >> 2), bits << sh) >> sh) & 0xffu;
+}
+__device__ __forceinline__ void pb_clear(uint32_t *probe, int c, uint32_t bits) { atomicAnd(probe + (c >> 2), ~(bits << ((c & 3) * 8))); }
 
 constexpr int OUTSIDE = -2;          // a tape cell that lies outside this shard's window (host-side translation, tsim.h)
 
@@ -29,7 +38,29 @@ struct TickArgs {
     tsim_tick_tapes tp;
     tsim_tick_state st;
     int tile_sx, tile_sy, tiles_x, n_tiles;   // live-list kernel, sorted append: tile = (y >> tile_sy) * tiles_x + (x >> tile_sx); n_tiles == 0: plain append
+    // live-list kernel, light groups (tsim_tick_state.group_ws, built by tsim_tick_init): occupancy as one bit per cell in 8 x 8-cell
+    // tiles (one 64-bit word each) and, per group, its incoming lanes and its cluster as (tile, mask) pairs
+    unsigned long long *occ;
+    const unsigned long long *gq_mask;
+    const int32_t *gq_tile, *gq_cnt;
+    int occ_tiles_x, gq_base_ew, gq_base_cl;
 };
+
+__device__ __forceinline__ void occ_word_bit(const TickArgs &a, int c, int &word, int &bit) {
+    const int y = c / a.W, x = c - y * a.W;
+    word = (y >> 3) * a.occ_tiles_x + (x >> 3);
+    bit = (y & 7) * 8 + (x & 7);
+}
+__device__ __forceinline__ void occ_set(const TickArgs &a, int c) { int w, b; occ_word_bit(a, c, w, b); atomicOr(a.occ + w, 1ull << b); }
+__device__ __forceinline__ void occ_clear(const TickArgs &a, int c) { int w, b; occ_word_bit(a, c, w, b); atomicAnd(a.occ + w, ~(1ull << b)); }
+// vehicles on the cells of list `kind` (0 N-S lanes, 1 W-E lanes, 2 cluster) of group g; a cell listed twice counts twice (its second
+// mention sits in an entry of its own)
+__device__ __forceinline__ int occ_count(const TickArgs &a, int kind, int base, int g) {
+    const int n = a.gq_cnt[kind * a.lt.n_groups + g];
+    int q = 0;
+    for (int i = 0; i < n; i++) q += __popcll(__ldcg(a.occ + a.gq_tile[base + i]) & a.gq_mask[base + i]);
+    return q;
+}
 
 template <class F>
 __device__ __forceinline__ void for_light_cells(const tsim_light_tables &lt, const int32_t *off, const int32_t *lights, int g, F f) {
@@ -50,8 +81,10 @@ __device__ void group_decide(const TickArgs &a, int g) {
         if (a.algo == 0) {   // run_queue_actuated :463-494
             const int qt = ++s.g_qt[g];
             int ns_q = 0, ew_q = 0;
-            for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += s.occupancy[lt.g_nsin[k]];
-            for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += s.occupancy[lt.g_ewin[k]];
+            if (PROBE) ns_q = occ_count(a, 0, lt.g_nsin_off[g], g);
+            else for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += (int)s.occupancy[lt.g_nsin[k]];
+            if (PROBE) ew_q = occ_count(a, 1, a.gq_base_ew + lt.g_ewin_off[g], g);
+            else for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += (int)s.occupancy[lt.g_ewin[k]];
             const int cur_q = cur == 0 ? ns_q : ew_q, opp_q = cur == 0 ? ew_q : ns_q;
             if (qt == 1) { s.g_last[g] = cur_q; s.g_gap[g] = 0; }
             if (cur_q > s.g_last[g]) { s.g_last[g] = cur_q; s.g_gap[g] = 0; } else s.g_gap[g]++;
@@ -69,16 +102,17 @@ __device__ void group_decide(const TickArgs &a, int g) {
     int plan = 0;
     if (pend >= 0) {         // _execute_phase_change :348-384
         bool occupied = false;
-        for (int k = lt.g_cl_off[g]; k < lt.g_cl_off[g + 1]; k++) occupied |= s.occupancy[lt.g_cl[k]] != 0;
+        if (PROBE) occupied = occ_count(a, 2, a.gq_base_cl + lt.g_cl_off[g], g) != 0;
+        else for (int k = lt.g_cl_off[g]; k < lt.g_cl_off[g + 1]; k++) occupied |= s.occupancy[lt.g_cl[k]] != 0;
         const int base = (g + 1) * 4;
         if (occupied) {
             plan = 1;
-            for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); if (PROBE) atomicOr(s.probe + c, P_STAGED); });
+            for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); if (PROBE) pb_or(s.probe, c, P_STAGED); });
         } else {
             plan = 2 + pend;
             const bool ns_go = pend == 0;
-            for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); if (PROBE) atomicOr(s.probe + c, P_STAGED); });
-            for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); if (PROBE) atomicOr(s.probe + c, P_STAGED); });
+            for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); if (PROBE) pb_or(s.probe, c, P_STAGED); });
+            for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); if (PROBE) pb_or(s.probe, c, P_STAGED); });
             cur = pend; pend = -1;
         }
     }
@@ -94,8 +128,9 @@ __device__ void group_apply(const TickArgs &a, int g) {
     auto commit = [&](int c) {
         const int w = *((volatile int32_t *)(s.stopw + c));
         if ((w >> 2) == g + 1) {
-            s.stop_map[c] = (uint8_t)(w & 1); s.stopw[c] = 0;
-            if (PROBE) { atomicAnd(s.probe + c, ~(P_STOP | P_STAGED)); if (w & 1) atomicOr(s.probe + c, P_STOP); }
+            s.stopw[c] = 0;
+            if (PROBE) { pb_clear(s.probe, c, (w & 1) ? P_STAGED : (P_STOP | P_STAGED)); if (w & 1) pb_or(s.probe, c, P_STOP); }   // the map itself: tsim_tick_export
+            else s.stop_map[c] = (uint8_t)(w & 1);
         }
     };
     if (plan == 1) {

@@ -124,13 +124,16 @@ class GpuTraffic:
         s["scalars"] = z(16, torch.int32)
         self.live_list = (window is None and own_rows is None) if live_list is None else bool(live_list)
         if self.live_list:
-            s["probe"] = z(n, torch.int32)
+            s["probe"] = z((n + 3) // 4, torch.int32)   # one byte per cell
             nt = C.c_int32(0)
             _lib.check(self.lib.tsim_tick_tiles(C.byref(self.cfg), C.byref(nt)))
             s["recs"] = torch.empty(max(3 * nv * 48, 16), dtype=torch.uint8, device=dev)   # two halves of the live list + the sort's staging copy
             s["sort_keys"], s["tile_ws"] = z(2 * nv, torch.int32), z(2 * nt.value, torch.int32)
             s["plans"] = torch.empty(max(nv * 32, 16), dtype=torch.uint8, device=dev)
             s["ev_stamp"], s["ev_plen"], s["ev_poff"] = z(nv, torch.int32), z(nv, torch.int32), z(nv, torch.int64)
+            nb = C.c_longlong(0)
+            _lib.check(self.lib.tsim_tick_group_ws_bytes(C.byref(self.cfg), C.byref(self.lt), C.byref(nb)))
+            s["group_ws"] = z((nb.value + 7) // 8, torch.int64)   # occupancy bit tiles + (tile, mask) lists of the light groups
         if window is not None and not self.live_list:
             s["live_idx"] = z(nv, torch.int32)   # a shard iterates the vehicles of its own window (rebuilt after every halo refresh)
         self.s = s
@@ -138,8 +141,10 @@ class GpuTraffic:
         v2 = ("probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff")
         self.st = _lib.TickState(*[s[k].data_ptr() for k in v1], *(own_rows or (0, 0)), *[(s[k].data_ptr() if self.live_list else 0) for k in v2],
                                  s["live_idx"].data_ptr() if "live_idx" in s else 0,
-                                 s["sort_keys"].data_ptr() if self.live_list else 0, s["tile_ws"].data_ptr() if self.live_list else 0)
+                                 s["sort_keys"].data_ptr() if self.live_list else 0, s["tile_ws"].data_ptr() if self.live_list else 0,
+                                 s["group_ws"].data_ptr() if self.live_list else 0)
         _lib.check(self.lib.tsim_tick_init(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), self._stream))
+        self._ticks_run, self._exported_at = 0, -1
 
     @staticmethod
     def _validate_tapes(tapes, n_ticks, nv, n_events, n_cells):
@@ -172,22 +177,32 @@ class GpuTraffic:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def export(self):
+        """Live-list kernel: bring the public maps and the vehicle SoA up to date (a tick itself only moves records and probe bytes)."""
+        if self.live_list and self._exported_at != self._ticks_run:
+            _lib.check(self.lib.tsim_tick_export(C.byref(self.cfg), C.byref(self.tp), C.byref(self.st), self._stream))
+            self._exported_at = self._ticks_run
+
     # public maps of the reference model (city_model.py:109-115)
     @property
     def occupancy_map(self):
+        self.export()
         return self.s["occupancy"].view(self.win_rows, self.W)
 
     @property
     def stop_map(self):
+        self.export()
         return self.s["stop_map"].view(self.win_rows, self.W)
 
     @property
     def stuck_map(self):
+        self.export()
         return self.s["stuck_map"].view(self.win_rows, self.W)
 
     def step(self, n=1, check=True):
         """Advance n ticks (CityModel.step, city_model.py:1831)."""
         _lib.check(self.lib.tsim_tick_run(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), int(n), self.algo, self._stream))
+        self._ticks_run += int(n)
         if check:
             err = int(self.s["scalars"][1].item())
             if err:
@@ -207,9 +222,8 @@ class GpuTraffic:
 
     def state_host(self):
         """Same dict as oracle.OracleTicks.state() / the reference fixtures."""
-        if self.live_list:   # the vehicle SoA is only written on demand
-            _lib.check(self.lib.tsim_tick_export(C.byref(self.cfg), C.byref(self.tp), C.byref(self.st), self._stream))
-        s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw", "probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff", "live_idx", "sort_keys", "tile_ws")}
+        self.export()   # live list: the maps and the vehicle SoA are only written on demand
+        s = {k: v.cpu().numpy() for k, v in self.s.items() if k not in ("claim", "stopw", "probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff", "live_idx", "sort_keys", "tile_ws", "group_ws")}
         alive = s["alive"][: self.nv] == 1
         cut = lambda a: a[: self.nv]
         # bit 0 is_stuck, bit 1 is_in_malfunction, bits 2-4 direction + 1, bit 5 is_in_collision (the live-list kernel exports the
