@@ -207,6 +207,41 @@ __device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const
     s.scalars[S_NCAND] = 0;
 }
 
+// The light cells of those of a warp's 32 groups (lane L: group g0 + L, plan != 0: it acts this tick) as ONE list the lanes stride
+// over, four items per lane at a time so that their loads travel together: f(groups[4], plans[4], indices into the flat cell list
+// [4], -1 = none).  All 32 lanes call.  A group that acts writes a few dozen cells, and idle intersections all switch in the same
+// tick (every MIN_GREEN ticks): taking the groups, or the cells, one after the other is a long chain of memory round trips that
+// the whole grid waits for at the next barrier.
+constexpr int GI = 4;
+template <class F>
+__device__ __forceinline__ void warp_group_cells(const TickArgs &a, int g0, int ng, int lane, int plan, F f) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    int b = 0, n = 0;
+    if (g0 + lane < ng) { b = a.gc_off[g0 + lane]; n = a.gc_off[g0 + lane + 1] - b; }   // (asked for before the plan is known to matter)
+    if (!__ballot_sync(FULL, plan != 0)) return;
+    if (plan == 0) n = 0;
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    for (int i0 = 0; i0 < total; i0 += 32 * GI) {
+        int gg[GI], pl[GI], k[GI];
+#pragma unroll
+        for (int u = 0; u < GI; u++) {
+            const int i = i0 + u * 32 + lane;
+            int lo = 0;   // the lane whose group owns item i: the first one with incl > i
+#pragma unroll
+            for (int step = 16; step; step >>= 1) { const int v = __shfl_sync(FULL, incl, min(lo + step - 1, 31)); if (v <= i) lo += step; }
+            lo = min(lo, 31);
+            const int start = __shfl_sync(FULL, incl - n, lo), ob = __shfl_sync(FULL, b, lo);
+            pl[u] = __shfl_sync(FULL, plan, lo);
+            gg[u] = g0 + lo;
+            k[u] = i < total ? ob + (i - start) : -1;
+        }
+        f(gg, pl, k);
+    }
+}
+
 // where a tick's time goes: nanoseconds (globaltimer) between the grid-wide barriers, summed over the ticks since the last reset
 // by one thread: [0] decide, [1] sideswipes, [2] sweep 0, [3] later sweeps, [4] move + append, [5] sorted append, [6] spawns + lights
 __device__ unsigned long long g_tick_phase_ns[16];   // [8..]: thread 0's own share: decide vehicles, decide groups, phase-4 record moves, spawns, group commits, events
@@ -221,11 +256,11 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
     const tsim_tick_tapes &tp = a.tp;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
     const int nv = tp.n_vehicles, ng = a.lt.n_groups;
+    const int gwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;   // warps in an order that deals a short list out over all SMs (the light groups)
     const size_t ncell = (size_t)a.W * a.H;
     u64 *plane[2] = {(u64 *)s.claim, (u64 *)s.claim + ncell};
     VRec *recs[2] = {(VRec *)s.recs, (VRec *)s.recs + nv};
     VRec *tmp = (VRec *)s.recs + 2 * (size_t)nv;   // sorted append only: the survivors before they move to their tile's slots
-    const bool sorted = a.n_tiles > 0;
     int32_t *tile_cnt = s.tile_ws, *tile_base = s.tile_ws ? s.tile_ws + a.n_tiles : nullptr;
     VPlan *plans = (VPlan *)s.plans;
 
@@ -248,6 +283,9 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
         VRec *rc = recs[cur], *rn = recs[nxt];
         const int n_live = *((volatile int32_t *)(s.scalars + S_NLIVE0 + cur));
         const uint32_t gen0 = (uint32_t)t * GEN_PER_TICK + 1u;   // generation nobody writes: "no claims yet"
+        // vehicles move at most 5 cells a tick and the plain append keeps the vehicles of a warp together: the tile order of the
+        // list decays slowly, so the list is only re-sorted every few ticks (two barriers and one more pass over the records)
+        const bool sorted = a.n_tiles > 0 && t % a.sort_every == 0;
         // ---- 1: phase A of every live vehicle + light-group decisions (staged)
         int live = 0;
         for (int i = tid; i < n_live; i += nth) {
@@ -262,7 +300,24 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
         OWN_DONE(8);
         live = __reduce_add_sync(FULL, live);
         if (lane == 0 && live) atomicAdd((unsigned long long *)(s.scalars + S_UPD_HI), (unsigned long long)live);
-        for (int g = tid; g < ng; g += nth) group_decide<true>(a, g);
+        // light groups: one thread per group runs the controller; the groups of a warp that act are then staged by the whole warp,
+        // lanes striding over the flat list of the cells their lights control (a few dozen atomics each; one thread doing them
+        // one after the other would keep the whole grid waiting at the barrier)
+        for (int g0 = gwarp * 32; g0 < ng; g0 += nth) {
+            const int g = g0 + lane;
+            const int plan = g < ng ? group_controller<true>(a, g) : 0;
+            warp_group_cells(a, g0, ng, lane, plan, [&](const int (&gg)[GI], const int (&pl)[GI], const int (&k)[GI]) {
+                int role[GI], c[GI];
+#pragma unroll
+                for (int u = 0; u < GI; u++) { role[u] = k[u] >= 0 ? a.gc_role[k[u]] : 0; c[u] = k[u] >= 0 ? a.gc_cell[k[u]] : -1; }
+#pragma unroll
+                for (int u = 0; u < GI; u++) {
+                    // all red: the lights of g_all stop; phase p goes: its axis goes (0), the other one stops (3)
+                    const int val = pl[u] == 1 ? (role[u] == 0 ? 1 : -1) : (role[u] == 0 ? -1 : ((role[u] == 1) == (pl[u] == 2) ? 0 : 3));
+                    if (c[u] >= 0 && val >= 0) { atomicMax(s.stopw + c[u], (gg[u] + 1) * 4 + val); pb_or(s.probe, c[u], P_STAGED); }
+                }
+            });
+        }
         OWN_DONE(9);
         if (tid == 0) s.scalars[S_NLIVE0 + nxt] = 0;   // the other half was last read as `cur` one tick ago
         grid.sync();
@@ -503,7 +558,24 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
             }
         }
         OWN_DONE(11);
-        for (int g = tid; g < ng; g += nth) group_apply<true>(a, g);
+        for (int g0 = gwarp * 32; g0 < ng; g0 += nth) {   // commit of the staged writes, the same way
+            const int g = g0 + lane;
+            const int plan = g < ng ? s.g_plan[g] : 0;
+            warp_group_cells(a, g0, ng, lane, plan, [&](const int (&gg)[GI], const int (&pl)[GI], const int (&k)[GI]) {
+                int c[GI], w[GI];
+#pragma unroll
+                for (int u = 0; u < GI; u++) c[u] = (k[u] >= 0 && (a.gc_role[k[u]] == 0) == (pl[u] == 1)) ? a.gc_cell[k[u]] : -1;
+#pragma unroll
+                for (int u = 0; u < GI; u++) w[u] = c[u] >= 0 ? __ldcg(s.stopw + c[u]) : 0;
+#pragma unroll
+                for (int u = 0; u < GI; u++)
+                    if (c[u] >= 0 && (w[u] >> 2) == gg[u] + 1) {   // this group's write won the cell (written twice if the cell is listed twice: same values)
+                        s.stopw[c[u]] = 0;
+                        pb_clear(s.probe, c[u], (w[u] & 1) ? P_STAGED : (P_STOP | P_STAGED));
+                        if (w[u] & 1) pb_or(s.probe, c[u], P_STOP);
+                    }
+            });
+        }
         OWN_DONE(12);
         scatter_events(t + 1);
         OWN_DONE(13);
@@ -536,25 +608,67 @@ __global__ void __launch_bounds__(256) tick2_export_stop_kernel(long long n, con
     if (t0 < n - n_words * 4) stop_map[n_words * 4 + t0] = (uint8_t)((reinterpret_cast<const uint8_t *>(probe)[n_words * 4 + t0] >> 1) & 1);
 }
 
-// tsim_tick_state.group_ws: | header int64[4] = entries of the N-S lane, W-E lane and cluster lists, occupancy words | occupancy
-// words u64 | masks u64[entries] | tiles int32[entries] | counts int32[3][n_groups] |.  The (tile, mask) pairs of a group's list
-// start where its cells start in the CSR table of tsim_light_tables (W-E lanes and clusters shifted by the lists before them).
+// tsim_tick_state.group_ws: | header int64[8] = entries of the N-S lane, W-E lane and cluster lists, occupancy words, flat light
+// cells | occupancy words u64 | masks u64[entries] | tiles int32[entries] | counts int32[3][n_groups] | flat offsets int32[n_groups
+// + 1] | flat cells int32[flat] | flat roles u8[flat] |.  The (tile, mask) pairs of a group's list start where its cells start in
+// the CSR table of tsim_light_tables (W-E lanes and clusters shifted by the lists before them).
 struct GroupWs {
-    long long n_ns, n_ew, n_cl, n_occ;
+    long long n_ns, n_ew, n_cl, n_occ, n_flat;
     unsigned long long *occ, *mask;
-    int32_t *tile, *cnt;
+    int32_t *tile, *cnt, *gc_off, *gc_cell;
+    uint8_t *gc_role;
     size_t bytes;
 };
-static GroupWs group_ws_layout(void *base, long long n_ns, long long n_ew, long long n_cl, long long n_occ, int ng) {
-    GroupWs w{n_ns, n_ew, n_cl, n_occ, nullptr, nullptr, nullptr, nullptr, 0};
+static GroupWs group_ws_layout(void *base, long long n_ns, long long n_ew, long long n_cl, long long n_occ, long long n_flat, int ng) {
+    GroupWs w{n_ns, n_ew, n_cl, n_occ, n_flat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     const long long e = n_ns + n_ew + n_cl;
-    char *p = (char *)base + 32;
+    char *p = (char *)base + 64;
     w.occ = (unsigned long long *)p; p += n_occ * 8;
     w.mask = (unsigned long long *)p; p += e * 8;
     w.tile = (int32_t *)p; p += e * 4;
     w.cnt = (int32_t *)p; p += (long long)3 * ng * 4;
+    w.gc_off = (int32_t *)p; p += ((long long)ng + 1) * 4;
+    w.gc_cell = (int32_t *)p; p += n_flat * 4;
+    w.gc_role = (uint8_t *)p; p += n_flat;
     w.bytes = (size_t)(p - (char *)base);
     return w;
+}
+
+// cells controlled by the lights of list `off/lights` of group g
+__device__ __forceinline__ int light_list_cells(const tsim_light_tables &lt, const int32_t *off, const int32_t *lights, int g) {
+    int n = 0;
+    for (int k = off[g]; k < off[g + 1]; k++) n += lt.tl_off[lights[k] + 1] - lt.tl_off[lights[k]];
+    return n;
+}
+// out[g + 1] = flat entries of group g (total != NULL: only their sum)
+__global__ void __launch_bounds__(256) group_flat_count_kernel(tsim_light_tables lt, int32_t *out, unsigned long long *total) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= lt.n_groups) return;
+    const int n = light_list_cells(lt, lt.g_all_off, lt.g_all, g) + light_list_cells(lt, lt.g_ns_off, lt.g_ns, g) + light_list_cells(lt, lt.g_ew_off, lt.g_ew, g);
+    if (total) atomicAdd(total, (unsigned long long)n); else out[g + 1] = n;
+}
+// in place: counts in off[1..n] -> offsets (one CTA; init time)
+__global__ void __launch_bounds__(1024) group_flat_scan_kernel(int n, int32_t *off) {
+    __shared__ int part[1024];
+    const int per = (n + 1023) / 1024, b = 1 + threadIdx.x * per, e = min(b + per, n + 1);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += off[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < 1024; i++) { const int v = part[i]; part[i] = run; run += v; } off[0] = 0; }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (int i = b; i < e; i++) { run += off[i]; off[i] = run; }
+}
+__global__ void __launch_bounds__(256) group_flat_fill_kernel(tsim_light_tables lt, const int32_t *off, int32_t *cell, uint8_t *role) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= lt.n_groups) return;
+    int o = off[g];
+    for (int r = 0; r < 3; r++) {
+        const int32_t *lo = r == 0 ? lt.g_all_off : r == 1 ? lt.g_ns_off : lt.g_ew_off, *ll = r == 0 ? lt.g_all : r == 1 ? lt.g_ns : lt.g_ew;
+        for (int k = lo[g]; k < lo[g + 1]; k++)
+            for (int q = lt.tl_off[ll[k]]; q < lt.tl_off[ll[k] + 1]; q++) { cell[o] = lt.tl_cells[q]; role[o] = (uint8_t)r; o++; }
+    }
 }
 
 __global__ void __launch_bounds__(256) group_masks_kernel(int ng, int W, int tiles_x, const int32_t *off0, const int32_t *cells0, const int32_t *off1,
@@ -599,15 +713,26 @@ static void tick_tiles(const tsim_cfg *cfg, int &sx, int &sy, int &tiles_x, int 
 
 bool tick2_enabled(const tsim_tick_state *st) { return st->probe != nullptr; }
 
-static tsim_status group_list_sizes(const tsim_light_tables *lt, long long *n_ns, long long *n_ew, long long *n_cl) {
+static tsim_status group_list_sizes(const tsim_light_tables *lt, long long *n_ns, long long *n_ew, long long *n_cl, long long *n_flat) {
     int32_t v[3] = {0, 0, 0};
+    unsigned long long flat = 0;
     if (lt->n_groups > 0) {
-        if (!lt->g_nsin_off || !lt->g_ewin_off || !lt->g_cl_off) { set_error("tick: NULL light-group table"); return TSIM_ERR_CONFIG; }
+        if (!lt->g_nsin_off || !lt->g_ewin_off || !lt->g_cl_off || !lt->tl_off || !lt->g_all_off || !lt->g_ns_off || !lt->g_ew_off) {
+            set_error("tick: NULL light-group table");
+            return TSIM_ERR_CONFIG;
+        }
         TSIM_CUDA(cudaMemcpy(&v[0], lt->g_nsin_off + lt->n_groups, 4, cudaMemcpyDeviceToHost));
         TSIM_CUDA(cudaMemcpy(&v[1], lt->g_ewin_off + lt->n_groups, 4, cudaMemcpyDeviceToHost));
         TSIM_CUDA(cudaMemcpy(&v[2], lt->g_cl_off + lt->n_groups, 4, cudaMemcpyDeviceToHost));
+        unsigned long long *d = nullptr;
+        TSIM_CUDA(cudaMalloc(&d, 8));
+        TSIM_CUDA(cudaMemset(d, 0, 8));
+        group_flat_count_kernel<<<div_up(lt->n_groups, 256), 256>>>(*lt, nullptr, d);
+        cudaError_t e = cudaMemcpy(&flat, d, 8, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        TSIM_CUDA(e);
     }
-    *n_ns = v[0]; *n_ew = v[1]; *n_cl = v[2];
+    *n_ns = v[0]; *n_ew = v[1]; *n_cl = v[2]; *n_flat = (long long)flat;
     return TSIM_OK;
 }
 
@@ -615,15 +740,15 @@ extern "C" tsim_status tsim_tick_group_ws_bytes(const tsim_cfg *cfg, const tsim_
     tsim_status r = check_cfg(cfg);
     if (r != TSIM_OK) return r;
     if (!lt || !bytes) { set_error("tsim_tick_group_ws_bytes: NULL argument"); return TSIM_ERR_CONFIG; }
-    long long a = 0, b = 0, c = 0;
-    if ((r = group_list_sizes(lt, &a, &b, &c)) != TSIM_OK) return r;
+    long long a = 0, b = 0, c = 0, f = 0;
+    if ((r = group_list_sizes(lt, &a, &b, &c, &f)) != TSIM_OK) return r;
     const long long n_occ = (long long)((cfg->width + 7) / 8) * ((cfg->win_rows + 7) / 8);
-    *bytes = (long long)group_ws_layout(nullptr, a, b, c, n_occ, lt->n_groups).bytes;
+    *bytes = (long long)group_ws_layout(nullptr, a, b, c, n_occ, f, lt->n_groups).bytes;
     return TSIM_OK;
 }
 
 // what tick2_init found in a workspace (tick2_run must not synchronise to read the header back)
-static struct { const void *ws; long long n_ns, n_ew, n_cl, n_occ; int ng; } g_ws_seen = {nullptr, 0, 0, 0, 0, 0};
+static struct { const void *ws; long long n_ns, n_ew, n_cl, n_occ, n_flat; int ng; } g_ws_seen = {nullptr, 0, 0, 0, 0, 0, 0};
 
 tsim_status tick2_check(const tsim_tick_state *st, const tsim_tick_tapes *tp) {
     if (!st->probe || !st->recs || !st->plans || !st->ev_stamp || !st->ev_plen || !st->ev_poff || !st->sort_keys || !st->group_ws) {
@@ -637,23 +762,30 @@ tsim_status tick2_check(const tsim_tick_state *st, const tsim_tick_tapes *tp) {
 
 tsim_status tick2_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st, cudaStream_t cs) {
     const size_t n = (size_t)cfg->width * cfg->win_rows, nv = (size_t)tp->n_vehicles;
-    {   // light groups: empty occupancy tiles, lanes and clusters as (tile, mask) pairs
-        long long a = 0, b = 0, c = 0;
-        tsim_status r = group_list_sizes(lt, &a, &b, &c);
+    {   // light groups: empty occupancy tiles, lanes and clusters as (tile, mask) pairs, the cells of their lights as flat lists
+        long long a = 0, b = 0, c = 0, f = 0;
+        tsim_status r = group_list_sizes(lt, &a, &b, &c, &f);
         if (r != TSIM_OK) return r;
         const int tiles_x = (cfg->width + 7) / 8;
         const long long n_occ = (long long)tiles_x * ((cfg->win_rows + 7) / 8);
-        const GroupWs w = group_ws_layout(st->group_ws, a, b, c, n_occ, lt->n_groups);
-        const long long hdr[4] = {a, b, c, n_occ};
+        const GroupWs w = group_ws_layout(st->group_ws, a, b, c, n_occ, f, lt->n_groups);
+        const long long hdr[8] = {a, b, c, n_occ, f, 0, 0, 0};
         TSIM_CUDA(cudaMemcpyAsync(st->group_ws, hdr, sizeof(hdr), cudaMemcpyHostToDevice, cs));
         TSIM_CUDA(cudaStreamSynchronize(cs));   // hdr lives on this stack frame
         TSIM_CUDA(cudaMemsetAsync(w.occ, 0, (size_t)n_occ * 8, cs));
+        TSIM_CUDA(cudaMemsetAsync(w.gc_off, 0, 4, cs));
         if (lt->n_groups > 0) {
             group_masks_kernel<<<div_up(3ll * lt->n_groups, 256), 256, 0, cs>>>(lt->n_groups, cfg->width, tiles_x, lt->g_nsin_off, lt->g_nsin, lt->g_ewin_off,
                                                                                  lt->g_ewin, lt->g_cl_off, lt->g_cl, (int)a, (int)(a + b), w.mask, w.tile, w.cnt);
             TSIM_LAUNCH_CHECK();
+            group_flat_count_kernel<<<div_up(lt->n_groups, 256), 256, 0, cs>>>(*lt, w.gc_off, nullptr);
+            TSIM_LAUNCH_CHECK();
+            group_flat_scan_kernel<<<1, 1024, 0, cs>>>(lt->n_groups, w.gc_off);
+            TSIM_LAUNCH_CHECK();
+            group_flat_fill_kernel<<<div_up(lt->n_groups, 256), 256, 0, cs>>>(*lt, w.gc_off, w.gc_cell, w.gc_role);
+            TSIM_LAUNCH_CHECK();
         }
-        g_ws_seen = {st->group_ws, a, b, c, n_occ, lt->n_groups};
+        g_ws_seen = {st->group_ws, a, b, c, n_occ, f, lt->n_groups};
     }
     TSIM_CUDA(cudaMemsetAsync(st->probe, 0, (n + 3) / 4 * 4, cs));   // one byte per cell, whole words
     if (nv) {
@@ -687,20 +819,23 @@ extern "C" tsim_status tsim_tick_tiles(const tsim_cfg *cfg, int32_t *n_tiles) {
 tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp, const tsim_tick_state *st, int32_t n_ticks,
                       int32_t algo, cudaStream_t cs) {
     TickArgs a{cfg->width, cfg->win_rows, n_ticks, algo, 0, cfg->win_rows * cfg->width, *lt, *tp, *st};
+    a.sort_every = 16;
     if (st->sort_keys && st->tile_ws) {   // sorted append: worth its extra pass and barrier once the fleet no longer fits the caches
         bool on = tp->n_vehicles >= 200000;
         if (const char *e = getenv("TSIM_TICK_SORT")) on = *e != '0';
         if (on) tick_tiles(cfg, a.tile_sx, a.tile_sy, a.tiles_x, a.n_tiles);
+        if (const char *e = getenv("TSIM_TICK_SORT_EVERY")) { const int v = atoi(e); if (v >= 1) a.sort_every = v; }
     }
     if (g_ws_seen.ws != st->group_ws || g_ws_seen.ng != lt->n_groups) {   // another state than the last tsim_tick_init prepared: read its header
-        long long hdr[4];
+        long long hdr[8];
         TSIM_CUDA(cudaMemcpy(hdr, st->group_ws, sizeof(hdr), cudaMemcpyDeviceToHost));
-        g_ws_seen = {st->group_ws, hdr[0], hdr[1], hdr[2], hdr[3], lt->n_groups};
+        g_ws_seen = {st->group_ws, hdr[0], hdr[1], hdr[2], hdr[3], hdr[4], lt->n_groups};
     }
     {
-        const GroupWs w = group_ws_layout(st->group_ws, g_ws_seen.n_ns, g_ws_seen.n_ew, g_ws_seen.n_cl, g_ws_seen.n_occ, lt->n_groups);
+        const GroupWs w = group_ws_layout(st->group_ws, g_ws_seen.n_ns, g_ws_seen.n_ew, g_ws_seen.n_cl, g_ws_seen.n_occ, g_ws_seen.n_flat, lt->n_groups);
         a.occ = w.occ; a.gq_mask = w.mask; a.gq_tile = w.tile; a.gq_cnt = w.cnt;
         a.occ_tiles_x = (cfg->width + 7) / 8; a.gq_base_ew = (int)g_ws_seen.n_ns; a.gq_base_cl = (int)(g_ws_seen.n_ns + g_ws_seen.n_ew);
+        a.gc_off = w.gc_off; a.gc_cell = w.gc_cell; a.gc_role = w.gc_role;
     }
     int dev = 0, sms = 0, per_sm = 0;
     TSIM_CUDA(cudaGetDevice(&dev));

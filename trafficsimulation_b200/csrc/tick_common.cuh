@@ -37,6 +37,7 @@ struct TickArgs {
     tsim_light_tables lt;
     tsim_tick_tapes tp;
     tsim_tick_state st;
+    int sort_every;                           // ... every so many ticks
     int tile_sx, tile_sy, tiles_x, n_tiles;   // live-list kernel, sorted append: tile = (y >> tile_sy) * tiles_x + (x >> tile_sx); n_tiles == 0: plain append
     // live-list kernel, light groups (tsim_tick_state.group_ws, built by tsim_tick_init): occupancy as one bit per cell in 8 x 8-cell
     // tiles (one 64-bit word each) and, per group, its incoming lanes and its cluster as (tile, mask) pairs
@@ -44,6 +45,9 @@ struct TickArgs {
     const unsigned long long *gq_mask;
     const int32_t *gq_tile, *gq_cnt;
     int occ_tiles_x, gq_base_ew, gq_base_cl;
+    // ... and the cells its lights control, flattened: group -> (cell, role) with role 0 = a light of g_all, 1 = of g_ns, 2 = of g_ew
+    const int32_t *gc_off, *gc_cell;
+    const uint8_t *gc_role;
 };
 
 __device__ __forceinline__ void occ_word_bit(const TickArgs &a, int c, int &word, int &bit) {
@@ -58,8 +62,36 @@ __device__ __forceinline__ void occ_clear(const TickArgs &a, int c) { int w, b; 
 __device__ __forceinline__ int occ_count(const TickArgs &a, int kind, int base, int g) {
     const int n = a.gq_cnt[kind * a.lt.n_groups + g];
     int q = 0;
-    for (int i = 0; i < n; i++) q += __popcll(__ldcg(a.occ + a.gq_tile[base + i]) & a.gq_mask[base + i]);
+    for (int i0 = 0; i0 < n; i0 += 4) {   // four entries at a time: the tile loads, then the occupancy loads, travel together
+        int t[4];
+        unsigned long long m[4], o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { t[j] = i0 + j < n ? a.gq_tile[base + i0 + j] : -1; m[j] = i0 + j < n ? a.gq_mask[base + i0 + j] : 0ull; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = t[j] >= 0 ? __ldcg(a.occ + t[j]) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; j++) q += __popcll(o[j] & m[j]);
+    }
     return q;
+}
+// both lane lists of a group at once (their loads overlap)
+__device__ __forceinline__ void occ_count_lanes(const TickArgs &a, int g, int &ns_q, int &ew_q) {
+    const int ng = a.lt.n_groups, n0 = a.gq_cnt[g], n1 = a.gq_cnt[ng + g], b0 = a.lt.g_nsin_off[g], b1 = a.gq_base_ew + a.lt.g_ewin_off[g];
+    int q0 = 0, q1 = 0;
+    for (int i0 = 0; i0 < max(n0, n1); i0 += 3) {
+        int t[6];
+        unsigned long long m[6], o[6];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            t[j] = i0 + j < n0 ? a.gq_tile[b0 + i0 + j] : -1; m[j] = i0 + j < n0 ? a.gq_mask[b0 + i0 + j] : 0ull;
+            t[3 + j] = i0 + j < n1 ? a.gq_tile[b1 + i0 + j] : -1; m[3 + j] = i0 + j < n1 ? a.gq_mask[b1 + i0 + j] : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) o[j] = t[j] >= 0 ? __ldcg(a.occ + t[j]) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { q0 += __popcll(o[j] & m[j]); q1 += __popcll(o[3 + j] & m[3 + j]); }
+    }
+    ns_q = q0; ew_q = q1;
 }
 
 template <class F>
@@ -70,10 +102,10 @@ __device__ __forceinline__ void for_light_cells(const tsim_light_tables &lt, con
     }
 }
 
-// light group: controller + decision; stop_map writes are staged in `stopw` (atomicMax, priority =
-// group index, then order inside the group) so that concurrent groups reproduce the sequential result
+// light group, controller (intersection_light_group.py:396-494): returns what the group does to its lights this tick -- 0 nothing,
+// 1 all red (a phase change is pending but the intersection is occupied), 2 + p phase p goes (0 N-S, 1 W-E) -- and writes its state
 template <bool PROBE>
-__device__ void group_decide(const TickArgs &a, int g) {
+__device__ __forceinline__ int group_controller(const TickArgs &a, int g) {
     const tsim_light_tables &lt = a.lt;
     const tsim_tick_state &s = a.st;
     int cur = s.g_cur[g], pend = s.g_pend[g];
@@ -81,10 +113,12 @@ __device__ void group_decide(const TickArgs &a, int g) {
         if (a.algo == 0) {   // run_queue_actuated :463-494
             const int qt = ++s.g_qt[g];
             int ns_q = 0, ew_q = 0;
-            if (PROBE) ns_q = occ_count(a, 0, lt.g_nsin_off[g], g);
-            else for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += (int)s.occupancy[lt.g_nsin[k]];
-            if (PROBE) ew_q = occ_count(a, 1, a.gq_base_ew + lt.g_ewin_off[g], g);
-            else for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += (int)s.occupancy[lt.g_ewin[k]];
+            if (PROBE) {
+                occ_count_lanes(a, g, ns_q, ew_q);
+            } else {
+                for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += (int)s.occupancy[lt.g_nsin[k]];
+                for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += (int)s.occupancy[lt.g_ewin[k]];
+            }
             const int cur_q = cur == 0 ? ns_q : ew_q, opp_q = cur == 0 ? ew_q : ns_q;
             if (qt == 1) { s.g_last[g] = cur_q; s.g_gap[g] = 0; }
             if (cur_q > s.g_last[g]) { s.g_last[g] = cur_q; s.g_gap[g] = 0; } else s.g_gap[g]++;
@@ -104,19 +138,29 @@ __device__ void group_decide(const TickArgs &a, int g) {
         bool occupied = false;
         if (PROBE) occupied = occ_count(a, 2, a.gq_base_cl + lt.g_cl_off[g], g) != 0;
         else for (int k = lt.g_cl_off[g]; k < lt.g_cl_off[g + 1]; k++) occupied |= s.occupancy[lt.g_cl[k]] != 0;
-        const int base = (g + 1) * 4;
-        if (occupied) {
-            plan = 1;
-            for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); if (PROBE) pb_or(s.probe, c, P_STAGED); });
-        } else {
-            plan = 2 + pend;
-            const bool ns_go = pend == 0;
-            for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); if (PROBE) pb_or(s.probe, c, P_STAGED); });
-            for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); if (PROBE) pb_or(s.probe, c, P_STAGED); });
-            cur = pend; pend = -1;
-        }
+        if (occupied) plan = 1;
+        else { plan = 2 + pend; cur = pend; pend = -1; }
     }
     s.g_cur[g] = cur; s.g_pend[g] = pend; s.g_plan[g] = plan;
+    return plan;
+}
+
+// light group: controller + decision; stop_map writes are staged in `stopw` (atomicMax, priority =
+// group index, then order inside the group) so that concurrent groups reproduce the sequential result
+template <bool PROBE>
+__device__ void group_decide(const TickArgs &a, int g) {
+    const tsim_light_tables &lt = a.lt;
+    const tsim_tick_state &s = a.st;
+    const int plan = group_controller<PROBE>(a, g);
+    if (plan == 0) return;
+    const int base = (g + 1) * 4;
+    if (plan == 1) {
+        for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); if (PROBE) pb_or(s.probe, c, P_STAGED); });
+    } else {
+        const bool ns_go = plan == 2;
+        for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); if (PROBE) pb_or(s.probe, c, P_STAGED); });
+        for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); if (PROBE) pb_or(s.probe, c, P_STAGED); });
+    }
 }
 
 template <bool PROBE>
