@@ -325,11 +325,11 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
     /* Working set of the LIVE-LIST kernel (all NULL: the vehicle-indexed kernel, which row-band shards use).  With these
        the tick iterates a compacted list of the live vehicles instead of the attempt array: a vehicle is a 48-byte record
        in `recs` that moves to a new slot every tick (warp-aggregated append into the other half), its plan for the tick
-       a 32-byte record in `plans`, and every cell probe reads ONE BYTE of `probe` (occupancy, stop, staged stop, "somebody
-       claimed this cell this tick" and "lies on the planned cells of one / several vehicles" bits).  A tick then touches
-       neither the vehicle SoA nor the occupancy / stop_map / stuck_map byte maps above: tsim_tick_export writes all of them
-       (the maps must start out all zero: tsim_tick_init builds the probe plane for an empty city with every light at go).   */
-    uint32_t *probe;                             /* [ceil(H*W / 4)] words = one byte per cell                                  */
+       a 32-byte record in `plans`, and what a vehicle asks about the cells ahead is answered by BIT PLANES over 8 x 8-cell
+       tiles in `probe` (occupancy, stop, "planned by one vehicle", "planned by several", staged stop, sideswipe query; one
+       64-bit word per tile and plane).  A tick then touches neither the vehicle SoA nor the occupancy / stop_map / stuck_map
+       byte maps above: tsim_tick_export writes all of them (tsim_tick_init starts from an empty city with every light at go). */
+    uint32_t *probe;                             /* tsim_tick_probe_bytes() bytes, 8-byte aligned                              */
     void *recs;                                  /* [2][n_vehicles] x TSIM_TICK_VREC_BYTES                                     */
     void *plans;                                 /* [n_vehicles] x TSIM_TICK_PLAN_BYTES                                        */
     int32_t *ev_stamp, *ev_plen;                 /* [n_vehicles] tick of the vehicle's pending route event, its length         */
@@ -346,8 +346,8 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
        `recs` then holds THREE halves of n_vehicles records.                                                                 */
     int32_t *tile_ws;                            /* [2 * n_tiles] vehicles per tile, first slot of the tile                    */
     /* live-list kernel: what the light groups read, tsim_tick_group_ws_bytes() bytes, 8-byte aligned, filled by tsim_tick_init:
-       occupancy as one bit per cell in 8 x 8-cell tiles, and every group's incoming lanes and cluster as (tile, mask) pairs,
-       so that a queue count (intersection_light_group.py:463-494) is a handful of popcounts instead of one load per lane cell */
+       every group's incoming lanes and cluster as (tile, mask) pairs over the occupancy plane of `probe`, and the cells its
+       lights control as one flat list, so that a queue count (intersection_light_group.py:463-494) is a handful of popcounts instead of one load per lane cell */
     void *group_ws;
 } tsim_tick_state;
 #define TSIM_TICK_VREC_BYTES 48
@@ -356,6 +356,9 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
 /* zero the maps / vehicle / group state and prepare the scratch planes */
 tsim_status tsim_tick_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                            const tsim_tick_state *st, void *stream);
+
+/* bytes of tsim_tick_state.probe for this grid */
+tsim_status tsim_tick_probe_bytes(const tsim_cfg *cfg, long long *bytes);
 
 /* bytes of tsim_tick_state.group_ws for these light tables (reads three table entries back: synchronises) */
 tsim_status tsim_tick_group_ws_bytes(const tsim_cfg *cfg, const tsim_light_tables *lt, long long *bytes);

@@ -19,7 +19,7 @@ SYMBOLS = [
     "tsim_layout_frame_roads", "tsim_layout_label_nothing", "tsim_shard_counts", "tsim_rows_digest", "tsim_debug_write_probe", "tsim_layout_carve", "tsim_layout_zones",
     "tsim_layout_dead_ends", "tsim_layout_upgrade_r2", "tsim_layout_entrances", "tsim_layout_fix_dirs",
     "tsim_layout_lights", "tsim_lights_prepare", "tsim_lights_seed", "tsim_lights_reach", "tsim_lights_reach_planes",
-    "tsim_lights_finish", "tsim_lights_eval", "tsim_lights_links", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_tick_export", "tsim_tick_tiles", "tsim_tick_group_ws_bytes", "tsim_debug_tick_phases", "tsim_tick_message_words", "tsim_tick_pack", "tsim_tick_unpack", "tsim_astar_scratch_bytes", "tsim_astar_batch", "tsim_density_map", "tsim_rain_discs", "tsim_label_mask",
+    "tsim_lights_finish", "tsim_lights_eval", "tsim_lights_links", "tsim_maps", "tsim_tick_init", "tsim_tick_run", "tsim_tick_export", "tsim_tick_tiles", "tsim_tick_group_ws_bytes", "tsim_tick_probe_bytes", "tsim_debug_tick_phases", "tsim_tick_message_words", "tsim_tick_pack", "tsim_tick_unpack", "tsim_astar_scratch_bytes", "tsim_astar_batch", "tsim_density_map", "tsim_rain_discs", "tsim_label_mask",
 ]
 
 

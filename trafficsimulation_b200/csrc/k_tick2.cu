@@ -5,11 +5,14 @@
 //     tick: survivors of the move phase and the spawns of the tick are appended (one atomic per warp) to the other half of
 //     `recs`, so that every phase reads its vehicles as consecutive 48-byte records and a fleet that has mostly arrived (or
 //     has mostly not spawned yet) costs what its live vehicles cost;
-//   * ONE probe byte per cell (`probe`: occupancy | stop | staged-stop bits and two bits "a vehicle claimed this cell in claim
-//     plane 0 / 1 during this tick").  Phase A reads one byte per look-ahead cell instead of two maps; a claim sweep reads one
-//     byte per planned cell and only follows it into the 64-bit claim plane (or the staged stop word) when the bit says there is
-//     something to find.  A byte per cell, because the plane of an 8192 x 8192 city (64 MB) then stays in the 126 MB L2 and the
-//     scattered look-ahead gathers of a large fleet stop going to DRAM one 32-byte sector per cell;
+//   * BIT PLANES over 8 x 8-cell tiles instead of per-cell maps (tick_common.cuh): occupancy, stop, "planned by one vehicle",
+//     "planned by several / stop write staged", staged-stop.  A look-ahead of five cells is two 64-bit loads per plane whatever
+//     the direction of travel, the planes of an 8192 x 8192 city are 8 MB each and stay in L2, and -- what bounds a large fleet
+//     is the rate of L2 atomics (~90 G/s measured), not bytes -- a vehicle makes one atomic per TILE it marks, unmarks or
+//     changes the occupancy of, not one per cell;
+//   * the claim fixed point (k_tick.cu) only for CONTESTED vehicles: phase A marks every cell a vehicle may end on; a vehicle
+//     none of whose cells carries a second mark cannot be blocked by anybody and blocks nobody: it moves as planned.  The others
+//     (1-2 % of a dense fleet) go on a list, and only that list is swept;
 //   * a per-tick PLAN record (32 bytes: the <= 5 planned cells, activation rank, max_steps, stop bits): the sweeps of the
 //     fixed point read it instead of the vehicle state, the tapes and the route arena;
 //   * the spawner's claims (lowest attempt index per origin cell) are made during the move phase in the claim plane the
@@ -53,24 +56,56 @@ static_assert(sizeof(VRec) == TSIM_TICK_VREC_BYTES, "VRec size");
 struct __align__(16) VPlan {   // TSIM_TICK_PLAN_BYTES
     int32_t cell[MAX_SPEED];   // the cells the vehicle may enter this tick (first max_steps entries)
     int32_t rank;
-    uint8_t m, k, stop, early;   // max_steps; steps granted by the last sweep (0xff: none yet); stop_now bits of the cells; early exit
+    uint8_t m, k, stop, early;   // max_steps; steps granted (phase A: = m, then by the last sweep); stop_now bits of the cells, bit 7 = contested; early exit
     int32_t target;              // an arriving vehicle claims nothing
 };
 static_assert(sizeof(VPlan) == TSIM_TICK_PLAN_BYTES, "VPlan size");
 
-// stop_map as the vehicles of this tick see it, from the probe byte (the staged write of a light group that acted this tick wins)
-__device__ __forceinline__ int stop_seen(const tsim_tick_state &s, int c, uint32_t p) {
-    return (p & P_STAGED) ? (__ldcg(s.stopw + c) & 1) : (int)((p >> 1) & 1u);
+// the planned cells of a vehicle as (tile word, bit mask) pairs; e[i] = pair of cell i, b[i] = its bit.  Everything is indexed
+// by unrolled loops so that it stays in registers.
+struct PathBits {
+    int w[MAX_SPEED];
+    u64 m[MAX_SPEED];
+    int e[MAX_SPEED], b[MAX_SPEED];
+    int n;
+};
+__device__ __forceinline__ void path_bits(const TickArgs &a, const int32_t (&cell)[MAX_SPEED], int cnt, PathBits &p) {
+    p.n = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++) { p.w[i] = -1; p.m[i] = 0; p.e[i] = 0; p.b[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < MAX_SPEED; i++) {
+        if (i >= cnt) continue;
+        int w, b;
+        cell_wb(a, cell[i], w, b);
+        int e = p.n;
+#pragma unroll
+        for (int q = 0; q < i; q++) if (q < p.n && p.w[q] == w) e = q;
+#pragma unroll
+        for (int q = 0; q <= i; q++) if (q == e) { p.w[q] = w; p.m[q] |= 1ull << b; }
+        if (e == p.n) p.n++;
+        p.e[i] = e; p.b[i] = b;
+    }
+}
+// bit of cell i in the words `v` loaded for the pairs of p
+__device__ __forceinline__ int path_bit(const PathBits &p, const u64 (&v)[MAX_SPEED], int i) {
+    u64 w = 0;
+#pragma unroll
+    for (int q = 0; q < MAX_SPEED; q++) if (p.e[i] == q) w = v[q];
+    return (int)((w >> p.b[i]) & 1ull);
+}
+__device__ __forceinline__ void path_load(const TickArgs &a, int plane, const PathBits &p, u64 (&v)[MAX_SPEED]) {
+    const u64 *pl = bit_plane(a, plane);
+#pragma unroll
+    for (int q = 0; q < MAX_SPEED; q++) v[q] = q < p.n ? __ldcg(pl + p.w[q]) : 0ull;
 }
 
-// rank of the lowest-ranked vehicle that claimed cell c in claim plane `pi` during sweep `gen` (NO_CLAIM: nobody); p = probe byte of c
-__device__ __forceinline__ int claim_seen(const u64 *plane, int pi, int c, uint32_t p, uint32_t gen) {
-    return (p & (P_CLAIM0 << pi)) ? claim_rank(plane, c, gen) : NO_CLAIM;
-}
-
-__device__ __forceinline__ void claim_marked(u64 *plane, uint32_t *probe, int pi, int c, uint32_t gen, int rank) {
-    claim_cell(plane, c, gen, rank);
-    if (!(pb_load(probe, c) & (P_CLAIM0 << pi))) pb_or(probe, c, P_CLAIM0 << pi);
+// stop_map of cell c as the vehicles of this tick see it (the staged write of a light group that acted this tick wins)
+__device__ __forceinline__ int stop_seen(const TickArgs &a, int c) {
+    int w, b;
+    cell_wb(a, c, w, b);
+    const u64 stg = __ldcg(bit_plane(a, PL_STG) + w), stp = __ldcg(bit_plane(a, PL_STOP) + w);
+    return ((stg >> b) & 1ull) ? (__ldcg(a.st.stopw + c) & 1) : (int)((stp >> b) & 1ull);
 }
 
 // phase A of one vehicle (vehicle_base.py:616-663 on the tick-start snapshot): updates the record, fills the plan
@@ -83,7 +118,7 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
     const int stamp = s.ev_stamp[v];
     const uint8_t malf = tp.malfunction[tv];
     pl.rank = tp.rank[tv];
-    pl.m = 0; pl.k = 0xff; pl.stop = 0; pl.early = 0; pl.target = r.target;
+    pl.m = 0; pl.k = 0; pl.stop = 0; pl.early = 0; pl.target = r.target;
 #pragma unroll
     for (int i = 0; i < MAX_SPEED; i++) pl.cell[i] = -1;
     if (stamp == t) { r.path_off = s.ev_poff[v]; r.path_len = s.ev_plen[v]; }   // the re-plan the reference made this tick (replayed)
@@ -110,11 +145,11 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
             const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
             if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
             const int c = ny * a.W + nx;
-            if (pb_load(s.probe, c) & P_OCC) { pb_or(s.probe, c, P_WANT); any = true; }
+            if (bit_get(a, PL_OCC, c)) { bit_set(a, PL_WANT, c); any = true; }
         }
         if (any) s.sort_keys[atomicAdd(s.scalars + S_NCAND, 1)] = slot;
     }
-    if (pb_load(s.probe, pos) & P_STOP) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }   // :639-643
+    if (bit_get(a, PL_STOP, pos)) { r.base_speed = 0; r.cur_speed = 0; pl.early = 1; return; }   // :639-643
     int base = r.base_speed;
     if (base == 0) { base = tp.speed[tv]; r.base_speed = (int8_t)base; }   // :94-112
     int sp = base;
@@ -125,27 +160,42 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
     const int len = r.path_len;
     const int32_t *path = tp.ev_cells + r.path_off;
     int ms = min(min(sp, len), MAX_SPEED);
-    int cell[MAX_SPEED];
-    uint32_t pw[MAX_SPEED];
+    int32_t cell[MAX_SPEED];
 #pragma unroll
     for (int i = 0; i < MAX_SPEED; i++) cell[i] = i < ms ? path[i] : -1;
 #pragma unroll
-    for (int i = 0; i < MAX_SPEED; i++) pw[i] = cell[i] >= 0 ? pb_load(s.probe, cell[i]) : 0u;
+    for (int i = MAX_SPEED - 1; i >= 0; i--) if (i < ms && cell[i] < 0) ms = i;   // a cell outside the window blocks, like a vehicle
+    PathBits pb;
+    path_bits(a, cell, ms, pb);
+    {
+        u64 occ[MAX_SPEED], stp[MAX_SPEED];
+        path_load(a, PL_OCC, pb, occ);
+        path_load(a, PL_STOP, pb, stp);
 #pragma unroll
-    for (int i = MAX_SPEED - 1; i >= 0; i--)
-        if (i < ms && (cell[i] < 0 || (pw[i] & (P_OCC | P_STOP)))) ms = i;   // a cell outside the window blocks, like a vehicle
+        for (int q = 0; q < MAX_SPEED; q++) occ[q] |= stp[q];
+#pragma unroll
+        for (int i = MAX_SPEED - 1; i >= 0; i--) if (i < ms && path_bit(pb, occ, i)) ms = i;
+    }
 #pragma unroll
     for (int i = 0; i < MAX_SPEED; i++) pl.cell[i] = i < ms ? cell[i] : -1;
     pl.m = (uint8_t)ms;
+    pl.k = (uint8_t)ms;   // what an uncontested vehicle does: none of its cells is a stop cell (max_steps ends before the first one)
     // Every cell this vehicle could end on is marked: once = nobody else plans to come here, twice = somebody does.  Only vehicles
-    // with a twice-marked cell take part in the claim fixed point (the marks come off again in the move phase).
-    uint32_t was[MAX_SPEED];
+    // with a twice-marked cell take part in the claim fixed point (the marks come off again in the move phase).  One atomic per tile.
+    if (!(a.debug & 4)) {
+        u64 mk[MAX_SPEED], was[MAX_SPEED];
 #pragma unroll
-    for (int i = 0; i < MAX_SPEED; i++)   // all marks first (independent round trips), then the second marks
-        was[i] = i < ms ? pb_or(s.probe, cell[i], (pw[i] & P_TOUCH1) ? (P_TOUCH1 | P_TOUCH2) : P_TOUCH1) : 0u;
+        for (int q = 0; q < MAX_SPEED; q++) {   // the cells this side of max_steps
+            mk[q] = 0;
 #pragma unroll
-    for (int i = 0; i < MAX_SPEED; i++)
-        if (i < ms && (was[i] & P_TOUCH1) && !(pw[i] & P_TOUCH1)) pb_or(s.probe, cell[i], P_TOUCH2);
+            for (int i = 0; i < MAX_SPEED; i++) if (i < ms && pb.e[i] == q) mk[q] |= 1ull << pb.b[i];
+        }
+        u64 *t1 = bit_plane(a, PL_T1), *t2 = bit_plane(a, PL_T2);
+#pragma unroll
+        for (int q = 0; q < MAX_SPEED; q++) was[q] = mk[q] ? atomicOr(t1 + pb.w[q], mk[q]) : 0ull;   // all first (independent round trips)
+#pragma unroll
+        for (int q = 0; q < MAX_SPEED; q++) if (was[q] & mk[q]) atomicOr(t2 + pb.w[q], was[q] & mk[q]);
+    }
     if (ms <= 0) {
         r.base_speed = 0;
         if (pos == r.target) s.scalars[S_ERR] = 30;   // tape contract: a live vehicle is never at its target in phase A
@@ -177,7 +227,7 @@ __device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const
             const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
             if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
             const int c = ny * a.W + nx;
-            if (settled || !(pb_load(s.probe, c) & P_OCC)) continue;
+            if (settled || !bit_get(a, PL_OCC, c)) continue;
             const u64 w = who[c];
             if ((uint32_t)(w >> 32) != gen0) { s.scalars[S_ERR] = 35; continue; }   // an occupied cell without a live vehicle on it
             const int j = (int)(uint32_t)w;
@@ -188,10 +238,10 @@ __device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const
             if (u_cur <= 0 || U.is_stuck || u_stranded) continue;
             if (U.direction != opp_of(d)) continue;
             R.collision = 1; R.malfunction = 0; R.stranded = COLLISION_TICKS; R.base_speed = 0; R.cur_speed = 0;
-            plans[i].k = 0xff; plans[i].early = 1;   // m stays: the marks on its planned cells still come off in the move phase
+            plans[i].k = 0; plans[i].early = 1;   // m stays: the marks on its planned cells still come off in the move phase
             U.collision = 1; U.malfunction = 0; U.base_speed = 0; U.cur_speed = 0; U.prev_cur = 0; U.prev_flags = 2;
             if (earlier) U.stranded = COLLISION_TICKS;                                   // decided before the hit: it still makes this tick's move
-            else { U.stranded = COLLISION_TICKS - 1; plans[j].k = 0xff; plans[j].early = 1; }   // _tick_stranded at its own turn
+            else { U.stranded = COLLISION_TICKS - 1; plans[j].k = 0; plans[j].early = 1; }   // _tick_stranded at its own turn
             settled = true;
         }
     }
@@ -201,7 +251,7 @@ __device__ void sideswipe_fixup(const TickArgs &a, VRec *rc, VPlan *plans, const
         for (int side = 0; side < 2; side++) {
             const int l = side ? right_of(d) : ((d + 3) & 3), nx = x + dx_of(l), ny = y + dy_of(l);
             if (nx < 0 || nx >= a.W || ny < 0 || ny >= a.H) continue;
-            if (pb_load(s.probe, ny * a.W + nx) & P_WANT) pb_clear(s.probe, ny * a.W + nx, P_WANT);
+            if (bit_get(a, PL_WANT, ny * a.W + nx)) bit_clear(a, PL_WANT, ny * a.W + nx);
         }
     }
     s.scalars[S_NCAND] = 0;
@@ -314,7 +364,13 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                 for (int u = 0; u < GI; u++) {
                     // all red: the lights of g_all stop; phase p goes: its axis goes (0), the other one stops (3)
                     const int val = pl[u] == 1 ? (role[u] == 0 ? 1 : -1) : (role[u] == 0 ? -1 : ((role[u] == 1) == (pl[u] == 2) ? 0 : 3));
-                    if (c[u] >= 0 && val >= 0) { atomicMax(s.stopw + c[u], (gg[u] + 1) * 4 + val); pb_or(s.probe, c[u], P_STAGED); }
+                    if (c[u] >= 0 && val >= 0) {   // whoever plans to enter the cell must look at the staged value: second mark
+                        int w, b;
+                        cell_wb(a, c[u], w, b);
+                        atomicMax(s.stopw + c[u], (gg[u] + 1) * 4 + val);
+                        atomicOr(bit_plane(a, PL_STG) + w, 1ull << b);
+                        atomicOr(bit_plane(a, PL_T2) + w, 1ull << b);
+                    }
                 }
             });
         }
@@ -328,7 +384,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
             // who stands on the cells the candidates asked about: slot of that vehicle, tagged with a generation nobody reads as a claim
             for (int i = tid; i < n_live; i += nth) {
                 const int p = rc[i].pos;
-                if (pb_load(s.probe, p) & P_WANT) plane[1][p] = ((u64)gen0 << 32) | (u64)(uint32_t)i;
+                if (bit_get(a, PL_WANT, p)) plane[1][p] = ((u64)gen0 << 32) | (u64)(uint32_t)i;
             }
             grid.sync();
             if (tid == 0) sideswipe_fixup(a, rc, plans, plane[1], gen0, n_cand);
@@ -355,28 +411,30 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                         VPlan pl = plans[i];
                         if (!pl.early && pl.m) {
                             const int m = pl.m;
-                            uint32_t pw[MAX_SPEED], sm = 0, any2 = 0;
+                            PathBits pb;
+                            path_bits(a, pl.cell, m, pb);
+                            u64 t2[MAX_SPEED];
+                            path_load(a, PL_T2, pb, t2);
 #pragma unroll
-                            for (int j = 0; j < MAX_SPEED; j++) pw[j] = j < m ? pb_load(s.probe, pl.cell[j]) : 0u;
+                            for (int q = 0; q < MAX_SPEED; q++) contested |= (t2[q] & pb.m[q]) != 0;
+                            if (contested) {   // the stop bits as of now (staged writes folded in), the first claim
+                                uint32_t sm = 0;
 #pragma unroll
-                            for (int j = 0; j < MAX_SPEED; j++) {
-                                if (j < m && stop_seen(s, pl.cell[j], pw[j]) == 1) sm |= 1u << j;
-                                any2 |= pw[j] & P_TOUCH2;
-                            }
-                            int k = 0;
-                            bool open = true;
+                                for (int j = 0; j < MAX_SPEED; j++) if (j < m && stop_seen(a, pl.cell[j]) == 1) sm |= 1u << j;
+                                int k = 0;
+                                bool open = true;
 #pragma unroll
-                            for (int j = 0; j < MAX_SPEED; j++) {   // _execute_movement :733-753: a stop cell may only be entered on the last step
-                                open = open && j < m && !(((sm >> j) & 1u) && j + 1 != m);
-                                if (open) k = j + 1;
-                            }
-                            contested = any2 != 0;
-                            pl.stop = (uint8_t)(sm | (contested ? 0x80u : 0u));
-                            pl.k = (uint8_t)k;
-                            *reinterpret_cast<uint32_t *>(&plans[i].m) = *reinterpret_cast<const uint32_t *>(&pl.m);   // m, k, stop, early
-                            if (contested && k >= 1) {
-                                const int c = pl.cell[k - 1];
-                                if (c != pl.target) claim_marked(plane[pc], s.probe, pc, c, gen_cur, pl.rank);   // an arriving vehicle is removed at once
+                                for (int j = 0; j < MAX_SPEED; j++) {   // _execute_movement :733-753: a stop cell may only be entered on the last step
+                                    open = open && j < m && !(((sm >> j) & 1u) && j + 1 != m);
+                                    if (open) k = j + 1;
+                                }
+                                pl.stop = (uint8_t)(sm | 0x80u);
+                                pl.k = (uint8_t)k;
+                                *reinterpret_cast<uint32_t *>(&plans[i].m) = *reinterpret_cast<const uint32_t *>(&pl.m);   // m, k, stop, early
+                                if (k >= 1) {
+                                    const int c = pl.cell[k - 1];
+                                    if (c != pl.target) claim_cell(plane[pc], c, gen_cur, pl.rank);   // an arriving vehicle is removed at once
+                                }
                             }
                         }
                     }
@@ -393,19 +451,17 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                 const int n_cont = *((volatile int32_t *)(s.scalars + S_NCONT));
                 for (int q = tid; q < n_cont; q += nth) {
                     const int i = cont[q];
-                    VPlan pl = plans[i];
-                    if (pl.early) continue;   // (a sideswipe cannot hit after sweep 0; kept for symmetry)
+                    const VPlan pl = plans[i];
                     const int m = pl.m;
-                    uint32_t pw[MAX_SPEED];
+                    int cr[MAX_SPEED];
 #pragma unroll
-                    for (int j = 0; j < MAX_SPEED; j++) pw[j] = j < m ? pb_load(s.probe, pl.cell[j]) : 0u;
+                    for (int j = 0; j < MAX_SPEED; j++) cr[j] = j < m ? claim_rank(plane[pp], pl.cell[j], gen_prev) : NO_CLAIM;
                     int k = 0;
                     bool open = true;
 #pragma unroll
                     for (int j = 0; j < MAX_SPEED; j++) {   // _execute_movement :733-753
                         // a lower-ranked vehicle ends here; a stop cell may only be entered on the last step
-                        const int cr = j < m ? claim_seen(plane[pp], pp, pl.cell[j], pw[j], gen_prev) : NO_CLAIM;
-                        open = open && j < m && !(cr < pl.rank) && !(((pl.stop >> j) & 1u) && j + 1 != m);
+                        open = open && j < m && !(cr[j] < pl.rank) && !(((pl.stop >> j) & 1u) && j + 1 != m);
                         if (open) k = j + 1;
                     }
                     if (k != pl.k) {
@@ -414,7 +470,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                     }
                     if (k >= 1) {
                         const int c = pl.cell[k - 1];
-                        if (c != pl.target) claim_marked(plane[pc], s.probe, pc, c, gen_cur, pl.rank);
+                        if (c != pl.target) claim_cell(plane[pc], c, gen_cur, pl.rank);
                     }
                 }
             }
@@ -441,18 +497,33 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                 const VPlan pl = plans[i];
                 int pos = r.pos;
                 const int target = r.target;
+                if (pl.m && !(a.debug & 1)) {   // nobody reads the marks of this tick any more: they come off, one atomic per tile
+                    PathBits pb;
+                    path_bits(a, pl.cell, pl.m, pb);
+                    u64 *t1 = bit_plane(a, PL_T1), *t2 = bit_plane(a, PL_T2);
 #pragma unroll
-                for (int j = 0; j < MAX_SPEED; j++)   // nobody reads the marks and claim bits of this tick any more
-                    if (j < pl.m) pb_clear(s.probe, pl.cell[j], P_TOUCH1 | P_TOUCH2 | P_CLAIM0 | P_CLAIM1);
+                    for (int q = 0; q < MAX_SPEED; q++) {
+                        if (q >= pb.n) continue;
+                        atomicAnd(t1 + pb.w[q], ~pb.m[q]);
+                        if (pl.stop & 0x80u) atomicAnd(t2 + pb.w[q], ~pb.m[q]);
+                    }
+                }
                 if (!pl.early) {
-                    const int k = pl.k == 0xff ? 0 : pl.k;
+                    const int k = pl.k;
                     if (k >= 1) {
                         const int fin = pl.cell[k - 1], prev = k >= 2 ? pl.cell[k - 2] : pos;
                         // move_vehicle city_model.py:1945-1963.  Nobody ends on the cell this vehicle leaves (it was occupied when
                         // everybody looked ahead), so its occupancy bit simply goes; what stuck_map says about the new cell
                         // travels in the record (:1956-1958, before _move_to resets is_stuck)
-                        pb_clear(s.probe, pos, P_OCC); occ_clear(a, pos);
-                        if (fin != target) { pb_or(s.probe, fin, P_OCC); occ_set(a, fin); }
+                        {
+                            int w0, b0, w1, b1;
+                            cell_wb(a, pos, w0, b0);
+                            cell_wb(a, fin, w1, b1);
+                            u64 *occ = bit_plane(a, PL_OCC);
+                            if (fin == target) atomicAnd(occ + w0, ~(1ull << b0));
+                            else if (w0 == w1) atomicXor(occ + w0, (1ull << b0) | (1ull << b1));   // both bits are known: one flips off, one on
+                            else { atomicAnd(occ + w0, ~(1ull << b0)); atomicOr(occ + w1, 1ull << b1); }
+                        }
                         r.mark = (k == 1 && r.is_stuck) ? 1 : 0;
                         const int d = fin - prev;                                // compute_direction numba_utilities.py:14-28
                         r.direction = (int8_t)(d == a.W ? DN : d == 1 ? DE : d == -a.W ? DS : d == -1 ? DW : r.direction);
@@ -463,12 +534,11 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                     }
                     r.prev_valid = 1;   // step() :677
                 } else {                // :679-680 tick_stuck :687-693
-                    const uint32_t pw = pb_load(s.probe, pos);
-                    if (r.prev_valid && stop_seen(s, pos, pw) != 1) {
+                    if (r.prev_valid && stop_seen(a, pos) != 1) {
                         const int st = ++r.stuck_ticks;
                         if (st > STUCK_THRESHOLD && !r.is_stuck) r.is_stuck = 1;
                     }
-                    if (pos == target) { pb_clear(s.probe, pos, P_OCC); occ_clear(a, pos); }
+                    if (pos == target) bit_clear(a, PL_OCC, pos);
                 }
                 keep = pos != target;   // on_target_reached :755-775 -> remove_vehicle city_model.py:1920-1929
             }
@@ -538,7 +608,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
             int o = -1;
             if (k < k1) {
                 o = tp.origin[k];
-                born = o >= 0 && !(pb_load(s.probe, o) & P_OCC) && claim_rank(plane[po], o, gen_spawn) == k;
+                born = o >= 0 && !bit_get(a, PL_OCC, o) && claim_rank(plane[po], o, gen_spawn) == k;
             }
             const uint32_t mask = __ballot_sync(FULL, born);
             if (mask) {
@@ -553,7 +623,7 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                     r.steps = 0; r.stranded = 0; r.stuck_ticks = 0; r.base_speed = 0; r.cur_speed = 0;
                     r.is_stuck = 0; r.prev_valid = 0; r.malfunction = 0; r.direction = -1; r.collision = 0; r.prev_cur = 0; r.prev_flags = 0; r.mark = 0; r.pad = 0;
                     rn[base + __popc(mask & ((1u << lane) - 1u))] = r;
-                    pb_or(s.probe, o, P_OCC); occ_set(a, o);   // place_vehicle city_model.py:1904-1907
+                    bit_set(a, PL_OCC, o);   // place_vehicle city_model.py:1904-1907
                 }
             }
         }
@@ -571,8 +641,11 @@ __global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
                 for (int u = 0; u < GI; u++)
                     if (c[u] >= 0 && (w[u] >> 2) == gg[u] + 1) {   // this group's write won the cell (written twice if the cell is listed twice: same values)
                         s.stopw[c[u]] = 0;
-                        pb_clear(s.probe, c[u], (w[u] & 1) ? P_STAGED : (P_STOP | P_STAGED));
-                        if (w[u] & 1) pb_or(s.probe, c[u], P_STOP);
+                        int tw, tb;
+                        cell_wb(a, c[u], tw, tb);
+                        if (w[u] & 1) atomicOr(bit_plane(a, PL_STOP) + tw, 1ull << tb); else atomicAnd(bit_plane(a, PL_STOP) + tw, ~(1ull << tb));
+                        atomicAnd(bit_plane(a, PL_STG) + tw, ~(1ull << tb));
+                        atomicAnd(bit_plane(a, PL_T2) + tw, ~(1ull << tb));
                     }
             });
         }
@@ -600,30 +673,30 @@ __global__ void __launch_bounds__(256) tick2_export_kernel(tsim_tick_state s, in
     }
 }
 
-// stop_map = the committed stop bit of every probe byte (four cells per thread; the plane is padded to whole words)
-__global__ void __launch_bounds__(256) tick2_export_stop_kernel(long long n, const uint32_t *probe, uint8_t *stop_map) {
-    const long long n_words = n / 4, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long i = t0; i < n_words; i += (long long)gridDim.x * blockDim.x)
-        reinterpret_cast<uint32_t *>(stop_map)[i] = (probe[i] >> 1) & 0x01010101u;
-    if (t0 < n - n_words * 4) stop_map[n_words * 4 + t0] = (uint8_t)((reinterpret_cast<const uint8_t *>(probe)[n_words * 4 + t0] >> 1) & 1);
+// stop_map = the committed stop plane, cell by cell
+__global__ void __launch_bounds__(256) tick2_export_stop_kernel(int W, int H, int tiles_x, const unsigned long long *stop, uint8_t *stop_map) {
+    const long long n = (long long)W * H;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(c / W), x = (int)(c - (long long)y * W);
+        stop_map[c] = (uint8_t)((stop[(y >> 3) * tiles_x + (x >> 3)] >> ((y & 7) * 8 + (x & 7))) & 1ull);
+    }
 }
 
 // tsim_tick_state.group_ws: | header int64[8] = entries of the N-S lane, W-E lane and cluster lists, occupancy words, flat light
-// cells | occupancy words u64 | masks u64[entries] | tiles int32[entries] | counts int32[3][n_groups] | flat offsets int32[n_groups
-// + 1] | flat cells int32[flat] | flat roles u8[flat] |.  The (tile, mask) pairs of a group's list start where its cells start in
+// cells | masks u64[entries] | tiles int32[entries] | counts int32[3][n_groups] | flat offsets int32[n_groups
+// + 1] | flat cells int32[flat] | flat roles u8[flat] |  (the occupancy words are plane PL_OCC of `probe`).  The (tile, mask) pairs of a group's list start where its cells start in
 // the CSR table of tsim_light_tables (W-E lanes and clusters shifted by the lists before them).
 struct GroupWs {
     long long n_ns, n_ew, n_cl, n_occ, n_flat;
-    unsigned long long *occ, *mask;
+    unsigned long long *mask;
     int32_t *tile, *cnt, *gc_off, *gc_cell;
     uint8_t *gc_role;
     size_t bytes;
 };
 static GroupWs group_ws_layout(void *base, long long n_ns, long long n_ew, long long n_cl, long long n_occ, long long n_flat, int ng) {
-    GroupWs w{n_ns, n_ew, n_cl, n_occ, n_flat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    GroupWs w{n_ns, n_ew, n_cl, n_occ, n_flat, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     const long long e = n_ns + n_ew + n_cl;
     char *p = (char *)base + 64;
-    w.occ = (unsigned long long *)p; p += n_occ * 8;
     w.mask = (unsigned long long *)p; p += e * 8;
     w.tile = (int32_t *)p; p += e * 4;
     w.cnt = (int32_t *)p; p += (long long)3 * ng * 4;
@@ -713,6 +786,16 @@ static void tick_tiles(const tsim_cfg *cfg, int &sx, int &sy, int &tiles_x, int 
 
 bool tick2_enabled(const tsim_tick_state *st) { return st->probe != nullptr; }
 
+static size_t probe_bytes(const tsim_cfg *cfg) { return (size_t)N_PLANES * ((cfg->width + 7) / 8) * ((cfg->win_rows + 7) / 8) * 8; }
+
+extern "C" tsim_status tsim_tick_probe_bytes(const tsim_cfg *cfg, long long *bytes) {
+    tsim_status r = check_cfg(cfg);
+    if (r != TSIM_OK) return r;
+    if (!bytes) { set_error("tsim_tick_probe_bytes: NULL output"); return TSIM_ERR_CONFIG; }
+    *bytes = (long long)probe_bytes(cfg);
+    return TSIM_OK;
+}
+
 static tsim_status group_list_sizes(const tsim_light_tables *lt, long long *n_ns, long long *n_ew, long long *n_cl, long long *n_flat) {
     int32_t v[3] = {0, 0, 0};
     unsigned long long flat = 0;
@@ -772,7 +855,6 @@ tsim_status tick2_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const t
         const long long hdr[8] = {a, b, c, n_occ, f, 0, 0, 0};
         TSIM_CUDA(cudaMemcpyAsync(st->group_ws, hdr, sizeof(hdr), cudaMemcpyHostToDevice, cs));
         TSIM_CUDA(cudaStreamSynchronize(cs));   // hdr lives on this stack frame
-        TSIM_CUDA(cudaMemsetAsync(w.occ, 0, (size_t)n_occ * 8, cs));
         TSIM_CUDA(cudaMemsetAsync(w.gc_off, 0, 4, cs));
         if (lt->n_groups > 0) {
             group_masks_kernel<<<div_up(3ll * lt->n_groups, 256), 256, 0, cs>>>(lt->n_groups, cfg->width, tiles_x, lt->g_nsin_off, lt->g_nsin, lt->g_ewin_off,
@@ -787,7 +869,7 @@ tsim_status tick2_init(const tsim_cfg *cfg, const tsim_light_tables *lt, const t
         }
         g_ws_seen = {st->group_ws, a, b, c, n_occ, f, lt->n_groups};
     }
-    TSIM_CUDA(cudaMemsetAsync(st->probe, 0, (n + 3) / 4 * 4, cs));   // one byte per cell, whole words
+    TSIM_CUDA(cudaMemsetAsync(st->probe, 0, probe_bytes(cfg), cs));   // every plane empty: nobody on the road, every light at go
     if (nv) {
         fill_i32_kernel2<<<div_up((long long)nv, 256) < 1184 ? div_up((long long)nv, 256) : 1184, 256, 0, cs>>>((long long)nv, st->ev_stamp, -1);
         TSIM_LAUNCH_CHECK();
@@ -820,6 +902,7 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
                       int32_t algo, cudaStream_t cs) {
     TickArgs a{cfg->width, cfg->win_rows, n_ticks, algo, 0, cfg->win_rows * cfg->width, *lt, *tp, *st};
     a.sort_every = 16;
+    if (const char *e = getenv("TSIM_TICK_DEBUG")) a.debug = atoi(e);
     if (st->sort_keys && st->tile_ws) {   // sorted append: worth its extra pass and barrier once the fleet no longer fits the caches
         bool on = tp->n_vehicles >= 200000;
         if (const char *e = getenv("TSIM_TICK_SORT")) on = *e != '0';
@@ -833,8 +916,11 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
     }
     {
         const GroupWs w = group_ws_layout(st->group_ws, g_ws_seen.n_ns, g_ws_seen.n_ew, g_ws_seen.n_cl, g_ws_seen.n_occ, g_ws_seen.n_flat, lt->n_groups);
-        a.occ = w.occ; a.gq_mask = w.mask; a.gq_tile = w.tile; a.gq_cnt = w.cnt;
-        a.occ_tiles_x = (cfg->width + 7) / 8; a.gq_base_ew = (int)g_ws_seen.n_ns; a.gq_base_cl = (int)(g_ws_seen.n_ns + g_ws_seen.n_ew);
+        a.occ_tiles_x = (cfg->width + 7) / 8;
+        a.n_tw = (long long)a.occ_tiles_x * ((cfg->win_rows + 7) / 8);
+        a.bits = (unsigned long long *)st->probe;
+        a.occ = a.bits + PL_OCC * a.n_tw; a.gq_mask = w.mask; a.gq_tile = w.tile; a.gq_cnt = w.cnt;
+        a.gq_base_ew = (int)g_ws_seen.n_ns; a.gq_base_cl = (int)(g_ws_seen.n_ns + g_ws_seen.n_ew);
         a.gc_off = w.gc_off; a.gc_cell = w.gc_cell; a.gc_role = w.gc_role;
     }
     int dev = 0, sms = 0, per_sm = 0;
@@ -854,7 +940,7 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
     const long long cap = (long long)sms * k;
     const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     void *args[] = {&a};
-    // The probe plane is what every look-ahead gathers from: ask for it to stay in L2 (persisting lines; everything else a tick
+    // The bit planes are what every look-ahead gathers from: ask for them to stay in L2 (persisting lines; everything else a tick
     // reads is streamed once per phase).  TSIM_TICK_L2_PERSIST=0 launches without the window.
     static int max_persist = -1, max_window = 0;
     if (max_persist < 0) {
@@ -863,7 +949,7 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
         if (const char *e = getenv("TSIM_TICK_L2_PERSIST")) if (*e == '0') max_persist = 0;
         if (getenv("TSIM_DEBUG")) fprintf(stderr, "[tsim] tick: persisting L2 up to %d bytes, access window up to %d bytes\n", max_persist, max_window);
     }
-    const size_t plane_bytes = ((size_t)cfg->width * cfg->win_rows + 3) / 4 * 4;
+    const size_t plane_bytes = probe_bytes(cfg);
     cudaLaunchAttribute attr[2];
     int n_attr = 0;
     attr[n_attr].id = cudaLaunchAttributeCooperative;
@@ -898,10 +984,14 @@ extern "C" tsim_status tsim_tick_export(const tsim_cfg *cfg, const tsim_tick_tap
     cudaStream_t cs = (cudaStream_t)stream;
     const long long n = (long long)cfg->width * cfg->win_rows;
     if (!st->occupancy || !st->stop_map || !st->stuck_map) { set_error("tsim_tick_export: NULL map"); return TSIM_ERR_CONFIG; }
-    if (((uintptr_t)st->stop_map & 3) != 0) { set_error("tsim_tick_export: stop_map must be 4-byte aligned"); return TSIM_ERR_CONFIG; }
     TSIM_CUDA(cudaMemsetAsync(st->occupancy, 0, (size_t)n, cs));
     TSIM_CUDA(cudaMemsetAsync(st->stuck_map, 0, (size_t)n, cs));
-    tick2_export_stop_kernel<<<div_up(n / 4 + 1, 256) < 2368 ? div_up(n / 4 + 1, 256) : 2368, 256, 0, cs>>>(n, st->probe, st->stop_map);
+    {
+        const int tiles_x = (cfg->width + 7) / 8;
+        const long long n_tw = (long long)tiles_x * ((cfg->win_rows + 7) / 8);
+        tick2_export_stop_kernel<<<div_up(n, 256) < 2368 ? div_up(n, 256) : 2368, 256, 0, cs>>>(cfg->width, cfg->win_rows, tiles_x,
+                                                                                              (const unsigned long long *)st->probe + PL_STOP * n_tw, st->stop_map);
+    }
     TSIM_LAUNCH_CHECK();
     if (nv == 0) return TSIM_OK;
     if (!st->alive || !st->pos || !st->path_off || !st->path_len || !st->steps || !st->stranded || !st->stuck_ticks || !st->base_speed ||

@@ -14,20 +14,17 @@ typedef unsigned long long u64;
 enum { S_TICK = 0, S_ERR = 1, S_ITERS = 2, S_UPDATES = 3, S_FLAG0 = 4, S_FLAG1 = 5, S_UPD_HI = 6 /* 64-bit: [6..7] */, S_FLAG2 = 8, S_XERR = 9 /* shard exchange */,
        S_NLIST = 12, S_LIST_OK = 13 /* live_idx: entries, valid for the next tick */, S_NCAND = 14 /* sideswipe candidates of the tick */, S_NCONT = 15 /* vehicles in the claim fixed point of the tick */ };
 
-// probe BYTE of a cell (live-list kernel): what a vehicle needs to know about a cell, in one load.  One byte per cell keeps the
-// whole plane (64 MB for 8192 x 8192) in the 126 MB L2, where the look-ahead gathers of a large fleet hit instead of going to DRAM
-constexpr uint32_t P_OCC = 1u, P_STOP = 2u, P_STAGED = 4u;   // occupancy_map, stop_map, "a light group staged a stop_map write this tick"
-constexpr uint32_t P_WANT = 8u;                               // a sideswipe candidate asks which vehicle stands here (this tick's phase A only)
-constexpr uint32_t P_CLAIM0 = 16u, P_CLAIM1 = 32u;            // some vehicle claimed the cell in claim plane 0 / 1 this tick (taken off again in phase 4;
-                                                              //   a stale bit only costs the load of a claim word of another generation)
-constexpr uint32_t P_TOUCH1 = 64u, P_TOUCH2 = 128u;           // the cell lies on the planned cells of one / of more than one vehicle this tick
-
-__device__ __forceinline__ uint32_t pb_load(const uint32_t *probe, int c) { return __ldcg(reinterpret_cast<const uint8_t *>(probe) + c); }
-__device__ __forceinline__ uint32_t pb_or(uint32_t *probe, int c, uint32_t bits) {   // returns the byte as it was
-    const int sh = (c & 3) * 8;
-    return (atomicOr(probe + (c >> 2), bits << sh) >> sh) & 0xffu;
-}
-__device__ __forceinline__ void pb_clear(uint32_t *probe, int c, uint32_t bits) { atomicAnd(probe + (c >> 2), ~(bits << ((c & 3) * 8))); }
+// Live-list kernel: what a vehicle needs to know about the cells ahead lives in BIT PLANES over 8 x 8-cell tiles (one 64-bit word
+// per tile and plane: bit (y & 7) * 8 + (x & 7) of word (y >> 3) * tiles_x + (x >> 3)).  A straight run of five cells lies in at
+// most two tiles, so a look-ahead is two loads per plane and a mark / an occupancy change one or two atomics whatever the
+// direction of travel; the hot planes of an 8192 x 8192 city are 8 MB each and stay in L2.
+enum { PL_OCC = 0,    // occupancy_map
+       PL_STOP = 1,   // stop_map (committed)
+       PL_T1 = 2,     // the cell lies on the planned cells of a vehicle this tick ...
+       PL_T2 = 3,     // ... of more than one, or a light group staged a stop_map write on it: whoever plans to enter it must look closer
+       PL_STG = 4,    // a light group staged a stop_map write this tick (value in `stopw`)
+       PL_WANT = 5,   // a sideswipe candidate asks which vehicle stands here (this tick's phase A only)
+       N_PLANES = 6 };
 
 constexpr int OUTSIDE = -2;          // a tape cell that lies outside this shard's window (host-side translation, tsim.h)
 
@@ -37,26 +34,37 @@ struct TickArgs {
     tsim_light_tables lt;
     tsim_tick_tapes tp;
     tsim_tick_state st;
+    int debug;
     int sort_every;                           // ... every so many ticks
     int tile_sx, tile_sy, tiles_x, n_tiles;   // live-list kernel, sorted append: tile = (y >> tile_sy) * tiles_x + (x >> tile_sx); n_tiles == 0: plain append
-    // live-list kernel, light groups (tsim_tick_state.group_ws, built by tsim_tick_init): occupancy as one bit per cell in 8 x 8-cell
-    // tiles (one 64-bit word each) and, per group, its incoming lanes and its cluster as (tile, mask) pairs
-    unsigned long long *occ;
+    // live-list kernel: the bit planes (tsim_tick_state.probe), words per plane, tiles per row
+    unsigned long long *bits;
+    long long n_tw;
+    int occ_tiles_x;
+    // live-list kernel, light groups (tsim_tick_state.group_ws, built by tsim_tick_init): per group, its incoming lanes and its
+    // cluster as (tile, mask) pairs over the occupancy plane
+    const unsigned long long *occ;   // = bits (plane PL_OCC)
     const unsigned long long *gq_mask;
     const int32_t *gq_tile, *gq_cnt;
-    int occ_tiles_x, gq_base_ew, gq_base_cl;
+    int gq_base_ew, gq_base_cl;
     // ... and the cells its lights control, flattened: group -> (cell, role) with role 0 = a light of g_all, 1 = of g_ns, 2 = of g_ew
     const int32_t *gc_off, *gc_cell;
     const uint8_t *gc_role;
 };
 
-__device__ __forceinline__ void occ_word_bit(const TickArgs &a, int c, int &word, int &bit) {
+__device__ __forceinline__ void cell_wb(const TickArgs &a, int c, int &word, int &bit) {
     const int y = c / a.W, x = c - y * a.W;
     word = (y >> 3) * a.occ_tiles_x + (x >> 3);
     bit = (y & 7) * 8 + (x & 7);
 }
-__device__ __forceinline__ void occ_set(const TickArgs &a, int c) { int w, b; occ_word_bit(a, c, w, b); atomicOr(a.occ + w, 1ull << b); }
-__device__ __forceinline__ void occ_clear(const TickArgs &a, int c) { int w, b; occ_word_bit(a, c, w, b); atomicAnd(a.occ + w, ~(1ull << b)); }
+__device__ __forceinline__ unsigned long long *bit_plane(const TickArgs &a, int plane) { return a.bits + (size_t)plane * a.n_tw; }
+__device__ __forceinline__ int bit_get(const TickArgs &a, int plane, int c) {
+    int w, b;
+    cell_wb(a, c, w, b);
+    return (int)((__ldcg(bit_plane(a, plane) + w) >> b) & 1ull);
+}
+__device__ __forceinline__ void bit_set(const TickArgs &a, int plane, int c) { int w, b; cell_wb(a, c, w, b); atomicOr(bit_plane(a, plane) + w, 1ull << b); }
+__device__ __forceinline__ void bit_clear(const TickArgs &a, int plane, int c) { int w, b; cell_wb(a, c, w, b); atomicAnd(bit_plane(a, plane) + w, ~(1ull << b)); }
 // vehicles on the cells of list `kind` (0 N-S lanes, 1 W-E lanes, 2 cluster) of group g; a cell listed twice counts twice (its second
 // mention sits in an entry of its own)
 __device__ __forceinline__ int occ_count(const TickArgs &a, int kind, int base, int g) {
@@ -155,11 +163,11 @@ __device__ void group_decide(const TickArgs &a, int g) {
     if (plan == 0) return;
     const int base = (g + 1) * 4;
     if (plan == 1) {
-        for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); if (PROBE) pb_or(s.probe, c, P_STAGED); });
+        for_light_cells(lt, lt.g_all_off, lt.g_all, g, [&](int c) { atomicMax(s.stopw + c, base + 1); });
     } else {
         const bool ns_go = plan == 2;
-        for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); if (PROBE) pb_or(s.probe, c, P_STAGED); });
-        for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); if (PROBE) pb_or(s.probe, c, P_STAGED); });
+        for_light_cells(lt, ns_go ? lt.g_ns_off : lt.g_ew_off, ns_go ? lt.g_ns : lt.g_ew, g, [&](int c) { atomicMax(s.stopw + c, base + 0); });
+        for_light_cells(lt, ns_go ? lt.g_ew_off : lt.g_ns_off, ns_go ? lt.g_ew : lt.g_ns, g, [&](int c) { atomicMax(s.stopw + c, base + 3); });
     }
 }
 
@@ -173,8 +181,7 @@ __device__ void group_apply(const TickArgs &a, int g) {
         const int w = *((volatile int32_t *)(s.stopw + c));
         if ((w >> 2) == g + 1) {
             s.stopw[c] = 0;
-            if (PROBE) { pb_clear(s.probe, c, (w & 1) ? P_STAGED : (P_STOP | P_STAGED)); if (w & 1) pb_or(s.probe, c, P_STOP); }   // the map itself: tsim_tick_export
-            else s.stop_map[c] = (uint8_t)(w & 1);
+            s.stop_map[c] = (uint8_t)(w & 1);
         }
     };
     if (plan == 1) {

@@ -124,7 +124,9 @@ class GpuTraffic:
         s["scalars"] = z(16, torch.int32)
         self.live_list = (window is None and own_rows is None) if live_list is None else bool(live_list)
         if self.live_list:
-            s["probe"] = z((n + 3) // 4, torch.int32)   # one byte per cell
+            nb = C.c_longlong(0)
+            _lib.check(self.lib.tsim_tick_probe_bytes(C.byref(self.cfg), C.byref(nb)))
+            s["probe"] = z(nb.value // 8, torch.int64)   # bit planes over 8 x 8-cell tiles
             nt = C.c_int32(0)
             _lib.check(self.lib.tsim_tick_tiles(C.byref(self.cfg), C.byref(nt)))
             s["recs"] = torch.empty(max(3 * nv * 48, 16), dtype=torch.uint8, device=dev)   # two halves of the live list + the sort's staging copy
