@@ -86,5 +86,5 @@ def test_sharded_ticks_flag_a_ghost_that_differs_from_its_owner():
     s0 = sim.sims[0]
     row = sim.plan.own_hi[0] + 3 - s0.win_y0          # a halo row of shard 0 inside its verify band
     s0.occupancy_map[row, 0] = 1                       # a wall cell: nothing will ever clear it
-    with pytest.raises(_lib.TsimError, match="halo too small"):
+    with pytest.raises(_lib.TsimError, match="ghost diverged from its owner"):
         sim.step(1)

@@ -299,7 +299,8 @@ __device__ __forceinline__ unsigned long long timer_ns() { unsigned long long t;
 #define OWN_DONE(slot) do { if (tid == 0) { const unsigned long long now_ = timer_ns(); g_tick_phase_ns[slot] += now_ - t_own; t_own = now_; } } while (0)
 #define PHASE_DONE(slot) do { if (tid == 0) { const unsigned long long now_ = timer_ns(); g_tick_phase_ns[slot] += now_ - t_phase; t_phase = now_; } } while (0)
 
-__global__ void __launch_bounds__(256) tick2_kernel(TickArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) tick2_kernel(TickArgs a) {
     cg::grid_group grid = cg::this_grid();
     constexpr uint32_t FULL = 0xffffffffu;
     const tsim_tick_state &s = a.st;
@@ -919,6 +920,8 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
         a.occ_tiles_x = (cfg->width + 7) / 8;
         a.n_tw = (long long)a.occ_tiles_x * ((cfg->win_rows + 7) / 8);
         a.bits = (unsigned long long *)st->probe;
+        if (cfg->width < 2) { set_error("tick (live list): the grid must be at least 2 cells wide"); return TSIM_ERR_CONFIG; }
+        a.w_magic = ~0ull / (unsigned long long)cfg->width + 1ull;
         a.occ = a.bits + PL_OCC * a.n_tw; a.gq_mask = w.mask; a.gq_tile = w.tile; a.gq_cnt = w.cnt;
         a.gq_base_ew = (int)g_ws_seen.n_ns; a.gq_base_cl = (int)(g_ws_seen.n_ns + g_ws_seen.n_ew);
         a.gc_off = w.gc_off; a.gc_cell = w.gc_cell; a.gc_role = w.gc_role;
@@ -926,7 +929,12 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
     int dev = 0, sms = 0, per_sm = 0;
     TSIM_CUDA(cudaGetDevice(&dev));
     TSIM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick2_kernel, 256, 0));
+    int minb = 2;   // registers per thread: 2 CTAs per SM = as many as the kernel wants, 3 / 4 = capped at 85 / 64
+    if (const char *e = getenv("TSIM_TICK_MINB")) { const int v = atoi(e); if (v >= 2 && v <= 4) minb = v; }
+    const void *kern = minb == 2 ? (const void *)tick2_kernel<2> : minb == 3 ? (const void *)tick2_kernel<3> : (const void *)tick2_kernel<4>;
+    if (minb == 2) TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick2_kernel<2>, 256, 0));
+    else if (minb == 3) TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick2_kernel<3>, 256, 0));
+    else TSIM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick2_kernel<4>, 256, 0));
     if (per_sm < 1) per_sm = 1;
     // A barrier costs more the more CTAs arrive, a thread with many vehicles serialises their load chains: one CTA per SM up to
     // ~4 vehicles per thread, then more (measured: 100 k vehicles 0.081 / 0.094 / 0.088 ms per tick at 1 / 2 / 4 CTAs per SM,
@@ -970,7 +978,7 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0; lc.stream = cs; lc.attrs = attr; lc.numAttrs = n_attr;
     count_launch();
-    TSIM_CUDA(cudaLaunchKernelExC(&lc, (const void *)tick2_kernel, args));
+    TSIM_CUDA(cudaLaunchKernelExC(&lc, kern, args));
     return TSIM_OK;
 }
 

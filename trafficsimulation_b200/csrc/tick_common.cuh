@@ -39,6 +39,7 @@ struct TickArgs {
     int tile_sx, tile_sy, tiles_x, n_tiles;   // live-list kernel, sorted append: tile = (y >> tile_sy) * tiles_x + (x >> tile_sx); n_tiles == 0: plain append
     // live-list kernel: the bit planes (tsim_tick_state.probe), words per plane, tiles per row
     unsigned long long *bits;
+    unsigned long long w_magic;   // ceil(2^64 / W)
     long long n_tw;
     int occ_tiles_x;
     // live-list kernel, light groups (tsim_tick_state.group_ws, built by tsim_tick_init): per group, its incoming lanes and its
@@ -53,7 +54,7 @@ struct TickArgs {
 };
 
 __device__ __forceinline__ void cell_wb(const TickArgs &a, int c, int &word, int &bit) {
-    const int y = c / a.W, x = c - y * a.W;
+    const int y = (int)__umul64hi((unsigned long long)(unsigned)c, a.w_magic), x = c - y * a.W;   // c / W by a multiplication (exact: c * W < 2^64)
     word = (y >> 3) * a.occ_tiles_x + (x >> 3);
     bit = (y & 7) * 8 + (x & 7);
 }
