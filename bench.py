@@ -232,9 +232,12 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
             "ms_per_tick": ms / ticks, "vehicle_updates": updates,
             "fixed_point_iterations_per_tick": (c1["fixed_point_iterations"] - c0["fixed_point_iterations"]) / ticks,
             "e2e": {"value": e2e, "unit": "agent-updates/s", "note": "one launch per tick + host read of the counters"},
-            "roofline": {"bound": "hbm", "alg_bytes_per_update": 84, "achieved": round(ups * 84 / 1e9, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(ups * 84 / 1e9 / peak, 5), "peak_source": peak_src,
-                         "note": "a tick costs its grid-wide barriers (3 + one per claim sweep + 2), not its bytes (DESIGN.md §4)"},
+            "roofline": {"bound": "hbm", "alg_bytes_per_update": 84, "alg_bytes_per_group_update": 104,
+                         "achieved": round((updates * 84 + ticks * sim.n_groups * 104) / (ms * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round((updates * 84 + ticks * sim.n_groups * 104) / (ms * 1e-3) / 1e9 / peak, 5), "peak_source": peak_src,
+                         "note": "SURVEY.md 8(d) compulsory bytes: 84 per agent-update + 104 per light-group update.  What bounds the tick is not bytes: "
+                                 "every access is a 32-byte-sector gather or an L2 atomic (~5 atomics and ~25 sectors per vehicle and tick), and each of "
+                                 "its phases is a chain of 3-5 dependent round trips between grid-wide barriers (DESIGN.md §5)"},
             "cpu_baseline": cpu, "parity": parity}
 
 
@@ -471,6 +474,14 @@ def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
             "frac_of_measured_peak": round(size * size * sum(PASS_BYTES.values()) / (ms * 1e-3) / 1e9 / measured_peaks()[0], 4)}
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (the JSON line on stdout stays alone)"""
+    print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -512,10 +523,12 @@ def ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    log(f"inputs ready ({W}x{H}, {world} GPU)")
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     city._check_flag("warmup")
+    log("warm-up done")
     # one city = one CUDA graph launch on a single device (every launch is static); shards interleave NCCL collectives and stay eager
     eager_step, graph, graph_launches = step, None, None
     if world == 1 and not args.no_graph:
@@ -608,6 +621,7 @@ def ours(args):
     t_clk1 = time.monotonic()
     clocks.__exit__(None, None, None)
 
+    log("timed steps and per-pass timing done")
     # ---- end to end through the public API with host buffers: tapes + band tables H2D, own rows of planes + maps D2H
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_tz, h_te, h_tc = pin(tz), pin(te), d_tc.cpu().pin_memory()
@@ -657,6 +671,7 @@ def ours(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = W * H * args.steps / float(t_e2e.item())
+    log("end-to-end steps done")
     n_blocks = int(sh._total.item())
     n_lights = torch.tensor([int(((city._link_tensors["light_cell"][: int(city.flags[3].item())] >= lo) &
                                   (city._link_tensors["light_cell"][: int(city.flags[3].item())] < lo + cells)).sum().item())],
@@ -694,6 +709,7 @@ def ours(args):
                     "frac": round(pipeline_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": cells * total_alg_per_cell}
         cpu_val, cpu_s = (cpu_arm(CPU_SAMPLE, 2, 1) if world == 1 else (None, None))
+        log("cpu baseline done")
         line = {
             "metric": "grid cells/sec, full layout generation (all passes)", "value": value, "unit": "cells/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -717,12 +733,16 @@ def ours(args):
         }
         if world == 1:
             line["config1_4096"] = small_city_leg(dev) if size != 4096 else None
+            log("4096 leg done")
             line["vehicle_step"] = vehicle_bench(dev)
+            log("tick leg (100k) done")
             line["vehicle_step_1M"] = vehicle_bench(dev, n_ticks=60, size=8192, n_vehicles=1000000, cpu_ticks=0, route_len=100, e2e_ticks=20)
+            log("tick leg (1M) done")
             try:
                 line["route_planning"] = route_planning_leg(dev)
             except Exception as e:   # noqa: BLE001 -- an extra leg never costs the headline line
                 line["route_planning"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            log("route planning leg done")
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                                     "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
     if world > 1 and not args.no_parity:   # is it the right city?  (after all timing; collective)

@@ -1,4 +1,4 @@
-// k_carve.cu -- _carve_subblock_roads (city_model.py:563-737): one warp per Nothing blob.
+// k_carve.cu -- _carve_subblock_roads (city_model.py:563-737): one warp per batch of 32 Nothing blobs.
 //
 // The reference visits blobs in raster discovery order and carves each with the decisions it draws
 // (the carve tape, one row per blob).  Blobs are disjoint and a carve only touches its own blob, the
@@ -72,74 +72,143 @@ __device__ void extend(const tsim_cfg &c, const LiveGrid &g, const uint32_t *row
     }
 }
 
-// One WARP per blob.  The cells of the two legs are laid by the lanes in parallel, in two steps that commute with the
-// reference's cell-by-cell order: (1) every leg cell becomes road, (2) every Nothing neighbour of a leg cell becomes
-// Sidewalk (a leg cell that the serial order would first edge as Sidewalk and then overwrite as road ends up road either
-// way).  The two extensions march on different lines outside the blob and run on two lanes; the pivot's 8 neighbours on 8.
+// One warp per BATCH of 32 blobs (lane L holds the decisions of blob L of the batch).  Carving one blob is a chain of a dozen
+// dependent memory round trips (tape row, blob box, leg cells, their neighbours, the marches, the pivot's neighbours) for a few
+// dozen cells; a warp that takes blobs one after the other spends its time waiting.  So every step is done for all 32 blobs at
+// once, over the FLAT list of their leg cells (or pivot neighbours), two items per lane in flight:
+//   (1) every leg cell becomes road, (2) every Nothing neighbour of a leg cell becomes Sidewalk -- two steps that commute with
+//   the reference's cell-by-cell order (a leg cell that the serial order would first edge as Sidewalk and then overwrite as road
+//   ends up road either way); (3) the pivot's arrow; (4) the two extensions of a blob march on different lines outside the blob:
+//   lane L marches those of its own blob; (5) the pivot's 8 neighbours.
+// Blobs are disjoint (header), so doing a step for 32 of them together orders nothing that was ordered before.
+struct CarveJob {   // one blob's taped decisions, checked
+    int px, py, hd, vd, nh, nv, h_arrow, v_arrow, inb_h, minx, miny, maxx, maxy;
+};
+
+// f(owner lane, index among the owner's items, valid) for the flat list of n_mine items per lane; all lanes call f together
+template <class F>
+__device__ __forceinline__ void warp_flat(int n_mine, int lane, F f) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    int incl = n_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    for (int i0 = 0; i0 < total; i0 += 64) {
+        int own[2], idx[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int i = i0 + u * 32 + lane;
+            int lo = 0;   // first lane with incl > i
+#pragma unroll
+            for (int step = 16; step; step >>= 1) { const int v = __shfl_sync(FULL, incl, min(lo + step - 1, 31)); if (v <= i) lo += step; }
+            lo = min(lo, 31);
+            own[u] = lo; idx[u] = i - __shfl_sync(FULL, incl - n_mine, lo); ok[u] = i < total;
+        }
+        f(own, idx, ok);
+    }
+}
+
 __global__ void __launch_bounds__(256) carve_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, const uint32_t *__restrict__ rowt,
                                                     const uint32_t *__restrict__ colt, const int32_t *__restrict__ blobs,
                                                     const int32_t *__restrict__ n_blobs, int cap_blobs, const int32_t *__restrict__ id_base,
                                                     const int32_t *__restrict__ tape, int n_tape, int32_t *err) {
+    constexpr uint32_t FULL = 0xffffffffu;
     const int nb = min(*n_blobs, cap_blobs);
     const int base = id_base ? *id_base : 0;
     const int y0 = c.win_y0;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int b = warp; b < nb; b += nwarps) {
-        const int gid = b + base;            // 0-based global blob id = tape row
-        if (gid < 0) continue;               // cut by the window's lower edge: owned (and carved) by the shard below
-        if (gid >= n_tape) { if (lane == 0) *err = 1; continue; }
-        const int32_t *row = tape + (size_t)gid * 8;
-        if (!row[1]) continue;
-        const int32_t *bl = blobs + (size_t)b * TSIM_BLOB_STRIDE;
-        const int minx = bl[0], miny = bl[1] - y0, maxx = bl[2], maxy = bl[3] - y0;   // window-local rows from here on
-        // a blob cut by a window edge that is not a grid edge lies in the halo: the shard that owns its rows sees it whole and carves it
-        if ((miny == 0 && y0 > 0) || (maxy == c.win_rows - 1 && y0 + c.win_rows < c.height)) continue;
-        const int px = row[2], py = row[3] - y0, hd = row[4], vd = row[5], inb_h = row[6];
-        const int ms = c.min_subblock_spacing;
-        // the tape must hold a decision the reference could have drawn (:659-675)
-        if (!((hd == DW || hd == DE) && (vd == DN || vd == DS)) || px < minx + ms || px > maxx - ms || py < miny + ms || py > maxy - ms ||
-            (long long)(maxx - minx + 1) * (maxy - miny + 1) != bl[4] /* non-rectangular blob: carve footprints may interact */) {
-            if (lane == 0) *err = 2;
-            continue;
+    const LiveGrid g{T, D, A, c.width, c.win_rows};
+    const uint32_t *rowl = rowt + y0;   // line table of local row ly = rowl[ly]
+    const int sub_t = T_R1 - 1 + c.subblock_road_type;
+    const int ms = c.min_subblock_spacing;
+    for (int b0 = warp * 32; b0 < nb; b0 += nwarps * 32) {
+        const int b = b0 + lane;
+        CarveJob j{};
+        bool valid = false;
+        if (b < nb) {
+            const int gid = b + base;            // 0-based global blob id = tape row; < 0: cut by the window's lower edge, owned (and carved) by the shard below
+            if (gid >= n_tape) *err = 1;
+            else if (gid >= 0) {
+                const int4 r0 = *reinterpret_cast<const int4 *>(tape + (size_t)gid * 8), r1 = *reinterpret_cast<const int4 *>(tape + (size_t)gid * 8 + 4);
+                const int32_t *bl = blobs + (size_t)b * TSIM_BLOB_STRIDE;
+                const int b0x = bl[0], b1y = bl[1], b2x = bl[2], b3y = bl[3], area = bl[4];
+                if (r0.y) {   // carved
+                    j.minx = b0x; j.miny = b1y - y0; j.maxx = b2x; j.maxy = b3y - y0;   // window-local rows from here on
+                    // a blob cut by a window edge that is not a grid edge lies in the halo: the shard that owns its rows sees it whole and carves it
+                    if (!((j.miny == 0 && y0 > 0) || (j.maxy == c.win_rows - 1 && y0 + c.win_rows < c.height))) {
+                        j.px = r0.z; j.py = r0.w - y0; j.hd = r1.x; j.vd = r1.y; j.inb_h = r1.z;
+                        // the tape must hold a decision the reference could have drawn (:659-675)
+                        if (!((j.hd == DW || j.hd == DE) && (j.vd == DN || j.vd == DS)) || j.px < j.minx + ms || j.px > j.maxx - ms || j.py < j.miny + ms ||
+                            j.py > j.maxy - ms ||
+                            (long long)(j.maxx - j.minx + 1) * (j.maxy - j.miny + 1) != area /* non-rectangular blob: carve footprints may interact */) {
+                            *err = 2;
+                        } else {
+                            valid = true;
+                            j.h_arrow = j.inb_h ? opp_of(j.hd) : j.hd;   // :683-696
+                            j.v_arrow = j.inb_h ? j.vd : opp_of(j.vd);   // :707-708
+                            // leg cells: horizontal leg from the pivot's neighbour to the blob edge, vertical leg from the pivot to the blob edge
+                            j.nh = j.hd == DW ? j.px - j.minx : j.maxx - j.px;
+                            j.nv = j.vd == DS ? j.py - j.miny + 1 : j.maxy - j.py + 1;
+                        }
+                    }
+                }
+            }
         }
-        const LiveGrid g{T, D, A, c.width, c.win_rows};
-        const uint32_t *rowl = rowt + y0;   // line table of local row ly = rowl[ly]
-        const int sub_t = T_R1 - 1 + c.subblock_road_type;
-        const int h_arrow = inb_h ? opp_of(hd) : hd;   // :683-696
-        const int v_arrow = inb_h ? vd : opp_of(vd);   // :707-708
-        // leg cells: horizontal leg from the pivot's neighbour to the blob edge, vertical leg from the pivot to the blob edge
-        const int nh = hd == DW ? px - minx : maxx - px, nv = vd == DS ? py - miny + 1 : maxy - py + 1;
-        auto leg_cell = [&](int i, int &x, int &y, int &arrow) {
-            if (i < nh) { x = hd == DW ? px - 1 - i : px + 1 + i; y = py; arrow = h_arrow; }
-            else { const int j = i - nh; x = px; y = vd == DS ? py - j : py + j; arrow = v_arrow; }
+        if (!__ballot_sync(FULL, valid)) continue;
+        // leg cell `i` of the blob lane `o` holds
+        auto leg_cell = [&](int o, int i, int &x, int &y, int &arrow) {
+            const int px = __shfl_sync(FULL, j.px, o), py = __shfl_sync(FULL, j.py, o), hd = __shfl_sync(FULL, j.hd, o), vd = __shfl_sync(FULL, j.vd, o);
+            const int nh = __shfl_sync(FULL, j.nh, o), ha = __shfl_sync(FULL, j.h_arrow, o), va = __shfl_sync(FULL, j.v_arrow, o);
+            if (i < nh) { x = hd == DW ? px - 1 - i : px + 1 + i; y = py; arrow = ha; }
+            else { const int q = i - nh; x = px; y = vd == DS ? py - q : py + q; arrow = va; }
         };
-        for (int i = lane; i < nh + nv; i += 32) {   // lay_r4_cell (:588-601), road part
-            int x, y, arrow;
-            leg_cell(i, x, y, arrow);
-            if (g.has(x, y) && !is_road_like(g.t(x, y))) { g.place(x, y, sub_t); g.D[g.at(x, y)] = (uint16_t)dl_one(arrow); }
+        const int n_leg = valid ? j.nh + j.nv : 0;
+        warp_flat(n_leg, lane, [&](const int (&own)[2], const int (&idx)[2], const bool (&ok)[2]) {   // lay_r4_cell (:588-601), road part
+            int x[2], y[2], arrow[2], t[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) { leg_cell(own[u], idx[u], x[u], y[u], arrow[u]); t[u] = (ok[u] && g.has(x[u], y[u])) ? g.t(x[u], y[u]) : -1; }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (t[u] >= 0 && !is_road_like(t[u])) { g.place(x[u], y[u], sub_t); g.D[g.at(x[u], y[u])] = (uint16_t)dl_one(arrow[u]); }
+        });
+        __syncwarp();
+        warp_flat(n_leg, lane, [&](const int (&own)[2], const int (&idx)[2], const bool (&ok)[2]) {   // lay_r4_cell, sidewalk edging
+            int x[2], y[2], arrow, t[2][4];
+            const int ox[4] = {1, -1, 0, 0}, oy[4] = {0, 0, 1, -1};
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                leg_cell(own[u], idx[u], x[u], y[u], arrow);
+                const bool in = ok[u] && g.has(x[u], y[u]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) t[u][k] = in ? g.t(x[u] + ox[k], y[u] + oy[k]) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (t[u][k] == T_NOTHING) g.place(x[u] + ox[k], y[u] + oy[k], T_SIDEWALK);
+        });
+        __syncwarp();
+        if (valid) {
+            g.D[g.at(j.px, j.py)] = (uint16_t)dl_one(j.inb_h ? j.v_arrow : j.h_arrow);   // pivot shows the outbound arrow only (:713-715)
+            const int hx_end = j.hd == DW ? j.minx : j.maxx, vy_end = j.vd == DS ? j.miny : j.maxy;
+            extend(c, g, rowl, colt, sub_t, hx_end + dx_of(j.hd), j.py, j.hd, j.h_arrow, err);
+            extend(c, g, rowl, colt, sub_t, j.px, vy_end + dy_of(j.vd), j.vd, j.v_arrow, err);
         }
         __syncwarp();
-        for (int i = lane; i < nh + nv; i += 32) {   // lay_r4_cell, sidewalk edging
-            int x, y, arrow;
-            leg_cell(i, x, y, arrow);
-            if (!g.has(x, y)) continue;
-            if (g.t(x + 1, y) == T_NOTHING) g.place(x + 1, y, T_SIDEWALK);
-            if (g.t(x - 1, y) == T_NOTHING) g.place(x - 1, y, T_SIDEWALK);
-            if (g.t(x, y + 1) == T_NOTHING) g.place(x, y + 1, T_SIDEWALK);
-            if (g.t(x, y - 1) == T_NOTHING) g.place(x, y - 1, T_SIDEWALK);
-        }
-        __syncwarp();
-        if (lane == 0) g.D[g.at(px, py)] = (uint16_t)dl_one(inb_h ? v_arrow : h_arrow);   // pivot shows the outbound arrow only (:713-715)
-        const int hx_end = hd == DW ? minx : maxx, vy_end = vd == DS ? miny : maxy;
-        if (lane == 0) extend(c, g, rowl, colt, sub_t, hx_end + dx_of(hd), py, hd, h_arrow, err);
-        if (lane == 1) extend(c, g, rowl, colt, sub_t, px, vy_end + dy_of(vd), vd, v_arrow, err);
-        __syncwarp();
-        if (lane < 8) {   // :731-737
-            const int k = lane < 4 ? lane : lane + 1, dx = k % 3 - 1, dy = k / 3 - 1;
-            const int t = g.t(px + dx, py + dy);
-            if (t >= 0 && !is_road_like(t) && t != T_WALL) g.place(px + dx, py + dy, T_SIDEWALK);
-        }
+        warp_flat(valid ? 8 : 0, lane, [&](const int (&own)[2], const int (&idx)[2], const bool (&ok)[2]) {   // :731-737
+            int x[2], y[2], t[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int px = __shfl_sync(FULL, j.px, own[u]), py = __shfl_sync(FULL, j.py, own[u]);
+                const int k = idx[u] < 4 ? idx[u] : idx[u] + 1;
+                x[u] = px + k % 3 - 1; y[u] = py + k / 3 - 1;
+                t[u] = ok[u] ? g.t(x[u], y[u]) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) if (t[u] >= 0 && !is_road_like(t[u]) && t[u] != T_WALL) g.place(x[u], y[u], T_SIDEWALK);
+        });
         __syncwarp();
     }
 }
@@ -158,7 +227,7 @@ extern "C" tsim_status tsim_layout_carve(const tsim_cfg *cfg, const tsim_planes 
         return TSIM_ERR_CONFIG;
     }
     if (n_tape == 0) return TSIM_OK;
-    const int grid = div_up(blobs->cap, 8) < 148 * 8 ? div_up(blobs->cap, 8) : 148 * 8;   // one warp per blob
+    const int grid = div_up(blobs->cap, 8 * 32) < 148 * 8 ? div_up(blobs->cap, 8 * 32) : 148 * 8;   // one warp per 32 blobs
     carve_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*cfg, p->cell_type, p->dirs, p->aux, lines->row, lines->col, blobs->table,
                                                          blobs->count, blobs->cap, blobs->id_base, tape, n_tape, err_flag);
     TSIM_LAUNCH_CHECK();

@@ -182,7 +182,7 @@ __device__ __forceinline__ void decide2(const TickArgs &a, VRec &r, VPlan &pl, i
     pl.k = (uint8_t)ms;   // what an uncontested vehicle does: none of its cells is a stop cell (max_steps ends before the first one)
     // Every cell this vehicle could end on is marked: once = nobody else plans to come here, twice = somebody does.  Only vehicles
     // with a twice-marked cell take part in the claim fixed point (the marks come off again in the move phase).  One atomic per tile.
-    if (!(a.debug & 4)) {
+    {
         u64 mk[MAX_SPEED], was[MAX_SPEED];
 #pragma unroll
         for (int q = 0; q < MAX_SPEED; q++) {   // the cells this side of max_steps
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(256, MINB) tick2_kernel(TickArgs a) {
                 const VPlan pl = plans[i];
                 int pos = r.pos;
                 const int target = r.target;
-                if (pl.m && !(a.debug & 1)) {   // nobody reads the marks of this tick any more: they come off, one atomic per tile
+                if (pl.m) {   // nobody reads the marks of this tick any more: they come off, one atomic per tile
                     PathBits pb;
                     path_bits(a, pl.cell, pl.m, pb);
                     u64 *t1 = bit_plane(a, PL_T1), *t2 = bit_plane(a, PL_T2);
@@ -903,7 +903,6 @@ tsim_status tick2_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const ts
                       int32_t algo, cudaStream_t cs) {
     TickArgs a{cfg->width, cfg->win_rows, n_ticks, algo, 0, cfg->win_rows * cfg->width, *lt, *tp, *st};
     a.sort_every = 16;
-    if (const char *e = getenv("TSIM_TICK_DEBUG")) a.debug = atoi(e);
     if (st->sort_keys && st->tile_ws) {   // sorted append: worth its extra pass and barrier once the fleet no longer fits the caches
         bool on = tp->n_vehicles >= 200000;
         if (const char *e = getenv("TSIM_TICK_SORT")) on = *e != '0';

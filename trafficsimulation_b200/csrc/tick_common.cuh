@@ -34,7 +34,6 @@ struct TickArgs {
     tsim_light_tables lt;
     tsim_tick_tapes tp;
     tsim_tick_state st;
-    int debug;
     int sort_every;                           // ... every so many ticks
     int tile_sx, tile_sy, tiles_x, n_tiles;   // live-list kernel, sorted append: tile = (y >> tile_sy) * tiles_x + (x >> tile_sx); n_tiles == 0: plain append
     // live-list kernel: the bit planes (tsim_tick_state.probe), words per plane, tiles per row
