@@ -163,6 +163,14 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()) if any(r[2].replace(".", "", 1).isdigit() for r in rows) else None}
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (the JSON line on stdout stays alone)"""
+    print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, route_len=400, e2e_ticks=50, parity_check=True):
     """Second headline metric: agent-updates/s of the vehicle CA tick (BASELINE.json configs[3], in the
     simultaneous-occupancy form SURVEY.md §8d defines: 100k vehicles live at once on a 2048^2 city)."""
@@ -176,13 +184,17 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
     city = GpuCityLayout(width=size, height=size, device=dev)
     city.set_bands(hb, vb)
     city.generate(tz, None, te)
+    log(f"  tick leg {size}: city generated")
     tabs = light_tables_from_layout(city)
     planes = city.planes_host()
+    log(f"  tick leg {size}: light tables built")
     tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], n_vehicles, n_ticks, route_len=route_len, spawn_ticks=1)
     nv = len(tp["origin"])
+    log(f"  tick leg {size}: tapes for {nv} vehicles")
     sim = GpuTraffic(size, size, tabs, tp, n_ticks, device=dev)
     sim.step(5)           # warm-up ticks (also spawns everybody)
     torch.cuda.synchronize()
+    log(f"  tick leg {size}: device state ready, 5 warm-up ticks done")
     c0 = sim.counters()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -195,6 +207,7 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
     ticks = c1["tick"] - c0["tick"]
     peak, peak_src = measured_peaks()
     ups = updates / (ms * 1e-3)
+    log(f"  tick leg {size}: timed ticks done ({ms / max(ticks, 1):.4f} ms/tick)")
     # end to end: one launch per tick with a host read of the tick counters after every tick
     sim2 = GpuTraffic(size, size, tabs, tp, n_ticks, device=dev)
     sim2.step(5)
@@ -205,6 +218,8 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
         sim2.step(1, check=True)
     t1 = time.perf_counter()
     e2e = (sim2.counters()["vehicle_updates"] - e0) / (t1 - t0)
+    del sim2
+    log(f"  tick leg {size}: end-to-end ticks done")
     # CPU port on the same tapes: timed on `cpu_ticks` ticks, then run on to the tick the device is at, where the WHOLE state --
     # every vehicle's position / speed / stuck counter / flags, the three maps, the light groups -- must be identical
     cpu, parity = None, None
@@ -221,8 +236,10 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
             cpu_s = time.perf_counter() - t0
             cpu = {"value": upd_cpu / cpu_s, "unit": "agent-updates/s", "cores": 1, "kind": "port",
                    "sample": f"oracle/vehicle_oracle.c, same tapes, {cpu_ticks} ticks, {live0} live vehicles"}
+        log(f"  tick leg {size}: oracle at tick {ora.sim.tick}")
         if parity_check:
             ora.run(n_ticks - ora.sim.tick)
+            log(f"  tick leg {size}: oracle at tick {ora.sim.tick}, comparing")
             got, want = sim.state_host(), ora.state()
             parity = {"parity_checked": bool(all(np.array_equal(got[k], want[k]) for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"))),
                       "against": f"oracle/vehicle_oracle.c after {n_ticks} ticks: positions, speeds, stuck counters, flags of all {nv} vehicles, occupancy / stop / stuck maps, light-group state"}
@@ -393,6 +410,41 @@ def guarded(fn, rank, limit_s, on_timeout):
         timer.cancel()
 
 
+LEGS = {
+    "tick100k": lambda dev: vehicle_bench(dev),
+    "tick1m": lambda dev: vehicle_bench(dev, n_ticks=60, size=8192, n_vehicles=1000000, cpu_ticks=0, route_len=100, e2e_ticks=20),
+    "routes": lambda dev: route_planning_leg(dev),
+}
+
+
+def run_leg(name, limit_s):
+    """One of LEGS in a child process (`bench.py --leg NAME` prints its JSON object on stdout, progress on stderr)."""
+    import subprocess
+    t0 = time.time()
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--leg", name], stdout=subprocess.PIPE, timeout=limit_s)
+    except subprocess.TimeoutExpired:
+        return {"error": f"leg {name}: no result within {limit_s} s (killed)"}
+    lines = p.stdout.decode(errors="replace").strip().splitlines()
+    if p.returncode != 0 or not lines:
+        return {"error": f"leg {name}: exit code {p.returncode}"}
+    try:
+        out = json.loads(lines[-1])
+    except ValueError:
+        return {"error": f"leg {name}: unreadable output"}
+    out["leg_wall_s"] = round(time.time() - t0, 1)
+    return out
+
+
+def leg_main(name):
+    import torch
+    try:
+        out = LEGS[name](torch.device("cuda", 0))
+    except Exception as e:   # noqa: BLE001 -- reported in the line
+        out = {"error": f"{type(e).__name__}: {e}"[:400]}
+    print(json.dumps(out))
+
+
 def route_planning_leg(dev, n_queries=16384):
     """reference-exact routes/s of the batched planner on the reference's default city (the maps of the committed
     fixture tests/golden/astar_default12345.npz), the C oracle on a sample of the same queries beside it (same code as
@@ -472,14 +524,6 @@ def small_city_leg(dev, size=4096, steps=10, warmup=3, seed=4096):
             "value": size * size / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms, "steps": steps,
             "cuda_graph": graph is not None, "launches_per_step": launches, "ms_per_step_without_graph": ms_eager,
             "frac_of_measured_peak": round(size * size * sum(PASS_BYTES.values()) / (ms * 1e-3) / 1e9 / measured_peaks()[0], 4)}
-
-
-_T0 = time.time()
-
-
-def log(msg):
-    """progress on stderr (the JSON line on stdout stays alone)"""
-    print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def ours(args):
@@ -734,15 +778,11 @@ def ours(args):
         if world == 1:
             line["config1_4096"] = small_city_leg(dev) if size != 4096 else None
             log("4096 leg done")
-            line["vehicle_step"] = vehicle_bench(dev)
-            log("tick leg (100k) done")
-            line["vehicle_step_1M"] = vehicle_bench(dev, n_ticks=60, size=8192, n_vehicles=1000000, cpu_ticks=0, route_len=100, e2e_ticks=20)
-            log("tick leg (1M) done")
-            try:
-                line["route_planning"] = route_planning_leg(dev)
-            except Exception as e:   # noqa: BLE001 -- an extra leg never costs the headline line
-                line["route_planning"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-            log("route planning leg done")
+            # the legs beside the headline run in processes of their own with a time limit each: a leg that fails, hangs or
+            # crawls on a slow host costs its own entry, never the line (the parent keeps its device memory meanwhile)
+            for key, leg, limit_s in (("vehicle_step", "tick100k", 150), ("vehicle_step_1M", "tick1m", 240), ("route_planning", "routes", 90)):
+                line[key] = run_leg(leg, limit_s)
+                log(f"leg {leg} done" + (f": {line[key]['error']}" if isinstance(line[key], dict) and "error" in line[key] else ""))
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
                                     "sample": f"C oracle (oracle/city_oracle.c), same pipeline on a {CPU_SAMPLE}x{CPU_SAMPLE} city, {cpu_s:.2f} s/step"}
     if world > 1 and not args.no_parity:   # is it the right city?  (after all timing; collective)
@@ -799,7 +839,10 @@ def main():
     ap.add_argument("--shard-rows", type=int, default=8192, help="N > 1: rows per GPU of the sharded city")
     ap.add_argument("--no-graph", action="store_true", help="N = 1: time eager launches instead of one CUDA graph per city")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the shifted-cut / single-GPU digest comparison")
+    ap.add_argument("--leg", choices=sorted(LEGS), help="run one of the legs beside the headline alone and print its JSON object")
     args = ap.parse_args()
+    if args.leg:
+        return leg_main(args.leg)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

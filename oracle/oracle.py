@@ -186,7 +186,8 @@ class VSim(C.Structure):
                     "stuck_ticks", "stranded",
                     "tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
                     "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl",
-                    "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "collision", "veh_at")])
+                    "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "collision", "veh_at",
+                    "g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout", "g_nsp", "g_ewp")])
 
 
 def csr(lists, dtype=np.int32):
@@ -213,6 +214,9 @@ def light_tables_from_reference(lights, ctrl_pairs, groups):
         t[key + "_off"], t[key] = csr([[lidx[int(c)] for c in g[src]] for g in groups])
     for key, src in (("g_nsin", "ns_in"), ("g_ewin", "ew_in"), ("g_cl", "cluster")):
         t[key + "_off"], t[key] = csr([g[src] for g in groups])
+    for key, src in (("g_nsout", "ns_out"), ("g_ewout", "ew_out")):   # newer harness runs / fixtures only (pressure controller)
+        if all(src in g for g in groups):
+            t[key + "_off"], t[key] = csr([g[src] for g in groups])
     t["n_lights"], t["n_groups"] = len(lights), len(groups)
     return t
 
@@ -251,6 +255,21 @@ class OracleTicks:
                   "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl"):
             a[k] = np.ascontiguousarray(tables[k], np.int32)
         ng = tables["n_groups"]
+        for k in ("g_nsout", "g_ewout"):
+            if k in tables:
+                a[k + "_off"], a[k] = np.ascontiguousarray(tables[k + "_off"], np.int32), np.ascontiguousarray(tables[k], np.int32)
+            elif algo == 2:
+                raise ValueError("PRESSURE_CONTROL needs the g_nsout / g_ewout lane tables")
+            else:
+                a[k + "_off"], a[k] = np.zeros(ng + 1, np.int32), np.zeros(0, np.int32)
+        a["g_nsp"] = np.zeros(ng, np.int32); a["g_ewp"] = np.zeros(ng, np.int32)
+        if algo == 2:
+            # run_pressure_control hands compute_max_pressure `to_int32(occ_map)` (intersection_light_group.py:443-453): the [H, W] map
+            # reshaped to (-1, 2).  Numba does not check bounds, so `occupancy_map[y, x]` reads flat element 2 * y + x of the map
+            # (always inside the buffer) -- the controller counts the vehicles on THOSE cells.  Restated as it runs.
+            for k in ("g_nsin", "g_ewin", "g_nsout", "g_ewout"):
+                c = a[k].astype(np.int64)
+                a[k] = np.ascontiguousarray(2 * (c // W) + c % W, np.int32)
         a["g_cur"] = np.full(ng, -1, np.int32); a["g_pend"] = np.zeros(ng, np.int32)   # apply_phase(0) in __init__ (:115-116)
         for k in ("g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer"):
             a[k] = np.zeros(ng, np.int32)
@@ -275,7 +294,8 @@ class OracleTicks:
                     vflags=np.where(alive, flags, 0).astype(np.uint8),
                     occ=np.flatnonzero(a["occ"]).astype(np.int32), stop=np.flatnonzero(a["stop"]).astype(np.int32),
                     stuckmap=np.flatnonzero(a["stuckmap"]).astype(np.int32),
-                    groups=np.stack([a["g_cur"], a["g_pend"], a["g_qt"], a["g_gap"], a["g_last"]], 1))
+                    groups=np.stack([a["g_cur"], a["g_pend"], a["g_qt"], a["g_gap"], a["g_last"]], 1),
+                    groups_ext=np.stack([a["g_ft_timer"], a["g_ft_phase"], a["g_nsp"], a["g_ewp"]], 1))
 
 
 # ------------------------------------------------------------------------------------------------

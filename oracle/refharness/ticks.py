@@ -46,7 +46,7 @@ def light_group_tables(model):
     """Canonical light-group tables of the reference model (for parity of the construction).
 
     Returns (groups, order) where groups[i] is a dict of sorted int arrays (cell indices y*W+x):
-      cluster, lights, ns_lights, ew_lights, ns_in, ew_in (multisets)
+      cluster, lights, ns_lights, ew_lights, ns_in, ew_in, ns_out, ew_out (multisets)
     in canonical order, and `order` lists the reference group objects in that order.
     """
     W = model.width
@@ -62,13 +62,17 @@ def light_group_tables(model):
             ew_lights=np.array(sorted(idx(t.position) for t in pairs["W-E"]), np.int32),
             ns_in=np.array(sorted(int(y) * W + int(x) for x, y in np.asarray(g.ns_in_coords).reshape(-1, 2)), np.int32),
             ew_in=np.array(sorted(int(y) * W + int(x) for x, y in np.asarray(g.ew_in_coords).reshape(-1, 2)), np.int32),
+            ns_out=np.array(sorted(int(y) * W + int(x) for x, y in np.asarray(g.ns_out_coords).reshape(-1, 2)), np.int32),
+            ew_out=np.array(sorted(int(y) * W + int(x) for x, y in np.asarray(g.ew_out_coords).reshape(-1, 2)), np.int32),
         )))
     groups.sort(key=lambda t: t[0])
     return [t[2] for t in groups], [t[1] for t in groups]
 
 
-def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=None, layout_kwargs=None, tape_seed=None, sideswipe_p=0.0):
+def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=None, layout_kwargs=None, tape_seed=None, sideswipe_p=0.0,
+              algo=None):
     """Build the reference city with `random.seed(seed)` and run `n_ticks` ticks under tapes.
+    `algo`: Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM for the run (config.py:341; None = as shipped, QUEUE_ACTUATED).
 
     Returns a dict with the layout (as harness.run_layout), the tapes and the per-tick states.
     """
@@ -79,6 +83,9 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
     from Simulation.agents.city_structure_entities.city_block import CityBlock
 
     saved = (Defaults.TOTAL_SERVICE_VEHICLES_FOOD, Defaults.TOTAL_SERVICE_VEHICLES_WASTE, Defaults.RAIN_ENABLED)
+    saved_algo = Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM
+    if algo is not None:
+        Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM = algo
     Defaults.TOTAL_SERVICE_VEHICLES_FOOD = 0
     Defaults.TOTAL_SERVICE_VEHICLES_WASTE = 0
     lay = H.run_layout(seed, enable_traffic=True, enable_rain=False, keep_model=True, **(layout_kwargs or {}))
@@ -184,7 +191,7 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
     base = np.zeros((n_ticks, n_attempts), np.int8)
     stuck = np.zeros((n_ticks, n_attempts), np.int16)
     flags = np.zeros((n_ticks, n_attempts), np.uint8)   # bit0 is_stuck, bit1 malfunction, bits 2-4 direction+1, bit5 collision
-    occ_cells, stop_cells, stuckmap_cells, group_phase = [], [], [], []
+    occ_cells, stop_cells, stuckmap_cells, group_phase, group_ext = [], [], [], [], []
     try:
         with H._in_tmpdir():
             for t in range(n_ticks):
@@ -204,11 +211,13 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
                 group_phase.append(np.array([[-1 if g.current_phase is None else g.current_phase,
                                               -1 if g.pending_phase is None else g.pending_phase,
                                               g.queue_timer, g.gap_timer, g.last_arrival] for g in group_order], np.int32))
+                group_ext.append(np.array([[g.fixed_time_timer, g._ft_phase, g.ns_pressure, g.ew_pressure] for g in group_order], np.int32))
     finally:
         VehicleAgent.step_decide = orig_decide
         VehicleAgent._compute_path = orig_compute
         cm.multiprocessing.cpu_count = old_cpu
         Defaults.TOTAL_SERVICE_VEHICLES_FOOD, Defaults.TOTAL_SERVICE_VEHICLES_WASTE, Defaults.RAIN_ENABLED = saved
+        Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM = saved_algo
         Defaults.ENABLE_TRAFFIC = False
 
     def ragged(lst):
@@ -228,6 +237,7 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
         ev_off=ev_off, ev_cells=ev_cells,
         pos=pos, base_speed=base, stuck_ticks=stuck, vflags=flags,
         groups=groups, group_state=np.stack(group_phase) if group_phase and len(group_order) else np.zeros((n_ticks, 0, 5), np.int32),
+        group_ext=np.stack(group_ext) if group_ext and len(group_order) else np.zeros((n_ticks, 0, 4), np.int32),   # fixed-time timer / phase, pressures
     )
     for name, lst in (("occ", occ_cells), ("stop", stop_cells), ("stuckmap", stuckmap_cells)):
         out[name + "_off"], out[name + "_cells"] = ragged(lst)

@@ -10,7 +10,8 @@
  *     _execute_movement :733-753, _move_to :521-532, tick_stuck :687-693, on_target_reached :755-775
  *   CityModel.move_vehicle / remove_vehicle / place_vehicle   city_model.py:1897-1963
  *   IntersectionLightGroup.step          agents/city_structure_entities/intersection_light_group.py:396-423
- *     run_queue_actuated :463-494, run_fixed_time :427-441, apply_phase :386-393,
+ *     run_queue_actuated :463-494, run_fixed_time :427-441, run_pressure_control :448-461 (compute_max_pressure
+ *     utilities/numba_utilities.py:74-85), apply_phase :386-393,
  *     _execute_phase_change :348-384, is_intersection_occupied :285-291
  *   CellAgent.set_light_stop / set_light_go   agents/city_structure_entities/cell.py:241-251
  *
@@ -25,7 +26,7 @@
 
 typedef struct {
     int32_t W, H, n_vehicles, n_groups, n_lights;
-    int32_t algo;                 /* 0 QUEUE_ACTUATED, 1 FIXED_TIME (config.py:341) */
+    int32_t algo;                 /* 0 QUEUE_ACTUATED, 1 FIXED_TIME, 2 PRESSURE_CONTROL (config.py:341) */
     int32_t rain_enabled;         /* Defaults.RAIN_ENABLED */
     int32_t tick;                 /* next tick to run */
     /* maps [H*W] */
@@ -49,6 +50,9 @@ typedef struct {
     int32_t *g_cur, *g_pend, *g_qt, *g_gap, *g_last, *g_ft_phase, *g_ft_timer;
     /* sideswipes: is_in_collision per vehicle, vehicle standing on a cell (-1: none) */
     int8_t *collision; int32_t *veh_at;
+    /* pressure controller: lane cells on the far side of their light (ns_out_coords / ew_out_coords :141-154), last pressures */
+    const int32_t *g_nsout_off, *g_nsout, *g_ewout_off, *g_ewout;
+    int32_t *g_nsp, *g_ewp;
 } vsim;
 
 enum { MIN_GREEN = 5, MAX_GREEN = 30, GAP = 3, GREEN_DURATION = 20, AWARENESS = 10,
@@ -75,6 +79,15 @@ static void group_step(vsim *s, int g) {
                 if (next != s->g_cur[g] && next != s->g_pend[g]) s->g_pend[g] = next; /* apply_phase :386-393 */
                 s->g_qt[g] = 0;
             }
+        } else if (s->algo == 2) { /* run_pressure_control :448-461: every tick without a pending phase, phase of the larger pressure */
+            int ns_p = 0, ew_p = 0;
+            for (int k = s->g_nsin_off[g]; k < s->g_nsin_off[g + 1]; k++) ns_p += s->occ[s->g_nsin[k]];
+            for (int k = s->g_nsout_off[g]; k < s->g_nsout_off[g + 1]; k++) ns_p -= s->occ[s->g_nsout[k]];
+            for (int k = s->g_ewin_off[g]; k < s->g_ewin_off[g + 1]; k++) ew_p += s->occ[s->g_ewin[k]];
+            for (int k = s->g_ewout_off[g]; k < s->g_ewout_off[g + 1]; k++) ew_p -= s->occ[s->g_ewout[k]];
+            s->g_nsp[g] = ns_p; s->g_ewp[g] = ew_p;
+            int ph = ns_p > ew_p ? 0 : 1;
+            if (ph != s->g_cur[g] && ph != s->g_pend[g]) s->g_pend[g] = ph;
         } else { /* run_fixed_time :427-441 */
             s->g_ft_timer[g]++;
             if (s->g_ft_timer[g] == 1) {
@@ -106,6 +119,8 @@ static void remove_vehicle(vsim *s, int v) { /* city_model.py:1920-1941 */
     if (s->veh_at[s->pos[v]] == v) s->veh_at[s->pos[v]] = -1;
     s->alive[v] = 0;
 }
+
+static const int32_t *g_ev_of;   /* vehicle -> index of its last route event of the running tick (built per tick by oracle_ticks_run) */
 
 static void set_collision(vsim *s, int v) { /* _set_collision vehicle_base.py:534-541 */
     s->collision[v] = 1; s->malfunction[v] = 0; s->stranded[v] = COLLISION_TICKS; s->base_speed[v] = 0; s->cur_speed[v] = 0;
@@ -154,8 +169,10 @@ static int decide(vsim *s, int v, int t) {
     int sp = s->base_speed[v];
     if (s->rain_enabled && s->rain[s->pos[v]] == 1) { sp -= RAIN_REDUCTION; if (sp < 1) sp = 1; }
     s->cur_speed[v] = (int8_t)sp;
-    for (int e = s->ev_first[t]; e < s->ev_first[t + 1]; e++) /* replayed re-plan (:506-517, :454-504) */
-        if (s->ev_vehicle[e] == v) { s->path_off[v] = (int32_t)s->ev_off[e]; s->path_len[v] = (int32_t)(s->ev_off[e + 1] - s->ev_off[e]); }
+    if (g_ev_of[v] >= 0) { /* replayed re-plan (:506-517, :454-504): the tick's LAST event of this vehicle */
+        const int e = g_ev_of[v];
+        s->path_off[v] = (int32_t)s->ev_off[e]; s->path_len[v] = (int32_t)(s->ev_off[e + 1] - s->ev_off[e]);
+    }
     /* _scan_ahead_for_obstacles :422-452 */
     int idx_stop = -1, idx_veh = -1, look = s->path_len[v] < AWARENESS ? s->path_len[v] : AWARENESS;
     for (int i = 0; i < look; i++) {
@@ -218,11 +235,15 @@ static int cmp_rank(const void *a, const void *b) {
 /* runs `n` ticks; returns 0, or -(tick+1) on a tape-contract violation */
 int oracle_ticks_run(vsim *s, int n) {
     int32_t *order = malloc((size_t)(s->n_vehicles + 1) * sizeof(int32_t));
+    int32_t *ev_of = malloc((size_t)(s->n_vehicles + 1) * sizeof(int32_t));   /* vehicle -> its last route event of the tick, -1: none */
+    for (int v = 0; v < s->n_vehicles; v++) ev_of[v] = -1;
+    g_ev_of = ev_of;
     for (int it = 0; it < n; it++) {
         const int t = s->tick;
         int na = 0;
+        for (int e = s->ev_first[t]; e < s->ev_first[t + 1]; e++) ev_of[s->ev_vehicle[e]] = e;
         for (int v = 0; v < s->n_vehicles; v++) /* phase A: run_parallel_decide, one worker, list order */
-            if (s->alive[v]) { if (decide(s, v, t) < 0) { free(order); return -(t + 1); } order[na++] = v; }
+            if (s->alive[v]) { if (decide(s, v, t) < 0) { free(order); free(ev_of); return -(t + 1); } order[na++] = v; }
         for (int g = 0; g < s->n_groups; g++) group_step(s, g); /* phase B: light groups first */
         g_rank_row = s->rank + (size_t)t * s->n_vehicles;
         qsort(order, (size_t)na, sizeof(int32_t), cmp_rank);
@@ -234,11 +255,14 @@ int oracle_ticks_run(vsim *s, int n) {
             s->occ[s->origin[v]] = 1; s->stuckmap[s->origin[v]] = 0; /* place_vehicle :1897-1908 */
             s->veh_at[s->origin[v]] = v;
             s->path_off[v] = 0; s->path_len[v] = 0;
-            for (int e = s->ev_first[t]; e < s->ev_first[t + 1]; e++)
-                if (s->ev_vehicle[e] == v) { s->path_off[v] = (int32_t)s->ev_off[e]; s->path_len[v] = (int32_t)(s->ev_off[e + 1] - s->ev_off[e]); }
+            if (g_ev_of[v] >= 0) {
+                const int e = g_ev_of[v];
+                s->path_off[v] = (int32_t)s->ev_off[e]; s->path_len[v] = (int32_t)(s->ev_off[e + 1] - s->ev_off[e]);
+            }
         }
+        for (int e = s->ev_first[t]; e < s->ev_first[t + 1]; e++) ev_of[s->ev_vehicle[e]] = -1;
         s->tick++;
     }
-    free(order);
+    free(order); free(ev_of);
     return 0;
 }

@@ -363,6 +363,67 @@ __global__ void __launch_bounds__(256) zones_table_kernel(const int32_t *__restr
     }
 }
 
+// one group of 8 cells of a row (inside one word): label plane + zone fill
+template <bool FILL>
+__device__ __forceinline__ void label_group8(const Runs &r, int x, long long y, long long i0, int base, bool prod, int n_cg, int cap_blobs,
+                                             int32_t *__restrict__ L, uint8_t *__restrict__ T, const uint8_t *__restrict__ fill) {
+    const int wp = r.wp;
+    const int wx = x >> 6, sh = x & 63;
+    const size_t wi = (size_t)y * wp + wx;
+    const uint32_t bits = (uint32_t)(r.M[wi] >> sh) & 0xffu;
+    int4 lo = make_int4(0, 0, 0, 0), hi = lo;
+    if (bits && prod) {   // product plane: id = row run * column runs + column run (rows / columns of a set cell always have one)
+        const int row0 = r.pr.row_gap[y] * n_cg;
+        const int4 c0 = *reinterpret_cast<const int4 *>(r.pr.col_gap + x), c1 = *reinterpret_cast<const int4 *>(r.pr.col_gap + x + 4);
+        const int cg[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        int ids[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (bits == 0xffu && cg[0] == cg[7]) {
+            const int cid = row0 + cg[0], id = cid + base;
+            lo = hi = make_int4(id, id, id, id);
+            if (FILL && cid < cap_blobs) {
+                const uint32_t f = fill[cid];
+                if (f != 0xffu) { const uint32_t f4 = f * 0x01010101u; *reinterpret_cast<uint2 *>(T + i0) = make_uint2(f4, f4); }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (!((bits >> k) & 1u)) continue;
+                const int cid = row0 + cg[k];
+                ids[k] = cid + base;
+                if (FILL && cid < cap_blobs) { const uint8_t f = fill[cid]; if (f != 0xff) T[i0 + k] = f; }
+            }
+            lo = make_int4(ids[0], ids[1], ids[2], ids[3]); hi = make_int4(ids[4], ids[5], ids[6], ids[7]);
+        }
+    } else if (bits) {
+        const u64 st = run_starts(r.M, wi, wx);
+        const int sp = r.sprefix[wi];
+        const uint32_t inner = (uint32_t)(st >> sh) & 0xfeu;   // run starts strictly inside the group
+        if (bits == 0xffu && !inner) {   // the whole group lies in one run: one look-up, splat
+            const int run = sp + __popcll(st & ((2ull << sh) - 1ull)) - 1;
+            const int cid = run < r.cap ? r.len[run] : 0, id = cid + base;
+            lo = hi = make_int4(id, id, id, id);
+            if (FILL && cid < cap_blobs) {
+                const uint32_t f = fill[cid];
+                if (f != 0xffu) { const uint32_t f4 = f * 0x01010101u; *reinterpret_cast<uint2 *>(T + i0) = make_uint2(f4, f4); }
+            }
+        } else {
+            int ids[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int last_run = -1, last_id = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (!((bits >> k) & 1u)) continue;
+                const int run = sp + __popcll(st & ((2ull << (sh + k)) - 1ull)) - 1;
+                if (run != last_run) { last_run = run; last_id = run < r.cap ? r.len[run] : 0; }
+                ids[k] = last_id + base;
+                if (FILL && last_id < cap_blobs) { const uint8_t f = fill[last_id]; if (f != 0xff) T[i0 + k] = f; }
+            }
+            lo = make_int4(ids[0], ids[1], ids[2], ids[3]); hi = make_int4(ids[4], ids[5], ids[6], ids[7]);
+        }
+    }
+    *reinterpret_cast<int4 *>(L + i0) = lo;
+    *reinterpret_cast<int4 *>(L + i0 + 4) = hi;
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Runs r, const int32_t *__restrict__ id_base, int cap_blobs,
                                                          int32_t *__restrict__ L, uint8_t *__restrict__ T, const uint8_t *__restrict__ fill) {
@@ -375,61 +436,8 @@ __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Run
     const int wp = r.wp;
     const bool prod = r.pr.scal[PS_FLAG] != 0;
     const int n_cg = r.pr.scal[PS_NCG];
-    if ((W & 7) == 0) {   // 8 cells of one row, inside one word
-        const int wx = x >> 6, sh = x & 63;
-        const size_t wi = (size_t)y * wp + wx;
-        const uint32_t bits = (uint32_t)(r.M[wi] >> sh) & 0xffu;
-        int4 lo = make_int4(0, 0, 0, 0), hi = lo;
-        if (bits && prod) {   // product plane: id = row run * column runs + column run (rows / columns of a set cell always have one)
-            const int row0 = r.pr.row_gap[y] * n_cg;
-            const int4 c0 = *reinterpret_cast<const int4 *>(r.pr.col_gap + x), c1 = *reinterpret_cast<const int4 *>(r.pr.col_gap + x + 4);
-            const int cg[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            int ids[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (bits == 0xffu && cg[0] == cg[7]) {
-                const int cid = row0 + cg[0], id = cid + base;
-                lo = hi = make_int4(id, id, id, id);
-                if (FILL && cid < cap_blobs) {
-                    const uint32_t f = fill[cid];
-                    if (f != 0xffu) { const uint32_t f4 = f * 0x01010101u; *reinterpret_cast<uint2 *>(T + i0) = make_uint2(f4, f4); }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if (!((bits >> k) & 1u)) continue;
-                    const int cid = row0 + cg[k];
-                    ids[k] = cid + base;
-                    if (FILL && cid < cap_blobs) { const uint8_t f = fill[cid]; if (f != 0xff) T[i0 + k] = f; }
-                }
-                lo = make_int4(ids[0], ids[1], ids[2], ids[3]); hi = make_int4(ids[4], ids[5], ids[6], ids[7]);
-            }
-        } else if (bits) {
-            const u64 st = run_starts(r.M, wi, wx);
-            const int sp = r.sprefix[wi];
-            const uint32_t inner = (uint32_t)(st >> sh) & 0xfeu;   // run starts strictly inside the group
-            if (bits == 0xffu && !inner) {   // the whole group lies in one run: one look-up, splat
-                const int run = sp + __popcll(st & ((2ull << sh) - 1ull)) - 1;
-                const int cid = run < r.cap ? r.len[run] : 0, id = cid + base;
-                lo = hi = make_int4(id, id, id, id);
-                if (FILL && cid < cap_blobs) {
-                    const uint32_t f = fill[cid];
-                    if (f != 0xffu) { const uint32_t f4 = f * 0x01010101u; *reinterpret_cast<uint2 *>(T + i0) = make_uint2(f4, f4); }
-                }
-            } else {
-                int ids[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                int last_run = -1, last_id = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if (!((bits >> k) & 1u)) continue;
-                    const int run = sp + __popcll(st & ((2ull << (sh + k)) - 1ull)) - 1;
-                    if (run != last_run) { last_run = run; last_id = run < r.cap ? r.len[run] : 0; }
-                    ids[k] = last_id + base;
-                    if (FILL && last_id < cap_blobs) { const uint8_t f = fill[last_id]; if (f != 0xff) T[i0 + k] = f; }
-                }
-                lo = make_int4(ids[0], ids[1], ids[2], ids[3]); hi = make_int4(ids[4], ids[5], ids[6], ids[7]);
-            }
-        }
-        *reinterpret_cast<int4 *>(L + i0) = lo;
-        *reinterpret_cast<int4 *>(L + i0 + 4) = hi;
+    if ((W & 7) == 0) {
+        label_group8<FILL>(r, x, y, i0, base, prod, n_cg, cap_blobs, L, T, fill);
     } else {
         for (int k = 0; k < 8 && x + k < W; k++) {
             const long long i = i0 + k;
@@ -444,6 +452,104 @@ __global__ void __launch_bounds__(256) ccl_labels_kernel(int W, long long n, Run
             }
             L[i] = id;
         }
+    }
+}
+
+// 4 bits -> 4 bytes of 0xff / 0x00
+__device__ __forceinline__ uint32_t spread4(uint32_t b) {
+    const uint32_t x = (b | (b << 7) | (b << 14) | (b << 21)) & 0x01010101u;
+    return x * 0xffu;
+}
+
+// The same plane, G rows per thread (W % 8 == 0).  The label write is a chain of dependent look-ups per group (word -> run -> component ->
+// fill type) ending in 32 bytes of stores: with one group per thread the stores in flight per SM bound the kernel at ~2.9 TB/s of the
+// ~6 TB/s a write stream reaches.  Here the G chains of a thread advance together, level by level, and every group's type bytes leave as
+// ONE blended 8-byte store instead of up to eight byte stores.
+template <bool FILL, int G>
+__global__ void __launch_bounds__(256) ccl_labels_rows_kernel(int W, int LH, Runs r, const int32_t *__restrict__ id_base, int cap_blobs,
+                                                              int32_t *__restrict__ L, uint8_t *__restrict__ T, const uint8_t *__restrict__ fill) {
+    const int yb = (int)(blockIdx.y + blockIdx.z * 65535u) * G;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (x >= W || yb >= LH) return;
+    const int base = (id_base ? *id_base : 0) + 1;
+    const bool prod = r.pr.scal[PS_FLAG] != 0;
+    if (prod) {
+        const int n_cg = r.pr.scal[PS_NCG];
+        for (int j = 0; j < G && yb + j < LH; j++) label_group8<FILL>(r, x, yb + j, (long long)(yb + j) * W + x, base, true, n_cg, cap_blobs, L, T, fill);
+        return;
+    }
+    const int wp = r.wp, wx = x >> 6, sh = x & 63, cap = r.cap;
+    const u64 *__restrict__ M = r.M;
+    const int32_t *__restrict__ sprefix = r.sprefix;
+    const int32_t *__restrict__ comp = r.len;   // component of every run by now
+    // level 1: the words
+    u64 m[G], pv[G];
+    int sp[G];
+    uint2 t8[G];
+    bool ok[G];
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+        ok[j] = yb + j < LH;
+        const size_t wi = (size_t)(yb + j) * wp + wx;
+        m[j] = ok[j] ? M[wi] : 0ull;
+        pv[j] = ok[j] && wx > 0 ? M[wi - 1] >> 63 : 0ull;
+        sp[j] = ok[j] ? sprefix[wi] : 0;
+        if (FILL) t8[j] = ok[j] ? *reinterpret_cast<const uint2 *>(T + (size_t)(yb + j) * W + x) : make_uint2(0u, 0u);
+    }
+    // level 2: the component of the first run of every group
+    uint32_t bits[G], seg[G];
+    u64 st[G];
+    int id0[G];
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+        bits[j] = (uint32_t)(m[j] >> sh) & 0xffu;
+        st[j] = m[j] & ~((m[j] << 1) | pv[j]);
+        seg[j] = 0; id0[j] = 0;
+        if (bits[j]) {
+            const int first = __ffs(bits[j]) - 1;
+            const uint32_t gap = ~(bits[j] >> first);             // the run goes on until the first clear bit (bits has 8 bits: there is one)
+            seg[j] = ((1u << (__ffs(gap) - 1)) - 1u) << first;
+            const int run = sp[j] + __popcll(st[j] & ((2ull << (sh + first)) - 1ull)) - 1;
+            id0[j] = run < cap ? comp[run] : 0;
+        }
+    }
+    // level 3: its fill type
+    uint32_t f0[G];
+#pragma unroll
+    for (int j = 0; j < G; j++) f0[j] = (FILL && seg[j] && id0[j] < cap_blobs) ? (uint32_t)fill[id0[j]] : 0xffu;
+    // level 4: ids, blended types, the rare further runs of a group, stores
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+        if (!ok[j]) continue;
+        int ids[8];
+        uint32_t tlo = t8[j].x, thi = t8[j].y;
+        bool tch = false;
+        auto put = [&](uint32_t sg, int id, uint32_t f) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) if ((sg >> k) & 1u) ids[k] = id + base;
+            if (FILL && f != 0xffu) {
+                const uint32_t f4 = f * 0x01010101u, ml = spread4(sg & 15u), mh = spread4(sg >> 4);
+                tlo = (tlo & ~ml) | (f4 & ml); thi = (thi & ~mh) | (f4 & mh);
+                tch = true;
+            }
+        };
+#pragma unroll
+        for (int k = 0; k < 8; k++) ids[k] = 0;
+        if (seg[j]) put(seg[j], id0[j], f0[j]);
+        uint32_t rem = bits[j] & ~seg[j];
+        while (rem) {
+            const int first = __ffs(rem) - 1;
+            const uint32_t gap = ~(rem >> first);
+            const uint32_t sg = ((1u << (__ffs(gap) - 1)) - 1u) << first;
+            const int run = sp[j] + __popcll(st[j] & ((2ull << (sh + first)) - 1ull)) - 1;
+            const int id = run < cap ? comp[run] : 0;
+            put(sg, id, (FILL && id < cap_blobs) ? (uint32_t)fill[id] : 0xffu);
+            rem &= ~sg;
+        }
+        const size_t i0 = (size_t)(yb + j) * W + x;
+        *reinterpret_cast<int4 *>(L + i0) = make_int4(ids[0], ids[1], ids[2], ids[3]);
+        *reinterpret_cast<int4 *>(L + i0 + 4) = make_int4(ids[4], ids[5], ids[6], ids[7]);
+        if (FILL && tch) *reinterpret_cast<uint2 *>(T + i0) = make_uint2(tlo, thi);
     }
 }
 
@@ -567,6 +673,25 @@ tsim_status label_type(const tsim_cfg *cfg, const uint8_t *T, int target, const 
     return TSIM_OK;
 }
 
+// label plane launcher: G rows per thread when the rows are made of whole 8-cell groups (TSIM_LABEL_ROWS=1: one row per thread, the r1 kernel)
+template <bool FILL>
+static void launch_labels(int W, int LH, long long n, const Runs &r, const int32_t *id_base, int cap_blobs, int32_t *L, uint8_t *T, const uint8_t *fill,
+                          cudaStream_t cs) {
+    static int rows = -1;
+    if (rows < 0) { const char *e = getenv("TSIM_LABEL_ROWS"); rows = e ? atoi(e) : 4; }
+    if ((W & 7) == 0 && rows == 4) {
+        const int yb = div_up(LH, 4);
+        ccl_labels_rows_kernel<FILL, 4><<<dim3(div_up(div_up(W, 8), 256), yb < 65535 ? yb : 65535, div_up(yb, 65535)), 256, 0, cs>>>(W, LH, r, id_base, cap_blobs,
+                                                                                                                                  L, T, fill);
+    } else if ((W & 7) == 0 && rows == 2) {
+        const int yb = div_up(LH, 2);
+        ccl_labels_rows_kernel<FILL, 2><<<dim3(div_up(div_up(W, 8), 256), yb < 65535 ? yb : 65535, div_up(yb, 65535)), 256, 0, cs>>>(W, LH, r, id_base, cap_blobs,
+                                                                                                                                  L, T, fill);
+    } else {
+        ccl_labels_kernel<FILL><<<dim3(div_up(div_up(W, 8), 256), LH < 65535 ? LH : 65535, div_up(LH, 65535)), 256, 0, cs>>>(W, n, r, id_base, cap_blobs, L, T, fill);
+    }
+}
+
 }  // namespace tsim
 
 using namespace tsim;
@@ -595,8 +720,7 @@ extern "C" tsim_status tsim_layout_zones(const tsim_cfg *cfg, const tsim_planes 
     zones_table_kernel<<<list_grid(blobs->cap), 256, 0, cs>>>(blobs->table, blobs->count, blobs->cap, blobs->id_base, zone_by_block, n_tape, fill, err_flag);
     TSIM_LAUNCH_CHECK();
     // Nothing cells carry no arrows and no aux bits (frame pass / place_cell), so only the type changes
-    ccl_labels_kernel<true><<<dim3(div_up(div_up(win.W, 8), 256), win.LH < 65535 ? win.LH : 65535, div_up(win.LH, 65535)), 256, 0, cs>>>(
-        win.W, n, r, blobs->id_base, blobs->cap, p->block_id, p->cell_type, fill);
+    launch_labels<true>(win.W, win.LH, n, r, blobs->id_base, blobs->cap, p->block_id, p->cell_type, fill, cs);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
@@ -613,8 +737,7 @@ extern "C" tsim_status tsim_label_mask(const tsim_cfg *cfg, const uint8_t *mask,
     if ((st = runs_layout(cfg, workspace, ws_bytes, r, scan_tmp, fill, blobs->cap)) != TSIM_OK) return st;
     const Win win(*cfg);
     const long long n = win.cells();
-    ccl_labels_kernel<false><<<dim3(div_up(div_up(win.W, 8), 256), win.LH < 65535 ? win.LH : 65535, div_up(win.LH, 65535)), 256, 0, cs>>>(
-        win.W, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr);
+    launch_labels<false>(win.W, win.LH, n, r, blobs->id_base, blobs->cap, labels, nullptr, nullptr, cs);
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }

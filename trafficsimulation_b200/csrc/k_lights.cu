@@ -98,14 +98,15 @@ __global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const ui
         // SWAR: type sets as byte-range tests on 4 cells at once, arrow bits from 2 cells per dirs word
         mI = strip_range_mask(tw, TypeRanges{T_INTER - 1, T_INTER + 1, 0, 0});
         mR = strip_range_mask(tw, TypeRanges{T_R1 - 1, T_HWY_OUT + 1, T_BE - 1, T_BE + 1}) & ~mI;   // ROAD_LIKE_TYPES_WITHOUT_INTERSECTIONS (config.py:69)
-        uint32_t nz = 0;   // cells with at least one arrow
+        // the arrow mask is the low nibble of every cell's dirs word: low bytes of 4 cells -> one word (PRMT), then one multiplication
+        // gathers bit d of the four bytes (the kernel is issue-bound: this is half the instructions of a shift-and-mask per dirs word)
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t w = dw[k];
-            auto two = [&](int d) { const uint32_t v = (w >> d) & 0x00010001u; return ((v | (v >> 15)) & 3u) << (2 * k); };
-            mN |= two(DN); mE |= two(DE); mS |= two(DS); mW |= two(DW);
-            nz |= ((uint32_t)((w & 0xffffu) != 0u) | ((uint32_t)((w >> 16) != 0u) << 1)) << (2 * k);
+        for (int j = 0; j < 4; j++) {
+            const uint32_t lb = __byte_perm(dw[2 * j], dw[2 * j + 1], 0x6420);
+            auto four = [&](int d) { return ((((lb >> d) & 0x01010101u) * 0x01020408u) >> 24) << (4 * j); };
+            mN |= four(DN); mE |= four(DE); mS |= four(DS); mW |= four(DW);
         }
+        const uint32_t nz = mN | mE | mS | mW;   // cells with at least one arrow (a dirs word is 0 or carries a non-empty mask: dl_append)
         uint32_t cand = mI & nz;   // Intersection cells that still have an arrow: pivot candidates
         if (cand) {
             p_all = (int)base + __ffs(cand) - 1;
