@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TSIM_ABI_VERSION 3
+#define TSIM_ABI_VERSION 4
 
 /* cell_type codes = index into Defaults.ZONES (Simulation/config.py:74-95) */
 enum tsim_cell_type {
@@ -273,7 +273,7 @@ tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint8_t *is_roa
 /* ------------------------------------------------------------------------------------------------
  * Tick: CityModel.step (city_model.py:1831-1860) = phase A VehicleAgent.step_decide for every active
  * vehicle (vehicle_base.py:616-663), then phase B in activation order: IntersectionLightGroup.step
- * (intersection_light_group.py:396-423, QUEUE_ACTUATED :463-494 / FIXED_TIME :427-441, phase commit
+ * (intersection_light_group.py:396-423, QUEUE_ACTUATED :463-494 / FIXED_TIME :427-441 / PRESSURE_CONTROL :448-461, phase commit
  * :348-384, stop_map writes cell.py:241-251), VehicleAgent.step (vehicle_base.py:666-685: movement
  * :733-753 via CityModel.move_vehicle city_model.py:1945-1963, tick_stuck :687-693, arrival :755-775),
  * and the tape-driven spawner (place_vehicle city_model.py:1897-1908).
@@ -288,6 +288,12 @@ typedef struct tsim_light_tables {   /* all device pointers; CSR offsets have n+
     const int32_t *g_nsin_off, *g_nsin;        /* group -> ns_in_coords cells (multiset)                     */
     const int32_t *g_ewin_off, *g_ewin;        /* group -> ew_in_coords cells (multiset)                     */
     const int32_t *g_cl_off, *g_cl;            /* group -> intersection cluster cells                        */
+    /* PRESSURE_CONTROL only (NULL otherwise): the lane cells on the far side of their light, ns_out_coords / ew_out_coords
+       (intersection_light_group.py:141-154).  NOTE for that controller all four lane lists hold the cells the reference
+       actually reads: run_pressure_control (:448-461) indexes the occupancy map reshaped to (-1, 2) (`to_int32`, :443-446),
+       i.e. flat element 2 * y + x instead of W * y + x -- the host tables carry that index (light_groups.pressure_cells).  */
+    const int32_t *g_nsout_off, *g_nsout;
+    const int32_t *g_ewout_off, *g_ewout;
 } tsim_light_tables;
 
 typedef struct tsim_tick_tapes {     /* all device pointers */
@@ -363,7 +369,8 @@ tsim_status tsim_tick_probe_bytes(const tsim_cfg *cfg, long long *bytes);
 /* bytes of tsim_tick_state.group_ws for these light tables (reads three table entries back: synchronises) */
 tsim_status tsim_tick_group_ws_bytes(const tsim_cfg *cfg, const tsim_light_tables *lt, long long *bytes);
 
-/* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME */
+/* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME, 2 PRESSURE_CONTROL (needs the
+   g_nsout / g_ewout tables; not on row-band shards: the cells that controller reads lie outside any window, see above) */
 tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                           const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
 

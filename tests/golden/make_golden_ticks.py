@@ -27,6 +27,11 @@ CASES = {
                       layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
     # sideswipe draws that fire (vehicle_base.py:567-605; stored as a second bit plane beside the malfunction tape)
     "s21_sideswipe": dict(seed=21, n_ticks=140, spawns_per_tick=12, malfunction_p=0.002, sideswipe_p=0.35),
+    # the other light controllers (Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM, intersection_light_group.py:396-461)
+    "s31_fixed_time": dict(seed=31, n_ticks=100, spawns_per_tick=8, malfunction_p=0.002, algo="FIXED_TIME"),
+    "s9_pressure": dict(seed=9, n_ticks=120, spawns_per_tick=8, malfunction_p=0.002, algo="PRESSURE_CONTROL"),
+    "s14_pressure_fwd": dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01, algo="PRESSURE_CONTROL",
+                             layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True, forward_traffic_light_range=True)),
 }
 
 
@@ -78,8 +83,10 @@ def main():
             arrays["sideswipe"] = np.packbits((r["malfunction"] >> 1) & 1, axis=1)
         for k in ("occ", "stop", "stuckmap"):
             arrays[k + "_off"], arrays[k + "_cells"] = r[k + "_off"], r[k + "_cells"]
-        for f in ("cluster", "lights", "ns_lights", "ew_lights", "ns_in", "ew_in"):
+        for f in ("cluster", "lights", "ns_lights", "ew_lights", "ns_in", "ew_in") + (("ns_out", "ew_out") if case.get("algo") else ()):
             arrays["g_" + f + "_off"], arrays["g_" + f] = csr([g[f] for g in r["groups"]])
+        if case.get("algo"):   # fixed-time timer / phase, pressures (older fixtures stay byte-identical without them)
+            arrays["group_ext"] = r["group_ext"].astype(np.int16)
         path = os.path.join(HERE, f"ticks_{name}.npz")
         np.savez_compressed(path, **arrays)
         print(name, os.path.getsize(path) // 1024, "KiB", "spawned", int(r["spawned"].sum()), "events", len(r["ev_tick"]))

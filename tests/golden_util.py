@@ -60,8 +60,9 @@ def load_ticks(path):
     ng = len(d["g_cluster_off"]) - 1
     for g in range(ng):
         groups.append({f: d["g_" + f][d["g_" + f + "_off"][g]:d["g_" + f + "_off"][g + 1]]
-                       for f in ("cluster", "lights", "ns_lights", "ew_lights", "ns_in", "ew_in")})
+                       for f in ("cluster", "lights", "ns_lights", "ew_lights", "ns_in", "ew_in", "ns_out", "ew_out") if "g_" + f in d})
     d["groups"] = groups
+    d["algo"] = d["meta"]["case"].get("algo") or "QUEUE_ACTUATED"
     d["group_state"] = d["group_state"].astype(np.int32)
     return d
 

@@ -12,10 +12,14 @@ from golden_util import tick_fixtures, load_ticks, compare_tick
 def test_tick_oracle_reproduces_golden(path):
     r = load_ticks(path)
     tables = O.light_tables_from_reference(r["links_lights"], r["links_ctrl"], r["groups"])
-    sim = O.OracleTicks(r["W"], r["H"], tables, r, r["n_ticks"], rain_enabled=r["meta"]["rain_enabled"])
+    algo = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2}[r["algo"]]
+    sim = O.OracleTicks(r["W"], r["H"], tables, r, r["n_ticks"], algo=algo, rain_enabled=r["meta"]["rain_enabled"])
     for t in range(r["n_ticks"]):
         sim.run(1)
-        compare_tick(t, sim.state(), r)
+        st = sim.state()
+        compare_tick(t, st, r)
+        if "group_ext" in r:   # fixed-time timer / phase, pressures of every group
+            assert np.array_equal(st["groups_ext"], r["group_ext"][t]), (t, "group_ext")
     assert (r["pos"] >= 0).sum() > 1000
 
 

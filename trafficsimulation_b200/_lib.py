@@ -61,7 +61,7 @@ class LightLinks(C.Structure):
 class LightTables(C.Structure):
     _fields_ = [("n_groups", C.c_int32), ("n_lights", C.c_int32)] + [(n, C.c_void_p) for n in (
         "tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
-        "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl")]
+        "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl", "g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout")]
 
 
 class TickTapes(C.Structure):

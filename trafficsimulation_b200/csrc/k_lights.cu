@@ -34,6 +34,7 @@
 //      light cells only (sparse), never as a full-plane sweep.
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <cstring>
 #include "scan.cuh"
 #include "bitplane.cuh"
 
@@ -66,6 +67,7 @@ struct LightsCtx {
 };
 
 // ---------------------------------------------------------------- 1. bit-planes from T and D
+template <bool MUL>
 __global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const uint8_t *__restrict__ T, const uint16_t *__restrict__ D, Bits bp,
                                                           long long mid, int32_t *piv /* [0] first >= mid, [1] first */) {
     // blockIdx.y = row, blockIdx.x * 256 + thread = 16-cell strip of the row (a quad of lanes = one word).  (As one flat index
@@ -98,15 +100,26 @@ __global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const ui
         // SWAR: type sets as byte-range tests on 4 cells at once, arrow bits from 2 cells per dirs word
         mI = strip_range_mask(tw, TypeRanges{T_INTER - 1, T_INTER + 1, 0, 0});
         mR = strip_range_mask(tw, TypeRanges{T_R1 - 1, T_HWY_OUT + 1, T_BE - 1, T_BE + 1}) & ~mI;   // ROAD_LIKE_TYPES_WITHOUT_INTERSECTIONS (config.py:69)
-        // the arrow mask is the low nibble of every cell's dirs word: low bytes of 4 cells -> one word (PRMT), then one multiplication
-        // gathers bit d of the four bytes (the kernel is issue-bound: this is half the instructions of a shift-and-mask per dirs word)
+        uint32_t nz = 0;   // cells with at least one arrow
+        if (MUL) {
+            // the arrow mask is the low nibble of every cell's dirs word: low bytes of 4 cells -> one word (PRMT), then one multiplication
+            // gathers bit d of the four bytes (632 -> 504 SASS instructions; TSIM_LIGHTS_BITS=mul, see launch site)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t lb = __byte_perm(dw[2 * j], dw[2 * j + 1], 0x6420);
-            auto four = [&](int d) { return ((((lb >> d) & 0x01010101u) * 0x01020408u) >> 24) << (4 * j); };
-            mN |= four(DN); mE |= four(DE); mS |= four(DS); mW |= four(DW);
+            for (int j = 0; j < 4; j++) {
+                const uint32_t lb = __byte_perm(dw[2 * j], dw[2 * j + 1], 0x6420);
+                auto four = [&](int d) { return ((((lb >> d) & 0x01010101u) * 0x01020408u) >> 24) << (4 * j); };
+                mN |= four(DN); mE |= four(DE); mS |= four(DS); mW |= four(DW);
+            }
+            nz = mN | mE | mS | mW;   // a dirs word is 0 or carries a non-empty mask (dl_append)
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t w = dw[k];
+                auto two = [&](int d) { const uint32_t v = (w >> d) & 0x00010001u; return ((v | (v >> 15)) & 3u) << (2 * k); };
+                mN |= two(DN); mE |= two(DE); mS |= two(DS); mW |= two(DW);
+                nz |= ((uint32_t)((w & 0xffffu) != 0u) | ((uint32_t)((w >> 16) != 0u) << 1)) << (2 * k);
+            }
         }
-        const uint32_t nz = mN | mE | mS | mW;   // cells with at least one arrow (a dirs word is 0 or carries a non-empty mask: dl_append)
         uint32_t cand = mI & nz;   // Intersection cells that still have an arrow: pivot candidates
         if (cand) {
             p_all = (int)base + __ffs(cand) - 1;
@@ -1147,7 +1160,12 @@ extern "C" tsim_status tsim_lights_prepare(const tsim_cfg *cfg, const tsim_plane
     TSIM_CUDA(cudaMemsetAsync(L.scal, 0, 64 * 4, cs));
     init_pivot_kernel<<<1, 1, 0, cs>>>(L.scal);
     TSIM_LAUNCH_CHECK();
-    lights_bits_kernel<<<dim3(div_up(L.wp * 4, 256), L.H < 65535 ? L.H : 65535, div_up(L.H, 65535)), 256, 0, cs>>>(L.W, L.H, p->cell_type, p->dirs, L.bp,
+    static int bits_mul = -1;   // arrow-bit extraction of lights_bits_kernel: 0 shift-and-mask per dirs word, 1 byte gather + multiplication
+    if (bits_mul < 0) { const char *e = getenv("TSIM_LIGHTS_BITS"); bits_mul = (e && !strcmp(e, "mul")) ? 1 : 0; }
+    const dim3 bits_grid(div_up(L.wp * 4, 256), L.H < 65535 ? L.H : 65535, div_up(L.H, 65535));
+    if (bits_mul) lights_bits_kernel<true><<<bits_grid, 256, 0, cs>>>(L.W, L.H, p->cell_type, p->dirs, L.bp,
+                                                                                                                   (long long)mid_row * L.W, L.scal);
+    else lights_bits_kernel<false><<<bits_grid, 256, 0, cs>>>(L.W, L.H, p->cell_type, p->dirs, L.bp,
                                                                                                                    (long long)mid_row * L.W, L.scal);
     TSIM_LAUNCH_CHECK();
     cr_bits_kernel<<<div_up(L.nw, 256), 256, 0, cs>>>(L.H, L.bp, L.cr_prefix);

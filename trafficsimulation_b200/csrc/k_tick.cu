@@ -587,7 +587,15 @@ extern "C" tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_table
                                      int32_t n_ticks, int32_t algo, void *stream) {
     tsim_status r = check_tick_args(cfg, lt, tp, st);
     if (r != TSIM_OK) return r;
-    if (n_ticks < 1 || (algo != 0 && algo != 1)) { set_error("tick: n_ticks %d algo %d", n_ticks, algo); return TSIM_ERR_CONFIG; }
+    if (n_ticks < 1 || algo < 0 || algo > 2) { set_error("tick: n_ticks %d algo %d", n_ticks, algo); return TSIM_ERR_CONFIG; }
+    if (algo == 2 && lt->n_groups > 0 && (!lt->g_nsout_off || !lt->g_nsout || !lt->g_ewout_off || !lt->g_ewout)) {
+        set_error("tick: PRESSURE_CONTROL needs the g_nsout / g_ewout tables");
+        return TSIM_ERR_CONFIG;
+    }
+    if (algo == 2 && (cfg->win_y0 != 0 || cfg->win_rows != cfg->height)) {
+        set_error("tick: PRESSURE_CONTROL reads cells outside a shard window (tsim.h): whole cities only");
+        return TSIM_ERR_CONFIG;
+    }
     if (tick2_enabled(st)) return tick2_run(cfg, lt, tp, st, n_ticks, algo, (cudaStream_t)stream);
     TickArgs a{cfg->width, cfg->win_rows, n_ticks, algo, 0, 0, *lt, *tp, *st};
     own_cells(cfg, st, a.own_lo, a.own_hi);

@@ -135,6 +135,16 @@ __device__ __forceinline__ int group_controller(const TickArgs &a, int g) {
                 if (next != cur && next != pend) pend = next;   // apply_phase :386-393
                 s.g_qt[g] = 0;
             }
+        } else if (a.algo == 2) {   // run_pressure_control :448-461 (compute_max_pressure numba_utilities.py:74-85): every tick without a
+            // pending phase, the phase of the larger in-minus-out pressure.  The lists hold the cells the reference reads (tsim.h)
+            auto occ_at = [&](int c) { return PROBE ? bit_get(a, PL_OCC, c) : (int)s.occupancy[c]; };
+            int ns_p = 0, ew_p = 0;
+            for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_p += occ_at(lt.g_nsin[k]);
+            for (int k = lt.g_nsout_off[g]; k < lt.g_nsout_off[g + 1]; k++) ns_p -= occ_at(lt.g_nsout[k]);
+            for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_p += occ_at(lt.g_ewin[k]);
+            for (int k = lt.g_ewout_off[g]; k < lt.g_ewout_off[g + 1]; k++) ew_p -= occ_at(lt.g_ewout[k]);
+            const int ph = ns_p > ew_p ? 0 : 1;
+            if (ph != cur && ph != pend) pend = ph;   // apply_phase :386-393
         } else {             // run_fixed_time :427-441
             const int ft = ++s.g_ft_timer[g];
             if (ft == 1) { const int ph = s.g_ft_phase[g]; if (ph != cur && ph != pend) pend = ph; }

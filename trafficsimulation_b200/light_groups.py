@@ -11,9 +11,10 @@ Mirrors, for the default QUEUE_ACTUATED / FIXED_TIME controllers, what the refer
   iterates a Python set there; the tick tapes fix the activation order to this canonical one);
 * ``opposite_pairs`` (:243-279): a light joins the N-S (W-E) list if one of its controlled road cells
   has, as its FIRST arrow that enters an Intersection cell of this very cluster, a N/S (E/W) arrow;
-* lane cells (:141-154): every assigned incoming lane cell (with multiplicity) goes to ``ns_in`` if it
-  has a N or S arrow and lies below the light, else to ``ew_in`` if it has an E or W arrow and lies left
-  of the light (the *_out lists are not read by the two controllers in scope).
+* lane cells (:141-154): every assigned incoming -- and, with ``forward_traffic_light_range``, outgoing -- lane cell (with
+  multiplicity) that has a N or S arrow goes to ``ns_in`` if it lies below the light, else to ``ns_out``; a cell without one
+  but with an E or W arrow goes to ``ew_in`` if it lies left of the light, else to ``ew_out`` (the *_out lists are only read
+  by PRESSURE_CONTROL, :448-461).
 
 Everything is returned as CSR int32 arrays in the layout of ``tsim_light_tables`` (include/tsim.h).
 """
@@ -34,8 +35,10 @@ def _csr_from_pairs(owner, value, n_owner):
     return np.cumsum(off).astype(np.int32), value[order].astype(np.int32)
 
 
-def build_light_tables(W, H, cell_type, dirs, cluster_label, cluster_table, lights, ctrl_off, ctrl_cell, inc_off, inc_cell):
-    """All inputs are host numpy arrays; planes are [H, W]."""
+def build_light_tables(W, H, cell_type, dirs, cluster_label, cluster_table, lights, ctrl_off, ctrl_cell, inc_off, inc_cell,
+                       out_off=None, out_cell=None):
+    """All inputs are host numpy arrays; planes are [H, W].  out_off / out_cell: the lights' assigned OUTGOING lane cells
+    (only a layout with ``forward_traffic_light_range`` has them)."""
     T = cell_type.reshape(-1)
     D = dirs.reshape(-1).astype(np.int64)
     L = cluster_label.reshape(-1)
@@ -90,20 +93,28 @@ def build_light_tables(W, H, cell_type, dirs, cluster_label, cluster_table, ligh
         sel = axis == ax
         pairs = np.unique(np.stack([pg[sel], pl[sel]], 1), axis=0) if sel.any() else np.zeros((0, 2), np.int64)
         tabs[key + "_off"], tabs[key] = _csr_from_pairs(pairs[:, 0], pairs[:, 1], ng)
-    # lane cells
-    n_inc = (inc_off[li + 1] - inc_off[li]).astype(np.int64)
-    qg = np.repeat(gi, n_inc); ql = np.repeat(li, n_inc)
-    start = np.repeat(inc_off[li], n_inc)
-    within = np.arange(len(qg)) - np.repeat(np.cumsum(n_inc) - n_inc, n_inc)
-    rb = inc_cell[start + within].astype(np.int64)
+    # lane cells: per light its incoming list, then its outgoing list (:141-142)
+    def lane_pairs(off, cell):
+        off = np.asarray(off, np.int64)
+        cnt = (off[li + 1] - off[li]).astype(np.int64)
+        start = np.repeat(off[li], cnt)
+        within = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        pair = np.repeat(np.arange(len(li)), cnt)          # index of the (group, light) pair: keeps the reference's order
+        return pair, np.asarray(cell)[start + within].astype(np.int64), np.zeros(len(pair), np.int64)
+    pi, rb, half = lane_pairs(inc_off, inc_cell)
+    if out_off is not None and len(np.asarray(out_cell)):
+        po, rbo, _ = lane_pairs(out_off, out_cell)
+        pi, rb, half = np.concatenate([pi, po]), np.concatenate([rb, rbo]), np.concatenate([half, np.ones(len(po), np.int64)])
+        order = np.lexsort((half, pi))                     # stable inside a half: a light's incoming cells, then its outgoing ones
+        pi, rb = pi[order], rb[order]
+    qg, ql = gi[pi], li[pi]
     rbd = D[rb] & 0xF
     tlx, tly = lights[ql] % W, lights[ql] // W
     vertical = (rbd & 0b0101) != 0
     horizontal = ~vertical & ((rbd & 0b1010) != 0)
-    ns_in = vertical & (rb // W < tly)
-    ew_in = horizontal & (rb % W < tlx)
-    tabs["g_nsin_off"], tabs["g_nsin"] = _csr_from_pairs(qg[ns_in], rb[ns_in], ng)
-    tabs["g_ewin_off"], tabs["g_ewin"] = _csr_from_pairs(qg[ew_in], rb[ew_in], ng)
+    below, left = rb // W < tly, rb % W < tlx
+    for key, sel in (("g_nsin", vertical & below), ("g_nsout", vertical & ~below), ("g_ewin", horizontal & left), ("g_ewout", horizontal & ~left)):
+        tabs[key + "_off"], tabs[key] = _csr_from_pairs(qg[sel], rb[sel], ng)
     # cluster cells of the groups
     cells = np.flatnonzero(L > 0)
     lab = L[cells].astype(np.int64) - 1
@@ -115,6 +126,18 @@ def build_light_tables(W, H, cell_type, dirs, cluster_label, cluster_table, ligh
     return tabs
 
 
+def pressure_cells(tabs, W):
+    """The lane tables as PRESSURE_CONTROL reads them.  ``run_pressure_control`` (intersection_light_group.py:448-461) passes
+    ``to_int32(occ_map)`` -- the [H, W] occupancy map reshaped to (-1, 2), :443-446 -- to ``compute_max_pressure``
+    (utilities/numba_utilities.py:74-85), whose ``occupancy_map[y, x]`` then reads flat element ``2 * y + x`` of the map (Numba
+    does not check bounds; the element always exists).  Bit-exact parity means counting the vehicles on THOSE cells."""
+    out = dict(tabs)
+    for k in ("g_nsin", "g_ewin", "g_nsout", "g_ewout"):
+        c = np.asarray(tabs[k], np.int64)
+        out[k] = (2 * (c // W) + c % W).astype(np.int32)
+    return out
+
+
 def groups_as_cell_lists(tabs, lights):
     """Group tables as sorted cell-index arrays (the form the reference fixtures use), for parity checks."""
     lights = np.asarray(lights)
@@ -122,5 +145,6 @@ def groups_as_cell_lists(tabs, lights):
     for g in range(tabs["n_groups"]):
         sl = lambda k: tabs[k][tabs[k + "_off"][g]:tabs[k + "_off"][g + 1]]
         out.append(dict(cluster=np.sort(sl("g_cl")), lights=np.sort(lights[sl("g_all")]), ns_lights=np.sort(lights[sl("g_ns")]),
-                        ew_lights=np.sort(lights[sl("g_ew")]), ns_in=np.sort(sl("g_nsin")), ew_in=np.sort(sl("g_ewin"))))
+                        ew_lights=np.sort(lights[sl("g_ew")]), ns_in=np.sort(sl("g_nsin")), ew_in=np.sort(sl("g_ewin")),
+                        ns_out=np.sort(sl("g_nsout")), ew_out=np.sort(sl("g_ewout"))))
     return out

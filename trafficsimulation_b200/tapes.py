@@ -209,3 +209,41 @@ def synth_trips(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarr
                 ev_tick=tick_of.copy(), ev_vehicle=np.arange(nv, dtype=np.int32), ev_off=ev_off, ev_cells=route[route >= 0].astype(np.int32),
                 rain_map=np.zeros((H, W), np.uint8))
     return base
+
+
+def spawn_tape_from_trips(depart_secs, origin_cells, target_cells, dt, n_ticks: int, elapsed: float = 0.0):
+    """The reference's trip schedule as a spawn tape.
+
+    ``DynamicTrafficAgent._generate_day`` (agents/dynamic_traffic_generator.py:307-396) fills ``pending`` with trips -- departure
+    time, origin cell, destination cell -- from draws of Python's ``random``; those draws are decisions, i.e. an input here (DESIGN.md
+    §2).  What is restated is WHEN ``step`` (:151-189) hands a pending trip to ``_spawn``: the clock advances by ``dt`` per tick BY
+    REPEATED FLOAT ADDITION (``self.elapsed += self.dt``) and tick k spawns, in ``pending`` order, the trips with
+    ``elapsed_k < depart_secs <= elapsed_k + dt``.  Trips that depart at or before ``elapsed`` are never spawned by the reference
+    either (the comparison is strict); trips after the last tick stay pending.
+
+    depart_secs / origin_cells / target_cells: one entry per pending trip, in ``pending`` order (cell = y * W + x).
+    Returns dict(spawn_tick, origin, target, trip) sorted by tick (stable), ``trip`` = index into the inputs.
+    """
+    d = np.asarray(depart_secs, np.float64)
+    edges = np.empty(n_ticks + 1, np.float64)
+    e = float(elapsed)
+    edges[0] = e
+    for k in range(n_ticks):   # the reference's own accumulation, not k * dt
+        e += dt
+        edges[k + 1] = e
+    tick = np.searchsorted(edges, d, side="left") - 1          # edges[tick] < d <= edges[tick + 1]
+    keep = np.flatnonzero((tick >= 0) & (tick < n_ticks))
+    order = keep[np.argsort(tick[keep], kind="stable")]
+    return dict(spawn_tick=tick[order].astype(np.int32), origin=np.asarray(origin_cells, np.int64)[order].astype(np.int32),
+                target=np.asarray(target_cells, np.int64)[order].astype(np.int32), trip=order.astype(np.int32))
+
+
+def spawn_tape_from_generator(gen, width: int, n_ticks: int, kinds=("internal", "through")):
+    """``spawn_tape_from_trips`` for a live ``DynamicTrafficAgent`` (``model.dynamic_traffic_generator``): reads its ``pending`` list,
+    clock and ``dt`` without touching them.  Service trips (``service_food`` / ``service_waste``: ``ServiceVehicleAgent``, out of
+    scope) are left out.  Returns the tape and the trips it was made from."""
+    trips = [t for t in gen.pending if t.kind in kinds]
+    cell = lambda a: a.position[1] * width + a.position[0]
+    tape = spawn_tape_from_trips([t.depart_secs for t in trips], [cell(t.origin) for t in trips], [cell(t.destination) for t in trips],
+                                 gen.dt, n_ticks, gen.elapsed)
+    return tape, trips

@@ -16,13 +16,15 @@ import numpy as np
 import torch
 
 from . import _lib
-from .light_groups import build_light_tables
+from .light_groups import build_light_tables, pressure_cells
 
 _I8 = ("alive", "base_speed", "cur_speed", "max_steps", "early", "is_stuck", "prev_valid", "malfunction", "direction", "moved")
 _I32 = ("pos", "path_len", "steps", "stranded")
 _G32 = ("g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "g_plan")
 _LT = ("tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
        "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl")
+_LT_OUT = ("g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout")   # PRESSURE_CONTROL only
+ALGOS = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2}   # Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM (config.py:341)
 
 
 def light_tables_from_layout(city):
@@ -47,10 +49,12 @@ def light_tables_from_layout(city):
     planes = city.planes_host()
     ctrl_off = t["ctrl_off"][: nl + 1].cpu().numpy()
     inc_off = t["inc_off"][: nl + 1].cpu().numpy()
+    out_off = t["out_off"][: nl + 1].cpu().numpy() if "out_off" in t else None
     return build_light_tables(
         W, H, planes["cell_type"], planes["dirs"], labels.cpu().numpy().reshape(H, W), blobs[: nc * 6].view(nc, 6).cpu().numpy(),
         t["light_cell"][:nl].cpu().numpy(), ctrl_off, t["ctrl_cell"][: int(ctrl_off[-1]) if nl else 0].cpu().numpy(),
-        inc_off, t["inc_cell"][: int(inc_off[-1]) if nl else 0].cpu().numpy())
+        inc_off, t["inc_cell"][: int(inc_off[-1]) if nl else 0].cpu().numpy(),
+        out_off, t["out_cell"][: int(out_off[-1]) if nl else 0].cpu().numpy() if out_off is not None else None)
 
 
 class GpuTraffic:
@@ -72,7 +76,11 @@ class GpuTraffic:
         self.lib = _lib.load()
         self.device = dev = torch.device(device)
         self.W, self.H, self.n_ticks = int(width), int(height), int(n_ticks)
-        self.algo = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1}[algo]
+        if algo not in ALGOS:
+            raise ValueError(f"light controller {algo!r}: the device runs {sorted(ALGOS)}")
+        self.algo = ALGOS[algo]
+        if self.algo == 2 and window is not None:
+            raise NotImplementedError("PRESSURE_CONTROL on a row-band shard: the cells that controller reads lie outside the shard's window")
         self.win_y0, self.win_rows, self.win_halo = (0, self.H, 0) if window is None else (int(v) for v in window)
         self.cfg = _lib.Cfg(self.W, self.H, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, self.win_y0, self.win_rows, self.win_halo)
         n = self.W * self.win_rows
@@ -82,9 +90,14 @@ class GpuTraffic:
                 return a.to(device=dev, dtype=getattr(torch, np.dtype(dt).name)).contiguous()
             return torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
         # ---- light tables
-        self.lt_t = {k: up(light_tables[k], np.int32) for k in _LT}
+        if self.algo == 2:
+            if any(k not in light_tables for k in _LT_OUT):
+                raise ValueError("PRESSURE_CONTROL needs the g_nsout / g_ewout lane tables (light_groups.build_light_tables)")
+            light_tables = pressure_cells(light_tables, self.W)   # the cells the reference's controller really reads
+        self.lt_t = {k: up(light_tables[k], np.int32) for k in _LT + (_LT_OUT if self.algo == 2 else ())}
         self.n_groups, self.n_lights = int(light_tables["n_groups"]), int(light_tables["n_lights"])
-        self.lt = _lib.LightTables(self.n_groups, self.n_lights, *[self.lt_t[k].data_ptr() for k in _LT])
+        self.lt = _lib.LightTables(self.n_groups, self.n_lights, *[self.lt_t[k].data_ptr() for k in _LT],
+                                   *[(self.lt_t[k].data_ptr() if self.algo == 2 else 0) for k in _LT_OUT])
         # ---- tapes
         spawn_tick = np.asarray(tapes["spawn_tick"], np.int32)
         ev_tick = np.asarray(tapes["ev_tick"], np.int32)
