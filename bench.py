@@ -780,7 +780,7 @@ def ours(args):
             log("4096 leg done")
             # the legs beside the headline run in processes of their own with a time limit each: a leg that fails, hangs or
             # crawls on a slow host costs its own entry, never the line (the parent keeps its device memory meanwhile)
-            for key, leg, limit_s in (("vehicle_step", "tick100k", 150), ("vehicle_step_1M", "tick1m", 240), ("route_planning", "routes", 90)):
+            for key, leg, limit_s in (() if args.no_legs else (("vehicle_step", "tick100k", 150), ("vehicle_step_1M", "tick1m", 240), ("route_planning", "routes", 90))):
                 line[key] = run_leg(leg, limit_s)
                 log(f"leg {leg} done" + (f": {line[key]['error']}" if isinstance(line[key], dict) and "error" in line[key] else ""))
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",
@@ -839,6 +839,7 @@ def main():
     ap.add_argument("--shard-rows", type=int, default=8192, help="N > 1: rows per GPU of the sharded city")
     ap.add_argument("--no-graph", action="store_true", help="N = 1: time eager launches instead of one CUDA graph per city")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the shifted-cut / single-GPU digest comparison")
+    ap.add_argument("--no-legs", action="store_true", help="N = 1: only the layout legs (no vehicle-tick / route-planning child processes)")
     ap.add_argument("--leg", choices=sorted(LEGS), help="run one of the legs beside the headline alone and print its JSON object")
     args = ap.parse_args()
     if args.leg:

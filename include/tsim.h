@@ -273,7 +273,7 @@ tsim_status tsim_maps(const tsim_cfg *cfg, const tsim_planes *p, uint8_t *is_roa
 /* ------------------------------------------------------------------------------------------------
  * Tick: CityModel.step (city_model.py:1831-1860) = phase A VehicleAgent.step_decide for every active
  * vehicle (vehicle_base.py:616-663), then phase B in activation order: IntersectionLightGroup.step
- * (intersection_light_group.py:396-423, QUEUE_ACTUATED :463-494 / FIXED_TIME :427-441 / PRESSURE_CONTROL :448-461, phase commit
+ * (intersection_light_group.py:396-423, QUEUE_ACTUATED :463-494 / FIXED_TIME :427-441 / PRESSURE_CONTROL :448-461 / NEIGHBOR_GREEN_WAVE :522-546, phase commit
  * :348-384, stop_map writes cell.py:241-251), VehicleAgent.step (vehicle_base.py:666-685: movement
  * :733-753 via CityModel.move_vehicle city_model.py:1945-1963, tick_stuck :687-693, arrival :755-775),
  * and the tape-driven spawner (place_vehicle city_model.py:1897-1908).
@@ -294,6 +294,9 @@ typedef struct tsim_light_tables {   /* all device pointers; CSR offsets have n+
        i.e. flat element 2 * y + x instead of W * y + x -- the host tables carry that index (light_groups.pressure_cells).  */
     const int32_t *g_nsout_off, *g_nsout;
     const int32_t *g_ewout_off, *g_ewout;
+    /* NEIGHBOR_GREEN_WAVE only (NULL otherwise): neighbor_groups of every group, [n_groups][4] = N, S, E, W, -1 = none
+       (IntersectionLightGroup.populate_links, intersection_light_group.py:175-242; host: light_groups.neighbor_links)     */
+    const int32_t *g_nbr;
 } tsim_light_tables;
 
 typedef struct tsim_tick_tapes {     /* all device pointers */
@@ -355,6 +358,10 @@ typedef struct tsim_tick_state {     /* all device pointers, owned by the caller
        every group's incoming lanes and cluster as (tile, mask) pairs over the occupancy plane of `probe`, and the cells its
        lights control as one flat list, so that a queue count (intersection_light_group.py:463-494) is a handful of popcounts instead of one load per lane cell */
     void *group_ws;
+    /* NEIGHBOR_GREEN_WAVE only (NULL otherwise): [3 * n_groups + 4] scratch of the per-tick fixed point that settles, in
+       activation order, which phase every group asks for (a group reads the phase its lower-ranked neighbours hold AFTER
+       their step of this very tick)                                                                                      */
+    int32_t *g_wave;
 } tsim_tick_state;
 #define TSIM_TICK_VREC_BYTES 48
 #define TSIM_TICK_PLAN_BYTES 32
@@ -370,7 +377,8 @@ tsim_status tsim_tick_probe_bytes(const tsim_cfg *cfg, long long *bytes);
 tsim_status tsim_tick_group_ws_bytes(const tsim_cfg *cfg, const tsim_light_tables *lt, long long *bytes);
 
 /* advance n ticks (one persistent cooperative launch); algo: 0 QUEUE_ACTUATED, 1 FIXED_TIME, 2 PRESSURE_CONTROL (needs the
-   g_nsout / g_ewout tables; not on row-band shards: the cells that controller reads lie outside any window, see above) */
+   g_nsout / g_ewout tables), 3 NEIGHBOR_GREEN_WAVE (:522-546; needs g_nbr and state.g_wave).  2 and 3 run on whole cities only:
+   the cells / neighbour groups they read lie outside a row-band window */
 tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_tables *lt, const tsim_tick_tapes *tp,
                           const tsim_tick_state *st, int32_t n_ticks, int32_t algo, void *stream);
 

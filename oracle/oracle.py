@@ -187,7 +187,7 @@ class VSim(C.Structure):
                     "tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
                     "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl",
                     "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "collision", "veh_at",
-                    "g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout", "g_nsp", "g_ewp")])
+                    "g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout", "g_nsp", "g_ewp", "g_nbr")])
 
 
 def csr(lists, dtype=np.int32):
@@ -214,9 +214,11 @@ def light_tables_from_reference(lights, ctrl_pairs, groups):
         t[key + "_off"], t[key] = csr([[lidx[int(c)] for c in g[src]] for g in groups])
     for key, src in (("g_nsin", "ns_in"), ("g_ewin", "ew_in"), ("g_cl", "cluster")):
         t[key + "_off"], t[key] = csr([g[src] for g in groups])
-    for key, src in (("g_nsout", "ns_out"), ("g_ewout", "ew_out")):   # newer harness runs / fixtures only (pressure controller)
+    for key, src in (("g_nsout", "ns_out"), ("g_ewout", "ew_out")):   # newer harness runs / fixtures only (pressure controllers)
         if all(src in g for g in groups):
             t[key + "_off"], t[key] = csr([g[src] for g in groups])
+    if len(groups) and all("nbr" in g for g in groups):                # neighbour links, canonical indices (N, S, E, W)
+        t["g_nbr"] = np.stack([g["nbr"] for g in groups]).astype(np.int32)
     t["n_lights"], t["n_groups"] = len(lights), len(groups)
     return t
 
@@ -263,6 +265,12 @@ class OracleTicks:
             else:
                 a[k + "_off"], a[k] = np.zeros(ng + 1, np.int32), np.zeros(0, np.int32)
         a["g_nsp"] = np.zeros(ng, np.int32); a["g_ewp"] = np.zeros(ng, np.int32)
+        if "g_nbr" in tables:
+            a["g_nbr"] = np.ascontiguousarray(tables["g_nbr"], np.int32).reshape(-1)
+        elif algo == 3:
+            raise ValueError("NEIGHBOR_GREEN_WAVE needs the g_nbr link table")
+        else:
+            a["g_nbr"] = np.full(4 * max(ng, 1), -1, np.int32)
         if algo == 2:
             # run_pressure_control hands compute_max_pressure `to_int32(occ_map)` (intersection_light_group.py:443-453): the [H, W] map
             # reshaped to (-1, 2).  Numba does not check bounds, so `occupancy_map[y, x]` reads flat element 2 * y + x of the map

@@ -65,7 +65,14 @@ def light_group_tables(model):
             ns_out=np.array(sorted(int(y) * W + int(x) for x, y in np.asarray(g.ns_out_coords).reshape(-1, 2)), np.int32),
             ew_out=np.array(sorted(int(y) * W + int(x) for x, y in np.asarray(g.ew_out_coords).reshape(-1, 2)), np.int32),
         )))
+    creation = {id(g): i for i, g in enumerate(model.intersection_light_groups)}
     groups.sort(key=lambda t: t[0])
+    canon = {id(t[1]): i for i, t in enumerate(groups)}
+    for i, (_, g, d) in enumerate(groups):
+        # neighbour links as populate_links left them (intersection_light_group.py:175-242; the second pass has just run: the
+        # get_opposite_traffic_lights() call above), canonical indices, columns N, S, E, W; and the group's creation rank
+        d["nbr"] = np.array([canon[id(g.neighbor_groups[k])] if k in (g.neighbor_groups or {}) else -1 for k in ("N", "S", "E", "W")], np.int32)
+        d["creation_rank"] = np.array([creation[id(g)]], np.int32)
     return [t[2] for t in groups], [t[1] for t in groups]
 
 
@@ -211,7 +218,8 @@ def run_ticks(seed, n_ticks, spawns_per_tick=6, malfunction_p=0.0, rain_rect=Non
                 group_phase.append(np.array([[-1 if g.current_phase is None else g.current_phase,
                                               -1 if g.pending_phase is None else g.pending_phase,
                                               g.queue_timer, g.gap_timer, g.last_arrival] for g in group_order], np.int32))
-                group_ext.append(np.array([[g.fixed_time_timer, g._ft_phase, g.ns_pressure, g.ew_pressure] for g in group_order], np.int32))
+                clamp = lambda v: max(-2 ** 31, min(2 ** 31 - 1, int(v)))   # NEIGHBOR_PRESSURE_CONTROL's pressures outgrow any fixed width
+                group_ext.append(np.array([[g.fixed_time_timer, g._ft_phase, clamp(g.ns_pressure), clamp(g.ew_pressure)] for g in group_order], np.int32))
     finally:
         VehicleAgent.step_decide = orig_decide
         VehicleAgent._compute_path = orig_compute

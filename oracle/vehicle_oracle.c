@@ -11,7 +11,8 @@
  *   CityModel.move_vehicle / remove_vehicle / place_vehicle   city_model.py:1897-1963
  *   IntersectionLightGroup.step          agents/city_structure_entities/intersection_light_group.py:396-423
  *     run_queue_actuated :463-494, run_fixed_time :427-441, run_pressure_control :448-461 (compute_max_pressure
- *     utilities/numba_utilities.py:74-85), apply_phase :386-393,
+ *     utilities/numba_utilities.py:74-85), run_neighbor_green_wave :522-546,
+ *     apply_phase :386-393,
  *     _execute_phase_change :348-384, is_intersection_occupied :285-291
  *   CellAgent.set_light_stop / set_light_go   agents/city_structure_entities/cell.py:241-251
  *
@@ -26,7 +27,10 @@
 
 typedef struct {
     int32_t W, H, n_vehicles, n_groups, n_lights;
-    int32_t algo;                 /* 0 QUEUE_ACTUATED, 1 FIXED_TIME, 2 PRESSURE_CONTROL (config.py:341) */
+    int32_t algo;                 /* 0 QUEUE_ACTUATED, 1 FIXED_TIME, 2 PRESSURE_CONTROL, 3 NEIGHBOR_GREEN_WAVE (config.py:341).
+                                     NEIGHBOR_PRESSURE_CONTROL (:496-520) is not restated: every group subtracts its neighbours' pressures from
+                                     its own, the neighbours do the same, and the values double every tick or two -- Python's integers follow
+                                     them past 2^63 within about 60 ticks (seen live: 2.7e9 after 30), fixed-width ones cannot */
     int32_t rain_enabled;         /* Defaults.RAIN_ENABLED */
     int32_t tick;                 /* next tick to run */
     /* maps [H*W] */
@@ -53,6 +57,8 @@ typedef struct {
     /* pressure controller: lane cells on the far side of their light (ns_out_coords / ew_out_coords :141-154), last pressures */
     const int32_t *g_nsout_off, *g_nsout, *g_ewout_off, *g_ewout;
     int32_t *g_nsp, *g_ewp;
+    /* neighbour controllers: neighbor_groups of every group, [n_groups][4] = N, S, E, W, -1 none (populate_links :175-242) */
+    const int32_t *g_nbr;
 } vsim;
 
 enum { MIN_GREEN = 5, MAX_GREEN = 30, GAP = 3, GREEN_DURATION = 20, AWARENESS = 10,
@@ -87,6 +93,19 @@ static void group_step(vsim *s, int g) {
             for (int k = s->g_ewout_off[g]; k < s->g_ewout_off[g + 1]; k++) ew_p -= s->occ[s->g_ewout[k]];
             s->g_nsp[g] = ns_p; s->g_ewp[g] = ew_p;
             int ph = ns_p > ew_p ? 0 : 1;
+            if (ph != s->g_cur[g] && ph != s->g_pend[g]) s->g_pend[g] = ph;
+        } else if (s->algo == 3) { /* run_neighbor_green_wave :522-546: follow the neighbours' CURRENT phase (this tick's if they stepped
+                                      before this group), else the longer own queue */
+            int ns_q = 0, ew_q = 0, favor_ns = 0, favor_ew = 0;
+            for (int k = s->g_nsin_off[g]; k < s->g_nsin_off[g + 1]; k++) ns_q += s->occ[s->g_nsin[k]];
+            for (int k = s->g_ewin_off[g]; k < s->g_ewin_off[g + 1]; k++) ew_q += s->occ[s->g_ewin[k]];
+            for (int d = 0; d < 4; d++) {
+                int nb = s->g_nbr[4 * g + d];
+                if (nb < 0) continue;
+                if (d < 2 && s->g_cur[nb] == 0) favor_ns = 1;
+                if (d >= 2 && s->g_cur[nb] == 1) favor_ew = 1;
+            }
+            int ph = (favor_ns && !favor_ew) ? 0 : (favor_ew && !favor_ns) ? 1 : (ns_q > ew_q ? 0 : 1);
             if (ph != s->g_cur[g] && ph != s->g_pend[g]) s->g_pend[g] = ph;
         } else { /* run_fixed_time :427-441 */
             s->g_ft_timer[g]++;

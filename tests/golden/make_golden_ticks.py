@@ -30,6 +30,9 @@ CASES = {
     # the other light controllers (Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM, intersection_light_group.py:396-461)
     "s31_fixed_time": dict(seed=31, n_ticks=100, spawns_per_tick=8, malfunction_p=0.002, algo="FIXED_TIME"),
     "s9_pressure": dict(seed=9, n_ticks=120, spawns_per_tick=8, malfunction_p=0.002, algo="PRESSURE_CONTROL"),
+    "s9_green_wave": dict(seed=9, n_ticks=120, spawns_per_tick=8, malfunction_p=0.002, algo="NEIGHBOR_GREEN_WAVE"),
+    "s14_green_wave": dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01, algo="NEIGHBOR_GREEN_WAVE",
+                           layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
     "s14_pressure_fwd": dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01, algo="PRESSURE_CONTROL",
                              layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True, forward_traffic_light_range=True)),
 }
@@ -87,6 +90,9 @@ def main():
             arrays["g_" + f + "_off"], arrays["g_" + f] = csr([g[f] for g in r["groups"]])
         if case.get("algo"):   # fixed-time timer / phase, pressures (older fixtures stay byte-identical without them)
             arrays["group_ext"] = r["group_ext"].astype(np.int16)
+            # neighbour links of the reference (canonical group indices, N S E W) and the order it created its groups in
+            arrays["g_nbr"] = np.stack([g["nbr"] for g in r["groups"]]).astype(np.int32)
+            arrays["g_creation_rank"] = np.array([int(g["creation_rank"][0]) for g in r["groups"]], np.int32)
         path = os.path.join(HERE, f"ticks_{name}.npz")
         np.savez_compressed(path, **arrays)
         print(name, os.path.getsize(path) // 1024, "KiB", "spawned", int(r["spawned"].sum()), "events", len(r["ev_tick"]))

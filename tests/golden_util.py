@@ -61,6 +61,9 @@ def load_ticks(path):
     for g in range(ng):
         groups.append({f: d["g_" + f][d["g_" + f + "_off"][g]:d["g_" + f + "_off"][g + 1]]
                        for f in ("cluster", "lights", "ns_lights", "ew_lights", "ns_in", "ew_in", "ns_out", "ew_out") if "g_" + f in d})
+    if "g_nbr" in d:
+        for g in range(ng):
+            groups[g]["nbr"] = d["g_nbr"][g]
     d["groups"] = groups
     d["algo"] = d["meta"]["case"].get("algo") or "QUEUE_ACTUATED"
     d["group_state"] = d["group_state"].astype(np.int32)

@@ -26,7 +26,10 @@ def test_gpu_ticks_match_reference_fixture(path, live_list):
     from trafficsimulation_b200.light_groups import groups_as_cell_lists
     r = load_ticks(path)
     city = build_city(r["meta"]["cfg"], r["hbands"], r["vbands"], r["tape_zone"], r["tape_carve"], r["tape_entrance"])
-    tabs = light_tables_from_layout(city)
+    green = r["algo"] == "NEIGHBOR_GREEN_WAVE"   # neighbour links: marched here in the order the reference created its groups in
+    tabs = light_tables_from_layout(city, links=green, creation_order=np.argsort(r["g_creation_rank"]) if green else None)
+    if green:
+        assert np.array_equal(tabs["g_nbr"], r["g_nbr"]) and (r["g_nbr"] >= 0).any()
     lights = city.light_links_host()["lights"]
     mine = groups_as_cell_lists(tabs, lights)
     assert len(mine) == len(r["groups"])
@@ -65,7 +68,8 @@ def test_gpu_ticks_multi_tick_launch_equals_single_ticks():
 
 @pytest.mark.parametrize("size,nveh,algo,live_list", [(512, 20000, "QUEUE_ACTUATED", True), (768, 60000, "FIXED_TIME", True),
                                                        (512, 20000, "FIXED_TIME", False), (768, 60000, "QUEUE_ACTUATED", "sorted"),
-                                                       (512, 20000, "PRESSURE_CONTROL", True), (512, 20000, "PRESSURE_CONTROL", False)])
+                                                       (512, 20000, "PRESSURE_CONTROL", True), (512, 20000, "PRESSURE_CONTROL", False),
+                                                       (384, 12000, "NEIGHBOR_GREEN_WAVE", True), (384, 12000, "NEIGHBOR_GREEN_WAVE", False)])
 def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo, live_list, monkeypatch):
     """Dense synthetic traffic on a city the reference cannot plan routes for: CUDA vs the pinned C oracle."""
     if live_list == "sorted":
@@ -78,13 +82,13 @@ def test_gpu_ticks_match_oracle_synthetic(size, nveh, algo, live_list, monkeypat
     hb, vb = tapes.synth_bands(seed, width=size, height=size)
     cap = 3 * (len(hb) + 2) * (len(vb) + 2) + 64
     city = build_city(dict(width=size, height=size), hb, vb, tapes.synth_zone_tape(seed, cap), None, np.zeros(cap, np.int32))
-    tabs = light_tables_from_layout(city)
+    tabs = light_tables_from_layout(city, links=algo == "NEIGHBOR_GREEN_WAVE")
     planes = city.planes_host()
     n_ticks = 50
     tp = tapes.synth_traffic(seed, size, size, planes["cell_type"], planes["dirs"], nveh, n_ticks, route_len=120, spawn_ticks=5,
                              malfunction_p=0.001)
     sim = GpuTraffic(size, size, tabs, tp, n_ticks, algo=algo, live_list=live_list)
-    ora = O.OracleTicks(size, size, tabs, tp, n_ticks, algo={"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2}[algo])
+    ora = O.OracleTicks(size, size, tabs, tp, n_ticks, algo={"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2, "NEIGHBOR_GREEN_WAVE": 3}[algo])
     moved = 0
     prev = None
     for t in range(n_ticks):

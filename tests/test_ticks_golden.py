@@ -12,7 +12,7 @@ from golden_util import tick_fixtures, load_ticks, compare_tick
 def test_tick_oracle_reproduces_golden(path):
     r = load_ticks(path)
     tables = O.light_tables_from_reference(r["links_lights"], r["links_ctrl"], r["groups"])
-    algo = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2}[r["algo"]]
+    algo = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2, "NEIGHBOR_GREEN_WAVE": 3}[r["algo"]]
     sim = O.OracleTicks(r["W"], r["H"], tables, r, r["n_ticks"], algo=algo, rain_enabled=r["meta"]["rain_enabled"])
     for t in range(r["n_ticks"]):
         sim.run(1)

@@ -19,8 +19,12 @@ CASES = [
     dict(seed=9, n_ticks=100, spawns_per_tick=8, malfunction_p=0.0, algo="PRESSURE_CONTROL"),
     dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01, algo="PRESSURE_CONTROL",
          layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True, forward_traffic_light_range=True)),
+    dict(seed=12345, n_ticks=100, spawns_per_tick=8, malfunction_p=0.0, algo="NEIGHBOR_GREEN_WAVE"),
+    dict(seed=9, n_ticks=100, spawns_per_tick=8, malfunction_p=0.002, algo="NEIGHBOR_GREEN_WAVE"),
+    dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01, algo="NEIGHBOR_GREEN_WAVE",
+         layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
 ]
-ALGO = {None: 0, "QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2}
+ALGO = {None: 0, "QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2, "NEIGHBOR_GREEN_WAVE": 3}
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"s{c['seed']}" + ("_sideswipe" if c.get("sideswipe_p") else "") + ("_" + c["algo"] if c.get("algo") else ""))

@@ -61,7 +61,7 @@ class LightLinks(C.Structure):
 class LightTables(C.Structure):
     _fields_ = [("n_groups", C.c_int32), ("n_lights", C.c_int32)] + [(n, C.c_void_p) for n in (
         "tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
-        "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl", "g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout")]
+        "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl", "g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout", "g_nbr")]
 
 
 class TickTapes(C.Structure):
@@ -76,7 +76,7 @@ class TickState(C.Structure):
         "alive", "base_speed", "cur_speed", "max_steps", "early", "is_stuck", "prev_valid", "malfunction", "direction", "moved",
         "g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer", "g_plan", "scalars")] + \
         [("own_row_lo", C.c_int32), ("own_row_hi", C.c_int32)] + \
-        [(n, C.c_void_p) for n in ("probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff", "live_idx", "sort_keys", "tile_ws", "group_ws")]
+        [(n, C.c_void_p) for n in ("probe", "recs", "plans", "ev_stamp", "ev_plen", "ev_poff", "live_idx", "sort_keys", "tile_ws", "group_ws", "g_wave")]
 
 
 class TickStrips(C.Structure):

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const ui
         uint32_t nz = 0;   // cells with at least one arrow
         if (MUL) {
             // the arrow mask is the low nibble of every cell's dirs word: low bytes of 4 cells -> one word (PRMT), then one multiplication
-            // gathers bit d of the four bytes (632 -> 504 SASS instructions; TSIM_LIGHTS_BITS=mul, see launch site)
+            // gathers bit d of the four bytes (632 -> 504 SASS instructions; TSIM_LIGHTS_BITS=shift selects the older form)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t lb = __byte_perm(dw[2 * j], dw[2 * j + 1], 0x6420);
@@ -1161,7 +1161,7 @@ extern "C" tsim_status tsim_lights_prepare(const tsim_cfg *cfg, const tsim_plane
     init_pivot_kernel<<<1, 1, 0, cs>>>(L.scal);
     TSIM_LAUNCH_CHECK();
     static int bits_mul = -1;   // arrow-bit extraction of lights_bits_kernel: 0 shift-and-mask per dirs word, 1 byte gather + multiplication
-    if (bits_mul < 0) { const char *e = getenv("TSIM_LIGHTS_BITS"); bits_mul = (e && !strcmp(e, "mul")) ? 1 : 0; }
+    if (bits_mul < 0) { const char *e = getenv("TSIM_LIGHTS_BITS"); bits_mul = (e && !strcmp(e, "shift")) ? 0 : 1; }   // measured in bench.py: lights pass 1.955 (shift) / 1.933 ms (mul)
     const dim3 bits_grid(div_up(L.wp * 4, 256), L.H < 65535 ? L.H : 65535, div_up(L.H, 65535));
     if (bits_mul) lights_bits_kernel<true><<<bits_grid, 256, 0, cs>>>(L.W, L.H, p->cell_type, p->dirs, L.bp,
                                                                                                                    (long long)mid_row * L.W, L.scal);

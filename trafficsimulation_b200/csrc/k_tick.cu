@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) tick_kernel(TickArgs a) {
         // a shard iterates the list of the vehicles alive in its window (built after the last halo refresh: valid for one tick)
         const bool use_list = it == 0 && s.live_idx && *((volatile int32_t *)(s.scalars + S_LIST_OK)) != 0;
         const int n_it = use_list ? min(*((volatile int32_t *)(s.scalars + S_NLIST)), nv) : nv;
+        if (a.algo == 3 && ng > 0) green_wave_prepass<false>(a, grid, tid, nth);
         // ---- 1: phase A + light-group decisions (staged)
         int live = 0;
         for (int i = tid; i < n_it; i += nth) {
@@ -587,13 +588,17 @@ extern "C" tsim_status tsim_tick_run(const tsim_cfg *cfg, const tsim_light_table
                                      int32_t n_ticks, int32_t algo, void *stream) {
     tsim_status r = check_tick_args(cfg, lt, tp, st);
     if (r != TSIM_OK) return r;
-    if (n_ticks < 1 || algo < 0 || algo > 2) { set_error("tick: n_ticks %d algo %d", n_ticks, algo); return TSIM_ERR_CONFIG; }
+    if (n_ticks < 1 || algo < 0 || algo > 3) { set_error("tick: n_ticks %d algo %d", n_ticks, algo); return TSIM_ERR_CONFIG; }
+    if (algo == 3 && lt->n_groups > 0 && (!lt->g_nbr || !st->g_wave)) {
+        set_error("tick: NEIGHBOR_GREEN_WAVE needs the g_nbr table and the g_wave scratch");
+        return TSIM_ERR_CONFIG;
+    }
     if (algo == 2 && lt->n_groups > 0 && (!lt->g_nsout_off || !lt->g_nsout || !lt->g_ewout_off || !lt->g_ewout)) {
         set_error("tick: PRESSURE_CONTROL needs the g_nsout / g_ewout tables");
         return TSIM_ERR_CONFIG;
     }
-    if (algo == 2 && (cfg->win_y0 != 0 || cfg->win_rows != cfg->height)) {
-        set_error("tick: PRESSURE_CONTROL reads cells outside a shard window (tsim.h): whole cities only");
+    if (algo >= 2 && (cfg->win_y0 != 0 || cfg->win_rows != cfg->height)) {
+        set_error("tick: PRESSURE_CONTROL / NEIGHBOR_GREEN_WAVE read cells / groups outside a shard window (tsim.h): whole cities only");
         return TSIM_ERR_CONFIG;
     }
     if (tick2_enabled(st)) return tick2_run(cfg, lt, tp, st, n_ticks, algo, (cudaStream_t)stream);

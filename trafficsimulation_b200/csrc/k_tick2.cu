@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(256, MINB) tick2_kernel(TickArgs a) {
         // vehicles move at most 5 cells a tick and the plain append keeps the vehicles of a warp together: the tile order of the
         // list decays slowly, so the list is only re-sorted every few ticks (two barriers and one more pass over the records)
         const bool sorted = a.n_tiles > 0 && t % a.sort_every == 0;
+        if (a.algo == 3 && ng > 0) green_wave_prepass<true>(a, grid, tid, nth);
         // ---- 1: phase A of every live vehicle + light-group decisions (staged)
         int live = 0;
         for (int i = tid; i < n_live; i += nth) {

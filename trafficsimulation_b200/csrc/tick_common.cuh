@@ -145,6 +145,9 @@ __device__ __forceinline__ int group_controller(const TickArgs &a, int g) {
             for (int k = lt.g_ewout_off[g]; k < lt.g_ewout_off[g + 1]; k++) ew_p -= occ_at(lt.g_ewout[k]);
             const int ph = ns_p > ew_p ? 0 : 1;
             if (ph != cur && ph != pend) pend = ph;   // apply_phase :386-393
+        } else if (a.algo == 3) {   // run_neighbor_green_wave :522-546: the phase was settled for all groups by green_wave_prepass
+            const int ph = s.g_wave[g];
+            if (ph != cur && ph != pend) pend = ph;
         } else {             // run_fixed_time :427-441
             const int ft = ++s.g_ft_timer[g];
             if (ft == 1) { const int ph = s.g_ft_phase[g]; if (ph != cur && ph != pend) pend = ph; }
@@ -161,6 +164,65 @@ __device__ __forceinline__ int group_controller(const TickArgs &a, int g) {
     }
     s.g_cur[g] = cur; s.g_pend[g] = pend; s.g_plan[g] = plan;
     return plan;
+}
+
+// NEIGHBOR_GREEN_WAVE (intersection_light_group.py:522-546): a group follows the phase its neighbours hold -- and a neighbour that steps
+// EARLIER in the activation order (lower index) has already run its own step of this tick, commit included (:348-384).  That is a
+// recurrence along the activation order; it is triangular, so it has one solution, and Jacobi sweeps over all groups reach it: after
+// k sweeps every group whose chain of lower-ranked neighbours is shorter than k is final.  A sweep that changes nothing has read only
+// final values, so the phases it computed (g_wave[g]) are the sequential ones.  Runs before phase 1 of a tick, on the tick-start
+// occupancy; scratch: g_wave[0..ng) phase asked for (-1: a phase is pending, the controller does not run), [ng..2ng) phase held
+// after this tick's step, [2ng..3ng) bit 0 = ns queue longer, bit 1 = cluster occupied, [3ng..3ng+3) sweep flags in rotation.
+template <bool PROBE, class Grid>
+__device__ void green_wave_prepass(const TickArgs &a, Grid &grid, int tid, int nth) {
+    const tsim_light_tables &lt = a.lt;
+    const tsim_tick_state &s = a.st;
+    const int ng = lt.n_groups;
+    int32_t *ph = s.g_wave, *c1 = s.g_wave + ng, *qq = s.g_wave + 2 * ng, *flags = s.g_wave + 3 * ng;
+    for (int g = tid; g < ng; g += nth) {
+        int ns_q = 0, ew_q = 0;
+        bool occupied = false;
+        if (PROBE) {
+            occ_count_lanes(a, g, ns_q, ew_q);
+            occupied = occ_count(a, 2, a.gq_base_cl + lt.g_cl_off[g], g) != 0;
+        } else {
+            for (int k = lt.g_nsin_off[g]; k < lt.g_nsin_off[g + 1]; k++) ns_q += (int)s.occupancy[lt.g_nsin[k]];
+            for (int k = lt.g_ewin_off[g]; k < lt.g_ewin_off[g + 1]; k++) ew_q += (int)s.occupancy[lt.g_ewin[k]];
+            for (int k = lt.g_cl_off[g]; k < lt.g_cl_off[g + 1]; k++) occupied |= s.occupancy[lt.g_cl[k]] != 0;
+        }
+        qq[g] = (ns_q > ew_q ? 1 : 0) | (occupied ? 2 : 0);
+        c1[g] = s.g_cur[g];
+    }
+    if (tid == 0) { flags[0] = 0; flags[1] = 0; flags[2] = 0; }
+    grid.sync();
+    for (int iter = 0; iter <= ng + 1; iter++) {
+        int32_t *flag = flags + iter % 3;
+        bool changed = false;
+        for (int g = tid; g < ng; g += nth) {
+            const int cur0 = s.g_cur[g], pend0 = s.g_pend[g], q = qq[g];
+            int p = -1, pend = pend0;
+            if (pend0 < 0) {
+                bool favor_ns = false, favor_ew = false;
+#pragma unroll
+                for (int d = 0; d < 4; d++) {
+                    const int nb = lt.g_nbr[4 * g + d];
+                    if (nb < 0) continue;
+                    const int c = nb < g ? __ldcg(c1 + nb) : s.g_cur[nb];   // stepped before me this tick / steps after me
+                    if (d < 2 && c == 0) favor_ns = true;
+                    if (d >= 2 && c == 1) favor_ew = true;
+                }
+                p = (favor_ns && !favor_ew) ? 0 : (favor_ew && !favor_ns) ? 1 : ((q & 1) ? 0 : 1);
+                if (p != cur0) pend = p;   // apply_phase :386-393 (nothing is pending here)
+            }
+            const int held = (pend >= 0 && !(q & 2)) ? pend : cur0;   // _execute_phase_change :348-384
+            ph[g] = p;
+            if (held != __ldcg(c1 + g)) { c1[g] = held; changed = true; }
+        }
+        if (changed) *flag = 1;
+        if (tid == 0) flags[(iter + 1) % 3] = 0;   // written in the next sweep; last read two barriers ago
+        grid.sync();
+        if (!*((volatile int32_t *)flag)) break;
+    }
 }
 
 // light group: controller + decision; stop_map writes are staged in `stopw` (atomicMax, priority =

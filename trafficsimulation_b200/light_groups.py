@@ -148,3 +148,103 @@ def groups_as_cell_lists(tabs, lights):
                         ew_lights=np.sort(lights[sl("g_ew")]), ns_in=np.sort(sl("g_nsin")), ew_in=np.sort(sl("g_ewin")),
                         ns_out=np.sort(sl("g_nsout")), ew_out=np.sort(sl("g_ewout"))))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Neighbour links: IntersectionLightGroup.populate_links (intersection_light_group.py:175-242)
+# ---------------------------------------------------------------------------------------------------------------
+LINK_DIRS = ("N", "S", "E", "W")                      # Defaults.AVAILABLE_DIRECTIONS (config.py:62)
+_STEP = {"N": (0, 1), "S": (0, -1), "E": (1, 0), "W": (-1, 0)}
+
+
+def neighbor_links(W, H, cell_type, cluster_label, tabs, lights, hbands, vbands, creation_order=None, max_depth=1000):
+    """``neighbor_groups`` of every light group as an int32 table [n_groups, 4] (columns N, S, E, W; -1 = none).
+
+    Restates the ray marches of ``populate_links`` INCLUDING their order dependence: whether a group ``g`` "blocks all lanes" for
+    marches in direction ``d`` is computed once, by the first march that reaches it, at that march's hit cell, and cached on ``g``
+    (``_blocks_<d>``, :226-228).  The reference runs the marches twice: once inside every group's constructor (only groups created
+    earlier are visible then, :141 / city_model.py:1638-1650) and once more when ``get_opposite_traffic_lights`` finds the axis lists
+    still empty (:303-307) -- under the harness that second pass happens for all groups, in creation order, before the first tick.
+    Both passes are replayed here in ``creation_order`` (group indices; default: the canonical order of ``tabs``).  The reference
+    creates its groups in the iteration order of a Python set (city_model.py:1595), so exact parity for a city whose cached answers
+    depend on that order needs the reference's order as an input; `order_dependent` in the result says whether any answer did.
+
+    Host-side and sequential (a Python loop per march): meant for reference-sized cities.
+    """
+    T = np.asarray(cell_type).reshape(H, W)
+    L = np.asarray(cluster_label).reshape(H, W)
+    ng = int(tabs["n_groups"])
+    lights = np.asarray(lights, np.int64)
+    group_of_cluster = np.full(int(L.max()) + 1, -1, np.int64)
+    group_of_cluster[np.asarray(tabs["group_clusters"], np.int64) + 1] = np.arange(ng)
+    hb = [tuple(int(v) for v in b[:2]) for b in np.asarray(hbands).reshape(-1, 4)]
+    vb = [tuple(int(v) for v in b[:2]) for b in np.asarray(vbands).reshape(-1, 4)]
+
+    def band_or_single(idx, bands):                    # _find_band_covering (city_model.py:1269-1273): the first band that covers idx
+        for st, en in bands:
+            if st <= idx <= en:
+                return st, en
+        return idx, idx
+
+    inter = lambda x, y: T[y, x] == T_INTER
+
+    def blocks_all_lanes(ix, iy, d):                   # :185-205
+        if d in ("N", "S"):
+            vx0, vx1 = band_or_single(ix, vb)
+            if vx1 == vx0:
+                hy0, hy1 = band_or_single(iy, hb)
+                return bool(inter(vx0, iy) and (hy1 != hy0 or inter(ix, hy0)))
+            return bool(all(inter(xx, iy) for xx in range(vx0, vx1 + 1)))
+        hy0, hy1 = band_or_single(iy, hb)
+        if hy1 == hy0:
+            vx0, vx1 = band_or_single(ix, vb)
+            return bool(inter(ix, hy0) and (vx1 != vx0 or inter(vx0, iy)))
+        return bool(all(inter(ix, yy) for yy in range(hy0, hy1 + 1)))
+
+    diag = []
+    for g in range(ng):                                # :213-221, the group's lights in corner order
+        cells = []
+        for l in tabs["g_all"][tabs["g_all_off"][g]:tabs["g_all_off"][g + 1]]:
+            lx, ly = int(lights[l] % W), int(lights[l] // W)
+            for dx, dy in ((1, 1), (1, -1), (-1, 1), (-1, -1)):
+                nx, ny = lx + dx, ly + dy
+                if 0 <= nx < W and 0 <= ny < H and inter(nx, ny):
+                    cells.append((nx, ny))
+        diag.append(cells)
+
+    blocks, answers = {}, {}                           # (group, direction) -> cached answer / every answer any march would get
+
+    def march(me, visible):
+        nbr = {}
+        for cx, cy in diag[me]:
+            for d in LINK_DIRS:
+                sx, sy = _STEP[d]
+                x, y, steps = cx, cy, 0
+                while steps < max_depth:
+                    x, y = x + sx, y + sy
+                    if not (0 <= x < W and 0 <= y < H):
+                        break
+                    g = int(group_of_cluster[L[y, x]]) if inter(x, y) else -1
+                    if g < 0 or g == me or not visible[g]:
+                        steps += 1
+                        continue
+                    ans = blocks_all_lanes(x, y, d)
+                    answers.setdefault((g, d), set()).add(ans)
+                    if (g, d) not in blocks:
+                        blocks[(g, d)] = ans
+                    if blocks[(g, d)]:
+                        nbr[d] = g
+                        break
+                    steps += 1
+        return nbr
+
+    order = list(range(ng)) if creation_order is None else [int(g) for g in creation_order]
+    visible = np.zeros(ng, bool)
+    for g in order:                                    # pass 1: inside the constructors
+        march(g, visible)
+        visible[g] = True
+    table = np.full((ng, 4), -1, np.int32)
+    for g in order:                                    # pass 2: everybody visible, cached answers kept
+        for d, n in march(g, visible).items():
+            table[g, LINK_DIRS.index(d)] = n
+    return dict(nbr=table, order_dependent=any(len(v) > 1 for v in answers.values()))

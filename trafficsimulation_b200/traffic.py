@@ -24,11 +24,13 @@ _G32 = ("g_cur", "g_pend", "g_qt", "g_gap", "g_last", "g_ft_phase", "g_ft_timer"
 _LT = ("tl_off", "tl_cells", "g_all_off", "g_all", "g_ns_off", "g_ns", "g_ew_off", "g_ew",
        "g_nsin_off", "g_nsin", "g_ewin_off", "g_ewin", "g_cl_off", "g_cl")
 _LT_OUT = ("g_nsout_off", "g_nsout", "g_ewout_off", "g_ewout")   # PRESSURE_CONTROL only
-ALGOS = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2}   # Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM (config.py:341)
+ALGOS = {"QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2, "NEIGHBOR_GREEN_WAVE": 3}   # Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM (config.py:341)
 
 
-def light_tables_from_layout(city):
-    """Build the light-group tables for a generated ``GpuCityLayout`` (device labelling + host table work)."""
+def light_tables_from_layout(city, links=False, creation_order=None):
+    """Build the light-group tables for a generated ``GpuCityLayout`` (device labelling + host table work).
+    links: also the neighbour-link table ``g_nbr`` NEIGHBOR_GREEN_WAVE reads (``light_groups.neighbor_links``: host-side ray marches,
+    reference-sized cities); creation_order: the reference's group creation order if it is known (see there)."""
     W, H = city.width, city.height
     dev = city.device
     mask = ((city.aux & 0x40) != 0).to(torch.uint8)
@@ -50,11 +52,17 @@ def light_tables_from_layout(city):
     ctrl_off = t["ctrl_off"][: nl + 1].cpu().numpy()
     inc_off = t["inc_off"][: nl + 1].cpu().numpy()
     out_off = t["out_off"][: nl + 1].cpu().numpy() if "out_off" in t else None
-    return build_light_tables(
+    tabs = build_light_tables(
         W, H, planes["cell_type"], planes["dirs"], labels.cpu().numpy().reshape(H, W), blobs[: nc * 6].view(nc, 6).cpu().numpy(),
         t["light_cell"][:nl].cpu().numpy(), ctrl_off, t["ctrl_cell"][: int(ctrl_off[-1]) if nl else 0].cpu().numpy(),
         inc_off, t["inc_cell"][: int(inc_off[-1]) if nl else 0].cpu().numpy(),
         out_off, t["out_cell"][: int(out_off[-1]) if nl else 0].cpu().numpy() if out_off is not None else None)
+    if links:
+        from .light_groups import neighbor_links
+        lk = neighbor_links(W, H, planes["cell_type"], labels.cpu().numpy().reshape(H, W), tabs, t["light_cell"][:nl].cpu().numpy(),
+                            city.hbands, city.vbands, creation_order=creation_order)
+        tabs["g_nbr"], tabs["links_order_dependent"] = lk["nbr"], lk["order_dependent"]
+    return tabs
 
 
 class GpuTraffic:
@@ -79,8 +87,8 @@ class GpuTraffic:
         if algo not in ALGOS:
             raise ValueError(f"light controller {algo!r}: the device runs {sorted(ALGOS)}")
         self.algo = ALGOS[algo]
-        if self.algo == 2 and window is not None:
-            raise NotImplementedError("PRESSURE_CONTROL on a row-band shard: the cells that controller reads lie outside the shard's window")
+        if self.algo >= 2 and window is not None:
+            raise NotImplementedError(f"{algo} on a row-band shard: the cells / neighbour groups that controller reads lie outside the shard's window")
         self.win_y0, self.win_rows, self.win_halo = (0, self.H, 0) if window is None else (int(v) for v in window)
         self.cfg = _lib.Cfg(self.W, self.H, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, self.win_y0, self.win_rows, self.win_halo)
         n = self.W * self.win_rows
@@ -96,8 +104,13 @@ class GpuTraffic:
             light_tables = pressure_cells(light_tables, self.W)   # the cells the reference's controller really reads
         self.lt_t = {k: up(light_tables[k], np.int32) for k in _LT + (_LT_OUT if self.algo == 2 else ())}
         self.n_groups, self.n_lights = int(light_tables["n_groups"]), int(light_tables["n_lights"])
+        if self.algo == 3:
+            if "g_nbr" not in light_tables:
+                raise ValueError("NEIGHBOR_GREEN_WAVE needs the g_nbr link table (light_tables_from_layout(city, links=True))")
+            self.lt_t["g_nbr"] = up(np.asarray(light_tables["g_nbr"]).reshape(-1), np.int32)
         self.lt = _lib.LightTables(self.n_groups, self.n_lights, *[self.lt_t[k].data_ptr() for k in _LT],
-                                   *[(self.lt_t[k].data_ptr() if self.algo == 2 else 0) for k in _LT_OUT])
+                                   *[(self.lt_t[k].data_ptr() if self.algo == 2 else 0) for k in _LT_OUT],
+                                   self.lt_t["g_nbr"].data_ptr() if self.algo == 3 else 0)
         # ---- tapes
         spawn_tick = np.asarray(tapes["spawn_tick"], np.int32)
         ev_tick = np.asarray(tapes["ev_tick"], np.int32)
@@ -149,6 +162,8 @@ class GpuTraffic:
             nb = C.c_longlong(0)
             _lib.check(self.lib.tsim_tick_group_ws_bytes(C.byref(self.cfg), C.byref(self.lt), C.byref(nb)))
             s["group_ws"] = z((nb.value + 7) // 8, torch.int64)   # occupancy bit tiles + (tile, mask) lists of the light groups
+        if self.algo == 3:
+            s["g_wave"] = z(3 * self.n_groups + 4, torch.int32)   # scratch of the green-wave fixed point
         if window is not None and not self.live_list:
             s["live_idx"] = z(nv, torch.int32)   # a shard iterates the vehicles of its own window (rebuilt after every halo refresh)
         self.s = s
@@ -157,7 +172,7 @@ class GpuTraffic:
         self.st = _lib.TickState(*[s[k].data_ptr() for k in v1], *(own_rows or (0, 0)), *[(s[k].data_ptr() if self.live_list else 0) for k in v2],
                                  s["live_idx"].data_ptr() if "live_idx" in s else 0,
                                  s["sort_keys"].data_ptr() if self.live_list else 0, s["tile_ws"].data_ptr() if self.live_list else 0,
-                                 s["group_ws"].data_ptr() if self.live_list else 0)
+                                 s["group_ws"].data_ptr() if self.live_list else 0, s["g_wave"].data_ptr() if "g_wave" in s else 0)
         _lib.check(self.lib.tsim_tick_init(C.byref(self.cfg), C.byref(self.lt), C.byref(self.tp), C.byref(self.st), self._stream))
         self._ticks_run, self._exported_at = 0, -1
 
