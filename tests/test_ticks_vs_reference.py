@@ -15,13 +15,13 @@ CASES = [
     # sideswipe draws that fire (vehicle_base.py:567-605): collisions strand both vehicles for 600 ticks
     dict(seed=21, n_ticks=140, spawns_per_tick=12, malfunction_p=0.002, sideswipe_p=0.35),
     # the other controllers of IntersectionLightGroup.step (intersection_light_group.py:396-423)
-    dict(seed=12345, n_ticks=100, spawns_per_tick=6, malfunction_p=0.002, algo="FIXED_TIME"),
-    dict(seed=9, n_ticks=100, spawns_per_tick=8, malfunction_p=0.0, algo="PRESSURE_CONTROL"),
-    dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01, algo="PRESSURE_CONTROL",
+    # (short runs: the committed fixtures ticks_s31_fixed_time / s9_pressure / s14_pressure_fwd / s9_green_wave / s14_green_wave hold longer ones)
+    dict(seed=12345, n_ticks=60, spawns_per_tick=6, malfunction_p=0.002, algo="FIXED_TIME"),
+    dict(seed=9, n_ticks=60, spawns_per_tick=8, malfunction_p=0.0, algo="PRESSURE_CONTROL"),
+    dict(seed=14, n_ticks=60, spawns_per_tick=4, malfunction_p=0.01, algo="PRESSURE_CONTROL",
          layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True, forward_traffic_light_range=True)),
-    dict(seed=12345, n_ticks=100, spawns_per_tick=8, malfunction_p=0.0, algo="NEIGHBOR_GREEN_WAVE"),
-    dict(seed=9, n_ticks=100, spawns_per_tick=8, malfunction_p=0.002, algo="NEIGHBOR_GREEN_WAVE"),
-    dict(seed=14, n_ticks=80, spawns_per_tick=4, malfunction_p=0.01, algo="NEIGHBOR_GREEN_WAVE",
+    dict(seed=12345, n_ticks=60, spawns_per_tick=8, malfunction_p=0.0, algo="NEIGHBOR_GREEN_WAVE"),
+    dict(seed=14, n_ticks=60, spawns_per_tick=4, malfunction_p=0.01, algo="NEIGHBOR_GREEN_WAVE",
          layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
 ]
 ALGO = {None: 0, "QUEUE_ACTUATED": 0, "FIXED_TIME": 1, "PRESSURE_CONTROL": 2, "NEIGHBOR_GREEN_WAVE": 3}
