@@ -208,16 +208,27 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
     peak, peak_src = measured_peaks()
     ups = updates / (ms * 1e-3)
     log(f"  tick leg {size}: timed ticks done ({ms / max(ticks, 1):.4f} ms/tick)")
-    # end to end: one launch per tick with a host read of the tick counters after every tick
+    # end to end through GpuTraffic with HOST buffers: every tick its tape rows (speed, malfunction, rank of that tick) go up from pinned
+    # memory, one launch advances the tick, and the positions of all vehicles + the tick counters come back to the host
     sim2 = GpuTraffic(size, size, tabs, tp, n_ticks, device=dev)
     sim2.step(5)
     torch.cuda.synchronize()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_rows = {k: pin(tp[k][5:5 + e2e_ticks]) for k in ("speed", "malfunction", "rank")}
+    d_rows = {k: sim2.tt[k].reshape(-1, nv) for k in ("speed", "malfunction", "rank")}
+    h_pos = torch.empty(nv, dtype=torch.int32).pin_memory()
     e0 = sim2.counters()["vehicle_updates"]
     t0 = time.perf_counter()
-    for _ in range(e2e_ticks):
-        sim2.step(1, check=True)
+    for k in range(e2e_ticks):
+        for name in ("speed", "malfunction", "rank"):
+            d_rows[name][5 + k].copy_(h_rows[name][k], non_blocking=True)
+        sim2.step(1, check=False)
+        sim2.export()
+        h_pos.copy_(sim2.s["pos"][:nv], non_blocking=True)
+        sim2.counters()   # host read of the tick counters: synchronises
     t1 = time.perf_counter()
     e2e = (sim2.counters()["vehicle_updates"] - e0) / (t1 - t0)
+    e2e_h2d, e2e_d2h = nv * (1 + 1 + 4), nv * 4 + 16 * 4
     del sim2
     log(f"  tick leg {size}: end-to-end ticks done")
     # CPU port on the same tapes: timed on `cpu_ticks` ticks, then run on to the tick the device is at, where the WHOLE state --
@@ -248,7 +259,8 @@ def vehicle_bench(dev, n_ticks=200, size=2048, n_vehicles=100000, cpu_ticks=20, 
                        "groups": sim.n_groups, "lights": sim.n_lights},
             "ms_per_tick": ms / ticks, "vehicle_updates": updates,
             "fixed_point_iterations_per_tick": (c1["fixed_point_iterations"] - c0["fixed_point_iterations"]) / ticks,
-            "e2e": {"value": e2e, "unit": "agent-updates/s", "note": "one launch per tick + host read of the counters"},
+            "e2e": {"value": e2e, "unit": "agent-updates/s", "h2d_bytes_per_tick": e2e_h2d, "d2h_bytes_per_tick": e2e_d2h,
+                    "note": "per tick: that tick's speed / malfunction / rank tape rows up from pinned host memory, one launch, all vehicle positions + the tick counters down"},
             "roofline": {"bound": "hbm", "alg_bytes_per_update": 84, "alg_bytes_per_group_update": 104,
                          "achieved": round((updates * 84 + ticks * sim.n_groups * 104) / (ms * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
                          "frac": round((updates * 84 + ticks * sim.n_groups * 104) / (ms * 1e-3) / 1e9 / peak, 5), "peak_source": peak_src,

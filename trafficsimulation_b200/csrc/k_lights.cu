@@ -51,6 +51,7 @@ struct Bits {
     u64 *I, *R;               // Intersection / road-like-without-intersection
     u64 *fw, *bw;             // reachable from the pivot / reaches the pivot
     u64 *cr, *tl;             // ControlledRoad candidates / TrafficLight cells
+    u64 *lm;                  // cells of the reverse marches of the accepted candidates ("nb.light = tl", :1542), merged into aux after the evaluation
     int wp;                   // words per row
 };
 
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) lights_bits_kernel(int W, int H, const ui
     if (row_ok && q == 0) {
         const size_t o = (size_t)y * bp.wp + (s >> 2);
         bp.aN[o] = wN; bp.aE[o] = wE; bp.aS[o] = wS; bp.aW[o] = wW; bp.I[o] = wI; bp.R[o] = wR;
-        bp.fw[o] = 0ull; bp.bw[o] = 0ull; bp.tl[o] = 0ull;
+        bp.fw[o] = 0ull; bp.bw[o] = 0ull; bp.tl[o] = 0ull; bp.lm[o] = 0ull;
     }
     p_all = __reduce_min_sync(0xffffffffu, p_all);
     p_mid = __reduce_min_sync(0xffffffffu, p_mid);
@@ -834,17 +835,54 @@ __device__ __forceinline__ void or_byte(uint8_t *p, uint32_t bits) {
 __device__ __forceinline__ void apply_aux(const LightsCtx &L, int c, u64 r, uint8_t *A) {
     const int na = rec_nacc(r);
     if (na) {
+        // The march cells are MARKED in a bit-plane (L2-resident, and the cells of a march along a row share one or two words: one or
+        // two atomics instead of one per cell); aux_light_merge_kernel ORs the marks into the aux plane once all records are there.
+        // (As byte atomics on the aux plane itself this was the evaluation's top stall: 60 M read-modify-writes of DRAM sectors.)
         const uint32_t rd = L.D[c];
         const int cx = c % L.W, cy = c / L.W;
         for (int d = 0; d < dl_len(rd); d++) {
-            const int k = opp_of(dl_get(rd, d));
-            for (int s = 1; s <= rec_cnt(r, d); s++) {
-                const int sx = cx + s * dx_of(k), sy = cy + s * dy_of(k);
-                if (!L.bit(L.b.cr, sx, sy)) or_byte(A + L.at(sx, sy), AUX_LIGHT);
+            const int k = opp_of(dl_get(rd, d)), cnt = rec_cnt(r, d);
+            if (!cnt) continue;
+            if (dy_of(k) == 0) {
+                const int x0 = dx_of(k) > 0 ? cx + 1 : cx - cnt, x1 = x0 + cnt - 1;   // cnt <= 31: at most two words
+                u64 *row = L.b.lm + (size_t)cy * L.b.wp;
+                const int w0 = x0 >> 6, w1 = x1 >> 6;
+                const u64 m0 = ~0ull << (x0 & 63), m1 = ~0ull >> (63 - (x1 & 63));
+                if (w0 == w1) atomicOr(row + w0, m0 & m1);
+                else { atomicOr(row + w0, m0); atomicOr(row + w1, m1); }
+            } else {
+                const u64 bit = 1ull << (cx & 63);
+                for (int s = 1; s <= cnt; s++) atomicOr(L.b.lm + (size_t)(cy + s * dy_of(k)) * L.b.wp + (cx >> 6), bit);
             }
         }
     }
     A[c] = (uint8_t)((A[c] & (AUX_RING | AUX_EVER)) | (na ? AUX_LIGHT : 0) | L.T[c]);
+}
+
+// marks of the reverse marches -> AUX_LIGHT, except on candidates (a converted cell is a fresh CellAgent: it only carries the light of
+// its own record, written by apply_aux).  One thread per word of the plane: it owns the 64 aux bytes it may touch.
+__global__ void __launch_bounds__(256) aux_light_merge_kernel(int W, long long nw, int wp, const u64 *__restrict__ lm, const u64 *__restrict__ cr,
+                                                              uint8_t *__restrict__ A) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nw) return;
+    const u64 m = lm[i] & ~cr[i];
+    if (!m) return;
+    const uint32_t y = (uint32_t)i / (uint32_t)wp, wx = (uint32_t)i - y * (uint32_t)wp;   // word indices fit 32 bits
+    uint8_t *row = A + (size_t)y * W + (size_t)wx * 64;
+    if ((W & 15) == 0) {
+        auto spread = [](uint32_t b) { return (((b | (b << 7) | (b << 14) | (b << 21)) & 0x01010101u) * (uint32_t)AUX_LIGHT); };   // 4 bits -> AUX_LIGHT in 4 bytes
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t mm = (uint32_t)(m >> (16 * q)) & 0xffffu;
+            if (!mm) continue;
+            uint4 v = *reinterpret_cast<uint4 *>(row + 16 * q);
+            v.x |= spread(mm & 15u); v.y |= spread((mm >> 4) & 15u); v.z |= spread((mm >> 8) & 15u); v.w |= spread(mm >> 12);
+            *reinterpret_cast<uint4 *>(row + 16 * q) = v;
+        }
+    } else {
+        u64 rest = m;
+        while (rest) { const int b = __ffsll((long long)rest) - 1; rest &= rest - 1; row[b] |= AUX_LIGHT; }
+    }
 }
 
 __device__ __forceinline__ void mark_lights(const LightsCtx &L, int c, u64 r) {
@@ -1113,7 +1151,7 @@ static tsim_status lights_ws(const tsim_cfg *cfg, void *workspace, size_t ws_byt
     size_t o = 0;
     auto take = [&](size_t bytes) { char *q = w + o; o += (bytes + 255) & ~(size_t)255; return q; };
     L.scal = (int32_t *)take(64 * 4);
-    u64 **planes[] = {&L.bp.aN, &L.bp.aE, &L.bp.aS, &L.bp.aW, &L.bp.I, &L.bp.R, &L.bp.fw, &L.bp.bw, &L.bp.cr, &L.bp.tl};
+    u64 **planes[] = {&L.bp.aN, &L.bp.aE, &L.bp.aS, &L.bp.aW, &L.bp.I, &L.bp.R, &L.bp.fw, &L.bp.bw, &L.bp.cr, &L.bp.tl, &L.bp.lm};
     for (u64 **pl : planes) *pl = (u64 *)take((size_t)L.nw * 8);
     L.bp.wp = L.wp;
     L.rt.wpT = div_up(L.H, 64);
@@ -1362,6 +1400,10 @@ static tsim_status lights_finish_impl(const tsim_cfg *cfg, const tsim_planes *p,
         if ((st = lights_reach_impl(cfg, -1, nullptr, err_flag, workspace, ws_bytes, stream, n_pend2)) != TSIM_OK) return st;
         const int pgrid = div_up(ws.cap_pend, 128) < 148 * 4 ? div_up(ws.cap_pend, 128) : 148 * 4;
         lights_eval_kernel<2><<<pgrid, 128, 0, cs>>>(L, n_pend2, cr_cell, rec, p->aux, ws.pend2, nullptr, nullptr, ws.cap_pend);
+        TSIM_LAUNCH_CHECK();
+    }
+    if (what & 1) {   // every record is final: the marks of their reverse marches go into the aux plane
+        aux_light_merge_kernel<<<div_up(nw, 256), 256, 0, cs>>>(W, nw, wp, bp.lm, bp.cr, p->aux);
         TSIM_LAUNCH_CHECK();
     }
     if (!(what & 2)) return TSIM_OK;
