@@ -7,6 +7,7 @@
 // cell becomes the BlockEntrance.  Blocks are independent: an entrance never changes another
 // block's ring or its road contacts (BlockEntrance is neither in the region test nor in
 // _touches_road's type list).
+#include <cstdlib>
 #include "bitplane.cuh"
 
 namespace tsim {
@@ -290,10 +291,12 @@ __global__ void __launch_bounds__(256) entrances_rect_kernel(tsim_cfg c, uint8_t
 // cell (member of this block / a type _touches_road accepts / a type the road-level filter prefers), so
 // global memory is read once per tile cell; marks, run union-find, run lengths, the taped choice and the
 // median all work on the warp's shared-memory slice.
-constexpr int ENT_WCAP = 768;    // tile cells a warp can stage
-constexpr int ENT_LCAP = 384;    // marked (ring and road) cells of a tile
 constexpr int ENT_WARPS = 4;
 
+// ENT_WCAP: tile cells a warp can stage; ENT_LCAP: marked (ring and road) cells of a tile.  <768, 384>: 37 KB of shared memory per CTA, 6
+// CTAs per SM; <512, 256>: 25 KB, 9 CTAs per SM -- the kernel is a chain of short warp-wide phases and lives on warps in flight; a block
+// whose tile does not fit goes to the CTA kernel either way.
+template <int ENT_WCAP, int ENT_LCAP>
 __global__ void __launch_bounds__(32 * ENT_WARPS) entrances_warp_kernel(tsim_cfg c, uint8_t *T, uint16_t *D, uint8_t *A, int32_t *B,
                                                                         const int32_t *__restrict__ blobs, const int32_t *__restrict__ n_gen,
                                                                         const int32_t *__restrict__ gen_list, const int32_t *__restrict__ id_base,
@@ -489,8 +492,13 @@ extern "C" tsim_status tsim_layout_entrances(const tsim_cfg *cfg, const tsim_pla
     entrances_rect_kernel<<<rgrid, 256, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, ep, blobs->table, blobs->count, blobs->cap,
                                                  blobs->id_base, run_by_block, n_tape, entrances, n_gen, gen_list, err_flag);
     TSIM_LAUNCH_CHECK();
-    const int wgrid = div_up(blobs->cap, ENT_WARPS) < 148 * 6 ? div_up(blobs->cap, ENT_WARPS) : 148 * 6;   // 6 CTAs of 37 KB shared memory per SM
-    entrances_warp_kernel<<<wgrid, 32 * ENT_WARPS, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, n_gen, gen_list,
+    static int small_tiles = -1;
+    if (small_tiles < 0) { const char *e = getenv("TSIM_ENT_TILE"); small_tiles = (e && atoi(e) == 768) ? 0 : 1; }
+    const int per_sm = small_tiles ? 9 : 6;
+    const int wgrid = div_up(blobs->cap, ENT_WARPS) < 148 * per_sm ? div_up(blobs->cap, ENT_WARPS) : 148 * per_sm;
+    if (small_tiles) entrances_warp_kernel<512, 256><<<wgrid, 32 * ENT_WARPS, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, n_gen, gen_list,
+                                                            blobs->id_base, run_by_block, n_tape, entrances, n_big, big_list, err_flag);
+    else entrances_warp_kernel<768, 384><<<wgrid, 32 * ENT_WARPS, 0, cs>>>(*cfg, p->cell_type, p->dirs, p->aux, p->block_id, blobs->table, n_gen, gen_list,
                                                             blobs->id_base, run_by_block, n_tape, entrances, n_big, big_list, err_flag);
     TSIM_LAUNCH_CHECK();
     const int grid = blobs->cap < 148 * 6 ? blobs->cap : 148 * 6;
