@@ -170,6 +170,13 @@ static void check_sideswipe(vsim *s, int v, int fires) {
 static int decide(vsim *s, int v, int t) {
     const int nv = s->n_vehicles;
     s->early[v] = 0;
+    if (g_ev_of[v] >= 0) { /* the route this vehicle follows from this tick on: the re-plan the reference made in this step_decide
+        (:506-517, :454-504; a recorded tape only holds one for a vehicle that got past the early exits below, so where in
+        step_decide it is installed makes no difference to it), or the first route of a vehicle that spawned in the tick before
+        (trafficsimulation_b200/replan.py hands those over with the next tick's events); the tick's LAST event of the vehicle */
+        const int e = g_ev_of[v];
+        s->path_off[v] = (int32_t)s->ev_off[e]; s->path_len[v] = (int32_t)(s->ev_off[e + 1] - s->ev_off[e]);
+    }
     if (s->malfunction[v] || s->collision[v]) { /* _tick_stranded :552-565 */
         s->stranded[v]--;
         if (s->stranded[v] <= 0) { s->malfunction[v] = 0; s->collision[v] = 0; s->stranded[v] = 0; }
@@ -188,10 +195,6 @@ static int decide(vsim *s, int v, int t) {
     int sp = s->base_speed[v];
     if (s->rain_enabled && s->rain[s->pos[v]] == 1) { sp -= RAIN_REDUCTION; if (sp < 1) sp = 1; }
     s->cur_speed[v] = (int8_t)sp;
-    if (g_ev_of[v] >= 0) { /* replayed re-plan (:506-517, :454-504): the tick's LAST event of this vehicle */
-        const int e = g_ev_of[v];
-        s->path_off[v] = (int32_t)s->ev_off[e]; s->path_len[v] = (int32_t)(s->ev_off[e + 1] - s->ev_off[e]);
-    }
     /* _scan_ahead_for_obstacles :422-452 */
     int idx_stop = -1, idx_veh = -1, look = s->path_len[v] < AWARENESS ? s->path_len[v] : AWARENESS;
     for (int i = 0; i < look; i++) {

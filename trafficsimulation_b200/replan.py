@@ -1,0 +1,361 @@
+"""Route planning joined to the tick: the vehicles plan their own routes, no route tape.
+
+Mirrors the planner side of ``VehicleAgent`` (``Simulation/agents/vehicles/vehicle_base.py``):
+
+* ``_compute_path`` :143-167 (cooldown, the path cache shared by all vehicles, used at spawn time only),
+* ``_compute_path_internal`` :199-420 (phase 0: merge back onto the saved route while overtaking / detouring; phase 1: strict
+  avoidance; phase 2: soft obstacles; phase 3: contraflow bypass of a stranded vehicle on the next cell; phase 4: contraflow detour
+  when stuck for long),
+* ``_recompute_path_on_stuck`` :506-517 and ``_recompute_path_on_obstacle`` :454-504 (the two re-plan triggers of ``step_decide``
+  :616-663, with the cooldown and its stranded-blocker exception).
+
+How it is joined.  With ``PATHFINDING_BATCHING`` (config.py:411, the shipped setting) the reference runs every vehicle's
+``step_decide`` before anything moves (``run_parallel_decide``, city_model.py:1811-1829, then ``schedule.step()`` :1858): every
+re-plan of a tick reads the tick-START occupancy / stop / density maps and the vehicle's own state.  The re-plans of one tick are
+therefore independent of each other -- the one cross-vehicle read is ``blocker.is_stranded()``, which sees the blocker's state after
+ITS ``step_decide`` when the blocker is earlier in ``active_vehicle_agents`` (spawn order) and its tick-start state otherwise; both
+are functions of the tick-start state and the malfunction tape.  So a tick is: snapshot -> every vehicle's trigger logic as a
+coroutine that yields its A* queries -> the queries of all vehicles answered round by round as ONE ``tsim_astar_batch`` launch per
+round -> the new routes handed to the tick kernel as this tick's route events -> ``tsim_tick_run`` for one tick.  A vehicle that
+spawns plans on the maps as they are at that moment of the tick (after the moves, with the earlier spawns of the same tick on the
+grid, city_model.py:1897-1908 / vehicle_base.py:72-76) against the density map of the tick's start; its route reaches the device as
+an event of the next tick, before phase A.
+
+This module holds the state machine and the batching; the searches run on the device (``pathfinding.GpuAstar``), the tick on the
+device (``traffic.GpuTraffic(route_capacity=...)``).  There is no CPU fallback: both collaborators are handed in by the caller, and
+``PlannedTraffic.on_gpu`` builds the CUDA ones.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .pathfinding import IGNORE_FLOW, SOFT_OBSTACLES, UNBOUNDED
+
+# Defaults of Simulation/config.py the planner side reads (line numbers there)
+AWARENESS_RANGE = 10                 # VEHICLE_AWARENESS_RANGE :279
+OVERTAKE_STEPS = 6                   # VEHICLE_MAX_CONTRAFLOW_OVERTAKE_STEPS :302
+OVERTAKE_DURATION = 30               # VEHICLE_CONTRAFLOW_OVERTAKE_DURATION :304
+STUCK_RECOMPUTE = 30                 # VEHICLE_STUCK_RECOMPUTE_THRESHOLD :306
+STUCK_RECOMPUTE_INTERSECTION = 1     # VEHICLE_STUCK_RECOMPUTE_THRESHOLD_INTERSECTION :307
+STUCK_CONTRAFLOW = 60                # VEHICLE_STUCK_CONTRAFLOW_THRESHOLD :310
+STUCK_CONTRAFLOW_INTERSECTION = 10   # VEHICLE_STUCK_CONTRAFLOW_THRESHOLD_INTERSECTION :311
+DETOUR_STEPS = 20                    # VEHICLE_MAX_CONTRAFLOW_STUCK_DETOUR_STEPS :312
+DETOUR_DURATION = 10                 # VEHICLE_CONTRAFLOW_STUCK_DETOUR_DURATION :313
+COOLDOWN = 5                         # PATHFINDING_COOLDOWN :409
+
+
+class PlanState:
+    """The planner-side fields of one ``VehicleAgent`` (vehicle_base.py:43-56); cells are ``y * W + x``."""
+    __slots__ = ("v", "target", "path", "cooldown", "is_overtaking", "overtake_path", "pre_overtake_path", "overtaking_duration",
+                 "is_in_stuck_detour", "stuck_detour_path", "pre_stuck_detour_path", "stuck_detour_duration", "pos", "stuck_ticks",
+                 "planned")
+
+    def __init__(self, v, target):
+        self.v, self.target = v, target
+        self.path = []
+        self.cooldown = 0
+        self.is_overtaking, self.overtake_path, self.pre_overtake_path, self.overtaking_duration = False, [], [], -1
+        self.is_in_stuck_detour, self.stuck_detour_path, self.pre_stuck_detour_path, self.stuck_detour_duration = False, [], [], -1
+        self.pos, self.stuck_ticks, self.planned = -1, 0, False
+
+
+class _View:
+    """What a vehicle's trigger logic may read of the city at the moment it runs."""
+    __slots__ = ("occ", "stop", "inter", "veh_at", "stranded_of")
+
+    def __init__(self, occ, stop, inter, veh_at, stranded_of):
+        self.occ, self.stop, self.inter, self.veh_at, self.stranded_of = occ, stop, inter, veh_at, stranded_of
+
+
+def _first_free(cells, occ):
+    for i, c in enumerate(cells):
+        if occ[c] == 0:
+            return i
+    return None
+
+
+def scan_ahead(path, occ, stop):
+    """``_scan_ahead_for_obstacles`` :422-452: indices of the first stop cell / occupied cell among the next cells of the route."""
+    idx_stop = idx_vehicle = None
+    for i in range(min(AWARENESS_RANGE, len(path))):
+        c = path[i]
+        if idx_stop is None and stop[c] == 1:
+            idx_stop = i
+        if idx_vehicle is None and occ[c] == 1:
+            idx_vehicle = i
+        if idx_stop == 0 or idx_vehicle == 0:
+            break
+    return idx_stop, idx_vehicle
+
+
+def compute_path_internal(s, view):
+    """``_compute_path_internal`` :199-420 as a coroutine: yields ``(start, goal, flags, maximum_steps)``, is sent the path."""
+    occ, stop = view.occ, view.stop
+    pos, goal = s.pos, s.target
+    # phase 0: back onto the saved route while overtaking / detouring (:218-274)
+    for overtaking in (True, False):
+        active, saved = (s.is_overtaking, s.pre_overtake_path) if overtaking else (s.is_in_stuck_detour, s.pre_stuck_detour_path)
+        if active and saved:
+            merge = _first_free(saved, occ)
+            if merge is not None:
+                b = saved[merge]
+                bypass = yield (pos, b, IGNORE_FLOW, OVERTAKE_STEPS)
+                if bypass and bypass[-1] == b:
+                    if overtaking:
+                        s.overtake_path = bypass
+                    else:
+                        s.stuck_detour_path = bypass
+                    return bypass + saved[merge + 1:]
+    # phase 1: strict avoidance, phase 2: soft obstacles (:276-303)
+    path = yield (pos, goal, 0, UNBOUNDED)
+    if not path:
+        path = yield (pos, goal, SOFT_OBSTACLES, UNBOUNDED)
+    # phase 3: contraflow bypass of a stranded / parked vehicle on the next cell (:305-364)
+    if path:
+        idx_stop = idx_vehicle = None
+        for i in range(min(AWARENESS_RANGE, len(path))):
+            c = path[i]
+            if idx_stop is None and stop[c] == 1:
+                idx_stop = i
+            if idx_vehicle is None and occ[c] == 1:
+                idx_vehicle = i
+            if idx_stop is not None and idx_vehicle is not None:
+                break
+        if idx_vehicle == 0:
+            blocker = view.veh_at.get(path[0])
+            if blocker is not None and view.stranded_of(blocker, s.v):
+                k = _first_free(path, occ)
+                if k is not None:
+                    b = path[k]
+                    bypass = yield (pos, b, IGNORE_FLOW, OVERTAKE_STEPS)
+                    if bypass and bypass[-1] == b and len(bypass) > 1:
+                        idx_bp = path.index(b)
+                        s.pre_overtake_path, s.overtake_path = path, bypass
+                        s.is_overtaking, s.overtaking_duration = True, 0
+                        return bypass + path[idx_bp + 1:]
+    # phase 4: contraflow detour when stuck for long (:366-418)
+    if path:
+        threshold = STUCK_CONTRAFLOW_INTERSECTION if view.inter[pos] else STUCK_CONTRAFLOW
+        if s.stuck_ticks >= threshold:
+            k = _first_free(path, occ)
+            if k is not None:
+                b = path[k]
+                bypass = yield (pos, b, SOFT_OBSTACLES | IGNORE_FLOW, DETOUR_STEPS)
+                if bypass and bypass[-1] == b and len(bypass) > 1:
+                    merge = path.index(b)
+                    s.pre_stuck_detour_path, s.stuck_detour_path = list(path), bypass
+                    s.is_in_stuck_detour, s.stuck_detour_duration = True, 0
+                    return bypass + path[merge + 1:]
+            return path
+    return path
+
+
+def compute_path(s, view, cache=None):
+    """``_compute_path`` :143-167.  ``cache``: the model-wide ``_path_cache`` dict (consulted when given: at spawn time)."""
+    s.cooldown = COOLDOWN
+    s.planned = True
+    key = (s.pos, s.target)
+    if cache is not None and key in cache:
+        return list(cache[key])
+    path = yield from compute_path_internal(s, view)
+    if cache is not None and path and not s.is_overtaking and not s.is_in_stuck_detour:
+        cache[key] = list(path)
+    return path
+
+
+def decide_replans(s, view):
+    """The planner side of ``step_decide`` :645-649 for a vehicle that got past its early exits."""
+    # _recompute_path_on_stuck :506-517
+    thresh = STUCK_RECOMPUTE_INTERSECTION if view.inter[s.pos] else STUCK_RECOMPUTE
+    if s.stuck_ticks >= thresh:
+        s.path = yield from compute_path(s, view)
+    # _recompute_path_on_obstacle :454-504
+    if s.is_overtaking and (not s.overtake_path or s.pos not in s.overtake_path):
+        s.overtake_path, s.is_overtaking = None, False
+    if s.is_in_stuck_detour and (not s.stuck_detour_path or s.pos not in s.stuck_detour_path):
+        s.stuck_detour_path, s.is_in_stuck_detour = None, False
+    idx_stop, idx_vehicle = scan_ahead(s.path, view.occ, view.stop)
+    if s.is_overtaking:
+        s.overtaking_duration += 1
+        if s.overtaking_duration <= OVERTAKE_DURATION:
+            return
+    if s.is_in_stuck_detour:
+        s.stuck_detour_duration += 1
+        if s.stuck_detour_duration <= DETOUR_DURATION:
+            return
+    if s.cooldown > 0:
+        hard_block = False
+        if idx_vehicle == 0:
+            blocker = view.veh_at.get(s.path[0])
+            hard_block = blocker is not None and view.stranded_of(blocker, s.v)
+        if not hard_block:
+            s.cooldown -= 1
+            return
+    if idx_stop is not None or idx_vehicle is not None:
+        path = yield from compute_path(s, view)
+        if path:
+            s.path = path
+
+
+def run_coroutines(jobs, answer):
+    """Drive coroutines that yield A* queries: every round, the pending queries of all of them go to ``answer(list of queries)``
+    (one batch launch) and each coroutine is resumed with its path.  ``jobs``: list of generators; returns their return values."""
+    results = [None] * len(jobs)
+    pending = []
+    for i, g in enumerate(jobs):
+        try:
+            pending.append((i, g, next(g)))
+        except StopIteration as e:
+            results[i] = e.value
+    while pending:
+        paths = answer([q for _, _, q in pending])
+        nxt = []
+        for (i, g, _), p in zip(pending, paths):
+            try:
+                nxt.append((i, g, g.send(p)))
+            except StopIteration as e:
+                results[i] = e.value
+        pending = nxt
+    return results
+
+
+class PlannedTraffic:
+    """The tick with the vehicles' own route planning: ``CityModel.step()`` (city_model.py:1831-1860) without a route tape.
+
+    traffic: a ``GpuTraffic`` built with ``route_capacity=`` (``plan_snapshot()``, ``push_route_events()``, ``step()``);
+    planner: a ``GpuAstar`` on the same city (``update``, ``update_density``, ``plan_cells``); ``on_gpu`` builds both.
+    tapes: the malfunction tape ``[T, V]`` and the spawn targets (the rest of the tapes is the tick kernel's business).
+    """
+
+    def __init__(self, traffic, planner, width, height, intersection_map, tapes):
+        self.traffic, self.planner = traffic, planner
+        self.W, self.H = int(width), int(height)
+        self.inter = np.ascontiguousarray(intersection_map, np.uint8).reshape(-1)
+        self.target = np.asarray(tapes["target"], np.int64)
+        self.malfunction = np.asarray(tapes["malfunction"])
+        if (self.malfunction & 2).any():
+            raise NotImplementedError("a firing sideswipe draw (tape bit 1) changes who is stranded in the middle of phase A; "
+                                      "the planner loop takes tapes without it")
+        self.veh = {}                 # live vehicle -> PlanState
+        self.cache = {}               # CityModel._path_cache
+        self.pending = {}             # vehicle -> route to hand to the device with the next tick's events
+        self.tick = 0
+        self.events = []              # (tick, vehicle, cells) in the reference's order: what a route tape of this run would hold
+        self.searches = 0             # A* queries answered
+        self.batches = 0              # planner launches
+        self.compactions = 0          # times the route buffer was started again
+        self._snap = None
+
+    @classmethod
+    def on_gpu(cls, width, height, light_tables, tapes, n_ticks, maps, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0",
+               route_cells=None):
+        """Both collaborators on the device.  maps: the city's simple maps (``GpuCityLayout.maps_host()`` or device planes):
+        is_road_map, road_type_map, intersection_map, allowed_dirs_map."""
+        from .pathfinding import GpuAstar
+        from .traffic import GpuTraffic
+        nv = len(tapes["spawn_tick"])
+        cells = int(route_cells or max(1 << 22, 64 * nv * 8))
+        traffic = GpuTraffic(width, height, light_tables, tapes, n_ticks, algo=algo, rain_enabled=rain_enabled, device=device,
+                             route_capacity=cells)
+        zero = np.zeros((height, width), np.uint8)
+        planner = GpuAstar(width, height, zero, zero, maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"], device=device)
+        inter = maps["intersection_map"]
+        inter = inter.cpu().numpy() if hasattr(inter, "cpu") else inter
+        return cls(traffic, planner, width, height, inter, tapes)
+
+    # ---- A* batches
+    def _answer(self, queries):
+        q = np.array([[a % self.W, a // self.W, b % self.W, b // self.W, fl, AWARENESS_RANGE, ms] for a, b, fl, ms in queries], np.int32)
+        self.searches += len(q)
+        self.batches += 1
+        return [p.tolist() for p in self.planner.plan_cells(q)]
+
+    # ---- one tick
+    def step(self, n=1):
+        for _ in range(int(n)):
+            self._step_one()
+
+    def _step_one(self):
+        t = self.tick
+        if self._snap is None:
+            if t != 0 or self.veh:
+                raise RuntimeError("PlannedTraffic drives its GpuTraffic from tick 0 on")
+            n = self.W * self.H   # nothing has run yet: an empty city (no vehicle reads its stop_map before the first tick has run)
+            self._snap = dict(occupancy=np.zeros(n, np.uint8), stop_map=np.zeros(n, np.uint8))
+        snap = self._snap
+        occ, stop = snap["occupancy"], snap["stop_map"]
+        # CityModel._update_density_map :1764-1778, from the tick-start occupancy; it also serves the spawns of this tick
+        self.planner.update(occupancy_map=occ.reshape(self.H, self.W), stop_map=stop.reshape(self.H, self.W))
+        self.planner.update_density()
+        live = sorted(self.veh)
+        if live:
+            lv = np.array(live)
+            start_stranded = dict(zip(live, (snap["stranded_flag"][lv] != 0).tolist()))
+            left = dict(zip(live, snap["stranded"][lv].tolist()))
+            draw = dict(zip(live, (self.malfunction[t, lv] & 1).astype(bool).tolist()))
+            # who is stranded once its own step_decide has run (_tick_stranded :552-565, _check_malfunction :608-610)
+            post_stranded = {v: ((start_stranded[v] and left[v] - 1 > 0) or draw[v]) for v in live}
+            veh_at = {self.veh[v].pos: v for v in live}
+            view = _View(occ, stop, self.inter, veh_at, lambda u, me: post_stranded[u] if u < me else start_stranded[u])
+            jobs, who = [], []
+            for v in live:
+                s = self.veh[v]
+                s.planned = False
+                if post_stranded[v] or stop[s.pos] == 1:     # early exits of step_decide :620-643
+                    continue
+                jobs.append(decide_replans(s, view))
+                who.append(v)
+            run_coroutines(jobs, self._answer)
+            for v in who:
+                if self.veh[v].planned:
+                    self.events.append((t, v, list(self.veh[v].path)))
+                    self.pending[v] = self.veh[v].path
+        # ---- the tick itself, with this tick's routes
+        vs = sorted(self.pending)
+        if sum(len(self.pending[v]) for v in vs) > self.traffic.route_room():
+            # the append-only route buffer is full: start it again with the remaining route of every live vehicle (a route event
+            # that repeats the route a vehicle already follows changes nothing)
+            vs = sorted(self.veh)
+            self.traffic.push_route_events(vs, [self.veh[v].path for v in vs], compact=True)
+            self.compactions += 1
+        else:
+            self.traffic.push_route_events(vs, [self.pending[v] for v in vs])
+        self.pending = {}
+        self.traffic.step(1)
+        self.tick = t + 1
+        snap = self._snap = self.traffic.plan_snapshot()
+        alive = snap["alive"]
+        # ---- routes advance by what the vehicles moved; the arrived are gone
+        for v in live:
+            s = self.veh[v]
+            if not alive[v]:
+                del self.veh[v]
+                continue
+            moved = len(s.path) - int(snap["path_len"][v])
+            if moved < 0 or moved > 5 or (moved and s.path[moved - 1] != snap["pos"][v]):
+                raise RuntimeError(f"tick {t}: vehicle {v} left its route (host route of {len(s.path)} cells, device {int(snap['path_len'][v])})")
+            if moved:
+                del s.path[:moved]
+            s.pos, s.stuck_ticks = int(snap["pos"][v]), int(snap["stuck_ticks"][v])
+        # ---- the spawns of this tick plan their first route (VehicleAgent.__init__ :72-76), one after the other: a later spawn of
+        # the same tick is not on the grid yet when an earlier one plans
+        born = [int(v) for v in np.flatnonzero(alive) if int(v) not in self.veh]
+        if born:
+            occ2, stop2 = snap["occupancy"], snap["stop_map"]
+            stranded_now = snap["stranded_flag"]
+            veh_at = {int(snap["pos"][v]): v for v in list(self.veh) + born}
+            for i, v in enumerate(born):
+                s = PlanState(v, int(self.target[v]))
+                s.pos = int(snap["pos"][v])
+                later = [int(snap["pos"][u]) for u in born[i + 1:]]
+                o = occ2
+                if later:
+                    o = occ2.copy()
+                    o[later] = 0
+                self.planner.update(occupancy_map=o.reshape(self.H, self.W), stop_map=stop2.reshape(self.H, self.W))
+                at = veh_at if not later else {c: u for c, u in veh_at.items() if c not in later}
+                view = _View(o, stop2, self.inter, at, lambda u, me: bool(stranded_now[u]))
+                s.path = run_coroutines([compute_path(s, view, self.cache)], self._answer)[0] or []
+                self.veh[v] = s
+                self.events.append((t, v, list(s.path)))
+                self.pending[v] = s.path

@@ -73,8 +73,10 @@ class GpuTraffic:
     """
 
     def __init__(self, width, height, light_tables, tapes, n_ticks, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0",
-                 window=None, own_rows=None, live_list=None):
-        """window = (win_y0, win_rows, win_halo): this object is one row-band shard (``ShardedTraffic`` builds those);
+                 window=None, own_rows=None, live_list=None, route_capacity=None):
+        """route_capacity: number of route cells the event buffer holds; the tapes then carry NO route events (`ev_*` ignored) and the
+        caller hands every tick's routes over with ``push_route_events`` before it runs the tick (``replan.PlannedTraffic``).
+        window = (win_y0, win_rows, win_halo): this object is one row-band shard (``ShardedTraffic`` builds those);
         every cell index in `light_tables` / `tapes` is then local to the window, cells outside it are -2;
         own_rows = (lo, hi): local rows the shard owns (the update counter skips the ghosts on the other rows).
         live_list: run the live-list kernel (k_tick2.cu: compacted vehicle records, one probe word per cell); default: yes
@@ -113,6 +115,13 @@ class GpuTraffic:
                                    self.lt_t["g_nbr"].data_ptr() if self.algo == 3 else 0)
         # ---- tapes
         spawn_tick = np.asarray(tapes["spawn_tick"], np.int32)
+        self.route_capacity = None if route_capacity is None else int(route_capacity)
+        if self.route_capacity is not None:
+            if window is not None:
+                raise NotImplementedError("pushed route events on a row-band shard")
+            ne = len(spawn_tick)   # at most one event per vehicle and tick; the cell buffer is append-only (live routes point into it)
+            tapes = dict(tapes, ev_tick=np.zeros(0, np.int32), ev_vehicle=np.zeros(0, np.int32), ev_off=np.zeros(1, np.int64),
+                         ev_cells=np.zeros(0, np.int32))
         ev_tick = np.asarray(tapes["ev_tick"], np.int32)
         if np.any(np.diff(spawn_tick) < 0) or np.any(np.diff(ev_tick) < 0):
             raise ValueError("spawn attempts and route events must be sorted by tick")
@@ -128,6 +137,12 @@ class GpuTraffic:
         tt["ev_off"] = up(tapes["ev_off"], np.int64)
         ev = tapes["ev_cells"]   # one spare entry at the end: the kernel may form the address of path[len]
         tt["ev_cells"] = up(ev, np.int32) if isinstance(ev, torch.Tensor) else up(np.append(np.asarray(ev, np.int32), 0), np.int32)
+        if self.route_capacity is not None:   # room for the pushed events: every tick's events are written at the front of ev_vehicle / ev_off
+            tt["ev_first"] = torch.zeros(n_ticks + 2, dtype=torch.int32, device=dev)
+            tt["ev_vehicle"] = torch.zeros(max(ne, 1), dtype=torch.int32, device=dev)
+            tt["ev_off"] = torch.zeros(max(ne, 1) + 1, dtype=torch.int64, device=dev)
+            tt["ev_cells"] = torch.zeros(self.route_capacity + 1, dtype=torch.int32, device=dev)
+            self._route_used = 0
         rain = tapes.get("rain_map") if rain_enabled else None
         tt["rain_map"] = up(np.asarray(rain).reshape(-1), np.uint8) if rain is not None else None
         self.tt = tt
@@ -206,6 +221,53 @@ class GpuTraffic:
     @property
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def route_room(self):
+        """Free cells of the route buffer (routes are appended: a live vehicle's route stays where it was written)."""
+        return self.route_capacity - self._route_used
+
+    def push_route_events(self, vehicles, paths, compact=False):
+        """Routes for the NEXT tick to run: ``vehicles[i]`` follows ``paths[i]`` (cell indices, first step first; may be empty) from
+        phase A of that tick on -- a live vehicle's re-plan, or the first route of a vehicle that spawned in the tick before.
+        compact: the caller hands over the remaining route of EVERY live vehicle, so the buffer starts again at its front."""
+        if self.route_capacity is None:
+            raise RuntimeError("push_route_events needs GpuTraffic(route_capacity=...)")
+        if compact:
+            self._route_used = 0
+        t = self._ticks_run
+        if t >= self.n_ticks:
+            raise ValueError(f"tick {t} is past the end of the tapes ({self.n_ticks} ticks)")
+        n = len(vehicles)
+        if n != len(paths) or n > self.nv or len(set(int(v) for v in vehicles)) != n:
+            raise ValueError("one route per vehicle and tick")
+        lens = np.array([len(p) for p in paths], np.int64)
+        off = np.zeros(n + 1, np.int64)
+        off[1:] = np.cumsum(lens)
+        total = int(off[-1])
+        if self._route_used + total > self.route_capacity:
+            raise _lib.TsimError(6, f"route buffer full: {self._route_used} + {total} cells > route_capacity {self.route_capacity}")
+        if n:
+            veh = np.asarray(vehicles, np.int32)
+            cells = np.concatenate([np.asarray(p, np.int32) for p in paths]) if total else np.zeros(0, np.int32)
+            if veh.min() < 0 or veh.max() >= self.nv or (total and (cells.min() < 0 or cells.max() >= self.W * self.win_rows)):
+                raise ValueError("route event outside the fleet / the grid")
+            self.tt["ev_vehicle"][:n] = torch.from_numpy(veh).to(self.device)
+            self.tt["ev_off"][: n + 1] = torch.from_numpy(off + self._route_used).to(self.device)
+            if total:
+                self.tt["ev_cells"][self._route_used: self._route_used + total] = torch.from_numpy(cells).to(self.device)
+            self._route_used += total
+        first = self.tt["ev_first"]
+        first[t] = 0
+        first[t + 1:] = n        # the events of tick t are entries [0, n); nothing is queued for the ticks after it yet
+
+    def plan_snapshot(self):
+        """What the route planner reads between two ticks (host arrays): the public maps and, per vehicle, alive / pos / path_len /
+        stuck_ticks / stranded (ticks left) / stranded_flag (is_in_malfunction or is_in_collision)."""
+        self.export()
+        s = self.s
+        g = lambda k: s[k][: max(self.nv, 1)].cpu().numpy()[: self.nv]
+        return dict(occupancy=s["occupancy"].cpu().numpy(), stop_map=s["stop_map"].cpu().numpy(), alive=g("alive") == 1, pos=g("pos"),
+                    path_len=g("path_len"), stuck_ticks=g("stuck_ticks"), stranded=g("stranded"), stranded_flag=g("malfunction") != 0)
 
     def export(self):
         """Live-list kernel: bring the public maps and the vehicle SoA up to date (a tick itself only moves records and probe bytes)."""
