@@ -426,6 +426,7 @@ LEGS = {
     "tick100k": lambda dev: vehicle_bench(dev),
     "tick1m": lambda dev: vehicle_bench(dev, n_ticks=60, size=8192, n_vehicles=1000000, cpu_ticks=0, route_len=100, e2e_ticks=20),
     "routes": lambda dev: route_planning_leg(dev),
+    "planned": lambda dev: planned_trips_leg(dev),
 }
 
 
@@ -491,6 +492,61 @@ def route_planning_leg(dev, n_queries=16384):
             "note": "host wall time: queries up, paths back on the host",
             "cpu_baseline": {"value": ns / cpu, "unit": "routes/s", "cores": 1, "kind": "port", "sample": f"{ns} of the same queries, oracle/astar_oracle.c"},
             "sample_matches_oracle": bool(same)}
+
+
+def planned_trips_leg(dev, trips_per_tick=20, n_ticks=100, seed=1):
+    """BASELINE.json configs[3] in the form it is named -- trips injected every tick on the reference's default city, NO route tape:
+    the vehicles plan and re-plan their own routes (trafficsimulation_b200/replan.py: the re-plan triggers and the four-phase planner
+    of vehicle_base.py:143-517, the searches as tsim_astar_batch launches, the tick as tsim_tick_run) -- bounded to `n_ticks` ticks.
+    The city is the one of the committed reference fixture tests/golden/ticks_default12345.npz, built on the device from its tapes.
+    Parity: the same loop with the C oracles behind the device interfaces must leave the same routes and the same final state."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import load_ticks
+    from planning_backends import OracleTrafficBackend, OraclePlannerBackend
+    from trafficsimulation_b200 import tapes
+    from trafficsimulation_b200.layout import GpuCityLayout
+    from trafficsimulation_b200.replan import PlannedTraffic
+    from trafficsimulation_b200.traffic import light_tables_from_layout
+    r = load_ticks(os.path.join(ROOT, "tests", "golden", "ticks_default12345.npz"))
+    W, H = r["W"], r["H"]
+    cfgd = dict(r["meta"]["cfg"])
+    carve = cfgd.pop("carve_subblock_roads", False)
+    city = GpuCityLayout(carve_subblock_roads=carve, **cfgd)
+    city.set_bands(r["hbands"], r["vbands"])
+    city.generate(r["tape_zone"], r["tape_carve"], r["tape_entrance"])
+    tabs = light_tables_from_layout(city)
+    maps, planes = city.maps_host(), city.planes_host()
+    tp = tapes.synth_planned_trips(seed, W, H, planes["cell_type"], trips_per_tick, n_ticks, malfunction_p=0.002)
+    sim = PlannedTraffic.on_gpu(W, H, tabs, tp, n_ticks, maps, device=str(dev))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim.step(n_ticks)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    got = sim.traffic.state_host()
+    updates = sim.traffic.counters()["vehicle_updates"]
+    log(f"planned trips: {n_ticks} ticks in {wall:.1f} s, {sim.searches} searches in {sim.batches} batches")
+    # the same loop on the CPU oracles: checker and baseline
+    ora = PlannedTraffic(OracleTrafficBackend(W, H, tabs, tp, n_ticks, route_capacity=1 << 24),
+                         OraclePlannerBackend(W, H, maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"]), W, H, maps["intersection_map"], tp)
+    t0 = time.perf_counter()
+    ora.step(n_ticks)
+    cpu = time.perf_counter() - t0
+    want = ora.traffic.state_host()
+    same = sim.events == ora.events and all(np.array_equal(got[k], want[k]) for k in ("pos", "base_speed", "stuck_ticks", "vflags", "occ", "stop", "stuckmap", "groups"))
+    return {"metric": "agent-updates/s with the vehicles planning their own routes (no route tape)", "value": updates / wall, "unit": "agent-updates/s",
+            "ms_per_tick": wall / n_ticks * 1e3, "routes_per_s": sim.searches / wall,
+            "config": {"workload": f"default {W}x{H} city, {trips_per_tick} trips injected per tick for {n_ticks} ticks, every route planned on the device "
+                                   "(re-plan triggers + four-phase planner of vehicle_base.py:143-517), malfunction chance 0.002",
+                       "trips": int(len(tp["spawn_tick"])), "spawned": int(len({v for _, v, _ in sim.events})), "live_at_end": int((got["pos"] >= 0).sum()),
+                       "searches": int(sim.searches), "planner_launch_rounds": int(sim.batches), "routes_planned": int(len(sim.events)),
+                       "route_buffer_compactions": int(sim.compactions)},
+            "note": "host-orchestrated: per tick one state snapshot to the host, the trigger logic in Python, one tsim_astar_batch launch per round "
+                    "of pending searches, one tsim_tick_run launch; wall time",
+            "cpu_baseline": {"value": updates / cpu, "unit": "agent-updates/s", "cores": 1, "kind": "port",
+                             "sample": f"the same {n_ticks} ticks: tick oracle + A* oracle behind the same loop, {cpu:.1f} s"},
+            "parity_checked": bool(same)}
 
 
 def capture_or_none(city, fn):
@@ -795,7 +851,8 @@ def ours(args):
             log("4096 leg done")
             # the legs beside the headline run in processes of their own with a time limit each: a leg that fails, hangs or
             # crawls on a slow host costs its own entry, never the line (the parent keeps its device memory meanwhile)
-            for key, leg, limit_s in (() if args.no_legs else (("vehicle_step", "tick100k", 150), ("vehicle_step_1M", "tick1m", 240), ("route_planning", "routes", 90))):
+            for key, leg, limit_s in (() if args.no_legs else (("vehicle_step", "tick100k", 150), ("vehicle_step_1M", "tick1m", 240), ("route_planning", "routes", 90),
+                                                                    ("planned_trips", "planned", 150))):
                 line[key] = run_leg(leg, limit_s)
                 log(f"leg {leg} done" + (f": {line[key]['error']}" if isinstance(line[key], dict) and "error" in line[key] else ""))
             line["cpu_baseline"] = {"value": cpu_val, "unit": "cells/s", "cores": 1, "kind": "port",

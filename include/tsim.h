@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TSIM_ABI_VERSION 4
+#define TSIM_ABI_VERSION 5
 
 /* cell_type codes = index into Defaults.ZONES (Simulation/config.py:74-95) */
 enum tsim_cell_type {
@@ -446,6 +446,10 @@ tsim_status tsim_tick_unpack(const tsim_cfg *cfg, const tsim_tick_tapes *tp, con
 typedef struct tsim_astar_maps {      /* device pointers, [height][width], values as in city_model.py:109-115 */
     const uint8_t *occupancy, *stop_map, *is_road_map, *road_type_map, *allowed_dirs_map;
     const double *density_map;        /* NULL = 0 everywhere (it only scales the soft vehicle penalty) */
+    const uint8_t *spawn_rank;        /* NULL, or per cell: 0 = whoever stands there was on the grid before this tick's spawner ran,
+                                         k in 1..127 = the k-th vehicle the spawner placed this tick stands there (127: that one or a
+                                         later one).  The spawns of a tick plan one after the other (VehicleAgent.__init__,
+                                         vehicle_base.py:72-76, inside dynamic_traffic_generator.py's loop): see spawn_rank_limit */
 } tsim_astar_maps;
 
 #define TSIM_ASTAR_RESPECT_AWARENESS 1
@@ -457,7 +461,8 @@ typedef struct tsim_astar_query {
     int32_t flags;                    /* TSIM_ASTAR_* */
     int32_t awareness_range;          /* Defaults.VEHICLE_AWARENESS_RANGE = 10 */
     int32_t maximum_steps;            /* 0x7FFFFFFF = unbounded */
-    int32_t reserved;
+    int32_t spawn_rank_limit;         /* an occupied cell whose spawn_rank is above this counts as FREE for this query (0 with no
+                                         spawn_rank plane: every occupied cell is occupied).  Query of the k-th spawn of a tick: k */
 } tsim_astar_query;
 
 /* every query works on its own dist / came_from / heap arrays (26 bytes per cell), like the reference's wrapper (:264-272) */

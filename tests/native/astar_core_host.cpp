@@ -5,13 +5,24 @@
 #include "../../trafficsimulation_b200/csrc/astar_core.cuh"
 
 // cap <= 0: the capacity tsim_astar_batch uses (half the grid)
+// spawn_rank may be null; rank_limit: see tsim_astar_query.spawn_rank_limit
+extern "C" int host_astar_ranked(int W, int H, const uint8_t *occ, const uint8_t *stop, const uint8_t *road, const uint8_t *rtype, const uint8_t *adirs,
+                                 const double *dens, int sx, int sy, int gx, int gy, int flags, int awareness, int max_steps, int32_t *out,
+                                 int out_cap, int cap, const uint8_t *spawn_rank, int rank_limit);
+
 extern "C" int host_astar(int W, int H, const uint8_t *occ, const uint8_t *stop, const uint8_t *road, const uint8_t *rtype, const uint8_t *adirs,
                           const double *dens, int sx, int sy, int gx, int gy, int flags, int awareness, int max_steps, int32_t *out, int out_cap,
                           int cap) {
+    return host_astar_ranked(W, H, occ, stop, road, rtype, adirs, dens, sx, sy, gx, gy, flags, awareness, max_steps, out, out_cap, cap, nullptr, 0);
+}
+
+extern "C" int host_astar_ranked(int W, int H, const uint8_t *occ, const uint8_t *stop, const uint8_t *road, const uint8_t *rtype, const uint8_t *adirs,
+                                 const double *dens, int sx, int sy, int gx, int gy, int flags, int awareness, int max_steps, int32_t *out,
+                                 int out_cap, int cap, const uint8_t *spawn_rank, int rank_limit) {
     const size_t n = (size_t)W * H;
     if (cap <= 0) cap = (int)(((n / 2 + 64) + 15) & ~(size_t)15);
     uint16_t *cell = (uint16_t *)malloc(n * sizeof(uint16_t));
-    for (size_t i = 0; i < n; i++) cell[i] = tsim::as_pack(occ[i], stop[i], road[i], rtype[i], adirs[i]);   // astar_pack_kernel
+    for (size_t i = 0; i < n; i++) cell[i] = tsim::as_pack(occ[i], stop[i], road[i], rtype[i], adirs[i], spawn_rank ? spawn_rank[i] : 0);   // astar_pack_kernel
     tsim::AstarMaps m{W, H, cell, dens};
     tsim::AstarWork w;
     w.dist = (uint32_t *)malloc(n * 4);
@@ -22,7 +33,7 @@ extern "C" int host_astar(int W, int H, const uint8_t *occ, const uint8_t *stop,
     memset(w.dist, 0x3F, n * 4);          // what tsim_astar_batch does with cudaMemsetAsync
     memset(w.heap, 0xA5, sizeof(tsim::AsEntry) * (size_t)cap);   // heap and dir start as garbage on the device
     memset(w.dir, 0x5A, cap);
-    const int r = tsim::astar_search(m, sx, sy, gx, gy, flags, awareness, max_steps, w, out, out_cap);
+    const int r = tsim::astar_search(m, sx, sy, gx, gy, flags, awareness, max_steps, w, out, out_cap, rank_limit);
     free(cell); free(w.dist); free(w.heap); free(w.dir); free(w.fov);
     return r;
 }

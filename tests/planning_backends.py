@@ -64,20 +64,28 @@ class OracleTrafficBackend:
         return self.sim.state()
 
 
+_KEEP = object()
+
+
 class OraclePlannerBackend:
+    speculate = False   # a CPU search is not free: the soft search only runs when the strict one found nothing, as in the reference
+
     def __init__(self, W, H, is_road_map, road_type_map, allowed_dirs_map):
         self.W, self.H = W, H
+        self.rank = None
         self.static = (np.asarray(is_road_map), np.asarray(road_type_map), np.asarray(allowed_dirs_map))
         self.occ = np.zeros((H, W), np.uint8)
         self.stop = np.zeros((H, W), np.uint8)
         self.density = np.zeros((H, W), np.float64)
         self._astar = None
 
-    def update(self, occupancy_map=None, stop_map=None):
+    def update(self, occupancy_map=None, stop_map=None, spawn_rank_map=_KEEP):
         if occupancy_map is not None:
             self.occ = np.array(occupancy_map, np.uint8).reshape(self.H, self.W)
         if stop_map is not None:
             self.stop = np.array(stop_map, np.uint8).reshape(self.H, self.W)
+        if spawn_rank_map is not _KEEP:
+            self.rank = None if spawn_rank_map is None else np.array(spawn_rank_map, np.uint8).reshape(self.H, self.W)
         self._astar = None
 
     def update_density(self):
@@ -86,9 +94,13 @@ class OraclePlannerBackend:
 
     def plan_cells(self, queries):
         if self._astar is None:
-            self._astar = O.OracleAstar(self.occ, self.stop, *self.static, self.density)
+            self._astar = {}
         out = []
-        for sx, sy, gx, gy, fl, aw, ms in np.asarray(queries).reshape(-1, 7).tolist():
-            p = self._astar.query(sx, sy, gx, gy, bool(fl & 1), aw, bool(fl & 2), bool(fl & 4), ms)
+        for sx, sy, gx, gy, fl, aw, ms, lim in np.asarray(queries).reshape(-1, 8).tolist():
+            key = lim if self.rank is not None else 0
+            if key not in self._astar:   # the k-th spawn of a tick plans on the map without the spawns after it (tsim_astar_query.spawn_rank_limit)
+                occ = self.occ if self.rank is None else np.where(self.rank > lim, 0, self.occ).astype(np.uint8)
+                self._astar[key] = O.OracleAstar(occ, self.stop, *self.static, self.density)
+            p = self._astar[key].query(sx, sy, gx, gy, bool(fl & 1), aw, bool(fl & 2), bool(fl & 4), ms)
             out.append(np.array([y * self.W + x for x, y in p], np.int32))
         return out

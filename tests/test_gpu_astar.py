@@ -88,3 +88,49 @@ def test_gpu_density_map_is_bit_exact(seed, shape, p_road, p_occ):
     want = O.density_map(occ, road)
     assert got.dtype == np.float64 and np.array_equal(got, want.astype(np.float64))
     assert planner.maps["density_map"].data_ptr() == planner._maps_struct().density_map   # the planner reads this plane
+
+
+def test_gpu_astar_spawn_rank_limit():
+    """tsim_astar_query.spawn_rank_limit / tsim_astar_maps.spawn_rank: the k-th spawn of a tick plans as if the vehicles spawned
+    after it were not on the grid yet -- ONE ranked batch on the full map == the plain searches on the maps with those cells
+    cleared (device and C oracle)."""
+    from oracle import oracle as O
+    from trafficsimulation_b200.pathfinding import GpuAstar
+    r = load_astar(FIXTURES[0])
+    W, H = r["W"], r["H"]
+    rng = np.random.default_rng(3)
+    road = np.flatnonzero(r["is_road_map"].reshape(-1) == 1)
+    born = rng.choice(road, 140, replace=False)            # more than the 7-bit rank field holds: the last ones share 127
+    occ = np.array(r["occupancy"], np.uint8).reshape(-1).copy()
+    occ[rng.choice(road, 300, replace=False)] = 1
+    occ[born] = 1
+    rank = np.zeros(W * H, np.uint8)
+    rank[born] = np.minimum(np.arange(1, len(born) + 1), 127)
+    static = (r["is_road_map"], r["road_type_map"], r["allowed_dirs_map"])
+    planner = GpuAstar(W, H, occ.reshape(H, W), r["stop_map"], *static, r["density"])
+    planner.update(spawn_rank_map=rank.reshape(H, W))
+    ks = [1, 2, 17, 60, 126]
+    q = []
+    for k in ks:
+        for flags in (0, 2, 4, 6):
+            for g in rng.choice(road, 6):
+                q.append([born[k - 1] % W, born[k - 1] // W, g % W, g // W, flags, 10, 0x7FFFFFFF, k])
+    q = np.array(q, np.int32)
+    ranked = planner.plan_cells(q)
+    differ = 0
+    for k in ks:
+        plain = occ.copy()
+        plain[born[k:]] = 0
+        sel = np.flatnonzero(q[:, 7] == k)
+        planner.update(occupancy_map=plain.reshape(H, W), spawn_rank_map=None)
+        alone = planner.plan_cells(q[sel, :7])
+        ora = O.OracleAstar(plain.reshape(H, W), r["stop_map"], *static, r["density"])
+        for i, p in zip(sel, alone):
+            assert ranked[i].tolist() == p.tolist(), (k, q[i].tolist())
+            sx, sy, gx, gy, fl = (int(v) for v in q[i, :5])
+            want = ora.query(sx, sy, gx, gy, False, 10, bool(fl & 2), bool(fl & 4))
+            assert [y * W + x for x, y in want] == p.tolist(), (k, q[i].tolist())
+    planner.update(occupancy_map=occ.reshape(H, W), spawn_rank_map=None)
+    full = planner.plan_cells(q[:, :7])
+    differ = sum(a.tolist() != b.tolist() for a, b in zip(full, ranked))
+    assert differ > 0                                      # the later spawns do change some of these routes

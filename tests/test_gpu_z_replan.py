@@ -13,7 +13,7 @@ from test_gpu_ticks import build_city
 
 pytestmark = pytest.mark.gpu
 
-CASES = [(p, n) for p in tick_fixtures() for name, n in (("s14_carve", 100), ("s31_fixed_time", 60)) if name in p]
+CASES = [(p, n) for p in tick_fixtures() for name, n in (("s14_carve", 100), ("s31_fixed_time", 70)) if name in p]
 
 
 @pytest.mark.parametrize("path,n_ticks", CASES, ids=lambda v: os.path.basename(v)[6:-4] if isinstance(v, str) else str(v))
@@ -26,6 +26,6 @@ def test_gpu_planned_traffic_reproduces_reference_routes(path, n_ticks):
     tapes = without_routes(r)
     # a route buffer far smaller than the run needs: the compaction path runs too
     sim = PlannedTraffic.on_gpu(r["W"], r["H"], tabs, tapes, r["n_ticks"], city.maps_host(), algo=r["algo"],
-                                rain_enabled=r["meta"]["rain_enabled"], route_cells=60000)
+                                rain_enabled=r["meta"]["rain_enabled"], route_cells=80000 if r["W"] < 200 else 400000)
     n = check_against_fixture(r, sim, n_ticks)
     assert n > 100 and sim.searches >= n // 2 and sim.compactions >= 1

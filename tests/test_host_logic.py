@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libtsim.so does not export {name}"
     assert declared == set(_lib.SYMBOLS)
-    assert lib.tsim_version() == 4
+    assert lib.tsim_version() == 5
 
 
 def test_dirs_roundtrip():

@@ -60,6 +60,25 @@ def test_planned_traffic_with_a_small_route_buffer():
     assert sim.compactions >= 5
 
 
+@pytest.mark.parametrize("variant", ["speculate", "rank_chunks"])
+def test_planned_traffic_batching_variants(variant, monkeypatch):
+    """The two batching devices of the device path, on the CPU stand-ins: the alternatives of a search answered in one round
+    (what GpuAstar does), and a tick with more spawns than one rank plane holds (planned chunk by chunk)."""
+    import trafficsimulation_b200.replan as R
+    r = load_ticks([p for p in PLANNABLE if "s7_rain" in p][0])   # 10 spawn attempts per tick
+    maps = fixture_maps(r)
+    tables = O.light_tables_from_reference(r["links_lights"], r["links_ctrl"], r["groups"])
+    tapes = without_routes(r)
+    traffic = OracleTrafficBackend(r["W"], r["H"], tables, tapes, r["n_ticks"], algo=r["algo"], rain_enabled=r["meta"]["rain_enabled"])
+    planner = OraclePlannerBackend(r["W"], r["H"], maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"])
+    if variant == "speculate":
+        planner.speculate = True
+    else:
+        monkeypatch.setattr(R, "RANK_CHUNK", 3)
+    sim = R.PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
+    check_against_fixture(r, sim, 60)
+
+
 @pytest.mark.parametrize("path", PLANNABLE, ids=lambda p: os.path.basename(p)[6:-4])
 def test_planned_traffic_reproduces_reference_routes(path):
     from trafficsimulation_b200.replan import PlannedTraffic

@@ -1,0 +1,37 @@
+"""Pins the route-planning loop (trafficsimulation_b200/replan.py) against the LIVE reference: fresh seeds and parameter corners the
+committed fixtures do not hold (many malfunctions -> contraflow overtakes of stranded vehicles; dense spawning -> stuck detours).
+The unmodified reference runs under the harness, which records every route it plans; the loop gets the same tapes minus the routes.
+Build container only (needs /root/reference); the tick and the searches are the C oracles behind the device interfaces."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from planning_backends import OracleTrafficBackend, OraclePlannerBackend, without_routes
+from test_replan_golden import check_against_fixture
+
+pytestmark = pytest.mark.reference
+
+CASES = [
+    dict(seed=5, n_ticks=90, spawns_per_tick=8, malfunction_p=0.03),
+    dict(seed=33, n_ticks=70, spawns_per_tick=14, malfunction_p=0.004),
+    dict(seed=18, n_ticks=80, spawns_per_tick=5, malfunction_p=0.02, rain_rect=(30, 30, 120, 90),
+         layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"s{c['seed']}")
+def test_planned_traffic_matches_live_reference(case):
+    from oracle.refharness import ticks
+    from trafficsimulation_b200.replan import PlannedTraffic
+    r = ticks.run_ticks(**case)
+    lay = r["layout"]
+    r["ev_off"], r["ev_cells"] = np.asarray(r["ev_off"]), np.asarray(r["ev_cells"])
+    tables = O.light_tables_from_reference(lay["links"]["lights"], lay["links"]["ctrl"], r["groups"])
+    tapes = without_routes(r)
+    rain = case.get("rain_rect") is not None
+    traffic = OracleTrafficBackend(r["W"], r["H"], tables, tapes, r["n_ticks"], rain_enabled=rain, route_capacity=1 << 21)
+    maps = lay["maps"]
+    planner = OraclePlannerBackend(r["W"], r["H"], maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"])
+    sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
+    n = check_against_fixture(r, sim, r["n_ticks"])
+    assert n > 200

@@ -87,10 +87,10 @@ class TickStrips(C.Structure):
 
 
 class AstarMaps(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("occupancy", "stop_map", "is_road_map", "road_type_map", "allowed_dirs_map", "density_map")]
+    _fields_ = [(n, C.c_void_p) for n in ("occupancy", "stop_map", "is_road_map", "road_type_map", "allowed_dirs_map", "density_map", "spawn_rank")]
 
 
-ASTAR_QUERY_WORDS = 8   # tsim_astar_query: sx, sy, gx, gy, flags, awareness_range, maximum_steps, reserved (int32 each)
+ASTAR_QUERY_WORDS = 8   # tsim_astar_query: sx, sy, gx, gy, flags, awareness_range, maximum_steps, spawn_rank_limit (int32 each)
 
 TICK_REC_WORDS, TICK_REC_HEADER, CELL_OUTSIDE = 12, 16, -2
 

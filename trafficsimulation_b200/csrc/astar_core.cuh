@@ -38,11 +38,15 @@ constexpr int AS_ERR_HEAP = -0x40000000;                 // the open list outgre
 //  * dist and came_from share a word: cost in the low 30 bits (AS_INF = 0x3F3F3F3F fits), the direction the cell was
 //    entered by in the top 2, which is all came_from is ever used for (the parent is the neighbour that direction came from).
 constexpr uint32_t AS_COST_MASK = 0x3FFFFFFFu;
-enum { ASC_DIRS = 0xF, ASC_ROAD = 0x10, ASC_RT_SHIFT = 5, ASC_OCC = 0x80, ASC_STOP = 0x100 };
+enum { ASC_DIRS = 0xF, ASC_ROAD = 0x10, ASC_RT_SHIFT = 5, ASC_OCC = 0x80, ASC_STOP = 0x100, ASC_RANK_SHIFT = 9, ASC_RANK_MAX = 127 };
+// bits 9-15: spawn rank of the vehicle on the cell (0 = it was there before this tick's spawner ran).  The spawns of one tick plan one
+// after the other (VehicleAgent.__init__ :72-76 inside the generator's loop): spawn k sees spawns 1..k on the grid, not k+1...  A query
+// carries k as its rank limit and treats an occupied cell of a higher rank as free, so all spawns of a tick share ONE batch.
 
-TSIM_HD uint16_t as_pack(uint8_t occupancy, uint8_t stop, uint8_t is_road, uint8_t road_type, uint8_t allowed_dirs) {
+TSIM_HD uint16_t as_pack(uint8_t occupancy, uint8_t stop, uint8_t is_road, uint8_t road_type, uint8_t allowed_dirs, uint8_t spawn_rank = 0) {
     return (uint16_t)((allowed_dirs & ASC_DIRS) | (is_road == 1 ? ASC_ROAD : 0) | ((road_type <= 3 ? road_type : 0) << ASC_RT_SHIFT) |
-                      (occupancy == 1 ? ASC_OCC : 0) | (stop == 1 ? ASC_STOP : 0));
+                      (occupancy == 1 ? ASC_OCC : 0) | (stop == 1 ? ASC_STOP : 0) |
+                      ((spawn_rank <= ASC_RANK_MAX ? spawn_rank : ASC_RANK_MAX) << ASC_RANK_SHIFT));
 }
 
 struct AstarMaps {      // [H][W]
@@ -76,7 +80,7 @@ TSIM_HD long long as_dynamic_penalty(double density) {   // int(p * (1.0 + SCALE
 // Returns the number of cells written to out (first step first, goal last), 0 = no path (or start == goal),
 // -(needed) if out_cap is too small, AS_ERR_HEAP on open-list overflow.
 TSIM_HD int astar_search(const AstarMaps &m, int sx, int sy, int gx, int gy, int flags, int awareness_range, int maximum_steps,
-                         const AstarWork &w, int32_t *out, int out_cap) {
+                         const AstarWork &w, int32_t *out, int out_cap, int rank_limit = 0) {
     static const int8_t DXY[8] = {0, 1, 1, 0, 0, -1, -1, 0};   // NEIGHBOR_DELTAS N, E, S, W (:9)
     const int W = m.W, H = m.H;
     const int start = sy * W + sx, goal = gy * W + gx;
@@ -151,7 +155,7 @@ TSIM_HD int astar_search(const AstarMaps &m, int sx, int sy, int gx, int gy, int
                 else continue;
             }
             const bool seen = !respect || w.fov[nidx] == 1;
-            if ((c & ASC_OCC) && seen) {
+            if ((c & ASC_OCC) && (int)(c >> ASC_RANK_SHIFT) <= rank_limit && seen) {
                 if (soft) ng += as_dynamic_penalty(m.density ? m.density[nidx] : 0.0);
                 else continue;
             }

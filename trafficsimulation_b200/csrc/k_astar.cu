@@ -28,7 +28,8 @@ struct AstarBatch {
 
 __global__ void __launch_bounds__(256) astar_pack_kernel(long long n, tsim_astar_maps maps, uint16_t *cell) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        cell[i] = as_pack(maps.occupancy[i], maps.stop_map[i], maps.is_road_map[i], maps.road_type_map[i], maps.allowed_dirs_map[i]);
+        cell[i] = as_pack(maps.occupancy[i], maps.stop_map[i], maps.is_road_map[i], maps.road_type_map[i], maps.allowed_dirs_map[i],
+                          maps.spawn_rank ? maps.spawn_rank[i] : (uint8_t)0);
 }
 
 __global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
@@ -36,14 +37,15 @@ __global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
     if (i >= b.n_queries) return;
     const size_t n = (size_t)b.m.W * b.m.H;
     const tsim_astar_query q = b.q[i];
-    if (q.sx < 0 || q.sx >= b.m.W || q.gx < 0 || q.gx >= b.m.W || q.sy < 0 || q.sy >= b.m.H || q.gy < 0 || q.gy >= b.m.H || q.awareness_range < 0) {
+    if (q.sx < 0 || q.sx >= b.m.W || q.gx < 0 || q.gx >= b.m.W || q.sy < 0 || q.sy >= b.m.H || q.gy < 0 || q.gy >= b.m.H || q.awareness_range < 0 ||
+        q.spawn_rank_limit < 0) {
         *b.err = 52;   // a query outside the grid
         b.path_len[i] = 0;
         return;
     }
     const AstarWork w{b.dist + n * i, b.heap + (size_t)b.cap * i, b.dir + (size_t)b.cap * i, b.fov + n * i, b.cap};
     const int r = astar_search(b.m, q.sx, q.sy, q.gx, q.gy, q.flags, q.awareness_range, q.maximum_steps, w, b.path_cells + (size_t)i * b.max_path,
-                               b.max_path);
+                               b.max_path, q.spawn_rank_limit);
     if (r == AS_ERR_HEAP) { *b.err = 51; b.path_len[i] = 0; }
     else if (r < 0) { *b.err = 50; b.path_len[i] = r; }   // -(cells needed): the caller's max_path is too small
     else b.path_len[i] = r;

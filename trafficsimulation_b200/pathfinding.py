@@ -39,11 +39,14 @@ class GpuAstar:
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def update(self, **maps):
-        """Replace maps (host arrays or device tensors, [H][W]); the tick's occupancy / stop planes can be passed as they are."""
+        """Replace maps (host arrays or device tensors, [H][W]); the tick's occupancy / stop planes can be passed as they are.
+        spawn_rank_map (u8, optional; None removes it): which spawn of the running tick stands on a cell, see ``plan_cells``."""
         for k, v in maps.items():
             if v is None:
                 self.maps[k] = None
                 continue
+            if k not in ("occupancy_map", "stop_map", "is_road_map", "road_type_map", "allowed_dirs_map", "density_map", "spawn_rank_map"):
+                raise ValueError(f"unknown map {k!r}")
             dt = torch.float64 if k == "density_map" else torch.uint8
             t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
             t = t.to(device=self.device, dtype=dt).contiguous().view(-1)
@@ -69,12 +72,18 @@ class GpuAstar:
         m = self.maps
         ptr = lambda k: m[k].data_ptr() if m.get(k) is not None else None
         return _lib.AstarMaps(ptr("occupancy_map"), ptr("stop_map"), ptr("is_road_map"), ptr("road_type_map"), ptr("allowed_dirs_map"),
-                              ptr("density_map"))
+                              ptr("density_map"), ptr("spawn_rank_map"))
 
     def plan_cells(self, queries, max_path=None):
-        """queries: int array [n, 7] = (sx, sy, gx, gy, flags, awareness_range, maximum_steps).  Returns a list of int32 arrays of
-        cell indices ``y * W + x`` (first step first, goal last; empty = no route)."""
-        q = np.ascontiguousarray(queries, np.int32).reshape(-1, 7)
+        """queries: int array [n, 7] = (sx, sy, gx, gy, flags, awareness_range, maximum_steps), or [n, 8] with a spawn-rank limit
+        as the last column: the query of the k-th vehicle the spawner placed this tick carries k and sees an occupied cell whose
+        ``spawn_rank_map`` entry is above k as free -- the vehicles spawned after it are not on the grid yet when it plans
+        (vehicle_base.py:72-76), so all spawns of a tick plan in one batch.  Returns a list of int32 arrays of cell indices
+        ``y * W + x`` (first step first, goal last; empty = no route)."""
+        q = np.ascontiguousarray(queries, np.int32)
+        q = q.reshape(-1, 8 if q.ndim == 2 and q.shape[1] == 8 else 7)
+        if q.shape[1] == 7:
+            q = np.concatenate([q, np.zeros((len(q), 1), np.int32)], 1)
         out = []
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         maps = self._maps_struct()
@@ -82,7 +91,7 @@ class GpuAstar:
         for a in range(0, len(q), self.chunk):
             part = q[a:a + self.chunk]
             n = len(part)
-            dq = torch.from_numpy(np.concatenate([part, np.zeros((n, 1), np.int32)], 1)).to(self.device)
+            dq = torch.from_numpy(np.ascontiguousarray(part)).to(self.device)
             need = C.c_size_t(0)
             _lib.check(self.lib.tsim_astar_scratch_bytes(C.byref(self.cfg), n, C.byref(need)))
             if self._scratch is None or self._scratch.numel() < need.value:

@@ -42,6 +42,7 @@ STUCK_CONTRAFLOW_INTERSECTION = 10   # VEHICLE_STUCK_CONTRAFLOW_THRESHOLD_INTERS
 DETOUR_STEPS = 20                    # VEHICLE_MAX_CONTRAFLOW_STUCK_DETOUR_STEPS :312
 DETOUR_DURATION = 10                 # VEHICLE_CONTRAFLOW_STUCK_DETOUR_DURATION :313
 COOLDOWN = 5                         # PATHFINDING_COOLDOWN :409
+RANK_CHUNK = 126                     # spawns of one tick that plan in one batch (tsim_astar_maps.spawn_rank holds 7 bits)
 
 
 class PlanState:
@@ -89,7 +90,8 @@ def scan_ahead(path, occ, stop):
 
 
 def compute_path_internal(s, view):
-    """``_compute_path_internal`` :199-420 as a coroutine: yields ``(start, goal, flags, maximum_steps)``, is sent the path."""
+    """``_compute_path_internal`` :199-420 as a coroutine: yields ``(start, goal, flags, maximum_steps)`` (or a list of such
+    alternatives), is sent the path."""
     occ, stop = view.occ, view.stop
     pos, goal = s.pos, s.target
     # phase 0: back onto the saved route while overtaking / detouring (:218-274)
@@ -107,9 +109,9 @@ def compute_path_internal(s, view):
                         s.stuck_detour_path = bypass
                     return bypass + saved[merge + 1:]
     # phase 1: strict avoidance, phase 2: soft obstacles (:276-303)
-    path = yield (pos, goal, 0, UNBOUNDED)
-    if not path:
-        path = yield (pos, goal, SOFT_OBSTACLES, UNBOUNDED)
+    # (a LIST of queries = "the first of these that finds a route": the strict search fails whenever a vehicle or a red light
+    # stands anywhere on every way to the goal, which is nearly always, so both searches travel in the same batch)
+    path = yield [(pos, goal, 0, UNBOUNDED), (pos, goal, SOFT_OBSTACLES, UNBOUNDED)]
     # phase 3: contraflow bypass of a stranded / parked vehicle on the next cell (:305-364)
     if path:
         idx_stop = idx_vehicle = None
@@ -197,26 +199,51 @@ def decide_replans(s, view):
             s.path = path
 
 
-def run_coroutines(jobs, answer):
+def run_coroutines(jobs, answer, limits=None, speculate=True):
     """Drive coroutines that yield A* queries: every round, the pending queries of all of them go to ``answer(list of queries)``
-    (one batch launch) and each coroutine is resumed with its path.  ``jobs``: list of generators; returns their return values."""
+    (one batch launch) and each coroutine is resumed with its path.  A coroutine may yield a LIST of alternatives ("the first one
+    that finds a route"): with ``speculate`` they all travel in the same round, otherwise one per round as long as they fail.
+    ``jobs``: list of generators; ``limits[i]``: spawn-rank limit of every query of job i (default 0); returns the return values."""
     results = [None] * len(jobs)
     pending = []
-    for i, g in enumerate(jobs):
+
+    def advance(i, g, send):
         try:
-            pending.append((i, g, next(g)))
+            q = g.send(send) if send is not None else next(g)
+            pending.append([i, g, q if isinstance(q, list) else [q], 0])
         except StopIteration as e:
             results[i] = e.value
+
+    for i, g in enumerate(jobs):
+        advance(i, g, None)
     while pending:
-        paths = answer([q for _, _, q in pending])
-        nxt = []
-        for (i, g, _), p in zip(pending, paths):
-            try:
-                nxt.append((i, g, g.send(p)))
-            except StopIteration as e:
-                results[i] = e.value
-        pending = nxt
+        todo, pending = pending, []
+        asked, span = [], []
+        for i, g, alts, k in todo:
+            take = alts[k:] if speculate else alts[k:k + 1]
+            span.append(len(take))
+            asked += [q + ((limits[i] if limits else 0),) for q in take]
+        paths = answer(asked)
+        at = 0
+        for (i, g, alts, k), n in zip(todo, span):
+            got = next((p for p in paths[at:at + n] if p), [])
+            at += n
+            if not got and k + n < len(alts):
+                pending.append([i, g, alts, k + n])     # (without speculation) the next alternative, next round
+            else:
+                advance(i, g, got)
     return results
+
+
+class _WithoutLater:
+    """An occupancy plane as the k-th spawn of a tick sees it: the cells of the vehicles spawned after it read as free."""
+    __slots__ = ("occ", "later")
+
+    def __init__(self, occ, later):
+        self.occ, self.later = occ, later
+
+    def __getitem__(self, c):
+        return 0 if c in self.later else self.occ[c]
 
 
 class PlannedTraffic:
@@ -245,6 +272,7 @@ class PlannedTraffic:
         self.batches = 0              # planner launches
         self.compactions = 0          # times the route buffer was started again
         self._snap = None
+        self.speculate = bool(getattr(planner, "speculate", True))   # alternatives of a search in one batch (cheap on the device)
 
     @classmethod
     def on_gpu(cls, width, height, light_tables, tapes, n_ticks, maps, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0",
@@ -265,7 +293,7 @@ class PlannedTraffic:
 
     # ---- A* batches
     def _answer(self, queries):
-        q = np.array([[a % self.W, a // self.W, b % self.W, b // self.W, fl, AWARENESS_RANGE, ms] for a, b, fl, ms in queries], np.int32)
+        q = np.array([[a % self.W, a // self.W, b % self.W, b // self.W, fl, AWARENESS_RANGE, ms, lim] for a, b, fl, ms, lim in queries], np.int32)
         self.searches += len(q)
         self.batches += 1
         return [p.tolist() for p in self.planner.plan_cells(q)]
@@ -285,7 +313,7 @@ class PlannedTraffic:
         snap = self._snap
         occ, stop = snap["occupancy"], snap["stop_map"]
         # CityModel._update_density_map :1764-1778, from the tick-start occupancy; it also serves the spawns of this tick
-        self.planner.update(occupancy_map=occ.reshape(self.H, self.W), stop_map=stop.reshape(self.H, self.W))
+        self.planner.update(occupancy_map=occ.reshape(self.H, self.W), stop_map=stop.reshape(self.H, self.W), spawn_rank_map=None)
         self.planner.update_density()
         live = sorted(self.veh)
         if live:
@@ -305,7 +333,7 @@ class PlannedTraffic:
                     continue
                 jobs.append(decide_replans(s, view))
                 who.append(v)
-            run_coroutines(jobs, self._answer)
+            run_coroutines(jobs, self._answer, speculate=self.speculate)
             for v in who:
                 if self.veh[v].planned:
                     self.events.append((t, v, list(self.veh[v].path)))
@@ -337,25 +365,33 @@ class PlannedTraffic:
             if moved:
                 del s.path[:moved]
             s.pos, s.stuck_ticks = int(snap["pos"][v]), int(snap["stuck_ticks"][v])
-        # ---- the spawns of this tick plan their first route (VehicleAgent.__init__ :72-76), one after the other: a later spawn of
-        # the same tick is not on the grid yet when an earlier one plans
+        # ---- the spawns of this tick plan their first route (VehicleAgent.__init__ :72-76).  The reference plans them one after the
+        # other, a later spawn of the same tick not being on the grid yet when an earlier one plans: every query carries its spawn's
+        # rank and the planner reads the cells of higher ranks as free, so they all plan in the same batches
         born = [int(v) for v in np.flatnonzero(alive) if int(v) not in self.veh]
-        if born:
-            occ2, stop2 = snap["occupancy"], snap["stop_map"]
-            stranded_now = snap["stranded_flag"]
-            veh_at = {int(snap["pos"][v]): v for v in list(self.veh) + born}
-            for i, v in enumerate(born):
+        occ2, stop2 = snap["occupancy"], snap["stop_map"]
+        stranded_now = snap["stranded_flag"]
+        veh_at = {int(snap["pos"][v]): v for v in list(self.veh) + born}
+        for j0 in range(0, len(born), RANK_CHUNK):
+            chunk = born[j0:j0 + RANK_CHUNK]
+            rank = np.zeros(self.W * self.H, np.uint8)
+            rank[[int(snap["pos"][u]) for u in born[j0 + RANK_CHUNK:]]] = RANK_CHUNK + 1
+            rank[[int(snap["pos"][u]) for u in chunk]] = np.arange(1, len(chunk) + 1)
+            self.planner.update(occupancy_map=occ2.reshape(self.H, self.W), stop_map=stop2.reshape(self.H, self.W),
+                                spawn_rank_map=rank.reshape(self.H, self.W))
+            jobs, states = [], []
+            for i, v in enumerate(chunk):
                 s = PlanState(v, int(self.target[v]))
                 s.pos = int(snap["pos"][v])
-                later = [int(snap["pos"][u]) for u in born[i + 1:]]
-                o = occ2
-                if later:
-                    o = occ2.copy()
-                    o[later] = 0
-                self.planner.update(occupancy_map=o.reshape(self.H, self.W), stop_map=stop2.reshape(self.H, self.W))
+                later = {int(snap["pos"][u]) for u in born[j0 + i + 1:]}
+                o = _WithoutLater(occ2, later) if later else occ2
                 at = veh_at if not later else {c: u for c, u in veh_at.items() if c not in later}
                 view = _View(o, stop2, self.inter, at, lambda u, me: bool(stranded_now[u]))
-                s.path = run_coroutines([compute_path(s, view, self.cache)], self._answer)[0] or []
-                self.veh[v] = s
-                self.events.append((t, v, list(s.path)))
-                self.pending[v] = s.path
+                jobs.append(compute_path(s, view, self.cache))
+                states.append(s)
+            paths = run_coroutines(jobs, self._answer, limits=list(range(1, len(chunk) + 1)), speculate=self.speculate)
+            for s, path in zip(states, paths):
+                s.path = path or []
+                self.veh[s.v] = s
+                self.events.append((t, s.v, list(s.path)))
+                self.pending[s.v] = s.path

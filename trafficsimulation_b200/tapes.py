@@ -211,6 +211,39 @@ def synth_trips(seed: int, W: int, H: int, cell_type: np.ndarray, dirs: np.ndarr
     return base
 
 
+def synth_planned_trips(seed: int, W: int, H: int, cell_type: np.ndarray, trips_per_tick: int, n_ticks: int, malfunction_p: float = 0.0):
+    """Tick tapes WITHOUT routes for ``replan.PlannedTraffic`` (SURVEY.md §8d config 4 as named: trips injected every tick, the
+    vehicles plan their own routes).  A trip starts on a cell of ``CityModel.get_start_blocks()`` (BlockEntrance / HighwayEntrance,
+    city_model.py:2102-2109) and ends on one of ``get_exit_blocks()`` (BlockEntrance / HighwayExit, :2111-2118) other than its
+    origin -- the harness's trip rule (oracle/refharness/ticks.py).  Activation order: an affine permutation per tick, as in
+    ``synth_trips``."""
+    rng = np.random.default_rng(seed)
+    T = np.asarray(cell_type).reshape(-1)
+    starts = np.flatnonzero((T == 19) | (T == 13))
+    exits = np.flatnonzero((T == 19) | (T == 14))
+    if len(starts) == 0 or len(exits) < 2:
+        raise ValueError("the city has no entrance / exit cells to run trips between")
+    nv = int(trips_per_tick) * int(n_ticks)
+    origin = starts[rng.integers(len(starts), size=nv)]
+    target = exits[rng.integers(len(exits), size=nv)]
+    same = target == origin
+    while same.any():                     # a trip to its own origin is never generated
+        target[same] = exits[rng.integers(len(exits), size=int(same.sum()))]
+        same = target == origin
+    P = 2147483647
+    a = rng.integers(1, P, size=n_ticks, dtype=np.int64)
+    b = rng.integers(0, P, size=n_ticks, dtype=np.int64)
+    rank = np.empty((n_ticks, nv), np.int32)
+    idx = np.arange(nv, dtype=np.int64)
+    for t in range(n_ticks):
+        rank[t] = (a[t] * idx + b[t]) % P
+    return dict(spawn_tick=np.repeat(np.arange(n_ticks, dtype=np.int32), trips_per_tick), origin=origin.astype(np.int32),
+                target=target.astype(np.int32), speed=rng.integers(1, 6, size=(n_ticks, nv), dtype=np.uint8),
+                malfunction=(rng.random((n_ticks, nv)) < malfunction_p).astype(np.uint8) if malfunction_p > 0 else np.zeros((n_ticks, nv), np.uint8),
+                rank=rank, ev_tick=np.zeros(0, np.int32), ev_vehicle=np.zeros(0, np.int32), ev_off=np.zeros(1, np.int64),
+                ev_cells=np.zeros(0, np.int32), rain_map=np.zeros((H, W), np.uint8))
+
+
 def spawn_tape_from_trips(depart_secs, origin_cells, target_cells, dt, n_ticks: int, elapsed: float = 0.0):
     """The reference's trip schedule as a spawn tape.
 
