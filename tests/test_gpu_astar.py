@@ -37,6 +37,22 @@ def test_gpu_astar_matches_reference_vectors(path):
     assert [y * r["W"] + x for x, y in one] == list(r["paths"][5])
 
 
+@pytest.mark.parametrize("mode,smem_cap", [("0", None), ("1", None), ("2", None), ("2", "64")],
+                         ids=["per_thread", "per_cta", "per_cta_smem", "per_cta_smem_overflow"])
+def test_gpu_astar_launch_forms(mode, smem_cap, monkeypatch):
+    """The three launch forms of tsim_astar_batch (a query per thread; per CTA -- the default for small batches; per CTA with the open
+    list in shared memory) give the reference's paths; so does the fall-back when an open list outgrows its shared memory."""
+    from trafficsimulation_b200.pathfinding import GpuAstar
+    monkeypatch.setenv("TSIM_ASTAR_MODE", mode)
+    if smem_cap:
+        monkeypatch.setenv("TSIM_ASTAR_SMEM_CAP", smem_cap)
+    r = load_astar(FIXTURES[0])
+    planner = GpuAstar(r["W"], r["H"], r["occupancy"], r["stop_map"], r["is_road_map"], r["road_type_map"], r["allowed_dirs_map"], r["density"])
+    got = planner.plan_cells(_queries(r)[:300])
+    for q, g, want in zip(r["queries"], got, r["paths"]):
+        assert g.tolist() == list(want), tuple(q)
+
+
 def test_gpu_astar_matches_oracle_on_a_synthetic_city():
     """A city the reference never saw (768 x 512 synthetic layout from the GPU pipeline), live maps from the tick planes."""
     from oracle import oracle as O

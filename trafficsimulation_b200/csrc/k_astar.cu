@@ -32,9 +32,8 @@ __global__ void __launch_bounds__(256) astar_pack_kernel(long long n, tsim_astar
                           maps.spawn_rank ? maps.spawn_rank[i] : (uint8_t)0);
 }
 
-__global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b.n_queries) return;
+// query i of the batch; smem / smem_cap: a shared-memory open list of that many entries (16 B entry + 1 B direction each), or null
+__device__ __forceinline__ void astar_one_query(const AstarBatch &b, int i, unsigned char *smem, int smem_cap) {
     const size_t n = (size_t)b.m.W * b.m.H;
     const tsim_astar_query q = b.q[i];
     if (q.sx < 0 || q.sx >= b.m.W || q.gx < 0 || q.gx >= b.m.W || q.sy < 0 || q.sy >= b.m.H || q.gy < 0 || q.gy >= b.m.H || q.awareness_range < 0 ||
@@ -44,11 +43,39 @@ __global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
         return;
     }
     const AstarWork w{b.dist + n * i, b.heap + (size_t)b.cap * i, b.dir + (size_t)b.cap * i, b.fov + n * i, b.cap};
-    const int r = astar_search(b.m, q.sx, q.sy, q.gx, q.gy, q.flags, q.awareness_range, q.maximum_steps, w, b.path_cells + (size_t)i * b.max_path,
-                               b.max_path, q.spawn_rank_limit);
+    int32_t *out = b.path_cells + (size_t)i * b.max_path;
+    int r = AS_ERR_HEAP;
+    if (smem) {
+        const AstarWork ws{w.dist, (AsEntry *)smem, (int8_t *)(smem + sizeof(AsEntry) * (size_t)smem_cap), w.fov, smem_cap};
+        r = astar_search(b.m, q.sx, q.sy, q.gx, q.gy, q.flags, q.awareness_range, q.maximum_steps, ws, out, b.max_path, q.spawn_rank_limit);
+        if (r == AS_ERR_HEAP) {   // the open list outgrew shared memory: once more from scratch on the arrays in global memory
+            for (size_t k = 0; k < n; k++) w.dist[k] = 0x3F3F3F3Fu;
+            for (size_t k = 0; k < n; k++) w.fov[k] = 0;
+        }
+    }
+    if (r == AS_ERR_HEAP)
+        r = astar_search(b.m, q.sx, q.sy, q.gx, q.gy, q.flags, q.awareness_range, q.maximum_steps, w, out, b.max_path, q.spawn_rank_limit);
     if (r == AS_ERR_HEAP) { *b.err = 51; b.path_len[i] = 0; }
     else if (r < 0) { *b.err = 50; b.path_len[i] = r; }   // -(cells needed): the caller's max_path is too small
     else b.path_len[i] = r;
+}
+
+// big batches: a query per THREAD (throughput: tens of thousands of dependent chains in flight)
+__global__ void __launch_bounds__(64) astar_kernel(AstarBatch b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_queries) return;
+    astar_one_query(b, i, nullptr, 0);
+}
+
+// small batches (a tick's re-plans, replan.py): a query per CTA, one lane working.  A serial search is a chain of dependent
+// accesses to its open list; 32 queries in one warp execute each other's divergent paths and share one SM's L1, a query alone on
+// its SM partition does neither (2 x faster per batch on the re-planning workload).  SMEM: the open list in shared memory -- no
+// gain over L1 (kept, tested, off by default; see the launch site).
+template <bool SMEM>
+__global__ void __launch_bounds__(32) astar_spread_kernel(AstarBatch b, int smem_cap) {
+    extern __shared__ __align__(16) unsigned char astar_smem[];
+    if (threadIdx.x != 0) return;
+    astar_one_query(b, blockIdx.x, SMEM ? astar_smem : nullptr, smem_cap);
 }
 
 // ---- CityModel._update_density_map (city_model.py:1764-1778): what the planner's soft vehicle penalty reads ----------------
@@ -86,6 +113,8 @@ __global__ void __launch_bounds__(256) density_rows_kernel(int W, int H, const u
 
 // open-list capacity per query: the reference's arrays hold W * H entries; on city maps the list peaks below a third of the
 // ROAD cells (~ W * H / 14 on the reference's default city), so half the grid is generous -- and overflow is an error, not UB
+constexpr int ASTAR_SMEM_CAP = 4096;      // open-list entries held in shared memory (68 KB per CTA: three queries per SM)
+constexpr int ASTAR_SPREAD_MAX = 148 * 8;  // batches up to this size run a query per CTA
 static int astar_cap(long long n) { return (int)(((n / 2 + 64) + 15) & ~15LL); }
 static size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
 static size_t astar_bytes(long long n, int nq) {
@@ -137,7 +166,29 @@ extern "C" tsim_status tsim_astar_batch(const tsim_cfg *cfg, const tsim_astar_ma
     TSIM_LAUNCH_CHECK();
     TSIM_CUDA(cudaMemsetAsync(b.dist, 0x3F, (size_t)n * 4 * n_queries, cs));   // dist = INF = 0x3F3F3F3F (:118), no parent direction
     TSIM_CUDA(cudaMemsetAsync(b.fov, 0, (size_t)n * n_queries, cs));           // fov_map = 0
-    astar_kernel<<<div_up(n_queries, 64), 64, 0, cs>>>(b);
+    // launch form: TSIM_ASTAR_MODE = 0 a query per thread, 1 a query per CTA, 2 a query per CTA with the open list in shared memory;
+    // default: 1 for batches that leave SMs idle in the per-thread form, 0 beyond.  Measured on the planned_trips workload of bench.py
+    // (471 batches of 74 queries on average, profiles/r2_planned_modes.json): 9.98 s per thread, 5.05 s per CTA, 6.21 s per CTA with
+    // the open list in shared memory -- a query alone in its CTA already finds its open list in L1, and 68 KB of shared memory per
+    // CTA only costs residency
+    // (TSIM_ASTAR_SMEM_CAP: a smaller shared-memory open list, for the test of the fall-back to global memory)
+    const char *mode_env = getenv("TSIM_ASTAR_MODE"), *cap_env = getenv("TSIM_ASTAR_SMEM_CAP");
+    const int mode = mode_env ? atoi(mode_env) : (n_queries <= ASTAR_SPREAD_MAX ? 1 : 0);
+    if (mode == 2) {
+        int smem_cap = cap < ASTAR_SMEM_CAP ? cap : ASTAR_SMEM_CAP;
+        if (cap_env && atoi(cap_env) >= 16 && atoi(cap_env) < smem_cap) smem_cap = atoi(cap_env) & ~15;
+        const size_t bytes = (sizeof(AsEntry) + 1) * (size_t)smem_cap;
+        static bool attr_set = false;
+        if (!attr_set) {
+            TSIM_CUDA(cudaFuncSetAttribute(astar_spread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((sizeof(AsEntry) + 1) * ASTAR_SMEM_CAP)));
+            attr_set = true;
+        }
+        astar_spread_kernel<true><<<n_queries, 32, bytes, cs>>>(b, smem_cap);
+    } else if (mode == 1) {
+        astar_spread_kernel<false><<<n_queries, 32, 0, cs>>>(b, 0);
+    } else {
+        astar_kernel<<<div_up(n_queries, 64), 64, 0, cs>>>(b);
+    }
     TSIM_LAUNCH_CHECK();
     return TSIM_OK;
 }
