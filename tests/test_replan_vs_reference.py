@@ -35,3 +35,44 @@ def test_planned_traffic_matches_live_reference(case):
     sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
     n = check_against_fixture(r, sim, r["n_ticks"])
     assert n > 200
+
+
+def test_tick_mirror_writes_the_planner_state_of_the_live_reference():
+    """The tick side of the seam with planning (adaptor.GpuTickMirror over a PlannedTraffic): after n ticks every VehicleAgent of a
+    duck-typed model holds the route AND the planner's private state (cooldown, overtake / detour flags, timers, saved routes) of the
+    same vehicle in the live reference model."""
+    import types
+    from fake_model import FakeModel
+    from oracle.refharness import ticks
+    from trafficsimulation_b200.adaptor import GpuTickMirror
+    from trafficsimulation_b200.replan import PlannedTraffic
+    case = dict(seed=5, n_ticks=90, spawns_per_tick=8, malfunction_p=0.03)
+    r = ticks.run_ticks(**case)
+    lay = r["layout"]
+    ref_model = lay["model"]
+    tables = O.light_tables_from_reference(lay["links"]["lights"], lay["links"]["ctrl"], r["groups"])
+    tapes = without_routes(r)
+    maps = lay["maps"]
+    sim = PlannedTraffic(OracleTrafficBackend(r["W"], r["H"], tables, tapes, r["n_ticks"], route_capacity=1 << 21),
+                         OraclePlannerBackend(r["W"], r["H"], maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"]),
+                         r["W"], r["H"], maps["intersection_map"], tapes)
+    m = FakeModel(width=r["W"], height=r["H"])
+    mirror = GpuTickMirror(m, sim, vehicle_factory=lambda v: types.SimpleNamespace(attempt=v, pos=None))
+    mirror.gpu_step(r["n_ticks"])
+    mirror.sync_to_model()
+    ref = {ag._tsim_idx: ag for ag in ref_model.active_vehicle_agents}
+    assert sorted(ref) == sorted(mirror.vehicles) and len(ref) > 100
+    names = ("path", "path_retry_cooldown", "is_overtaking", "is_in_stuck_detour", "overtaking_duration", "stuck_detour_duration")
+    busy = 0
+    for v, want in ref.items():
+        got = mirror.vehicles[v]
+        assert got.pos == tuple(want.pos)
+        for n in names:
+            a, b = getattr(got, n), getattr(want, n)
+            assert (list(map(tuple, a)) if n == "path" else a) == (list(map(tuple, b)) if n == "path" else b), (v, n, a, b)
+        for n, flag in (("overtake_path", "is_overtaking"), ("pre_overtake_path", "is_overtaking"),
+                        ("stuck_detour_path", "is_in_stuck_detour"), ("pre_stuck_detour_path", "is_in_stuck_detour")):
+            if getattr(want, flag):   # the saved routes only mean something while the manoeuvre lasts
+                assert list(map(tuple, getattr(got, n))) == list(map(tuple, getattr(want, n))), (v, n)
+                busy += 1
+    assert busy > 0

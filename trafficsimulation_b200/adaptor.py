@@ -308,7 +308,8 @@ class GpuTickMirror:
     """The tick side of the seam: ``CityModel.step()`` (city_model.py:1831-1860) with the vehicle CA and the light groups on
     the device.
 
-        mirror = GpuTickMirror(model, sim, vehicles)      # sim: GpuTraffic / ShardedTraffic built from the model's tapes
+        mirror = GpuTickMirror(model, sim, vehicles)      # sim: GpuTraffic / ShardedTraffic built from the model's tapes, or a
+                                                          # replan.PlannedTraffic (no route tape: the vehicles plan their routes)
         mirror.gpu_step(n)                                # instead of model.schedule.step() n times
         mirror.sync_to_model()                            # only when a front-end / statistic reads the Python objects
 
@@ -316,7 +317,9 @@ class GpuTickMirror:
     ``sync_to_model`` writes the device state back into the reference's own containers, the way its own movement code leaves
     them (city_model.py:1897-1963, vehicle_base.py:521-532): ``occupancy_map`` / ``stop_map`` / ``stuck_map`` (numpy [H, W]),
     and per vehicle ``pos`` (through ``model.move_vehicle`` bookkeeping: ``grid.move_agent``), ``current_speed``, ``base_speed``,
-    ``is_stuck``, ``stuck_ticks``, ``direction``, ``is_in_malfunction``; vehicles that arrived are removed through
+    ``is_stuck``, ``stuck_ticks``, ``direction``, ``is_in_malfunction`` -- with a ``PlannedTraffic`` also ``path`` and the planner's
+    fields (``path_retry_cooldown``, ``is_overtaking``, ``overtake_path``, ``pre_overtake_path``, ``overtaking_duration`` and their
+    stuck-detour twins, vehicle_base.py:43-56); vehicles that arrived are removed through
     ``model.remove_vehicle``, vehicles the device spawned are placed through ``model.place_vehicle`` (the caller supplies them
     through ``vehicles``: spawn-attempt index -> VehicleAgent, or a factory called with the attempt index).
     """
@@ -349,6 +352,7 @@ class GpuTickMirror:
             self._placed.discard(v)
             self._untrack(ag)
         flags = st["vflags"]
+        planner_fields = getattr(self.sim, "planner_fields", None)
         for v in live.tolist():
             xy = (int(pos[v] % W), int(pos[v] // W))
             ag = self.vehicles.get(v)
@@ -372,6 +376,9 @@ class GpuTickMirror:
             ag.stuck_ticks = int(st["stuck_ticks"][v])
             d = (f >> 2) - 1
             ag.direction = self.DIRS[d] if d >= 0 else None
+            if planner_fields is not None:                           # replan.PlannedTraffic: the route and the planner's own state
+                for name, value in planner_fields(v).items():
+                    setattr(ag, name, value)
         assert H * W == m.occupancy_map.size
         return st
 

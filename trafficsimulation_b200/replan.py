@@ -299,9 +299,25 @@ class PlannedTraffic:
         return [p.tolist() for p in self.planner.plan_cells(q)]
 
     # ---- one tick
-    def step(self, n=1):
+    def step(self, n=1, check=True):
+        """``CityModel.step()`` n times.  (check: accepted for ``GpuTraffic.step``'s signature; every tick is checked -- the planner
+        reads the device state between two ticks anyway.)"""
         for _ in range(int(n)):
             self._step_one()
+
+    def state_host(self):
+        """The city as ``GpuTraffic.state_host()`` gives it (positions, flags, maps, light groups)."""
+        return self.traffic.state_host()
+
+    def planner_fields(self, v):
+        """The planner-side attributes of live vehicle v under the reference's names (vehicle_base.py:43-56), paths as ``(x, y)`` lists:
+        what ``adaptor.GpuTickMirror.sync_to_model`` writes into the ``VehicleAgent``."""
+        s, W = self.veh[v], self.W
+        xy = lambda cells: None if cells is None else [(c % W, c // W) for c in cells]
+        return dict(path=xy(s.path), path_retry_cooldown=s.cooldown, is_overtaking=s.is_overtaking, overtake_path=xy(s.overtake_path),
+                    pre_overtake_path=xy(s.pre_overtake_path), overtaking_duration=s.overtaking_duration,
+                    is_in_stuck_detour=s.is_in_stuck_detour, stuck_detour_path=xy(s.stuck_detour_path),
+                    pre_stuck_detour_path=xy(s.pre_stuck_detour_path), stuck_detour_duration=s.stuck_detour_duration)
 
     def _step_one(self):
         t = self.tick
