@@ -89,7 +89,7 @@ def test_planned_traffic_reproduces_reference_routes(path):
     traffic = OracleTrafficBackend(r["W"], r["H"], tables, tapes, r["n_ticks"], algo=r["algo"], rain_enabled=r["meta"]["rain_enabled"])
     planner = OraclePlannerBackend(r["W"], r["H"], maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"])
     sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
-    n = check_against_fixture(r, sim, min(r["n_ticks"], 120))   # (the longest fixture holds 240 ticks: the first 120 keep the suite short)
+    n = check_against_fixture(r, sim, r["n_ticks"])   # default12345: 240 ticks, 1 440 trips, 37 k planned routes
     assert n > 100 and sim.searches >= n // 2
 
 
