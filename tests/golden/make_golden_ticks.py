@@ -27,6 +27,9 @@ CASES = {
                       layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
     # sideswipe draws that fire (vehicle_base.py:567-605; stored as a second bit plane beside the malfunction tape)
     "s21_sideswipe": dict(seed=21, n_ticks=140, spawns_per_tick=12, malfunction_p=0.002, sideswipe_p=0.35),
+    # many malfunctions: stranded vehicles on the lanes -> contraflow overtakes and stuck detours (vehicle_base.py:305-418), the case the
+    # route-planning loop (trafficsimulation_b200/replan.py) is checked on without the route events
+    "s5_stranded": dict(seed=5, n_ticks=90, spawns_per_tick=8, malfunction_p=0.03),
     # the other light controllers (Defaults.TRAFFIC_LIGHT_AGENT_ALGORITHM, intersection_light_group.py:396-461)
     "s31_fixed_time": dict(seed=31, n_ticks=100, spawns_per_tick=8, malfunction_p=0.002, algo="FIXED_TIME"),
     "s9_pressure": dict(seed=9, n_ticks=120, spawns_per_tick=8, malfunction_p=0.002, algo="PRESSURE_CONTROL"),

@@ -13,7 +13,7 @@ from test_gpu_ticks import build_city
 
 pytestmark = pytest.mark.gpu
 
-CASES = [(p, n) for p in tick_fixtures() for name, n in (("s14_carve", 100), ("s31_fixed_time", 70)) if name in p]
+CASES = [(p, n) for p in tick_fixtures() for name, n in (("s14_carve", 100), ("s31_fixed_time", 70), ("s5_stranded", 90)) if name in p]
 
 
 @pytest.mark.parametrize("path,n_ticks", CASES, ids=lambda v: os.path.basename(v)[6:-4] if isinstance(v, str) else str(v))
