@@ -22,7 +22,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libtsim.so does not export {name}"
     assert declared == set(_lib.SYMBOLS)
-    assert lib.tsim_version() == 5
+    assert lib.tsim_version() == 5 == _lib.ABI_VERSION
+    assert f"#define TSIM_ABI_VERSION {_lib.ABI_VERSION}" in header
 
 
 def test_dirs_roundtrip():

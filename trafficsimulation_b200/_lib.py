@@ -94,6 +94,8 @@ ASTAR_QUERY_WORDS = 8   # tsim_astar_query: sx, sy, gx, gy, flags, awareness_ran
 
 TICK_REC_WORDS, TICK_REC_HEADER, CELL_OUTSIDE = 12, 16, -2
 
+ABI_VERSION = 5   # TSIM_ABI_VERSION of include/tsim.h these bindings were written against
+
 _lib = None
 
 
@@ -112,6 +114,8 @@ def load():
     lib.tsim_tick_message_words.restype = C.c_longlong
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError if the library does not export a declared symbol
+    if lib.tsim_version() != ABI_VERSION:   # the struct layouts below are those of include/tsim.h at this version
+        raise ImportError(f"{LIB_PATH} was built for TSIM_ABI_VERSION {lib.tsim_version()}, this package binds version {ABI_VERSION}: rebuild it")
     _lib = lib
     return lib
 
