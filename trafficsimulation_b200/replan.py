@@ -254,7 +254,7 @@ class PlannedTraffic:
     tapes: the malfunction tape ``[T, V]`` and the spawn targets (the rest of the tapes is the tick kernel's business).
     """
 
-    def __init__(self, traffic, planner, width, height, intersection_map, tapes):
+    def __init__(self, traffic, planner, width, height, intersection_map, tapes, record_events=True):
         self.traffic, self.planner = traffic, planner
         self.W, self.H = int(width), int(height)
         self.inter = np.ascontiguousarray(intersection_map, np.uint8).reshape(-1)
@@ -268,6 +268,8 @@ class PlannedTraffic:
         self.pending = {}             # vehicle -> route to hand to the device with the next tick's events
         self.tick = 0
         self.events = []              # (tick, vehicle, cells) in the reference's order: what a route tape of this run would hold
+        self.record_events = bool(record_events)   # (a long run plans millions of routes: switch the log off and count instead)
+        self.routes_planned = 0
         self.searches = 0             # A* queries answered
         self.batches = 0              # planner launches
         self.compactions = 0          # times the route buffer was started again
@@ -276,7 +278,7 @@ class PlannedTraffic:
 
     @classmethod
     def on_gpu(cls, width, height, light_tables, tapes, n_ticks, maps, algo="QUEUE_ACTUATED", rain_enabled=False, device="cuda:0",
-               route_cells=None):
+               route_cells=None, record_events=True):
         """Both collaborators on the device.  maps: the city's simple maps (``GpuCityLayout.maps_host()`` or device planes):
         is_road_map, road_type_map, intersection_map, allowed_dirs_map."""
         from .pathfinding import GpuAstar
@@ -289,7 +291,12 @@ class PlannedTraffic:
         planner = GpuAstar(width, height, zero, zero, maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"], device=device)
         inter = maps["intersection_map"]
         inter = inter.cpu().numpy() if hasattr(inter, "cpu") else inter
-        return cls(traffic, planner, width, height, inter, tapes)
+        return cls(traffic, planner, width, height, inter, tapes, record_events=record_events)
+
+    def _log(self, t, v, path):
+        self.routes_planned += 1
+        if self.record_events:
+            self.events.append((t, v, list(path)))
 
     # ---- A* batches
     def _answer(self, queries):
@@ -352,7 +359,7 @@ class PlannedTraffic:
             run_coroutines(jobs, self._answer, speculate=self.speculate)
             for v in who:
                 if self.veh[v].planned:
-                    self.events.append((t, v, list(self.veh[v].path)))
+                    self._log(t, v, self.veh[v].path)
                     self.pending[v] = self.veh[v].path
         # ---- the tick itself, with this tick's routes
         vs = sorted(self.pending)
@@ -409,5 +416,5 @@ class PlannedTraffic:
             for s, path in zip(states, paths):
                 s.path = path or []
                 self.veh[s.v] = s
-                self.events.append((t, s.v, list(s.path)))
+                self._log(t, s.v, s.path)
                 self.pending[s.v] = s.path
