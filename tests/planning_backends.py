@@ -58,7 +58,9 @@ class OracleTrafficBackend:
     def plan_snapshot(self):
         a = self.sim.a
         return dict(occupancy=a["occ"].copy(), stop_map=a["stop"].copy(), alive=a["alive"] == 1, pos=a["pos"].copy(), path_len=a["path_len"].copy(),
-                    stuck_ticks=a["stuck_ticks"].copy(), stranded=a["stranded"].copy(), stranded_flag=(a["malfunction"] != 0) | (a["collision"] != 0))
+                    stuck_ticks=a["stuck_ticks"].copy(), stranded=a["stranded"].copy(), malfunction_flag=a["malfunction"] != 0,
+                    collision_flag=a["collision"] != 0, base_speed=a["base_speed"].copy(), cur_speed=a["cur_speed"].copy(),
+                    is_stuck=a["is_stuck"].copy(), direction=a["direction"].copy())
 
     def state_host(self):
         return self.sim.state()

@@ -13,7 +13,7 @@ from test_gpu_ticks import build_city
 
 pytestmark = pytest.mark.gpu
 
-CASES = [(p, n) for p in tick_fixtures() for name, n in (("s14_carve", 100), ("s31_fixed_time", 70), ("s5_stranded", 90)) if name in p]
+CASES = [(p, n) for p in tick_fixtures() for name, n in (("s14_carve", 100), ("s31_fixed_time", 70), ("s5_stranded", 90), ("s21_sideswipe", 80)) if name in p]
 
 
 @pytest.mark.parametrize("path,n_ticks", CASES, ids=lambda v: os.path.basename(v)[6:-4] if isinstance(v, str) else str(v))
@@ -29,3 +29,5 @@ def test_gpu_planned_traffic_reproduces_reference_routes(path, n_ticks):
                                 rain_enabled=r["meta"]["rain_enabled"], route_cells=80000 if r["W"] < 200 else 400000)
     n = check_against_fixture(r, sim, n_ticks)
     assert n > 100 and sim.searches >= n // 2 and sim.compactions >= 1
+    if (r["malfunction"] & 2).any():
+        assert (r["vflags"][:n_ticks] & 32).any()   # sideswipe collisions happen inside the ticks that ran

@@ -42,7 +42,7 @@ def check_against_fixture(r, sim, n_ticks):
     return len(want)
 
 
-PLANNABLE = [p for p in tick_fixtures() if "sideswipe" not in p]
+PLANNABLE = tick_fixtures()
 
 
 def test_planned_traffic_with_a_small_route_buffer():
@@ -55,7 +55,7 @@ def test_planned_traffic_with_a_small_route_buffer():
     traffic = OracleTrafficBackend(r["W"], r["H"], tables, tapes, r["n_ticks"], algo=r["algo"], rain_enabled=r["meta"]["rain_enabled"],
                                    route_capacity=30000)
     planner = OraclePlannerBackend(r["W"], r["H"], maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"])
-    sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
+    sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes, rain_enabled=r["meta"]["rain_enabled"])
     check_against_fixture(r, sim, r["n_ticks"])
     assert sim.compactions >= 5
 
@@ -75,7 +75,7 @@ def test_planned_traffic_batching_variants(variant, monkeypatch):
         planner.speculate = True
     else:
         monkeypatch.setattr(R, "RANK_CHUNK", 3)
-    sim = R.PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
+    sim = R.PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes, rain_enabled=r["meta"]["rain_enabled"])
     check_against_fixture(r, sim, 60)
 
 
@@ -88,14 +88,6 @@ def test_planned_traffic_reproduces_reference_routes(path):
     tapes = without_routes(r)
     traffic = OracleTrafficBackend(r["W"], r["H"], tables, tapes, r["n_ticks"], algo=r["algo"], rain_enabled=r["meta"]["rain_enabled"])
     planner = OraclePlannerBackend(r["W"], r["H"], maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"])
-    sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
+    sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes, rain_enabled=r["meta"]["rain_enabled"])
     n = check_against_fixture(r, sim, r["n_ticks"])   # default12345: 240 ticks, 1 440 trips, 37 k planned routes
     assert n > 100 and sim.searches >= n // 2
-
-
-def test_sideswipe_tape_is_refused():
-    from trafficsimulation_b200.replan import PlannedTraffic
-    path = [p for p in tick_fixtures() if "sideswipe" in p][0]
-    r = load_ticks(path)
-    with pytest.raises(NotImplementedError, match="sideswipe"):
-        PlannedTraffic(None, None, r["W"], r["H"], np.zeros((r["H"], r["W"]), np.uint8), without_routes(r))

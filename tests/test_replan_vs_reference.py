@@ -14,6 +14,7 @@ pytestmark = pytest.mark.reference
 CASES = [
     dict(seed=5, n_ticks=90, spawns_per_tick=8, malfunction_p=0.03),
     dict(seed=33, n_ticks=70, spawns_per_tick=14, malfunction_p=0.004),
+    dict(seed=27, n_ticks=90, spawns_per_tick=12, malfunction_p=0.004, sideswipe_p=0.4),   # sideswipe collisions strand both vehicles mid phase A
     dict(seed=18, n_ticks=80, spawns_per_tick=5, malfunction_p=0.02, rain_rect=(30, 30, 120, 90),
          layout_kwargs=dict(width=150, height=110, carve_subblock_roads=True)),
 ]
@@ -32,9 +33,11 @@ def test_planned_traffic_matches_live_reference(case):
     traffic = OracleTrafficBackend(r["W"], r["H"], tables, tapes, r["n_ticks"], rain_enabled=rain, route_capacity=1 << 21)
     maps = lay["maps"]
     planner = OraclePlannerBackend(r["W"], r["H"], maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"])
-    sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes)
+    sim = PlannedTraffic(traffic, planner, r["W"], r["H"], maps["intersection_map"], tapes, rain_enabled=rain)
     n = check_against_fixture(r, sim, r["n_ticks"])
     assert n > 200
+    if case.get("sideswipe_p"):
+        assert r["sideswipes_fired"] >= 3 and (r["vflags"] & 32).any(), r["sideswipes_fired"]
 
 
 def test_tick_mirror_writes_the_planner_state_of_the_live_reference():

@@ -42,6 +42,9 @@ STUCK_CONTRAFLOW_INTERSECTION = 10   # VEHICLE_STUCK_CONTRAFLOW_THRESHOLD_INTERS
 DETOUR_STEPS = 20                    # VEHICLE_MAX_CONTRAFLOW_STUCK_DETOUR_STEPS :312
 DETOUR_DURATION = 10                 # VEHICLE_CONTRAFLOW_STUCK_DETOUR_DURATION :313
 COOLDOWN = 5                         # PATHFINDING_COOLDOWN :409
+MALFUNCTION_TICKS = 400              # VEHICLE_MALFUNCTION_DURATION :321
+COLLISION_TICKS = 600                # VEHICLE_SIDESWIPE_COLLISION_DURATION :326
+RAIN_SPEED_REDUCTION = 2             # RAIN_SPEED_REDUCTION :263
 RANK_CHUNK = 126                     # spawns of one tick that plan in one batch (tsim_astar_maps.spawn_rank holds 7 bits)
 
 
@@ -254,15 +257,15 @@ class PlannedTraffic:
     tapes: the malfunction tape ``[T, V]`` and the spawn targets (the rest of the tapes is the tick kernel's business).
     """
 
-    def __init__(self, traffic, planner, width, height, intersection_map, tapes, record_events=True):
+    def __init__(self, traffic, planner, width, height, intersection_map, tapes, record_events=True, rain_enabled=False):
         self.traffic, self.planner = traffic, planner
         self.W, self.H = int(width), int(height)
         self.inter = np.ascontiguousarray(intersection_map, np.uint8).reshape(-1)
         self.target = np.asarray(tapes["target"], np.int64)
         self.malfunction = np.asarray(tapes["malfunction"])
-        if (self.malfunction & 2).any():
-            raise NotImplementedError("a firing sideswipe draw (tape bit 1) changes who is stranded in the middle of phase A; "
-                                      "the planner loop takes tapes without it")
+        self.speed = np.asarray(tapes["speed"])
+        rain = tapes.get("rain_map") if rain_enabled else None
+        self.rain = None if rain is None else np.ascontiguousarray(rain, np.uint8).reshape(-1)
         self.veh = {}                 # live vehicle -> PlanState
         self.cache = {}               # CityModel._path_cache
         self.pending = {}             # vehicle -> route to hand to the device with the next tick's events
@@ -291,7 +294,7 @@ class PlannedTraffic:
         planner = GpuAstar(width, height, zero, zero, maps["is_road_map"], maps["road_type_map"], maps["allowed_dirs_map"], device=device)
         inter = maps["intersection_map"]
         inter = inter.cpu().numpy() if hasattr(inter, "cpu") else inter
-        return cls(traffic, planner, width, height, inter, tapes, record_events=record_events)
+        return cls(traffic, planner, width, height, inter, tapes, record_events=record_events, rain_enabled=rain_enabled)
 
     def _log(self, t, v, path):
         self.routes_planned += 1
@@ -304,6 +307,87 @@ class PlannedTraffic:
         self.searches += len(q)
         self.batches += 1
         return [p.tolist() for p in self.planner.plan_cells(q)]
+
+    def _early_exits(self, t, snap, live, veh_at):
+        """The head of every vehicle's ``step_decide`` (:616-643) in ``active_vehicle_agents`` order, on the tick-start state: the
+        stranded countdown, the malfunction draw, the sideswipe check -- which strands BOTH vehicles when its draw fires (:567-605) -- and
+        the stop cell.  Returns the vehicles that get as far as the re-plan triggers, and ``stranded_of(u, me)``: ``u.is_stranded()`` as
+        vehicle ``me`` reads it when its own turn comes (u's state after its own head if it is earlier in the list, plus whatever
+        collision an earlier vehicle has inflicted on it by then)."""
+        W, H = self.W, self.H
+        lv = np.array(live)
+        malf = dict(zip(live, (snap["malfunction_flag"][lv] != 0).tolist()))
+        coll = dict(zip(live, (snap["collision_flag"][lv] != 0).tolist()))
+        left = dict(zip(live, snap["stranded"][lv].tolist()))
+        draws = dict(zip(live, self.malfunction[t, lv].tolist()))
+        swipe = bool((self.malfunction[t, lv] & 2).any())
+        if swipe:   # what the sideswipe check reads of the neighbours: speed granted by their last step_decide, is_stuck, direction
+            cur = dict(zip(live, snap["cur_speed"][lv].tolist()))
+            base = dict(zip(live, snap["base_speed"][lv].tolist()))
+            stuck = dict(zip(live, (snap["is_stuck"][lv] != 0).tolist()))
+            heading = dict(zip(live, snap["direction"][lv].tolist()))
+            speed = dict(zip(live, self.speed[t, lv].tolist()))
+        stop = snap["stop_map"]
+        turn = {v: i for i, v in enumerate(live)}
+        history = {}            # vehicle -> [(turn, stranded)] where its state changed during this phase A
+        start = {v: malf[v] or coll[v] for v in live}
+        who = []
+        LEFT, RIGHT, DX, DY = (3, 0, 1, 2), (1, 2, 3, 0), (0, 1, 0, -1), (1, 0, -1, 0)
+        for i, v in enumerate(live):
+            if malf[v] or coll[v]:                              # _tick_stranded :552-565
+                left[v] -= 1
+                if left[v] <= 0:
+                    malf[v] = coll[v] = False
+                    left[v] = 0
+                    history.setdefault(v, []).append((i, False))
+                if malf[v] or coll[v]:
+                    if swipe:
+                        base[v] = cur[v] = 0
+                    continue
+            if draws[v] & 1:                                    # _check_malfunction :608-610
+                malf[v], coll[v], left[v] = True, False, MALFUNCTION_TICKS
+                history.setdefault(v, []).append((i, True))
+                if swipe:
+                    base[v] = cur[v] = 0
+                continue
+            pos = self.veh[v].pos
+            if swipe and heading[v] >= 0:                       # _check_sideswipe_collision :567-605
+                x, y = pos % W, pos // W
+                for side in (LEFT[heading[v]], RIGHT[heading[v]]):
+                    nx, ny = x + DX[side], y + DY[side]
+                    if not (0 <= nx < W and 0 <= ny < H):
+                        continue
+                    u = veh_at.get(ny * W + nx)
+                    if u is None or cur[u] <= 0 or stuck[u] or coll[u] or malf[u] or heading[u] != (heading[v] + 2) % 4:
+                        continue
+                    if draws[v] & 2:                            # the draw fires: _set_collision for both (:534-541)
+                        for k in (v, u):
+                            coll[k], malf[k], left[k], base[k], cur[k] = True, False, COLLISION_TICKS, 0, 0
+                            history.setdefault(k, []).append((i, True))
+                    break                                       # one draw per step_decide, whatever it gave
+                if coll[v]:
+                    continue
+            if stop[pos] == 1:                                  # _is_at_stopped_cell :639-643
+                if swipe:
+                    base[v] = cur[v] = 0
+                continue
+            if swipe:                                           # _compute_speed :94-107 (the neighbours' checks read current_speed)
+                if base[v] == 0:
+                    base[v] = speed[v]
+                sp = base[v]
+                if self.rain is not None and self.rain[pos] == 1:
+                    sp = max(1, sp - RAIN_SPEED_REDUCTION)
+                cur[v] = sp
+            who.append(v)
+
+        def stranded_of(u, me):
+            state = start[u]
+            for when, value in history.get(u, ()):
+                if when <= turn[me]:
+                    state = value
+            return state
+
+        return who, stranded_of
 
     # ---- one tick
     def step(self, n=1, check=True):
@@ -340,22 +424,13 @@ class PlannedTraffic:
         self.planner.update_density()
         live = sorted(self.veh)
         if live:
-            lv = np.array(live)
-            start_stranded = dict(zip(live, (snap["stranded_flag"][lv] != 0).tolist()))
-            left = dict(zip(live, snap["stranded"][lv].tolist()))
-            draw = dict(zip(live, (self.malfunction[t, lv] & 1).astype(bool).tolist()))
-            # who is stranded once its own step_decide has run (_tick_stranded :552-565, _check_malfunction :608-610)
-            post_stranded = {v: ((start_stranded[v] and left[v] - 1 > 0) or draw[v]) for v in live}
             veh_at = {self.veh[v].pos: v for v in live}
-            view = _View(occ, stop, self.inter, veh_at, lambda u, me: post_stranded[u] if u < me else start_stranded[u])
-            jobs, who = [], []
-            for v in live:
-                s = self.veh[v]
-                s.planned = False
-                if post_stranded[v] or stop[s.pos] == 1:     # early exits of step_decide :620-643
-                    continue
-                jobs.append(decide_replans(s, view))
-                who.append(v)
+            who, stranded_of = self._early_exits(t, snap, live, veh_at)
+            view = _View(occ, stop, self.inter, veh_at, stranded_of)
+            jobs = []
+            for v in who:
+                self.veh[v].planned = False
+                jobs.append(decide_replans(self.veh[v], view))
             run_coroutines(jobs, self._answer, speculate=self.speculate)
             for v in who:
                 if self.veh[v].planned:
@@ -393,7 +468,7 @@ class PlannedTraffic:
         # rank and the planner reads the cells of higher ranks as free, so they all plan in the same batches
         born = [int(v) for v in np.flatnonzero(alive) if int(v) not in self.veh]
         occ2, stop2 = snap["occupancy"], snap["stop_map"]
-        stranded_now = snap["stranded_flag"]
+        stranded_now = snap["malfunction_flag"] | snap["collision_flag"]
         veh_at = {int(snap["pos"][v]): v for v in list(self.veh) + born}
         for j0 in range(0, len(born), RANK_CHUNK):
             chunk = born[j0:j0 + RANK_CHUNK]

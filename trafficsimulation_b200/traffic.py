@@ -262,12 +262,14 @@ class GpuTraffic:
 
     def plan_snapshot(self):
         """What the route planner reads between two ticks (host arrays): the public maps and, per vehicle, alive / pos / path_len /
-        stuck_ticks / stranded (ticks left) / stranded_flag (is_in_malfunction or is_in_collision)."""
+        stuck_ticks / stranded (ticks left) / malfunction_flag / collision_flag / base_speed / cur_speed / is_stuck / direction."""
         self.export()
         s = self.s
         g = lambda k: s[k][: max(self.nv, 1)].cpu().numpy()[: self.nv]
         return dict(occupancy=s["occupancy"].cpu().numpy(), stop_map=s["stop_map"].cpu().numpy(), alive=g("alive") == 1, pos=g("pos"),
-                    path_len=g("path_len"), stuck_ticks=g("stuck_ticks"), stranded=g("stranded"), stranded_flag=g("malfunction") != 0)
+                    path_len=g("path_len"), stuck_ticks=g("stuck_ticks"), stranded=g("stranded"), malfunction_flag=(g("malfunction") & 1) != 0,
+                    collision_flag=(g("malfunction") & 2) != 0, base_speed=g("base_speed"), cur_speed=g("cur_speed"), is_stuck=g("is_stuck"),
+                    direction=g("direction"))
 
     def export(self):
         """Live-list kernel: bring the public maps and the vehicle SoA up to date (a tick itself only moves records and probe bytes)."""
