@@ -14,7 +14,8 @@ How it is joined.  With ``PATHFINDING_BATCHING`` (config.py:411, the shipped set
 re-plan of a tick reads the tick-START occupancy / stop / density maps and the vehicle's own state.  The re-plans of one tick are
 therefore independent of each other -- the one cross-vehicle read is ``blocker.is_stranded()``, which sees the blocker's state after
 ITS ``step_decide`` when the blocker is earlier in ``active_vehicle_agents`` (spawn order) and its tick-start state otherwise; both
-are functions of the tick-start state and the malfunction tape.  So a tick is: snapshot -> every vehicle's trigger logic as a
+are functions of the tick-start state and the draw tapes (a sideswipe draw that fires strands two vehicles in the middle of the phase:
+``PlannedTraffic._early_exits`` replays the head of every ``step_decide`` in list order to know who is stranded at whose turn).  So a tick is: snapshot -> every vehicle's trigger logic as a
 coroutine that yields its A* queries -> the queries of all vehicles answered round by round as ONE ``tsim_astar_batch`` launch per
 round -> the new routes handed to the tick kernel as this tick's route events -> ``tsim_tick_run`` for one tick.  A vehicle that
 spawns plans on the maps as they are at that moment of the tick (after the moves, with the earlier spawns of the same tick on the
@@ -254,7 +255,8 @@ class PlannedTraffic:
 
     traffic: a ``GpuTraffic`` built with ``route_capacity=`` (``plan_snapshot()``, ``push_route_events()``, ``step()``);
     planner: a ``GpuAstar`` on the same city (``update``, ``update_density``, ``plan_cells``); ``on_gpu`` builds both.
-    tapes: the malfunction tape ``[T, V]`` and the spawn targets (the rest of the tapes is the tick kernel's business).
+    tapes: the draw tapes ``malfunction[T, V]`` (bit 0 malfunction, bit 1 sideswipe) and ``speed[T, V]``, the spawn targets and, with
+    ``rain_enabled``, ``rain_map`` (the same tapes the tick kernel consumes -- minus the route events).
     """
 
     def __init__(self, traffic, planner, width, height, intersection_map, tapes, record_events=True, rain_enabled=False):
