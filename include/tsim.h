@@ -315,6 +315,13 @@ typedef struct tsim_tick_tapes {     /* all device pointers */
     const int32_t *ev_cells;         /* route arena: cell indices, next cell first                            */
     const uint8_t *rain_map;         /* [H*W] or NULL (Defaults.RAIN_ENABLED False)                           */
 } tsim_tick_tapes;
+/* Route events.  Event e of tick t (ev_first[t] <= e < ev_first[t+1]) makes vehicle ev_vehicle[e] follow
+   ev_cells[ev_off[e] .. ev_off[e+1]) from phase A of tick t on (a spawn of tick t takes it as its first route): every return of
+   VehicleAgent._compute_path (vehicle_base.py:143-167).  The kernels read the four arrays anew at every tsim_tick_run, and a live
+   vehicle keeps POINTING into ev_cells; so a caller that plans the routes itself between two ticks (trafficsimulation_b200/replan.py:
+   the re-plan triggers and the planner of vehicle_base.py:143-517 around tsim_astar_batch) rewrites ev_first[t], ev_first[t+1..],
+   ev_vehicle and ev_off before it runs tick t and APPENDS the new routes to ev_cells -- or, when that arena is full, starts it again
+   with an event for the remaining route of every live vehicle.                                                                    */
 
 typedef struct tsim_tick_state {     /* all device pointers, owned by the caller */
     uint8_t *occupancy, *stop_map, *stuck_map;   /* [H*W] CityModel.occupancy_map / stop_map / stuck_map      */
